@@ -1,0 +1,293 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of the CPU oracle (oracle/mdpp_oracle.c).
+
+The oracle is the checker, never the product.  Only tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py may import this module.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmdpp_oracle.so")
+
+ORC_NONE = 255
+ACTIONS = "SLRFBT"  # reference src/env_gym.py:6-21
+HEADS = "NESW"      # reference src/layout.py:10
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("mdpp_oracle.c", "mdpp_oracle_batch.c", "mdpp_oracle.h", "Makefile")]
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", HERE, "-B", "libmdpp_oracle.so"])
+    return LIB_PATH
+
+
+# ---- node / box strings <-> ids --------------------------------------------------------------
+def node_id(s):
+    m = re.fullmatch(r"([UD])(\d+)([NESW])", s)
+    return (m.group(1) == "D") * 36 + (int(m.group(2)) - 1) * 4 + HEADS.index(m.group(3))
+
+
+def box_id(s):
+    m = re.fullmatch(r"([UD])(\d+)", s)
+    return (m.group(1) == "D") * 9 + int(m.group(2)) - 1
+
+
+def node_str(n):
+    if n == ORC_NONE:
+        return "?YY"
+    return "UD"[n // 36] + str((n % 36) // 4 + 1) + HEADS[n & 3]
+
+
+class Layout(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32),
+                ("n_no_box", C.c_int32), ("no_box", C.c_int32 * 18),
+                ("n_disc", C.c_int32), ("disc_nodes", C.c_int32 * 72),
+                ("n_station", C.c_int32), ("station_box", C.c_int32 * 8), ("station_entrance", C.c_int32 * 8),
+                ("n_dest", C.c_int32), ("dest_nodes", (C.c_int32 * 8) * 2),
+                ("tcdi", C.c_int32),
+                ("n_sel", C.c_int32), ("sel_key", C.c_int32 * 4), ("sel_n", C.c_int32 * 4),
+                ("sel_boxes", (C.c_int32 * 18) * 4)]
+
+
+class State(C.Structure):
+    _fields_ = [("pnode", C.c_uint8), ("dnode", C.c_uint8), ("n_others", C.c_uint8),
+                ("others", (C.c_uint8 * 2) * 6)]
+
+    def key(self):
+        return (self.pnode, self.dnode, tuple((self.others[i][0], self.others[i][1]) for i in range(self.n_others)))
+
+
+def layout_struct(d):
+    """Layout dict (reference src/layout.py schema) -> orc_layout."""
+    lay = Layout()
+    lay.rows, lay.cols = d["number_of_rows"], d["number_of_cols"]
+    lay.n_no_box = len(d["no_box_list"])
+    for i, b in enumerate(d["no_box_list"]):
+        lay.no_box[i] = box_id(b)
+    lay.n_disc = len(d["disconnected_nodes_list"])
+    for i, n in enumerate(d["disconnected_nodes_list"]):
+        lay.disc_nodes[i] = node_id(n)
+    lay.n_station = len(d["station_box_list"])
+    for i, b in enumerate(d["station_box_list"]):
+        lay.station_box[i] = box_id(b)
+        lay.station_entrance[i] = sum(1 << HEADS.index(h) for h in d["station_entrance_list"][i])
+    lists = d["station_destination_list"]
+    assert len(lists) == 2
+    lay.n_dest = len(lists[0])
+    for li in range(2):
+        for i, n in enumerate(lists[li]):
+            lay.dest_nodes[li][i] = node_id(n)
+    lay.tcdi = d["training_complete_destination_index"]
+    sel = d["selective_blocked_boxes_dictionary"]
+    lay.n_sel = len(sel)
+    for k, (key, boxes) in enumerate(sel.items()):
+        lay.sel_key[k] = box_id(key)
+        lay.sel_n[k] = len(boxes)
+        for j, b in enumerate(boxes):
+            lay.sel_boxes[k][j] = box_id(b)
+    return lay
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    SP = C.POINTER(State)
+    sig = {
+        "orc_cfg_create": (P, [C.POINTER(Layout)]),
+        "orc_cfg_destroy": (None, [P]),
+        "orc_cfg_successor": (C.c_int, [P, C.c_int, C.c_int]),
+        "orc_cfg_in_no_node_list": (C.c_int, [P, C.c_int]),
+        "orc_cfg_base_legal": (C.c_int, [P, C.c_int]),
+        "orc_cfg_bfs_len": (C.c_int, [P, C.c_int, C.c_int]),
+        "orc_env_create": (P, [P]),
+        "orc_env_destroy": (None, [P]),
+        "orc_env_set_bad_states": (None, [P, C.c_char_p]),
+        "orc_env_reset": (None, [P]),
+        "orc_env_initialize_cars": (None, [P, C.c_int]),
+        "orc_env_initialize": (None, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "orc_env_encodestate": (None, [P, C.c_int, C.c_int, SP]),
+        "orc_env_legal": (C.c_int, [P, SP]),
+        "orc_env_successor_state": (None, [P, SP, C.c_int, SP]),
+        "orc_env_reward": (C.c_double, [P, SP, SP, C.c_int, C.c_int]),
+        "orc_env_update_car": (None, [P, C.c_int, C.c_int]),
+        "orc_env_is_game_ended": (C.c_int, [P]),
+        "orc_env_car_done": (C.c_int, [P, C.c_int]),
+        "orc_env_car_node": (C.c_int, [P, C.c_int]),
+        "orc_env_car_dest_index": (C.c_int, [P, C.c_int]),
+        "orc_env_car_done_count": (C.c_int, [P, C.c_int]),
+        "orc_env_set_car": (None, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "orc_state_to_string": (C.c_int, [SP, C.c_char_p, C.c_int]),
+        "orc_state_from_string": (C.c_int, [C.c_char_p, SP]),
+        "orc_q_create": (P, [C.c_int]),
+        "orc_q_destroy": (None, [P]),
+        "orc_q_set_params": (None, [P, C.c_double, C.c_double]),
+        "orc_q_get": (C.c_double, [P, SP, C.c_int]),
+        "orc_q_peek": (C.c_double, [P, SP, C.c_int, C.POINTER(C.c_int)]),
+        "orc_q_set": (None, [P, SP, C.c_int, C.c_double]),
+        "orc_q_greedy": (C.c_int, [P, P, SP]),
+        "orc_q_value": (C.c_double, [P, P, SP]),
+        "orc_q_update": (None, [P, P, SP, C.c_int, SP, C.c_double]),
+        "orc_q_size": (C.c_int64, [P]),
+        "orc_q_entry": (None, [P, C.c_int64, SP, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+        "orc_epsilon": (C.c_double, [C.c_int, C.c_int, C.c_int]),
+        "orc_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def state_str(st):
+    buf = C.create_string_buffer(128)
+    lib().orc_state_to_string(C.byref(st), buf, 128)
+    return buf.value.decode()
+
+
+def state_from_str(s):
+    st = State()
+    if lib().orc_state_from_string(s.encode(), C.byref(st)) != 0:
+        raise ValueError("bad state string %r" % s)
+    return st
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return list(o)
+
+
+class Config:
+    """Static graph, reference src/configuration.py Configuration."""
+
+    def __init__(self, layout_dict):
+        self.layout = layout_dict
+        self._lay = layout_struct(layout_dict)
+        self.h = lib().orc_cfg_create(C.byref(self._lay))
+        if not self.h:
+            raise ValueError("unsupported layout")
+
+    def successor(self, node, a):
+        return lib().orc_cfg_successor(self.h, node, a)
+
+    def base_legal(self, node):
+        return lib().orc_cfg_base_legal(self.h, node)
+
+    def bfs_len(self, src, dst):
+        return lib().orc_cfg_bfs_len(self.h, src, dst)
+
+    def in_no_node_list(self, node):
+        return bool(lib().orc_cfg_in_no_node_list(self.h, node))
+
+
+def mask_str(m):
+    return "".join(ACTIONS[a] for a in range(6) if (m >> a) & 1)
+
+
+class Env:
+    """One scalar env, reference src/env_gym.py Environment (string API kept for the tests)."""
+
+    def __init__(self, cfg, bad_states_text=None):
+        self.cfg = cfg
+        self.h = lib().orc_env_create(cfg.h)
+        self._bad = bad_states_text.encode() if bad_states_text is not None else None
+        lib().orc_env_set_bad_states(self.h, self._bad)
+        self.n = 0
+
+    def reset(self):
+        lib().orc_env_reset(self.h)
+
+    def initialize_cars(self, n):
+        self.n = n
+        lib().orc_env_initialize_cars(self.h, n)
+
+    def initialize(self, dest_index, start_nodes, choose):
+        n = self.n
+        di = (C.c_int32 * n)(*dest_index)
+        sn = (C.c_int32 * n)(*[node_id(x) if isinstance(x, str) else x for x in start_nodes])
+        ch = (C.c_int32 * (3 * n))(*[(list(c) + [0, 0, 0])[:3][k] for c in choose for k in range(3)])
+        lib().orc_env_initialize(self.h, di, sn, ch)
+
+    def encodestate(self, car, deadlock_id):
+        st = State()
+        lib().orc_env_encodestate(self.h, car, deadlock_id, C.byref(st))
+        return st
+
+    def legal(self, st):
+        return lib().orc_env_legal(self.h, C.byref(st))
+
+    def successor_state(self, st, a):
+        out = State()
+        lib().orc_env_successor_state(self.h, C.byref(st), a, C.byref(out))
+        return out
+
+    def reward(self, prev, nxt, car, dqn=False):
+        return lib().orc_env_reward(self.h, C.byref(prev), C.byref(nxt), car, int(dqn))
+
+    def update_car(self, car, node):
+        lib().orc_env_update_car(self.h, car, node)
+
+    def is_game_ended(self):
+        return bool(lib().orc_env_is_game_ended(self.h))
+
+    def car_done(self, car):
+        return bool(lib().orc_env_car_done(self.h, car))
+
+    def car(self, i):
+        L = lib()
+        return (L.orc_env_car_node(self.h, i), L.orc_env_car_dest_index(self.h, i),
+                L.orc_env_car_done(self.h, i), L.orc_env_car_done_count(self.h, i))
+
+    def set_car(self, i, node, dest_index, done=0, done_count=5):
+        lib().orc_env_set_car(self.h, i, node_id(node) if isinstance(node, str) else node, dest_index, done, done_count)
+
+
+class QTable:
+    """reference src/algorithms/qlearning.py RL.qvals (a Counter) + update rule."""
+
+    def __init__(self, f32=False, alpha=0.9, discount=0.15):
+        self.h = lib().orc_q_create(int(f32))
+        lib().orc_q_set_params(self.h, alpha, discount)
+
+    def get(self, st, a):
+        return lib().orc_q_get(self.h, C.byref(st), a)
+
+    def set(self, st, a, v):
+        lib().orc_q_set(self.h, C.byref(st), a, v)
+
+    def greedy(self, env, st):
+        return lib().orc_q_greedy(self.h, env.h, C.byref(st))
+
+    def value(self, env, st):
+        return lib().orc_q_value(self.h, env.h, C.byref(st))
+
+    def update(self, env, st, a, nst, r):
+        lib().orc_q_update(self.h, env.h, C.byref(st), a, C.byref(nst), r)
+
+    def items(self):
+        """[(state_string, action_char, value)] in insertion order (the qvalue .txt line order)."""
+        out = []
+        st, a, v = State(), C.c_int(), C.c_double()
+        for i in range(lib().orc_q_size(self.h)):
+            lib().orc_q_entry(self.h, i, C.byref(st), C.byref(a), C.byref(v))
+            out.append((state_str(st), ACTIONS[a.value], v.value))
+        return out
+
+
+def epsilon(episodes, episode, model=3):
+    return lib().orc_epsilon(episodes, episode, model)

@@ -1,0 +1,168 @@
+"""CPU oracle (oracle/mdpp_oracle.c) pinned against vectors recorded from the live reference."""
+import glob
+import os
+
+import pytest
+
+from conftest import GOLDEN, bad_states_text, load_golden
+from oracle import oracle as orc
+
+TRAJ = sorted(os.path.basename(p)[:-8] for p in glob.glob(os.path.join(GOLDEN, "traj_*.json.gz")))
+QRUN = sorted(os.path.basename(p)[:-8] for p in glob.glob(os.path.join(GOLDEN, "qrun_*.json.gz")))
+
+
+def cfg_for(block):
+    return orc.Config(load_golden("tables_b%d" % block)["layout"])
+
+
+@pytest.mark.parametrize("block", [0, 2])
+def test_static_graph_matches_reference(block):
+    g = load_golden("tables_b%d" % block)
+    cfg = cfg_for(block)
+    for n, succ in g["action_dictionary"].items():
+        nid = orc.node_id(n)
+        for a, s in enumerate(succ):
+            got = cfg.successor(nid, a)
+            assert (got == orc.ORC_NONE) == s.endswith("YY"), (n, a, s)
+            if got != orc.ORC_NONE:
+                assert orc.node_str(got) == s, (n, a)
+        assert orc.mask_str(cfg.base_legal(nid)) == g["base_legal"][n], n
+        assert cfg.in_no_node_list(nid) == (n in g["no_node_list"])
+    for d, row in g["bfs_len"].items():
+        for n, length in row.items():
+            assert cfg.bfs_len(orc.node_id(n), orc.node_id(d)) == length, (n, d)
+
+
+def test_state_string_roundtrip():
+    for s in ["D2NxD6NzD3xD6", "U4WxU2W", "D5ExD6NzD1xD6zD8xD8", "D1SxD4EzD2xD6zD3xD8zD5xD4zD7xD7"]:
+        assert orc.state_str(orc.state_from_str(s)) == s
+
+
+def replay_traj(g):
+    cfg = cfg_for(g["block"])
+    env = orc.Env(cfg, bad_states_text(g["block"]) if g["bad_states"] else None)
+    n = len(g["boxes"])
+    dqn = g["reward"] == "dqn_reward"
+    checked = 0
+    for ep in g["episodes"]:
+        env.reset()
+        env.initialize_cars(n)
+        env.initialize(g["idx"], ep["headings"], g["choose"])
+        it = iter(ep["steps"])
+        done = False
+        exhausted = False
+        while not done and not exhausted:
+            for car in range(n):
+                if env.car_done(car):
+                    continue
+                rec = next(it, None)
+                if rec is None:
+                    exhausted = True
+                    break
+                num, state, legal, action, nxt, reward = rec
+                assert num == car
+                st = env.encodestate(car, g["deadlock_id"])
+                assert orc.state_str(st) == state
+                assert orc.mask_str(env.legal(st)) == legal, state
+                a = orc.ACTIONS.index(action)
+                ns = env.successor_state(st, a)
+                assert orc.state_str(ns) == nxt
+                assert env.reward(st, ns, car, dqn) == reward, (state, action)
+                env.update_car(car, ns.pnode)
+                checked += 1
+            done = env.is_game_ended()
+        assert next(it, None) is None
+        assert done == ep["done"]
+    assert checked == g["n_steps"]
+
+
+@pytest.mark.parametrize("name", TRAJ)
+def test_trajectory_bit_exact(name):
+    replay_traj(load_golden(name))
+
+
+@pytest.mark.parametrize("name", QRUN)
+def test_qlearning_run_bit_exact(name):
+    """train_given_state replayed with the recorded coin / choice / heading stream: every greedy
+    action, every updated Q value (float64, compared exactly) and the final Counter incl. its
+    insertion order must match the reference."""
+    g = load_golden(name)
+    cfg = cfg_for(g["block"])
+    env = orc.Env(cfg, bad_states_text(g["block"]) if g["bad_states"] else None)
+    q = orc.QTable(f32=False, alpha=g["alpha"], discount=g["discount"])
+    n = len(g["boxes"])
+    for e, ep in enumerate(g["log"]):
+        assert orc.epsilon(g["episodes_total"], e, 3) == ep["eps"]
+        env.reset()
+        env.initialize_cars(n)
+        env.initialize(g["idx"], ep["headings"], g["choose"])
+        it = iter(ep["steps"])
+        done = False
+        stop = False
+        while not done and not stop:
+            for car in range(n):
+                if env.car_done(car):
+                    continue
+                rec = next(it, None)
+                if rec is None:
+                    stop = True
+                    break
+                state, explore, action, nxt, reward, qafter = rec
+                st = env.encodestate(car, 1)
+                assert orc.state_str(st) == state
+                if explore:
+                    a = orc.ACTIONS.index(action)
+                else:
+                    a = q.greedy(env, st)
+                    assert orc.ACTIONS[a] == action, (e, state)
+                ns = env.successor_state(st, a)
+                r = env.reward(st, ns, car, False)
+                assert r == reward
+                q.update(env, st, a, ns, r)
+                assert q.get(st, a) == float(qafter)
+                env.update_car(car, ns.pnode)
+            done = env.is_game_ended()
+    got = q.items()
+    want = [(s, a, float(v)) for s, a, v in g["qvals"]]
+    assert got == want
+
+
+def test_known_answers():
+    g = load_golden("known_answers")
+    cfg = cfg_for(2)
+    env = orc.Env(cfg, None)
+    env.initialize_cars(2)
+    env.initialize([0, 0], ["D2N", "D3E"], [[0, 1, 0], [0, 1, 0]])
+    st = env.encodestate(0, 1)
+    t = g["transition"]
+    assert orc.state_str(st) == t["state"] and orc.mask_str(env.legal(st)) == t["legal"]
+    ns = env.successor_state(st, orc.ACTIONS.index(t["action"]))
+    assert orc.state_str(ns) == t["next"] and env.reward(st, ns, 0) == t["reward"]
+    # ghost of a finished car: 5 encodes, then it vanishes
+    env = orc.Env(cfg, None)
+    env.initialize_cars(2)
+    env.initialize([0, 1], ["D5E", "D8N"], [[0, 1, 0], [0, 1, 0]])
+    env.update_car(1, orc.node_id("D8E"))
+    for want_state, want_legal, want_count in g["ghost"]["encodes"]:
+        st = env.encodestate(0, 1)
+        assert orc.state_str(st) == want_state
+        assert orc.mask_str(env.legal(st)) == want_legal
+        assert env.car(1)[3] == want_count
+    assert orc.node_str(env.car(1)[0]) == g["ghost"]["parked"]
+    assert env.car(1)[1] == g["ghost"]["parked_di"]
+    assert orc.state_str(env.encodestate(0, 0)) == g["ghost"]["mode0"]
+    for E, sched in g["eps_model3"].items():
+        E = int(E)
+        if len(sched) == E and not isinstance(sched[0], list):
+            assert [orc.epsilon(E, e, 3) for e in range(E)] == sched
+        else:
+            full = [orc.epsilon(E, e, 3) for e in range(E)]
+            assert [[i, full[i]] for i in range(E) if i == 0 or full[i] != full[i - 1]] == sched
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    assert orc.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert orc.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert orc.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
