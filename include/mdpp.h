@@ -1,0 +1,185 @@
+/*
+ * mdpp.h -- C ABI of the B200-native (sm_100a) batched MARL-DPP simulator + tabular learner.
+ *
+ * Drop-in boundary.  The reference (DosepackAIR/MARL-DPP) is pure Python with no FFI; its
+ * boundary for this path is two duck-typed contracts:
+ *   (1) the gym-style env  `Environment(env_conf)`  -- reference src/env_gym.py:4-99
+ *   (2) the algorithm plugin `RL(**params, sess=, env_config=)` -- reference app.py:42-72,91-96
+ * The Python facade in marl_dpp_b200/ keeps both contracts and calls the entry points below
+ * through ctypes (INTEGRATION.md shows the stub a reference maintainer would add).  Each entry
+ * point names the reference interface it replaces.
+ *
+ * Conventions: every pointer marked DEV is caller-owned device memory; `stream` is a
+ * cudaStream_t passed as void*; calls are asynchronous on that stream unless the name ends in
+ * `_host`; the return value is 0 on success, otherwise an MDPP_E* code with text available
+ * from mdpp_last_error_string() (thread local).  The library allocates no device memory: the
+ * caller provides one workspace blob sized by mdpp_workspace_bytes().  One host thread per
+ * handle.  There is no CPU fallback: without a CUDA device every compute entry point fails
+ * with MDPP_ENODEVICE.
+ */
+#ifndef MDPP_H
+#define MDPP_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDPP_ABI_VERSION 1
+#define MDPP_MAX_CARS 5   /* 12 bits per car in one 64-bit word; reference DQN TOTAL_CARS=5, settings.py:7 */
+#define MDPP_NODES 72     /* 2 floors x 9 boxes x 4 headings, reference src/configuration.py:100-118 */
+#define MDPP_BOXES 18
+#define MDPP_NONE 255
+#define MDPP_MAX_DEST 8
+#define MDPP_Q_ROW 8      /* floats per Q row: S,L,R,F,T + 3 spare (kept 0) = one 32-byte sector */
+#define MDPP_FIXED_SHIFT 18 /* fixed-point fraction bits of the TD accumulators */
+
+enum {
+    MDPP_OK = 0,
+    MDPP_EINVAL = 1,
+    MDPP_ENODEVICE = 2,
+    MDPP_ECUDA = 3,
+    MDPP_EWORKSPACE = 4
+};
+
+/* action indices on this ABI: the reference's 6 actions minus 'B', which its legal filter always
+ * removes (reference src/env_gym.py:158-159); order S,L,R,F,T = reference argMax tie-break order */
+enum { MDPP_A_S = 0, MDPP_A_L = 1, MDPP_A_R = 2, MDPP_A_F = 3, MDPP_A_T = 4, MDPP_N_ACT = 5 };
+#define MDPP_ACT_SKIP 0xFF
+#define MDPP_ACT_GREEDY 0xFE /* mdpp_q_substep `forced`: take the argmax, no coin */
+
+/* reward kinds, reference src/env_gym.py:101-112 select_reward_function */
+enum { MDPP_REWARD_Q = 0, MDPP_REWARD_DQN = 1 };
+
+/* Static tables of one (layout block, initial state) pair.  Built on the host from the layout
+ * dict (reference src/layout.py schema) by marl_dpp_b200/tables.py; replaces Configuration
+ * (reference src/configuration.py:44-145) and the per-episode BFS memo (src/env_gym.py:443-483). */
+typedef struct {
+    int32_t abi_version;
+    int32_t n_cars;          /* 1..MDPP_MAX_CARS */
+    int32_t n_local_nodes;   /* nodes in the state-id universe (36 for a one-floor block) */
+    int32_t n_dest_nodes;    /* distinct destination nodes */
+    int32_t n_dest_boxes;    /* distinct destination boxes */
+    int32_t n_src_boxes;     /* boxes another car can be listed in (9 for a one-floor block) */
+    int32_t parking_node;    /* no_box_list[0] + 'W', reference src/env_gym.py:439 */
+    int32_t tcdi;            /* training_complete_destination_index */
+    int32_t bad_states_on;   /* give_bad_state_reward, reference src/env_gym.py:71-83 */
+    int32_t step_cap;        /* agent-steps per episode before a forced reset; 0 = none (qlearning.py:274) */
+    uint8_t node_local[MDPP_NODES];          /* node -> local index, MDPP_NONE outside the universe */
+    uint8_t fwd[MDPP_NODES];                 /* 'F' successor or MDPP_NONE */
+    uint8_t base_legal[MDPP_NODES];          /* 5-bit mask over S,L,R,F,T */
+    uint8_t bfs_len[MDPP_MAX_DEST][MDPP_NODES]; /* len(BFS actions) node -> destination node */
+    uint8_t dest_node[MDPP_MAX_DEST];        /* destination-node index -> node id */
+    uint8_t dest_node_box[MDPP_MAX_DEST];    /* destination-node index -> destination-box index */
+    uint8_t dest_box[MDPP_MAX_DEST];         /* destination-box index -> box18 */
+    uint8_t src_box_idx[MDPP_BOXES];         /* box18 -> index in the others universe or MDPP_NONE */
+    uint32_t sel_mask[MDPP_MAX_DEST];        /* per destination box: 18-bit selective-block mask */
+    uint8_t car_dest[MDPP_MAX_CARS][2];      /* per car, per destination_index: destination-node index */
+    uint8_t start_box[MDPP_MAX_CARS];        /* box18 of the initial state */
+    uint8_t start_di[MDPP_MAX_CARS];         /* initial destination_index */
+    int64_t n_states;        /* rows of the Q table */
+    int64_t n_box_states;    /* bits of the bad-state bitmap */
+} mdpp_config;
+
+/* Learner parameters (reference src/algorithms/qlearning.py:20-27 and src/utils/utils.py:33-52). */
+typedef struct {
+    float alpha, discount;      /* 0.9, 0.15 */
+    int32_t episodes;           /* per-env episode budget; an env that finished it is frozen */
+    int32_t eps_threshold[5];   /* int(episodes*{0.4,0.6,0.7,0.85,0.99}) */
+    uint32_t eps_q16[6];        /* epsilon * 65536 per schedule segment: {1,.8,.5,.3,.15,0} */
+    uint32_t seed;
+} mdpp_learner;
+
+/* counters accumulated on the device, fetched with mdpp_get_stats_host */
+typedef struct {
+    uint64_t agent_steps;       /* update_car calls, the BASELINE metric's unit */
+    uint64_t q_updates;
+    uint64_t episodes_done;
+    uint64_t episodes_capped;
+    int64_t reward_sum;         /* sum of integer q_rewards (dqn: x100) */
+    uint64_t explore_steps;
+    uint64_t touched_keys;      /* distinct (state, action) keys finalised */
+    uint64_t reserved;
+} mdpp_stats;
+
+typedef struct mdpp_handle mdpp_handle;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int64_t mdpp_workspace_bytes(const mdpp_config *cfg, int64_t n_envs);
+/* env_id_base: global id of env 0 (rank * n_envs for data-parallel shards) -- keys the RNG so that
+ * results do not depend on the rank count.  bad_bitmap_host: n_box_states bits or NULL. */
+int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base,
+                void *workspace /*DEV*/, int64_t workspace_bytes,
+                const uint32_t *bad_bitmap_host, void *stream, mdpp_handle **out);
+int mdpp_destroy(mdpp_handle *h);
+const char *mdpp_last_error_string(void);
+int mdpp_abi_version(void);
+/* device pointer to the packed env records, 16 bytes per env (see DESIGN.md "Data layout") */
+void *mdpp_env_records(mdpp_handle *h);
+/* device pointer to [n_states] u32: bit a set = key (state, a) has been updated (qvalue file writer) */
+void *mdpp_visited_bits(mdpp_handle *h);
+
+/* ---- env: reset / initialize (reference src/env_gym.py:643-672,331-352) -------------------- */
+/* headings: [n_envs][n_cars] u8 in 0..3 (N,E,S,W) or NULL => Philox.  env_mask: [n_envs] u8, NULL = all.
+ * Resets cars to the initial state; episode counters are zeroed only when zero_counters != 0. */
+int mdpp_reset(mdpp_handle *h, const uint8_t *env_mask /*DEV*/, const uint8_t *headings /*DEV*/,
+               uint32_t seed, int zero_counters, void *stream);
+
+/* ---- env: one agent-step of car `car_slot` in every env, externally supplied actions --------
+ * Replaces encodestate + getlegalactions + get_successor_state + reward_function + update_car
+ * (reference src/algorithms/qlearning.py:218-229) == Environment.step (src/env_gym.py:85-99).
+ * deadlock_id as in encodestate (src/env_gym.py:281); outputs are optional (NULL = skip):
+ * status: 0 stepped, 1 car already done (nothing happens), 2 illegal action (nothing happens). */
+int mdpp_step_car(mdpp_handle *h, int car_slot, int deadlock_id, int reward_kind,
+                  const uint8_t *actions /*DEV [n_envs]*/,
+                  uint32_t *state_idx /*DEV*/, uint32_t *next_idx /*DEV*/, float *reward /*DEV*/,
+                  uint8_t *legal /*DEV*/, uint8_t *status /*DEV*/, uint8_t *all_done /*DEV*/,
+                  void *stream);
+/* same call with HOST buffers (pinned or pageable): copies in, steps, copies out, synchronises */
+int mdpp_step_car_host(mdpp_handle *h, int car_slot, int deadlock_id, int reward_kind,
+                       const uint8_t *actions, uint32_t *state_idx, uint32_t *next_idx, float *reward,
+                       uint8_t *legal, uint8_t *status, uint8_t *all_done, void *stream);
+
+/* ---- env: lockstep rollout under the uniform-random legal policy (reference eps = 1 behaviour,
+ * src/algorithms/qlearning.py:99-102) with Philox4x32-10 and auto-reset.  `rounds` full
+ * round-robin rounds (qlearning.py:211-233) per launch; outputs (optional) are SoA
+ * [rounds][n_cars][n_envs]: action (MDPP_ACT_SKIP when the car did not move), reward, env-done
+ * flag after the step, next-state id. */
+int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32_t seed, int reward_kind,
+                        uint8_t *action /*DEV*/, float *reward /*DEV*/, uint8_t *done /*DEV*/,
+                        uint32_t *next_idx /*DEV*/, void *stream);
+
+/* ---- learner: fused epsilon-greedy select + step + TD update -------------------------------
+ * One sub-step = car `car_slot` of every env: getaction (qlearning.py:74-105), the env step and
+ * update (qlearning.py:107-116), all envs reading the Q table as it was when the sub-step
+ * began; each env's new value is accumulated in fixed point and mdpp_q_finalize writes, per
+ * touched key, the mean over the envs that updated it (exactly the reference's value when one env
+ * did).  forced: optional [n_envs] u8, MDPP_ACT_SKIP = choose by coin/argmax, MDPP_ACT_GREEDY = argmax,
+ * otherwise take that action as an exploration step (replays a recorded decision stream).  Optional outputs as in
+ * mdpp_step_car plus the chosen action. */
+int mdpp_q_substep(mdpp_handle *h, float *q /*DEV [n_states][8]*/, const mdpp_learner *lp, int car_slot,
+                   uint64_t round, const uint8_t *forced /*DEV*/, uint8_t *action_out /*DEV*/,
+                   uint32_t *state_idx /*DEV*/, float *reward /*DEV*/, void *stream);
+int mdpp_q_finalize(mdpp_handle *h, float *q /*DEV*/, void *stream);
+/* `rounds` full rounds (n_cars sub-steps + finalize each) starting at round index first_round */
+int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t first_round,
+                        int rounds, void *stream);
+/* end-to-end variant: learner parameters from host memory, stats copied back, synchronised */
+int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp_host,
+                             uint64_t first_round, int rounds, mdpp_stats *stats_host, void *stream);
+
+/* ---- state-id codec (for the qvalue .txt format, reference src/algorithms/qlearning.py:159-185) */
+/* decode: state id -> primary node, destination node, others as (src box18, dst box18) pairs in the
+ * reference's ascend_array order; returns the number of others or a negative error */
+int mdpp_decode_state(const mdpp_config *cfg, int64_t state_idx, int32_t *pnode, int32_t *dnode,
+                      int32_t *others /*[(MDPP_MAX_CARS-1)*2]*/);
+int64_t mdpp_encode_state(const mdpp_config *cfg, int32_t pnode, int32_t dnode, int32_t n_others,
+                          const int32_t *others);
+
+/* ---- stats ---------------------------------------------------------------------------------- */
+int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,92 @@
+"""ctypes binding of libmdpp.so (include/mdpp.h).  The library is built in-tree by
+`python -m marl_dpp_b200.build` / __graft_entry__.build() with nvcc for sm_100a.  There is no
+fallback: if the shared library is missing, importing the compute API raises."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libmdpp.so")
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh")] + \
+          [os.path.join(ROOT, "include", "mdpp.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+# every symbol include/mdpp.h declares (tests check that the built library exports all of them)
+EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_error_string", "mdpp_abi_version",
+           "mdpp_env_records", "mdpp_visited_bits", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
+           "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
+           "mdpp_q_train_rounds_host", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in SOURCES)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> marl_dpp_b200/libmdpp.so (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libmdpp.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                           "marl_dpp_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    P, U8, U32, F32 = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # device or host pointers as integers
+    I, I64, U64 = C.c_int, C.c_int64, C.c_uint64
+    sig = {
+        "mdpp_workspace_bytes": (I64, [P, I64]),
+        "mdpp_create": (I, [P, I64, I64, P, I64, P, P, C.POINTER(P)]),
+        "mdpp_destroy": (I, [P]),
+        "mdpp_last_error_string": (C.c_char_p, []),
+        "mdpp_abi_version": (I, []),
+        "mdpp_env_records": (P, [P]),
+        "mdpp_visited_bits": (P, [P]),
+        "mdpp_reset": (I, [P, U8, U8, C.c_uint32, I, P]),
+        "mdpp_step_car": (I, [P, I, I, I, U8, U32, U32, F32, U8, U8, U8, P]),
+        "mdpp_step_car_host": (I, [P, I, I, I, U8, U32, U32, F32, U8, U8, U8, P]),
+        "mdpp_rollout_random": (I, [P, I, U64, C.c_uint32, I, U8, F32, U8, U32, P]),
+        "mdpp_q_substep": (I, [P, F32, P, I, U64, U8, U8, U32, F32, P]),
+        "mdpp_q_finalize": (I, [P, F32, P]),
+        "mdpp_q_train_rounds": (I, [P, F32, P, U64, I, P]),
+        "mdpp_q_train_rounds_host": (I, [P, F32, P, U64, I, P, P]),
+        "mdpp_decode_state": (I, [P, I64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "mdpp_encode_state": (I64, [P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+        "mdpp_get_stats_host": (I, [P, P, I, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().mdpp_last_error_string().decode()
+
+
+class MdppError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise MdppError("mdpp error %d: %s" % (rc, last_error()))

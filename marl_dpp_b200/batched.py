@@ -1,0 +1,222 @@
+"""Batched env + tabular learner: torch tensors in, the C ABI of include/mdpp.h underneath.
+
+PyTorch is plumbing here: it owns device memory (one workspace blob per handle, the Q table,
+the I/O tensors), the stream, and the NCCL process group used to average Q replicas.  Every
+compute step is a hand-written sm_100a kernel in csrc/.  No CPU fallback: constructing a
+BatchedEnv without a CUDA device raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .tables import ACTIONS5, MdppStats, Scenario, learner_params
+
+ACT_SKIP = 0xFF
+ACT_GREEDY = 0xFE
+REWARD_KINDS = {"q_reward": 0, "dqn_reward": 1}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BatchedEnv:
+    """n_envs independent copies of one (block, initial state) scenario, stepped in lockstep.
+
+    Mirrors, per env, reference src/env_gym.py Environment: reset / initialize_cars / initialize
+    (-> reset), encodestate + getlegalactions + step (-> step_car), is_game_ended (-> all_done).
+    """
+
+    def __init__(self, scenario, n_envs, device=None, env_id_base=0, seed=3):
+        if not torch.cuda.is_available():
+            raise RuntimeError("marl_dpp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        assert isinstance(scenario, Scenario)
+        self.scenario = scenario
+        self.n_envs = int(n_envs)
+        self.n_cars = scenario.n_cars
+        self.device = torch.device(device if device is not None else "cuda")
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            nbytes = L.mdpp_workspace_bytes(C.byref(scenario.cfg), self.n_envs)
+            if nbytes < 0:
+                raise _lib.MdppError("invalid scenario: " + _lib.last_error())
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            h = C.c_void_p()
+            bad = scenario.bad_bitmap.ctypes.data_as(C.c_void_p) if scenario.bad_bitmap is not None else None
+            _lib.check(L.mdpp_create(C.byref(scenario.cfg), self.n_envs, self.env_id_base, _ptr(self.workspace),
+                                     nbytes, bad, _stream(), C.byref(h)))
+        self._h = h
+        self._L = L
+        off = L.mdpp_env_records(h) - self.workspace.data_ptr()
+        self.records = self.workspace[off:off + 16 * self.n_envs].view(torch.int32).view(self.n_envs, 4)
+        self.reset()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.mdpp_destroy(h)
+
+    # -- reset / initialize ---------------------------------------------------------------------
+    def reset(self, headings=None, mask=None, zero_counters=True, seed=None):
+        """headings: uint8 [n_envs, n_cars] in 0..3 = N,E,S,W (what the reference draws with
+        random.shuffle, src/env_gym.py:345-349) or None for Philox; mask: uint8 [n_envs] or None."""
+        if headings is not None:
+            headings = headings.to(self.device, torch.uint8).contiguous()
+            assert headings.shape == (self.n_envs, self.n_cars)
+        if mask is not None:
+            mask = mask.to(self.device, torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_reset(self._h, _ptr(mask), _ptr(headings),
+                                          self.seed if seed is None else int(seed), int(zero_counters), _stream()))
+
+    # -- one agent-step of one car slot ------------------------------------------------------------
+    def step_car(self, car, actions, deadlock_id=1, reward="q_reward", outputs=True):
+        """actions: uint8 [n_envs], 0..4 = S,L,R,F,T, 0xFF = leave this env alone."""
+        actions = actions.to(self.device, torch.uint8).contiguous()
+        n, dev = self.n_envs, self.device
+        out = {}
+        if outputs:
+            out = {"state": torch.empty(n, dtype=torch.int32, device=dev),
+                   "next_state": torch.empty(n, dtype=torch.int32, device=dev),
+                   "reward": torch.empty(n, dtype=torch.float32, device=dev),
+                   "legal": torch.empty(n, dtype=torch.uint8, device=dev),
+                   "status": torch.empty(n, dtype=torch.uint8, device=dev),
+                   "done": torch.empty(n, dtype=torch.uint8, device=dev)}
+        with torch.cuda.device(dev):
+            _lib.check(self._L.mdpp_step_car(self._h, car, deadlock_id, REWARD_KINDS[reward], _ptr(actions),
+                                             _ptr(out.get("state")), _ptr(out.get("next_state")),
+                                             _ptr(out.get("reward")), _ptr(out.get("legal")),
+                                             _ptr(out.get("status")), _ptr(out.get("done")), _stream()))
+        return out
+
+    def step_car_host(self, car, actions, out, deadlock_id=1, reward="q_reward"):
+        """End-to-end variant: `actions` and every tensor in `out` are (pinned) HOST tensors; the
+        H2D copy, the kernel, the D2H copies and the synchronisation all happen inside the call."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_step_car_host(self._h, car, deadlock_id, REWARD_KINDS[reward], _ptr(actions),
+                                                  _ptr(out.get("state")), _ptr(out.get("next_state")),
+                                                  _ptr(out.get("reward")), _ptr(out.get("legal")),
+                                                  _ptr(out.get("status")), _ptr(out.get("done")), _stream()))
+        return out
+
+    # -- random-policy rollout -------------------------------------------------------------------
+    def rollout_random(self, rounds, first_round=0, reward="q_reward", outputs=None):
+        """`rounds` round-robin rounds under the uniform-random legal policy with auto-reset.
+        outputs: None or dict of preallocated [rounds, n_cars, n_envs] tensors
+        (action u8, reward f32, done u8, next_state i32)."""
+        o = outputs or {}
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_rollout_random(self._h, int(rounds), int(first_round), self.seed,
+                                                   REWARD_KINDS[reward], _ptr(o.get("action")), _ptr(o.get("reward")),
+                                                   _ptr(o.get("done")), _ptr(o.get("next_state")), _stream()))
+        return outputs
+
+    def alloc_rollout_outputs(self, rounds):
+        shape, dev = (rounds, self.n_cars, self.n_envs), self.device
+        return {"action": torch.empty(shape, dtype=torch.uint8, device=dev),
+                "reward": torch.empty(shape, dtype=torch.float32, device=dev),
+                "done": torch.empty(shape, dtype=torch.uint8, device=dev),
+                "next_state": torch.empty(shape, dtype=torch.int32, device=dev)}
+
+    # -- inspection ----------------------------------------------------------------------------
+    def stats(self, reset=False):
+        s = MdppStats()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_get_stats_host(self._h, C.byref(s), int(reset), _stream()))
+        return s.as_dict()
+
+    def cars(self):
+        """Decoded car records: int64 tensors [n_envs, n_cars] node, dest_index, done, ghost."""
+        r = self.records.to(torch.int64) & 0xFFFFFFFF
+        packed = r[:, 0] | (r[:, 1] << 32)
+        f = torch.stack([(packed >> (12 * i)) & 0xFFF for i in range(self.n_cars)], dim=1)
+        return {"node": f & 127, "dest_index": (f >> 7) & 1, "done": (f >> 8) & 1, "ghost": (f >> 9) & 7,
+                "episode": r[:, 2] & 0xFFFF, "steps": r[:, 2] >> 16}
+
+
+class BatchedQLearner:
+    """Tabular Q-learning over a BatchedEnv (reference src/algorithms/qlearning.py RL, batched).
+
+    Semantics of one sub-step (car slot c of every env): all envs read the Q table as it was when
+    the sub-step began, pick epsilon-greedily (per-env episode counter drives the reference's
+    epsilon schedule), step, and compute the reference update; each touched key then receives
+    the mean of the values the contributing envs computed.  With one env this IS the reference's
+    sequential update, bit for bit in float32.
+    """
+
+    def __init__(self, env, episodes=5000, alpha=0.9, discount=0.15, probability_model=3, seed=None, q=None):
+        self.env = env
+        self.params = learner_params(episodes, alpha, discount, probability_model,
+                                     env.seed if seed is None else seed)
+        n_states = env.scenario.n_states
+        self.q = q if q is not None else torch.zeros((n_states, 8), dtype=torch.float32, device=env.device)
+        assert self.q.shape == (n_states, 8) and self.q.dtype == torch.float32 and self.q.is_contiguous()
+        self.round = 0
+        L, h = env._L, env._h
+        off = L.mdpp_visited_bits(h) - env.workspace.data_ptr()
+        self.visited = env.workspace[off:off + 4 * n_states].view(torch.int32)
+
+    def substep(self, car, forced=None, outputs=False):
+        env = self.env
+        n, dev = env.n_envs, env.device
+        if forced is not None:
+            forced = forced.to(dev, torch.uint8).contiguous()
+        out = {}
+        if outputs:
+            out = {"action": torch.empty(n, dtype=torch.uint8, device=dev),
+                   "state": torch.empty(n, dtype=torch.int32, device=dev),
+                   "reward": torch.empty(n, dtype=torch.float32, device=dev)}
+        with torch.cuda.device(dev):
+            _lib.check(env._L.mdpp_q_substep(env._h, _ptr(self.q), C.byref(self.params), car, self.round,
+                                             _ptr(forced), _ptr(out.get("action")), _ptr(out.get("state")),
+                                             _ptr(out.get("reward")), _stream()))
+        return out
+
+    def finalize(self):
+        with torch.cuda.device(self.env.device):
+            _lib.check(self.env._L.mdpp_q_finalize(self.env._h, _ptr(self.q), _stream()))
+
+    def train_rounds(self, rounds):
+        """`rounds` full round-robin rounds (n_cars x (sub-step + finalize)); asynchronous."""
+        env = self.env
+        with torch.cuda.device(env.device):
+            _lib.check(env._L.mdpp_q_train_rounds(env._h, _ptr(self.q), C.byref(self.params), self.round,
+                                                  int(rounds), _stream()))
+        self.round += int(rounds)
+
+    def train_rounds_host(self, rounds):
+        """End-to-end call: learner parameters from host memory in, stats back, synchronised."""
+        env = self.env
+        s = MdppStats()
+        with torch.cuda.device(env.device):
+            _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self.q), C.byref(self.params), self.round,
+                                                       int(rounds), C.byref(s), _stream()))
+        self.round += int(rounds)
+        return s.as_dict()
+
+    def sync_replicas(self, group=None):
+        """Average the per-GPU Q replicas: one NCCL all-reduce (AVG) over NVLink, in place."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.q, op=dist.ReduceOp.AVG, group=group)
+
+    # -- qvalue .txt format (reference src/algorithms/qlearning.py:159-185) --------------------------
+    def qvalue_items(self):
+        """[(state string, action char, float)] for every key updated so far, in state-id order."""
+        sc = self.env.scenario
+        vis = self.visited.cpu()
+        q = self.q.cpu()
+        out = []
+        for s in torch.nonzero(vis).flatten().tolist():
+            name = sc.decode(s)
+            for a in range(5):
+                if (int(vis[s]) >> a) & 1:
+                    out.append((name, ACTIONS5[a], float(q[s, a])))
+        return out

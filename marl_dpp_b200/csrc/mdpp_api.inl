@@ -1,0 +1,399 @@
+// mdpp_api.inl -- host side of the C ABI declared in include/mdpp.h (included by mdpp_kernels.cu).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace mdpp {
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define MDPP_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t err__ = (call);                                                             \
+        if (err__ != cudaSuccess)                                                               \
+            return fail(err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver      \
+                            ? MDPP_ENODEVICE : MDPP_ECUDA,                                      \
+                        "%s failed: %s", #call, cudaGetErrorString(err__));                     \
+    } while (0)
+
+struct Carve {
+    size_t tables, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, total;
+    uint32_t touched_capacity;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
+    Carve c{};
+    size_t off = 0;
+    const size_t keys = (size_t)cfg.n_states * MDPP_Q_ROW;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    c.tables = take(sizeof(SmemTables));
+    c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
+    c.recs = take((size_t)n_envs * 16);
+    c.sum = take(keys * 8);
+    c.cnt = take(keys * 4);
+    c.last = take(keys * 4);
+    c.bits = take(keys / 8 + 4);
+    c.touched_capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
+    c.touched = take((size_t)c.touched_capacity * 4);
+    c.visited = take((size_t)cfg.n_states * 4);
+    c.control = take(sizeof(Control));
+    c.stage = take((size_t)n_envs * 16);
+    c.total = off;
+    return c;
+}
+
+} // namespace mdpp
+
+struct mdpp_handle {
+    mdpp_config cfg;
+    mdpp::DevCfg dev;
+    mdpp::Carve cv;
+    int64_t n_envs;
+    uint32_t env_id_base;
+    char *ws;
+    int sm_count;
+};
+
+using namespace mdpp;
+
+static int validate_config(const mdpp_config *cfg) {
+    if (!cfg) return fail(MDPP_EINVAL, "cfg is NULL");
+    if (cfg->abi_version != MDPP_ABI_VERSION)
+        return fail(MDPP_EINVAL, "abi_version %d != %d", cfg->abi_version, MDPP_ABI_VERSION);
+    if (cfg->n_cars < 1 || cfg->n_cars > MDPP_MAX_CARS) return fail(MDPP_EINVAL, "n_cars %d out of 1..%d", cfg->n_cars, MDPP_MAX_CARS);
+    if (cfg->n_local_nodes != 36 && cfg->n_local_nodes != 72) return fail(MDPP_EINVAL, "n_local_nodes must be 36 or 72");
+    if (cfg->n_src_boxes != 9 && cfg->n_src_boxes != 18) return fail(MDPP_EINVAL, "n_src_boxes must be 9 or 18");
+    if (cfg->n_dest_nodes < 1 || cfg->n_dest_nodes > MDPP_MAX_DEST || cfg->n_dest_boxes < 1 || cfg->n_dest_boxes > MDPP_MAX_DEST)
+        return fail(MDPP_EINVAL, "destination counts out of range");
+    if (cfg->tcdi != 0 && cfg->tcdi != 1) return fail(MDPP_EINVAL, "training_complete_destination_index must be 0 or 1");
+    if (cfg->n_states <= 0 || cfg->n_states * MDPP_Q_ROW >= (int64_t)1 << 32)
+        return fail(MDPP_EINVAL, "n_states %lld does not fit 32-bit keys", (long long)cfg->n_states);
+    if (cfg->step_cap < 0 || cfg->step_cap > 65535) return fail(MDPP_EINVAL, "step_cap out of 0..65535");
+    return MDPP_OK;
+}
+
+static int find_base(const uint8_t *tab, int n) {
+    for (int i = 0; i < n; i++)
+        if (tab[i] == 0) return i;
+    return 0;
+}
+
+static void make_devcfg(const mdpp_config &c, DevCfg &d) {
+    memset(&d, 0, sizeof d);
+    d.n_cars = c.n_cars;
+    d.n_local_nodes = c.n_local_nodes;
+    d.n_dest_nodes = c.n_dest_nodes;
+    d.n_dest_boxes = c.n_dest_boxes;
+    d.n_src_boxes = c.n_src_boxes;
+    d.node_base = find_base(c.node_local, MDPP_NODES);
+    d.box_base = find_base(c.src_box_idx, MDPP_BOXES);
+    d.parking_node = c.parking_node;
+    d.tcdi = c.tcdi;
+    d.bad_on = c.bad_states_on;
+    d.step_cap = c.step_cap;
+    for (int i = 0; i < c.n_cars; i++) {
+        for (int di = 0; di < 2; di++) {
+            uint32_t dn = c.car_dest[i][di];
+            d.car_dnidx[i][di] = dn;
+            d.car_dnode[i][di] = c.dest_node[dn];
+            d.car_dbox[i][di] = c.dest_node_box[dn];
+            d.car_dbox18[i][di] = c.dest_box[c.dest_node_box[dn]];
+            d.car_sel[i][di] = c.sel_mask[c.dest_node_box[dn]];
+        }
+        // ghost of a finished car: [final box, final box] (reference src/env_gym.py:313-317)
+        uint32_t fb = d.car_dbox18[i][c.tcdi];
+        d.car_ghost_box18[i] = fb;
+        d.car_ghost_code[i] = 1u + (fb - d.box_base) * c.n_dest_boxes + d.car_dbox[i][c.tcdi];
+        d.start_box18[i] = c.start_box[i];
+        d.start_di[i] = c.start_di[i];
+    }
+}
+
+extern "C" {
+
+int mdpp_abi_version(void) { return MDPP_ABI_VERSION; }
+const char *mdpp_last_error_string(void) { return g_err; }
+
+int64_t mdpp_workspace_bytes(const mdpp_config *cfg, int64_t n_envs) {
+    if (validate_config(cfg) != MDPP_OK || n_envs <= 0) return -1;
+    return (int64_t)carve(*cfg, n_envs).total;
+}
+
+int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, void *workspace,
+                int64_t workspace_bytes, const uint32_t *bad_bitmap_host, void *stream, mdpp_handle **out) {
+    if (!out) return fail(MDPP_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (n_envs <= 0 || n_envs >= (int64_t)1 << 31) return fail(MDPP_EINVAL, "n_envs out of range");
+    if (env_id_base < 0 || env_id_base + n_envs > (int64_t)1 << 32) return fail(MDPP_EINVAL, "env ids must fit 32 bits");
+    if (cfg->bad_states_on && !bad_bitmap_host) return fail(MDPP_EINVAL, "bad_states_on without a bitmap");
+    int ndev = 0;
+    MDPP_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(MDPP_ENODEVICE, "no CUDA device: this library has no CPU fallback");
+    Carve cv = carve(*cfg, n_envs);
+    if (!workspace || workspace_bytes < (int64_t)cv.total)
+        return fail(MDPP_EWORKSPACE, "workspace %lld B < required %lld B", (long long)workspace_bytes, (long long)cv.total);
+    if ((uintptr_t)workspace & 255) return fail(MDPP_EWORKSPACE, "workspace must be 256-byte aligned");
+    mdpp_handle *h = new (std::nothrow) mdpp_handle();
+    if (!h) return fail(MDPP_EINVAL, "out of host memory");
+    h->cfg = *cfg;
+    h->cv = cv;
+    h->n_envs = n_envs;
+    h->env_id_base = (uint32_t)env_id_base;
+    h->ws = (char *)workspace;
+    make_devcfg(*cfg, h->dev);
+    h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
+    h->dev.bad_bitmap = (const uint32_t *)(h->ws + cv.bad);
+    int devid = 0;
+    cudaGetDevice(&devid);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, devid);
+    cudaStream_t s = (cudaStream_t)stream;
+    SmemTables img;
+    memset(&img, 0, sizeof img);
+    for (int n = 0; n < MDPP_NODES; n++) img.nodeinfo[n] = (uint16_t)(cfg->fwd[n] | (cfg->base_legal[n] << 8));
+    memcpy(img.bfs, cfg->bfs_len, sizeof img.bfs);
+    cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.tables, &img, sizeof img, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && bad_bitmap_host)
+        e = cudaMemcpyAsync(h->ws + cv.bad, bad_bitmap_host, (((size_t)cfg->n_box_states + 31) / 32) * 4,
+                            cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(MDPP_ECUDA, "workspace initialisation failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return MDPP_OK;
+}
+
+int mdpp_destroy(mdpp_handle *h) {
+    delete h;
+    return MDPP_OK;
+}
+
+void *mdpp_env_records(mdpp_handle *h) { return h ? h->ws + h->cv.recs : nullptr; }
+void *mdpp_visited_bits(mdpp_handle *h) { return h ? h->ws + h->cv.visited : nullptr; }
+
+#define MDPP_DISPATCH_NC(h, KERNEL, grid, s, ...)                                               \
+    switch ((h)->cfg.n_cars) {                                                                  \
+    case 1: KERNEL<1><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                            \
+    case 2: KERNEL<2><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                            \
+    case 3: KERNEL<3><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                            \
+    case 4: KERNEL<4><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                            \
+    default: KERNEL<5><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                           \
+    }
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+static inline Control *control_of(mdpp_handle *h) { return (Control *)(h->ws + h->cv.control); }
+static inline uint4 *recs_of(mdpp_handle *h) { return (uint4 *)(h->ws + h->cv.recs); }
+
+int mdpp_reset(mdpp_handle *h, const uint8_t *env_mask, const uint8_t *headings, uint32_t seed, int zero_counters,
+               void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, reset_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
+                     env_mask, headings, seed, zero_counters);
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_step_car(mdpp_handle *h, int car_slot, int deadlock_id, int reward_kind, const uint8_t *actions,
+                  uint32_t *state_idx, uint32_t *next_idx, float *reward, uint8_t *legal, uint8_t *status,
+                  uint8_t *all_done_out, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
+    if (!actions) return fail(MDPP_EINVAL, "actions is NULL");
+    if (deadlock_id != 0 && deadlock_id != 1) return fail(MDPP_EINVAL, "deadlock_id must be 0 or 1");
+    if (reward_kind != MDPP_REWARD_Q && reward_kind != MDPP_REWARD_DQN) return fail(MDPP_EINVAL, "unknown reward kind");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, step_car_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, car_slot,
+                     deadlock_id, reward_kind, actions, state_idx, next_idx, reward, legal, status, all_done_out,
+                     control_of(h));
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_step_car_host(mdpp_handle *h, int car_slot, int deadlock_id, int reward_kind, const uint8_t *actions,
+                       uint32_t *state_idx, uint32_t *next_idx, float *reward, uint8_t *legal, uint8_t *status,
+                       uint8_t *all_done_out, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!actions) return fail(MDPP_EINVAL, "actions is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->n_envs;
+    char *st = h->ws + h->cv.stage; // [state 4n | next 4n | reward 4n | actions n | legal n | status n | done n]
+    uint32_t *d_state = (uint32_t *)st, *d_next = (uint32_t *)(st + 4 * n);
+    float *d_reward = (float *)(st + 8 * n);
+    uint8_t *d_act = (uint8_t *)(st + 12 * n), *d_legal = d_act + n, *d_status = d_act + 2 * n, *d_done = d_act + 3 * n;
+    MDPP_CUDA(cudaMemcpyAsync(d_act, actions, n, cudaMemcpyHostToDevice, s));
+    int rc = mdpp_step_car(h, car_slot, deadlock_id, reward_kind, d_act, state_idx ? d_state : nullptr,
+                           next_idx ? d_next : nullptr, reward ? d_reward : nullptr, legal ? d_legal : nullptr,
+                           status ? d_status : nullptr, all_done_out ? d_done : nullptr, stream);
+    if (rc) return rc;
+    if (state_idx) MDPP_CUDA(cudaMemcpyAsync(state_idx, d_state, 4 * n, cudaMemcpyDeviceToHost, s));
+    if (next_idx) MDPP_CUDA(cudaMemcpyAsync(next_idx, d_next, 4 * n, cudaMemcpyDeviceToHost, s));
+    if (reward) MDPP_CUDA(cudaMemcpyAsync(reward, d_reward, 4 * n, cudaMemcpyDeviceToHost, s));
+    if (legal) MDPP_CUDA(cudaMemcpyAsync(legal, d_legal, n, cudaMemcpyDeviceToHost, s));
+    if (status) MDPP_CUDA(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, s));
+    if (all_done_out) MDPP_CUDA(cudaMemcpyAsync(all_done_out, d_done, n, cudaMemcpyDeviceToHost, s));
+    MDPP_CUDA(cudaStreamSynchronize(s));
+    return MDPP_OK;
+}
+
+int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32_t seed, int reward_kind,
+                        uint8_t *action, float *reward, uint8_t *done, uint32_t *next_idx, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (rounds <= 0) return fail(MDPP_EINVAL, "rounds must be positive");
+    if (reward_kind != MDPP_REWARD_Q && reward_kind != MDPP_REWARD_DQN) return fail(MDPP_EINVAL, "unknown reward kind");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, rollout_random_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs,
+                     h->env_id_base, rounds, first_round, seed, reward_kind, action, reward, done, next_idx,
+                     control_of(h));
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+static Accum accum_of(mdpp_handle *h) {
+    Accum a;
+    a.sum = (long long *)(h->ws + h->cv.sum);
+    a.cnt = (uint32_t *)(h->ws + h->cv.cnt);
+    a.last = (float *)(h->ws + h->cv.last);
+    a.touched_bits = (uint32_t *)(h->ws + h->cv.bits);
+    a.touched = (uint32_t *)(h->ws + h->cv.touched);
+    a.visited = (uint32_t *)(h->ws + h->cv.visited);
+    a.capacity = h->cv.touched_capacity;
+    return a;
+}
+
+int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
+                   const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
+    if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, q_substep_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
+                     car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward, control_of(h));
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_q_finalize(mdpp_handle *h, float *q, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q) return fail(MDPP_EINVAL, "q is NULL");
+    unsigned grid = (unsigned)std::min<int64_t>((h->cv.touched_capacity + kThreads - 1) / kThreads,
+                                                (int64_t)h->sm_count * 8);
+    q_finalize_kernel<<<std::max(grid, 1u), kThreads, 0, (cudaStream_t)stream>>>(q, accum_of(h), control_of(h));
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64_t first_round, int rounds,
+                        void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    for (int r = 0; r < rounds; r++)
+        for (int c = 0; c < h->cfg.n_cars; c++) {
+            int rc = mdpp_q_substep(h, q, lp, c, first_round + (uint64_t)r, nullptr, nullptr, nullptr, nullptr, stream);
+            if (rc) return rc;
+            rc = mdpp_q_finalize(h, q, stream);
+            if (rc) return rc;
+        }
+    return MDPP_OK;
+}
+
+int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *stream) {
+    if (!h || !out_host) return fail(MDPP_EINVAL, "handle / out is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_CUDA(cudaMemcpyAsync(out_host, &control_of(h)->stats, sizeof(mdpp_stats), cudaMemcpyDeviceToHost, s));
+    if (reset) MDPP_CUDA(cudaMemsetAsync(&control_of(h)->stats, 0, sizeof(mdpp_stats), s));
+    MDPP_CUDA(cudaStreamSynchronize(s));
+    return MDPP_OK;
+}
+
+int mdpp_q_train_rounds_host(mdpp_handle *h, float *q, const mdpp_learner *lp_host, uint64_t first_round, int rounds,
+                             mdpp_stats *stats_host, void *stream) {
+    int rc = mdpp_q_train_rounds(h, q, lp_host, first_round, rounds, stream);
+    if (rc) return rc;
+    return mdpp_get_stats_host(h, stats_host, 0, stream);
+}
+
+// ---- state-id codec: pure host arithmetic, usable without a device --------------------------------
+static uint64_t binom_u64(uint64_t n, int j) {
+    if (n < (uint64_t)j) return 0;
+    uint64_t r = 1;
+    for (int i = 1; i <= j; i++) r = r * (n - (uint64_t)j + (uint64_t)i) / (uint64_t)i;
+    return r;
+}
+// ordering of the reference's ascend_array (src/env_gym.py:267-279): (box number, [src, dst] as strings)
+static bool other_before(const int32_t *a, const int32_t *b) {
+    int ka[4] = {a[0] % 9, a[0] < 9, a[1] < 9, a[1] % 9}; // 'D' (floor 1) sorts before 'U' (floor 0)
+    int kb[4] = {b[0] % 9, b[0] < 9, b[1] < 9, b[1] % 9};
+    for (int i = 0; i < 4; i++)
+        if (ka[i] != kb[i]) return ka[i] < kb[i];
+    return false;
+}
+
+int mdpp_decode_state(const mdpp_config *cfg, int64_t idx, int32_t *pnode, int32_t *dnode, int32_t *others) {
+    if (validate_config(cfg)) return -MDPP_EINVAL;
+    if (idx < 0 || idx >= cfg->n_states) return -fail(MDPP_EINVAL, "state index out of range");
+    const int node_base = find_base(cfg->node_local, MDPP_NODES), box_base = find_base(cfg->src_box_idx, MDPP_BOXES);
+    int64_t nl = idx % cfg->n_local_nodes, t = idx / cfg->n_local_nodes;
+    int64_t dn = t % cfg->n_dest_nodes;
+    uint64_t rank = (uint64_t)(t / cfg->n_dest_nodes);
+    *pnode = (int32_t)nl + node_base;
+    *dnode = cfg->dest_node[dn];
+    int n = 0;
+    for (int j = cfg->n_cars - 1; j >= 1; j--) { // unrank the multiset, largest element first
+        uint64_t d = (uint64_t)j - 1;
+        while (binom_u64(d + 1, j) <= rank) d++;
+        rank -= binom_u64(d, j);
+        uint64_t code = d - (uint64_t)j + 1;
+        if (code == 0) continue;
+        code -= 1;
+        others[2 * n] = (int32_t)(code / (uint64_t)cfg->n_dest_boxes) + box_base;
+        others[2 * n + 1] = cfg->dest_box[code % (uint64_t)cfg->n_dest_boxes];
+        n++;
+    }
+    for (int i = 1; i < n; i++) // insertion sort into the reference's order
+        for (int k = i; k > 0 && other_before(others + 2 * k, others + 2 * (k - 1)); k--) {
+            std::swap(others[2 * k], others[2 * k - 2]);
+            std::swap(others[2 * k + 1], others[2 * k - 1]);
+        }
+    return n;
+}
+
+int64_t mdpp_encode_state(const mdpp_config *cfg, int32_t pnode, int32_t dnode, int32_t n_others, const int32_t *others) {
+    if (validate_config(cfg)) return -MDPP_EINVAL;
+    if (n_others < 0 || n_others > cfg->n_cars - 1) return -fail(MDPP_EINVAL, "too many others for n_cars");
+    if (pnode < 0 || pnode >= MDPP_NODES || cfg->node_local[pnode] == MDPP_NONE) return -fail(MDPP_EINVAL, "primary node outside the universe");
+    int dn = -1;
+    for (int i = 0; i < cfg->n_dest_nodes; i++)
+        if (cfg->dest_node[i] == dnode) dn = i;
+    if (dn < 0) return -fail(MDPP_EINVAL, "destination node is not a destination");
+    uint64_t codes[MDPP_MAX_CARS] = {0, 0, 0, 0, 0};
+    const int k = cfg->n_cars - 1;
+    for (int i = 0; i < n_others; i++) {
+        int sb = others[2 * i], db = -1;
+        if (sb < 0 || sb >= MDPP_BOXES || cfg->src_box_idx[sb] == MDPP_NONE) return -fail(MDPP_EINVAL, "source box outside the universe");
+        for (int j = 0; j < cfg->n_dest_boxes; j++)
+            if (cfg->dest_box[j] == others[2 * i + 1]) db = j;
+        if (db < 0) return -fail(MDPP_EINVAL, "destination box is not a destination");
+        codes[i] = 1 + (uint64_t)cfg->src_box_idx[sb] * (uint64_t)cfg->n_dest_boxes + (uint64_t)db;
+    }
+    std::sort(codes, codes + k);
+    uint64_t rank = 0;
+    for (int j = 1; j <= k; j++) rank += binom_u64(codes[j - 1] + (uint64_t)j - 1, j);
+    return (int64_t)((rank * (uint64_t)cfg->n_dest_nodes + (uint64_t)dn) * (uint64_t)cfg->n_local_nodes + cfg->node_local[pnode]);
+}
+
+} // extern "C"

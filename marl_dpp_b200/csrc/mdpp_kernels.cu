@@ -1,0 +1,383 @@
+// mdpp_kernels.cu -- sm_100a kernels of the batched MARL-DPP hot path.
+//
+// Mapping: one lane = one env, one warp = a tile of 32 consecutive envs, 16-byte env records read
+// and written with one 128-bit access per lane (512 contiguous bytes per warp).  All env work is
+// integer ALU + shared-memory table lookups; HBM/L2 traffic is the env records, the optional
+// per-step outputs and (learner) two 32-byte Q-row gathers plus the accumulator atomics.
+#include "env_core.cuh"
+
+namespace mdpp {
+
+// ------------------------------------------------------------------------------------------------
+// workspace-resident control block
+// ------------------------------------------------------------------------------------------------
+struct Control {
+    mdpp_stats stats;
+    uint32_t touched_count;
+    uint32_t finalize_ticket;
+    uint32_t pad[14];
+};
+
+struct StatAcc {
+    uint32_t steps = 0, episodes = 0, capped = 0, explore = 0, qupd = 0;
+    int32_t reward = 0;
+};
+
+__device__ __forceinline__ void flush_stats(const StatAcc &a, int64_t reward64, Control *ctl) {
+    // warp-level integer reductions (REDUX), one atomic per warp and counter
+    uint32_t steps = __reduce_add_sync(0xFFFFFFFFu, a.steps);
+    uint32_t episodes = __reduce_add_sync(0xFFFFFFFFu, a.episodes);
+    uint32_t capped = __reduce_add_sync(0xFFFFFFFFu, a.capped);
+    uint32_t explore = __reduce_add_sync(0xFFFFFFFFu, a.explore);
+    uint32_t qupd = __reduce_add_sync(0xFFFFFFFFu, a.qupd);
+    long long rsum = reward64;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (steps) atomicAdd((unsigned long long *)&ctl->stats.agent_steps, (unsigned long long)steps);
+        if (episodes) atomicAdd((unsigned long long *)&ctl->stats.episodes_done, (unsigned long long)episodes);
+        if (capped) atomicAdd((unsigned long long *)&ctl->stats.episodes_capped, (unsigned long long)capped);
+        if (explore) atomicAdd((unsigned long long *)&ctl->stats.explore_steps, (unsigned long long)explore);
+        if (qupd) atomicAdd((unsigned long long *)&ctl->stats.q_updates, (unsigned long long)qupd);
+        if (rsum) atomicAdd((unsigned long long *)&ctl->stats.reward_sum, (unsigned long long)rsum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset / initialize  (reference src/env_gym.py:643-672,331-352)
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+reset_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base,
+             const uint8_t *__restrict__ env_mask, const uint8_t *__restrict__ headings, uint32_t seed,
+             int zero_counters) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    if (env_mask && !env_mask[e]) return;
+    uint32_t hb = 0;
+    if (headings) {
+#pragma unroll
+        for (int i = 0; i < NC; i++) hb |= (uint32_t)(headings[e * NC + i] & 3u) << (2 * i);
+    } else {
+        hb = heading_word(0, 3, seed, env_id_base + (uint32_t)e);
+    }
+    uint64_t cars = initial_cars<NC>(cfg, hb);
+    uint4 r = recs[e];
+    r.x = (uint32_t)cars;
+    r.y = (uint32_t)(cars >> 32);
+    if (zero_counters) { r.z = 0; r.w = 0; }
+    else r.z &= 0xFFFFu; // new episode: steps_in_episode = 0, episode index kept
+    recs[e] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one agent-step of car `c` in every env, externally supplied actions (parity / gym mode)
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+step_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, int mode, int kind,
+                const uint8_t *__restrict__ actions, uint32_t *__restrict__ state_idx,
+                uint32_t *__restrict__ next_idx, float *__restrict__ reward, uint8_t *__restrict__ legal,
+                uint8_t *__restrict__ status, uint8_t *__restrict__ done_out, Control *ctl) {
+    __shared__ SmemTables sm;
+    load_tables(sm, cfg.tables);
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    StatAcc acc;
+    int64_t rsum = 0;
+    if (e < n_envs) {
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t st = 0, sidx = 0xFFFFFFFFu, nidx = 0xFFFFFFFFu, lm = 0;
+        float rw = 0.f;
+        uint32_t a = actions[e];
+        if (f_done(car_field(cars, c)) || a == MDPP_ACT_SKIP) {
+            st = 1; // reference: `if env.check_car_training(num): continue` (qlearning.py:216-217)
+        } else {
+            View v = view_of<NC>(cars, c, mode, cfg);
+            lm = legal_mask(v, v.pnode, sm);
+            sidx = state_index(v, v.pnode, cfg);
+            if (a >= MDPP_N_ACT || !((lm >> a) & 1u)) {
+                st = 2;
+            } else {
+                uint32_t nn = next_node(v.pnode, a, sm);
+                nidx = state_index(v, nn, cfg);
+                int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, sm);
+                rw = reward_float(ri, kind);
+                cars = advance_car(cars, c, v, nn, cfg);
+                uint32_t steps = rec.z >> 16;
+                steps = steps < 0xFFFFu ? steps + 1 : steps;
+                rec.z = (rec.z & 0xFFFFu) | (steps << 16);
+                acc.steps = 1;
+                rsum = ri;
+            }
+            rec.x = (uint32_t)cars; // ghost counters move even when the action was rejected
+            rec.y = (uint32_t)(cars >> 32);
+            recs[e] = rec;
+        }
+        if (state_idx) state_idx[e] = sidx;
+        if (next_idx) next_idx[e] = nidx;
+        if (reward) reward[e] = rw;
+        if (legal) legal[e] = (uint8_t)lm;
+        if (status) status[e] = (uint8_t)st;
+        if (done_out) done_out[e] = (uint8_t)all_done<NC>(cars);
+    }
+    flush_stats(acc, rsum, ctl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lockstep rollout, uniform-random legal policy, auto-reset (config "random-policy sweep")
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int rounds,
+                      uint64_t first_round, uint32_t seed, int kind, uint8_t *__restrict__ action_out,
+                      float *__restrict__ reward_out, uint8_t *__restrict__ done_out,
+                      uint32_t *__restrict__ next_out, Control *ctl) {
+    __shared__ SmemTables sm;
+    load_tables(sm, cfg.tables);
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    StatAcc acc;
+    int64_t rsum = 0;
+    if (e < n_envs) {
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        const uint32_t env = env_id_base + (uint32_t)e;
+        for (int r = 0; r < rounds; r++) {
+            const uint64_t round = first_round + (uint64_t)r;
+            uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                uint32_t a = MDPP_ACT_SKIP, nidx = 0xFFFFFFFFu;
+                float rw = 0.f;
+                if (!f_done(car_field(cars, c))) {
+                    View v = view_of<NC>(cars, c, 1, cfg);
+                    uint32_t lm = legal_mask(v, v.pnode, sm);
+                    if (lm) {
+                        uint32_t w = c == 0 ? p.x : c == 1 ? p.y : c == 2 ? p.z : c == 3 ? p.w
+                                     : philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
+                        // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
+                        a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
+                        uint32_t nn = next_node(v.pnode, a, sm);
+                        nidx = state_index(v, nn, cfg);
+                        int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, sm);
+                        rw = reward_float(ri, kind);
+                        cars = advance_car(cars, c, v, nn, cfg);
+                        steps = steps < 0xFFFFu ? steps + 1 : steps;
+                        acc.steps++;
+                        acc.explore++;
+                        rsum += ri;
+                    }
+                }
+                size_t o = ((size_t)r * NC + c) * (size_t)n_envs + (size_t)e;
+                if (action_out) action_out[o] = (uint8_t)a;
+                if (reward_out) reward_out[o] = rw;
+                if (next_out) next_out[o] = nidx;
+                if (done_out) done_out[o] = (uint8_t)all_done<NC>(cars);
+            }
+            // end of round: is_game_ended (src/env_gym.py:622-638) or the step cap -> next episode
+            bool finished = all_done<NC>(cars);
+            bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                acc.episodes++;
+                acc.capped += capped;
+                episode = (episode + 1) & 0xFFFFu;
+                steps = 0;
+                cars = initial_cars<NC>(cfg, heading_word(round, 2, seed, env));
+            }
+        }
+        rec.x = (uint32_t)cars;
+        rec.y = (uint32_t)(cars >> 32);
+        rec.z = episode | (steps << 16);
+        recs[e] = rec;
+    }
+    flush_stats(acc, rsum, ctl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// learner: fused epsilon-greedy select + env step + TD accumulate
+// ------------------------------------------------------------------------------------------------
+using LearnArgs = mdpp_learner;
+
+struct Accum {
+    long long *sum;        // [n_states*8] fixed-point sums of the per-env new values
+    uint32_t *cnt;         // [n_states*8] contributors
+    float *last;           // [n_states*8] the value itself, exact when cnt ends at 1
+    uint32_t *touched_bits;// [n_states*8/32] key touched in this sub-step
+    uint32_t *touched;     // [capacity] list of touched keys
+    uint32_t *visited;     // [n_states] bit a = (state, a) has been updated at least once
+    uint32_t capacity;
+};
+
+// epsilon schedule (reference src/utils/utils.py:33-52, model 3) on the per-env episode counter
+__device__ __forceinline__ uint32_t eps_q16_of(const LearnArgs &lp, int32_t episode) {
+    uint32_t e = lp.eps_q16[5];
+#pragma unroll
+    for (int i = 4; i >= 0; i--)
+        if (episode < lp.eps_threshold[i]) e = lp.eps_q16[i];
+    return e;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c,
+                 uint64_t round, LearnArgs lp, const float *__restrict__ q, Accum ac,
+                 const uint8_t *__restrict__ forced, uint8_t *__restrict__ action_out,
+                 uint32_t *__restrict__ state_out, float *__restrict__ reward_out, Control *ctl) {
+    __shared__ SmemTables sm;
+    load_tables(sm, cfg.tables);
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    StatAcc acc;
+    int64_t rsum = 0;
+    if (e < n_envs) {
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        const uint32_t env = env_id_base + (uint32_t)e;
+        uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
+        float r_out = 0.f;
+        const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
+        if (live && !f_done(car_field(cars, c))) {
+            View v = view_of<NC>(cars, c, 1, cfg);
+            const uint32_t lm = legal_mask(v, v.pnode, sm);
+            const uint32_t sidx = state_index(v, v.pnode, cfg);
+            s_out = sidx;
+            uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
+            const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
+            if (lm && forced_ok) {
+                // ---- getaction (reference src/algorithms/qlearning.py:74-105) ----
+                const float4 q0 = __ldg(reinterpret_cast<const float4 *>(q + (size_t)sidx * MDPP_Q_ROW));
+                const float q4 = __ldg(q + (size_t)sidx * MDPP_Q_ROW + 4);
+                const float qs[5] = {q0.x, q0.y, q0.z, q0.w, q4};
+                uint32_t a;
+                bool explore;
+                if (f == MDPP_ACT_GREEDY) {
+                    a = 0;
+                    explore = false;
+                } else if (f != MDPP_ACT_SKIP) {
+                    a = f;
+                    explore = true;
+                } else {
+                    uint32_t w = decision_word(round, c, lp.seed, env);
+                    explore = (w >> 16) < eps_q16_of(lp, (int32_t)episode); // flipcoin (utils.py:255-265)
+                    a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
+                }
+                if (!explore) { // computeactionfromqvalues: first maximum in S,L,R,F,T order (:659-667)
+                    float best = 0.f;
+                    bool have = false;
+#pragma unroll
+                    for (int k = 0; k < MDPP_N_ACT; k++) {
+                        bool ok = (lm >> k) & 1u;
+                        if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
+                    }
+                }
+                acc.explore += explore;
+                // ---- env step ----
+                const uint32_t nn = next_node(v.pnode, a, sm);
+                const int32_t ri = reward_int<NC>(v, nn, cars, c, MDPP_REWARD_Q, cfg, sm);
+                // ---- update (qlearning.py:107-116): value of the successor STATE STRING, same others ----
+                const uint32_t nidx = state_index(v, nn, cfg);
+                const uint32_t lm2 = legal_mask(v, nn, sm);
+                const float4 n0 = __ldg(reinterpret_cast<const float4 *>(q + (size_t)nidx * MDPP_Q_ROW));
+                const float n4 = __ldg(q + (size_t)nidx * MDPP_Q_ROW + 4);
+                const float ns[5] = {n0.x, n0.y, n0.z, n0.w, n4};
+                float nv = 0.f;
+                bool have = false;
+#pragma unroll
+                for (int k = 0; k < MDPP_N_ACT; k++) {
+                    bool ok = (lm2 >> k) & 1u;
+                    if (ok && (!have || ns[k] > nv)) { nv = ns[k]; have = true; }
+                }
+                float qa = qs[0];
+#pragma unroll
+                for (int k = 1; k < MDPP_N_ACT; k++) qa = (a == (uint32_t)k) ? qs[k] : qa;
+                // explicit roundings: the same operation order as the reference expression, no FMA
+                const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
+                const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
+                // ---- accumulate: mean over the envs that update this key in this sub-step ----
+                const uint32_t key = sidx * MDPP_Q_ROW + a;
+                const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
+                atomicAdd((unsigned long long *)(ac.sum + key), (unsigned long long)fx);
+                atomicAdd(ac.cnt + key, 1u);
+                const uint32_t bit = 1u << (key & 31u);
+                uint32_t seen = *(volatile uint32_t *)(ac.touched_bits + (key >> 5));
+                if (!(seen & bit)) {
+                    ac.last[key] = newv; // only matters if this env stays the key's single contributor
+                    uint32_t old = atomicOr(ac.touched_bits + (key >> 5), bit);
+                    if (!(old & bit)) {
+                        uint32_t slot = atomicAdd(&ctl->touched_count, 1u);
+                        if (slot < ac.capacity) ac.touched[slot] = key;
+                    }
+                }
+                cars = advance_car(cars, c, v, nn, cfg);
+                steps = steps < 0xFFFFu ? steps + 1 : steps;
+                acc.steps = 1;
+                acc.qupd = 1;
+                rsum = ri;
+                a_out = a;
+                r_out = (float)ri;
+            }
+        }
+        if (live && c == NC - 1) { // end of the round-robin round (qlearning.py:233)
+            bool finished = all_done<NC>(cars);
+            bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                acc.episodes = 1;
+                acc.capped = capped;
+                episode = episode + 1;
+                steps = 0;
+                cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+            }
+        }
+        if (live) {
+            rec.x = (uint32_t)cars;
+            rec.y = (uint32_t)(cars >> 32);
+            rec.z = (episode & 0xFFFFu) | (steps << 16);
+            recs[e] = rec;
+        }
+        if (action_out) action_out[e] = (uint8_t)a_out;
+        if (state_out) state_out[e] = s_out;
+        if (reward_out) reward_out[e] = r_out;
+    }
+    flush_stats(acc, rsum, ctl);
+}
+
+// finalize: per touched key write the mean of the accumulated values (the value itself when one
+// env contributed), clear the accumulators, record the visited bit used by the qvalue file writer.
+__global__ void __launch_bounds__(kThreads)
+q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
+    const uint32_t n = min(ctl->touched_count, ac.capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = ac.touched[i];
+        const uint32_t cnt = ac.cnt[key];
+        float v;
+        if (cnt == 1u) {
+            v = ac.last[key];
+        } else {
+            const double mean = (double)ac.sum[key] / ((double)cnt * (double)(1 << MDPP_FIXED_SHIFT));
+            v = (float)mean;
+        }
+        q[key] = v;
+        ac.sum[key] = 0;
+        ac.cnt[key] = 0;
+        ac.touched_bits[key >> 5] = 0; // every set bit of the word belongs to a key finalised in this launch
+        uint32_t *vis = ac.visited + (key >> 3);
+        const uint32_t vb = 1u << (key & 7u);
+        if (!(*vis & vb)) atomicOr(vis, vb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t t = atomicAdd(&ctl->finalize_ticket, 1u);
+        if (t == gridDim.x - 1) { // last block: every block has read touched_count by now
+            atomicAdd((unsigned long long *)&ctl->stats.touched_keys, (unsigned long long)n);
+            ctl->touched_count = 0;
+            ctl->finalize_ticket = 0;
+            __threadfence();
+        }
+    }
+}
+
+} // namespace mdpp
+
+#include "mdpp_api.inl"

@@ -662,3 +662,12 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+
+/* index-level access for the batched driver (mdpp_oracle_batch.c) */
+int64_t orc_q_index(orc_q *q, const orc_state *s, int action) {
+    qkey k;
+    make_key(&k, s, action);
+    return q_insert(q, &k);
+}
+double orc_q_at(const orc_q *q, int64_t i) { return q->vals[i]; }
+void orc_q_set_at(orc_q *q, int64_t i, double v) { q->vals[i] = v; }

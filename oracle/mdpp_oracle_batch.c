@@ -1,1 +1,348 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- batched driver on top of the scalar oracle (mdpp_oracle.c).
+ *
+ * Restates, on the CPU and one env at a time, the BATCH semantics the CUDA path defines
+ * (DESIGN.md "Batch semantics"): N independent envs stepped in lockstep, car slot by car slot,
+ * decisions drawn from Philox4x32-10 keyed (seed, env id) with counter (round, stream), per-env
+ * episode counters driving the reference's epsilon schedule, auto-reset at the end of a round,
+ * and -- for the learner -- every env of a sub-step reading the Q table as it was when the
+ * sub-step began, with each touched key receiving the mean (fixed point, 18 fraction bits) of
+ * the values the contributing envs computed (the value itself when one env contributed).
+ * The per-env pieces are the reference-pinned scalar functions; nothing here is shared with the
+ * product code.  pthreads spread envs over host cores for the CPU baseline in bench.py.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "mdpp_oracle.h"
+
+/* from mdpp_oracle.c */
+int64_t orc_q_index(orc_q *q, const orc_state *s, int action);
+double orc_q_at(const orc_q *q, int64_t i);
+void orc_q_set_at(orc_q *q, int64_t i, double v);
+
+#define ACT_SKIP 0xFF
+#define ACT_GREEDY 0xFE
+static const int ACT5[5] = {0, 1, 2, 3, 5}; /* S L R F T in the oracle's 6-action numbering */
+
+typedef struct {
+    const orc_cfg *cfg;
+    int64_t n_envs;
+    int n_cars;
+    uint32_t env_id_base;
+    int step_cap;
+    int32_t start_box[ORC_MAX_CARS], dest_index[ORC_MAX_CARS], choose[3 * ORC_MAX_CARS];
+    orc_env **envs;
+    int32_t *episode, *steps;
+    /* stats */
+    uint64_t agent_steps, episodes_done, episodes_capped, explore_steps;
+    int64_t reward_sum;
+} orc_batch;
+
+static void init_env(orc_batch *b, int64_t e, uint32_t heading_bits) {
+    int32_t nodes[ORC_MAX_CARS];
+    for (int i = 0; i < b->n_cars; i++) nodes[i] = b->start_box[i] * 4 + (int)((heading_bits >> (2 * i)) & 3u);
+    orc_env_reset(b->envs[e]);
+    orc_env_initialize_cars(b->envs[e], b->n_cars);
+    orc_env_initialize(b->envs[e], b->dest_index, nodes, b->choose);
+}
+
+orc_batch *orc_batch_create(const orc_cfg *cfg, int64_t n_envs, int n_cars, const int32_t *start_box,
+                            const int32_t *dest_index, const int32_t *choose3, const char *bad_text, int step_cap,
+                            uint32_t env_id_base) {
+    orc_batch *b = (orc_batch *)calloc(1, sizeof(orc_batch));
+    b->cfg = cfg;
+    b->n_envs = n_envs;
+    b->n_cars = n_cars;
+    b->env_id_base = env_id_base;
+    b->step_cap = step_cap;
+    memcpy(b->start_box, start_box, sizeof(int32_t) * (size_t)n_cars);
+    memcpy(b->dest_index, dest_index, sizeof(int32_t) * (size_t)n_cars);
+    memcpy(b->choose, choose3, sizeof(int32_t) * 3 * (size_t)n_cars);
+    b->envs = (orc_env **)calloc((size_t)n_envs, sizeof(orc_env *));
+    b->episode = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
+    b->steps = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
+    for (int64_t e = 0; e < n_envs; e++) {
+        b->envs[e] = orc_env_create(cfg);
+        orc_env_set_bad_states(b->envs[e], bad_text);
+    }
+    return b;
+}
+void orc_batch_destroy(orc_batch *b) {
+    for (int64_t e = 0; e < b->n_envs; e++) orc_env_destroy(b->envs[e]);
+    free(b->envs);
+    free(b->episode);
+    free(b->steps);
+    free(b);
+}
+orc_env *orc_batch_env(orc_batch *b, int64_t e) { return b->envs[e]; }
+int32_t orc_batch_episode(const orc_batch *b, int64_t e) { return b->episode[e]; }
+int32_t orc_batch_steps(const orc_batch *b, int64_t e) { return b->steps[e]; }
+void orc_batch_stats(const orc_batch *b, uint64_t *out5) {
+    out5[0] = b->agent_steps;
+    out5[1] = b->episodes_done;
+    out5[2] = b->episodes_capped;
+    out5[3] = b->explore_steps;
+    out5[4] = (uint64_t)b->reward_sum;
+}
+
+static uint32_t philox_word(uint64_t round, uint32_t stream, uint32_t seed, uint32_t env, int word) {
+    uint32_t ctr[4] = {(uint32_t)round, (uint32_t)(round >> 32), stream, 0}, key[2] = {seed, env}, out[4];
+    orc_philox4x32_10(ctr, key, out);
+    return out[word];
+}
+/* decision word of car c in round r: cars 0..3 share one Philox block, car 4 uses the next stream */
+static uint32_t decision_word(uint64_t round, int car, uint32_t seed, uint32_t env) {
+    return philox_word(round, (uint32_t)(car >> 2), seed, env, car & 3);
+}
+
+/* headings: [n_envs][n_cars] values 0..3 or NULL (Philox stream 3, round 0) */
+void orc_batch_reset(orc_batch *b, const uint8_t *headings, uint32_t seed, int zero_counters) {
+    for (int64_t e = 0; e < b->n_envs; e++) {
+        uint32_t hb = 0;
+        if (headings)
+            for (int i = 0; i < b->n_cars; i++) hb |= (uint32_t)(headings[e * b->n_cars + i] & 3u) << (2 * i);
+        else
+            hb = philox_word(0, 3, seed, b->env_id_base + (uint32_t)e, 0);
+        init_env(b, e, hb);
+        b->steps[e] = 0;
+        if (zero_counters) b->episode[e] = 0;
+    }
+}
+
+static int nth_set_bit(int mask, int n) {
+    for (int a = 0; a < 8; a++)
+        if ((mask >> a) & 1) {
+            if (n == 0) return a;
+            n--;
+        }
+    return -1;
+}
+/* 6-action oracle mask -> 5-bit S,L,R,F,T mask of the ABI */
+static int mask5(int m6) { return (m6 & 0xF) | (((m6 >> 5) & 1) << 4); }
+
+static void end_of_round(orc_batch *b, int64_t e, uint64_t round, uint32_t seed, uint64_t *episodes, uint64_t *capped) {
+    int finished = orc_env_is_game_ended(b->envs[e]);
+    int cap = !finished && b->step_cap > 0 && b->steps[e] >= b->step_cap;
+    if (finished || cap) {
+        (*episodes)++;
+        *capped += (uint64_t)cap;
+        b->episode[e] += 1;
+        b->steps[e] = 0;
+        init_env(b, e, philox_word(round, 2, seed, b->env_id_base + (uint32_t)e, 0));
+    }
+}
+
+/* ---- random-policy rollout (the reference's epsilon = 1 behaviour, qlearning.py:99-102) -------- */
+typedef struct {
+    orc_batch *b;
+    int64_t lo, hi;
+    int rounds, dqn;
+    uint64_t first_round;
+    uint32_t seed;
+    uint8_t *action, *done;
+    float *reward;
+    orc_state *next;
+    uint64_t steps, episodes, capped;
+    int64_t rsum;
+} rollout_job;
+
+static void *rollout_worker(void *arg) {
+    rollout_job *j = (rollout_job *)arg;
+    orc_batch *b = j->b;
+    const int nc = b->n_cars;
+    for (int64_t e = j->lo; e < j->hi; e++) {
+        orc_env *env = b->envs[e];
+        uint32_t envid = b->env_id_base + (uint32_t)e;
+        for (int r = 0; r < j->rounds; r++) {
+            uint64_t round = j->first_round + (uint64_t)r;
+            for (int c = 0; c < nc; c++) {
+                size_t o = ((size_t)r * (size_t)nc + (size_t)c) * (size_t)b->n_envs + (size_t)e;
+                int a5 = ACT_SKIP;
+                double rw = 0;
+                orc_state ns;
+                memset(&ns, 0, sizeof ns);
+                ns.pnode = ORC_NONE;
+                if (!orc_env_car_done(env, c)) {
+                    orc_state st;
+                    orc_env_encodestate(env, c, 1, &st);
+                    int lm = mask5(orc_env_legal(env, &st));
+                    if (lm) {
+                        uint32_t w = decision_word(round, c, j->seed, envid);
+                        int cnt = __builtin_popcount((unsigned)lm);
+                        a5 = nth_set_bit(lm, (int)(((w & 0xFFFFu) * (uint32_t)cnt) >> 16));
+                        orc_env_successor_state(env, &st, ACT5[a5], &ns);
+                        rw = orc_env_reward(env, &st, &ns, c, j->dqn);
+                        orc_env_update_car(env, c, ns.pnode);
+                        if (b->steps[e] < 0xFFFF) b->steps[e]++;
+                        j->steps++;
+                        j->rsum += (int64_t)llround(j->dqn ? rw * 100.0 : rw);
+                    }
+                }
+                if (j->action) j->action[o] = (uint8_t)a5;
+                if (j->reward) j->reward[o] = (float)rw;
+                if (j->next) j->next[o] = ns;
+                if (j->done) j->done[o] = (uint8_t)orc_env_is_game_ended(env);
+            }
+            end_of_round(b, e, round, j->seed, &j->episodes, &j->capped);
+        }
+    }
+    return NULL;
+}
+
+void orc_batch_rollout_random(orc_batch *b, int rounds, uint64_t first_round, uint32_t seed, int dqn, int threads,
+                              uint8_t *action, float *reward, uint8_t *done, orc_state *next) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    rollout_job jobs[256];
+    pthread_t tid[256];
+    for (int t = 0; t < threads; t++) {
+        rollout_job *j = &jobs[t];
+        memset(j, 0, sizeof *j);
+        j->b = b;
+        j->lo = b->n_envs * t / threads;
+        j->hi = b->n_envs * (t + 1) / threads;
+        j->rounds = rounds;
+        j->dqn = dqn;
+        j->first_round = first_round;
+        j->seed = seed;
+        j->action = action;
+        j->reward = reward;
+        j->done = done;
+        j->next = next;
+        if (threads == 1) rollout_worker(j);
+        else pthread_create(&tid[t], NULL, rollout_worker, j);
+    }
+    for (int t = 0; t < threads; t++) {
+        if (threads > 1) pthread_join(tid[t], NULL);
+        b->agent_steps += jobs[t].steps;
+        b->explore_steps += jobs[t].steps;
+        b->episodes_done += jobs[t].episodes;
+        b->episodes_capped += jobs[t].capped;
+        b->reward_sum += jobs[t].rsum;
+    }
+}
+
+/* ---- learner sub-step ---------------------------------------------------------------------- */
+typedef struct {
+    float alpha, discount;
+    int32_t episodes;
+    int32_t eps_threshold[5];
+    uint32_t eps_q16[6];
+    uint32_t seed;
+} orc_learner;
+
+static uint32_t eps_q16_of(const orc_learner *lp, int32_t episode) {
+    uint32_t e = lp->eps_q16[5];
+    for (int i = 4; i >= 0; i--)
+        if (episode < lp->eps_threshold[i]) e = lp->eps_q16[i];
+    return e;
+}
+
+typedef struct {
+    int64_t key; /* index into the oracle Q map, -1 = no update */
+    float newv;
+} pending;
+
+/* One sub-step for car slot c.  q must have been created with f32 = 1.  forced: NULL or [n_envs]
+ * (ACT_SKIP = own decision, else take that action as exploration).  Outputs optional. */
+void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, uint64_t round, const uint8_t *forced,
+                         uint8_t *action_out, orc_state *state_out, float *reward_out) {
+    const int nc = b->n_cars;
+    pending *pend = (pending *)malloc(sizeof(pending) * (size_t)b->n_envs);
+    /* phase 1: every env decides and steps against the Q table as it stands (no writes yet) */
+    for (int64_t e = 0; e < b->n_envs; e++) {
+        orc_env *env = b->envs[e];
+        uint32_t envid = b->env_id_base + (uint32_t)e;
+        pend[e].key = -1;
+        int a_out = ACT_SKIP;
+        float r_out = 0.f;
+        orc_state st;
+        memset(&st, 0, sizeof st);
+        st.pnode = ORC_NONE;
+        int live = b->episode[e] < lp->episodes;
+        if (live && !orc_env_car_done(env, c)) {
+            orc_env_encodestate(env, c, 1, &st);
+            int lm = mask5(orc_env_legal(env, &st));
+            int f = forced ? forced[e] : ACT_SKIP;
+            int forced_ok = f >= ACT_GREEDY || (f < 5 && ((lm >> f) & 1));
+            if (lm && forced_ok) {
+                int a5, explore;
+                if (f == ACT_GREEDY) {
+                    a5 = 0;
+                    explore = 0;
+                } else if (f != ACT_SKIP) {
+                    a5 = f;
+                    explore = 1;
+                } else {
+                    uint32_t w = decision_word(round, c, lp->seed, envid);
+                    explore = (w >> 16) < eps_q16_of(lp, b->episode[e]);
+                    a5 = nth_set_bit(lm, (int)(((w & 0xFFFFu) * (uint32_t)__builtin_popcount((unsigned)lm)) >> 16));
+                }
+                if (!explore) { /* first maximum in S,L,R,F,T order; absent keys read 0.0 */
+                    float best = 0.f;
+                    int have = 0;
+                    for (int k = 0; k < 5; k++) {
+                        if (!((lm >> k) & 1)) continue;
+                        float v = (float)orc_q_peek(q, &st, ACT5[k], NULL);
+                        if (!have || v > best) { best = v; a5 = k; have = 1; }
+                    }
+                }
+                b->explore_steps += (uint64_t)explore;
+                orc_state ns;
+                orc_env_successor_state(env, &st, ACT5[a5], &ns);
+                double rw = orc_env_reward(env, &st, &ns, c, 0);
+                int lm2 = mask5(orc_env_legal(env, &ns));
+                float nv = 0.f;
+                int have = 0;
+                for (int k = 0; k < 5; k++) {
+                    if (!((lm2 >> k) & 1)) continue;
+                    float v = (float)orc_q_peek(q, &ns, ACT5[k], NULL);
+                    if (!have || v > nv) { nv = v; have = 1; }
+                }
+                float qa = (float)orc_q_peek(q, &st, ACT5[a5], NULL);
+                float target = (float)rw + lp->discount * nv;
+                float diff = target - qa;
+                float newv = qa + lp->alpha * diff;
+                pend[e].key = orc_q_index(q, &st, ACT5[a5]);
+                pend[e].newv = newv;
+                orc_env_update_car(env, c, ns.pnode);
+                if (b->steps[e] < 0xFFFF) b->steps[e]++;
+                b->agent_steps++;
+                b->reward_sum += (int64_t)rw;
+                a_out = a5;
+                r_out = (float)rw;
+            }
+        }
+        if (live && c == nc - 1) end_of_round(b, e, round, lp->seed, &b->episodes_done, &b->episodes_capped);
+        if (action_out) action_out[e] = (uint8_t)a_out;
+        if (state_out) state_out[e] = st;
+        if (reward_out) reward_out[e] = r_out;
+    }
+    /* phase 2: per key, mean of the contributed values in 2^-18 fixed point; exact when alone */
+    int64_t nq = orc_q_size(q);
+    int64_t *sum = (int64_t *)calloc((size_t)nq, sizeof(int64_t));
+    uint32_t *cnt = (uint32_t *)calloc((size_t)nq, sizeof(uint32_t));
+    float *last = (float *)calloc((size_t)nq, sizeof(float));
+    for (int64_t e = 0; e < b->n_envs; e++) {
+        if (pend[e].key < 0) continue;
+        sum[pend[e].key] += (int64_t)llrintf(pend[e].newv * 262144.0f);
+        cnt[pend[e].key] += 1;
+        last[pend[e].key] = pend[e].newv;
+    }
+    for (int64_t k = 0; k < nq; k++) {
+        if (!cnt[k]) continue;
+        float v = cnt[k] == 1 ? last[k] : (float)((double)sum[k] / ((double)cnt[k] * 262144.0));
+        orc_q_set_at(q, k, (double)v);
+    }
+    free(sum);
+    free(cnt);
+    free(last);
+    free(pend);
+}
+
+void orc_batch_q_round(orc_batch *b, orc_q *q, const orc_learner *lp, uint64_t round) {
+    for (int c = 0; c < b->n_cars; c++) orc_batch_q_substep(b, q, lp, c, round, NULL, NULL, NULL, NULL);
+}

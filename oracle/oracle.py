@@ -291,3 +291,136 @@ class QTable:
 
 def epsilon(episodes, episode, model=3):
     return lib().orc_epsilon(episodes, episode, model)
+
+
+# ---- batched driver (oracle/mdpp_oracle_batch.c) -------------------------------------------------
+class Learner(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("discount", C.c_float), ("episodes", C.c_int32),
+                ("eps_threshold", C.c_int32 * 5), ("eps_q16", C.c_uint32 * 6), ("seed", C.c_uint32)]
+
+
+def learner(episodes, alpha=0.9, discount=0.15, model=3, seed=3):
+    """Schedule derived from the oracle's own epsilon function (reference src/utils/utils.py:12-52)."""
+    lp = Learner()
+    lp.alpha, lp.discount, lp.episodes, lp.seed = alpha, discount, episodes, seed
+    eps = [epsilon(episodes, e, model) for e in range(episodes)]
+    values = [1.0, 0.8, 0.5, 0.3, 0.15, 0.0] if model == 3 else None
+    if model != 3:
+        raise NotImplementedError
+    for i in range(5):  # threshold i = first episode whose epsilon is below values[i]
+        lp.eps_threshold[i] = next((e for e in range(episodes) if eps[e] < values[i]), episodes)
+    for i in range(6):
+        lp.eps_q16[i] = int(round(values[i] * 65536))
+    return lp
+
+
+_batch_sigs_done = False
+
+
+def _batch_lib():
+    global _batch_sigs_done
+    L = lib()
+    if not _batch_sigs_done:
+        P = C.c_void_p
+        I32P = C.POINTER(C.c_int32)
+        L.orc_batch_create.restype = P
+        L.orc_batch_create.argtypes = [P, C.c_int64, C.c_int, I32P, I32P, I32P, C.c_char_p, C.c_int, C.c_uint32]
+        L.orc_batch_destroy.argtypes = [P]
+        L.orc_batch_destroy.restype = None
+        L.orc_batch_env.restype = P
+        L.orc_batch_env.argtypes = [P, C.c_int64]
+        L.orc_batch_episode.restype = C.c_int32
+        L.orc_batch_episode.argtypes = [P, C.c_int64]
+        L.orc_batch_steps.restype = C.c_int32
+        L.orc_batch_steps.argtypes = [P, C.c_int64]
+        L.orc_batch_stats.restype = None
+        L.orc_batch_stats.argtypes = [P, C.POINTER(C.c_uint64)]
+        L.orc_batch_reset.restype = None
+        L.orc_batch_reset.argtypes = [P, P, C.c_uint32, C.c_int]
+        L.orc_batch_rollout_random.restype = None
+        L.orc_batch_rollout_random.argtypes = [P, C.c_int, C.c_uint64, C.c_uint32, C.c_int, C.c_int, P, P, P, P]
+        L.orc_batch_q_substep.restype = None
+        L.orc_batch_q_substep.argtypes = [P, P, C.POINTER(Learner), C.c_int, C.c_uint64, P, P, P, P]
+        L.orc_batch_q_round.restype = None
+        L.orc_batch_q_round.argtypes = [P, P, C.POINTER(Learner), C.c_uint64]
+        _batch_sigs_done = True
+    return L
+
+
+class Batch:
+    """N scalar oracle envs driven with the batch semantics of DESIGN.md (CPU, for checking)."""
+
+    def __init__(self, cfg, n_envs, boxes, dest_index, choose, bad_states_text=None, step_cap=0, env_id_base=0):
+        import numpy as np
+        self.np = np
+        self.cfg = cfg
+        self.n_envs, self.n_cars = n_envs, len(boxes)
+        n = self.n_cars
+        sb = (C.c_int32 * n)(*[box_id(b) for b in boxes])
+        di = (C.c_int32 * n)(*dest_index)
+        ch = (C.c_int32 * (3 * n))(*[(list(c) + [0, 0, 0])[:3][k] for c in choose for k in range(3)])
+        self._bad = bad_states_text.encode() if bad_states_text is not None else None
+        self.h = _batch_lib().orc_batch_create(cfg.h, n_envs, n, sb, di, ch, self._bad, step_cap, env_id_base)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _batch_lib().orc_batch_destroy(self.h)
+            self.h = None
+
+    def reset(self, headings=None, seed=3, zero_counters=True):
+        np = self.np
+        hp = None
+        if headings is not None:
+            headings = np.ascontiguousarray(headings, dtype=np.uint8)
+            hp = headings.ctypes.data_as(C.c_void_p)
+        _batch_lib().orc_batch_reset(self.h, hp, seed, int(zero_counters))
+
+    def rollout_random(self, rounds, first_round=0, seed=3, dqn=False, threads=1, outputs=True):
+        np = self.np
+        shape = (rounds, self.n_cars, self.n_envs)
+        out = {}
+        if outputs:
+            out = {"action": np.empty(shape, np.uint8), "reward": np.empty(shape, np.float32),
+                   "done": np.empty(shape, np.uint8), "next": (State * (rounds * self.n_cars * self.n_envs))()}
+        p = lambda k: out[k].ctypes.data_as(C.c_void_p) if k in out else None
+        _batch_lib().orc_batch_rollout_random(
+            self.h, rounds, first_round, seed, int(dqn), threads, p("action"), p("reward"), p("done"),
+            C.cast(out["next"], C.c_void_p) if outputs else None)
+        return out
+
+    def q_substep(self, q, lp, car, rnd, forced=None, outputs=True):
+        np = self.np
+        n = self.n_envs
+        out = {}
+        if outputs:
+            out = {"action": np.empty(n, np.uint8), "reward": np.empty(n, np.float32), "state": (State * n)()}
+        fp = None
+        if forced is not None:
+            forced = np.ascontiguousarray(forced, dtype=np.uint8)
+            fp = forced.ctypes.data_as(C.c_void_p)
+        _batch_lib().orc_batch_q_substep(
+            self.h, q.h, C.byref(lp), car, rnd, fp,
+            out["action"].ctypes.data_as(C.c_void_p) if outputs else None,
+            C.cast(out["state"], C.c_void_p) if outputs else None,
+            out["reward"].ctypes.data_as(C.c_void_p) if outputs else None)
+        return out
+
+    def q_round(self, q, lp, rnd):
+        _batch_lib().orc_batch_q_round(self.h, q.h, C.byref(lp), rnd)
+
+    def env_cars(self, e):
+        L = lib()
+        h = _batch_lib().orc_batch_env(self.h, e)
+        return [(L.orc_env_car_node(h, i), L.orc_env_car_dest_index(h, i), L.orc_env_car_done(h, i),
+                 L.orc_env_car_done_count(h, i)) for i in range(self.n_cars)]
+
+    def counters(self, e):
+        L = _batch_lib()
+        return L.orc_batch_episode(self.h, e), L.orc_batch_steps(self.h, e)
+
+    def stats(self):
+        o = (C.c_uint64 * 5)()
+        _batch_lib().orc_batch_stats(self.h, o)
+        rs = o[4] if o[4] < (1 << 63) else o[4] - (1 << 64)
+        return {"agent_steps": o[0], "episodes_done": o[1], "episodes_capped": o[2], "explore_steps": o[3],
+                "reward_sum": rs}
