@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched MARL-DPP hot path on B200.
+
+Workload (BASELINE.json configs[1]): tabular Q-learning on layout 3 block 2 (down_right), the
+layout's live initial state (2 cars), bad-states ON, 2^20 lockstep envs per GPU, reference
+hyper-parameters (alpha 0.9, gamma 0.15, epsilon model 3, 5000 episodes per env, step cap
+10000).  One "step" = one round-robin round over every env of the batch = n_cars x (fused
+select+step+TD kernel, finalize kernel).  Metric: agent-env-steps/s (== Q-updates/s on this path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = device-timed whole-job
+throughput, e2e = the same metric through the public host-facing call (parameters from host
+memory in, counters back, synchronised every step), roofline = the dominant kernel against the
+measured HBM peak, cpu_baseline = the CPU oracle port on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-env-steps/sec"
+UNIT = "agent-env-steps/s"
+BLOCK = 2
+STEP_CAP = 10000
+EPISODES = 5000
+WORKLOAD = "qlearning-layout3-block2-2car-badstates-1Mi-envs-per-gpu"
+FUSED_Q_BYTES_PER_STEP = lambda k: 44.0 + 16.0 / k  # fused Q-learning, per agent-step
+
+
+def bad_text():
+    import gzip
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "bad_states.json.gz")) as f:
+        return json.load(f)["down_right"]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(seconds, threads=None, envs_per_thread=2048, rounds_per_chunk=20):
+    """The CPU arm: oracle port (the reference is pure Python and cannot travel to the GPU box; its
+    measured rate here is quoted in DESIGN.md).  One independent learner replica per host thread."""
+    from oracle import oracle as orc
+    import marl_dpp_b200 as m
+    threads = threads or os.cpu_count() or 1
+    boxes, idx, choose = m.layout_3[BLOCK]["initial_states"][0]
+    lp = orc.learner(EPISODES, seed=3)
+    b = orc.CpuBench(orc.Config(m.layout_3[BLOCK]), threads, envs_per_thread, boxes, idx, choose, bad_text(),
+                     STEP_CAP, lp)
+    b.run(2)  # warm the tables
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        steps += b.run(rounds_per_chunk)
+    dt = time.perf_counter() - t0
+    b.close()
+    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d independent oracle learners x %d envs, %.1f s, same scenario/hyper-parameters"
+                      % (threads, envs_per_thread, dt)}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    import marl_dpp_b200 as m
+    threads = os.cpu_count() or 1
+    envs_per_thread, rounds_per_step = 2048, 10
+    boxes, idx, choose = m.layout_3[BLOCK]["initial_states"][0]
+    lp = orc.learner(EPISODES, seed=3)
+    b = orc.CpuBench(orc.Config(m.layout_3[BLOCK]), threads, envs_per_thread, boxes, idx, choose, bad_text(),
+                     STEP_CAP, lp)
+    for _ in range(args.warmup):
+        b.run(rounds_per_step)
+    steps, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        steps += b.run(rounds_per_step)
+    dt = time.perf_counter() - t0
+    b.close()
+    v = steps / dt
+    sample = ("each step = %d rounds of %d independent oracle learners x %d envs (bounded sample of the workload)"
+              % (rounds_per_step, threads, envs_per_thread))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arm": "CPU oracle port on host cores (reference is pure Python)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--sync-interval", type=int, default=16, help="rounds between Q-replica all-reduces (N>1)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-aux", action="store_true", help="skip the secondary (random-rollout, gym e2e) lines")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import marl_dpp_b200 as m
+    from marl_dpp_b200 import _lib
+    from marl_dpp_b200.batched import BatchedEnv, BatchedQLearner
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        cpu = cpu_reference(args.cpu_seconds)  # before CUDA start-up: host cores are otherwise idle
+
+    if _lib.needs_build():
+        if local == 0:
+            _lib.build()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    boxes, idx, choose = m.layout_3[BLOCK]["initial_states"][0]
+    sc = m.Scenario(m.layout_3[BLOCK], boxes, idx, choose, bad_states_text=bad_text(), step_cap=STEP_CAP)
+    n, k = args.envs, sc.n_cars
+    env = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=3)
+    lr = BatchedQLearner(env, episodes=EPISODES, seed=3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        lr.train_rounds(1)
+        if world > 1 and args.sync_interval > 0 and (i + 1) % args.sync_interval == 0:
+            lr.sync_replicas()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    env.stats(reset=True)
+
+    # ---- timed region: K steps, per-step CUDA events on the launching stream, L2 flushed between
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        one_step(args.warmup + i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    st = env.stats(reset=True)
+    t = torch.tensor([dev_ms, float(st["agent_steps"]), float(st["q_updates"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dev_ms = float(tmax[0])
+    total_steps, total_upd = float(t[1]), float(t[2])
+    value = total_steps / (dev_ms * 1e-3)
+
+    # ---- e2e: the public host-facing call, one round per call, counters read back every step ----
+    barrier()
+    e2e_steps0 = env.stats(reset=True)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        lr.train_rounds_host(1)  # learner params from host memory in, mdpp_stats back, stream synchronised
+        if world > 1 and args.sync_interval > 0 and (i + 1) % args.sync_interval == 0:
+            lr.sync_replicas()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    st2 = env.stats(reset=True)
+    t2 = torch.tensor([e2e_dt, float(st2["agent_steps"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        t2max = t2.clone()
+        dist.all_reduce(t2max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        e2e_dt = float(t2max[0])
+    e2e_value = float(t2[1]) / e2e_dt
+
+    # ---- roofline of the dominant kernel: q_substep, timed alone with CUDA events ---------------
+    roof = None
+    if rank == 0:
+        reps = min(args.steps, 100)
+        kev = []
+        before = env.stats(reset=True)
+        for i in range(reps):
+            for c in range(k):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                lr.substep(c)
+                b.record()
+                lr.finalize()
+                kev.append((a, b))
+            lr.round += 1
+        torch.cuda.synchronize()
+        st3 = env.stats(reset=True)
+        avg_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+        units = st3["agent_steps"] / len(kev)
+        bytes_per_launch = FUSED_Q_BYTES_PER_STEP(k) * units
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        peak, how = measured_peak()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("q_substep_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "q_substep_kernel<%d>" % k, "avg_launch_ms": avg_ms,
+                "units_per_launch": units, "algorithmic_bytes_per_unit": FUSED_Q_BYTES_PER_STEP(k), "peak_source": how,
+                "note": "integer-ALU/latency-bound kernel; state and Q table are L2-resident at this size"}
+
+    # ---- secondary lines (not the headline): random-policy rollout and gym-style host stepping ----
+    aux = {}
+    if rank == 0 and not args.no_aux:
+        rounds = 16
+        env2 = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=4)
+        for w in range(3):
+            env2.rollout_random(rounds, w * rounds)
+        torch.cuda.synchronize()
+        env2.stats(reset=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        flush.zero_()
+        a.record()
+        for w in range(reps):
+            env2.rollout_random(rounds, (3 + w) * rounds)
+        b.record()
+        torch.cuda.synchronize()
+        s = env2.stats(reset=True)
+        aux["random_rollout_no_outputs"] = {"value": s["agent_steps"] / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
+                                            "rounds_per_launch": rounds}
+        outs = env2.alloc_rollout_outputs(1)
+        a.record()
+        for w in range(reps * 4):
+            env2.rollout_random(1, 1000 + w, outputs=outs)
+        b.record()
+        torch.cuda.synchronize()
+        s = env2.stats(reset=True)
+        ms = a.elapsed_time(b)
+        aux["random_rollout_outputs_materialised"] = {
+            "value": s["agent_steps"] / (ms * 1e-3), "unit": UNIT, "rounds_per_launch": 1,
+            "algorithmic_GBps": (10.0 + 16.0 / k) * s["agent_steps"] / (ms * 1e-3) / 1e9}
+        # gym-style e2e: host actions in, host (state, next, reward, legal, status, done) out, per car slot
+        acts = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        out = {"state": torch.empty(n, dtype=torch.int32).pin_memory(),
+               "next_state": torch.empty(n, dtype=torch.int32).pin_memory(),
+               "reward": torch.empty(n, dtype=torch.float32).pin_memory(),
+               "legal": torch.empty(n, dtype=torch.uint8).pin_memory(),
+               "status": torch.empty(n, dtype=torch.uint8).pin_memory(),
+               "done": torch.empty(n, dtype=torch.uint8).pin_memory()}
+        env2.reset()
+        env2.stats(reset=True)
+        t0 = time.perf_counter()
+        for w in range(10):
+            for c in range(k):
+                env2.step_car_host(c, acts, out)
+        dt = time.perf_counter() - t0
+        s = env2.stats(reset=True)
+        aux["gym_step_host_buffers"] = {"value": s["agent_steps"] / dt, "unit": UNIT,
+                                        "h2d_bytes_per_call": n, "d2h_bytes_per_call": 15 * n}
+        del env2
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "layout": 3, "block": BLOCK, "n_cars": k, "envs_per_gpu": n,
+                       "bad_states": True, "episodes_per_env": EPISODES, "step_cap": STEP_CAP,
+                       "alpha": 0.9, "discount": 0.15, "epsilon_model": 3,
+                       "step": "one round-robin round over every env = n_cars x (q_substep + q_finalize)",
+                       "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
+                       "sync_interval_rounds": args.sync_interval if world > 1 else None,
+                       "parallelism": "dp%d: env shards + per-GPU Q replicas, NCCL all-reduce(AVG)" % world},
+            "q_updates_per_s": total_upd / (dev_ms * 1e-3),
+            "wall_s_timed_region": wall,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(lr.params),
+                    "d2h_bytes_per_step": 64,
+                    "call": "BatchedQLearner.train_rounds_host(1) -> mdpp_q_train_rounds_host (sync each step)"},
+            "gpu_launches": args.steps * k * 2,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "aux": aux,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

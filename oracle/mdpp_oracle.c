@@ -573,7 +573,8 @@ static int64_t q_insert(orc_q *q, const qkey *k) {
 double orc_q_get(orc_q *q, const orc_state *s, int action) {
     qkey k;
     make_key(&k, s, action);
-    return q->vals[q_insert(q, &k)];
+    int64_t i = q_insert(q, &k); /* may realloc vals: index first */
+    return q->vals[i];
 }
 double orc_q_peek(const orc_q *q, const orc_state *s, int action, int *present) {
     qkey k;
@@ -585,7 +586,8 @@ double orc_q_peek(const orc_q *q, const orc_state *s, int action, int *present) 
 void orc_q_set(orc_q *q, const orc_state *s, int action, double v) {
     qkey k;
     make_key(&k, s, action);
-    q->vals[q_insert(q, &k)] = v;
+    int64_t i = q_insert(q, &k);
+    q->vals[i] = v;
 }
 
 /* reference src/algorithms/qlearning.py:60-72 + Counter.argMax :659-667 (first maximum in legal order) */

@@ -346,3 +346,78 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
 void orc_batch_q_round(orc_batch *b, orc_q *q, const orc_learner *lp, uint64_t round) {
     for (int c = 0; c < b->n_cars; c++) orc_batch_q_substep(b, q, lp, c, round, NULL, NULL, NULL, NULL);
 }
+
+/* ---- CPU baseline: independent learner replicas, one per host thread --------------------------
+ * The reference is single-threaded with a module-global env (qlearning.py:17-18); the way to use
+ * every host core is one independent learner per core.  Each thread owns a
+ * batch of `envs_per_thread` envs and its own Q table and runs `rounds` full rounds. */
+typedef struct {
+    orc_batch *b;
+    orc_q *q;
+    const orc_learner *lp;
+    uint64_t first_round;
+    int rounds;
+} bench_job;
+
+static void *bench_worker(void *arg) {
+    bench_job *j = (bench_job *)arg;
+    for (int r = 0; r < j->rounds; r++) orc_batch_q_round(j->b, j->q, j->lp, j->first_round + (uint64_t)r);
+    return NULL;
+}
+
+typedef struct {
+    int threads;
+    orc_batch **b;
+    orc_q **q;
+    orc_learner lp;
+    uint64_t round;
+} orc_bench;
+
+orc_bench *orc_bench_create(const orc_cfg *cfg, int threads, int64_t envs_per_thread, int n_cars,
+                            const int32_t *start_box, const int32_t *dest_index, const int32_t *choose3,
+                            const char *bad_text, int step_cap, const orc_learner *lp) {
+    for (int s = 0; s < ORC_NODES; s++) /* fill the BFS memo up front: workers only read it */
+        for (int d = 0; d < ORC_NODES; d++) orc_cfg_bfs_len(cfg, s, d);
+    orc_bench *o = (orc_bench *)calloc(1, sizeof(orc_bench));
+    o->threads = threads;
+    o->b = (orc_batch **)calloc((size_t)threads, sizeof(orc_batch *));
+    o->q = (orc_q **)calloc((size_t)threads, sizeof(orc_q *));
+    o->lp = *lp;
+    for (int t = 0; t < threads; t++) {
+        o->b[t] = orc_batch_create(cfg, envs_per_thread, n_cars, start_box, dest_index, choose3, bad_text, step_cap,
+                                   (uint32_t)((int64_t)t * envs_per_thread));
+        orc_batch_reset(o->b[t], NULL, lp->seed, 1);
+        o->q[t] = orc_q_create(1);
+        orc_q_set_params(o->q[t], lp->alpha, lp->discount);
+    }
+    return o;
+}
+void orc_bench_destroy(orc_bench *o) {
+    for (int t = 0; t < o->threads; t++) {
+        orc_batch_destroy(o->b[t]);
+        orc_q_destroy(o->q[t]);
+    }
+    free(o->b);
+    free(o->q);
+    free(o);
+}
+/* runs `rounds` rounds on every replica in parallel; returns the agent-steps taken */
+uint64_t orc_bench_run(orc_bench *o, int rounds) {
+    bench_job jobs[256];
+    pthread_t tid[256];
+    uint64_t before = 0, after = 0;
+    int T = o->threads > 256 ? 256 : o->threads;
+    for (int t = 0; t < T; t++) before += o->b[t]->agent_steps;
+    for (int t = 0; t < T; t++) {
+        jobs[t].b = o->b[t];
+        jobs[t].q = o->q[t];
+        jobs[t].lp = &o->lp;
+        jobs[t].first_round = o->round;
+        jobs[t].rounds = rounds;
+        pthread_create(&tid[t], NULL, bench_worker, &jobs[t]);
+    }
+    for (int t = 0; t < T; t++) pthread_join(tid[t], NULL);
+    o->round += (uint64_t)rounds;
+    for (int t = 0; t < T; t++) after += o->b[t]->agent_steps;
+    return after - before;
+}

@@ -424,3 +424,34 @@ class Batch:
         rs = o[4] if o[4] < (1 << 63) else o[4] - (1 << 64)
         return {"agent_steps": o[0], "episodes_done": o[1], "episodes_capped": o[2], "explore_steps": o[3],
                 "reward_sum": rs}
+
+
+class CpuBench:
+    """Independent oracle learner replicas, one per host thread (CPU baseline of bench.py)."""
+
+    def __init__(self, cfg, threads, envs_per_thread, boxes, dest_index, choose, bad_states_text, step_cap, lp):
+        L = _batch_lib()
+        L.orc_bench_create.restype = C.c_void_p
+        L.orc_bench_create.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_char_p, C.c_int,
+                                       C.POINTER(Learner)]
+        L.orc_bench_run.restype = C.c_uint64
+        L.orc_bench_run.argtypes = [C.c_void_p, C.c_int]
+        L.orc_bench_destroy.restype = None
+        L.orc_bench_destroy.argtypes = [C.c_void_p]
+        n = len(boxes)
+        sb = (C.c_int32 * n)(*[box_id(b) for b in boxes])
+        di = (C.c_int32 * n)(*dest_index)
+        ch = (C.c_int32 * (3 * n))(*[(list(c) + [0, 0, 0])[:3][k] for c in choose for k in range(3)])
+        self._bad = bad_states_text.encode() if bad_states_text is not None else None
+        self.cfg = cfg
+        self.threads = threads
+        self.h = L.orc_bench_create(cfg.h, threads, envs_per_thread, n, sb, di, ch, self._bad, step_cap, C.byref(lp))
+
+    def run(self, rounds):
+        return int(_batch_lib().orc_bench_run(self.h, rounds))
+
+    def close(self):
+        if self.h:
+            _batch_lib().orc_bench_destroy(self.h)
+            self.h = None
