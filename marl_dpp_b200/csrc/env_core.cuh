@@ -270,7 +270,10 @@ __device__ __forceinline__ uint64_t advance_car(uint64_t cars, int c, const View
 
 // n-th (0-based) set bit of a 5-bit mask
 __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t n) {
-    return __fns(mask, 0, n + 1);
+    // drop the n lowest set bits (n <= 4), then find-first-set; __fns() is a ~40-instruction emulation
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) mask = (n > k) ? (mask & (mask - 1u)) : mask;
+    return (uint32_t)__ffs((int)mask) - 1u;
 }
 
 } // namespace mdpp

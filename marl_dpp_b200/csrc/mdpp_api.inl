@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -27,7 +28,7 @@ static int fail(int code, const char *fmt, ...) {
 
 struct Carve {
     size_t tables, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, total;
-    uint32_t touched_capacity;
+    uint32_t touched_capacity, replicas;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -40,8 +41,17 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.tables = take(sizeof(SmemTables));
     c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
     c.recs = take((size_t)n_envs * 16);
-    c.sum = take(keys * 8);
-    c.cnt = take(keys * 4);
+    // accumulator replicas (power of two, <= 64): 8 unless that exceeds a 48 MB budget.  Measured on B200,
+    // 2^20 envs: more replicas cut the same-address tail when all envs share a few states (first
+    // rounds) but widen the L2 footprint in steady state; 4-8 is the flat optimum
+    c.replicas = 8;
+    while (c.replicas > 1 && (size_t)c.replicas * keys * 12 > ((size_t)48 << 20)) c.replicas >>= 1;
+    if (const char *env = getenv("MDPP_REPLICAS")) {
+        int r = atoi(env);
+        if (r >= 1 && r <= 64 && (r & (r - 1)) == 0) c.replicas = (uint32_t)r;
+    }
+    c.sum = take(keys * 8 * c.replicas);
+    c.cnt = take(keys * 4 * c.replicas);
     c.last = take(keys * 4);
     c.bits = take(keys / 8 + 4);
     c.touched_capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
@@ -63,6 +73,8 @@ struct mdpp_handle {
     uint32_t env_id_base;
     char *ws;
     int sm_count;
+    uint32_t parity;        // sub-step parity of the touched-key counters
+    mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
 };
 
 using namespace mdpp;
@@ -170,6 +182,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
         e = cudaMemcpyAsync(h->ws + cv.bad, bad_bitmap_host, (((size_t)cfg->n_box_states + 31) / 32) * 4,
                             cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, sizeof(mdpp_stats) * kStatSlots);
     if (e != cudaSuccess) {
         delete h;
         return fail(MDPP_ECUDA, "workspace initialisation failed: %s", cudaGetErrorString(e));
@@ -179,6 +192,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
 }
 
 int mdpp_destroy(mdpp_handle *h) {
+    if (h && h->stat_slots) cudaFreeHost(h->stat_slots);
     delete h;
     return MDPP_OK;
 }
@@ -273,6 +287,9 @@ static Accum accum_of(mdpp_handle *h) {
     a.touched = (uint32_t *)(h->ws + h->cv.touched);
     a.visited = (uint32_t *)(h->ws + h->cv.visited);
     a.capacity = h->cv.touched_capacity;
+    a.replica_mask = h->cv.replicas - 1;
+    a.parity = h->parity;
+    a.replica_stride = (size_t)h->cfg.n_states * MDPP_Q_ROW;
     return a;
 }
 
@@ -291,10 +308,11 @@ int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slo
 int mdpp_q_finalize(mdpp_handle *h, float *q, void *stream) {
     if (!h) return fail(MDPP_EINVAL, "handle is NULL");
     if (!q) return fail(MDPP_EINVAL, "q is NULL");
-    unsigned grid = (unsigned)std::min<int64_t>((h->cv.touched_capacity + kThreads - 1) / kThreads,
-                                                (int64_t)h->sm_count * 8);
+    unsigned grid = (unsigned)std::min<int64_t>(((int64_t)h->cv.touched_capacity * 32 + kThreads - 1) / kThreads,
+                                                (int64_t)h->sm_count * 4);
     q_finalize_kernel<<<std::max(grid, 1u), kThreads, 0, (cudaStream_t)stream>>>(q, accum_of(h), control_of(h));
     MDPP_CUDA(cudaGetLastError());
+    h->parity ^= 1u;
     return MDPP_OK;
 }
 
@@ -314,9 +332,22 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
 int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *stream) {
     if (!h || !out_host) return fail(MDPP_EINVAL, "handle / out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
-    MDPP_CUDA(cudaMemcpyAsync(out_host, &control_of(h)->stats, sizeof(mdpp_stats), cudaMemcpyDeviceToHost, s));
-    if (reset) MDPP_CUDA(cudaMemsetAsync(&control_of(h)->stats, 0, sizeof(mdpp_stats), s));
+    mdpp_stats *slots = h->stat_slots; // the device keeps kStatSlots privatised copies; summed here
+    MDPP_CUDA(cudaMemcpyAsync(slots, control_of(h)->stats, sizeof(mdpp_stats) * kStatSlots, cudaMemcpyDeviceToHost, s));
+    if (reset) MDPP_CUDA(cudaMemsetAsync(control_of(h)->stats, 0, sizeof(mdpp_stats) * kStatSlots, s));
     MDPP_CUDA(cudaStreamSynchronize(s));
+    mdpp_stats t;
+    memset(&t, 0, sizeof t);
+    for (int i = 0; i < kStatSlots; i++) {
+        t.agent_steps += slots[i].agent_steps;
+        t.q_updates += slots[i].q_updates;
+        t.episodes_done += slots[i].episodes_done;
+        t.episodes_capped += slots[i].episodes_capped;
+        t.reward_sum += slots[i].reward_sum;
+        t.explore_steps += slots[i].explore_steps;
+        t.touched_keys += slots[i].touched_keys;
+    }
+    *out_host = t;
     return MDPP_OK;
 }
 

@@ -11,36 +11,81 @@ namespace mdpp {
 // ------------------------------------------------------------------------------------------------
 // workspace-resident control block
 // ------------------------------------------------------------------------------------------------
+// Counters are privatised over kStatSlots slots (one 64-byte sector each): a CTA reduces its own
+// counts in shared memory and adds them to slot (blockIdx & (kStatSlots-1)).  With one slot every
+// warp of a 1M-env launch hit the same sector with 5 atomics and the launch waited ~60 us on it.
+constexpr int kStatSlots = 128;
 struct Control {
-    mdpp_stats stats;
-    uint32_t touched_count;
-    uint32_t finalize_ticket;
+    mdpp_stats stats[kStatSlots];
+    // double-buffered by sub-step parity: the sub-step appends under [p], its finalize consumes [p] and
+    // zeroes [p^1] for the next sub-step -- no grid-wide fence or "last block" ticket is needed
+    uint32_t touched_count[2];
     uint32_t pad[14];
 };
 
 struct StatAcc {
-    uint32_t steps = 0, episodes = 0, capped = 0, explore = 0, qupd = 0;
+    uint32_t steps = 0, episodes = 0, capped = 0, explore = 0;
     int32_t reward = 0;
 };
 
-__device__ __forceinline__ void flush_stats(const StatAcc &a, int64_t reward64, Control *ctl) {
-    // warp-level integer reductions (REDUX), one atomic per warp and counter
-    uint32_t steps = __reduce_add_sync(0xFFFFFFFFu, a.steps);
-    uint32_t episodes = __reduce_add_sync(0xFFFFFFFFu, a.episodes);
-    uint32_t capped = __reduce_add_sync(0xFFFFFFFFu, a.capped);
-    uint32_t explore = __reduce_add_sync(0xFFFFFFFFu, a.explore);
-    uint32_t qupd = __reduce_add_sync(0xFFFFFFFFu, a.qupd);
-    long long rsum = reward64;
+struct SmemStats {
+    unsigned long long reward;
+    unsigned long long packed; // kSmall kernels: steps | explore << 16 | episodes << 32 | capped << 48
+    uint32_t steps, episodes, capped, explore;
+};
+
+// Call once per thread at kernel end; `ss` must have been zeroed before a __syncthreads().
+// kSmall: every per-thread counter is 0/1 and |reward| < 2^26 (one agent-step per thread), so the
+// five counters travel in one REDUX and one shared-memory atomic per warp.  kQ: each step is a Q-update.
+template <bool kSmall, bool kQ>
+__device__ __forceinline__ void flush_stats(const StatAcc &a, int64_t reward64, Control *ctl, SmemStats &ss) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if constexpr (kSmall) {
+        uint32_t packed = a.steps | (a.explore << 8) | (a.episodes << 16) | (a.capped << 24);
+        packed = __reduce_add_sync(0xFFFFFFFFu, packed);
+        const int rs = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(int)reward64);
+        if (lane == 0) {
+            const unsigned long long wide = (unsigned long long)(packed & 0xFFu) |
+                                            ((unsigned long long)((packed >> 8) & 0xFFu) << 16) |
+                                            ((unsigned long long)((packed >> 16) & 0xFFu) << 32) |
+                                            ((unsigned long long)(packed >> 24) << 48);
+            if (wide) atomicAdd(&ss.packed, wide);
+            if (rs) atomicAdd(&ss.reward, (unsigned long long)(long long)rs);
+        }
+    } else {
+        uint32_t steps = __reduce_add_sync(0xFFFFFFFFu, a.steps);
+        uint32_t episodes = __reduce_add_sync(0xFFFFFFFFu, a.episodes);
+        uint32_t capped = __reduce_add_sync(0xFFFFFFFFu, a.capped);
+        uint32_t explore = __reduce_add_sync(0xFFFFFFFFu, a.explore);
+        long long rsum = reward64;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
-    if ((threadIdx.x & 31) == 0) {
-        if (steps) atomicAdd((unsigned long long *)&ctl->stats.agent_steps, (unsigned long long)steps);
-        if (episodes) atomicAdd((unsigned long long *)&ctl->stats.episodes_done, (unsigned long long)episodes);
-        if (capped) atomicAdd((unsigned long long *)&ctl->stats.episodes_capped, (unsigned long long)capped);
-        if (explore) atomicAdd((unsigned long long *)&ctl->stats.explore_steps, (unsigned long long)explore);
-        if (qupd) atomicAdd((unsigned long long *)&ctl->stats.q_updates, (unsigned long long)qupd);
-        if (rsum) atomicAdd((unsigned long long *)&ctl->stats.reward_sum, (unsigned long long)rsum);
+        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
+        if (lane == 0) {
+            if (steps) atomicAdd(&ss.steps, steps);
+            if (episodes) atomicAdd(&ss.episodes, episodes);
+            if (capped) atomicAdd(&ss.capped, capped);
+            if (explore) atomicAdd(&ss.explore, explore);
+            if (rsum) atomicAdd(&ss.reward, (unsigned long long)rsum);
+        }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mdpp_stats *slot = &ctl->stats[blockIdx.x & (kStatSlots - 1)];
+        const unsigned long long steps = ss.steps + (ss.packed & 0xFFFFull);
+        const unsigned long long explore = ss.explore + ((ss.packed >> 16) & 0xFFFFull);
+        const unsigned long long episodes = ss.episodes + ((ss.packed >> 32) & 0xFFFFull);
+        const unsigned long long capped = ss.capped + (ss.packed >> 48);
+        if (steps) atomicAdd((unsigned long long *)&slot->agent_steps, steps);
+        if (episodes) atomicAdd((unsigned long long *)&slot->episodes_done, episodes);
+        if (capped) atomicAdd((unsigned long long *)&slot->episodes_capped, capped);
+        if (explore) atomicAdd((unsigned long long *)&slot->explore_steps, explore);
+        if (kQ && steps) atomicAdd((unsigned long long *)&slot->q_updates, steps);
+        if (ss.reward) atomicAdd((unsigned long long *)&slot->reward_sum, ss.reward);
+    }
+}
+
+__device__ __forceinline__ void zero_stats(SmemStats &ss) {
+    if (threadIdx.x == 0) ss = SmemStats{0ull, 0ull, 0u, 0u, 0u, 0u};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -80,6 +125,8 @@ step_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, int
                 uint32_t *__restrict__ next_idx, float *__restrict__ reward, uint8_t *__restrict__ legal,
                 uint8_t *__restrict__ status, uint8_t *__restrict__ done_out, Control *ctl) {
     __shared__ SmemTables sm;
+    __shared__ SmemStats ss;
+    zero_stats(ss);
     load_tables(sm, cfg.tables);
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StatAcc acc;
@@ -121,7 +168,7 @@ step_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, int
         if (status) status[e] = (uint8_t)st;
         if (done_out) done_out[e] = (uint8_t)all_done<NC>(cars);
     }
-    flush_stats(acc, rsum, ctl);
+    flush_stats<true, false>(acc, rsum, ctl, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -134,6 +181,8 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
                       float *__restrict__ reward_out, uint8_t *__restrict__ done_out,
                       uint32_t *__restrict__ next_out, Control *ctl) {
     __shared__ SmemTables sm;
+    __shared__ SmemStats ss;
+    zero_stats(ss);
     load_tables(sm, cfg.tables);
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StatAcc acc;
@@ -191,7 +240,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
         rec.z = episode | (steps << 16);
         recs[e] = rec;
     }
-    flush_stats(acc, rsum, ctl);
+    flush_stats<false, false>(acc, rsum, ctl, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,6 +256,11 @@ struct Accum {
     uint32_t *touched;     // [capacity] list of touched keys
     uint32_t *visited;     // [n_states] bit a = (state, a) has been updated at least once
     uint32_t capacity;
+    // sum/cnt are privatised: CTA b accumulates into replica (b & replica_mask), so that a hot key is
+    // spread over up to 64 L2 addresses instead of serialising every env of the batch on one
+    uint32_t replica_mask;
+    uint32_t parity;       // which touched_count the current sub-step uses
+    size_t replica_stride; // in keys
 };
 
 // epsilon schedule (reference src/utils/utils.py:33-52, model 3) on the per-env episode counter
@@ -225,6 +279,8 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                  const uint8_t *__restrict__ forced, uint8_t *__restrict__ action_out,
                  uint32_t *__restrict__ state_out, float *__restrict__ reward_out, Control *ctl) {
     __shared__ SmemTables sm;
+    __shared__ SmemStats ss;
+    zero_stats(ss);
     load_tables(sm, cfg.tables);
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StatAcc acc;
@@ -297,22 +353,22 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 // ---- accumulate: mean over the envs that update this key in this sub-step ----
                 const uint32_t key = sidx * MDPP_Q_ROW + a;
                 const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
-                atomicAdd((unsigned long long *)(ac.sum + key), (unsigned long long)fx);
-                atomicAdd(ac.cnt + key, 1u);
+                const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
+                atomicAdd((unsigned long long *)(ac.sum + rkey), (unsigned long long)fx);
+                atomicAdd(ac.cnt + rkey, 1u);
                 const uint32_t bit = 1u << (key & 31u);
                 uint32_t seen = *(volatile uint32_t *)(ac.touched_bits + (key >> 5));
                 if (!(seen & bit)) {
                     ac.last[key] = newv; // only matters if this env stays the key's single contributor
                     uint32_t old = atomicOr(ac.touched_bits + (key >> 5), bit);
                     if (!(old & bit)) {
-                        uint32_t slot = atomicAdd(&ctl->touched_count, 1u);
+                        uint32_t slot = atomicAdd(&ctl->touched_count[ac.parity], 1u);
                         if (slot < ac.capacity) ac.touched[slot] = key;
                     }
                 }
                 cars = advance_car(cars, c, v, nn, cfg);
                 steps = steps < 0xFFFFu ? steps + 1 : steps;
                 acc.steps = 1;
-                acc.qupd = 1;
                 rsum = ri;
                 a_out = a;
                 r_out = (float)ri;
@@ -339,42 +395,51 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         if (state_out) state_out[e] = s_out;
         if (reward_out) reward_out[e] = r_out;
     }
-    flush_stats(acc, rsum, ctl);
+    flush_stats<true, true>(acc, rsum, ctl, ss);
 }
 
 // finalize: per touched key write the mean of the accumulated values (the value itself when one
 // env contributed), clear the accumulators, record the visited bit used by the qvalue file writer.
 __global__ void __launch_bounds__(kThreads)
 q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
-    const uint32_t n = min(ctl->touched_count, ac.capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t n = min(ctl->touched_count[ac.parity], ac.capacity);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += nwarps) { // one warp per touched key, lanes over the replicas
         const uint32_t key = ac.touched[i];
-        const uint32_t cnt = ac.cnt[key];
-        float v;
-        if (cnt == 1u) {
-            v = ac.last[key];
-        } else {
-            const double mean = (double)ac.sum[key] / ((double)cnt * (double)(1 << MDPP_FIXED_SHIFT));
-            v = (float)mean;
+        long long s = 0;
+        uint32_t cnt = 0;
+        for (uint32_t r = lane; r <= ac.replica_mask; r += 32u) {
+            const size_t rkey = (size_t)r * ac.replica_stride + key;
+            const uint32_t c = ac.cnt[rkey];
+            if (c) {
+                cnt += c;
+                s += ac.sum[rkey];
+                ac.cnt[rkey] = 0;
+                ac.sum[rkey] = 0;
+            }
         }
-        q[key] = v;
-        ac.sum[key] = 0;
-        ac.cnt[key] = 0;
-        ac.touched_bits[key >> 5] = 0; // every set bit of the word belongs to a key finalised in this launch
-        uint32_t *vis = ac.visited + (key >> 3);
-        const uint32_t vb = 1u << (key & 7u);
-        if (!(*vis & vb)) atomicOr(vis, vb);
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (lane == 0) {
+            float v;
+            if (cnt == 1u) {
+                v = ac.last[key];
+            } else {
+                const double mean = (double)s / ((double)cnt * (double)(1 << MDPP_FIXED_SHIFT));
+                v = (float)mean;
+            }
+            q[key] = v;
+            ac.touched_bits[key >> 5] = 0; // every set bit of the word belongs to a key finalised in this launch
+            uint32_t *vis = ac.visited + (key >> 3);
+            const uint32_t vb = 1u << (key & 7u);
+            if (!(*vis & vb)) atomicOr(vis, vb);
+        }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        uint32_t t = atomicAdd(&ctl->finalize_ticket, 1u);
-        if (t == gridDim.x - 1) { // last block: every block has read touched_count by now
-            atomicAdd((unsigned long long *)&ctl->stats.touched_keys, (unsigned long long)n);
-            ctl->touched_count = 0;
-            ctl->finalize_ticket = 0;
-            __threadfence();
-        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->touched_count[ac.parity ^ 1u] = 0;
+        if (n) atomicAdd((unsigned long long *)&ctl->stats[0].touched_keys, (unsigned long long)n);
     }
 }
 
