@@ -203,9 +203,8 @@ class BatchedQLearner:
 
     def sync_replicas(self, group=None):
         """Average the per-GPU Q replicas: one NCCL all-reduce (AVG) over NVLink, in place."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.q, op=dist.ReduceOp.AVG, group=group)
+        from . import parallel
+        parallel.average_(self.q, group)
 
     # -- qvalue .txt format (reference src/algorithms/qlearning.py:159-185) --------------------------
     def qvalue_items(self):
