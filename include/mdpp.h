@@ -88,7 +88,12 @@ typedef struct {
     int32_t eps_threshold[5];   /* int(episodes*{0.4,0.6,0.7,0.85,0.99}) */
     uint32_t eps_q16[6];        /* epsilon * 65536 per schedule segment: {1,.8,.5,.3,.15,0} */
     uint32_t seed;
+    uint32_t flags;             /* MDPP_LEARN_* */
 } mdpp_learner;
+
+#define MDPP_LEARN_FROZEN 1u /* select + step but no TD update: validate_given_state (qlearning.py:384-437) */
+#define MDPP_LEARN_MODE0 2u  /* encodestate(car, 0): finished cars are not listed (qlearning.py:342) */
+#define MDPP_LEARN_DETECT 4u /* stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360) */
 
 /* counters accumulated on the device, fetched with mdpp_get_stats_host */
 typedef struct {
@@ -118,6 +123,8 @@ int mdpp_abi_version(void);
 void *mdpp_env_records(mdpp_handle *h);
 /* device pointer to [n_states] u32: bit a set = key (state, a) has been updated (qvalue file writer) */
 void *mdpp_visited_bits(mdpp_handle *h);
+/* device pointer to [n_envs] u32: state id at which MDPP_LEARN_DETECT flagged env e, 0xFFFFFFFF = none */
+void *mdpp_deadlock_states(mdpp_handle *h);
 
 /* ---- env: reset / initialize (reference src/env_gym.py:643-672,331-352) -------------------- */
 /* headings: [n_envs][n_cars] u8 in 0..3 (N,E,S,W) or NULL => Philox.  env_mask: [n_envs] u8, NULL = all.
@@ -139,6 +146,16 @@ int mdpp_step_car(mdpp_handle *h, int car_slot, int deadlock_id, int reward_kind
 int mdpp_step_car_host(mdpp_handle *h, int car_slot, int deadlock_id, int reward_kind,
                        const uint8_t *actions, uint32_t *state_idx, uint32_t *next_idx, float *reward,
                        uint8_t *legal, uint8_t *status, uint8_t *all_done, void *stream);
+
+/* ---- string-API support: the reference's getlegalactions / get_successor_state / reward_function take
+ * state STRINGS, not the env (src/env_gym.py:188-265,485-620).  Entry i evaluates action[i] from state
+ * state_idx[i]; only the reward's clash term reads env i's cars.  action may be NULL (legal only).
+ * mdpp_update_car is the bare update_car (src/env_gym.py:386-441); nodes[e] = MDPP_NONE skips env e. */
+int mdpp_query_transitions(mdpp_handle *h, int car_slot, int reward_kind, const uint32_t *state_idx /*DEV*/,
+                           const uint8_t *action /*DEV*/, int64_t n, uint8_t *legal /*DEV*/,
+                           uint32_t *next_idx /*DEV*/, float *reward /*DEV*/, uint8_t *next_legal /*DEV*/,
+                           void *stream);
+int mdpp_update_car(mdpp_handle *h, int car_slot, const uint8_t *nodes /*DEV [n_envs]*/, void *stream);
 
 /* ---- env: lockstep rollout under the uniform-random legal policy (reference eps = 1 behaviour,
  * src/algorithms/qlearning.py:99-102) with Philox4x32-10 and auto-reset.  `rounds` full

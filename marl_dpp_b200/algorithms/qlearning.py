@@ -1,0 +1,200 @@
+"""Tabular Q-learning plugin with the reference's algorithm contract
+(reference src/algorithms/qlearning.py:13-437; constructed by app.py:91-96 as
+`RL(**settings.params, sess=, env_config=)` and driven through train_given_state /
+detect_deadlocks_v0 / validate_given_state, app.py:42-72).
+
+The per-episode Python loop of the reference (qlearning.py:187-239) is replaced by the fused
+CUDA learner over `n_envs` lockstep copies of the initial state (marl_dpp_b200.batched); with
+n_envs = 1 it performs the reference's update sequence.  File arguments keep the reference's
+meaning: strings, '0' = none, files under ./src/data/qvalue_files/layout-3/.
+"""
+import numpy as np
+import torch
+
+from .. import formats
+from ..batched import BatchedEnv, BatchedQLearner
+from ..configuration import Configuration
+from ..tables import ACTIONS5, LEARN_DETECT, LEARN_FROZEN, LEARN_MODE0, Scenario
+
+
+class RL:
+    def __init__(self, input_dim=None, output_dim=None, cars=None, sess=None, env_config=None,
+                 learning_rate=0.0001, batch_size=32, n_envs=1, device=None, step_cap=10000, seed=3,
+                 bad_states=None, qvalue_dir=formats.QVALUE_DIR):
+        """input_dim / output_dim / cars / sess / learning_rate / batch_size are accepted and ignored,
+        exactly like the reference (qlearning.py:14-15).  Extra keywords: n_envs lockstep copies,
+        step_cap agent-steps per episode before a forced reset (the reference's train_given_state has
+        none and can spin forever at epsilon 0 -- SURVEY fact 5; 0 restores that), bad_states: None =
+        try the layout's file like the reference (env_gym.py:71-83), or the file's text."""
+        self.env_config = env_config if isinstance(env_config, Configuration) else Configuration(env_config)
+        self.alpha = 0.9
+        self.discount = 0.15
+        self.probability_model = 3
+        self.epsilon = 0
+        self.n_envs = int(n_envs)
+        self.device = device
+        self.step_cap = int(step_cap)
+        self.seed = int(seed)
+        self.qvalue_dir = qvalue_dir
+        self.training_complete_destination_index = self.env_config.training_complete_destination_index
+        if bad_states is None:
+            try:
+                with open(self.env_config.environment_bad_states_file, "r") as f:
+                    bad_states = f.read()
+            except OSError:
+                bad_states = None  # "as run" from the repo root: the file is not found
+        self.bad_states_text = bad_states
+        self.qvals = {}          # (state string, action char) -> float, the reference's Counter
+        self.last_stats = None
+        self.learner = None
+
+    # ---- Q values <-> files (reference :159-185) -------------------------------------------------
+    def load_qvalues(self, inputfile_number):
+        self.qvals = {}
+        if str(inputfile_number) == '0':
+            return None
+        for state, action, value in formats.read_qvalues(formats.qvalue_path(inputfile_number, self.qvalue_dir)):
+            self.qvals[(state, action)] = value
+
+    def save_qvalues(self, outputfile_number):
+        if str(outputfile_number) == '0':
+            return None
+        self._pull()
+        formats.write_qvalues(formats.qvalue_path(outputfile_number, self.qvalue_dir),
+                              [(s, a, v) for (s, a), v in self.qvals.items()])
+
+    def _push(self, learner):
+        """Loaded Counter -> dense device table (keys outside this scenario's state space are kept
+        on the host and written back unchanged)."""
+        sc = learner.env.scenario
+        q = torch.zeros((sc.n_states, 8), dtype=torch.float32)
+        vis = torch.zeros(sc.n_states, dtype=torch.int32)
+        self._foreign = {}
+        for (state, action), value in self.qvals.items():
+            try:
+                idx, a = sc.encode(state), ACTIONS5.index(action)
+            except ValueError:
+                self._foreign[(state, action)] = value
+                continue
+            q[idx, a] = value
+            vis[idx] |= 1 << a
+        learner.q.copy_(q)
+        learner.visited.copy_(vis)
+
+    def _pull(self):
+        if self.learner is None:
+            return
+        self.qvals = dict(getattr(self, "_foreign", {}))
+        for state, action, value in self.learner.qvalue_items():
+            self.qvals[(state, action)] = value
+
+    # ---- Counter-style accessors (reference :34-72) -----------------------------------------------
+    def getqvalue(self, state, action):
+        self._pull()
+        return self.qvals.get((state, action), 0.0)
+
+    def computeactionfromqvalues(self, state):
+        """First maximum over the legal actions in S,L,R,F,T order (reference :60-72, :659-667)."""
+        env = self.learner.env
+        sc = env.scenario
+        idx = sc.encode(state)
+        legal = int(env.query(0, [idx])["legal"][0])
+        if legal == 0:
+            return None
+        row = self.learner.q[idx].tolist()
+        best = None
+        for a in range(5):
+            if (legal >> a) & 1 and (best is None or row[a] > row[best]):
+                best = a
+        return ACTIONS5[best]
+
+    getpolicy = computeactionfromqvalues
+
+    # ---- training (reference :187-239) -----------------------------------------------------------
+    def _make(self, episodes, boxes, n, idx, choose, flags=0, model=None):
+        sc = Scenario(self.env_config.layout, list(boxes[:n]), list(idx[:n]), [list(c) for c in choose[:n]],
+                      bad_states_text=self.bad_states_text, step_cap=self.step_cap)
+        benv = BatchedEnv(sc, self.n_envs, device=self.device, seed=self.seed)
+        self.learner = BatchedQLearner(benv, episodes=episodes, alpha=self.alpha, discount=self.discount,
+                                       probability_model=self.probability_model if model is None else model,
+                                       seed=self.seed, flags=flags)
+        self._push(self.learner)
+        return self.learner
+
+    def _run(self, learner, episodes, on_episode=None, max_rounds=None):
+        """Rounds until every env used its episode budget.  Returns rounds run."""
+        chunk = 1 if self.n_envs == 1 else 64
+        rounds = 0
+        while True:
+            learner.train_rounds(chunk)
+            rounds += chunk
+            ep = learner.env.cars()["episode"]
+            lo = int(ep.min())
+            if on_episode is not None:
+                on_episode(lo)
+            if lo >= episodes or (max_rounds is not None and rounds >= max_rounds):
+                return rounds
+
+    def train_given_state(self, episodes, inputfile_number, outputfile_number, input_car_states=None, no_of_cars=1,
+                          destination_index_array=[0, 0, 0, 0], destination_choose_arrays=[0, 0, 0]):
+        self.load_qvalues(inputfile_number)
+        learner = self._make(episodes, input_car_states, no_of_cars, destination_index_array,
+                             destination_choose_arrays)
+        saved = []
+
+        def snapshot(min_episode):  # `if episode == 30: self.save_qvalues(outputfile_number)` (:194-195)
+            if not saved and min_episode >= 30:
+                saved.append(True)
+                self.save_qvalues(outputfile_number)
+        self._run(learner, episodes, on_episode=snapshot)
+        self.last_stats = learner.env.stats()
+        self.save_qvalues(outputfile_number)
+        self._pull()
+
+    # ---- deadlock detection (reference :297-382) -----------------------------------------------------
+    def detect_deadlocks_v0(self, episodes=40, inputfile_number=0, outputfile_number=0, input_car_states=None,
+                            no_of_cars=1, destination_index_array=[0, 0, 0, 0], destination_choose_arrays=[0, 0, 0],
+                            max_cars=6):
+        """Stall heuristic: Q-learning episodes with encodestate(., 0); in the epsilon = 0 episodes an
+        env whose greedy policy emits 3*n_cars consecutive 'S' flags that state.  Every flagged state
+        that is not already in the bad-states file is expanded and written (utils.py:159-199).
+        Returns like the reference: the last episode index, or False when a flagged state was
+        already known (the reference's `skip`)."""
+        self.env_config.no_of_cars = no_of_cars
+        self.load_qvalues(inputfile_number)
+        learner = self._make(episodes, input_car_states, no_of_cars, destination_index_array,
+                             destination_choose_arrays, flags=LEARN_MODE0 | LEARN_DETECT)
+        self._run(learner, episodes)
+        sc = learner.env.scenario
+        flagged = learner.env.deadlock_states().cpu().numpy()
+        states = sorted({sc.decode(int(i)) for i in np.unique(flagged[flagged >= 0])})
+        self.detected_deadlocks = states
+        known = set(formats.read_bad_states(self.env_config.environment_bad_states_file)) \
+            if self.bad_states_text is not None else set()
+        result = episodes - 1
+        for state in states:
+            if state in known:  # reference :350,357-366 compares the full string (with headings)
+                result = False
+                continue
+            if self.bad_states_text is not None:
+                formats.save_deadlock_state(state, self.env_config.station_box_list,
+                                            self.env_config.environment_bad_states_file,
+                                            state.count('z') + 1, max_cars)
+        self.save_qvalues(outputfile_number)
+        self._pull()
+        return result
+
+    # ---- validation (reference :384-437, minus the cv2 key-press UI) -----------------------------------
+    def validate_given_state(self, episodes, inputfile_number, outputfile_number, input_car_states=None, no_of_cars=1,
+                             destination_index_array=[0, 0, 0, 0], destination_choose_arrays=[0, 0, 0], waitkey=0,
+                             max_rounds=4096):
+        """Greedy (epsilon 0) rollout of the loaded table, no learning; cars move round-robin instead
+        of by key press.  Returns {"success": fraction of envs that finished, "rounds": ...}."""
+        self.load_qvalues(inputfile_number)
+        learner = self._make(max(int(episodes), 1), input_car_states, no_of_cars, destination_index_array,
+                             destination_choose_arrays, flags=LEARN_FROZEN, model=0)
+        rounds = self._run(learner, max(int(episodes), 1), max_rounds=max_rounds)
+        st = learner.env.stats()
+        finished = st["episodes_done"] - st["episodes_capped"]
+        return {"success": finished / float(self.n_envs * max(int(episodes), 1)), "rounds": rounds,
+                "agent_steps": st["agent_steps"], "capped": st["episodes_capped"]}

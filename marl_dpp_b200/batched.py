@@ -106,6 +106,36 @@ class BatchedEnv:
                                                   _ptr(out.get("status")), _ptr(out.get("done")), _stream()))
         return out
 
+    # -- string-API support ---------------------------------------------------------------------
+    def query(self, car, state_idx, actions=None, reward="q_reward"):
+        """Evaluate transitions from ARBITRARY state ids (entry i reads env i's cars for the clash
+        term only): legal mask of the state, successor id, reward, legal mask of the successor."""
+        dev = self.device
+        state_idx = torch.as_tensor(state_idx, dtype=torch.int32, device=dev).contiguous()
+        n = state_idx.numel()
+        if actions is not None:
+            actions = torch.as_tensor(actions, dtype=torch.uint8, device=dev).contiguous()
+        out = {"legal": torch.empty(n, dtype=torch.uint8, device=dev),
+               "next_state": torch.empty(n, dtype=torch.int32, device=dev),
+               "reward": torch.empty(n, dtype=torch.float32, device=dev),
+               "next_legal": torch.empty(n, dtype=torch.uint8, device=dev)}
+        with torch.cuda.device(dev):
+            _lib.check(self._L.mdpp_query_transitions(self._h, car, REWARD_KINDS[reward], _ptr(state_idx),
+                                                      _ptr(actions), n, _ptr(out["legal"]), _ptr(out["next_state"]),
+                                                      _ptr(out["reward"]), _ptr(out["next_legal"]), _stream()))
+        return out
+
+    def update_car(self, car, nodes):
+        """Bare update_car (reference src/env_gym.py:386-441): uint8 [n_envs] node ids, 255 = skip."""
+        nodes = torch.as_tensor(nodes, dtype=torch.uint8, device=self.device).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_update_car(self._h, car, _ptr(nodes), _stream()))
+
+    def deadlock_states(self):
+        """int32 [n_envs]: state id flagged by the stall heuristic, -1 = none."""
+        off = self._L.mdpp_deadlock_states(self._h) - self.workspace.data_ptr()
+        return self.workspace[off:off + 4 * self.n_envs].view(torch.int32)
+
     # -- random-policy rollout -------------------------------------------------------------------
     def rollout_random(self, rounds, first_round=0, reward="q_reward", outputs=None):
         """`rounds` round-robin rounds under the uniform-random legal policy with auto-reset.
@@ -151,10 +181,11 @@ class BatchedQLearner:
     sequential update, bit for bit in float32.
     """
 
-    def __init__(self, env, episodes=5000, alpha=0.9, discount=0.15, probability_model=3, seed=None, q=None):
+    def __init__(self, env, episodes=5000, alpha=0.9, discount=0.15, probability_model=3, seed=None, q=None,
+                 flags=0):
         self.env = env
         self.params = learner_params(episodes, alpha, discount, probability_model,
-                                     env.seed if seed is None else seed)
+                                     env.seed if seed is None else seed, flags)
         n_states = env.scenario.n_states
         self.q = q if q is not None else torch.zeros((n_states, 8), dtype=torch.float32, device=env.device)
         assert self.q.shape == (n_states, 8) and self.q.dtype == torch.float32 and self.q.is_contiguous()

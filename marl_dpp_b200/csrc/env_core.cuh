@@ -36,6 +36,9 @@ struct DevCfg {
     uint32_t car_ghost_code[MDPP_MAX_CARS]; // others-code of the finished car's ghost
     uint32_t car_ghost_box18[MDPP_MAX_CARS];
     uint32_t start_box18[MDPP_MAX_CARS], start_di[MDPP_MAX_CARS];
+    uint32_t dn_node[MDPP_MAX_DEST];  // destination-node index -> node id           (query kernel only:
+    uint32_t dn_dbox[MDPP_MAX_DEST];  // destination-node index -> destination-box   per-lane divergent
+    uint32_t dbox_sel[MDPP_MAX_DEST]; // destination-box index -> selective mask     constant reads)
     const uint32_t *tables;      // DEV: SmemTables image
     const uint32_t *bad_bitmap;  // DEV: n_box_states bits
 };

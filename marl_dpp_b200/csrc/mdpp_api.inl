@@ -27,7 +27,7 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct Carve {
-    size_t tables, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, total;
+    size_t tables, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, dl, total;
     uint32_t touched_capacity, replicas;
 };
 
@@ -59,6 +59,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
     c.stage = take((size_t)n_envs * 16);
+    c.dl = take((size_t)n_envs * 4);
     c.total = off;
     return c;
 }
@@ -130,6 +131,11 @@ static void make_devcfg(const mdpp_config &c, DevCfg &d) {
         d.start_box18[i] = c.start_box[i];
         d.start_di[i] = c.start_di[i];
     }
+    for (int i = 0; i < c.n_dest_nodes; i++) {
+        d.dn_node[i] = c.dest_node[i];
+        d.dn_dbox[i] = c.dest_node_box[i];
+    }
+    for (int i = 0; i < c.n_dest_boxes; i++) d.dbox_sel[i] = c.sel_mask[i];
 }
 
 extern "C" {
@@ -177,6 +183,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     for (int n = 0; n < MDPP_NODES; n++) img.nodeinfo[n] = (uint16_t)(cfg->fwd[n] | (cfg->base_legal[n] << 8));
     memcpy(img.bfs, cfg->bfs_len, sizeof img.bfs);
     cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->ws + cv.dl, 0xFF, (size_t)n_envs * 4, s); // no deadlock state yet
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.tables, &img, sizeof img, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && bad_bitmap_host)
         e = cudaMemcpyAsync(h->ws + cv.bad, bad_bitmap_host, (((size_t)cfg->n_box_states + 31) / 32) * 4,
@@ -199,6 +206,7 @@ int mdpp_destroy(mdpp_handle *h) {
 
 void *mdpp_env_records(mdpp_handle *h) { return h ? h->ws + h->cv.recs : nullptr; }
 void *mdpp_visited_bits(mdpp_handle *h) { return h ? h->ws + h->cv.visited : nullptr; }
+void *mdpp_deadlock_states(mdpp_handle *h) { return h ? h->ws + h->cv.dl : nullptr; }
 
 #define MDPP_DISPATCH_NC(h, KERNEL, grid, s, ...)                                               \
     switch ((h)->cfg.n_cars) {                                                                  \
@@ -220,6 +228,7 @@ int mdpp_reset(mdpp_handle *h, const uint8_t *env_mask, const uint8_t *headings,
     MDPP_DISPATCH_NC(h, reset_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
                      env_mask, headings, seed, zero_counters);
     MDPP_CUDA(cudaGetLastError());
+    if (zero_counters && !env_mask) MDPP_CUDA(cudaMemsetAsync(h->ws + h->cv.dl, 0xFF, (size_t)h->n_envs * 4, s));
     return MDPP_OK;
 }
 
@@ -300,7 +309,33 @@ int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slo
     if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
     cudaStream_t s = (cudaStream_t)stream;
     MDPP_DISPATCH_NC(h, q_substep_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
-                     car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward, control_of(h));
+                     car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward,
+                     (uint32_t *)(h->ws + h->cv.dl), control_of(h));
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_query_transitions(mdpp_handle *h, int car_slot, int reward_kind, const uint32_t *state_idx,
+                           const uint8_t *action, int64_t n, uint8_t *legal, uint32_t *next_idx, float *reward,
+                           uint8_t *next_legal, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!state_idx) return fail(MDPP_EINVAL, "state_idx is NULL");
+    if (n <= 0 || n > h->n_envs) return fail(MDPP_EINVAL, "n must be in 1..n_envs (entry i reads env i's cars)");
+    if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
+    if (reward_kind != MDPP_REWARD_Q && reward_kind != MDPP_REWARD_DQN) return fail(MDPP_EINVAL, "unknown reward kind");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, query_kernel, grid_for(n), s, h->dev, (const uint4 *)recs_of(h), n, car_slot, reward_kind,
+                     state_idx, action, legal, next_idx, reward, next_legal);
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_update_car(mdpp_handle *h, int car_slot, const uint8_t *nodes, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!nodes) return fail(MDPP_EINVAL, "nodes is NULL");
+    if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, update_car_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, car_slot, nodes);
     MDPP_CUDA(cudaGetLastError());
     return MDPP_OK;
 }

@@ -111,7 +111,7 @@ reset_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_
     r.x = (uint32_t)cars;
     r.y = (uint32_t)(cars >> 32);
     if (zero_counters) { r.z = 0; r.w = 0; }
-    else r.z &= 0xFFFFu; // new episode: steps_in_episode = 0, episode index kept
+    else { r.z &= 0xFFFFu; r.w &= ~0xFFu; } // new episode: steps and stall run = 0, episode index kept
     recs[e] = r;
 }
 
@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(kThreads)
 q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c,
                  uint64_t round, LearnArgs lp, const float *__restrict__ q, Accum ac,
                  const uint8_t *__restrict__ forced, uint8_t *__restrict__ action_out,
-                 uint32_t *__restrict__ state_out, float *__restrict__ reward_out, Control *ctl) {
+                 uint32_t *__restrict__ state_out, float *__restrict__ reward_out,
+                 uint32_t *__restrict__ dl_state, Control *ctl) {
     __shared__ SmemTables sm;
     __shared__ SmemStats ss;
     zero_stats(ss);
@@ -293,8 +294,10 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
         float r_out = 0.f;
         const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
+        // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
+        const int mode = (lp.flags & MDPP_LEARN_MODE0) ? 0 : 1;
         if (live && !f_done(car_field(cars, c))) {
-            View v = view_of<NC>(cars, c, 1, cfg);
+            View v = view_of<NC>(cars, c, mode, cfg);
             const uint32_t lm = legal_mask(v, v.pnode, sm);
             const uint32_t sidx = state_index(v, v.pnode, cfg);
             s_out = sidx;
@@ -307,6 +310,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 const float qs[5] = {q0.x, q0.y, q0.z, q0.w, q4};
                 uint32_t a;
                 bool explore;
+                const uint32_t eps16 = eps_q16_of(lp, (int32_t)episode);
                 if (f == MDPP_ACT_GREEDY) {
                     a = 0;
                     explore = false;
@@ -315,7 +319,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                     explore = true;
                 } else {
                     uint32_t w = decision_word(round, c, lp.seed, env);
-                    explore = (w >> 16) < eps_q16_of(lp, (int32_t)episode); // flipcoin (utils.py:255-265)
+                    explore = (w >> 16) < eps16; // flipcoin (utils.py:255-265)
                     a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
                 }
                 if (!explore) { // computeactionfromqvalues: first maximum in S,L,R,F,T order (:659-667)
@@ -328,6 +332,20 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                     }
                 }
                 acc.explore += explore;
+                // ---- stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360): 3*n_cars consecutive
+                // 'S' actions while epsilon == 0 flag the state; the env stops there (the reference returns)
+                bool stalled = false;
+                if (lp.flags & MDPP_LEARN_DETECT) {
+                    uint32_t run = rec.w & 0xFFu;
+                    run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
+                    stalled = run == 3u * NC;
+                    rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
+                    if (stalled) {
+                        dl_state[e] = sidx;
+                        episode = (uint32_t)lp.episodes; // frozen from now on
+                    }
+                }
+                if (!stalled) {
                 // ---- env step ----
                 const uint32_t nn = next_node(v.pnode, a, sm);
                 const int32_t ri = reward_int<NC>(v, nn, cars, c, MDPP_REWARD_Q, cfg, sm);
@@ -351,6 +369,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
                 const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
                 // ---- accumulate: mean over the envs that update this key in this sub-step ----
+                if (!(lp.flags & MDPP_LEARN_FROZEN)) {
                 const uint32_t key = sidx * MDPP_Q_ROW + a;
                 const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
                 const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
@@ -366,12 +385,14 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                         if (slot < ac.capacity) ac.touched[slot] = key;
                     }
                 }
+                }
                 cars = advance_car(cars, c, v, nn, cfg);
                 steps = steps < 0xFFFFu ? steps + 1 : steps;
                 acc.steps = 1;
                 rsum = ri;
-                a_out = a;
                 r_out = (float)ri;
+                }
+                a_out = a;
             }
         }
         if (live && c == NC - 1) { // end of the round-robin round (qlearning.py:233)
@@ -382,6 +403,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 acc.capped = capped;
                 episode = episode + 1;
                 steps = 0;
+                rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
                 cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
             }
         }
@@ -395,7 +417,103 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         if (state_out) state_out[e] = s_out;
         if (reward_out) reward_out[e] = r_out;
     }
-    flush_stats<true, true>(acc, rsum, ctl, ss);
+    if (lp.flags & MDPP_LEARN_FROZEN) flush_stats<true, false>(acc, rsum, ctl, ss);
+    else flush_stats<true, true>(acc, rsum, ctl, ss);
+}
+
+// ------------------------------------------------------------------------------------------------
+// string-API support (n_envs small): evaluate a transition from an ARBITRARY state id, and the bare
+// update_car.  The reference's getlegalactions / get_successor_state / reward_function take state
+// strings, not the env (src/env_gym.py:188-265,485-620); only the clash term reads the cars.
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ View view_from_state(uint32_t sidx, const DevCfg &cfg) {
+    View v;
+    const uint32_t nl = sidx % cfg.n_local_nodes, t = sidx / cfg.n_local_nodes;
+    v.dnidx = t % cfg.n_dest_nodes;
+    v.rank = t / cfg.n_dest_nodes;
+    v.pnode = nl + cfg.node_base;
+    v.di = 0;
+    v.dnode = cfg.dn_node[v.dnidx];
+    v.dbox = cfg.dn_dbox[v.dnidx];
+    v.sel = cfg.dbox_sel[v.dbox];
+    v.occ9 = 0;
+    v.occ18 = 0;
+    uint32_t rank = v.rank;
+    for (int j = NC - 1; j >= 1; j--) { // unrank the multiset of the others, largest code first
+        uint32_t d = (uint32_t)j - 1u;
+        auto binom = [](uint32_t n, int k) -> uint32_t {
+            if (n < (uint32_t)k) return 0u;
+            unsigned long long r = 1;
+            for (int i = 1; i <= k; i++) r = r * (n - (uint32_t)k + (uint32_t)i) / (uint32_t)i;
+            return (uint32_t)r;
+        };
+        while (binom(d + 1u, j) <= rank) d++;
+        rank -= binom(d, j);
+        const uint32_t code = d - (uint32_t)j + 1u;
+        if (code) {
+            const uint32_t box18 = (code - 1u) / cfg.n_dest_boxes + cfg.box_base;
+            v.occ9 |= 1u << boxnum0(box18);
+            v.occ18 |= 1u << box18;
+        }
+    }
+    return v;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+query_kernel(DevCfg cfg, const uint4 *__restrict__ recs, int64_t n, int c, int kind,
+             const uint32_t *__restrict__ state_idx, const uint8_t *__restrict__ action,
+             uint8_t *__restrict__ legal, uint32_t *__restrict__ next_idx, float *__restrict__ reward,
+             uint8_t *__restrict__ next_legal) {
+    __shared__ SmemTables sm;
+    load_tables(sm, cfg.tables);
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint32_t sidx = state_idx[e];
+    View v = view_from_state<NC>(sidx, cfg);
+    const uint32_t lm = legal_mask(v, v.pnode, sm);
+    if (legal) legal[e] = (uint8_t)lm;
+    const uint32_t a = action ? action[e] : (uint32_t)MDPP_ACT_SKIP;
+    uint32_t nidx = 0xFFFFFFFFu, lm2 = 0;
+    float rw = 0.f;
+    // like the reference, the successor of a move the base graph allows is defined even when the
+    // legal filter would reject it; a move off the graph has no successor
+    const bool exists = a < MDPP_N_ACT && (a != MDPP_A_F || (sm.nodeinfo[v.pnode] & 0xFFu) != kNone);
+    if (exists) {
+        const uint4 rec = recs[e];
+        const uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        const uint32_t nn = next_node(v.pnode, a, sm);
+        nidx = state_index(v, nn, cfg);
+        lm2 = legal_mask(v, nn, sm);
+        rw = reward_float(reward_int<NC>(v, nn, cars, c, kind, cfg, sm), kind);
+    }
+    if (next_idx) next_idx[e] = nidx;
+    if (reward) reward[e] = rw;
+    if (next_legal) next_legal[e] = (uint8_t)lm2;
+}
+
+// update_car (reference src/env_gym.py:386-441) on its own: place car c on `nodes[e]` and apply the
+// destination / done logic.  nodes[e] == MDPP_NONE leaves env e alone.
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+update_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, const uint8_t *__restrict__ nodes) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    const uint32_t node = nodes[e];
+    if (node >= MDPP_NODES) return;
+    uint4 rec = recs[e];
+    uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+    const uint32_t f = car_field(cars, c);
+    View v;
+    v.di = f_di(f);
+    v.dnode = cfg.car_dnode[c][v.di];
+    cars = set_car_field(cars, c, make_field(f_node(f), v.di, 0, f_ghost(f))); // advance_car rewrites the field
+    cars = advance_car(cars, c, v, node, cfg);
+    if (f_done(f)) cars = set_car_field(cars, c, car_field(cars, c) | (1u << 8)); // a finished car stays finished
+    rec.x = (uint32_t)cars;
+    rec.y = (uint32_t)(cars >> 32);
+    recs[e] = rec;
 }
 
 // finalize: per touched key write the mean of the accumulated values (the value itself when one

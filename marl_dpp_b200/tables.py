@@ -156,7 +156,7 @@ class MdppConfig(C.Structure):
 
 class MdppLearner(C.Structure):
     _fields_ = [("alpha", C.c_float), ("discount", C.c_float), ("episodes", C.c_int32),
-                ("eps_threshold", C.c_int32 * 5), ("eps_q16", C.c_uint32 * 6), ("seed", C.c_uint32)]
+                ("eps_threshold", C.c_int32 * 5), ("eps_q16", C.c_uint32 * 6), ("seed", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class MdppStats(C.Structure):
@@ -345,10 +345,13 @@ def epsilon_schedule(episodes, model=3):
     raise ValueError("unknown probability model %r" % (model,))
 
 
-def learner_params(episodes, alpha=0.9, discount=0.15, model=3, seed=3):
+LEARN_FROZEN, LEARN_MODE0, LEARN_DETECT = 1, 2, 4
+
+
+def learner_params(episodes, alpha=0.9, discount=0.15, model=3, seed=3, flags=0):
     th, eps = epsilon_schedule(episodes, model)
     lp = MdppLearner()
-    lp.alpha, lp.discount, lp.episodes, lp.seed = alpha, discount, episodes, seed
+    lp.alpha, lp.discount, lp.episodes, lp.seed, lp.flags = alpha, discount, episodes, seed, flags
     for i in range(5):
         lp.eps_threshold[i] = th[i]
     for i in range(6):

@@ -36,6 +36,8 @@ typedef struct {
     int32_t start_box[ORC_MAX_CARS], dest_index[ORC_MAX_CARS], choose[3 * ORC_MAX_CARS];
     orc_env **envs;
     int32_t *episode, *steps;
+    int32_t *stall;      /* consecutive greedy 'S' at epsilon 0 (detect_deadlocks_v0, qlearning.py:347-360) */
+    orc_state *dl_state; /* state flagged by the stall heuristic; pnode == ORC_NONE: none */
     /* stats */
     uint64_t agent_steps, episodes_done, episodes_capped, explore_steps;
     int64_t reward_sum;
@@ -64,6 +66,9 @@ orc_batch *orc_batch_create(const orc_cfg *cfg, int64_t n_envs, int n_cars, cons
     b->envs = (orc_env **)calloc((size_t)n_envs, sizeof(orc_env *));
     b->episode = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
     b->steps = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
+    b->stall = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
+    b->dl_state = (orc_state *)calloc((size_t)n_envs, sizeof(orc_state));
+    for (int64_t e = 0; e < n_envs; e++) b->dl_state[e].pnode = ORC_NONE;
     for (int64_t e = 0; e < n_envs; e++) {
         b->envs[e] = orc_env_create(cfg);
         orc_env_set_bad_states(b->envs[e], bad_text);
@@ -75,11 +80,14 @@ void orc_batch_destroy(orc_batch *b) {
     free(b->envs);
     free(b->episode);
     free(b->steps);
+    free(b->stall);
+    free(b->dl_state);
     free(b);
 }
 orc_env *orc_batch_env(orc_batch *b, int64_t e) { return b->envs[e]; }
 int32_t orc_batch_episode(const orc_batch *b, int64_t e) { return b->episode[e]; }
 int32_t orc_batch_steps(const orc_batch *b, int64_t e) { return b->steps[e]; }
+const orc_state *orc_batch_deadlock_state(const orc_batch *b, int64_t e) { return &b->dl_state[e]; }
 void orc_batch_stats(const orc_batch *b, uint64_t *out5) {
     out5[0] = b->agent_steps;
     out5[1] = b->episodes_done;
@@ -108,7 +116,11 @@ void orc_batch_reset(orc_batch *b, const uint8_t *headings, uint32_t seed, int z
             hb = philox_word(0, 3, seed, b->env_id_base + (uint32_t)e, 0);
         init_env(b, e, hb);
         b->steps[e] = 0;
-        if (zero_counters) b->episode[e] = 0;
+        b->stall[e] = 0;
+        if (zero_counters) {
+            b->episode[e] = 0;
+            b->dl_state[e].pnode = ORC_NONE;
+        }
     }
 }
 
@@ -131,6 +143,7 @@ static void end_of_round(orc_batch *b, int64_t e, uint64_t round, uint32_t seed,
         *capped += (uint64_t)cap;
         b->episode[e] += 1;
         b->steps[e] = 0;
+        b->stall[e] = 0; /* deadlock_count = 0 per episode, qlearning.py:331 */
         init_env(b, e, philox_word(round, 2, seed, b->env_id_base + (uint32_t)e, 0));
     }
 }
@@ -232,6 +245,7 @@ typedef struct {
     int32_t eps_threshold[5];
     uint32_t eps_q16[6];
     uint32_t seed;
+    uint32_t flags; /* 1 frozen (no update), 2 encodestate(.,0), 4 stall detection */
 } orc_learner;
 
 static uint32_t eps_q16_of(const orc_learner *lp, int32_t episode) {
@@ -264,7 +278,7 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
         st.pnode = ORC_NONE;
         int live = b->episode[e] < lp->episodes;
         if (live && !orc_env_car_done(env, c)) {
-            orc_env_encodestate(env, c, 1, &st);
+            orc_env_encodestate(env, c, (lp->flags & 2u) ? 0 : 1, &st);
             int lm = mask5(orc_env_legal(env, &st));
             int f = forced ? forced[e] : ACT_SKIP;
             int forced_ok = f >= ACT_GREEDY || (f < 5 && ((lm >> f) & 1));
@@ -291,6 +305,19 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
                     }
                 }
                 b->explore_steps += (uint64_t)explore;
+                int stalled = 0;
+                if (lp->flags & 4u) { /* qlearning.py:347-360 */
+                    if (a5 == 0 && eps_q16_of(lp, b->episode[e]) == 0) b->stall[e] += 1;
+                    else b->stall[e] = 0;
+                    if (b->stall[e] == 3 * nc) {
+                        stalled = 1;
+                        b->stall[e] = 0;
+                        b->dl_state[e] = st;
+                        b->episode[e] = lp->episodes;
+                    }
+                }
+                a_out = a5;
+                if (stalled) goto after_step;
                 orc_state ns;
                 orc_env_successor_state(env, &st, ACT5[a5], &ns);
                 double rw = orc_env_reward(env, &st, &ns, c, 0);
@@ -306,16 +333,19 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
                 float target = (float)rw + lp->discount * nv;
                 float diff = target - qa;
                 float newv = qa + lp->alpha * diff;
-                pend[e].key = orc_q_index(q, &st, ACT5[a5]);
-                pend[e].newv = newv;
+                if (!(lp->flags & 1u)) {
+                    pend[e].key = orc_q_index(q, &st, ACT5[a5]);
+                    pend[e].newv = newv;
+                }
                 orc_env_update_car(env, c, ns.pnode);
                 if (b->steps[e] < 0xFFFF) b->steps[e]++;
                 b->agent_steps++;
                 b->reward_sum += (int64_t)rw;
-                a_out = a5;
                 r_out = (float)rw;
+            after_step:;
             }
         }
+        live = b->episode[e] < lp->episodes || live;
         if (live && c == nc - 1) end_of_round(b, e, round, lp->seed, &b->episodes_done, &b->episodes_capped);
         if (action_out) action_out[e] = (uint8_t)a_out;
         if (state_out) state_out[e] = st;
