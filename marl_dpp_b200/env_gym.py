@@ -162,7 +162,9 @@ class Environment:
         if action is None:
             raise ValueError("%s is not a successor of %s" % (state, previous_state))
         r = float(self._benv.query(car_id, [sc.encode(previous_state)], [action], reward=kind)["reward"][0])
-        if kind == 'q_reward' and not (self.give_bad_state_reward and r == -10000.0):
+        if kind == 'dqn_reward':
+            return int(round(r * 100)) / 100  # the kernel returns float32; the reference `reward/100` in float64
+        if not (self.give_bad_state_reward and r == -10000.0):
             return int(r)
         return r
 

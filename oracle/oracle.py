@@ -296,13 +296,14 @@ def epsilon(episodes, episode, model=3):
 # ---- batched driver (oracle/mdpp_oracle_batch.c) -------------------------------------------------
 class Learner(C.Structure):
     _fields_ = [("alpha", C.c_float), ("discount", C.c_float), ("episodes", C.c_int32),
-                ("eps_threshold", C.c_int32 * 5), ("eps_q16", C.c_uint32 * 6), ("seed", C.c_uint32)]
+                ("eps_threshold", C.c_int32 * 5), ("eps_q16", C.c_uint32 * 6), ("seed", C.c_uint32),
+                ("flags", C.c_uint32)]
 
 
-def learner(episodes, alpha=0.9, discount=0.15, model=3, seed=3):
+def learner(episodes, alpha=0.9, discount=0.15, model=3, seed=3, flags=0):
     """Schedule derived from the oracle's own epsilon function (reference src/utils/utils.py:12-52)."""
     lp = Learner()
-    lp.alpha, lp.discount, lp.episodes, lp.seed = alpha, discount, episodes, seed
+    lp.alpha, lp.discount, lp.episodes, lp.seed, lp.flags = alpha, discount, episodes, seed, flags
     eps = [epsilon(episodes, e, model) for e in range(episodes)]
     values = [1.0, 0.8, 0.5, 0.3, 0.15, 0.0] if model == 3 else None
     if model != 3:
