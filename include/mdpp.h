@@ -185,6 +185,15 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp
 int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp_host,
                              uint64_t first_round, int rounds, mdpp_stats *stats_host, void *stream);
 
+/* ---- deadlock precompute (-dd): backward reachability bitmap over the joint state space -------------
+ * NEW definition next to the reference's stall heuristic: joint state = per car
+ * (node, destination_index) or FINISHED, index = sum_c v_c * V^c with v_c = node_local*2 + di and
+ * V-1 = finished, V = 2*n_local_nodes + 1.  Bit set = "all cars finished" is reachable when any
+ * unfinished car may take any action its legal filter (encodestate(., 0) view) allows.  Synchronous:
+ * sweeps until a fixpoint; *sweeps_out (host) receives the sweep count. */
+int64_t mdpp_joint_state_count(const mdpp_config *cfg);
+int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap /*DEV*/, int32_t *sweeps_out, void *stream);
+
 /* ---- state-id codec (for the qvalue .txt format, reference src/algorithms/qlearning.py:159-185) */
 /* decode: state id -> primary node, destination node, others as (src box18, dst box18) pairs in the
  * reference's ascend_array order; returns the number of others or a negative error */

@@ -131,6 +131,30 @@ class BatchedEnv:
         with torch.cuda.device(self.device):
             _lib.check(self._L.mdpp_update_car(self._h, car, _ptr(nodes), _stream()))
 
+    def deadlock_reachability(self):
+        """-dd precompute: bitmap (int32 words, bit j = joint state j can still reach "all cars
+        finished") over the joint state space, and the number of sweeps the fixpoint took.
+        Joint index = sum_c v_c * V^c, v_c = node_local*2 + destination_index, V-1 = finished."""
+        n = self._L.mdpp_joint_state_count(C.byref(self.scenario.cfg))
+        if n <= 0:
+            raise _lib.MdppError("joint state space too large: " + _lib.last_error())
+        bitmap = torch.empty((n + 31) // 32, dtype=torch.int32, device=self.device)
+        sweeps = C.c_int32()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_deadlock_reachability(self._h, _ptr(bitmap), C.byref(sweeps), _stream()))
+        return bitmap, int(sweeps.value)
+
+    def joint_index(self, cars):
+        """cars: [(node name or None for finished, destination_index)] -> joint state index."""
+        from .tables import node_id
+        sc = self.scenario
+        V = 2 * sc.n_local_nodes + 1
+        idx = 0
+        for c, (node, di) in enumerate(cars):
+            v = V - 1 if node is None else (node_id(node) - sc.node_base) * 2 + di
+            idx += v * V ** c
+        return idx
+
     def deadlock_states(self):
         """int32 [n_envs]: state id flagged by the stall heuristic, -1 = none."""
         off = self._L.mdpp_deadlock_states(self._h) - self.workspace.data_ptr()

@@ -340,6 +340,41 @@ int mdpp_update_car(mdpp_handle *h, int car_slot, const uint8_t *nodes, void *st
     return MDPP_OK;
 }
 
+int64_t mdpp_joint_state_count(const mdpp_config *cfg) {
+    if (validate_config(cfg)) return -1;
+    const uint64_t V = 2ull * (uint64_t)cfg->n_local_nodes + 1ull;
+    uint64_t n = 1;
+    for (int c = 0; c < cfg->n_cars; c++) {
+        if (n > ((uint64_t)1 << 40) / V) return -fail(MDPP_EINVAL, "joint state space too large");
+        n *= V;
+    }
+    return (int64_t)n;
+}
+
+int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *sweeps_out, void *stream) {
+    if (!h || !reach_bitmap) return fail(MDPP_EINVAL, "handle / bitmap is NULL");
+    const int64_t n = mdpp_joint_state_count(&h->cfg);
+    if (n <= 0) return MDPP_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t *changed = (uint32_t *)(h->ws + h->cv.stage); // scratch word in the staging area
+    const size_t words = ((size_t)n + 31) / 32;
+    MDPP_CUDA(cudaMemsetAsync(reach_bitmap, 0, words * 4, s));
+    int sweeps = 0;
+    for (;;) {
+        MDPP_CUDA(cudaMemsetAsync(changed, 0, 4, s));
+        MDPP_DISPATCH_NC(h, reach_sweep_kernel, grid_for(n), s, h->dev, reach_bitmap, (uint64_t)n, changed);
+        MDPP_CUDA(cudaGetLastError());
+        uint32_t flag = 0;
+        MDPP_CUDA(cudaMemcpyAsync(&flag, changed, 4, cudaMemcpyDeviceToHost, s));
+        MDPP_CUDA(cudaStreamSynchronize(s));
+        sweeps++;
+        if (!flag) break;
+        if (sweeps > 100000) return fail(MDPP_ECUDA, "reachability did not converge");
+    }
+    if (sweeps_out) *sweeps_out = sweeps;
+    return MDPP_OK;
+}
+
 int mdpp_q_finalize(mdpp_handle *h, float *q, void *stream) {
     if (!h) return fail(MDPP_EINVAL, "handle is NULL");
     if (!q) return fail(MDPP_EINVAL, "q is NULL");

@@ -561,6 +561,64 @@ q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// deadlock precompute: backward reachability of "all cars finished" over the JOINT state space.
+// This is a new definition (the reference's -dd is the stall heuristic above): a joint
+// state = per car (node, destination_index) or FINISHED; any unfinished car may take any action its
+// legal filter allows (encodestate(., 0) view: finished cars are not listed); a state is live iff the
+// all-finished state is reachable.  Joint index = sum_c v_c * V^c, v_c = node_local*2 + di, V-1 = finished.
+// One thread per joint state and sweep; sweeps repeat until no bit changes (monotone fixpoint, so the
+// in-place update order does not matter).
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t n_joint, uint32_t *__restrict__ changed) {
+    __shared__ SmemTables sm;
+    load_tables(sm, cfg.tables);
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_joint) return;
+    if ((reach[idx >> 5] >> (idx & 31u)) & 1u) return;
+    const uint32_t V = 2u * (uint32_t)cfg.n_local_nodes + 1u;
+    uint64_t cars = 0, rest = idx, pw[NC];
+    uint32_t digit[NC];
+    bool all_fin = true;
+    {
+        uint64_t p = 1;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            pw[c] = p;
+            p *= V;
+            digit[c] = (uint32_t)(rest % V);
+            rest /= V;
+            const bool fin = digit[c] == V - 1u;
+            all_fin = all_fin && fin;
+            const uint32_t f = fin ? make_field((uint32_t)cfg.parking_node, 0, 1, 7)
+                                   : make_field((digit[c] >> 1) + (uint32_t)cfg.node_base, digit[c] & 1u, 0, 5);
+            cars |= (uint64_t)f << (12 * c);
+        }
+    }
+    bool live = all_fin; // the goal itself
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        if (live || digit[c] == V - 1u) continue;
+        uint64_t tmp = cars;
+        const View v = view_of<NC>(tmp, c, 0, cfg);
+        const uint32_t lm = legal_mask(v, v.pnode, sm);
+        for (uint32_t a = 0; a < MDPP_N_ACT; a++) {
+            if (!((lm >> a) & 1u)) continue;
+            const uint32_t nn = next_node(v.pnode, a, sm);
+            const uint32_t f = car_field(advance_car(cars, c, v, nn, cfg), c);
+            const uint32_t nd = f_done(f) ? V - 1u : ((f_node(f) - (uint32_t)cfg.node_base) << 1) | f_di(f);
+            const uint64_t j = idx - (uint64_t)digit[c] * pw[c] + (uint64_t)nd * pw[c];
+            if ((*(volatile uint32_t *)(reach + (j >> 5)) >> (j & 31u)) & 1u) { live = true; break; }
+        }
+    }
+    if (live) {
+        atomicOr(reach + (idx >> 5), 1u << (idx & 31u));
+        *changed = 1u;
+    }
+}
+
 } // namespace mdpp
 
 #include "mdpp_api.inl"

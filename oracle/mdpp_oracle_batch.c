@@ -451,3 +451,75 @@ uint64_t orc_bench_run(orc_bench *o, int rounds) {
     for (int t = 0; t < T; t++) after += o->b[t]->agent_steps;
     return after - before;
 }
+
+/* ---- deadlock reachability: CPU brute force over the reference-pinned transition functions --------
+ * Same NEW definition as the CUDA bitmap (include/mdpp.h): joint state = per car (node, dest index)
+ * or FINISHED; any unfinished car may take any action of getlegalactions on its encodestate(., 0)
+ * state; live iff all-finished is reachable.  Joint index = sum_c v_c * V^c, v_c = node_local*2 + di,
+ * V - 1 = finished.  Forward successors are enumerated once through the scalar env functions, then a
+ * backward closure runs over the reverse adjacency.  Returns the number of live states. */
+int64_t orc_reachability(const orc_cfg *cfg, int n_cars, const int32_t *choose3, int n_local_nodes, int node_base,
+                         uint32_t *bitmap_out) {
+    const uint64_t V = 2ull * (uint64_t)n_local_nodes + 1ull;
+    uint64_t n = 1, pw[ORC_MAX_CARS];
+    for (int c = 0; c < n_cars; c++) { pw[c] = n; n *= V; }
+    const int maxs = n_cars * 5;
+    uint32_t *succ = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n * (size_t)maxs);
+    uint8_t *nsucc = (uint8_t *)calloc((size_t)n, 1);
+    orc_env *env = orc_env_create(cfg);
+    int32_t di0[ORC_MAX_CARS] = {0}, nodes0[ORC_MAX_CARS] = {0};
+    for (uint64_t idx = 0; idx < n; idx++) {
+        uint64_t rest = idx;
+        int digit[ORC_MAX_CARS];
+        orc_env_reset(env);
+        orc_env_initialize_cars(env, n_cars);
+        orc_env_initialize(env, di0, nodes0, choose3);
+        for (int c = 0; c < n_cars; c++) {
+            digit[c] = (int)(rest % V);
+            rest /= V;
+            if (digit[c] == (int)V - 1) orc_env_set_car(env, c, 0, 0, 1, -1); /* finished: never listed in mode 0 */
+            else orc_env_set_car(env, c, digit[c] / 2 + node_base, digit[c] & 1, 0, 5);
+        }
+        for (int c = 0; c < n_cars; c++) {
+            if (digit[c] == (int)V - 1) continue;
+            orc_state st, ns;
+            orc_env_encodestate(env, c, 0, &st);
+            int legal = orc_env_legal(env, &st);
+            for (int a = 0; a < ORC_ACT; a++) {
+                if (!((legal >> a) & 1)) continue;
+                orc_env_successor_state(env, &st, a, &ns);
+                orc_env_update_car(env, c, ns.pnode);
+                int nd = orc_env_car_done(env, c) ? (int)V - 1
+                                                  : (orc_env_car_node(env, c) - node_base) * 2 + orc_env_car_dest_index(env, c);
+                succ[idx * (uint64_t)maxs + nsucc[idx]++] = (uint32_t)(idx - (uint64_t)digit[c] * pw[c] + (uint64_t)nd * pw[c]);
+                orc_env_set_car(env, c, digit[c] / 2 + node_base, digit[c] & 1, 0, 5); /* undo */
+            }
+        }
+    }
+    orc_env_destroy(env);
+    /* reverse adjacency (CSR) + backward BFS from the all-finished state */
+    uint64_t *start = (uint64_t *)calloc((size_t)n + 2, sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++)
+        for (int k = 0; k < nsucc[i]; k++) start[succ[i * (uint64_t)maxs + k] + 2]++;
+    for (uint64_t i = 2; i < n + 2; i++) start[i] += start[i - 1];
+    uint32_t *pred = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(start[n + 1] + 1));
+    for (uint64_t i = 0; i < n; i++)
+        for (int k = 0; k < nsucc[i]; k++) pred[start[succ[i * (uint64_t)maxs + k] + 1]++] = (uint32_t)i;
+    uint8_t *live = (uint8_t *)calloc((size_t)n, 1);
+    uint32_t *queue = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+    uint64_t head = 0, tail = 0;
+    live[n - 1] = 1;
+    queue[tail++] = (uint32_t)(n - 1);
+    while (head < tail) {
+        uint32_t u = queue[head++];
+        for (uint64_t k = start[u]; k < start[u + 1]; k++) {
+            uint32_t p = pred[k];
+            if (!live[p]) { live[p] = 1; queue[tail++] = p; }
+        }
+    }
+    memset(bitmap_out, 0, (((size_t)n + 31) / 32) * 4);
+    for (uint64_t i = 0; i < n; i++)
+        if (live[i]) bitmap_out[i >> 5] |= 1u << (i & 31);
+    free(succ); free(nsucc); free(start); free(pred); free(live); free(queue);
+    return (int64_t)tail;
+}

@@ -456,3 +456,17 @@ class CpuBench:
         if self.h:
             _batch_lib().orc_bench_destroy(self.h)
             self.h = None
+
+
+def reachability(cfg, n_cars, choose, n_local_nodes=36, node_base=36):
+    """CPU brute-force deadlock reachability bitmap (numpy uint32 words) + number of live states."""
+    import numpy as np
+    L = _batch_lib()
+    L.orc_reachability.restype = C.c_int64
+    L.orc_reachability.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p]
+    V = 2 * n_local_nodes + 1
+    n = V ** n_cars
+    ch = (C.c_int32 * (3 * n_cars))(*[(list(c) + [0, 0, 0])[:3][k] for c in choose for k in range(3)])
+    out = np.zeros((n + 31) // 32, dtype=np.uint32)
+    live = L.orc_reachability(cfg.h, n_cars, ch, n_local_nodes, node_base, out.ctypes.data_as(C.c_void_p))
+    return out, int(live)
