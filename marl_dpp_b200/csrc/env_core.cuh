@@ -50,6 +50,33 @@ struct SmemTables {
 };
 constexpr int kTableWords = (sizeof(SmemTables) + 3) / 4;
 
+// Two ways to read the tables: a shared-memory copy (one load + barrier per CTA; right for kernels that
+// run many steps per launch) or straight from global memory through the read-only L1 path (720 bytes,
+// always L1-resident; no barrier, no per-CTA copy: right for the one-step-per-launch learner kernel).
+struct SharedTab {
+    const SmemTables *sm;
+    __device__ __forceinline__ uint32_t info(uint32_t node) const { return sm->nodeinfo[node]; }
+    __device__ __forceinline__ uint32_t bfs(uint32_t d, uint32_t node) const { return sm->bfs[d][node]; }
+};
+struct GlobalTab {
+    const SmemTables *g;
+    __device__ __forceinline__ uint32_t info(uint32_t node) const { return __ldg(&g->nodeinfo[node]); }
+    __device__ __forceinline__ uint32_t bfs(uint32_t d, uint32_t node) const { return __ldg(&g->bfs[d][node]); }
+};
+
+template <bool GT>
+struct AnyTab { // compile-time choice between the two
+    const SmemTables *p;
+    __device__ __forceinline__ uint32_t info(uint32_t node) const {
+        if constexpr (GT) return __ldg(&p->nodeinfo[node]);
+        else return p->nodeinfo[node];
+    }
+    __device__ __forceinline__ uint32_t bfs(uint32_t d, uint32_t node) const {
+        if constexpr (GT) return __ldg(&p->bfs[d][node]);
+        else return p->bfs[d][node];
+    }
+};
+
 __device__ __forceinline__ void load_tables(SmemTables &sm, const uint32_t *src) {
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sm);
     for (int i = threadIdx.x; i < kTableWords; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -208,9 +235,10 @@ __device__ __forceinline__ uint32_t state_index(const View &v, uint32_t node, co
 // `node`: 5-bit mask over S,L,R,F,T.  'B' never survives (:158-159).  S,L,R,T keep the car in its
 // own box, so they die together when a listed car shares the box NUMBER (:211-217, floor ignored);
 // F dies on the same test for the box ahead or on the selective-block rule (:143-186).
-__device__ __forceinline__ uint32_t legal_mask(const View &v, uint32_t node, const SmemTables &sm) {
+template <class Tab>
+__device__ __forceinline__ uint32_t legal_mask(const View &v, uint32_t node, const Tab &sm) {
     const uint32_t sel = v.sel;
-    uint32_t info = sm.nodeinfo[node];
+    uint32_t info = sm.info(node);
     uint32_t mask = info >> 8, fwd = info & 0xFFu;
     if ((v.occ9 >> boxnum0(node >> 2)) & 1u) mask &= 1u << MDPP_A_F;
     if (mask & (1u << MDPP_A_F)) {
@@ -224,24 +252,25 @@ __device__ __forceinline__ uint32_t legal_mask(const View &v, uint32_t node, con
 
 // get_successor_node (reference src/env_gym.py:132-141): L = heading-1, R = heading+1, T = heading-2
 // in N,E,S,W order (src/configuration.py:147-156,251-254); F from the table.
-__device__ __forceinline__ uint32_t next_node(uint32_t node, uint32_t a, const SmemTables &sm) {
+template <class Tab>
+__device__ __forceinline__ uint32_t next_node(uint32_t node, uint32_t a, const Tab &sm) {
     uint32_t rot = (0x20130u >> (4u * a)) & 3u;
     uint32_t turned = (node & ~3u) | ((node + rot) & 3u);
-    return a == MDPP_A_F ? (uint32_t)(sm.nodeinfo[node] & 0xFFu) : turned;
+    return a == MDPP_A_F ? (sm.info(node) & 0xFFu) : turned;
 }
 
 // q_reward / dqn_reward as an integer (dqn: before the /100).  `cars` = the records BEFORE
 // update_car, as in the reference where the reward is computed first (qlearning.py:223-229).
-template <int NC>
+template <int NC, class Tab>
 __device__ __forceinline__ int32_t reward_int(const View &v, uint32_t nnode, uint64_t cars, int c,
-                                              int kind, const DevCfg &cfg, const SmemTables &sm) {
+                                              int kind, const DevCfg &cfg, const Tab &sm) {
     if (kind == MDPP_REWARD_Q && cfg.bad_on) { // reference src/env_gym.py:568-577
         uint32_t base = (v.rank * cfg.n_dest_boxes + v.dbox) * cfg.n_src_boxes;
         uint32_t idn = base + ((nnode >> 2) - cfg.box_base), idp = base + ((v.pnode >> 2) - cfg.box_base);
         if ((__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u) return -10000;
         if ((__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u) return 0;
     }
-    int32_t prev_steps = sm.bfs[v.dnidx][v.pnode], cur_steps = sm.bfs[v.dnidx][nnode];
+    int32_t prev_steps = (int32_t)sm.bfs(v.dnidx, v.pnode), cur_steps = (int32_t)sm.bfs(v.dnidx, nnode);
     int32_t r = -10 + 50 * (prev_steps - cur_steps);                 // :603-605
     if (nnode == v.dnode) r += (kind == MDPP_REWARD_DQN) ? 110 : 10010; // :606-607 / :536-537
     int32_t clash = 0;
@@ -269,6 +298,20 @@ __device__ __forceinline__ uint64_t advance_car(uint64_t cars, int c, const View
         di ^= 1u;
     }
     return set_car_field(cars, c, make_field(node, di, done, f_ghost(f)));
+}
+
+// Programmatic dependent launch (sm_90+): no-ops unless the kernel was launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// One Q row = 8 floats = one 32-byte sector: a single 256-bit read-only load (LDG.E.256, sm_100+)
+// instead of a 128-bit + a 32-bit request -- the learner kernel is bound by L1 wavefronts, and every
+// lane of a warp gathers a different row.
+__device__ __forceinline__ void ldg_row(const float *p, float (&r)[MDPP_Q_ROW]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(p));
 }
 
 // n-th (0-based) set bit of a 5-bit mask

@@ -75,6 +75,9 @@ struct mdpp_handle {
     char *ws;
     int sm_count;
     uint32_t parity;        // sub-step parity of the touched-key counters
+    int q_ctas_per_sm;      // co-resident CTAs of the persistent learner kernel (occupancy query)
+    bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
+    bool q_global_tables;   // learner kernel variant (MDPP_QTAB=0 selects the shared-memory one)
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
 };
 
@@ -172,6 +175,8 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->env_id_base = (uint32_t)env_id_base;
     h->ws = (char *)workspace;
     make_devcfg(*cfg, h->dev);
+    h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
+    h->q_global_tables = !(getenv("MDPP_QTAB") && atoi(getenv("MDPP_QTAB")) == 0);
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
     h->dev.bad_bitmap = (const uint32_t *)(h->ws + cv.bad);
     int devid = 0;
@@ -298,6 +303,10 @@ static Accum accum_of(mdpp_handle *h) {
     a.capacity = h->cv.touched_capacity;
     a.replica_mask = h->cv.replicas - 1;
     a.parity = h->parity;
+    a.n_keys = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW);
+    // scanning keys x replicas is cheaper than keeping a touched list up to ~4M accumulator slots
+    a.dense = ((size_t)a.n_keys * h->cv.replicas <= ((size_t)4 << 20)) ? 1u : 0u;
+    if (const char *env = getenv("MDPP_DENSE")) a.dense = atoi(env) ? 1u : 0u;
     a.replica_stride = (size_t)h->cfg.n_states * MDPP_Q_ROW;
     return a;
 }
@@ -308,9 +317,50 @@ int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slo
     if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
     if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
     cudaStream_t s = (cudaStream_t)stream;
-    MDPP_DISPATCH_NC(h, q_substep_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
-                     car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward,
-                     (uint32_t *)(h->ws + h->cv.dl), control_of(h));
+    // GT variant: persistent grid (8 CTAs of 256 threads per SM), tables through L1, no barriers
+    const bool gt = h->q_global_tables;
+    if (gt && h->q_ctas_per_sm == 0) { // persistent grid = exactly the CTAs that are co-resident
+        int occ = 0;
+        cudaError_t oe = cudaSuccess;
+        switch (h->cfg.n_cars) {
+        case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<1, true>, kThreads, 0); break;
+        case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<2, true>, kThreads, 0); break;
+        case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<3, true>, kThreads, 0); break;
+        case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<4, true>, kThreads, 0); break;
+        default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<5, true>, kThreads, 0); break;
+        }
+        h->q_ctas_per_sm = (oe == cudaSuccess && occ > 0) ? occ : 4;
+        if (const char *env = getenv("MDPP_QGRID")) { int g = atoi(env); if (g > 0) h->q_ctas_per_sm = g; }
+    }
+    const unsigned grid = gt ? (unsigned)std::min<int64_t>(grid_for(h->n_envs), (int64_t)h->sm_count * h->q_ctas_per_sm)
+                             : grid_for(h->n_envs);
+    // Programmatic dependent launch: the kernel's Q-independent prologue (record load, encode, legal
+    // mask, Philox) may overlap the tail of the preceding finalize; it waits (griddepcontrol.wait)
+    // before its first Q read.  MDPP_PDL=0 falls back to plain stream order.
+    cudaLaunchAttribute pdl_attr;
+    pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.stream = s;
+    lc.attrs = &pdl_attr;
+    lc.numAttrs = 1;
+#define MDPP_QSUB(NCV)                                                                                         \
+    if (gt) MDPP_CUDA(cudaLaunchKernelEx(&lc, q_substep_kernel<NCV, true>, h->dev, recs_of(h), h->n_envs,       \
+            h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), forced, action_out, state_idx, \
+            reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                           \
+    else q_substep_kernel<NCV, false><<<grid, kThreads, 0, s>>>(h->dev, recs_of(h), h->n_envs, h->env_id_base,  \
+            car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward,                       \
+            (uint32_t *)(h->ws + h->cv.dl), control_of(h));
+    switch (h->cfg.n_cars) {
+    case 1: MDPP_QSUB(1) break;
+    case 2: MDPP_QSUB(2) break;
+    case 3: MDPP_QSUB(3) break;
+    case 4: MDPP_QSUB(4) break;
+    default: MDPP_QSUB(5) break;
+    }
+#undef MDPP_QSUB
     MDPP_CUDA(cudaGetLastError());
     return MDPP_OK;
 }
@@ -378,9 +428,20 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *
 int mdpp_q_finalize(mdpp_handle *h, float *q, void *stream) {
     if (!h) return fail(MDPP_EINVAL, "handle is NULL");
     if (!q) return fail(MDPP_EINVAL, "q is NULL");
-    unsigned grid = (unsigned)std::min<int64_t>(((int64_t)h->cv.touched_capacity * 32 + kThreads - 1) / kThreads,
-                                                (int64_t)h->sm_count * 4);
-    q_finalize_kernel<<<std::max(grid, 1u), kThreads, 0, (cudaStream_t)stream>>>(q, accum_of(h), control_of(h));
+    const Accum acf = accum_of(h);
+    unsigned grid = acf.dense ? (unsigned)std::min<int64_t>((acf.n_keys + kThreads - 1) / kThreads, (int64_t)h->sm_count * 4)
+                              : (unsigned)std::min<int64_t>(((int64_t)h->cv.touched_capacity * 32 + kThreads - 1) / kThreads,
+                                                            (int64_t)h->sm_count * 4);
+    cudaLaunchAttribute pdl_attr;
+    pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(std::max(grid, 1u));
+    lc.blockDim = dim3(kThreads);
+    lc.stream = (cudaStream_t)stream;
+    lc.attrs = &pdl_attr;
+    lc.numAttrs = 1;
+    MDPP_CUDA(cudaLaunchKernelEx(&lc, q_finalize_kernel, q, accum_of(h), control_of(h)));
     MDPP_CUDA(cudaGetLastError());
     h->parity ^= 1u;
     return MDPP_OK;

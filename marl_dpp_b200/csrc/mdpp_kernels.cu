@@ -84,6 +84,27 @@ __device__ __forceinline__ void flush_stats(const StatAcc &a, int64_t reward64, 
     }
 }
 
+// Barrier-free variant for one-step-per-thread kernels: one REDUX per warp, lane 0 adds straight to the
+// privatised global slot of its warp (3 atomics per warp spread over kStatSlots sectors).
+template <bool kQ>
+__device__ __forceinline__ void flush_stats_warp(const StatAcc &a, int64_t reward64, Control *ctl) {
+    uint32_t packed = a.steps | (a.explore << 8) | (a.episodes << 16) | (a.capped << 24);
+    packed = __reduce_add_sync(0xFFFFFFFFu, packed);
+    const int rs = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(int)reward64);
+    if ((threadIdx.x & 31u) == 0 && packed) {
+        const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        mdpp_stats *slot = &ctl->stats[w & (kStatSlots - 1)];
+        const unsigned long long steps = packed & 0xFFu, explore = (packed >> 8) & 0xFFu;
+        const unsigned long long episodes = (packed >> 16) & 0xFFu, capped = packed >> 24;
+        if (steps) atomicAdd((unsigned long long *)&slot->agent_steps, steps);
+        if (kQ && steps) atomicAdd((unsigned long long *)&slot->q_updates, steps);
+        if (explore) atomicAdd((unsigned long long *)&slot->explore_steps, explore);
+        if (episodes) atomicAdd((unsigned long long *)&slot->episodes_done, episodes);
+        if (capped) atomicAdd((unsigned long long *)&slot->episodes_capped, capped);
+        if (rs) atomicAdd((unsigned long long *)&slot->reward_sum, (unsigned long long)(long long)rs);
+    }
+}
+
 __device__ __forceinline__ void zero_stats(SmemStats &ss) {
     if (threadIdx.x == 0) ss = SmemStats{0ull, 0ull, 0u, 0u, 0u, 0u};
 }
@@ -128,6 +149,7 @@ step_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, int
     __shared__ SmemStats ss;
     zero_stats(ss);
     load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StatAcc acc;
     int64_t rsum = 0;
@@ -141,14 +163,14 @@ step_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, int
             st = 1; // reference: `if env.check_car_training(num): continue` (qlearning.py:216-217)
         } else {
             View v = view_of<NC>(cars, c, mode, cfg);
-            lm = legal_mask(v, v.pnode, sm);
+            lm = legal_mask(v, v.pnode, tab);
             sidx = state_index(v, v.pnode, cfg);
             if (a >= MDPP_N_ACT || !((lm >> a) & 1u)) {
                 st = 2;
             } else {
-                uint32_t nn = next_node(v.pnode, a, sm);
+                uint32_t nn = next_node(v.pnode, a, tab);
                 nidx = state_index(v, nn, cfg);
-                int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, sm);
+                int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, tab);
                 rw = reward_float(ri, kind);
                 cars = advance_car(cars, c, v, nn, cfg);
                 uint32_t steps = rec.z >> 16;
@@ -184,6 +206,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
     __shared__ SmemStats ss;
     zero_stats(ss);
     load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StatAcc acc;
     int64_t rsum = 0;
@@ -201,15 +224,15 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
                 float rw = 0.f;
                 if (!f_done(car_field(cars, c))) {
                     View v = view_of<NC>(cars, c, 1, cfg);
-                    uint32_t lm = legal_mask(v, v.pnode, sm);
+                    uint32_t lm = legal_mask(v, v.pnode, tab);
                     if (lm) {
                         uint32_t w = c == 0 ? p.x : c == 1 ? p.y : c == 2 ? p.z : c == 3 ? p.w
                                      : philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
                         // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
                         a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
-                        uint32_t nn = next_node(v.pnode, a, sm);
+                        uint32_t nn = next_node(v.pnode, a, tab);
                         nidx = state_index(v, nn, cfg);
-                        int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, sm);
+                        int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, tab);
                         rw = reward_float(ri, kind);
                         cars = advance_car(cars, c, v, nn, cfg);
                         steps = steps < 0xFFFFu ? steps + 1 : steps;
@@ -260,6 +283,8 @@ struct Accum {
     // spread over up to 64 L2 addresses instead of serialising every env of the batch on one
     uint32_t replica_mask;
     uint32_t parity;       // which touched_count the current sub-step uses
+    uint32_t dense;        // small table: finalize scans every key, no touched list is kept
+    uint32_t n_keys;
     size_t replica_stride; // in keys
 };
 
@@ -272,7 +297,9 @@ __device__ __forceinline__ uint32_t eps_q16_of(const LearnArgs &lp, int32_t epis
     return e;
 }
 
-template <int NC>
+// GT = tables read from global memory through L1 (no shared copy, no barrier, per-warp stats flush) and
+// a grid-stride loop over env tiles; GT = false keeps the shared-memory variant for comparison.
+template <int NC, bool GT>
 __global__ void __launch_bounds__(kThreads)
 q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c,
                  uint64_t round, LearnArgs lp, const float *__restrict__ q, Accum ac,
@@ -281,9 +308,17 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                  uint32_t *__restrict__ dl_state, Control *ctl) {
     __shared__ SmemTables sm;
     __shared__ SmemStats ss;
-    zero_stats(ss);
-    load_tables(sm, cfg.tables);
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (!GT) {
+        zero_stats(ss);
+        load_tables(sm, cfg.tables);
+    }
+    const AnyTab<GT> tab{GT ? reinterpret_cast<const SmemTables *>(cfg.tables) : &sm};
+    // PDL: let the finalize that follows be scheduled as soon as SM slots free up (it waits for this
+    // grid to complete before touching the accumulators)
+    pdl_launch_dependents();
+    // whole warps iterate together (n_envs is padded to the warp by the bound check inside)
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_envs; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = base + threadIdx.x;
     StatAcc acc;
     int64_t rsum = 0;
     if (e < n_envs) {
@@ -298,16 +333,18 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         const int mode = (lp.flags & MDPP_LEARN_MODE0) ? 0 : 1;
         if (live && !f_done(car_field(cars, c))) {
             View v = view_of<NC>(cars, c, mode, cfg);
-            const uint32_t lm = legal_mask(v, v.pnode, sm);
+            const uint32_t lm = legal_mask(v, v.pnode, tab);
             const uint32_t sidx = state_index(v, v.pnode, cfg);
             s_out = sidx;
             uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
             const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
             if (lm && forced_ok) {
                 // ---- getaction (reference src/algorithms/qlearning.py:74-105) ----
-                const float4 q0 = __ldg(reinterpret_cast<const float4 *>(q + (size_t)sidx * MDPP_Q_ROW));
-                const float q4 = __ldg(q + (size_t)sidx * MDPP_Q_ROW + 4);
-                const float qs[5] = {q0.x, q0.y, q0.z, q0.w, q4};
+                // everything above (record, encode, legal mask) is independent of the Q table and may
+                // have overlapped the preceding finalize; from here on its writes must be visible
+                pdl_wait();
+                float qs[MDPP_Q_ROW];
+                ldg_row(q + (size_t)sidx * MDPP_Q_ROW, qs); // one 256-bit load = the whole 32-byte row
                 uint32_t a;
                 bool explore;
                 const uint32_t eps16 = eps_q16_of(lp, (int32_t)episode);
@@ -347,14 +384,13 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 }
                 if (!stalled) {
                 // ---- env step ----
-                const uint32_t nn = next_node(v.pnode, a, sm);
-                const int32_t ri = reward_int<NC>(v, nn, cars, c, MDPP_REWARD_Q, cfg, sm);
+                const uint32_t nn = next_node(v.pnode, a, tab);
+                const int32_t ri = reward_int<NC>(v, nn, cars, c, MDPP_REWARD_Q, cfg, tab);
                 // ---- update (qlearning.py:107-116): value of the successor STATE STRING, same others ----
                 const uint32_t nidx = state_index(v, nn, cfg);
-                const uint32_t lm2 = legal_mask(v, nn, sm);
-                const float4 n0 = __ldg(reinterpret_cast<const float4 *>(q + (size_t)nidx * MDPP_Q_ROW));
-                const float n4 = __ldg(q + (size_t)nidx * MDPP_Q_ROW + 4);
-                const float ns[5] = {n0.x, n0.y, n0.z, n0.w, n4};
+                const uint32_t lm2 = legal_mask(v, nn, tab);
+                float ns[MDPP_Q_ROW];
+                ldg_row(q + (size_t)nidx * MDPP_Q_ROW, ns);
                 float nv = 0.f;
                 bool have = false;
 #pragma unroll
@@ -374,15 +410,16 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
                 const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
                 atomicAdd((unsigned long long *)(ac.sum + rkey), (unsigned long long)fx);
-                atomicAdd(ac.cnt + rkey, 1u);
-                const uint32_t bit = 1u << (key & 31u);
-                uint32_t seen = *(volatile uint32_t *)(ac.touched_bits + (key >> 5));
-                if (!(seen & bit)) {
-                    ac.last[key] = newv; // only matters if this env stays the key's single contributor
-                    uint32_t old = atomicOr(ac.touched_bits + (key >> 5), bit);
-                    if (!(old & bit)) {
-                        uint32_t slot = atomicAdd(&ctl->touched_count[ac.parity], 1u);
-                        if (slot < ac.capacity) ac.touched[slot] = key;
+                // the count comes back: the first contributor of a (replica, key) leaves the value itself
+                // (exact result when it stays alone) and, for tables too big to scan, lists the key
+                if (atomicAdd(ac.cnt + rkey, 1u) == 0u) {
+                    ac.last[key] = newv;
+                    if (!ac.dense) {
+                        const uint32_t bit = 1u << (key & 31u);
+                        if (!(atomicOr(ac.touched_bits + (key >> 5), bit) & bit)) {
+                            uint32_t slot = atomicAdd(&ctl->touched_count[ac.parity], 1u);
+                            if (slot < ac.capacity) ac.touched[slot] = key;
+                        }
                     }
                 }
                 }
@@ -417,8 +454,14 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         if (state_out) state_out[e] = s_out;
         if (reward_out) reward_out[e] = r_out;
     }
-    if (lp.flags & MDPP_LEARN_FROZEN) flush_stats<true, false>(acc, rsum, ctl, ss);
-    else flush_stats<true, true>(acc, rsum, ctl, ss);
+    if constexpr (GT) {
+        if (lp.flags & MDPP_LEARN_FROZEN) flush_stats_warp<false>(acc, rsum, ctl);
+        else flush_stats_warp<true>(acc, rsum, ctl);
+    } else {
+        if (lp.flags & MDPP_LEARN_FROZEN) flush_stats<true, false>(acc, rsum, ctl, ss);
+        else flush_stats<true, true>(acc, rsum, ctl, ss);
+    }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,25 +511,26 @@ query_kernel(DevCfg cfg, const uint4 *__restrict__ recs, int64_t n, int c, int k
              uint8_t *__restrict__ next_legal) {
     __shared__ SmemTables sm;
     load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const uint32_t sidx = state_idx[e];
     View v = view_from_state<NC>(sidx, cfg);
-    const uint32_t lm = legal_mask(v, v.pnode, sm);
+    const uint32_t lm = legal_mask(v, v.pnode, tab);
     if (legal) legal[e] = (uint8_t)lm;
     const uint32_t a = action ? action[e] : (uint32_t)MDPP_ACT_SKIP;
     uint32_t nidx = 0xFFFFFFFFu, lm2 = 0;
     float rw = 0.f;
     // like the reference, the successor of a move the base graph allows is defined even when the
     // legal filter would reject it; a move off the graph has no successor
-    const bool exists = a < MDPP_N_ACT && (a != MDPP_A_F || (sm.nodeinfo[v.pnode] & 0xFFu) != kNone);
+    const bool exists = a < MDPP_N_ACT && (a != MDPP_A_F || (tab.info(v.pnode) & 0xFFu) != kNone);
     if (exists) {
         const uint4 rec = recs[e];
         const uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-        const uint32_t nn = next_node(v.pnode, a, sm);
+        const uint32_t nn = next_node(v.pnode, a, tab);
         nidx = state_index(v, nn, cfg);
-        lm2 = legal_mask(v, nn, sm);
-        rw = reward_float(reward_int<NC>(v, nn, cars, c, kind, cfg, sm), kind);
+        lm2 = legal_mask(v, nn, tab);
+        rw = reward_float(reward_int<NC>(v, nn, cars, c, kind, cfg, tab), kind);
     }
     if (next_idx) next_idx[e] = nidx;
     if (reward) reward[e] = rw;
@@ -518,8 +562,59 @@ update_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, c
 
 // finalize: per touched key write the mean of the accumulated values (the value itself when one
 // env contributed), clear the accumulators, record the visited bit used by the qvalue file writer.
+__device__ __forceinline__ void finalize_key(float *__restrict__ q, const Accum &ac, uint32_t key, long long s,
+                                             uint32_t cnt) {
+    float v;
+    if (cnt == 1u) {
+        v = ac.last[key];
+    } else {
+        const double mean = (double)s / ((double)cnt * (double)(1 << MDPP_FIXED_SHIFT));
+        v = (float)mean;
+    }
+    q[key] = v;
+    uint32_t *vis = ac.visited + (key >> 3);
+    const uint32_t vb = 1u << (key & 7u);
+    if (!(*vis & vb)) atomicOr(vis, vb);
+}
+
 __global__ void __launch_bounds__(kThreads)
 q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
+    pdl_wait();              // the sub-step that filled the accumulators has completed
+    pdl_launch_dependents(); // the next sub-step may start its Q-independent prologue now
+    if (ac.dense) {
+        // small table: one thread per key, coalesced sweep over the replicas
+        uint32_t touched = 0;
+        for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < ac.n_keys; key += gridDim.x * blockDim.x) {
+            if ((key & 7u) >= MDPP_N_ACT) continue;
+            long long s = 0;
+            uint32_t cnt = 0;
+            for (uint32_t r0 = 0; r0 <= ac.replica_mask; r0 += 8u) { // 8 independent count loads in flight
+                uint32_t c[8];
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; j++)
+                    c[j] = (r0 + j <= ac.replica_mask) ? ac.cnt[(size_t)(r0 + j) * ac.replica_stride + key] : 0u;
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; j++) {
+                    if (c[j]) {
+                        const size_t rkey = (size_t)(r0 + j) * ac.replica_stride + key;
+                        cnt += c[j];
+                        s += ac.sum[rkey];
+                        ac.cnt[rkey] = 0;
+                        ac.sum[rkey] = 0;
+                    }
+                }
+            }
+            if (cnt) {
+                finalize_key(q, ac, key, s, cnt);
+                touched++;
+            }
+        }
+        touched = __reduce_add_sync(0xFFFFFFFFu, touched);
+        if ((threadIdx.x & 31u) == 0 && touched)
+            atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
+                      (unsigned long long)touched);
+        return;
+    }
     const uint32_t n = min(ctl->touched_count[ac.parity], ac.capacity);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -541,18 +636,8 @@ q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
         if (lane == 0) {
-            float v;
-            if (cnt == 1u) {
-                v = ac.last[key];
-            } else {
-                const double mean = (double)s / ((double)cnt * (double)(1 << MDPP_FIXED_SHIFT));
-                v = (float)mean;
-            }
-            q[key] = v;
+            finalize_key(q, ac, key, s, cnt);
             ac.touched_bits[key >> 5] = 0; // every set bit of the word belongs to a key finalised in this launch
-            uint32_t *vis = ac.visited + (key >> 3);
-            const uint32_t vb = 1u << (key & 7u);
-            if (!(*vis & vb)) atomicOr(vis, vb);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -575,6 +660,7 @@ __global__ void __launch_bounds__(kThreads)
 reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t n_joint, uint32_t *__restrict__ changed) {
     __shared__ SmemTables sm;
     load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_joint) return;
     if ((reach[idx >> 5] >> (idx & 31u)) & 1u) return;
@@ -603,10 +689,10 @@ reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t n_joint, u
         if (live || digit[c] == V - 1u) continue;
         uint64_t tmp = cars;
         const View v = view_of<NC>(tmp, c, 0, cfg);
-        const uint32_t lm = legal_mask(v, v.pnode, sm);
+        const uint32_t lm = legal_mask(v, v.pnode, tab);
         for (uint32_t a = 0; a < MDPP_N_ACT; a++) {
             if (!((lm >> a) & 1u)) continue;
-            const uint32_t nn = next_node(v.pnode, a, sm);
+            const uint32_t nn = next_node(v.pnode, a, tab);
             const uint32_t f = car_field(advance_car(cars, c, v, nn, cfg), c);
             const uint32_t nd = f_done(f) ? V - 1u : ((f_node(f) - (uint32_t)cfg.node_base) << 1) | f_di(f);
             const uint64_t j = idx - (uint64_t)digit[c] * pw[c] + (uint64_t)nd * pw[c];
