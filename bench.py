@@ -132,7 +132,7 @@ def run_reference_arm(args, rank, world):
     from oracle import oracle as orc
     import marl_dpp_b200 as m
     threads = os.cpu_count() or 1
-    envs_per_thread, rounds_per_step = 2048, 10
+    envs_per_thread, rounds_per_step = 512, 4   # bounded sample: the whole K-step run ends within minutes
     boxes, idx, choose = m.layout_3[BLOCK]["initial_states"][0]
     lp = orc.learner(EPISODES, seed=3)
     b = orc.CpuBench(orc.Config(m.layout_3[BLOCK]), threads, envs_per_thread, boxes, idx, choose, bad_text(),
@@ -161,8 +161,8 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--sync-interval", type=int, default=16, help="rounds between Q-replica all-reduces (N>1)")
@@ -250,15 +250,18 @@ def main():
 
     # ---- e2e: the public host-facing call, one round per call, counters read back every step ----
     barrier()
-    e2e_steps0 = env.stats(reset=True)
-    t0 = time.perf_counter()
+    env.stats(reset=True)
+    e2e_dt = 0.0
     for i in range(args.steps):
         flush.zero_()
+        torch.cuda.synchronize()           # the L2 flush is outside the timed window
+        t0 = time.perf_counter()
         lr.train_rounds_host(1)  # learner params from host memory in, mdpp_stats back, stream synchronised
         if world > 1 and args.sync_interval > 0 and (i + 1) % args.sync_interval == 0:
             lr.sync_replicas()
+            torch.cuda.synchronize()
+        e2e_dt += time.perf_counter() - t0
     barrier()
-    e2e_dt = time.perf_counter() - t0
     st2 = env.stats(reset=True)
     t2 = torch.tensor([e2e_dt, float(st2["agent_steps"])], dtype=torch.float64, device=dev)
     if world > 1:
@@ -353,6 +356,29 @@ def main():
         aux["gym_step_host_buffers"] = {"value": s["agent_steps"] / dt, "unit": UNIT,
                                         "h2d_bytes_per_call": n, "d2h_bytes_per_call": 15 * n}
         del env2
+        # config 3 point: random-policy sweep, max agents (4 cars), 2^24 envs, outputs materialised
+        b4, i4 = ["D2", "D6", "D4", "D8"], [0, 0, 0, 0]
+        c4 = [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]]
+        sc4 = m.Scenario(m.layout_3[BLOCK], b4, i4, c4, bad_states_text=bad_text(), step_cap=STEP_CAP)
+        n4 = 1 << 24
+        env4 = BatchedEnv(sc4, n4, device=dev, seed=5)
+        outs4 = env4.alloc_rollout_outputs(1)
+        for w in range(3):
+            env4.rollout_random(1, w, outputs=outs4)
+        torch.cuda.synchronize()
+        env4.stats(reset=True)
+        a.record()
+        for w in range(10):
+            env4.rollout_random(1, 3 + w, outputs=outs4)
+        b.record()
+        torch.cuda.synchronize()
+        s = env4.stats(reset=True)
+        ms = a.elapsed_time(b)
+        aux["random_rollout_4car_16Mi_envs_outputs"] = {
+            "value": s["agent_steps"] / (ms * 1e-3), "unit": UNIT, "rounds_per_launch": 1,
+            "algorithmic_GBps": (10.0 + 16.0 / 4) * s["agent_steps"] / (ms * 1e-3) / 1e9,
+            "note": "records (256 MiB) + outputs (640 MiB) exceed L2: HBM-streaming regime"}
+        del env4, outs4
 
     if rank == 0:
         line = {
@@ -369,7 +395,7 @@ def main():
             "q_updates_per_s": total_upd / (dev_ms * 1e-3),
             "wall_s_timed_region": wall,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(lr.params),
-                    "d2h_bytes_per_step": 64,
+                    "d2h_bytes_per_step": 64 * 128,
                     "call": "BatchedQLearner.train_rounds_host(1) -> mdpp_q_train_rounds_host (sync each step)"},
             "gpu_launches": args.steps * k * 2,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "aux": aux,

@@ -323,11 +323,11 @@ int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slo
         int occ = 0;
         cudaError_t oe = cudaSuccess;
         switch (h->cfg.n_cars) {
-        case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<1, true>, kThreads, 0); break;
-        case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<2, true>, kThreads, 0); break;
-        case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<3, true>, kThreads, 0); break;
-        case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<4, true>, kThreads, 0); break;
-        default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<5, true>, kThreads, 0); break;
+        case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<1, true, true>, kThreads, 0); break;
+        case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<2, true, true>, kThreads, 0); break;
+        case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<3, true, true>, kThreads, 0); break;
+        case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<4, true, true>, kThreads, 0); break;
+        default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<5, true, true>, kThreads, 0); break;
         }
         h->q_ctas_per_sm = (oe == cudaSuccess && occ > 0) ? occ : 4;
         if (const char *env = getenv("MDPP_QGRID")) { int g = atoi(env); if (g > 0) h->q_ctas_per_sm = g; }
@@ -346,11 +346,15 @@ int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slo
     lc.stream = s;
     lc.attrs = &pdl_attr;
     lc.numAttrs = 1;
+    const bool plain = !forced && !action_out && !state_idx && !reward && lp->flags == 0;
 #define MDPP_QSUB(NCV)                                                                                         \
-    if (gt) MDPP_CUDA(cudaLaunchKernelEx(&lc, q_substep_kernel<NCV, true>, h->dev, recs_of(h), h->n_envs,       \
-            h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), forced, action_out, state_idx, \
-            reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                           \
-    else q_substep_kernel<NCV, false><<<grid, kThreads, 0, s>>>(h->dev, recs_of(h), h->n_envs, h->env_id_base,  \
+    if (gt && plain) MDPP_CUDA(cudaLaunchKernelEx(&lc, q_substep_kernel<NCV, true, true>, h->dev, recs_of(h),    \
+            h->n_envs, h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), forced, action_out, \
+            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                \
+    else if (gt) MDPP_CUDA(cudaLaunchKernelEx(&lc, q_substep_kernel<NCV, true, false>, h->dev, recs_of(h),      \
+            h->n_envs, h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), forced, action_out, \
+            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                \
+    else q_substep_kernel<NCV, false, false><<<grid, kThreads, 0, s>>>(h->dev, recs_of(h), h->n_envs, h->env_id_base,  \
             car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward,                       \
             (uint32_t *)(h->ws + h->cv.dl), control_of(h));
     switch (h->cfg.n_cars) {

@@ -299,7 +299,9 @@ __device__ __forceinline__ uint32_t eps_q16_of(const LearnArgs &lp, int32_t epis
 
 // GT = tables read from global memory through L1 (no shared copy, no barrier, per-warp stats flush) and
 // a grid-stride loop over env tiles; GT = false keeps the shared-memory variant for comparison.
-template <int NC, bool GT>
+// PLAIN = the training fast path: no forced actions, no per-env outputs, no learner flags -- those
+// branches fold away at compile time.
+template <int NC, bool GT, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
 q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c,
                  uint64_t round, LearnArgs lp, const float *__restrict__ q, Accum ac,
@@ -312,6 +314,8 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         zero_stats(ss);
         load_tables(sm, cfg.tables);
     }
+    const uint32_t lflags = PLAIN ? 0u : lp.flags;
+    if constexpr (PLAIN) { forced = nullptr; action_out = nullptr; state_out = nullptr; reward_out = nullptr; }
     const AnyTab<GT> tab{GT ? reinterpret_cast<const SmemTables *>(cfg.tables) : &sm};
     // PDL: let the finalize that follows be scheduled as soon as SM slots free up (it waits for this
     // grid to complete before touching the accumulators)
@@ -330,7 +334,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         float r_out = 0.f;
         const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
         // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
-        const int mode = (lp.flags & MDPP_LEARN_MODE0) ? 0 : 1;
+        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : 1;
         if (live && !f_done(car_field(cars, c))) {
             View v = view_of<NC>(cars, c, mode, cfg);
             const uint32_t lm = legal_mask(v, v.pnode, tab);
@@ -372,7 +376,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 // ---- stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360): 3*n_cars consecutive
                 // 'S' actions while epsilon == 0 flag the state; the env stops there (the reference returns)
                 bool stalled = false;
-                if (lp.flags & MDPP_LEARN_DETECT) {
+                if (lflags & MDPP_LEARN_DETECT) {
                     uint32_t run = rec.w & 0xFFu;
                     run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
                     stalled = run == 3u * NC;
@@ -405,7 +409,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
                 const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
                 const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
                 // ---- accumulate: mean over the envs that update this key in this sub-step ----
-                if (!(lp.flags & MDPP_LEARN_FROZEN)) {
+                if (!(lflags & MDPP_LEARN_FROZEN)) {
                 const uint32_t key = sidx * MDPP_Q_ROW + a;
                 const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
                 const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
@@ -455,10 +459,10 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         if (reward_out) reward_out[e] = r_out;
     }
     if constexpr (GT) {
-        if (lp.flags & MDPP_LEARN_FROZEN) flush_stats_warp<false>(acc, rsum, ctl);
+        if (lflags & MDPP_LEARN_FROZEN) flush_stats_warp<false>(acc, rsum, ctl);
         else flush_stats_warp<true>(acc, rsum, ctl);
     } else {
-        if (lp.flags & MDPP_LEARN_FROZEN) flush_stats<true, false>(acc, rsum, ctl, ss);
+        if (lflags & MDPP_LEARN_FROZEN) flush_stats<true, false>(acc, rsum, ctl, ss);
         else flush_stats<true, true>(acc, rsum, ctl, ss);
     }
     }
