@@ -185,6 +185,21 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp
 int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp_host,
                              uint64_t first_round, int rounds, mdpp_stats *stats_host, void *stream);
 
+/* ---- DQN feed: the env-facing half of the noisy double DQN's collection loop (reference
+ * src/algorithms/dqn_open_source.py:490-526); the MLP stays in PyTorch.  observe = encodestate(car, 1)
+ * (ghost side effect included) -> RL.convert(state) as 80 {0,1} bytes per env (:245-313) + give_mask
+ * (:200-209) + state id.  act = env.step(state, action, car) on the observed state -> convert(next_state),
+ * reward, give_mask(next_state), env-done flag, status as in mdpp_step_car; with auto_reset the last car
+ * slot starts the next episode (Philox headings, key (seed, env id), counter (round, 2)).
+ * features / next_features: [n_envs][80] u8, 16-byte aligned; rows of envs that did not move are zero. */
+#define MDPP_DQN_FEATURES 80
+int mdpp_dqn_observe(mdpp_handle *h, int car_slot, uint8_t *features /*DEV*/, uint8_t *legal /*DEV*/,
+                     uint32_t *state_idx /*DEV*/, void *stream);
+int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *actions /*DEV*/,
+                 uint8_t *next_features /*DEV*/, float *reward /*DEV*/, uint8_t *next_legal /*DEV*/,
+                 uint8_t *done /*DEV*/, uint8_t *status /*DEV*/, int auto_reset, uint64_t round, uint32_t seed,
+                 void *stream);
+
 /* ---- deadlock precompute (-dd): backward reachability bitmap over the joint state space -------------
  * NEW definition next to the reference's stall heuristic: joint state = per car
  * (node, destination_index) or FINISHED, index = sum_c v_c * V^c with v_c = node_local*2 + di and

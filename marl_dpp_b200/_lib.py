@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # every symbol include/mdpp.h declares (tests check that the built library exports all of them)
 EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_error_string", "mdpp_abi_version",
            "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_query_transitions",
-           "mdpp_update_car", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
+           "mdpp_update_car", "mdpp_dqn_observe", "mdpp_dqn_act", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
            "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
            "mdpp_q_train_rounds_host", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
 
@@ -63,6 +63,8 @@ def lib():
         "mdpp_deadlock_states": (P, [P]),
         "mdpp_query_transitions": (I, [P, I, I, U32, U8, I64, U8, U32, F32, U8, P]),
         "mdpp_update_car": (I, [P, I, U8, P]),
+        "mdpp_dqn_observe": (I, [P, I, U8, U8, U32, P]),
+        "mdpp_dqn_act": (I, [P, I, I, U8, U8, F32, U8, U8, U8, I, U64, C.c_uint32, P]),
         "mdpp_joint_state_count": (I64, [P]),
         "mdpp_deadlock_reachability": (I, [P, U32, C.POINTER(C.c_int32), P]),
         "mdpp_reset": (I, [P, U8, U8, C.c_uint32, I, P]),

@@ -160,6 +160,37 @@ class BatchedEnv:
         off = self._L.mdpp_deadlock_states(self._h) - self.workspace.data_ptr()
         return self.workspace[off:off + 4 * self.n_envs].view(torch.int32)
 
+    # -- DQN feed ---------------------------------------------------------------------------------
+    def dqn_observe(self, car, features=None, legal=None, state=None):
+        """encodestate(car, 1) for every env -> (features uint8 [n_envs, 80] = RL.convert(state),
+        legal uint8 [n_envs] = give_mask as a bit mask, state id int32 [n_envs]).  Preallocated
+        outputs (e.g. slices of a replay ring) may be passed in."""
+        n, dev = self.n_envs, self.device
+        features = torch.empty((n, 80), dtype=torch.uint8, device=dev) if features is None else features
+        legal = torch.empty(n, dtype=torch.uint8, device=dev) if legal is None else legal
+        state = torch.empty(n, dtype=torch.int32, device=dev) if state is None else state
+        with torch.cuda.device(dev):
+            _lib.check(self._L.mdpp_dqn_observe(self._h, car, _ptr(features), _ptr(legal), _ptr(state), _stream()))
+        return features, legal, state
+
+    def dqn_act(self, car, actions, reward="dqn_reward", next_features=None, out=None, auto_reset=False, round=0):
+        """env.step(state, action, car) on the observed state -> dict(next_features, reward, next_legal,
+        done, status)."""
+        n, dev = self.n_envs, self.device
+        actions = actions.to(dev, torch.uint8).contiguous()
+        o = out or {}
+        o.setdefault("next_features", torch.empty((n, 80), dtype=torch.uint8, device=dev)
+                     if next_features is None else next_features)
+        o.setdefault("reward", torch.empty(n, dtype=torch.float32, device=dev))
+        o.setdefault("next_legal", torch.empty(n, dtype=torch.uint8, device=dev))
+        o.setdefault("done", torch.empty(n, dtype=torch.uint8, device=dev))
+        o.setdefault("status", torch.empty(n, dtype=torch.uint8, device=dev))
+        with torch.cuda.device(dev):
+            _lib.check(self._L.mdpp_dqn_act(self._h, car, REWARD_KINDS[reward], _ptr(actions), _ptr(o["next_features"]),
+                                            _ptr(o["reward"]), _ptr(o["next_legal"]), _ptr(o["done"]),
+                                            _ptr(o["status"]), int(auto_reset), int(round), self.seed, _stream()))
+        return o
+
     # -- random-policy rollout -------------------------------------------------------------------
     def rollout_random(self, rounds, first_round=0, reward="q_reward", outputs=None):
         """`rounds` round-robin rounds under the uniform-random legal policy with auto-reset.

@@ -199,6 +199,11 @@ __device__ __forceinline__ View view_of(uint64_t &cars, int c, int mode, const D
                     }
                     cars = set_car_field(cars, i, (f & 0x1FFu) | (g << 9));
                 }
+            } else if (mode == 2 && f_ghost(f) != 7u) {
+                // the view a previous encodestate(., 1) of this agent-step produced: no second decrement
+                listed = true;
+                code = cfg.car_ghost_code[i];
+                box18 = cfg.car_ghost_box18[i];
             }
         } else {
             listed = true;

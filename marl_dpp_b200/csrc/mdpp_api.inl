@@ -394,6 +394,33 @@ int mdpp_update_car(mdpp_handle *h, int car_slot, const uint8_t *nodes, void *st
     return MDPP_OK;
 }
 
+int mdpp_dqn_observe(mdpp_handle *h, int car_slot, uint8_t *features, uint8_t *legal, uint32_t *state_idx, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
+    if (features && ((uintptr_t)features & 15)) return fail(MDPP_EINVAL, "features must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, dqn_observe_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, car_slot, features,
+                     legal, state_idx);
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
+int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *actions, uint8_t *next_features,
+                 float *reward, uint8_t *next_legal, uint8_t *done, uint8_t *status, int auto_reset, uint64_t round,
+                 uint32_t seed, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!actions) return fail(MDPP_EINVAL, "actions is NULL");
+    if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
+    if (reward_kind != MDPP_REWARD_Q && reward_kind != MDPP_REWARD_DQN) return fail(MDPP_EINVAL, "unknown reward kind");
+    if (next_features && ((uintptr_t)next_features & 15)) return fail(MDPP_EINVAL, "next_features must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, dqn_act_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base, car_slot,
+                     reward_kind, actions, next_features, reward, next_legal, done, status, auto_reset, round, seed,
+                     control_of(h));
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+
 int64_t mdpp_joint_state_count(const mdpp_config *cfg) {
     if (validate_config(cfg)) return -1;
     const uint64_t V = 2ull * (uint64_t)cfg->n_local_nodes + 1ull;

@@ -651,6 +651,223 @@ q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// DQN feed: the env-facing half of the noisy double DQN's collection loop
+// (reference src/algorithms/dqn_open_source.py:490-526): encodestate -> convert(state) + give_mask for
+// the network, then env.step(state, action) -> (convert(next_state), dqn_reward, mask(next_state)).
+// The MLP itself stays in PyTorch.  Features are RL.convert's 80 {0,1} bytes (:245-313).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFeat = 16 * MDPP_MAX_CARS; // 80
+
+// 8 bytes of one car entry: box NUMBER as 5 bits MSB first, then 3 heading bits (N,W,E,S = 0..3, 7 = none)
+__device__ __forceinline__ unsigned long long feat_entry(uint32_t number, uint32_t dir) {
+    const uint32_t v = (number << 3) | dir;          // b7..b0 = n4 n3 n2 n1 n0 d2 d1 d0
+    const uint32_t vr = __brev(v) >> 24;             // byte i of the entry = bit (7 - i) of v
+    unsigned long long x = ((unsigned long long)vr * 0x0101010101010101ull) & 0x8040201008040201ull;
+    return ((x + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+}
+
+// Others in the reference's string order (ascend_array, src/env_gym.py:267-279): box number, then the
+// source / destination strings ('D' < 'U').  keys[i] = sortable key | (src box18 << 20) | (dst box18 << 25).
+template <int NC>
+__device__ __forceinline__ void listed_others(uint64_t cars, int c, int mode, const DevCfg &cfg, uint32_t (&keys)[NC]) {
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        const uint32_t f = car_field(cars, i);
+        uint32_t sb = 0, db = 0;
+        bool listed = false;
+        if (i != c) {
+            if (f_done(f)) {
+                if (mode != 0 && f_ghost(f) != 7u) { // counters already advanced by the observe kernel
+                    listed = true;
+                    sb = db = cfg.car_ghost_box18[i];
+                }
+            } else {
+                listed = true;
+                sb = f_node(f) >> 2;
+                db = cfg.car_dbox18[i][f_di(f)];
+            }
+        }
+        const uint32_t order = (boxnum0(sb) << 8) | ((sb < 9u) << 7) | ((db < 9u) << 6) | (boxnum0(db) << 2);
+        keys[i] = listed ? ((order << 0) & 0xFFFFFu) | (sb << 20) | (db << 25) : 0xFFFFFFFFu;
+    }
+    // the low 20 bits order the entries; box ids ride along in the high bits -> sort on a rotated key
+#pragma unroll
+    for (int i = 0; i < NC; i++)
+        if (keys[i] != 0xFFFFFFFFu) keys[i] = (keys[i] << 12) | (keys[i] >> 20);
+    if constexpr (NC > 1) sort_codes<NC>(keys);
+}
+
+// writes the 80 feature bytes of (primary node, destination node, others) to dst (16-byte aligned)
+template <int NC>
+__device__ __forceinline__ void write_features(uint4 *dst, uint32_t pnode, uint32_t dnode, const uint32_t (&keys)[NC]) {
+    const uint32_t dirmap = 0x1320u; // our N,E,S,W (0..3) -> the reference's N=0 W=1 E=2 S=3, one nibble each
+    unsigned long long src[MDPP_MAX_CARS], dstv[MDPP_MAX_CARS];
+    src[0] = feat_entry(boxnum0(pnode >> 2) + 1u, (dirmap >> (4u * (pnode & 3u))) & 7u);
+    dstv[0] = feat_entry(boxnum0(dnode >> 2) + 1u, (dirmap >> (4u * (dnode & 3u))) & 7u);
+#pragma unroll
+    for (int i = 1; i < MDPP_MAX_CARS; i++) {
+        src[i] = 0x0101010101010101ull; // missing cars: all ones (:303)
+        dstv[i] = 0x0101010101010101ull;
+        if (i - 1 < NC) {
+            const uint32_t k = keys[i - 1];
+            if (k != 0xFFFFFFFFu) {
+                const uint32_t sb = k & 31u, db = (k >> 5) & 31u; // after the rotation: bits 0-4 src, 5-9 dst
+                src[i] = feat_entry(boxnum0(sb) + 1u, 7u);
+                dstv[i] = feat_entry(boxnum0(db) + 1u, 7u);
+            }
+        }
+    }
+    unsigned long long all[10] = {src[0], src[1], src[2], src[3], src[4], dstv[0], dstv[1], dstv[2], dstv[3], dstv[4]};
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+        dst[j] = make_uint4((uint32_t)all[2 * j], (uint32_t)(all[2 * j] >> 32), (uint32_t)all[2 * j + 1],
+                            (uint32_t)(all[2 * j + 1] >> 32));
+}
+
+// Stage a warp's 32 x 80 feature bytes in shared memory and write them out as 5 fully coalesced
+// 512-byte rows (a lane's own 80 bytes are 80 apart from its neighbour's: direct stores would touch
+// 32 different sectors per instruction).
+template <int NC>
+__device__ __forceinline__ void store_features_coalesced(uint8_t *__restrict__ out, int64_t warp_first_env, int64_t n_envs,
+                                                         uint4 *stage, bool valid, uint32_t pnode, uint32_t dnode,
+                                                         const uint32_t (&keys)[NC]) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint4 *mine = stage + lane * 5; // 80 bytes per lane
+    if (valid) write_features<NC>(mine, pnode, dnode, keys);
+    else {
+#pragma unroll
+        for (int j = 0; j < 5; j++) mine[j] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    uint4 *gout = reinterpret_cast<uint4 *>(out + warp_first_env * kFeat);
+    const int64_t remaining = n_envs - warp_first_env;
+    const uint32_t n16 = (uint32_t)((remaining >= 32 ? 32 : remaining) * 5);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint32_t i = j * 32u + lane;
+        if (i < n16) gout[i] = stage[i];
+    }
+    __syncwarp();
+}
+
+// observe: encodestate(car, 1) with its ghost side effect -> convert(state), give_mask(state), state id
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+dqn_observe_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, uint8_t *__restrict__ features,
+                   uint8_t *__restrict__ legal, uint32_t *__restrict__ state_idx) {
+    __shared__ SmemTables sm;
+    __shared__ uint4 stage[kThreads * 5];
+    load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t warp_first = e - (threadIdx.x & 31);
+    uint32_t keys[NC], pnode = 0, dnode = 0, lm = 0, sidx = 0xFFFFFFFFu;
+    bool valid = false;
+    if (e < n_envs) {
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        if (!f_done(car_field(cars, c))) {
+            const View v = view_of<NC>(cars, c, 1, cfg);
+            lm = legal_mask(v, v.pnode, tab);
+            sidx = state_index(v, v.pnode, cfg);
+            listed_others<NC>(cars, c, 2, cfg, keys);
+            pnode = v.pnode;
+            dnode = v.dnode;
+            valid = true;
+            rec.x = (uint32_t)cars;
+            rec.y = (uint32_t)(cars >> 32);
+            recs[e] = rec;
+        }
+        if (legal) legal[e] = (uint8_t)lm;
+        if (state_idx) state_idx[e] = sidx;
+    }
+    if (!valid) {
+#pragma unroll
+        for (int i = 0; i < NC; i++) keys[i] = 0xFFFFFFFFu;
+    }
+    if (warp_first < n_envs && features)
+        store_features_coalesced<NC>(features, warp_first, n_envs, stage + (threadIdx.x & ~31) * 5, valid, pnode, dnode, keys);
+}
+
+// act: env.step(state, action, num) for the state the observe kernel produced (ghost counters are NOT
+// advanced again) -> convert(next_state), reward, give_mask(next_state), env-done flag; optional
+// end-of-round auto-reset with Philox headings when c is the last slot.
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+dqn_act_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c, int kind,
+               const uint8_t *__restrict__ actions, uint8_t *__restrict__ next_features, float *__restrict__ reward,
+               uint8_t *__restrict__ next_legal, uint8_t *__restrict__ done_out, uint8_t *__restrict__ status,
+               int auto_reset, uint64_t round, uint32_t seed, Control *ctl) {
+    __shared__ SmemTables sm;
+    __shared__ SmemStats ss;
+    __shared__ uint4 stage[kThreads * 5];
+    zero_stats(ss);
+    load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t warp_first = e - (threadIdx.x & 31);
+    uint32_t keys[NC], pnode = 0, dnode = 0;
+    bool valid = false;
+    StatAcc acc;
+    int64_t rsum = 0;
+    if (e < n_envs) {
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        uint32_t st = 1, lm2 = 0;
+        float rw = 0.f;
+        const uint32_t a = actions[e];
+        if (!f_done(car_field(cars, c)) && a != MDPP_ACT_SKIP) {
+            uint64_t tmp = cars;
+            const View v = view_of<NC>(tmp, c, 2, cfg); // mode 2: counters as the observe kernel left them
+            const uint32_t lm = legal_mask(v, v.pnode, tab);
+            st = 2;
+            if (a < MDPP_N_ACT && ((lm >> a) & 1u)) {
+                st = 0;
+                const uint32_t nn = next_node(v.pnode, a, tab);
+                const int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, tab);
+                rw = reward_float(ri, kind);
+                lm2 = legal_mask(v, nn, tab);
+                listed_others<NC>(cars, c, 2, cfg, keys);
+                pnode = nn;
+                dnode = v.dnode;
+                valid = true;
+                cars = advance_car(cars, c, v, nn, cfg);
+                steps = steps < 0xFFFFu ? steps + 1 : steps;
+                acc.steps = 1;
+                rsum = ri;
+            }
+        }
+        const bool finished = all_done<NC>(cars);
+        if (done_out) done_out[e] = (uint8_t)finished;
+        if (auto_reset && c == NC - 1) {
+            const bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                acc.episodes = 1;
+                acc.capped = capped;
+                episode = (episode + 1) & 0xFFFFu;
+                steps = 0;
+                cars = initial_cars<NC>(cfg, heading_word(round, 2, seed, env_id_base + (uint32_t)e));
+            }
+        }
+        rec.x = (uint32_t)cars;
+        rec.y = (uint32_t)(cars >> 32);
+        rec.z = episode | (steps << 16);
+        recs[e] = rec;
+        if (reward) reward[e] = rw;
+        if (next_legal) next_legal[e] = (uint8_t)lm2;
+        if (status) status[e] = (uint8_t)st;
+    }
+    if (!valid) {
+#pragma unroll
+        for (int i = 0; i < NC; i++) keys[i] = 0xFFFFFFFFu;
+    }
+    if (warp_first < n_envs && next_features)
+        store_features_coalesced<NC>(next_features, warp_first, n_envs, stage + (threadIdx.x & ~31) * 5, valid, pnode, dnode, keys);
+    flush_stats<true, false>(acc, rsum, ctl, ss);
+}
+
+// ------------------------------------------------------------------------------------------------
 // deadlock precompute: backward reachability of "all cars finished" over the JOINT state space.
 // This is a new definition (the reference's -dd is the stall heuristic above): a joint
 // state = per car (node, destination_index) or FINISHED; any unfinished car may take any action its

@@ -244,6 +244,38 @@ def gen_known_answers(ref):
     dump("known_answers", out)
 
 
+def gen_convert(ref):
+    """RL.convert (the 80-bit DQN featurizer) and give_mask of the noisy double DQN
+    (reference src/algorithms/dqn_open_source.py:200-209,245-313), called unbound on recorded states."""
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        import src.algorithms.dqn_open_source as D
+    out = {}
+    for name in ("traj_b2_4car_bad", "traj_b2_5car", "traj_b0_3car_bad", "traj_b2_2car_dqn_step", "traj_b0_1car"):
+        with gzip.open(os.path.join(OUT, name + ".json.gz")) as f:
+            g = json.load(f)
+        states = []
+        for ep in g["episodes"]:
+            for st in ep["steps"]:
+                for s in (st[1], st[4]):
+                    if s not in states:
+                        states.append(s)
+        rng = random.Random(7)
+        rng.shuffle(states)
+        states = states[:120]
+        feats = D.RL.convert(None, states, 5)
+        env = ref.make_env(g["block"], bad_states=False)
+        masks = []
+        for s in states:
+            valid = env.getlegalactions(env.state_to_array(s))
+            masks.append([i for i, a in enumerate(['S', 'L', 'R', 'F', 'T']) if a in valid])
+        out[name] = {"block": g["block"], "boxes": g["boxes"], "idx": g["idx"], "choose": g["choose"],
+                     "states": states, "features": ["".join(str(int(x)) for x in row) for row in feats],
+                     "masks": masks}
+    dump("dqn_convert", out)
+
+
 def main():
     ref = ref_harness.load()
     for b in (0, 2):
@@ -272,6 +304,7 @@ def main():
     G(ref, "b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 60, 40000, 3)
     G(ref, "b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 60, 40000, 4)
     G(ref, "b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 40, 30000, 5)
+    gen_convert(ref)
     ref.close()
 
 

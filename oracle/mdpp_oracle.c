@@ -673,3 +673,32 @@ int64_t orc_q_index(orc_q *q, const orc_state *s, int action) {
 }
 double orc_q_at(const orc_q *q, int64_t i) { return q->vals[i]; }
 void orc_q_set_at(orc_q *q, int64_t i, double v) { q->vals[i] = v; }
+
+/* reference src/algorithms/dqn_open_source.py:245-313 RL.convert: 16*total_cars values in {0,1}.
+ * Per listed car 8 values: box NUMBER (floor dropped) as 5 bits MSB first, then the heading as 3 bits
+ * with N,W,E,S = 0,1,2,3 (:262-268) and "no heading" (the other cars, listed by box) = -1 = 111.
+ * Sources of the primary car and the others in string order, missing cars padded with ones (:303),
+ * then the destinations the same way. */
+void orc_convert(const orc_state *s, int total_cars, uint8_t *out) {
+    static const int dir_code[4] = {0, 2, 3, 1}; /* our N,E,S,W -> the reference's N=0 W=1 E=2 S=3 */
+    int n = 1 + s->n_others, k = 0;
+    for (int half = 0; half < 2; half++) {
+        for (int i = 0; i < total_cars; i++) {
+            if (i >= n) {
+                for (int b = 0; b < 8; b++) out[k++] = 1;
+                continue;
+            }
+            int number, dir;
+            if (i == 0) {
+                int node = half ? s->dnode : s->pnode;
+                number = node_boxnum(node);
+                dir = dir_code[node_head(node)];
+            } else {
+                number = box18_num(s->others[i - 1][half]);
+                dir = 7; /* np.binary_repr(-1, width=3) == '111' */
+            }
+            for (int b = 4; b >= 0; b--) out[k++] = (uint8_t)((number >> b) & 1);
+            for (int b = 2; b >= 0; b--) out[k++] = (uint8_t)((dir >> b) & 1);
+        }
+    }
+}

@@ -90,6 +90,9 @@ void orc_q_update(orc_q *q, const orc_env *e, const orc_state *s, int a, const o
 int64_t orc_q_size(const orc_q *q);
 void orc_q_entry(const orc_q *q, int64_t i, orc_state *s, int *action, double *v); /* insertion order */
 
+/* DQN featurizer (reference src/algorithms/dqn_open_source.py:245-313 RL.convert) */
+void orc_convert(const orc_state *s, int total_cars, uint8_t *out);
+
 /* epsilon schedule (reference src/utils/utils.py:12-52) */
 double orc_epsilon(int episodes, int episode, int model);
 

@@ -470,3 +470,13 @@ def reachability(cfg, n_cars, choose, n_local_nodes=36, node_base=36):
     out = np.zeros((n + 31) // 32, dtype=np.uint32)
     live = L.orc_reachability(cfg.h, n_cars, ch, n_local_nodes, node_base, out.ctypes.data_as(C.c_void_p))
     return out, int(live)
+
+
+def convert(st, total_cars=5):
+    """reference dqn_open_source.RL.convert for one state -> list of 16*total_cars ints."""
+    L = lib()
+    L.orc_convert.restype = None
+    L.orc_convert.argtypes = [C.POINTER(State), C.c_int, C.c_void_p]
+    buf = (C.c_uint8 * (16 * total_cars))()
+    L.orc_convert(C.byref(st), total_cars, C.cast(buf, C.c_void_p))
+    return list(buf)

@@ -166,3 +166,52 @@ def test_philox_known_answers():
     assert orc.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert orc.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_dqn_convert_and_mask_match_reference():
+    """RL.convert (80 feature bits) and give_mask recorded from the reference's dqn_open_source."""
+    g = load_golden("dqn_convert")
+    n = 0
+    for name, d in g.items():
+        env = orc.Env(cfg_for(d["block"]), None)
+        for s, f, mask in zip(d["states"], d["features"], d["masks"]):
+            st = orc.state_from_str(s)
+            assert "".join(map(str, orc.convert(st))) == f, s
+            lm = env.legal(st)
+            assert [i for i, a in enumerate([0, 1, 2, 3, 5]) if (lm >> a) & 1] == mask, s
+            n += 1
+    assert n >= 400
+
+
+def test_float32_oracle_tracks_float64_reference_within_1e5():
+    """Same recorded action stream, float32 arithmetic: every table entry within 1e-5 relative of the
+    reference's float64 value (the tolerance the north star states for the GPU table)."""
+    g = load_golden("qrun_b2_2car_bad")
+    env = orc.Env(cfg_for(g["block"]), bad_states_text(g["block"]))
+    q = orc.QTable(f32=True, alpha=g["alpha"], discount=g["discount"])
+    n = len(g["boxes"])
+    for ep in g["log"]:
+        env.reset()
+        env.initialize_cars(n)
+        env.initialize(g["idx"], ep["headings"], g["choose"])
+        it = iter(ep["steps"])
+        done = False
+        while not done:
+            for car in range(n):
+                if env.car_done(car):
+                    continue
+                rec = next(it, None)
+                if rec is None:
+                    done = True
+                    break
+                st = env.encodestate(car, 1)
+                a = orc.ACTIONS.index(rec[2])
+                ns = env.successor_state(st, a)
+                q.update(env, st, a, ns, env.reward(st, ns, car, False))
+                env.update_car(car, ns.pnode)
+            done = done or env.is_game_ended()
+    want = {(s, a): float(v) for s, a, v in g["qvals"]}
+    got = {(s, a): v for s, a, v in q.items()}
+    assert set(got) <= set(want)
+    for k, v in got.items():
+        assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
