@@ -379,6 +379,41 @@ def main():
             "algorithmic_GBps": (10.0 + 16.0 / 4) * s["agent_steps"] / (ms * 1e-3) / 1e9,
             "note": "records (256 MiB) + outputs (640 MiB) exceed L2: HBM-streaming regime"}
         del env4, outs4
+        # config 5 point: DQN feed, 2^24 envs, (convert(s), action, convert(s'), reward, mask(s')) per agent-step
+        n5 = 1 << 24
+        env5 = BatchedEnv(sc, n5, device=dev, seed=6)
+        f_s = torch.empty((n5, 80), dtype=torch.uint8, device=dev)
+        f_n = torch.empty((n5, 80), dtype=torch.uint8, device=dev)
+        lg = torch.empty(n5, dtype=torch.uint8, device=dev)
+        sid = torch.empty(n5, dtype=torch.int32, device=dev)
+        o5 = {"reward": torch.empty(n5, dtype=torch.float32, device=dev),
+              "next_legal": torch.empty(n5, dtype=torch.uint8, device=dev),
+              "done": torch.empty(n5, dtype=torch.uint8, device=dev),
+              "status": torch.empty(n5, dtype=torch.uint8, device=dev)}
+        kernel_ms, reps5 = 0.0, 6
+        for w in range(2 + reps5):
+            if w == 2:
+                env5.stats(reset=True)
+            for c in range(k):
+                e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                e0.record()
+                env5.dqn_observe(c, features=f_s, legal=lg, state=sid)
+                e1.record()
+                acts = torch.where(lg != 0, torch.log2((lg & (0 - lg)).float()).to(torch.uint8),
+                                   torch.full_like(lg, 0xFF))   # lowest legal action (stand-in policy)
+                e2.record()
+                env5.dqn_act(c, acts, next_features=f_n, out=o5, auto_reset=True, round=w)
+                e3.record()
+                torch.cuda.synchronize()
+                if w >= 2:
+                    kernel_ms += e0.elapsed_time(e1) + e2.elapsed_time(e3)
+        s = env5.stats(reset=True)
+        aux["dqn_feed_16Mi_envs"] = {
+            "value": s["agent_steps"] / (kernel_ms * 1e-3), "unit": UNIT,
+            "algorithmic_GBps": (166.0 + 16.0 / k) * s["agent_steps"] / (kernel_ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": (166.0 + 16.0 / k) * s["agent_steps"] / (kernel_ms * 1e-3) / 1e9 / measured_peak()[0],
+            "note": "dqn_observe + dqn_act kernels only (the policy network is PyTorch and not timed)"}
+        del env5, f_s, f_n
 
     if rank == 0:
         line = {

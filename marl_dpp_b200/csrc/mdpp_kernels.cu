@@ -196,8 +196,10 @@ step_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, int
 // ------------------------------------------------------------------------------------------------
 // lockstep rollout, uniform-random legal policy, auto-reset (config "random-policy sweep")
 // ------------------------------------------------------------------------------------------------
+// 4 CTAs/SM (<= 64 registers): the unrolled per-car loop wants ~95 registers, but at 2 CTAs/SM the
+// kernel sat at 24 % occupancy stalled on fixed-latency ALU dependencies (ncu: "wait")
 template <int NC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int rounds,
                       uint64_t first_round, uint32_t seed, int kind, uint8_t *__restrict__ action_out,
                       float *__restrict__ reward_out, uint8_t *__restrict__ done_out,
