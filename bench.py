@@ -302,7 +302,7 @@ def main():
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "q_substep_kernel<%d>" % k, "avg_launch_ms": avg_ms,
+                "traffic": traffic, "kernel": "q_fast_kernel<%d,PLAIN>" % k, "avg_launch_ms": avg_ms,
                 "units_per_launch": units, "algorithmic_bytes_per_unit": FUSED_Q_BYTES_PER_STEP(k), "peak_source": how,
                 "note": "integer-ALU/latency-bound kernel; state and Q table are L2-resident at this size"}
 

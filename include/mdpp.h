@@ -31,7 +31,7 @@ extern "C" {
 #define MDPP_BOXES 18
 #define MDPP_NONE 255
 #define MDPP_MAX_DEST 8
-#define MDPP_Q_ROW 8      /* floats per Q row: S,L,R,F,T + 3 spare (kept 0) = one 32-byte sector */
+#define MDPP_Q_ROW 8      /* floats per Q row: S,L,R,F,T + 3 library slots = one 32-byte sector */
 #define MDPP_FIXED_SHIFT 18 /* fixed-point fraction bits of the TD accumulators */
 
 enum {
@@ -174,6 +174,11 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
  * did).  forced: optional [n_envs] u8, MDPP_ACT_SKIP = choose by coin/argmax, MDPP_ACT_GREEDY = argmax,
  * otherwise take that action as an exploration step (replays a recorded decision stream).  Optional outputs as in
  * mdpp_step_car plus the chosen action. */
+/* Q rows are 8 floats: slots 0..4 = Q(s, S/L/R/F/T); slots 5..7 belong to the library (slot 5 carries the
+ * bad-state flag of the row's state, written by mdpp_q_init; it is identical in every replica, so an
+ * all-reduce average leaves it intact).  mdpp_q_substep initialises a table it has not seen; call
+ * mdpp_q_init yourself after overwriting whole rows (e.g. zeroing the tensor).  q is 32-byte aligned. */
+int mdpp_q_init(mdpp_handle *h, float *q /*DEV [n_states][8]*/, void *stream);
 int mdpp_q_substep(mdpp_handle *h, float *q /*DEV [n_states][8]*/, const mdpp_learner *lp, int car_slot,
                    uint64_t round, const uint8_t *forced /*DEV*/, uint8_t *action_out /*DEV*/,
                    uint32_t *state_idx /*DEV*/, float *reward /*DEV*/, void *stream);

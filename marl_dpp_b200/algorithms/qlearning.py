@@ -78,7 +78,7 @@ class RL:
                 continue
             q[idx, a] = value
             vis[idx] |= 1 << a
-        learner.q.copy_(q)
+        learner.q[:, :5] = q[:, :5].to(learner.q.device)   # slots 5..7 of a row belong to the library
         learner.visited.copy_(vis)
 
     def _pull(self):

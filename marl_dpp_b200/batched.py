@@ -246,6 +246,8 @@ class BatchedQLearner:
         assert self.q.shape == (n_states, 8) and self.q.dtype == torch.float32 and self.q.is_contiguous()
         self.round = 0
         L, h = env._L, env._h
+        with torch.cuda.device(env.device):  # slot 5 of every row <- bad-state flag of that state
+            _lib.check(L.mdpp_q_init(h, _ptr(self.q), _stream()))
         off = L.mdpp_visited_bits(h) - env.workspace.data_ptr()
         self.visited = env.workspace[off:off + 4 * n_states].view(torch.int32)
 

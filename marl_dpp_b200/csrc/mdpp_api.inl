@@ -27,7 +27,7 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct Carve {
-    size_t tables, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, dl, total;
+    size_t tables, nodetab, rng, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, dl, total;
     uint32_t touched_capacity, replicas;
 };
 
@@ -39,6 +39,8 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     const size_t keys = (size_t)cfg.n_states * MDPP_Q_ROW;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
     c.tables = take(sizeof(SmemTables));
+    c.nodetab = take((size_t)MDPP_NODES * 16);
+    c.rng = take((size_t)n_envs * 4 * 3);
     c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
     c.recs = take((size_t)n_envs * 16);
     // accumulator replicas (power of two, <= 64): 8 unless that exceeds a 48 MB budget.  Measured on B200,
@@ -76,6 +78,11 @@ struct mdpp_handle {
     int sm_count;
     uint32_t parity;        // sub-step parity of the touched-key counters
     int q_ctas_per_sm;      // co-resident CTAs of the persistent learner kernel (occupancy query)
+    bool q_fast;            // fast learner kernel (MDPP_QFAST=0 selects the first-generation one)
+    const float *q_inited;  // Q table whose slot-5 bad-state flags were written by q_init_kernel
+    uint64_t rng_round;     // round whose Philox words the car-0 launch published
+    uint32_t rng_seed;
+    int qf_ctas_per_sm;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool q_global_tables;   // learner kernel variant (MDPP_QTAB=0 selects the shared-memory one)
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
@@ -175,6 +182,9 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->env_id_base = (uint32_t)env_id_base;
     h->ws = (char *)workspace;
     make_devcfg(*cfg, h->dev);
+    h->q_fast = !(getenv("MDPP_QFAST") && atoi(getenv("MDPP_QFAST")) == 0);
+    h->q_inited = nullptr;
+    h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
     h->q_global_tables = !(getenv("MDPP_QTAB") && atoi(getenv("MDPP_QTAB")) == 0);
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
@@ -187,7 +197,15 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     memset(&img, 0, sizeof img);
     for (int n = 0; n < MDPP_NODES; n++) img.nodeinfo[n] = (uint16_t)(cfg->fwd[n] | (cfg->base_legal[n] << 8));
     memcpy(img.bfs, cfg->bfs_len, sizeof img.bfs);
+    uint8_t nodeimg[MDPP_NODES][16];
+    memset(nodeimg, 0, sizeof nodeimg);
+    for (int n = 0; n < MDPP_NODES; n++) {
+        for (int d = 0; d < MDPP_MAX_DEST; d++) nodeimg[n][d] = cfg->bfs_len[d][n];
+        nodeimg[n][8] = cfg->fwd[n];
+        nodeimg[n][9] = cfg->base_legal[n];
+    }
     cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.nodetab, nodeimg, sizeof nodeimg, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->ws + cv.dl, 0xFF, (size_t)n_envs * 4, s); // no deadlock state yet
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.tables, &img, sizeof img, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && bad_bitmap_host)
@@ -311,12 +329,86 @@ static Accum accum_of(mdpp_handle *h) {
     return a;
 }
 
+int mdpp_q_init(mdpp_handle *h, float *q, void *stream) {
+    if (!h || !q) return fail(MDPP_EINVAL, "handle / q is NULL");
+    if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
+    q_init_kernel<<<grid_for(h->cfg.n_states), kThreads, 0, (cudaStream_t)stream>>>(h->dev, q, h->cfg.n_states);
+    MDPP_CUDA(cudaGetLastError());
+    h->q_inited = q;
+    return MDPP_OK;
+}
+
 int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
                    const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward, void *stream) {
     if (!h) return fail(MDPP_EINVAL, "handle is NULL");
     if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
     if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
     cudaStream_t s = (cudaStream_t)stream;
+    if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
+    if (h->q_fast) {
+        if (h->q_inited != q) { // slot 5 of every row carries the bad-state flag of that state
+            int rc = mdpp_q_init(h, q, stream);
+            if (rc) return rc;
+        }
+        if (h->qf_ctas_per_sm == 0) {
+            int occ = 0;
+            cudaError_t oe;
+            switch (h->cfg.n_cars) {
+            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<1, true>, kThreads, 0); break;
+            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<2, true>, kThreads, 0); break;
+            case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<3, true>, kThreads, 0); break;
+            case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<4, true>, kThreads, 0); break;
+            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<5, true>, kThreads, 0); break;
+            }
+            h->qf_ctas_per_sm = (oe == cudaSuccess && occ > 0) ? occ : 4;
+            // one CTA per 256-env tile by default: the hardware scheduler balances the 4096 tiles better
+            // than a one-wave persistent grid, whose last pass is only half full (measured 8 % slower)
+            h->qf_ctas_per_sm = 1 << 20;
+            if (const char *env = getenv("MDPP_QGRID")) { int g = atoi(env); if (g > 0) h->qf_ctas_per_sm = g; }
+        }
+        // Philox hand-over: the car-0 launch of a round publishes the decision words of cars 1..3
+        int rng_mode = 0;
+        if (h->cfg.n_cars > 1 && !(getenv("MDPP_RNGCACHE") && atoi(getenv("MDPP_RNGCACHE")) == 0)) {
+            if (car_slot == 0) {
+                rng_mode = 1;
+                h->rng_round = round;
+                h->rng_seed = lp->seed;
+            } else if (car_slot < 4 && h->rng_round == round && h->rng_seed == lp->seed) {
+                rng_mode = 2;
+            }
+        }
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+        cudaLaunchConfig_t lcf = {};
+        int bs = kThreads;
+        if (const char *env = getenv("MDPP_QTHREADS")) { int t = atoi(env); if (t >= 32 && t <= kThreads && t % 32 == 0) bs = t; }
+        lcf.gridDim = dim3((unsigned)std::min<int64_t>((h->n_envs + bs - 1) / bs, (int64_t)h->sm_count * h->qf_ctas_per_sm));
+        lcf.blockDim = dim3(bs);
+        lcf.stream = s;
+        lcf.attrs = &attr;
+        lcf.numAttrs = 1;
+        const bool plainf = !forced && !action_out && !state_idx && !reward && lp->flags == 0;
+        const uint4 *nodetab = (const uint4 *)(h->ws + h->cv.nodetab);
+        uint32_t *rngw = (uint32_t *)(h->ws + h->cv.rng);
+#define MDPP_QFAST(NCV)                                                                                          \
+        if (plainf) MDPP_CUDA(cudaLaunchKernelEx(&lcf, q_fast_kernel<NCV, true>, h->dev, recs_of(h), h->n_envs,    \
+                h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), nodetab, rngw, rng_mode,    \
+                forced, action_out, state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));          \
+        else MDPP_CUDA(cudaLaunchKernelEx(&lcf, q_fast_kernel<NCV, false>, h->dev, recs_of(h), h->n_envs,         \
+                h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), nodetab, rngw, rng_mode,    \
+                forced, action_out, state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));
+        switch (h->cfg.n_cars) {
+        case 1: MDPP_QFAST(1) break;
+        case 2: MDPP_QFAST(2) break;
+        case 3: MDPP_QFAST(3) break;
+        case 4: MDPP_QFAST(4) break;
+        default: MDPP_QFAST(5) break;
+        }
+#undef MDPP_QFAST
+        MDPP_CUDA(cudaGetLastError());
+        return MDPP_OK;
+    }
     // GT variant: persistent grid (8 CTAs of 256 threads per SM), tables through L1, no barriers
     const bool gt = h->q_global_tables;
     if (gt && h->q_ctas_per_sm == 0) { // persistent grid = exactly the CTAs that are co-resident

@@ -471,6 +471,227 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// learner, fast variant (default).  Same semantics as q_substep_kernel, fewer memory requests and
+// instructions per agent-step (the kernel is bound by instruction issue and L1 wavefronts, not HBM):
+//   * one 16-byte table entry per node (BFS lengths to every destination, F successor, base legal
+//     mask) read with a single LDG.128 -> 2 table loads per step instead of 5;
+//   * the bad-state bit of a state rides in slot 5 of its Q row (written once by q_init_kernel), so
+//     the two bad-states probes cost nothing: both rows are loaded anyway;
+//   * the Philox block of a round is computed once, by the car-0 launch, and the decision words of
+//     cars 1..3 are handed over through a coalesced side array.
+// ------------------------------------------------------------------------------------------------
+struct NodeEnt {
+    uint4 v; // bytes 0-7: bfs_len to destination node 0..7, byte 8: F successor, byte 9: base legal mask
+    __device__ __forceinline__ uint32_t bfs(uint32_t d) const {
+        return (uint32_t)((((unsigned long long)v.y << 32) | v.x) >> (8u * d)) & 0xFFu;
+    }
+    __device__ __forceinline__ uint32_t fwd() const { return v.z & 0xFFu; }
+    __device__ __forceinline__ uint32_t base() const { return (v.z >> 8) & 0xFFu; }
+};
+__device__ __forceinline__ NodeEnt load_ent(const uint4 *__restrict__ tab, uint32_t node) {
+    NodeEnt e;
+    e.v = __ldg(tab + node);
+    return e;
+}
+__device__ __forceinline__ uint32_t legal_mask_ent(const View &v, uint32_t node, const NodeEnt &ent) {
+    uint32_t mask = ent.base();
+    if ((v.occ9 >> boxnum0(node >> 2)) & 1u) mask &= 1u << MDPP_A_F;
+    if (mask & (1u << MDPP_A_F)) {
+        const uint32_t fb = ent.fwd() >> 2;
+        bool blocked = (v.occ9 >> boxnum0(fb)) & 1u;
+        blocked = blocked || (((v.sel >> fb) & 1u) && (v.sel & v.occ18));
+        if (blocked) mask &= ~(1u << MDPP_A_F);
+    }
+    return mask;
+}
+
+// slot 5 of every Q row <- 1.0f iff the heading-stripped state is in the bad-states set (else 0.0f).
+// Identical in every replica, so an all-reduce average leaves it intact.
+__global__ void __launch_bounds__(kThreads)
+q_init_kernel(DevCfg cfg, float *__restrict__ q, int64_t n_states) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_states) return;
+    float flag = 0.f;
+    if (cfg.bad_on) {
+        const uint32_t nl = (uint32_t)(s % cfg.n_local_nodes), t = (uint32_t)(s / cfg.n_local_nodes);
+        const uint32_t dnidx = t % cfg.n_dest_nodes, rank = t / cfg.n_dest_nodes;
+        const uint32_t id = (rank * cfg.n_dest_boxes + cfg.dn_dbox[dnidx]) * cfg.n_src_boxes +
+                            (((nl + cfg.node_base) >> 2) - cfg.box_base);
+        flag = ((__ldg(cfg.bad_bitmap + (id >> 5)) >> (id & 31u)) & 1u) ? 1.f : 0.f;
+    }
+    q[s * MDPP_Q_ROW + 5] = flag;
+}
+
+// rng_mode: 0 = compute the Philox block here; 1 = car-0 launch: compute it for every live env and
+// publish the words of cars 1..3; 2 = read this car's word from the side array.
+template <int NC, bool PLAIN>
+__global__ void __launch_bounds__(kThreads)   // 48 registers; forcing 6 CTAs/SM (40 + spills) measured 10 % slower
+q_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c, uint64_t round,
+              LearnArgs lp, const float *__restrict__ q, Accum ac, const uint4 *__restrict__ nodetab,
+              uint32_t *__restrict__ rng_words, int rng_mode, const uint8_t *__restrict__ forced,
+              uint8_t *__restrict__ action_out, uint32_t *__restrict__ state_out, float *__restrict__ reward_out,
+              uint32_t *__restrict__ dl_state, Control *ctl) {
+    const uint32_t lflags = PLAIN ? 0u : lp.flags;
+    if constexpr (PLAIN) { forced = nullptr; action_out = nullptr; state_out = nullptr; reward_out = nullptr; }
+    pdl_launch_dependents();
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_envs; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = base + threadIdx.x;
+    StatAcc acc;
+    int64_t rsum = 0;
+    if (e < n_envs) {
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        const uint32_t env = env_id_base + (uint32_t)e;
+        uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
+        float r_out = 0.f;
+        const bool live = (int32_t)episode < lp.episodes;
+        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : 1;
+        uint32_t word = 0;
+        if (rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
+            if (live) {
+                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+                word = p.x;
+                if (NC > 1) rng_words[e] = p.y;
+                if (NC > 2) rng_words[(size_t)n_envs + e] = p.z;
+                if (NC > 3) rng_words[2 * (size_t)n_envs + e] = p.w;
+            }
+        } else if (rng_mode == 2) {
+            word = rng_words[(size_t)(c - 1) * n_envs + e];
+        }
+        if (live && !f_done(car_field(cars, c))) {
+            View v = view_of<NC>(cars, c, mode, cfg);
+            const NodeEnt entP = load_ent(nodetab, v.pnode);
+            const uint32_t lm = legal_mask_ent(v, v.pnode, entP);
+            const uint32_t sidx = state_index(v, v.pnode, cfg);
+            s_out = sidx;
+            uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
+            const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
+            if (lm && forced_ok) {
+                pdl_wait(); // first Q read: the preceding finalize must be complete
+                float qs[MDPP_Q_ROW];
+                ldg_row(q + (size_t)sidx * MDPP_Q_ROW, qs);
+                uint32_t a;
+                bool explore;
+                const uint32_t eps16 = eps_q16_of(lp, (int32_t)episode);
+                if (f == MDPP_ACT_GREEDY) {
+                    a = 0;
+                    explore = false;
+                } else if (f != MDPP_ACT_SKIP) {
+                    a = f;
+                    explore = true;
+                } else {
+                    const uint32_t w = rng_mode ? word : decision_word(round, c, lp.seed, env);
+                    explore = (w >> 16) < eps16;
+                    a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
+                }
+                if (!explore) {
+                    float best = 0.f;
+                    bool have = false;
+#pragma unroll
+                    for (int k = 0; k < MDPP_N_ACT; k++) {
+                        bool ok = (lm >> k) & 1u;
+                        if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
+                    }
+                }
+                acc.explore += explore;
+                bool stalled = false;
+                if (lflags & MDPP_LEARN_DETECT) {
+                    uint32_t run = rec.w & 0xFFu;
+                    run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
+                    stalled = run == 3u * NC;
+                    rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
+                    if (stalled) {
+                        dl_state[e] = sidx;
+                        episode = (uint32_t)lp.episodes;
+                    }
+                }
+                if (!stalled) {
+                    const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
+                    const uint32_t nn = a == MDPP_A_F ? entP.fwd() : ((v.pnode & ~3u) | ((v.pnode + rot) & 3u));
+                    const NodeEnt entN = load_ent(nodetab, nn);
+                    const uint32_t nidx = state_index(v, nn, cfg);
+                    const uint32_t lm2 = legal_mask_ent(v, nn, entN);
+                    float ns[MDPP_Q_ROW];
+                    ldg_row(q + (size_t)nidx * MDPP_Q_ROW, ns);
+                    // q_reward (src/env_gym.py:555-620); the bad-state bits came with the two rows
+                    int32_t ri;
+                    if (cfg.bad_on && ns[5] != 0.f) ri = -10000;
+                    else if (cfg.bad_on && qs[5] != 0.f) ri = 0;
+                    else {
+                        ri = -10 + 50 * ((int32_t)entP.bfs(v.dnidx) - (int32_t)entN.bfs(v.dnidx));
+                        if (nn == v.dnode) ri += 10010;
+                        int32_t clash = 0;
+#pragma unroll
+                        for (int i = 0; i < NC; i++)
+                            if (i != c) clash += ((f_node(car_field(cars, i)) >> 2) == (nn >> 2));
+                        ri -= clash * 100000;
+                    }
+                    float nv = 0.f;
+                    bool have = false;
+#pragma unroll
+                    for (int k = 0; k < MDPP_N_ACT; k++) {
+                        bool ok = (lm2 >> k) & 1u;
+                        if (ok && (!have || ns[k] > nv)) { nv = ns[k]; have = true; }
+                    }
+                    float qa = qs[0];
+#pragma unroll
+                    for (int k = 1; k < MDPP_N_ACT; k++) qa = (a == (uint32_t)k) ? qs[k] : qa;
+                    const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
+                    const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
+                    if (!(lflags & MDPP_LEARN_FROZEN)) {
+                        const uint32_t key = sidx * MDPP_Q_ROW + a;
+                        const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
+                        const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
+                        atomicAdd((unsigned long long *)(ac.sum + rkey), (unsigned long long)fx);
+                        if (atomicAdd(ac.cnt + rkey, 1u) == 0u) {
+                            ac.last[key] = newv;
+                            if (!ac.dense) {
+                                const uint32_t bit = 1u << (key & 31u);
+                                if (!(atomicOr(ac.touched_bits + (key >> 5), bit) & bit)) {
+                                    uint32_t slot = atomicAdd(&ctl->touched_count[ac.parity], 1u);
+                                    if (slot < ac.capacity) ac.touched[slot] = key;
+                                }
+                            }
+                        }
+                    }
+                    cars = advance_car(cars, c, v, nn, cfg);
+                    steps = steps < 0xFFFFu ? steps + 1 : steps;
+                    acc.steps = 1;
+                    rsum = ri;
+                    r_out = (float)ri;
+                }
+                a_out = a;
+            }
+        }
+        if (live && c == NC - 1) {
+            bool finished = all_done<NC>(cars);
+            bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                acc.episodes = 1;
+                acc.capped = capped;
+                episode = episode + 1;
+                steps = 0;
+                rec.w &= ~0xFFu;
+                cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+            }
+        }
+        if (live) {
+            rec.x = (uint32_t)cars;
+            rec.y = (uint32_t)(cars >> 32);
+            rec.z = (episode & 0xFFFFu) | (steps << 16);
+            recs[e] = rec;
+        }
+        if (action_out) action_out[e] = (uint8_t)a_out;
+        if (state_out) state_out[e] = s_out;
+        if (reward_out) reward_out[e] = r_out;
+    }
+    if (lflags & MDPP_LEARN_FROZEN) flush_stats_warp<false>(acc, rsum, ctl);
+    else flush_stats_warp<true>(acc, rsum, ctl);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // string-API support (n_envs small): evaluate a transition from an ARBITRARY state id, and the bare
 // update_car.  The reference's getlegalactions / get_successor_state / reward_function take state
 // strings, not the env (src/env_gym.py:188-265,485-620); only the clash term reads the cars.

@@ -251,7 +251,7 @@ def test_batched_qlearning_matches_oracle(case):
     items = [x for x in oq.items() if x[1] != "B"]
     for s, a, v in items:
         assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
-    assert np.count_nonzero(q) == sum(1 for _, _, v in items if v != 0.0)
+    assert np.count_nonzero(q[:, :5]) == sum(1 for _, _, v in items if v != 0.0)
     gs, ws = env.stats(), ob.stats()
     for k in ("agent_steps", "episodes_done", "episodes_capped", "reward_sum", "explore_steps"):
         assert gs[k] == ws[k], k
