@@ -46,7 +46,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     // accumulator replicas (power of two, <= 64): 8 unless that exceeds a 48 MB budget.  Measured on B200,
     // 2^20 envs: more replicas cut the same-address tail when all envs share a few states (first
     // rounds) but widen the L2 footprint in steady state; 4-8 is the flat optimum
-    c.replicas = 8;
+    c.replicas = keys <= 8192 ? 64 : 8; // a tiny table means every key is hot (1-car block: 110 keys)
     while (c.replicas > 1 && (size_t)c.replicas * keys * 12 > ((size_t)48 << 20)) c.replicas >>= 1;
     if (const char *env = getenv("MDPP_REPLICAS")) {
         int r = atoi(env);
