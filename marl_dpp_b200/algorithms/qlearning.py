@@ -26,7 +26,7 @@ class RL:
         step_cap agent-steps per episode before a forced reset (the reference's train_given_state has
         none and can spin forever at epsilon 0 -- SURVEY fact 5; 0 restores that), bad_states: None =
         try the layout's file like the reference (env_gym.py:71-83), or the file's text."""
-        self.env_config = env_config if isinstance(env_config, Configuration) else Configuration(env_config)
+        self.env_config = Configuration.coerce(env_config)  # ours, a layout dict, or the reference's object
         self.alpha = 0.9
         self.discount = 0.15
         self.probability_model = 3

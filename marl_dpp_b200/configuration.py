@@ -54,6 +54,35 @@ class Configuration:
         self.stations_info = [[self.station_box_list[i], 0, self.station_processing_count_list[i]]
                               for i in range(self.no_of_stations)]
 
+    @classmethod
+    def from_reference(cls, ref_config):
+        """Accept the reference's own Configuration object (reference src/configuration.py:44-145): the
+        layout dict is rebuilt from its attributes, so `RL(..., env_config=ed)` works unchanged when
+        the plugin is imported from the reference's app.py."""
+        r = ref_config
+        return cls({
+            "number_of_rows": r.environment_rows, "number_of_cols": r.environment_columns,
+            "bad_states_file": r.environment_bad_states_file, "no_box_list": list(r.no_box_list),
+            "no_node_list": [],  # the reference's list is the derived one (every node of a no_box)
+            "no_floor": r.no_floor, "environment_node_name_list": list(r.environment_node_name_list),
+            "is_destination_node": r.is_destination_node, "no_of_stations": r.no_of_stations,
+            "disconnected_nodes_list": list(r.disconnected_nodes_list), "station_box_list": list(r.station_box_list),
+            "station_destination_list": [list(x) for x in r.destination_nodes_list],
+            "station_processing_count_list": list(r.station_processing_count_list),
+            "station_entrance_list": [list(x) for x in r.station_entrance_list], "no_of_cars": r.no_of_cars,
+            "training_complete_destination_index": r.training_complete_destination_index,
+            "selective_blocked_nodes_dictionary": dict(r.selective_blocked_nodes_dictionary),
+            "selective_blocked_boxes_dictionary": dict(r.selective_blocked_boxes_dictionary),
+            "cars_info": deepcopy(r.cars_info), "initial_states": deepcopy(r.initial_states)})
+
+    @classmethod
+    def coerce(cls, env_config):
+        if isinstance(env_config, cls):
+            return env_config
+        if isinstance(env_config, dict):
+            return cls(env_config)
+        return cls.from_reference(env_config)
+
     def get_legal_actions(self, node):
         """reference src/env_gym.py:114-130 (unfiltered, 'B' included)."""
         m = int(self.graph.base_legal6[node_id(node)])

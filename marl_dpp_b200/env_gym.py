@@ -32,8 +32,7 @@ class _Car:
 
 class Environment:
     def __init__(self, env_conf, device=None):
-        if not isinstance(env_conf, Configuration):
-            env_conf = Configuration(env_conf)
+        env_conf = Configuration.coerce(env_conf)
         self.action_mapping = {a: i for i, a in enumerate(ACTIONS6)}
         self.reverse_action_mapping = {i: a for i, a in enumerate(ACTIONS6)}
         self.env_conf = env_conf

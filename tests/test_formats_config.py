@@ -56,3 +56,25 @@ def test_qvalue_file_roundtrip(tmp_path):
     g = load_golden("qrun_b0_1car")["qvals"]
     formats.write_qvalues(path, [(s, a, float(v)) for s, a, v in g])
     assert [(s, a, repr(v)) for s, a, v in formats.read_qvalues(path)] == [tuple(x) for x in g]
+
+
+def test_configuration_accepts_the_references_object():
+    """A stand-in with the reference Configuration's attribute names (src/configuration.py:44-145)."""
+    from types import SimpleNamespace
+    d = layout_3[2]
+    ref_like = SimpleNamespace(
+        environment_rows=3, environment_columns=3, environment_bad_states_file=d["bad_states_file"],
+        no_box_list=d["no_box_list"], no_node_list=["D9N", "D9E", "D9S", "D9W"], no_floor=1,
+        environment_node_name_list=d["environment_node_name_list"], is_destination_node=True,
+        no_of_stations=3, disconnected_nodes_list=d["disconnected_nodes_list"],
+        station_box_list=d["station_box_list"], destination_nodes_list=d["station_destination_list"],
+        station_processing_count_list=d["station_processing_count_list"],
+        station_entrance_list=d["station_entrance_list"], no_of_cars=3,
+        training_complete_destination_index=1,
+        selective_blocked_nodes_dictionary=d["selective_blocked_nodes_dictionary"],
+        selective_blocked_boxes_dictionary=d["selective_blocked_boxes_dictionary"],
+        cars_info=d["cars_info"], initial_states=d["initial_states"])
+    c = Configuration.coerce(ref_like)
+    assert c.action_dictionary == Configuration(d).action_dictionary
+    assert c.no_node_list == ["D9N", "D9E", "D9S", "D9W"] and c.initial_states == d["initial_states"]
+    assert Configuration.coerce(c) is c and Configuration.coerce(d).layout["no_box_list"] == ["D9"]
