@@ -553,8 +553,8 @@ int mdpp_q_finalize(mdpp_handle *h, float *q, void *stream) {
     if (!q) return fail(MDPP_EINVAL, "q is NULL");
     const Accum acf = accum_of(h);
     unsigned grid = acf.dense ? (unsigned)std::min<int64_t>((acf.n_keys + kThreads - 1) / kThreads, (int64_t)h->sm_count * 4)
-                              : (unsigned)std::min<int64_t>(((int64_t)h->cv.touched_capacity * 32 + kThreads - 1) / kThreads,
-                                                            (int64_t)h->sm_count * 4);
+                              : (unsigned)std::min<int64_t>(((int64_t)h->cv.touched_capacity + kThreads - 1) / kThreads,
+                                                            (int64_t)h->sm_count * 8);
     cudaLaunchAttribute pdl_attr;
     pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl_attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;

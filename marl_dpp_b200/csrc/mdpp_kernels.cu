@@ -842,30 +842,32 @@ q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
                       (unsigned long long)touched);
         return;
     }
+    // large table: one THREAD per listed key (a warp per key left 31 lanes idle behind a chain of
+    // dependent L2/DRAM loads: 35-49 us for 22 k keys on the 4-car table)
     const uint32_t n = min(ctl->touched_count[ac.parity], ac.capacity);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = warp; i < n; i += nwarps) { // one warp per touched key, lanes over the replicas
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t key = ac.touched[i];
         long long s = 0;
         uint32_t cnt = 0;
-        for (uint32_t r = lane; r <= ac.replica_mask; r += 32u) {
-            const size_t rkey = (size_t)r * ac.replica_stride + key;
-            const uint32_t c = ac.cnt[rkey];
-            if (c) {
-                cnt += c;
-                s += ac.sum[rkey];
-                ac.cnt[rkey] = 0;
-                ac.sum[rkey] = 0;
+        for (uint32_t r0 = 0; r0 <= ac.replica_mask; r0 += 8u) {
+            uint32_t c[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; j++)
+                c[j] = (r0 + j <= ac.replica_mask) ? ac.cnt[(size_t)(r0 + j) * ac.replica_stride + key] : 0u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8u; j++) {
+                if (c[j]) {
+                    const size_t rkey = (size_t)(r0 + j) * ac.replica_stride + key;
+                    cnt += c[j];
+                    s += ac.sum[rkey];
+                    ac.cnt[rkey] = 0;
+                    ac.sum[rkey] = 0;
+                }
             }
         }
-        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        if (lane == 0) {
-            finalize_key(q, ac, key, s, cnt);
-            ac.touched_bits[key >> 5] = 0; // every set bit of the word belongs to a key finalised in this launch
-        }
+        finalize_key(q, ac, key, s, cnt);
+        // several listed keys can share a bitmap word: clear only this key's bit
+        atomicAnd(ac.touched_bits + (key >> 5), ~(1u << (key & 31u)));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl->touched_count[ac.parity ^ 1u] = 0;
