@@ -525,7 +525,7 @@ q_init_kernel(DevCfg cfg, float *__restrict__ q, int64_t n_states) {
 // rng_mode: 0 = compute the Philox block here; 1 = car-0 launch: compute it for every live env and
 // publish the words of cars 1..3; 2 = read this car's word from the side array.
 template <int NC, bool PLAIN>
-__global__ void __launch_bounds__(kThreads)   // 48 registers; forcing 6 CTAs/SM (40 + spills) measured 10 % slower
+__global__ void __launch_bounds__(kThreads)   // 54 registers; capping at 51 (5 CTAs/SM) or 40 (6) measured 4-10 % slower
 q_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c, uint64_t round,
               LearnArgs lp, const float *__restrict__ q, Accum ac, const uint4 *__restrict__ nodetab,
               uint32_t *__restrict__ rng_words, int rng_mode, const uint8_t *__restrict__ forced,
@@ -607,6 +607,13 @@ q_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env
                     }
                 }
                 if (!stalled) {
+                    // The contributor count is bumped as soon as the key is known: its round trip to L2
+                    // then overlaps the successor-row gather and the TD arithmetic instead of stalling the
+                    // warp at the very end (the returning atomic was 26 % of all stall samples there).
+                    const uint32_t key = sidx * MDPP_Q_ROW + a;
+                    const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
+                    bool first = false;
+                    if (!(lflags & MDPP_LEARN_FROZEN)) first = atomicAdd(ac.cnt + rkey, 1u) == 0u;
                     const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
                     const uint32_t nn = a == MDPP_A_F ? entP.fwd() : ((v.pnode & ~3u) | ((v.pnode + rot) & 3u));
                     const NodeEnt entN = load_ent(nodetab, nn);
@@ -640,11 +647,11 @@ q_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env
                     const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
                     const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
                     if (!(lflags & MDPP_LEARN_FROZEN)) {
-                        const uint32_t key = sidx * MDPP_Q_ROW + a;
                         const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
-                        const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
                         atomicAdd((unsigned long long *)(ac.sum + rkey), (unsigned long long)fx);
-                        if (atomicAdd(ac.cnt + rkey, 1u) == 0u) {
+                        // the first contributor of a (replica, key) leaves the value itself (exact result
+                        // when it stays alone) and, for tables too big to scan, lists the key
+                        if (first) {
                             ac.last[key] = newv;
                             if (!ac.dense) {
                                 const uint32_t bit = 1u << (key & 31u);
