@@ -379,6 +379,22 @@ def main():
             "algorithmic_GBps": (10.0 + 16.0 / 4) * s["agent_steps"] / (ms * 1e-3) / 1e9,
             "note": "records (256 MiB) + outputs (640 MiB) exceed L2: HBM-streaming regime"}
         del env4, outs4
+        # -dd precompute of the headline scenario (2 cars) and of the 4-car scenario: reachability bitmap
+        for tag, scn in (("2car", sc), ("4car", sc4)):
+            envd = BatchedEnv(scn, 1024, device=dev, seed=7)
+            envd.deadlock_reachability()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            bm, sweeps = envd.deadlock_reachability()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            joint = (2 * scn.n_local_nodes + 1) ** scn.n_cars
+            live = int(sum(int((bm[i:i + (1 << 22)].view(torch.uint8).to(torch.int16).unsqueeze(1)
+                                >> torch.arange(8, device=dev, dtype=torch.int16) & 1).sum())
+                           for i in range(0, bm.numel(), 1 << 22)))
+            aux["dd_reachability_" + tag] = {"joint_states": joint, "live_states": live, "sweeps": sweeps,
+                                             "ms": dt * 1e3, "joint_states_per_s": joint * sweeps / dt}
+            del envd, bm
         # config 5 point: DQN feed, 2^24 envs, (convert(s), action, convert(s'), reward, mask(s')) per agent-step
         n5 = 1 << 24
         env5 = BatchedEnv(sc, n5, device=dev, seed=6)
