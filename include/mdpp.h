@@ -94,6 +94,8 @@ typedef struct {
 #define MDPP_LEARN_FROZEN 1u /* select + step but no TD update: validate_given_state (qlearning.py:384-437) */
 #define MDPP_LEARN_MODE0 2u  /* encodestate(car, 0): finished cars are not listed (qlearning.py:342) */
 #define MDPP_LEARN_DETECT 4u /* stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360) */
+#define MDPP_LEARN_OBSERVED 8u /* the state was already encoded for this agent-step (mdpp_step_car peek or
+                                  mdpp_dqn_observe): do not advance the ghost counters a second time */
 
 /* counters accumulated on the device, fetched with mdpp_get_stats_host */
 typedef struct {

@@ -14,18 +14,24 @@ import torch
 from .. import formats
 from ..batched import BatchedEnv, BatchedQLearner
 from ..configuration import Configuration
-from ..tables import ACTIONS5, LEARN_DETECT, LEARN_FROZEN, LEARN_MODE0, Scenario
+import random
+
+from ..tables import ACTIONS5, HEADS, LEARN_DETECT, LEARN_FROZEN, LEARN_MODE0, LEARN_OBSERVED, Scenario, epsilon_schedule
 
 
 class RL:
     def __init__(self, input_dim=None, output_dim=None, cars=None, sess=None, env_config=None,
                  learning_rate=0.0001, batch_size=32, n_envs=1, device=None, step_cap=10000, seed=3,
-                 bad_states=None, qvalue_dir=formats.QVALUE_DIR):
+                 bad_states=None, qvalue_dir=formats.QVALUE_DIR, reference_rng=False):
         """input_dim / output_dim / cars / sess / learning_rate / batch_size are accepted and ignored,
         exactly like the reference (qlearning.py:14-15).  Extra keywords: n_envs lockstep copies,
         step_cap agent-steps per episode before a forced reset (the reference's train_given_state has
         none and can spin forever at epsilon 0 -- SURVEY fact 5; 0 restores that), bad_states: None =
-        try the layout's file like the reference (env_gym.py:71-83), or the file's text."""
+        try the layout's file like the reference (env_gym.py:71-83), or the file's text.
+        reference_rng (n_envs == 1 only): draw headings, coins and exploratory actions from Python's
+        global `random` in the reference's exact call order (random.shuffle per car at initialize,
+        one random.random() per getaction, random.choice(legal) when exploring), so a run seeded like
+        the reference (`random.seed(settings.SEED)`) visits the same states and learns the same table."""
         self.env_config = Configuration.coerce(env_config)  # ours, a layout dict, or the reference's object
         self.alpha = 0.9
         self.discount = 0.15
@@ -36,6 +42,9 @@ class RL:
         self.step_cap = int(step_cap)
         self.seed = int(seed)
         self.qvalue_dir = qvalue_dir
+        self.reference_rng = bool(reference_rng)
+        if self.reference_rng and self.n_envs != 1:
+            raise ValueError("reference_rng replays the reference's single-env random stream: n_envs must be 1")
         self.training_complete_destination_index = self.env_config.training_complete_destination_index
         if bad_states is None:
             try:
@@ -135,9 +144,65 @@ class RL:
             if lo >= episodes or (max_rounds is not None and rounds >= max_rounds):
                 return rounds
 
+    def _train_reference_rng(self, episodes, outputfile_number, boxes, n, idx, choose):
+        """The reference's loop (qlearning.py:191-238) on the host, one env, every decision drawn from
+        Python's `random` in the reference's order; the env step, the greedy argmax and the TD update
+        run on the GPU."""
+        learner = self._make(episodes, boxes, n, idx, choose, flags=LEARN_OBSERVED)
+        env = learner.env
+        th, eps_values = epsilon_schedule(episodes, self.probability_model)
+        peek = torch.tensor([0xFE], dtype=torch.uint8)
+        self.trace = []
+        for episode in range(episodes):
+            if episode == 30:
+                self.save_qvalues(outputfile_number)
+            self.epsilon = next((v for t, v in zip(th, eps_values) if episode < t), eps_values[5])
+            heads = []
+            for num in range(n):                        # env.initialize: random.shuffle(nodes)[0] per car
+                nodes = list("NESW")
+                random.shuffle(nodes)
+                heads.append(HEADS.index(nodes[0]))
+            env.reset(headings=torch.tensor([heads], dtype=torch.uint8), zero_counters=False)
+            done = [False] * n
+            steps = 0
+            ep0 = int(env.cars()["episode"][0])
+            while not all(done):
+                for num in range(n):
+                    if done[num]:
+                        continue
+                    o = env.step_car(num, peek)          # encodestate(num, 1) + getlegalactions
+                    legal = int(o["legal"][0])
+                    legal_actions = [a for a in range(5) if (legal >> a) & 1]
+                    forced = 0xFF
+                    if legal_actions:
+                        if random.random() < self.epsilon:      # flipcoin
+                            forced = random.choice(legal_actions)
+                        else:
+                            forced = 0xFE                       # computeactionfromqvalues on the device
+                    out = learner.substep(num, forced=torch.tensor([forced], dtype=torch.uint8), outputs=True)
+                    learner.finalize()
+                    self.trace.append((int(out["state"][0]), int(out["action"][0])))
+                    steps += 1
+                learner.round += 1
+                cars = env.cars()
+                # the last car slot's launch starts the next episode by itself when every car is done
+                if int(cars["episode"][0]) != ep0:
+                    break
+                done = [bool(x) for x in cars["done"][0].tolist()]
+                if self.step_cap and steps >= self.step_cap:
+                    break
+        return learner
+
     def train_given_state(self, episodes, inputfile_number, outputfile_number, input_car_states=None, no_of_cars=1,
                           destination_index_array=[0, 0, 0, 0], destination_choose_arrays=[0, 0, 0]):
         self.load_qvalues(inputfile_number)
+        if self.reference_rng:
+            learner = self._train_reference_rng(episodes, outputfile_number, input_car_states, no_of_cars,
+                                                destination_index_array, destination_choose_arrays)
+            self.last_stats = learner.env.stats()
+            self.save_qvalues(outputfile_number)
+            self._pull()
+            return
         learner = self._make(episodes, input_car_states, no_of_cars, destination_index_array,
                              destination_choose_arrays)
         saved = []

@@ -7,6 +7,7 @@ settings.params (+ sess=None, env_config=) and runs the same per-initial-state l
 import argparse
 import datetime
 import importlib
+import random
 from copy import deepcopy
 
 from . import layout as layout_module
@@ -24,6 +25,8 @@ def parse_arguments(argv=None):
     ap.add_argument("-v", "--validate", required=True)
     ap.add_argument("--envs", type=int, default=1, help="lockstep env copies (1 = the reference's single env)")
     ap.add_argument("--episodes", type=int, default=settings.EPISODES)
+    ap.add_argument("--reference-rng", action="store_true",
+                    help="one env, decisions from Python's random in the reference's call order (same seed -> same run)")
     return vars(ap.parse_args(argv))
 
 
@@ -52,12 +55,13 @@ def start_training(alg, input_file_number, validate, ed, dd, output_file_number,
 
 def main(argv=None):
     args = parse_arguments(argv)
+    random.seed(settings.SEED)      # the reference seeds at import (app.py:4, src/utils/utils.py:8)
     params = deepcopy(settings.params)
     ed = give_configuration_object(int(args["layout_number"]), int(args["block_number"]))
     RL = importlib.import_module(__package__ + '.algorithms.' + settings.algorithm).RL
     params['sess'] = None
     params['env_config'] = ed
-    rl = RL(**params, n_envs=args["envs"])
+    rl = RL(**params, n_envs=args["envs"], reference_rng=args["reference_rng"])
     out = start_training(rl, args["inputfile"], int(args["validate"]), ed, int(args["detect_deadlock"]),
                          args["outputfile"], args["episodes"])
     print(out, rl.last_stats)

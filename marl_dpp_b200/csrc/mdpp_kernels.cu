@@ -336,7 +336,7 @@ q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t 
         float r_out = 0.f;
         const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
         // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
-        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : 1;
+        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
         if (live && !f_done(car_field(cars, c))) {
             View v = view_of<NC>(cars, c, mode, cfg);
             const uint32_t lm = legal_mask(v, v.pnode, tab);
@@ -546,7 +546,7 @@ q_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env
         uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
         float r_out = 0.f;
         const bool live = (int32_t)episode < lp.episodes;
-        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : 1;
+        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
         uint32_t word = 0;
         if (rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
             if (live) {

@@ -184,3 +184,29 @@ def test_rl_detect_deadlocks_writes_bad_states(scratch):
     assert res in (19, False) and before <= after
     for s in rl.detected_deadlocks:
         assert formats.strip_headings(s) in after
+
+
+@pytest.mark.parametrize("name", ["qrun_b0_1car", "qrun_b2_2car"])
+def test_rl_plugin_reproduces_reference_run_from_the_same_seed(scratch, name):
+    """The strongest drop-in statement: seed Python's `random` like the reference's recorded run and
+    the plugin (one env, reference_rng) visits the same (state, action) sequence and ends with the same
+    table (float32 vs the reference's float64: <= 1e-5 relative), with the env, the argmax and the TD
+    update all on the GPU."""
+    import random
+    import marl_dpp_b200 as m
+    from marl_dpp_b200 import settings
+    from marl_dpp_b200.algorithms.qlearning import RL
+    g = load_golden(name)
+    os.remove(scratch / "data" / "bad_states_files" / "layout-3" / ("down_right.txt" if g["block"] == 2 else "up_left.txt"))
+    rl = RL(**settings.params, sess=None, env_config=m.layout_3[g["block"]], n_envs=1, step_cap=0, reference_rng=True)
+    random.seed(3)                                   # gen_qrun seeds with 3 right before train_given_state
+    rl.train_given_state(g["episodes_total"], '0', '0', g["boxes"], len(g["boxes"]), g["idx"], g["choose"])
+    sc = rl.learner.env.scenario
+    want_trace = [(s[0], s[2]) for ep in g["log"] for s in ep["steps"]]
+    got_trace = [(sc.decode(s), A5[a]) for s, a in rl.trace]
+    assert got_trace == want_trace
+    want = {(s, a): float(v) for s, a, v in g["qvals"]}
+    updated = set(want_trace)
+    assert set(rl.qvals) == updated
+    for k, v in rl.qvals.items():
+        assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
