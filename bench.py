@@ -302,7 +302,7 @@ def main():
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "q_fast_kernel<%d,PLAIN>" % k, "avg_launch_ms": avg_ms,
+                "traffic": traffic, "kernel": "q_env_kernel<%d,PLAIN>" % k, "avg_launch_ms": avg_ms,
                 "units_per_launch": units, "algorithmic_bytes_per_unit": FUSED_Q_BYTES_PER_STEP(k), "peak_source": how,
                 "note": "integer-ALU/latency-bound kernel; state and Q table are L2-resident at this size"}
 
@@ -439,7 +439,7 @@ def main():
             "config": {"workload": WORKLOAD, "layout": 3, "block": BLOCK, "n_cars": k, "envs_per_gpu": n,
                        "bad_states": True, "episodes_per_env": EPISODES, "step_cap": STEP_CAP,
                        "alpha": 0.9, "discount": 0.15, "epsilon_model": 3,
-                       "step": "one round-robin round over every env = n_cars x (q_substep + q_finalize)",
+                       "step": "one round-robin round over every env = n_cars x (q_env_kernel + q_pull_dense_kernel)",
                        "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
                        "sync_interval_rounds": args.sync_interval if world > 1 else None,
                        "parallelism": "dp%d: env shards + per-GPU Q replicas, NCCL all-reduce(AVG)" % world},

@@ -31,8 +31,7 @@ extern "C" {
 #define MDPP_BOXES 18
 #define MDPP_NONE 255
 #define MDPP_MAX_DEST 8
-#define MDPP_Q_ROW 8      /* floats per Q row: S,L,R,F,T + 3 library slots = one 32-byte sector */
-#define MDPP_FIXED_SHIFT 18 /* fixed-point fraction bits of the TD accumulators */
+#define MDPP_Q_ROW 8      /* floats per Q row: S,L,R,F,T + 3 padding slots = one 32-byte sector */
 
 enum {
     MDPP_OK = 0,
@@ -168,24 +167,25 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
                         uint8_t *action /*DEV*/, float *reward /*DEV*/, uint8_t *done /*DEV*/,
                         uint32_t *next_idx /*DEV*/, void *stream);
 
-/* ---- learner: fused epsilon-greedy select + step + TD update -------------------------------
+/* ---- learner: epsilon-greedy select + step + TD update ("mark and pull") ---------------------
  * One sub-step = car `car_slot` of every env: getaction (qlearning.py:74-105), the env step and
- * update (qlearning.py:107-116), all envs reading the Q table as it was when the sub-step
- * began; each env's new value is accumulated in fixed point and mdpp_q_finalize writes, per
- * touched key, the mean over the envs that updated it (exactly the reference's value when one env
- * did).  forced: optional [n_envs] u8, MDPP_ACT_SKIP = choose by coin/argmax, MDPP_ACT_GREEDY = argmax,
- * otherwise take that action as an exploration step (replays a recorded decision stream).  Optional outputs as in
- * mdpp_step_car plus the chosen action. */
-/* Q rows are 8 floats: slots 0..4 = Q(s, S/L/R/F/T); slots 5..7 belong to the library (slot 5 carries the
- * bad-state flag of the row's state, written by mdpp_q_init; it is identical in every replica, so an
- * all-reduce average leaves it intact).  mdpp_q_substep initialises a table it has not seen; call
- * mdpp_q_init yourself after overwriting whole rows (e.g. zeroing the tensor).  q is 32-byte aligned. */
-int mdpp_q_init(mdpp_handle *h, float *q /*DEV [n_states][8]*/, void *stream);
+ * update (qlearning.py:107-116), all envs reading the Q table as it was when the sub-step began.
+ * (state, action) and that snapshot determine the updated value completely, so every env that
+ * updates one key computes the same value: mdpp_q_substep only MARKS the keys its envs touch and
+ * mdpp_q_finalize computes the reference update once per marked key and writes it (exactly the
+ * reference's sequential update when there is one env).  forced: optional [n_envs] u8,
+ * MDPP_ACT_SKIP = choose by coin/argmax, MDPP_ACT_GREEDY = argmax, otherwise take that action as an
+ * exploration step (replays a recorded decision stream).  Optional outputs as in mdpp_step_car plus
+ * the chosen action.
+ * Q rows are 8 floats: slots 0..4 = Q(s, S/L/R/F/T); slots 5..7 are padding to one 32-byte sector
+ * (carried through unchanged).  q is 32-byte aligned. */
 int mdpp_q_substep(mdpp_handle *h, float *q /*DEV [n_states][8]*/, const mdpp_learner *lp, int car_slot,
                    uint64_t round, const uint8_t *forced /*DEV*/, uint8_t *action_out /*DEV*/,
                    uint32_t *state_idx /*DEV*/, float *reward /*DEV*/, void *stream);
-int mdpp_q_finalize(mdpp_handle *h, float *q /*DEV*/, void *stream);
-/* `rounds` full rounds (n_cars sub-steps + finalize each) starting at round index first_round */
+int mdpp_q_finalize(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, void *stream);
+/* `rounds` full rounds (n_cars x (sub-step + finalize)) starting at round index first_round.  The kernels of
+ * consecutive sub-steps overlap through programmatic dependent launch; small tables ping-pong between q and a
+ * workspace copy and are back in q when the call's work completes. */
 int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t first_round,
                         int rounds, void *stream);
 /* end-to-end variant: learner parameters from host memory, stats copied back, synchronised */

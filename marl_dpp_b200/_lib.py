@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libmdpp.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "q_learner.cuh")] + \
           [os.path.join(ROOT, "include", "mdpp.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_error_string", "mdpp_abi_version",
            "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_query_transitions",
            "mdpp_update_car", "mdpp_dqn_observe", "mdpp_dqn_act", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
-           "mdpp_rollout_random", "mdpp_q_init", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
+           "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
            "mdpp_q_train_rounds_host", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
 
 
@@ -71,9 +71,8 @@ def lib():
         "mdpp_step_car": (I, [P, I, I, I, U8, U32, U32, F32, U8, U8, U8, P]),
         "mdpp_step_car_host": (I, [P, I, I, I, U8, U32, U32, F32, U8, U8, U8, P]),
         "mdpp_rollout_random": (I, [P, I, U64, C.c_uint32, I, U8, F32, U8, U32, P]),
-        "mdpp_q_init": (I, [P, F32, P]),
         "mdpp_q_substep": (I, [P, F32, P, I, U64, U8, U8, U32, F32, P]),
-        "mdpp_q_finalize": (I, [P, F32, P]),
+        "mdpp_q_finalize": (I, [P, F32, P, P]),
         "mdpp_q_train_rounds": (I, [P, F32, P, U64, I, P]),
         "mdpp_q_train_rounds_host": (I, [P, F32, P, U64, I, P, P]),
         "mdpp_decode_state": (I, [P, I64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

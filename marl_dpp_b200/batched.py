@@ -231,9 +231,9 @@ class BatchedQLearner:
 
     Semantics of one sub-step (car slot c of every env): all envs read the Q table as it was when
     the sub-step began, pick epsilon-greedily (per-env episode counter drives the reference's
-    epsilon schedule), step, and compute the reference update; each touched key then receives
-    the mean of the values the contributing envs computed.  With one env this IS the reference's
-    sequential update, bit for bit in float32.
+    epsilon schedule) and step; each touched key then receives the reference update, which
+    (state, action) and the snapshot determine completely, so it is computed once per key.  With
+    one env this IS the reference's sequential update, bit for bit in float32.
     """
 
     def __init__(self, env, episodes=5000, alpha=0.9, discount=0.15, probability_model=3, seed=None, q=None,
@@ -246,8 +246,6 @@ class BatchedQLearner:
         assert self.q.shape == (n_states, 8) and self.q.dtype == torch.float32 and self.q.is_contiguous()
         self.round = 0
         L, h = env._L, env._h
-        with torch.cuda.device(env.device):  # slot 5 of every row <- bad-state flag of that state
-            _lib.check(L.mdpp_q_init(h, _ptr(self.q), _stream()))
         off = L.mdpp_visited_bits(h) - env.workspace.data_ptr()
         self.visited = env.workspace[off:off + 4 * n_states].view(torch.int32)
 
@@ -269,7 +267,7 @@ class BatchedQLearner:
 
     def finalize(self):
         with torch.cuda.device(self.env.device):
-            _lib.check(self.env._L.mdpp_q_finalize(self.env._h, _ptr(self.q), _stream()))
+            _lib.check(self.env._L.mdpp_q_finalize(self.env._h, _ptr(self.q), C.byref(self.params), _stream()))
 
     def train_rounds(self, rounds):
         """`rounds` full round-robin rounds (n_cars x (sub-step + finalize)); asynchronous."""

@@ -41,6 +41,7 @@ struct DevCfg {
     uint32_t dbox_sel[MDPP_MAX_DEST]; // destination-box index -> selective mask     constant reads)
     const uint32_t *tables;      // DEV: SmemTables image
     const uint32_t *bad_bitmap;  // DEV: n_box_states bits
+    uint16_t nth_lut[32];        // per 5-bit mask: positions of its set bits, 3 bits each, lowest first
 };
 
 // Divergently indexed tables live in shared memory (a constant-bank lookup would serialise).
@@ -208,7 +209,7 @@ __device__ __forceinline__ View view_of(uint64_t &cars, int c, int mode, const D
         } else {
             listed = true;
             box18 = f_node(f) >> 2;
-            code = 1u + (box18 - cfg.box_base) * cfg.n_dest_boxes + cfg.car_dbox[i][f_di(f)];
+            code = 1u + (box18 - cfg.box_base) * cfg.n_dest_boxes + (f_di(f) ? cfg.car_dbox[i][1] : cfg.car_dbox[i][0]);
         }
         codes[i] = listed ? code : 0u;
         if (listed) {
@@ -216,10 +217,11 @@ __device__ __forceinline__ View view_of(uint64_t &cars, int c, int mode, const D
             v.occ18 |= 1u << box18;
         }
     }
-    v.dnidx = cfg.car_dnidx[c][v.di];
-    v.dnode = cfg.car_dnode[c][v.di];
-    v.dbox = cfg.car_dbox[c][v.di];
-    v.sel = cfg.car_sel[c][v.di];
+    // two uniform constants and a select each (a register-indexed constant load is slow)
+    v.dnidx = v.di ? cfg.car_dnidx[c][1] : cfg.car_dnidx[c][0];
+    v.dnode = v.di ? cfg.car_dnode[c][1] : cfg.car_dnode[c][0];
+    v.dbox = v.di ? cfg.car_dbox[c][1] : cfg.car_dbox[c][0];
+    v.sel = v.di ? cfg.car_sel[c][1] : cfg.car_sel[c][0];
     uint32_t rank = 0;
     if constexpr (NC > 1) {
         sort_codes<NC>(codes);
@@ -317,6 +319,12 @@ __device__ __forceinline__ void ldg_row(const float *p, float (&r)[MDPP_Q_ROW]) 
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
                  : "l"(p));
+}
+
+// n-th (0-based) set bit of a 5-bit mask through the 32-entry table in the kernel-parameter block: one
+// indexed constant load (a warp rarely holds more than 3-4 distinct masks) instead of ~22 ALU instructions
+__device__ __forceinline__ uint32_t nth_set_bit_lut(const DevCfg &cfg, uint32_t mask, uint32_t n) {
+    return ((uint32_t)cfg.nth_lut[mask] >> (3u * n)) & 7u;
 }
 
 // n-th (0-based) set bit of a 5-bit mask

@@ -27,8 +27,10 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct Carve {
-    size_t tables, nodetab, rng, bad, recs, sum, cnt, last, bits, touched, visited, control, stage, dl, total;
-    uint32_t touched_capacity, replicas;
+    size_t tables, nodetab, rng, bad, recs, sinfo, qalt, marks, bits, list, vals, visited, control, stage, dl, total;
+    uint32_t capacity; // touched-list entries per parity (list mode)
+    uint32_t replicas; // mark-array replicas (dense mode)
+    bool dense;        // small table: byte marks + ping-pong pull; else bitmap + list + two-pass pull
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -43,21 +45,24 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.rng = take((size_t)n_envs * 4 * 3);
     c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
     c.recs = take((size_t)n_envs * 16);
-    // accumulator replicas (power of two, <= 64): 8 unless that exceeds a 48 MB budget.  Measured on B200,
-    // 2^20 envs: more replicas cut the same-address tail when all envs share a few states (first
-    // rounds) but widen the L2 footprint in steady state; 4-8 is the flat optimum
-    c.replicas = keys <= 8192 ? 64 : 8; // a tiny table means every key is hot (1-car block: 110 keys)
-    while (c.replicas > 1 && (size_t)c.replicas * keys * 12 > ((size_t)48 << 20)) c.replicas >>= 1;
-    if (const char *env = getenv("MDPP_REPLICAS")) {
-        int r = atoi(env);
-        if (r >= 1 && r <= 64 && (r & (r - 1)) == 0) c.replicas = (uint32_t)r;
+    c.sinfo = take((size_t)cfg.n_states * 4);
+    // dense mode sweeps the whole table once per sub-step (copy + substitute the marked keys): right
+    // while the table is a few MB, i.e. L2-resident and cheaper to sweep than to list
+    c.dense = keys <= ((size_t)1 << 20);
+    if (const char *env = getenv("MDPP_DENSE")) c.dense = atoi(env) != 0;
+    c.capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
+    if (c.dense) {
+        c.qalt = take(keys * 4);
+        c.replicas = 8;
+        if (const char *env = getenv("MDPP_MARKREP")) { int r = atoi(env); if (r >= 1 && r <= 64 && !(r & (r - 1))) c.replicas = (uint32_t)r; }
+        c.marks = take(keys * 4 * 2 * c.replicas);
+        c.bits = c.list = c.vals = 0;
+    } else {
+        c.qalt = c.marks = 0;
+        c.bits = take(2 * (keys / 8 + 4));
+        c.list = take(2 * (size_t)c.capacity * 4);
+        c.vals = take((size_t)c.capacity * 4);
     }
-    c.sum = take(keys * 8 * c.replicas);
-    c.cnt = take(keys * 4 * c.replicas);
-    c.last = take(keys * 4);
-    c.bits = take(keys / 8 + 4);
-    c.touched_capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
-    c.touched = take((size_t)c.touched_capacity * 4);
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
     c.stage = take((size_t)n_envs * 16);
@@ -76,15 +81,11 @@ struct mdpp_handle {
     uint32_t env_id_base;
     char *ws;
     int sm_count;
-    uint32_t parity;        // sub-step parity of the touched-key counters
-    int q_ctas_per_sm;      // co-resident CTAs of the persistent learner kernel (occupancy query)
-    bool q_fast;            // fast learner kernel (MDPP_QFAST=0 selects the first-generation one)
-    const float *q_inited;  // Q table whose slot-5 bad-state flags were written by q_init_kernel
+    uint32_t parity;        // sub-step parity of the marks / touched lists
     uint64_t rng_round;     // round whose Philox words the car-0 launch published
     uint32_t rng_seed;
-    int qf_ctas_per_sm;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
-    bool q_global_tables;   // learner kernel variant (MDPP_QTAB=0 selects the shared-memory one)
+    bool chain;             // the previous launch on the stream was one of our learner kernels
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
 };
 
@@ -146,6 +147,12 @@ static void make_devcfg(const mdpp_config &c, DevCfg &d) {
         d.dn_dbox[i] = c.dest_node_box[i];
     }
     for (int i = 0; i < c.n_dest_boxes; i++) d.dbox_sel[i] = c.sel_mask[i];
+    for (int m = 0; m < 32; m++) {
+        uint32_t packed = 0, n = 0;
+        for (int k = 0; k < 5; k++)
+            if ((m >> k) & 1) packed |= (uint32_t)k << (3 * n++);
+        d.nth_lut[m] = (uint16_t)packed;
+    }
 }
 
 extern "C" {
@@ -182,11 +189,9 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->env_id_base = (uint32_t)env_id_base;
     h->ws = (char *)workspace;
     make_devcfg(*cfg, h->dev);
-    h->q_fast = !(getenv("MDPP_QFAST") && atoi(getenv("MDPP_QFAST")) == 0);
-    h->q_inited = nullptr;
     h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
-    h->q_global_tables = !(getenv("MDPP_QTAB") && atoi(getenv("MDPP_QTAB")) == 0);
+    h->chain = false;
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
     h->dev.bad_bitmap = (const uint32_t *)(h->ws + cv.bad);
     int devid = 0;
@@ -211,6 +216,18 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     if (e == cudaSuccess && bad_bitmap_host)
         e = cudaMemcpyAsync(h->ws + cv.bad, bad_bitmap_host, (((size_t)cfg->n_box_states + 31) / 32) * 4,
                             cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) { // per-state info words of the pull kernels
+        uint32_t *sinfo = (uint32_t *)(h->ws + cv.sinfo);
+        const unsigned g = (unsigned)((cfg->n_states + kThreads - 1) / kThreads);
+        switch (cfg->n_cars) {
+        case 1: state_info_kernel<1><<<g, kThreads, 0, s>>>(h->dev, sinfo, cfg->n_states); break;
+        case 2: state_info_kernel<2><<<g, kThreads, 0, s>>>(h->dev, sinfo, cfg->n_states); break;
+        case 3: state_info_kernel<3><<<g, kThreads, 0, s>>>(h->dev, sinfo, cfg->n_states); break;
+        case 4: state_info_kernel<4><<<g, kThreads, 0, s>>>(h->dev, sinfo, cfg->n_states); break;
+        default: state_info_kernel<5><<<g, kThreads, 0, s>>>(h->dev, sinfo, cfg->n_states); break;
+        }
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, sizeof(mdpp_stats) * kStatSlots);
     if (e != cudaSuccess) {
@@ -310,31 +327,120 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
     return MDPP_OK;
 }
 
-static Accum accum_of(mdpp_handle *h) {
-    Accum a;
-    a.sum = (long long *)(h->ws + h->cv.sum);
-    a.cnt = (uint32_t *)(h->ws + h->cv.cnt);
-    a.last = (float *)(h->ws + h->cv.last);
-    a.touched_bits = (uint32_t *)(h->ws + h->cv.bits);
-    a.touched = (uint32_t *)(h->ws + h->cv.touched);
-    a.visited = (uint32_t *)(h->ws + h->cv.visited);
-    a.capacity = h->cv.touched_capacity;
-    a.replica_mask = h->cv.replicas - 1;
-    a.parity = h->parity;
-    a.n_keys = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW);
-    // scanning keys x replicas is cheaper than keeping a touched list up to ~4M accumulator slots
-    a.dense = ((size_t)a.n_keys * h->cv.replicas <= ((size_t)4 << 20)) ? 1u : 0u;
-    if (const char *env = getenv("MDPP_DENSE")) a.dense = atoi(env) ? 1u : 0u;
-    a.replica_stride = (size_t)h->cfg.n_states * MDPP_Q_ROW;
-    return a;
+static Marks marks_of(mdpp_handle *h) {
+    Marks m{};
+    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
+    const uint32_t p = h->parity;
+    Control *ctl = (Control *)(h->ws + h->cv.control);
+    m.dense = h->cv.dense ? 1u : 0u;
+    if (h->cv.dense) {
+        m.words = (uint32_t *)(h->ws + h->cv.marks) + (size_t)p * keys * h->cv.replicas;
+        m.replica_mask = h->cv.replicas - 1;
+    } else {
+        m.bits = (uint32_t *)(h->ws + h->cv.bits) + (size_t)p * (keys / 32 + 1);
+        m.list = (uint32_t *)(h->ws + h->cv.list) + (size_t)p * h->cv.capacity;
+        m.vals = (float *)(h->ws + h->cv.vals);
+        m.count = &ctl->touched_count[p];
+        m.count_other = &ctl->touched_count[p ^ 1u];
+    }
+    m.visited = (uint32_t *)(h->ws + h->cv.visited);
+    m.sinfo = (const uint32_t *)(h->ws + h->cv.sinfo);
+    m.capacity = h->cv.capacity;
+    m.n_keys = (uint32_t)keys;
+    return m;
 }
 
-int mdpp_q_init(mdpp_handle *h, float *q, void *stream) {
-    if (!h || !q) return fail(MDPP_EINVAL, "handle / q is NULL");
-    if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
-    q_init_kernel<<<grid_for(h->cfg.n_states), kThreads, 0, (cudaStream_t)stream>>>(h->dev, q, h->cfg.n_states);
+// Launch configuration of one learner kernel.  Programmatic dependent launch lets a kernel start while
+// its predecessor drains; every learner kernel orders itself with griddepcontrol.wait.  The first
+// learner kernel after anything else on the stream (reset, a memset, a caller's kernel) is launched
+// with plain stream order: its prologue reads records that predecessor may have written.
+struct LearnLaunch {
+    cudaLaunchAttribute attr;
+    cudaLaunchConfig_t cfg;
+    LearnLaunch(mdpp_handle *h, unsigned grid, cudaStream_t s) {
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = (h->pdl && h->chain) ? 1 : 0;
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = dim3(grid ? grid : 1u);
+        cfg.blockDim = dim3(kThreads);
+        cfg.stream = s;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+    }
+};
+
+static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
+                        const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward,
+                        cudaStream_t s) {
+    // Philox hand-over: the car-0 launch of a round publishes the decision words of cars 1..3
+    int rng_mode = 0;
+    if (h->cfg.n_cars > 1) {
+        if (car_slot == 0) {
+            rng_mode = 1;
+            h->rng_round = round;
+            h->rng_seed = lp->seed;
+        } else if (car_slot < 4 && h->rng_round == round && h->rng_seed == lp->seed) {
+            rng_mode = 2;
+        }
+    }
+    LearnLaunch ll(h, grid_for(h->n_envs), s);
+    const bool plain = !forced && !action_out && !state_idx && !reward && lp->flags == 0;
+    const uint4 *nodetab = (const uint4 *)(h->ws + h->cv.nodetab);
+    uint32_t *rngw = (uint32_t *)(h->ws + h->cv.rng);
+#define MDPP_QENV_C(NCV, CV)                                                                                     \
+    if (plain) MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_env_kernel<NCV, CV, true>, h->dev, recs_of(h), h->n_envs,   \
+            h->env_id_base, round, *lp, q, marks_of(h), nodetab, rngw, rng_mode, forced, action_out,             \
+            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                  \
+    else MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_env_kernel<NCV, CV, false>, h->dev, recs_of(h), h->n_envs,        \
+            h->env_id_base, round, *lp, q, marks_of(h), nodetab, rngw, rng_mode, forced, action_out,             \
+            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));
+#define MDPP_QENV(NCV)                                                                                           \
+    switch (car_slot) {                                                                                          \
+    case 0: MDPP_QENV_C(NCV, 0) break;                                                                           \
+    case 1: if constexpr (NCV > 1) { MDPP_QENV_C(NCV, (NCV > 1 ? 1 : 0)) } break;                                \
+    case 2: if constexpr (NCV > 2) { MDPP_QENV_C(NCV, (NCV > 2 ? 2 : 0)) } break;                                \
+    case 3: if constexpr (NCV > 3) { MDPP_QENV_C(NCV, (NCV > 3 ? 3 : 0)) } break;                                \
+    default: if constexpr (NCV > 4) { MDPP_QENV_C(NCV, (NCV > 4 ? 4 : 0)) } break;                               \
+    }
+    switch (h->cfg.n_cars) {
+    case 1: MDPP_QENV(1) break;
+    case 2: MDPP_QENV(2) break;
+    case 3: MDPP_QENV(3) break;
+    case 4: MDPP_QENV(4) break;
+    default: MDPP_QENV(5) break;
+    }
+#undef MDPP_QENV_C
+#undef MDPP_QENV
+    h->chain = true;
+    return MDPP_OK;
+}
+
+// dense: qsrc -> qdst (whole table, marked keys substituted).  list: in place on qsrc, two passes.
+static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s) {
+    const Marks mk = marks_of(h);
+    if (h->cv.dense) {
+        LearnLaunch ll(h, grid_for(mk.n_keys), s);
+        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
+                                     lp->discount, control_of(h)));
+    } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)mk.capacity + kThreads - 1) / kThreads,
+                                                          (int64_t)h->sm_count * 8);
+        LearnLaunch l1(h, grid, s);
+        MDPP_CUDA(cudaLaunchKernelEx(&l1.cfg, q_pull_list_compute_kernel, (const float *)qsrc, mk, lp->alpha, lp->discount));
+        h->chain = true;
+        LearnLaunch l2(h, grid, s);
+        MDPP_CUDA(cudaLaunchKernelEx(&l2.cfg, q_pull_list_apply_kernel, qsrc, mk, control_of(h)));
+    }
+    h->chain = true;
+    h->parity ^= 1u;
+    return MDPP_OK;
+}
+
+static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStream_t s) {
+    const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
+    q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
     MDPP_CUDA(cudaGetLastError());
-    h->q_inited = q;
+    h->chain = false;
     return MDPP_OK;
 }
 
@@ -343,122 +449,50 @@ int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slo
     if (!h) return fail(MDPP_EINVAL, "handle is NULL");
     if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
     if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
-    cudaStream_t s = (cudaStream_t)stream;
     if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
-    if (h->q_fast) {
-        if (h->q_inited != q) { // slot 5 of every row carries the bad-state flag of that state
-            int rc = mdpp_q_init(h, q, stream);
+    h->chain = false; // the caller may have put anything on the stream since our last launch
+    return q_env_launch(h, q, lp, car_slot, round, forced, action_out, state_idx, reward, (cudaStream_t)stream);
+}
+
+int mdpp_q_finalize(mdpp_handle *h, float *q, const mdpp_learner *lp, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    h->chain = false;
+    float *alt = h->cv.dense ? (float *)(h->ws + h->cv.qalt) : q;
+    int rc = q_pull_launch(h, q, alt, lp, s);
+    if (rc) return rc;
+    if (h->cv.dense) rc = q_copy_launch(h, alt, q, s);
+    h->chain = false;
+    return rc;
+}
+
+int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64_t first_round, int rounds,
+                        void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
+    if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
+    if (lp->flags & MDPP_LEARN_OBSERVED) return fail(MDPP_EINVAL, "MDPP_LEARN_OBSERVED is a per-sub-step flag");
+    cudaStream_t s = (cudaStream_t)stream;
+    h->chain = false;
+    float *cur = q, *alt = h->cv.dense ? (float *)(h->ws + h->cv.qalt) : q; // dense: the table ping-pongs
+    const bool frozen = (lp->flags & MDPP_LEARN_FROZEN) != 0;
+    for (int r = 0; r < rounds; r++)
+        for (int c = 0; c < h->cfg.n_cars; c++) {
+            int rc = q_env_launch(h, cur, lp, c, first_round + (uint64_t)r, nullptr, nullptr, nullptr, nullptr, s);
             if (rc) return rc;
-        }
-        if (h->qf_ctas_per_sm == 0) {
-            int occ = 0;
-            cudaError_t oe;
-            switch (h->cfg.n_cars) {
-            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<1, true>, kThreads, 0); break;
-            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<2, true>, kThreads, 0); break;
-            case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<3, true>, kThreads, 0); break;
-            case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<4, true>, kThreads, 0); break;
-            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_fast_kernel<5, true>, kThreads, 0); break;
+            if (frozen) { // nothing was marked; back-to-back env kernels must not overlap (records)
+                h->chain = false;
+                continue;
             }
-            h->qf_ctas_per_sm = (oe == cudaSuccess && occ > 0) ? occ : 4;
-            // one CTA per 256-env tile by default: the hardware scheduler balances the 4096 tiles better
-            // than a one-wave persistent grid, whose last pass is only half full (measured 8 % slower)
-            h->qf_ctas_per_sm = 1 << 20;
-            if (const char *env = getenv("MDPP_QGRID")) { int g = atoi(env); if (g > 0) h->qf_ctas_per_sm = g; }
+            rc = q_pull_launch(h, cur, alt, lp, s);
+            if (rc) return rc;
+            std::swap(cur, alt);
         }
-        // Philox hand-over: the car-0 launch of a round publishes the decision words of cars 1..3
-        int rng_mode = 0;
-        if (h->cfg.n_cars > 1 && !(getenv("MDPP_RNGCACHE") && atoi(getenv("MDPP_RNGCACHE")) == 0)) {
-            if (car_slot == 0) {
-                rng_mode = 1;
-                h->rng_round = round;
-                h->rng_seed = lp->seed;
-            } else if (car_slot < 4 && h->rng_round == round && h->rng_seed == lp->seed) {
-                rng_mode = 2;
-            }
-        }
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
-        cudaLaunchConfig_t lcf = {};
-        int bs = kThreads;
-        if (const char *env = getenv("MDPP_QTHREADS")) { int t = atoi(env); if (t >= 32 && t <= kThreads && t % 32 == 0) bs = t; }
-        lcf.gridDim = dim3((unsigned)std::min<int64_t>((h->n_envs + bs - 1) / bs, (int64_t)h->sm_count * h->qf_ctas_per_sm));
-        lcf.blockDim = dim3(bs);
-        lcf.stream = s;
-        lcf.attrs = &attr;
-        lcf.numAttrs = 1;
-        const bool plainf = !forced && !action_out && !state_idx && !reward && lp->flags == 0;
-        const uint4 *nodetab = (const uint4 *)(h->ws + h->cv.nodetab);
-        uint32_t *rngw = (uint32_t *)(h->ws + h->cv.rng);
-#define MDPP_QFAST(NCV)                                                                                          \
-        if (plainf) MDPP_CUDA(cudaLaunchKernelEx(&lcf, q_fast_kernel<NCV, true>, h->dev, recs_of(h), h->n_envs,    \
-                h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), nodetab, rngw, rng_mode,    \
-                forced, action_out, state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));          \
-        else MDPP_CUDA(cudaLaunchKernelEx(&lcf, q_fast_kernel<NCV, false>, h->dev, recs_of(h), h->n_envs,         \
-                h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), nodetab, rngw, rng_mode,    \
-                forced, action_out, state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));
-        switch (h->cfg.n_cars) {
-        case 1: MDPP_QFAST(1) break;
-        case 2: MDPP_QFAST(2) break;
-        case 3: MDPP_QFAST(3) break;
-        case 4: MDPP_QFAST(4) break;
-        default: MDPP_QFAST(5) break;
-        }
-#undef MDPP_QFAST
-        MDPP_CUDA(cudaGetLastError());
-        return MDPP_OK;
-    }
-    // GT variant: persistent grid (8 CTAs of 256 threads per SM), tables through L1, no barriers
-    const bool gt = h->q_global_tables;
-    if (gt && h->q_ctas_per_sm == 0) { // persistent grid = exactly the CTAs that are co-resident
-        int occ = 0;
-        cudaError_t oe = cudaSuccess;
-        switch (h->cfg.n_cars) {
-        case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<1, true, true>, kThreads, 0); break;
-        case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<2, true, true>, kThreads, 0); break;
-        case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<3, true, true>, kThreads, 0); break;
-        case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<4, true, true>, kThreads, 0); break;
-        default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, q_substep_kernel<5, true, true>, kThreads, 0); break;
-        }
-        h->q_ctas_per_sm = (oe == cudaSuccess && occ > 0) ? occ : 4;
-        if (const char *env = getenv("MDPP_QGRID")) { int g = atoi(env); if (g > 0) h->q_ctas_per_sm = g; }
-    }
-    const unsigned grid = gt ? (unsigned)std::min<int64_t>(grid_for(h->n_envs), (int64_t)h->sm_count * h->q_ctas_per_sm)
-                             : grid_for(h->n_envs);
-    // Programmatic dependent launch: the kernel's Q-independent prologue (record load, encode, legal
-    // mask, Philox) may overlap the tail of the preceding finalize; it waits (griddepcontrol.wait)
-    // before its first Q read.  MDPP_PDL=0 falls back to plain stream order.
-    cudaLaunchAttribute pdl_attr;
-    pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl_attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kThreads);
-    lc.stream = s;
-    lc.attrs = &pdl_attr;
-    lc.numAttrs = 1;
-    const bool plain = !forced && !action_out && !state_idx && !reward && lp->flags == 0;
-#define MDPP_QSUB(NCV)                                                                                         \
-    if (gt && plain) MDPP_CUDA(cudaLaunchKernelEx(&lc, q_substep_kernel<NCV, true, true>, h->dev, recs_of(h),    \
-            h->n_envs, h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), forced, action_out, \
-            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                \
-    else if (gt) MDPP_CUDA(cudaLaunchKernelEx(&lc, q_substep_kernel<NCV, true, false>, h->dev, recs_of(h),      \
-            h->n_envs, h->env_id_base, car_slot, round, *lp, (const float *)q, accum_of(h), forced, action_out, \
-            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                \
-    else q_substep_kernel<NCV, false, false><<<grid, kThreads, 0, s>>>(h->dev, recs_of(h), h->n_envs, h->env_id_base,  \
-            car_slot, round, *lp, q, accum_of(h), forced, action_out, state_idx, reward,                       \
-            (uint32_t *)(h->ws + h->cv.dl), control_of(h));
-    switch (h->cfg.n_cars) {
-    case 1: MDPP_QSUB(1) break;
-    case 2: MDPP_QSUB(2) break;
-    case 3: MDPP_QSUB(3) break;
-    case 4: MDPP_QSUB(4) break;
-    default: MDPP_QSUB(5) break;
-    }
-#undef MDPP_QSUB
-    MDPP_CUDA(cudaGetLastError());
-    return MDPP_OK;
+    int rc = MDPP_OK;
+    if (cur != q) rc = q_copy_launch(h, cur, q, s); // odd number of sub-steps: bring the table home
+    h->chain = false;
+    return rc;
 }
 
 int mdpp_query_transitions(mdpp_handle *h, int car_slot, int reward_kind, const uint32_t *state_idx,
@@ -545,41 +579,6 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *
         if (sweeps > 100000) return fail(MDPP_ECUDA, "reachability did not converge");
     }
     if (sweeps_out) *sweeps_out = sweeps;
-    return MDPP_OK;
-}
-
-int mdpp_q_finalize(mdpp_handle *h, float *q, void *stream) {
-    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
-    if (!q) return fail(MDPP_EINVAL, "q is NULL");
-    const Accum acf = accum_of(h);
-    unsigned grid = acf.dense ? (unsigned)std::min<int64_t>((acf.n_keys + kThreads - 1) / kThreads, (int64_t)h->sm_count * 4)
-                              : (unsigned)std::min<int64_t>(((int64_t)h->cv.touched_capacity + kThreads - 1) / kThreads,
-                                                            (int64_t)h->sm_count * 8);
-    cudaLaunchAttribute pdl_attr;
-    pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl_attr.val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(std::max(grid, 1u));
-    lc.blockDim = dim3(kThreads);
-    lc.stream = (cudaStream_t)stream;
-    lc.attrs = &pdl_attr;
-    lc.numAttrs = 1;
-    MDPP_CUDA(cudaLaunchKernelEx(&lc, q_finalize_kernel, q, accum_of(h), control_of(h)));
-    MDPP_CUDA(cudaGetLastError());
-    h->parity ^= 1u;
-    return MDPP_OK;
-}
-
-int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64_t first_round, int rounds,
-                        void *stream) {
-    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
-    for (int r = 0; r < rounds; r++)
-        for (int c = 0; c < h->cfg.n_cars; c++) {
-            int rc = mdpp_q_substep(h, q, lp, c, first_round + (uint64_t)r, nullptr, nullptr, nullptr, nullptr, stream);
-            if (rc) return rc;
-            rc = mdpp_q_finalize(h, q, stream);
-            if (rc) return rc;
-        }
     return MDPP_OK;
 }
 

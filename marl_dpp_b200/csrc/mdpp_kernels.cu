@@ -269,434 +269,11 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// learner: fused epsilon-greedy select + env step + TD accumulate
+// learner: epsilon-greedy select + env step + key marks, and the pull kernels that apply the update
 // ------------------------------------------------------------------------------------------------
-using LearnArgs = mdpp_learner;
-
-struct Accum {
-    long long *sum;        // [n_states*8] fixed-point sums of the per-env new values
-    uint32_t *cnt;         // [n_states*8] contributors
-    float *last;           // [n_states*8] the value itself, exact when cnt ends at 1
-    uint32_t *touched_bits;// [n_states*8/32] key touched in this sub-step
-    uint32_t *touched;     // [capacity] list of touched keys
-    uint32_t *visited;     // [n_states] bit a = (state, a) has been updated at least once
-    uint32_t capacity;
-    // sum/cnt are privatised: CTA b accumulates into replica (b & replica_mask), so that a hot key is
-    // spread over up to 64 L2 addresses instead of serialising every env of the batch on one
-    uint32_t replica_mask;
-    uint32_t parity;       // which touched_count the current sub-step uses
-    uint32_t dense;        // small table: finalize scans every key, no touched list is kept
-    uint32_t n_keys;
-    size_t replica_stride; // in keys
-};
-
-// epsilon schedule (reference src/utils/utils.py:33-52, model 3) on the per-env episode counter
-__device__ __forceinline__ uint32_t eps_q16_of(const LearnArgs &lp, int32_t episode) {
-    uint32_t e = lp.eps_q16[5];
-#pragma unroll
-    for (int i = 4; i >= 0; i--)
-        if (episode < lp.eps_threshold[i]) e = lp.eps_q16[i];
-    return e;
-}
-
-// GT = tables read from global memory through L1 (no shared copy, no barrier, per-warp stats flush) and
-// a grid-stride loop over env tiles; GT = false keeps the shared-memory variant for comparison.
-// PLAIN = the training fast path: no forced actions, no per-env outputs, no learner flags -- those
-// branches fold away at compile time.
-template <int NC, bool GT, bool PLAIN>
-__global__ void __launch_bounds__(kThreads)
-q_substep_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c,
-                 uint64_t round, LearnArgs lp, const float *__restrict__ q, Accum ac,
-                 const uint8_t *__restrict__ forced, uint8_t *__restrict__ action_out,
-                 uint32_t *__restrict__ state_out, float *__restrict__ reward_out,
-                 uint32_t *__restrict__ dl_state, Control *ctl) {
-    __shared__ SmemTables sm;
-    __shared__ SmemStats ss;
-    if constexpr (!GT) {
-        zero_stats(ss);
-        load_tables(sm, cfg.tables);
-    }
-    const uint32_t lflags = PLAIN ? 0u : lp.flags;
-    if constexpr (PLAIN) { forced = nullptr; action_out = nullptr; state_out = nullptr; reward_out = nullptr; }
-    const AnyTab<GT> tab{GT ? reinterpret_cast<const SmemTables *>(cfg.tables) : &sm};
-    // PDL: let the finalize that follows be scheduled as soon as SM slots free up (it waits for this
-    // grid to complete before touching the accumulators)
-    pdl_launch_dependents();
-    // whole warps iterate together (n_envs is padded to the warp by the bound check inside)
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_envs; base += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = base + threadIdx.x;
-    StatAcc acc;
-    int64_t rsum = 0;
-    if (e < n_envs) {
-        uint4 rec = recs[e];
-        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
-        const uint32_t env = env_id_base + (uint32_t)e;
-        uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
-        float r_out = 0.f;
-        const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
-        // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
-        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
-        if (live && !f_done(car_field(cars, c))) {
-            View v = view_of<NC>(cars, c, mode, cfg);
-            const uint32_t lm = legal_mask(v, v.pnode, tab);
-            const uint32_t sidx = state_index(v, v.pnode, cfg);
-            s_out = sidx;
-            uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
-            const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
-            if (lm && forced_ok) {
-                // ---- getaction (reference src/algorithms/qlearning.py:74-105) ----
-                // everything above (record, encode, legal mask) is independent of the Q table and may
-                // have overlapped the preceding finalize; from here on its writes must be visible
-                pdl_wait();
-                float qs[MDPP_Q_ROW];
-                ldg_row(q + (size_t)sidx * MDPP_Q_ROW, qs); // one 256-bit load = the whole 32-byte row
-                uint32_t a;
-                bool explore;
-                const uint32_t eps16 = eps_q16_of(lp, (int32_t)episode);
-                if (f == MDPP_ACT_GREEDY) {
-                    a = 0;
-                    explore = false;
-                } else if (f != MDPP_ACT_SKIP) {
-                    a = f;
-                    explore = true;
-                } else {
-                    uint32_t w = decision_word(round, c, lp.seed, env);
-                    explore = (w >> 16) < eps16; // flipcoin (utils.py:255-265)
-                    a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
-                }
-                if (!explore) { // computeactionfromqvalues: first maximum in S,L,R,F,T order (:659-667)
-                    float best = 0.f;
-                    bool have = false;
-#pragma unroll
-                    for (int k = 0; k < MDPP_N_ACT; k++) {
-                        bool ok = (lm >> k) & 1u;
-                        if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
-                    }
-                }
-                acc.explore += explore;
-                // ---- stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360): 3*n_cars consecutive
-                // 'S' actions while epsilon == 0 flag the state; the env stops there (the reference returns)
-                bool stalled = false;
-                if (lflags & MDPP_LEARN_DETECT) {
-                    uint32_t run = rec.w & 0xFFu;
-                    run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
-                    stalled = run == 3u * NC;
-                    rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
-                    if (stalled) {
-                        dl_state[e] = sidx;
-                        episode = (uint32_t)lp.episodes; // frozen from now on
-                    }
-                }
-                if (!stalled) {
-                // ---- env step ----
-                const uint32_t nn = next_node(v.pnode, a, tab);
-                const int32_t ri = reward_int<NC>(v, nn, cars, c, MDPP_REWARD_Q, cfg, tab);
-                // ---- update (qlearning.py:107-116): value of the successor STATE STRING, same others ----
-                const uint32_t nidx = state_index(v, nn, cfg);
-                const uint32_t lm2 = legal_mask(v, nn, tab);
-                float ns[MDPP_Q_ROW];
-                ldg_row(q + (size_t)nidx * MDPP_Q_ROW, ns);
-                float nv = 0.f;
-                bool have = false;
-#pragma unroll
-                for (int k = 0; k < MDPP_N_ACT; k++) {
-                    bool ok = (lm2 >> k) & 1u;
-                    if (ok && (!have || ns[k] > nv)) { nv = ns[k]; have = true; }
-                }
-                float qa = qs[0];
-#pragma unroll
-                for (int k = 1; k < MDPP_N_ACT; k++) qa = (a == (uint32_t)k) ? qs[k] : qa;
-                // explicit roundings: the same operation order as the reference expression, no FMA
-                const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
-                const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
-                // ---- accumulate: mean over the envs that update this key in this sub-step ----
-                if (!(lflags & MDPP_LEARN_FROZEN)) {
-                const uint32_t key = sidx * MDPP_Q_ROW + a;
-                const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
-                const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
-                atomicAdd((unsigned long long *)(ac.sum + rkey), (unsigned long long)fx);
-                // the count comes back: the first contributor of a (replica, key) leaves the value itself
-                // (exact result when it stays alone) and, for tables too big to scan, lists the key
-                if (atomicAdd(ac.cnt + rkey, 1u) == 0u) {
-                    ac.last[key] = newv;
-                    if (!ac.dense) {
-                        const uint32_t bit = 1u << (key & 31u);
-                        if (!(atomicOr(ac.touched_bits + (key >> 5), bit) & bit)) {
-                            uint32_t slot = atomicAdd(&ctl->touched_count[ac.parity], 1u);
-                            if (slot < ac.capacity) ac.touched[slot] = key;
-                        }
-                    }
-                }
-                }
-                cars = advance_car(cars, c, v, nn, cfg);
-                steps = steps < 0xFFFFu ? steps + 1 : steps;
-                acc.steps = 1;
-                rsum = ri;
-                r_out = (float)ri;
-                }
-                a_out = a;
-            }
-        }
-        if (live && c == NC - 1) { // end of the round-robin round (qlearning.py:233)
-            bool finished = all_done<NC>(cars);
-            bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
-            if (finished || capped) {
-                acc.episodes = 1;
-                acc.capped = capped;
-                episode = episode + 1;
-                steps = 0;
-                rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
-                cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
-            }
-        }
-        if (live) {
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
-            rec.z = (episode & 0xFFFFu) | (steps << 16);
-            recs[e] = rec;
-        }
-        if (action_out) action_out[e] = (uint8_t)a_out;
-        if (state_out) state_out[e] = s_out;
-        if (reward_out) reward_out[e] = r_out;
-    }
-    if constexpr (GT) {
-        if (lflags & MDPP_LEARN_FROZEN) flush_stats_warp<false>(acc, rsum, ctl);
-        else flush_stats_warp<true>(acc, rsum, ctl);
-    } else {
-        if (lflags & MDPP_LEARN_FROZEN) flush_stats<true, false>(acc, rsum, ctl, ss);
-        else flush_stats<true, true>(acc, rsum, ctl, ss);
-    }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// learner, fast variant (default).  Same semantics as q_substep_kernel, fewer memory requests and
-// instructions per agent-step (the kernel is bound by instruction issue and L1 wavefronts, not HBM):
-//   * one 16-byte table entry per node (BFS lengths to every destination, F successor, base legal
-//     mask) read with a single LDG.128 -> 2 table loads per step instead of 5;
-//   * the bad-state bit of a state rides in slot 5 of its Q row (written once by q_init_kernel), so
-//     the two bad-states probes cost nothing: both rows are loaded anyway;
-//   * the Philox block of a round is computed once, by the car-0 launch, and the decision words of
-//     cars 1..3 are handed over through a coalesced side array.
-// ------------------------------------------------------------------------------------------------
-struct NodeEnt {
-    uint4 v; // bytes 0-7: bfs_len to destination node 0..7, byte 8: F successor, byte 9: base legal mask
-    __device__ __forceinline__ uint32_t bfs(uint32_t d) const {
-        return (uint32_t)((((unsigned long long)v.y << 32) | v.x) >> (8u * d)) & 0xFFu;
-    }
-    __device__ __forceinline__ uint32_t fwd() const { return v.z & 0xFFu; }
-    __device__ __forceinline__ uint32_t base() const { return (v.z >> 8) & 0xFFu; }
-};
-__device__ __forceinline__ NodeEnt load_ent(const uint4 *__restrict__ tab, uint32_t node) {
-    NodeEnt e;
-    e.v = __ldg(tab + node);
-    return e;
-}
-__device__ __forceinline__ uint32_t legal_mask_ent(const View &v, uint32_t node, const NodeEnt &ent) {
-    uint32_t mask = ent.base();
-    if ((v.occ9 >> boxnum0(node >> 2)) & 1u) mask &= 1u << MDPP_A_F;
-    if (mask & (1u << MDPP_A_F)) {
-        const uint32_t fb = ent.fwd() >> 2;
-        bool blocked = (v.occ9 >> boxnum0(fb)) & 1u;
-        blocked = blocked || (((v.sel >> fb) & 1u) && (v.sel & v.occ18));
-        if (blocked) mask &= ~(1u << MDPP_A_F);
-    }
-    return mask;
-}
-
-// slot 5 of every Q row <- 1.0f iff the heading-stripped state is in the bad-states set (else 0.0f).
-// Identical in every replica, so an all-reduce average leaves it intact.
-__global__ void __launch_bounds__(kThreads)
-q_init_kernel(DevCfg cfg, float *__restrict__ q, int64_t n_states) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_states) return;
-    float flag = 0.f;
-    if (cfg.bad_on) {
-        const uint32_t nl = (uint32_t)(s % cfg.n_local_nodes), t = (uint32_t)(s / cfg.n_local_nodes);
-        const uint32_t dnidx = t % cfg.n_dest_nodes, rank = t / cfg.n_dest_nodes;
-        const uint32_t id = (rank * cfg.n_dest_boxes + cfg.dn_dbox[dnidx]) * cfg.n_src_boxes +
-                            (((nl + cfg.node_base) >> 2) - cfg.box_base);
-        flag = ((__ldg(cfg.bad_bitmap + (id >> 5)) >> (id & 31u)) & 1u) ? 1.f : 0.f;
-    }
-    q[s * MDPP_Q_ROW + 5] = flag;
-}
-
-// rng_mode: 0 = compute the Philox block here; 1 = car-0 launch: compute it for every live env and
-// publish the words of cars 1..3; 2 = read this car's word from the side array.
-template <int NC, bool PLAIN>
-__global__ void __launch_bounds__(kThreads)   // 54 registers; capping at 51 (5 CTAs/SM) or 40 (6) measured 4-10 % slower
-q_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c, uint64_t round,
-              LearnArgs lp, const float *__restrict__ q, Accum ac, const uint4 *__restrict__ nodetab,
-              uint32_t *__restrict__ rng_words, int rng_mode, const uint8_t *__restrict__ forced,
-              uint8_t *__restrict__ action_out, uint32_t *__restrict__ state_out, float *__restrict__ reward_out,
-              uint32_t *__restrict__ dl_state, Control *ctl) {
-    const uint32_t lflags = PLAIN ? 0u : lp.flags;
-    if constexpr (PLAIN) { forced = nullptr; action_out = nullptr; state_out = nullptr; reward_out = nullptr; }
-    pdl_launch_dependents();
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_envs; base += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = base + threadIdx.x;
-    StatAcc acc;
-    int64_t rsum = 0;
-    if (e < n_envs) {
-        uint4 rec = recs[e];
-        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
-        const uint32_t env = env_id_base + (uint32_t)e;
-        uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
-        float r_out = 0.f;
-        const bool live = (int32_t)episode < lp.episodes;
-        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
-        uint32_t word = 0;
-        if (rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
-            if (live) {
-                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
-                word = p.x;
-                if (NC > 1) rng_words[e] = p.y;
-                if (NC > 2) rng_words[(size_t)n_envs + e] = p.z;
-                if (NC > 3) rng_words[2 * (size_t)n_envs + e] = p.w;
-            }
-        } else if (rng_mode == 2) {
-            word = rng_words[(size_t)(c - 1) * n_envs + e];
-        }
-        if (live && !f_done(car_field(cars, c))) {
-            View v = view_of<NC>(cars, c, mode, cfg);
-            const NodeEnt entP = load_ent(nodetab, v.pnode);
-            const uint32_t lm = legal_mask_ent(v, v.pnode, entP);
-            const uint32_t sidx = state_index(v, v.pnode, cfg);
-            s_out = sidx;
-            uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
-            const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
-            if (lm && forced_ok) {
-                pdl_wait(); // first Q read: the preceding finalize must be complete
-                float qs[MDPP_Q_ROW];
-                ldg_row(q + (size_t)sidx * MDPP_Q_ROW, qs);
-                uint32_t a;
-                bool explore;
-                const uint32_t eps16 = eps_q16_of(lp, (int32_t)episode);
-                if (f == MDPP_ACT_GREEDY) {
-                    a = 0;
-                    explore = false;
-                } else if (f != MDPP_ACT_SKIP) {
-                    a = f;
-                    explore = true;
-                } else {
-                    const uint32_t w = rng_mode ? word : decision_word(round, c, lp.seed, env);
-                    explore = (w >> 16) < eps16;
-                    a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
-                }
-                if (!explore) {
-                    float best = 0.f;
-                    bool have = false;
-#pragma unroll
-                    for (int k = 0; k < MDPP_N_ACT; k++) {
-                        bool ok = (lm >> k) & 1u;
-                        if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
-                    }
-                }
-                acc.explore += explore;
-                bool stalled = false;
-                if (lflags & MDPP_LEARN_DETECT) {
-                    uint32_t run = rec.w & 0xFFu;
-                    run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
-                    stalled = run == 3u * NC;
-                    rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
-                    if (stalled) {
-                        dl_state[e] = sidx;
-                        episode = (uint32_t)lp.episodes;
-                    }
-                }
-                if (!stalled) {
-                    // The contributor count is bumped as soon as the key is known: its round trip to L2
-                    // then overlaps the successor-row gather and the TD arithmetic instead of stalling the
-                    // warp at the very end (the returning atomic was 26 % of all stall samples there).
-                    const uint32_t key = sidx * MDPP_Q_ROW + a;
-                    const size_t rkey = (size_t)(blockIdx.x & ac.replica_mask) * ac.replica_stride + key;
-                    bool first = false;
-                    if (!(lflags & MDPP_LEARN_FROZEN)) first = atomicAdd(ac.cnt + rkey, 1u) == 0u;
-                    const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
-                    const uint32_t nn = a == MDPP_A_F ? entP.fwd() : ((v.pnode & ~3u) | ((v.pnode + rot) & 3u));
-                    const NodeEnt entN = load_ent(nodetab, nn);
-                    const uint32_t nidx = state_index(v, nn, cfg);
-                    const uint32_t lm2 = legal_mask_ent(v, nn, entN);
-                    float ns[MDPP_Q_ROW];
-                    ldg_row(q + (size_t)nidx * MDPP_Q_ROW, ns);
-                    // q_reward (src/env_gym.py:555-620); the bad-state bits came with the two rows
-                    int32_t ri;
-                    if (cfg.bad_on && ns[5] != 0.f) ri = -10000;
-                    else if (cfg.bad_on && qs[5] != 0.f) ri = 0;
-                    else {
-                        ri = -10 + 50 * ((int32_t)entP.bfs(v.dnidx) - (int32_t)entN.bfs(v.dnidx));
-                        if (nn == v.dnode) ri += 10010;
-                        int32_t clash = 0;
-#pragma unroll
-                        for (int i = 0; i < NC; i++)
-                            if (i != c) clash += ((f_node(car_field(cars, i)) >> 2) == (nn >> 2));
-                        ri -= clash * 100000;
-                    }
-                    float nv = 0.f;
-                    bool have = false;
-#pragma unroll
-                    for (int k = 0; k < MDPP_N_ACT; k++) {
-                        bool ok = (lm2 >> k) & 1u;
-                        if (ok && (!have || ns[k] > nv)) { nv = ns[k]; have = true; }
-                    }
-                    float qa = qs[0];
-#pragma unroll
-                    for (int k = 1; k < MDPP_N_ACT; k++) qa = (a == (uint32_t)k) ? qs[k] : qa;
-                    const float target = __fadd_rn((float)ri, __fmul_rn(lp.discount, nv));
-                    const float newv = __fadd_rn(qa, __fmul_rn(lp.alpha, __fsub_rn(target, qa)));
-                    if (!(lflags & MDPP_LEARN_FROZEN)) {
-                        const long long fx = __float2ll_rn(newv * (float)(1 << MDPP_FIXED_SHIFT));
-                        atomicAdd((unsigned long long *)(ac.sum + rkey), (unsigned long long)fx);
-                        // the first contributor of a (replica, key) leaves the value itself (exact result
-                        // when it stays alone) and, for tables too big to scan, lists the key
-                        if (first) {
-                            ac.last[key] = newv;
-                            if (!ac.dense) {
-                                const uint32_t bit = 1u << (key & 31u);
-                                if (!(atomicOr(ac.touched_bits + (key >> 5), bit) & bit)) {
-                                    uint32_t slot = atomicAdd(&ctl->touched_count[ac.parity], 1u);
-                                    if (slot < ac.capacity) ac.touched[slot] = key;
-                                }
-                            }
-                        }
-                    }
-                    cars = advance_car(cars, c, v, nn, cfg);
-                    steps = steps < 0xFFFFu ? steps + 1 : steps;
-                    acc.steps = 1;
-                    rsum = ri;
-                    r_out = (float)ri;
-                }
-                a_out = a;
-            }
-        }
-        if (live && c == NC - 1) {
-            bool finished = all_done<NC>(cars);
-            bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
-            if (finished || capped) {
-                acc.episodes = 1;
-                acc.capped = capped;
-                episode = episode + 1;
-                steps = 0;
-                rec.w &= ~0xFFu;
-                cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
-            }
-        }
-        if (live) {
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
-            rec.z = (episode & 0xFFFFu) | (steps << 16);
-            recs[e] = rec;
-        }
-        if (action_out) action_out[e] = (uint8_t)a_out;
-        if (state_out) state_out[e] = s_out;
-        if (reward_out) reward_out[e] = r_out;
-    }
-    if (lflags & MDPP_LEARN_FROZEN) flush_stats_warp<false>(acc, rsum, ctl);
-    else flush_stats_warp<true>(acc, rsum, ctl);
-    }
-}
+} // namespace mdpp
+#include "q_learner.cuh" // needs Control / StatAcc / flush_stats_warp from above
+namespace mdpp {
 
 // ------------------------------------------------------------------------------------------------
 // string-API support (n_envs small): evaluate a transition from an ARBITRARY state id, and the bare
@@ -794,92 +371,29 @@ update_car_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, c
     recs[e] = rec;
 }
 
-// finalize: per touched key write the mean of the accumulated values (the value itself when one
-// env contributed), clear the accumulators, record the visited bit used by the qvalue file writer.
-__device__ __forceinline__ void finalize_key(float *__restrict__ q, const Accum &ac, uint32_t key, long long s,
-                                             uint32_t cnt) {
-    float v;
-    if (cnt == 1u) {
-        v = ac.last[key];
-    } else {
-        const double mean = (double)s / ((double)cnt * (double)(1 << MDPP_FIXED_SHIFT));
-        v = (float)mean;
-    }
-    q[key] = v;
-    uint32_t *vis = ac.visited + (key >> 3);
-    const uint32_t vb = 1u << (key & 7u);
-    if (!(*vis & vb)) atomicOr(vis, vb);
-}
-
+// per-state info words for the pull kernels (q_learner.cuh): everything the reference update of a key
+// needs besides the two Q rows, precomputed once per handle from the state id alone.
+template <int NC>
 __global__ void __launch_bounds__(kThreads)
-q_finalize_kernel(float *__restrict__ q, Accum ac, Control *ctl) {
-    pdl_wait();              // the sub-step that filled the accumulators has completed
-    pdl_launch_dependents(); // the next sub-step may start its Q-independent prologue now
-    if (ac.dense) {
-        // small table: one thread per key, coalesced sweep over the replicas
-        uint32_t touched = 0;
-        for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < ac.n_keys; key += gridDim.x * blockDim.x) {
-            if ((key & 7u) >= MDPP_N_ACT) continue;
-            long long s = 0;
-            uint32_t cnt = 0;
-            for (uint32_t r0 = 0; r0 <= ac.replica_mask; r0 += 8u) { // 8 independent count loads in flight
-                uint32_t c[8];
-#pragma unroll
-                for (uint32_t j = 0; j < 8u; j++)
-                    c[j] = (r0 + j <= ac.replica_mask) ? ac.cnt[(size_t)(r0 + j) * ac.replica_stride + key] : 0u;
-#pragma unroll
-                for (uint32_t j = 0; j < 8u; j++) {
-                    if (c[j]) {
-                        const size_t rkey = (size_t)(r0 + j) * ac.replica_stride + key;
-                        cnt += c[j];
-                        s += ac.sum[rkey];
-                        ac.cnt[rkey] = 0;
-                        ac.sum[rkey] = 0;
-                    }
-                }
-            }
-            if (cnt) {
-                finalize_key(q, ac, key, s, cnt);
-                touched++;
-            }
-        }
-        touched = __reduce_add_sync(0xFFFFFFFFu, touched);
-        if ((threadIdx.x & 31u) == 0 && touched)
-            atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
-                      (unsigned long long)touched);
-        return;
+state_info_kernel(DevCfg cfg, uint32_t *__restrict__ sinfo, int64_t n_states) {
+    __shared__ SmemTables sm;
+    load_tables(sm, cfg.tables);
+    const SharedTab tab{&sm};
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_states) return;
+    const View v = view_from_state<NC>((uint32_t)s, cfg);
+    const uint32_t lm = legal_mask(v, v.pnode, tab);
+    const uint32_t fwd = tab.info(v.pnode) & 0xFFu;
+    const uint32_t fwd_local = (fwd == kNone || fwd < (uint32_t)cfg.node_base ||
+                                fwd - (uint32_t)cfg.node_base >= (uint32_t)cfg.n_local_nodes)
+                                   ? 127u : fwd - (uint32_t)cfg.node_base;
+    uint32_t bad = 0;
+    if (cfg.bad_on) {
+        const uint32_t id = (v.rank * cfg.n_dest_boxes + v.dbox) * cfg.n_src_boxes + ((v.pnode >> 2) - cfg.box_base);
+        bad = (__ldg(cfg.bad_bitmap + (id >> 5)) >> (id & 31u)) & 1u;
     }
-    // large table: one THREAD per listed key (a warp per key left 31 lanes idle behind a chain of
-    // dependent L2/DRAM loads: 35-49 us for 22 k keys on the 4-car table)
-    const uint32_t n = min(ctl->touched_count[ac.parity], ac.capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = ac.touched[i];
-        long long s = 0;
-        uint32_t cnt = 0;
-        for (uint32_t r0 = 0; r0 <= ac.replica_mask; r0 += 8u) {
-            uint32_t c[8];
-#pragma unroll
-            for (uint32_t j = 0; j < 8u; j++)
-                c[j] = (r0 + j <= ac.replica_mask) ? ac.cnt[(size_t)(r0 + j) * ac.replica_stride + key] : 0u;
-#pragma unroll
-            for (uint32_t j = 0; j < 8u; j++) {
-                if (c[j]) {
-                    const size_t rkey = (size_t)(r0 + j) * ac.replica_stride + key;
-                    cnt += c[j];
-                    s += ac.sum[rkey];
-                    ac.cnt[rkey] = 0;
-                    ac.sum[rkey] = 0;
-                }
-            }
-        }
-        finalize_key(q, ac, key, s, cnt);
-        // several listed keys can share a bitmap word: clear only this key's bit
-        atomicAnd(ac.touched_bits + (key >> 5), ~(1u << (key & 31u)));
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        ctl->touched_count[ac.parity ^ 1u] = 0;
-        if (n) atomicAdd((unsigned long long *)&ctl->stats[0].touched_keys, (unsigned long long)n);
-    }
+    sinfo[s] = lm | (fwd_local << 5) | (tab.bfs(v.dnidx, v.pnode) << 12) | (bad << 20) |
+               ((uint32_t)(v.pnode == v.dnode) << 21) | ((v.pnode - (uint32_t)cfg.node_base) << 22);
 }
 
 // ------------------------------------------------------------------------------------------------

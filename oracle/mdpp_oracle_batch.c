@@ -6,8 +6,13 @@
  * decisions drawn from Philox4x32-10 keyed (seed, env id) with counter (round, stream), per-env
  * episode counters driving the reference's epsilon schedule, auto-reset at the end of a round,
  * and -- for the learner -- every env of a sub-step reading the Q table as it was when the
- * sub-step began, with each touched key receiving the mean (fixed point, 18 fraction bits) of
- * the values the contributing envs computed (the value itself when one env contributed).
+ * sub-step began, with each touched key receiving the value its contributing envs computed.  All
+ * contributors of one key compute the SAME value: (state, action) fixes the successor state string,
+ * the reward (the clash term is 0 under legal actions: a listed car blocks its box number, a finished
+ * car is parked on a no-box node) and both Q rows are read from the same snapshot.  The batch
+ * definition is therefore "the value" -- formally the maximum, so that it stays order-independent
+ * should the claim ever fail; orc_batch_disagreements() counts keys whose contributors differed and
+ * the tests assert it stays 0.
  * The per-env pieces are the reference-pinned scalar functions; nothing here is shared with the
  * product code.  pthreads spread envs over host cores for the CPU baseline in bench.py.
  */
@@ -41,6 +46,8 @@ typedef struct {
     /* stats */
     uint64_t agent_steps, episodes_done, episodes_capped, explore_steps;
     int64_t reward_sum;
+    uint64_t disagreements; /* (sub-step, key) groups whose contributors computed different values */
+    uint64_t touched_keys;  /* distinct keys written, summed over sub-steps */
 } orc_batch;
 
 static void init_env(orc_batch *b, int64_t e, uint32_t heading_bits) {
@@ -88,6 +95,8 @@ orc_env *orc_batch_env(orc_batch *b, int64_t e) { return b->envs[e]; }
 int32_t orc_batch_episode(const orc_batch *b, int64_t e) { return b->episode[e]; }
 int32_t orc_batch_steps(const orc_batch *b, int64_t e) { return b->steps[e]; }
 const orc_state *orc_batch_deadlock_state(const orc_batch *b, int64_t e) { return &b->dl_state[e]; }
+uint64_t orc_batch_disagreements(const orc_batch *b) { return b->disagreements; }
+uint64_t orc_batch_touched_keys(const orc_batch *b) { return b->touched_keys; }
 void orc_batch_stats(const orc_batch *b, uint64_t *out5) {
     out5[0] = b->agent_steps;
     out5[1] = b->episodes_done;
@@ -351,25 +360,31 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
         if (state_out) state_out[e] = st;
         if (reward_out) reward_out[e] = r_out;
     }
-    /* phase 2: per key, mean of the contributed values in 2^-18 fixed point; exact when alone */
+    /* phase 2: per key, the value the contributing envs computed (identical for all of them;
+     * formally the maximum) */
     int64_t nq = orc_q_size(q);
-    int64_t *sum = (int64_t *)calloc((size_t)nq, sizeof(int64_t));
     uint32_t *cnt = (uint32_t *)calloc((size_t)nq, sizeof(uint32_t));
-    float *last = (float *)calloc((size_t)nq, sizeof(float));
+    float *val = (float *)calloc((size_t)nq, sizeof(float));
+    uint8_t *differ = (uint8_t *)calloc((size_t)nq, 1);
     for (int64_t e = 0; e < b->n_envs; e++) {
         if (pend[e].key < 0) continue;
-        sum[pend[e].key] += (int64_t)llrintf(pend[e].newv * 262144.0f);
-        cnt[pend[e].key] += 1;
-        last[pend[e].key] = pend[e].newv;
+        const int64_t k = pend[e].key;
+        if (cnt[k] == 0) val[k] = pend[e].newv;
+        else if (pend[e].newv != val[k]) {
+            differ[k] = 1;
+            if (pend[e].newv > val[k]) val[k] = pend[e].newv;
+        }
+        cnt[k] += 1;
     }
     for (int64_t k = 0; k < nq; k++) {
         if (!cnt[k]) continue;
-        float v = cnt[k] == 1 ? last[k] : (float)((double)sum[k] / ((double)cnt[k] * 262144.0));
-        orc_q_set_at(q, k, (double)v);
+        b->touched_keys++;
+        b->disagreements += differ[k];
+        orc_q_set_at(q, k, (double)val[k]);
     }
-    free(sum);
     free(cnt);
-    free(last);
+    free(val);
+    free(differ);
     free(pend);
 }
 

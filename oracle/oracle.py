@@ -344,6 +344,10 @@ def _batch_lib():
         L.orc_batch_q_substep.argtypes = [P, P, C.POINTER(Learner), C.c_int, C.c_uint64, P, P, P, P]
         L.orc_batch_q_round.restype = None
         L.orc_batch_q_round.argtypes = [P, P, C.POINTER(Learner), C.c_uint64]
+        L.orc_batch_disagreements.restype = C.c_uint64
+        L.orc_batch_disagreements.argtypes = [P]
+        L.orc_batch_touched_keys.restype = C.c_uint64
+        L.orc_batch_touched_keys.argtypes = [P]
         _batch_sigs_done = True
     return L
 
@@ -408,6 +412,14 @@ class Batch:
 
     def q_round(self, q, lp, rnd):
         _batch_lib().orc_batch_q_round(self.h, q.h, C.byref(lp), rnd)
+
+    def disagreements(self):
+        """(sub-step, key) groups whose contributing envs computed different values; the batch
+        semantics rest on this being 0 (see the header of mdpp_oracle_batch.c)."""
+        return int(_batch_lib().orc_batch_disagreements(self.h))
+
+    def touched_keys(self):
+        return int(_batch_lib().orc_batch_touched_keys(self.h))
 
     def env_cars(self, e):
         L = lib()

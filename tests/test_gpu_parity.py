@@ -218,6 +218,11 @@ QBATCH = [
     ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 400, 512, 40, 300),
     ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 0, 256, 30, 200),
     ("b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 300, 384, 30, 150),
+    # 1.65 M states: touched bitmap + list + two-pass pull instead of the dense ping-pong
+    ("b2_4car_bad_list", 2, ["D2", "D6", "D4", "D8"], [0, 0, 0, 0], [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]],
+     True, 300, 320, 20, 80),
+    # the same small table forced through the list path
+    ("b2_2car_bad_forced_list", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 400, 512, 40, 120),
 ]
 
 
@@ -227,10 +232,15 @@ def test_batched_qlearning_matches_oracle(case):
     episode budget: per-sub-step actions and the final table are bit-identical to the oracle's
     restatement of the batch semantics."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
-    _, block, boxes, idx, choose, bad, cap, n, episodes, rounds = case
+    name, block, boxes, idx, choose, bad, cap, n, episodes, rounds = case
     badtxt = bad_states_text(block) if bad else None
     sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
-    env = BatchedEnv(sc, n, seed=5)
+    if name.endswith("forced_list"):
+        os.environ["MDPP_DENSE"] = "0"
+    try:
+        env = BatchedEnv(sc, n, seed=5)
+    finally:
+        os.environ.pop("MDPP_DENSE", None)
     lr = BatchedQLearner(env, episodes=episodes, seed=5)
     ob = orc.Batch(orc.Config(m.layout_3[block]), n, boxes, idx, choose, badtxt, cap)
     ob.reset(seed=5)
@@ -256,6 +266,9 @@ def test_batched_qlearning_matches_oracle(case):
     for k in ("agent_steps", "episodes_done", "episodes_capped", "reward_sum", "explore_steps"):
         assert gs[k] == ws[k], k
     assert gs["q_updates"] == gs["agent_steps"]
+    # the batch definition rests on every contributor of a key computing the same value
+    assert ob.disagreements() == 0
+    assert gs["touched_keys"] == ob.touched_keys()
     # the fused multi-round entry point continues identically
     lr.train_rounds(5)
     for r in range(rounds, rounds + 5):

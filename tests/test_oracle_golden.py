@@ -215,3 +215,31 @@ def test_float32_oracle_tracks_float64_reference_within_1e5():
     assert set(got) <= set(want)
     for k, v in got.items():
         assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
+
+
+BATCH_CLAIM = [
+    (2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 1024, 150, 0),
+    (2, ["D2", "D6", "D4", "D8"], [0, 0, 0, 0], [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 512, 120, 0),
+    (0, ["U4", "U8", "U5", "U7"], [0, 1, 0, 0], [[0, 0, 0]] * 4, False, 512, 120, 0),
+    (2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 512, 150, 2 | 4),  # encodestate(.,0) + stall detection
+]
+
+
+@pytest.mark.parametrize("case", BATCH_CLAIM, ids=lambda c: "b%d_%dcar_f%d" % (c[0], len(c[1]), c[7]))
+def test_batch_contributors_of_a_key_agree(case):
+    """The batch semantics define the value a touched key receives as "the value its contributing
+    envs computed": (state, action) and the table snapshot determine it (the reward's clash term is
+    0 under legal actions).  The oracle computes every contributor's value independently from its
+    own env and counts the keys whose contributors differ: there must be none."""
+    import marl_dpp_b200 as m
+    block, boxes, idx, choose, bad, n, rounds, flags = case
+    badtxt = bad_states_text(block) if bad else None
+    b = orc.Batch(orc.Config(m.layout_3[block]), n, boxes, idx, choose, badtxt, 300)
+    b.reset(seed=21)
+    q = orc.QTable(f32=True)
+    lp = orc.learner(6, seed=21, flags=flags)
+    for r in range(rounds):
+        b.q_round(q, lp, r)
+    assert b.stats()["agent_steps"] > 10000
+    assert b.touched_keys() > 0
+    assert b.disagreements() == 0
