@@ -26,10 +26,13 @@ static int fail(int code, const char *fmt, ...) {
                         "%s failed: %s", #call, cudaGetErrorString(err__));                     \
     } while (0)
 
+constexpr size_t kMaxDenseKeys = 200 * 1024; // shared-memory byte map of the persistent env kernel
+constexpr uint32_t kMaxEnvCtas = 256;       // per-CTA bitmap slices reserved per parity (>= SM count)
+
 struct Carve {
     size_t tables, nodetab, rng, bad, recs, sinfo, qalt, marks, bits, list, vals, visited, control, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
-    uint32_t replicas; // mark-array replicas (dense mode)
+    uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
     bool dense;        // small table: byte marks + ping-pong pull; else bitmap + list + two-pass pull
 };
 
@@ -46,16 +49,16 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
     c.recs = take((size_t)n_envs * 16);
     c.sinfo = take((size_t)cfg.n_states * 4);
-    // dense mode sweeps the whole table once per sub-step (copy + substitute the marked keys): right
-    // while the table is a few MB, i.e. L2-resident and cheaper to sweep than to list
-    c.dense = keys <= ((size_t)1 << 20);
-    if (const char *env = getenv("MDPP_DENSE")) c.dense = atoi(env) != 0;
+    // dense mode: the mark byte map of a persistent CTA lives in shared memory (one byte per key) and the pull
+    // kernel sweeps the whole table once per sub-step (copy + substitute the marked keys) -- right while
+    // the table is a few hundred KB.  Larger tables keep a touched bitmap + list in global memory.
+    c.dense = keys <= kMaxDenseKeys;
+    if (const char *env = getenv("MDPP_DENSE")) c.dense = c.dense && atoi(env) != 0;
     c.capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
+    c.words_per_cta = (uint32_t)(((keys + 31) / 32 + 3) & ~(size_t)3);
     if (c.dense) {
         c.qalt = take(keys * 4);
-        c.replicas = 8;
-        if (const char *env = getenv("MDPP_MARKREP")) { int r = atoi(env); if (r >= 1 && r <= 64 && !(r & (r - 1))) c.replicas = (uint32_t)r; }
-        c.marks = take(keys * 4 * 2 * c.replicas);
+        c.marks = take((size_t)2 * kMaxEnvCtas * c.words_per_cta * 4);
         c.bits = c.list = c.vals = 0;
     } else {
         c.qalt = c.marks = 0;
@@ -86,6 +89,7 @@ struct mdpp_handle {
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool chain;             // the previous launch on the stream was one of our learner kernels
+    uint32_t smem_configured; // env-kernel variants whose dynamic shared-memory limit has been raised
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
 };
 
@@ -192,6 +196,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
     h->chain = false;
+    h->smem_configured = 0;
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
     h->dev.bad_bitmap = (const uint32_t *)(h->ws + cv.bad);
     int devid = 0;
@@ -208,6 +213,15 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
         for (int d = 0; d < MDPP_MAX_DEST; d++) nodeimg[n][d] = cfg->bfs_len[d][n];
         nodeimg[n][8] = cfg->fwd[n];
         nodeimg[n][9] = cfg->base_legal[n];
+        const uint32_t fwd = cfg->fwd[n];
+        uint32_t selbits = 0, w3 = 1u << ((n >> 2) % 9);
+        if (fwd != MDPP_NONE) {
+            w3 |= 1u << (9 + (fwd >> 2) % 9);
+            for (int d = 0; d < cfg->n_dest_boxes; d++)
+                if ((cfg->sel_mask[d] >> (fwd >> 2)) & 1u) selbits |= 1u << d;
+        }
+        nodeimg[n][10] = (uint8_t)selbits;
+        memcpy(&nodeimg[n][12], &w3, 4);
     }
     cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.nodetab, nodeimg, sizeof nodeimg, cudaMemcpyHostToDevice, s);
@@ -327,6 +341,11 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
     return MDPP_OK;
 }
 
+static unsigned env_ctas(mdpp_handle *h) { // persistent env CTAs (dense mode): one per SM
+    const int64_t tiles = (h->n_envs + 31) / 32;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(h->sm_count, kMaxEnvCtas), tiles));
+}
+
 static Marks marks_of(mdpp_handle *h) {
     Marks m{};
     const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
@@ -334,8 +353,9 @@ static Marks marks_of(mdpp_handle *h) {
     Control *ctl = (Control *)(h->ws + h->cv.control);
     m.dense = h->cv.dense ? 1u : 0u;
     if (h->cv.dense) {
-        m.words = (uint32_t *)(h->ws + h->cv.marks) + (size_t)p * keys * h->cv.replicas;
-        m.replica_mask = h->cv.replicas - 1;
+        m.words_per_cta = h->cv.words_per_cta;
+        m.n_ctas = env_ctas(h);
+        m.cta_bits = (uint32_t *)(h->ws + h->cv.marks) + (size_t)p * kMaxEnvCtas * h->cv.words_per_cta;
     } else {
         m.bits = (uint32_t *)(h->ws + h->cv.bits) + (size_t)p * (keys / 32 + 1);
         m.list = (uint32_t *)(h->ws + h->cv.list) + (size_t)p * h->cv.capacity;
@@ -357,12 +377,13 @@ static Marks marks_of(mdpp_handle *h) {
 struct LearnLaunch {
     cudaLaunchAttribute attr;
     cudaLaunchConfig_t cfg;
-    LearnLaunch(mdpp_handle *h, unsigned grid, cudaStream_t s) {
+    LearnLaunch(mdpp_handle *h, unsigned grid, cudaStream_t s, unsigned block = kThreads, size_t smem = 0) {
         attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr.val.programmaticStreamSerializationAllowed = (h->pdl && h->chain) ? 1 : 0;
         cfg = cudaLaunchConfig_t{};
         cfg.gridDim = dim3(grid ? grid : 1u);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = smem;
         cfg.stream = s;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
@@ -383,17 +404,43 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
             rng_mode = 2;
         }
     }
-    LearnLaunch ll(h, grid_for(h->n_envs), s);
     const bool plain = !forced && !action_out && !state_idx && !reward && lp->flags == 0;
-    const uint4 *nodetab = (const uint4 *)(h->ws + h->cv.nodetab);
-    uint32_t *rngw = (uint32_t *)(h->ws + h->cv.rng);
+    EnvArgs ea{};
+    ea.recs = recs_of(h);
+    ea.n_envs = h->n_envs;
+    ea.env_id_base = h->env_id_base;
+    ea.round = round;
+    ea.q = q;
+    ea.nodetab = (const uint4 *)(h->ws + h->cv.nodetab);
+    ea.rng_words = (uint32_t *)(h->ws + h->cv.rng);
+    ea.rng_mode = rng_mode;
+    ea.forced = forced;
+    ea.action_out = action_out;
+    ea.state_out = state_idx;
+    ea.reward_out = reward;
+    ea.dl_state = (uint32_t *)(h->ws + h->cv.dl);
+    const Marks mk = marks_of(h);
+    const size_t map_bytes = (((size_t)mk.n_keys + 15) / 16) * 16;
+    LearnLaunch ll = h->cv.dense ? LearnLaunch(h, env_ctas(h), s, kEnvSmemThreads, map_bytes)
+                                 : LearnLaunch(h, grid_for(h->n_envs), s);
+    ll.cfg.attrs = &ll.attr; // the struct was copied: re-point at this copy's attribute
+    const int variant = car_slot * 2 + (plain ? 1 : 0);
+#define MDPP_QENV_K(KERNEL)                                                                                      \
+    do {                                                                                                         \
+        if (h->cv.dense && !((h->smem_configured >> variant) & 1u)) {                                            \
+            MDPP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_bytes)); \
+            h->smem_configured |= 1u << variant;                                                                 \
+        }                                                                                                        \
+        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ea, mk, control_of(h)));                       \
+    } while (0)
 #define MDPP_QENV_C(NCV, CV)                                                                                     \
-    if (plain) MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_env_kernel<NCV, CV, true>, h->dev, recs_of(h), h->n_envs,   \
-            h->env_id_base, round, *lp, q, marks_of(h), nodetab, rngw, rng_mode, forced, action_out,             \
-            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));                                  \
-    else MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_env_kernel<NCV, CV, false>, h->dev, recs_of(h), h->n_envs,        \
-            h->env_id_base, round, *lp, q, marks_of(h), nodetab, rngw, rng_mode, forced, action_out,             \
-            state_idx, reward, (uint32_t *)(h->ws + h->cv.dl), control_of(h)));
+    if (h->cv.dense) {                                                                                           \
+        if (plain) MDPP_QENV_K((q_env_smem_kernel<NCV, CV, true>));                                              \
+        else MDPP_QENV_K((q_env_smem_kernel<NCV, CV, false>));                                                   \
+    } else {                                                                                                     \
+        if (plain) MDPP_QENV_K((q_env_kernel<NCV, CV, true>));                                                   \
+        else MDPP_QENV_K((q_env_kernel<NCV, CV, false>));                                                        \
+    }
 #define MDPP_QENV(NCV)                                                                                           \
     switch (car_slot) {                                                                                          \
     case 0: MDPP_QENV_C(NCV, 0) break;                                                                           \
@@ -409,6 +456,7 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     case 4: MDPP_QENV(4) break;
     default: MDPP_QENV(5) break;
     }
+#undef MDPP_QENV_K
 #undef MDPP_QENV_C
 #undef MDPP_QENV
     h->chain = true;

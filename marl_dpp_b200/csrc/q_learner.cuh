@@ -36,18 +36,18 @@ __device__ __forceinline__ int32_t si_bfs(uint32_t i) { return (int32_t)((i >> 1
 __device__ __forceinline__ uint32_t si_node(uint32_t i) { return (i >> 22) & 127u; }
 
 struct Marks {
-    uint32_t *words;    // dense: [n_keys], parity of the current sub-step; nonzero = key touched
-    uint32_t *bits;     // list: [n_keys / 32] touched bitmap, parity of the current sub-step
-    uint32_t *list;     // list: [capacity] touched keys
-    uint32_t *count;    // list: number of listed keys (Control::touched_count[parity])
+    uint32_t *cta_bits;  // dense: [n_ctas][words_per_cta] per-CTA touched bitmaps of the current parity
+    uint32_t n_ctas, words_per_cta;
+    uint32_t *bits;      // list: [n_keys / 32] touched bitmap, parity of the current sub-step
+    uint32_t *list;      // list: [capacity] touched keys
+    uint32_t *count;     // list: number of listed keys (Control::touched_count[parity])
     uint32_t *count_other; // list: the other parity's counter (zeroed by the compute pass)
-    float *vals;        // list: [capacity] new values between the compute and the apply pass
-    uint32_t *visited;  // [n_states] bit a = (state, a) has been updated at least once (qvalue file writer)
+    float *vals;         // list: [capacity] new values between the compute and the apply pass
+    uint32_t *visited;   // [n_states] bit a = (state, a) has been updated at least once (qvalue file writer)
     const uint32_t *sinfo; // [n_states] per-state info words
     uint32_t capacity;
     uint32_t dense;
     uint32_t n_keys;
-    uint32_t replica_mask; // dense: mark replicas - 1 (power of two)
 };
 
 // epsilon schedule (reference src/utils/utils.py:33-52, model 3) on the per-env episode counter
@@ -59,8 +59,12 @@ __device__ __forceinline__ uint32_t eps_q16_of(const LearnArgs &lp, int32_t epis
     return e;
 }
 
-// One 16-byte table entry per node: bytes 0-7 BFS length to destination node 0..7, byte 8 F successor,
-// byte 9 base legal mask.  One LDG.128 through L1; the 36 entries of a block span 5 cache lines.
+// One 16-byte table entry per node, one LDG through L1 (the 36 entries of a block span 5 cache lines):
+//   bytes 0-7  BFS length to destination node 0..7
+//   byte 8     F successor            byte 9   base legal mask
+//   byte 10    bit d = the box ahead is in the selective-block list keyed by destination box d
+//   word 3     bits 0-8 = 1 << (own box number - 1), bits 9-17 = 1 << (number of the box ahead - 1), 0 if none
+// so that the legal filter (src/env_gym.py:143-224) is a handful of mask tests.
 struct NodeEnt {
     uint4 v;
     __device__ __forceinline__ uint32_t bfs(uint32_t d) const {
@@ -68,204 +72,272 @@ struct NodeEnt {
     }
     __device__ __forceinline__ uint32_t fwd() const { return v.z & 0xFFu; }
     __device__ __forceinline__ uint32_t base() const { return (v.z >> 8) & 0xFFu; }
+    __device__ __forceinline__ uint32_t selbits() const { return (v.z >> 16) & 0xFFu; }
 };
 __device__ __forceinline__ NodeEnt load_ent(const uint4 *__restrict__ tab, uint32_t node) {
     NodeEnt e;
     e.v = __ldg(tab + node);
     return e;
 }
-__device__ __forceinline__ uint32_t legal_mask_ent(const View &v, uint32_t node, const NodeEnt &ent) {
+// the half of the entry the legal filter and the successor need (training fast path: no BFS lengths)
+__device__ __forceinline__ NodeEnt load_ent_hi(const uint4 *__restrict__ tab, uint32_t node) {
+    NodeEnt e;
+    const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(tab + node) + 1);
+    e.v = make_uint4(0u, 0u, hi.x, hi.y);
+    return e;
+}
+// getlegalactions_filtered for the primary standing on the entry's node: S,L,R,T keep the car in its own box,
+// so they die together when a listed car shares the box NUMBER (:211-217); F dies on the same test for the
+// box ahead or on the selective-block rule (:143-186)
+__device__ __forceinline__ uint32_t legal_mask_ent(const View &v, const NodeEnt &ent) {
     uint32_t mask = ent.base();
-    if ((v.occ9 >> boxnum0(node >> 2)) & 1u) mask &= 1u << MDPP_A_F;
-    if (mask & (1u << MDPP_A_F)) {
-        const uint32_t fb = ent.fwd() >> 2;
-        bool blocked = (v.occ9 >> boxnum0(fb)) & 1u;
-        blocked = blocked || (((v.sel >> fb) & 1u) && (v.sel & v.occ18));
-        if (blocked) mask &= ~(1u << MDPP_A_F);
-    }
+    const uint32_t hit = (v.occ9 * 0x201u) & ent.v.w; // occupancy against the own box (bits 0-8) and the box ahead (9-17)
+    if (hit & 0x1FFu) mask &= 1u << MDPP_A_F;
+    const bool sel_blocked = ((ent.selbits() >> v.dbox) & 1u) && (v.sel & v.occ18);
+    if ((hit >> 9) || sel_blocked) mask &= ~(1u << MDPP_A_F);
     return mask;
 }
 
 // ------------------------------------------------------------------------------------------------
 // env side of one sub-step: car slot C of every env
 // ------------------------------------------------------------------------------------------------
-// The kernel is bound by instruction issue (ncu: ~430 warp-instructions per 32 envs before this
-// version, issue slots 72 % busy), so everything that can be decided at compile time is: the car slot
-// is a template parameter (fixed shifts instead of variable ones, no register-indexed constant loads),
-// the epsilon schedule has a one-compare fast path, the random legal action comes from a 32-entry
-// table, counters are reduced per CTA, and on the PLAIN path the reward -- which only the pull kernel
-// needs -- is not computed on this side at all.
+// The env side is bound by instruction issue and by what it sends to L2 (ncu, 2^20 envs: ~430
+// warp-instructions per 32 envs in the first version, issue slots 72 % busy; one scattered RED per env
+// caps at ~1e11/s chip-wide however the addresses are spread), so:
+//   * everything that can be decided at compile time is: the car slot is a template parameter (fixed
+//     shifts, no register-indexed constant loads), the epsilon schedule has a one-compare fast path,
+//     the random legal action comes from a 32-entry table, the legal filter is three mask tests on a
+//     precomputed node entry, counters are reduced per CTA, and on the PLAIN path the reward -- which
+//     only the pull kernel needs -- is not computed on this side at all;
+//   * small tables: marks go to a byte map in SHARED memory (one plain STS per env); a persistent CTA
+//     per SM compresses its map to a bitmap and writes it with coalesced stores when it is done, and the
+//     pull kernel ORs the per-CTA bitmaps.  No L2 atomics, ~1 MB of mark traffic per sub-step.
 //
 // rng_mode: 0 = compute the Philox block here; 1 = car-0 launch: compute it for every live env and
 // publish the words of cars 1..3; 2 = read this car's word from the side array.
 // PLAIN = the training fast path: no forced actions, no per-env outputs, no learner flags, no reward_sum.
 
+struct EnvArgs {
+    uint4 *recs;
+    int64_t n_envs;
+    uint32_t env_id_base;
+    uint64_t round;
+    const float *q;
+    const uint4 *nodetab;
+    uint32_t *rng_words;
+    int rng_mode;
+    const uint8_t *forced;
+    uint8_t *action_out;
+    uint32_t *state_out;
+    float *reward_out;
+    uint32_t *dl_state;
+};
+
+struct StepCounts {
+    uint32_t steps = 0, explore = 0, episodes = 0, capped = 0;
+    int32_t reward = 0;
+};
+
+// One agent-step of car C in env e (record `rec` already loaded).  Returns true and sets `key` when the env
+// updated a key; the caller owns the marking.  Writes the record back and the optional outputs.
+template <int NC, int C, bool PLAIN>
+__device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &lp, const EnvArgs &ea, int64_t e,
+                                            uint4 rec, uint32_t &key, StepCounts &cnt) {
+    const uint32_t lflags = PLAIN ? 0u : lp.flags;
+    const uint8_t *forced = PLAIN ? nullptr : ea.forced;
+    uint8_t *action_out = PLAIN ? nullptr : ea.action_out;
+    uint32_t *state_out = PLAIN ? nullptr : ea.state_out;
+    float *reward_out = PLAIN ? nullptr : ea.reward_out;
+    bool touched = false;
+    uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+    uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+    const uint32_t env = ea.env_id_base + (uint32_t)e;
+    uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
+    float r_out = 0.f;
+    const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
+    // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
+    const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
+    uint32_t word = 0;
+    if (C == 0 && ea.rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
+        if (live) {
+            const uint4 p = philox4x32_10((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 0, 0, lp.seed, env);
+            word = p.x;
+            if (NC > 1) ea.rng_words[e] = p.y;
+            if (NC > 2) ea.rng_words[(size_t)ea.n_envs + e] = p.z;
+            if (NC > 3) ea.rng_words[2 * (size_t)ea.n_envs + e] = p.w;
+        }
+    } else if (C > 0 && C < 4 && ea.rng_mode == 2) {
+        word = ea.rng_words[(size_t)(C - 1) * ea.n_envs + e];
+    }
+    if (live && !f_done(car_field(cars, C))) {
+        View v = view_of<NC>(cars, C, mode, cfg);
+        const NodeEnt entP = PLAIN ? load_ent_hi(ea.nodetab, v.pnode) : load_ent(ea.nodetab, v.pnode);
+        const uint32_t lm = legal_mask_ent(v, entP);
+        const uint32_t sidx = state_index(v, v.pnode, cfg);
+        s_out = sidx;
+        uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
+        const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
+        if (lm && forced_ok) {
+            // ---- getaction (reference src/algorithms/qlearning.py:74-105) ----
+            uint32_t a;
+            bool explore;
+            // epsilon schedule; the first segment (40 % of the episodes, most of the steps) costs one compare
+            uint32_t eps16 = lp.eps_q16[0];
+            if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
+            if (f == MDPP_ACT_GREEDY) {
+                a = 0;
+                explore = false;
+            } else if (f != MDPP_ACT_SKIP) {
+                a = f;
+                explore = true;
+            } else {
+                const uint32_t w = ea.rng_mode ? word : decision_word(ea.round, C, lp.seed, env);
+                explore = (w >> 16) < eps16; // flipcoin (utils.py:255-265)
+                // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
+                a = nth_set_bit_lut(cfg, lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
+            }
+            if (!explore) { // computeactionfromqvalues: first maximum in S,L,R,F,T order (:659-667)
+                pdl_wait();  // the only Q read of this kernel: the preceding pull must be complete
+                float qs[MDPP_Q_ROW];
+                ldg_row(ea.q + (size_t)sidx * MDPP_Q_ROW, qs); // one 256-bit load = the whole 32-byte row
+                float best = 0.f;
+                bool have = false;
+#pragma unroll
+                for (int k = 0; k < MDPP_N_ACT; k++) {
+                    bool ok = (lm >> k) & 1u;
+                    if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
+                }
+            }
+            cnt.explore += explore;
+            // ---- stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360): 3*n_cars consecutive
+            // 'S' actions while epsilon == 0 flag the state; the env stops there (the reference returns)
+            bool stalled = false;
+            if (lflags & MDPP_LEARN_DETECT) {
+                uint32_t run = rec.w & 0xFFu;
+                run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
+                stalled = run == 3u * NC;
+                rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
+                if (stalled) {
+                    ea.dl_state[e] = sidx;
+                    episode = (uint32_t)lp.episodes; // frozen from now on
+                }
+            }
+            if (!stalled) {
+                // ---- update (qlearning.py:107-116): the key is marked; the pull kernel computes the value ----
+                if (!(lflags & MDPP_LEARN_FROZEN)) {
+                    key = sidx * MDPP_Q_ROW + a;
+                    touched = true;
+                }
+                // ---- env step: successor (src/env_gym.py:256-265), update_car (:386-441) ----
+                const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
+                const uint32_t nn = a == MDPP_A_F ? entP.fwd() : ((v.pnode & ~3u) | ((v.pnode + rot) & 3u));
+                if constexpr (!PLAIN) { // q_reward (:555-620) for reward_out / reward_sum
+                    int32_t ri;
+                    bool bad_next = false, bad_prev = false;
+                    if (cfg.bad_on) { // :568-577 on the heading-stripped strings
+                        const uint32_t base = (v.rank * cfg.n_dest_boxes + v.dbox) * cfg.n_src_boxes;
+                        const uint32_t idn = base + ((nn >> 2) - cfg.box_base), idp = base + ((v.pnode >> 2) - cfg.box_base);
+                        bad_next = (__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u;
+                        bad_prev = (__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u;
+                    }
+                    if (bad_next) ri = -10000;
+                    else if (bad_prev) ri = 0;
+                    else {
+                        const NodeEnt entN = load_ent(ea.nodetab, nn);
+                        ri = -10 + 50 * ((int32_t)entP.bfs(v.dnidx) - (int32_t)entN.bfs(v.dnidx));
+                        if (nn == v.dnode) ri += 10010;
+                        int32_t clash = 0;
+#pragma unroll
+                        for (int i = 0; i < NC; i++)
+                            if (i != C) clash += ((f_node(car_field(cars, i)) >> 2) == (nn >> 2));
+                        ri -= clash * 100000;
+                    }
+                    cnt.reward += ri;
+                    r_out = (float)ri;
+                }
+                cars = advance_car(cars, C, v, nn, cfg);
+                steps = steps < 0xFFFFu ? steps + 1 : steps;
+                cnt.steps += 1;
+            }
+            a_out = a;
+        }
+    }
+    if (live && C == NC - 1) { // end of the round-robin round (qlearning.py:233)
+        bool finished = all_done<NC>(cars);
+        bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+        if (finished || capped) {
+            cnt.episodes += 1;
+            cnt.capped += capped;
+            episode = episode + 1;
+            steps = 0;
+            rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
+            cars = initial_cars<NC>(cfg, heading_word(ea.round, 2, lp.seed, env));
+        }
+    }
+    if (live) {
+        rec.x = (uint32_t)cars;
+        rec.y = (uint32_t)(cars >> 32);
+        rec.z = (episode & 0xFFFFu) | (steps << 16);
+        ea.recs[e] = rec;
+    }
+    if (action_out) action_out[e] = (uint8_t)a_out;
+    if (state_out) state_out[e] = s_out;
+    if (reward_out) reward_out[e] = r_out;
+    return touched;
+}
+
+// counters of a CTA: warp REDUX -> one shared-memory atomic per warp -> one thread adds the CTA's totals to a
+// privatised global slot.  Fields of the packed words hold up to 2^16 (a persistent CTA steps <= 2^16 envs).
+struct CtaCounters {
+    uint32_t steps, explore, episodes, capped;
+    int32_t reward;
+};
+template <bool PLAIN>
+__device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &cc, uint32_t lflags, Control *ctl) {
+    const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, c.steps), x = __reduce_add_sync(0xFFFFFFFFu, c.explore);
+    const uint32_t ep = __reduce_add_sync(0xFFFFFFFFu, c.episodes | (c.capped << 16));
+    int32_t rs = 0;
+    if constexpr (!PLAIN) rs = (int32_t)__reduce_add_sync(0xFFFFFFFFu, (unsigned)c.reward);
+    if ((threadIdx.x & 31u) == 0) {
+        if (s) atomicAdd(&cc.steps, s);
+        if (x) atomicAdd(&cc.explore, x);
+        if (ep & 0xFFFFu) atomicAdd(&cc.episodes, ep & 0xFFFFu);
+        if (ep >> 16) atomicAdd(&cc.capped, ep >> 16);
+        if (!PLAIN && rs) atomicAdd(&cc.reward, rs);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mdpp_stats *slot = &ctl->stats[blockIdx.x & (kStatSlots - 1)];
+        if (cc.steps) atomicAdd((unsigned long long *)&slot->agent_steps, (unsigned long long)cc.steps);
+        if (cc.steps && !(lflags & MDPP_LEARN_FROZEN)) atomicAdd((unsigned long long *)&slot->q_updates, (unsigned long long)cc.steps);
+        if (cc.explore) atomicAdd((unsigned long long *)&slot->explore_steps, (unsigned long long)cc.explore);
+        if (cc.episodes) atomicAdd((unsigned long long *)&slot->episodes_done, (unsigned long long)cc.episodes);
+        if (cc.capped) atomicAdd((unsigned long long *)&slot->episodes_capped, (unsigned long long)cc.capped);
+        if (!PLAIN && cc.reward) atomicAdd((unsigned long long *)&slot->reward_sum, (unsigned long long)(long long)cc.reward);
+    }
+}
+
+// list mode (large tables): one CTA per 256-env tile, touched bitmap + key list in global memory
 template <int NC, int C, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
-q_env_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, uint64_t round,
-             LearnArgs lp, const float *__restrict__ q, Marks mk, const uint4 *__restrict__ nodetab,
-             uint32_t *__restrict__ rng_words, int rng_mode, const uint8_t *__restrict__ forced,
-             uint8_t *__restrict__ action_out, uint32_t *__restrict__ state_out, float *__restrict__ reward_out,
-             uint32_t *__restrict__ dl_state, Control *ctl) {
-    __shared__ unsigned long long cta_counts; // steps | explore << 16 | episodes << 32 | capped << 48
-    __shared__ long long cta_reward;
-    const uint32_t lflags = PLAIN ? 0u : lp.flags;
-    if constexpr (PLAIN) { forced = nullptr; action_out = nullptr; state_out = nullptr; reward_out = nullptr; }
-    if (threadIdx.x == 0) { cta_counts = 0ull; cta_reward = 0ll; }
+q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
+    __shared__ CtaCounters cc;
+    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0};
     // PDL: the pull kernel that follows may be scheduled as SM slots free up (it waits for this grid to
     // complete before it looks at the marks)
     pdl_launch_dependents();
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t stepped = 0, explored = 0, ep_done = 0, ep_capped = 0;
-    int32_t rsum = 0;
-    bool first = false;   // list mode: this lane is the first toucher of its key
+    StepCounts cnt;
+    bool first = false; // this lane is the first toucher of its key in this sub-step
     uint32_t key = 0;
-    if (e < n_envs) {
-        uint4 rec = recs[e];
-        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
-        const uint32_t env = env_id_base + (uint32_t)e;
-        uint32_t a_out = MDPP_ACT_SKIP, s_out = 0xFFFFFFFFu;
-        float r_out = 0.f;
-        const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
-        // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
-        const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
-        uint32_t word = 0;
-        if (C == 0 && rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
-            if (live) {
-                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
-                word = p.x;
-                if (NC > 1) rng_words[e] = p.y;
-                if (NC > 2) rng_words[(size_t)n_envs + e] = p.z;
-                if (NC > 3) rng_words[2 * (size_t)n_envs + e] = p.w;
-            }
-        } else if (C > 0 && C < 4 && rng_mode == 2) {
-            word = rng_words[(size_t)(C - 1) * n_envs + e];
+    if (e < ea.n_envs) {
+        if (env_substep<NC, C, PLAIN>(cfg, lp, ea, e, ea.recs[e], key, cnt)) {
+            const uint32_t bit = 1u << (key & 31u);
+            first = !(atomicOr(mk.bits + (key >> 5), bit) & bit);
         }
-        if (live && !f_done(car_field(cars, C))) {
-            View v = view_of<NC>(cars, C, mode, cfg);
-            const NodeEnt entP = load_ent(nodetab, v.pnode);
-            const uint32_t lm = legal_mask_ent(v, v.pnode, entP);
-            const uint32_t sidx = state_index(v, v.pnode, cfg);
-            s_out = sidx;
-            uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
-            const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
-            if (lm && forced_ok) {
-                // ---- getaction (reference src/algorithms/qlearning.py:74-105) ----
-                uint32_t a;
-                bool explore;
-                // epsilon schedule; the first segment (40 % of the episodes, most of the steps) costs one compare
-                uint32_t eps16 = lp.eps_q16[0];
-                if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
-                if (f == MDPP_ACT_GREEDY) {
-                    a = 0;
-                    explore = false;
-                } else if (f != MDPP_ACT_SKIP) {
-                    a = f;
-                    explore = true;
-                } else {
-                    const uint32_t w = rng_mode ? word : decision_word(round, C, lp.seed, env);
-                    explore = (w >> 16) < eps16; // flipcoin (utils.py:255-265)
-                    // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
-                    a = nth_set_bit_lut(cfg, lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
-                }
-                if (!explore) { // computeactionfromqvalues: first maximum in S,L,R,F,T order (:659-667)
-                    pdl_wait();  // the only Q read of this kernel: the preceding pull must be complete
-                    float qs[MDPP_Q_ROW];
-                    ldg_row(q + (size_t)sidx * MDPP_Q_ROW, qs); // one 256-bit load = the whole 32-byte row
-                    float best = 0.f;
-                    bool have = false;
-#pragma unroll
-                    for (int k = 0; k < MDPP_N_ACT; k++) {
-                        bool ok = (lm >> k) & 1u;
-                        if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
-                    }
-                }
-                explored = explore;
-                // ---- stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360): 3*n_cars consecutive
-                // 'S' actions while epsilon == 0 flag the state; the env stops there (the reference returns)
-                bool stalled = false;
-                if (lflags & MDPP_LEARN_DETECT) {
-                    uint32_t run = rec.w & 0xFFu;
-                    run = (a == MDPP_A_S && eps16 == 0u) ? run + 1u : 0u;
-                    stalled = run == 3u * NC;
-                    rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
-                    if (stalled) {
-                        dl_state[e] = sidx;
-                        episode = (uint32_t)lp.episodes; // frozen from now on
-                    }
-                }
-                if (!stalled) {
-                    // ---- update (qlearning.py:107-116): mark the key; the pull kernel computes the value ----
-                    if (!(lflags & MDPP_LEARN_FROZEN)) {
-                        key = sidx * MDPP_Q_ROW + a;
-                        if (mk.dense) {
-                            // RED.OR into one of R CTA-indexed replicas of the mark array: a hot key is spread
-                            // over R L2 addresses (same-address traffic serialises in L2, loads included)
-                            atomicOr(mk.words + (blockIdx.x & mk.replica_mask) * mk.n_keys + key, 1u);
-                        } else {
-                            const uint32_t bit = 1u << (key & 31u);
-                            first = !(atomicOr(mk.bits + (key >> 5), bit) & bit);
-                        }
-                    }
-                    // ---- env step: successor (src/env_gym.py:256-265), update_car (:386-441) ----
-                    const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
-                    const uint32_t nn = a == MDPP_A_F ? entP.fwd() : ((v.pnode & ~3u) | ((v.pnode + rot) & 3u));
-                    if constexpr (!PLAIN) { // q_reward (:555-620) for reward_out / reward_sum
-                        int32_t ri;
-                        bool bad_next = false, bad_prev = false;
-                        if (cfg.bad_on) { // :568-577 on the heading-stripped strings
-                            const uint32_t base = (v.rank * cfg.n_dest_boxes + v.dbox) * cfg.n_src_boxes;
-                            const uint32_t idn = base + ((nn >> 2) - cfg.box_base), idp = base + ((v.pnode >> 2) - cfg.box_base);
-                            bad_next = (__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u;
-                            bad_prev = (__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u;
-                        }
-                        if (bad_next) ri = -10000;
-                        else if (bad_prev) ri = 0;
-                        else {
-                            const NodeEnt entN = load_ent(nodetab, nn);
-                            ri = -10 + 50 * ((int32_t)entP.bfs(v.dnidx) - (int32_t)entN.bfs(v.dnidx));
-                            if (nn == v.dnode) ri += 10010;
-                            int32_t clash = 0;
-#pragma unroll
-                            for (int i = 0; i < NC; i++)
-                                if (i != C) clash += ((f_node(car_field(cars, i)) >> 2) == (nn >> 2));
-                            ri -= clash * 100000;
-                        }
-                        rsum = ri;
-                        r_out = (float)ri;
-                    }
-                    cars = advance_car(cars, C, v, nn, cfg);
-                    steps = steps < 0xFFFFu ? steps + 1 : steps;
-                    stepped = 1;
-                }
-                a_out = a;
-            }
-        }
-        if (live && C == NC - 1) { // end of the round-robin round (qlearning.py:233)
-            bool finished = all_done<NC>(cars);
-            bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
-            if (finished || capped) {
-                ep_done = 1;
-                ep_capped = capped;
-                episode = episode + 1;
-                steps = 0;
-                rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
-                cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
-            }
-        }
-        if (live) {
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
-            rec.z = (episode & 0xFFFFu) | (steps << 16);
-            recs[e] = rec;
-        }
-        if (action_out) action_out[e] = (uint8_t)a_out;
-        if (state_out) state_out[e] = s_out;
-        if (reward_out) reward_out[e] = r_out;
     }
-    if (!mk.dense) { // list mode: first touchers append their key, one counter atomic per warp
+    { // first touchers append their key, one counter atomic per warp
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, first);
         if (bal) {
             const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)bal) - 1u;
@@ -276,33 +348,64 @@ q_env_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_
             if (first && slot < mk.capacity) mk.list[slot] = key;
         }
     }
-    // ---- counters: warp REDUX -> one shared-memory atomic per warp -> one thread flushes the CTA ----
-    {
-        const uint32_t packed = __reduce_add_sync(0xFFFFFFFFu, stepped | (explored << 8) | (ep_done << 16) | (ep_capped << 24));
-        int32_t rs = 0;
-        if constexpr (!PLAIN) rs = (int32_t)__reduce_add_sync(0xFFFFFFFFu, (unsigned)rsum);
-        if ((threadIdx.x & 31u) == 0) {
-            if (packed)
-                atomicAdd(&cta_counts, (unsigned long long)(packed & 0xFFu) | ((unsigned long long)((packed >> 8) & 0xFFu) << 16) |
-                                           ((unsigned long long)((packed >> 16) & 0xFFu) << 32) |
-                                           ((unsigned long long)(packed >> 24) << 48));
-            if (!PLAIN && rs) atomicAdd((unsigned long long *)&cta_reward, (unsigned long long)(long long)rs);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && cta_counts) {
-            mdpp_stats *slot = &ctl->stats[blockIdx.x & (kStatSlots - 1)];
-            const unsigned long long cc = cta_counts;
-            const unsigned long long st = cc & 0xFFFFull, ex = (cc >> 16) & 0xFFFFull, ep = (cc >> 32) & 0xFFFFull, cp = cc >> 48;
-            if (st) atomicAdd((unsigned long long *)&slot->agent_steps, st);
-            if (st && !(lflags & MDPP_LEARN_FROZEN)) atomicAdd((unsigned long long *)&slot->q_updates, st);
-            if (ex) atomicAdd((unsigned long long *)&slot->explore_steps, ex);
-            if (ep) atomicAdd((unsigned long long *)&slot->episodes_done, ep);
-            if (cp) atomicAdd((unsigned long long *)&slot->episodes_capped, cp);
-            if (!PLAIN && cta_reward) atomicAdd((unsigned long long *)&slot->reward_sum, (unsigned long long)cta_reward);
-        }
-    }
+    flush_counts<PLAIN>(cnt, cc, PLAIN ? 0u : lp.flags, ctl);
     // every kernel of the chain waits for its predecessor before it exits, so that "my predecessor has
     // completed" implies "everything before it has completed" (lanes that explored never waited above)
+    pdl_wait();
+}
+
+// dense mode (small tables): persistent CTAs, marks in a shared-memory byte map.  CTA b owns the warp tiles
+// [b * T / G, (b + 1) * T / G) of the batch (T tiles of 32 envs, G CTAs); warp w takes every n_warps-th of
+// them.  At the end the CTA compresses its map to bits and writes them to its own slice of the global bitmap
+// array [G][words] with coalesced stores (all words, so nothing has to be cleared between sub-steps).
+constexpr int kEnvSmemThreads = 1024;
+template <int NC, int C, bool PLAIN>
+__global__ void __launch_bounds__(kEnvSmemThreads, 1)
+q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
+    extern __shared__ uint4 smem_map4[];          // [ceil(n_keys / 16)] 16 keys per uint4
+    __shared__ CtaCounters cc;
+    uint8_t *map = reinterpret_cast<uint8_t *>(smem_map4);
+    const uint32_t n16 = (mk.n_keys + 15u) >> 4;
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) smem_map4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0};
+    pdl_launch_dependents();
+    __syncthreads();
+    const int64_t tiles = (ea.n_envs + 31) >> 5;
+    const int64_t t0 = tiles * blockIdx.x / gridDim.x, t1 = tiles * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    StepCounts cnt;
+    int64_t t = t0 + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t1 && t * 32 + lane < ea.n_envs) rec = ea.recs[t * 32 + lane];
+    while (t < t1) {
+        const int64_t e = t * 32 + lane, tn = t + n_warps;
+        uint4 rec_next = make_uint4(0u, 0u, 0u, 0u); // the next tile's records are in flight during this tile's work
+        if (tn < t1 && tn * 32 + lane < ea.n_envs) rec_next = ea.recs[tn * 32 + lane];
+        if (e < ea.n_envs) {
+            uint32_t key = 0;
+            if (env_substep<NC, C, PLAIN>(cfg, lp, ea, e, rec, key, cnt)) map[key] = 1;
+        }
+        rec = rec_next;
+        t = tn;
+    }
+    __syncthreads();
+    // bytes -> bits: 32 keys = two uint4 -> one word; (w * 0x01020408) >> 24 packs four 0/1 bytes into a nibble
+    uint32_t *out = mk.cta_bits + (size_t)blockIdx.x * mk.words_per_cta;
+    for (uint32_t w = threadIdx.x; w < mk.words_per_cta; w += blockDim.x) {
+        uint32_t bits = 0;
+        if (2u * w < n16) {
+            const uint4 lo = smem_map4[2u * w];
+            bits = ((lo.x * 0x01020408u) >> 24) | (((lo.y * 0x01020408u) >> 24) << 4) |
+                   (((lo.z * 0x01020408u) >> 24) << 8) | (((lo.w * 0x01020408u) >> 24) << 12);
+        }
+        if (2u * w + 1u < n16) {
+            const uint4 hi = smem_map4[2u * w + 1u];
+            bits |= (((hi.x * 0x01020408u) >> 24) << 16) | (((hi.y * 0x01020408u) >> 24) << 20) |
+                    (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
+        }
+        out[w] = bits;
+    }
+    flush_counts<PLAIN>(cnt, cc, PLAIN ? 0u : lp.flags, ctl);
     pdl_wait();
 }
 
@@ -343,24 +446,24 @@ __device__ __forceinline__ void mark_visited(uint32_t *__restrict__ visited, uin
     if (!(*vis & vb)) atomicOr(vis, vb);
 }
 
-// dense mode: one thread per table word.  qnew <- qold with every marked key replaced by its update.
+// dense mode: one thread per table word, one warp per 32 keys.  The warp ORs the per-CTA bitmaps of its
+// word (lane l reads CTAs l, l + 32, ...: all loads in flight at once), then qnew <- qold with every marked
+// key replaced by its update.
 __global__ void __launch_bounds__(kThreads)
 q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Marks mk, float alpha, float discount,
                     Control *ctl) {
-    pdl_wait();              // the env kernel that set the marks has completed
+    pdl_wait();              // the env kernel that wrote the bitmaps has completed
     pdl_launch_dependents(); // the next env kernel may start; it waits for us before its first Q read
-    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const uint32_t word = key >> 5; // warp-uniform
+    uint32_t bits = 0;
+    if (word < mk.words_per_cta)
+        for (uint32_t b = lane; b < mk.n_ctas; b += 32u) bits |= mk.cta_bits[(size_t)b * mk.words_per_cta + word];
+    bits = __reduce_or_sync(0xFFFFFFFFu, bits);
     uint32_t touched = 0;
     if (key < mk.n_keys) {
         float v = qold[key];
-        uint32_t marked = 0;
-        if ((key & 7u) < MDPP_N_ACT) {
-            for (uint32_t r = 0; r <= mk.replica_mask; r++) {
-                uint32_t *w = mk.words + (size_t)r * mk.n_keys + key;
-                if (*w) { marked = 1; *w = 0; }
-            }
-        }
-        if (marked) {
+        if ((bits >> lane) & 1u) {
             v = td_value(qold, mk.sinfo, key >> 3, key & 7u, v, alpha, discount);
             mark_visited(mk.visited, key);
             touched = 1;
@@ -368,7 +471,7 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
         qnew[key] = v;
     }
     touched = __reduce_add_sync(0xFFFFFFFFu, touched);
-    if ((threadIdx.x & 31u) == 0 && touched)
+    if (lane == 0 && touched)
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
                   (unsigned long long)touched);
 }

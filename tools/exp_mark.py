@@ -1,4 +1,4 @@
-"""Timing experiment (GPU): env-kernel / pull-kernel duration vs marking variant and training phase."""
+"""Timing experiment (GPU): env-kernel / pull-kernel duration, dense (1) vs list (0) mode, by training phase."""
 import gzip, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,10 +9,10 @@ bad = json.load(gzip.open("tests/golden/bad_states.json.gz"))["down_right"]
 boxes, idx, choose = m.layout_3[2]["initial_states"][0]
 sc = m.Scenario(m.layout_3[2], boxes, idx, choose, bad_states_text=bad, step_cap=10000)
 n = 1 << 20
-modes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1,2,4,8,16,64").split(",")]
+modes = [x for x in (sys.argv[1] if len(sys.argv) > 1 else "1").split(",")]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for mode in modes:
-    os.environ["MDPP_MARKREP"] = str(mode)
+    os.environ["MDPP_DENSE"] = mode
     env = BatchedEnv(sc, n, seed=3)
     lr = BatchedQLearner(env, episodes=5000, seed=3)
     out = []
@@ -39,5 +39,5 @@ for mode in modes:
         out.append("%s: env %.1f us pull+copy %.1f us | chained round %.1f us (%.2e steps/s, %d keys/substep)" %
                    (phase, s_ms * 1e3, f_ms * 1e3, a.elapsed_time(b) / 50 * 1e3,
                     st2["agent_steps"] / (a.elapsed_time(b) * 1e-3), st2["touched_keys"] / 100))
-    print("mark replicas", mode, "\n   " + "\n   ".join(out), flush=True)
+    print("dense", mode, "\n   " + "\n   ".join(out), flush=True)
     del lr, env
