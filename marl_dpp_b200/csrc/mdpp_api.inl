@@ -26,8 +26,9 @@ static int fail(int code, const char *fmt, ...) {
                         "%s failed: %s", #call, cudaGetErrorString(err__));                     \
     } while (0)
 
-constexpr size_t kMaxDenseKeys = 200 * 1024; // shared-memory byte map of the persistent env kernel
-constexpr uint32_t kMaxEnvCtas = 256;       // per-CTA bitmap slices reserved per parity (>= SM count)
+constexpr size_t kMaxByteMapKeys = 200 * 1024;    // shared-memory BYTE map of the persistent env kernel
+constexpr size_t kMaxDenseKeys = 8 * 200 * 1024;  // shared-memory BIT map (atomic OR) up to here; list mode beyond
+constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices reserved per parity (>= SM count)
 
 struct Carve {
     size_t tables, nodetab, rng, bad, recs, sinfo, qalt, marks, bits, list, vals, visited, control, stage, dl, total;
@@ -420,7 +421,8 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     ea.reward_out = reward;
     ea.dl_state = (uint32_t *)(h->ws + h->cv.dl);
     const Marks mk = marks_of(h);
-    const size_t map_bytes = (((size_t)mk.n_keys + 15) / 16) * 16;
+    const bool bitmap = (size_t)mk.n_keys > kMaxByteMapKeys;
+    const size_t map_bytes = bitmap ? (size_t)mk.words_per_cta * 4 : (((size_t)mk.n_keys + 15) / 16) * 16;
     LearnLaunch ll = h->cv.dense ? LearnLaunch(h, env_ctas(h), s, kEnvSmemThreads, map_bytes)
                                  : LearnLaunch(h, grid_for(h->n_envs), s);
     ll.cfg.attrs = &ll.attr; // the struct was copied: re-point at this copy's attribute
@@ -435,8 +437,13 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     } while (0)
 #define MDPP_QENV_C(NCV, CV)                                                                                     \
     if (h->cv.dense) {                                                                                           \
-        if (plain) MDPP_QENV_K((q_env_smem_kernel<NCV, CV, true>));                                              \
-        else MDPP_QENV_K((q_env_smem_kernel<NCV, CV, false>));                                                   \
+        if (bitmap) {                                                                                            \
+            if (plain) MDPP_QENV_K((q_env_smem_kernel<NCV, CV, true, true>));                                    \
+            else MDPP_QENV_K((q_env_smem_kernel<NCV, CV, false, true>));                                         \
+        } else {                                                                                                 \
+            if (plain) MDPP_QENV_K((q_env_smem_kernel<NCV, CV, true, false>));                                   \
+            else MDPP_QENV_K((q_env_smem_kernel<NCV, CV, false, false>));                                        \
+        }                                                                                                        \
     } else {                                                                                                     \
         if (plain) MDPP_QENV_K((q_env_kernel<NCV, CV, true>));                                                   \
         else MDPP_QENV_K((q_env_kernel<NCV, CV, false>));                                                        \
