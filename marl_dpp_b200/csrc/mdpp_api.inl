@@ -29,9 +29,10 @@ static int fail(int code, const char *fmt, ...) {
 constexpr size_t kMaxByteMapKeys = 200 * 1024;    // shared-memory BYTE map of the persistent env kernel
 constexpr size_t kMaxDenseKeys = 8 * 200 * 1024;  // shared-memory BIT map (atomic OR) up to here; list mode beyond
 constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices reserved per parity (>= SM count)
+constexpr uint32_t kMarkRegions = 3;              // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1
 
 struct Carve {
-    size_t tables, nodetab, rng, bad, recs, sinfo, qalt, marks, bits, list, vals, visited, control, stage, dl, total;
+    size_t tables, nodetab, fast, rng, bad, recs, sinfo, qalt, marks, flags, bits, list, vals, visited, control, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
     uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
     bool dense;        // small table: byte marks + ping-pong pull; else bitmap + list + two-pass pull
@@ -46,6 +47,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
     c.tables = take(sizeof(SmemTables));
     c.nodetab = take((size_t)MDPP_NODES * 16);
+    c.fast = take(sizeof(FastTabs));
     c.rng = take((size_t)n_envs * 4 * 3);
     c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
     c.recs = take((size_t)n_envs * 16);
@@ -59,10 +61,11 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.words_per_cta = (uint32_t)(((keys + 31) / 32 + 3) & ~(size_t)3);
     if (c.dense) {
         c.qalt = take(keys * 4);
-        c.marks = take((size_t)2 * kMaxEnvCtas * c.words_per_cta * 4);
+        c.marks = take((size_t)2 * kMarkRegions * kMaxEnvCtas * c.words_per_cta * 4); // [parity][region][cta][word]
+        c.flags = take((size_t)2 * kMaxEnvCtas * 4);
         c.bits = c.list = c.vals = 0;
     } else {
-        c.qalt = c.marks = 0;
+        c.qalt = c.marks = c.flags = 0;
         c.bits = take(2 * (keys / 8 + 4));
         c.list = take(2 * (size_t)c.capacity * 4);
         c.vals = take((size_t)c.capacity * 4);
@@ -91,6 +94,7 @@ struct mdpp_handle {
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool chain;             // the previous launch on the stream was one of our learner kernels
     uint32_t smem_configured; // env-kernel variants whose dynamic shared-memory limit has been raised
+    uint32_t round_parity;    // fused rounds alternate between two sets of mark regions
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
 };
 
@@ -160,6 +164,53 @@ static void make_devcfg(const mdpp_config &c, DevCfg &d) {
     }
 }
 
+// Table image of the fused round kernel (q_round.cuh): everything the reference derives from a car's
+// (node, destination_index), per car, as the primary and as an "other".
+static void build_fast_tabs(const mdpp_config &c, FastTabs &t) {
+    memset(&t, 0, sizeof t);
+    for (int car = 0; car < c.n_cars; car++) {
+        for (int di = 0; di < 2; di++) {
+            const uint32_t dn = c.car_dest[car][di], dnode = c.dest_node[dn], dbox = c.dest_node_box[dn];
+            const uint32_t sel = c.sel_mask[dbox];
+            for (int node = 0; node < MDPP_NODES; node++) {
+                const int idx = node | (di << 7);
+                const uint32_t box18 = (uint32_t)node >> 2;
+                if (c.node_local[node] != MDPP_NONE) { // as the primary
+                    const uint32_t fwd = c.fwd[node];
+                    uint32_t y = 1u << (box18 % 9);
+                    if (fwd != MDPP_NONE) {
+                        y |= 1u << (9 + (fwd >> 2) % 9);
+                        if ((sel >> (fwd >> 2)) & 1u) y |= 1u << 18;
+                    }
+                    t.own[car][idx].x = (dn * (uint32_t)c.n_local_nodes + c.node_local[node]) | (dnode << 10) |
+                                        ((fwd == MDPP_NONE ? 127u : fwd) << 17) | ((uint32_t)c.base_legal[node] << 24) |
+                                        (dbox << 29);
+                    t.own[car][idx].y = y;
+                    t.own[car][idx].z = sel;
+                }
+                if (c.src_box_idx[box18] != MDPP_NONE) { // as a listed other: (box, destination box)
+                    const uint32_t code = 1u + (uint32_t)c.src_box_idx[box18] * (uint32_t)c.n_dest_boxes + dbox;
+                    t.oth[car][idx].x = (1u << box18) | (code << 18);
+                    t.oth[car][idx].y = 1u << (box18 % 9);
+                }
+            }
+        }
+        // ghost of a finished car: [final box, final box] (reference src/env_gym.py:313-317)
+        const uint32_t gdbox = c.dest_node_box[c.car_dest[car][c.tcdi]], gbox18 = c.dest_box[gdbox];
+        if (c.src_box_idx[gbox18] != MDPP_NONE) {
+            const uint32_t code = 1u + (uint32_t)c.src_box_idx[gbox18] * (uint32_t)c.n_dest_boxes + gdbox;
+            t.ghost[car].x = (1u << gbox18) | (code << 18);
+            t.ghost[car].y = 1u << (gbox18 % 9);
+        }
+    }
+    for (int m = 0; m < 32; m++) {
+        uint32_t packed = 0, n = 0;
+        for (int k = 0; k < 5; k++)
+            if ((m >> k) & 1) packed |= (uint32_t)k << (3 * n++);
+        t.nth[m] = packed;
+    }
+}
+
 extern "C" {
 
 int mdpp_abi_version(void) { return MDPP_ABI_VERSION; }
@@ -198,6 +249,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
     h->chain = false;
     h->smem_configured = 0;
+    h->round_parity = 0;
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
     h->dev.bad_bitmap = (const uint32_t *)(h->ws + cv.bad);
     int devid = 0;
@@ -224,7 +276,11 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
         nodeimg[n][10] = (uint8_t)selbits;
         memcpy(&nodeimg[n][12], &w3, 4);
     }
+    FastTabs *ft = new (std::nothrow) FastTabs();
+    if (!ft) { delete h; return fail(MDPP_EINVAL, "out of host memory"); }
+    build_fast_tabs(*cfg, *ft);
     cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.fast, ft, sizeof(FastTabs), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.nodetab, nodeimg, sizeof nodeimg, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->ws + cv.dl, 0xFF, (size_t)n_envs * 4, s); // no deadlock state yet
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.tables, &img, sizeof img, cudaMemcpyHostToDevice, s);
@@ -244,6 +300,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
+    delete ft;
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, sizeof(mdpp_stats) * kStatSlots);
     if (e != cudaSuccess) {
         delete h;
@@ -347,6 +404,10 @@ static unsigned env_ctas(mdpp_handle *h) { // persistent env CTAs (dense mode): 
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(h->sm_count, kMaxEnvCtas), tiles));
 }
 
+static uint32_t *mark_region(mdpp_handle *h, uint32_t parity, uint32_t region) {
+    return (uint32_t *)(h->ws + h->cv.marks) + ((size_t)parity * kMarkRegions + region) * kMaxEnvCtas * h->cv.words_per_cta;
+}
+
 static Marks marks_of(mdpp_handle *h) {
     Marks m{};
     const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
@@ -356,7 +417,7 @@ static Marks marks_of(mdpp_handle *h) {
     if (h->cv.dense) {
         m.words_per_cta = h->cv.words_per_cta;
         m.n_ctas = env_ctas(h);
-        m.cta_bits = (uint32_t *)(h->ws + h->cv.marks) + (size_t)p * kMaxEnvCtas * h->cv.words_per_cta;
+        m.cta_bits = mark_region(h, p, 0);
     } else {
         m.bits = (uint32_t *)(h->ws + h->cv.bits) + (size_t)p * (keys / 32 + 1);
         m.list = (uint32_t *)(h->ws + h->cv.list) + (size_t)p * h->cv.capacity;
@@ -471,8 +532,9 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
 }
 
 // dense: qsrc -> qdst (whole table, marked keys substituted).  list: in place on qsrc, two passes.
-static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s) {
-    const Marks mk = marks_of(h);
+static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s,
+                         const Marks *marks = nullptr) {
+    const Marks mk = marks ? *marks : marks_of(h);
     if (h->cv.dense) {
         LearnLaunch ll(h, grid_for(mk.n_keys), s);
         MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
@@ -487,7 +549,85 @@ static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_le
         MDPP_CUDA(cudaLaunchKernelEx(&l2.cfg, q_pull_list_apply_kernel, qsrc, mk, control_of(h)));
     }
     h->chain = true;
-    h->parity ^= 1u;
+    if (!marks) h->parity ^= 1u;
+    return MDPP_OK;
+}
+
+// ---- fused round (q_round.cuh): 1- and 2-car tables whose byte maps fit shared memory ------------------
+static size_t round_smem_bytes(int n_cars, size_t map_bytes, int maps) {
+    const size_t tabs = n_cars == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>);
+    return ((tabs + 15) & ~(size_t)15) + (size_t)maps * map_bytes;
+}
+static bool round_eligible(const mdpp_handle *h) {
+    if (!h->cv.dense || h->cfg.n_cars > 2) return false;
+    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
+    if (keys > kMaxByteMapKeys) return false;
+    const size_t map_bytes = ((keys + 15) / 16) * 16;
+    const size_t need = h->cfg.n_cars == 1 ? round_smem_bytes(1, map_bytes, 1) : round_smem_bytes(2, map_bytes, 2);
+    if (getenv("MDPP_FUSED") && atoi(getenv("MDPP_FUSED")) == 0) return false;
+    return need <= (size_t)220 * 1024;
+}
+
+static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round, cudaStream_t s) {
+    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
+    const uint32_t P = h->round_parity;
+    h->round_parity ^= 1u;
+    RoundArgs ra{};
+    ra.recs = recs_of(h);
+    ra.n_envs = (uint32_t)h->n_envs;
+    ra.env_id_base = h->env_id_base;
+    ra.round = round;
+    ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
+    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)P * kMaxEnvCtas;
+    ra.words_per_cta = h->cv.words_per_cta;
+    ra.n_keys = (uint32_t)keys;
+    ra.map_bytes = (uint32_t)(((keys + 15) / 16) * 16);
+    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    const unsigned grid = env_ctas(h);
+    Marks mk = marks_of(h);
+    mk.n_ctas = grid;
+#define MDPP_ROUND_K(KERNEL, SMEM, BIT)                                                                          \
+    do {                                                                                                         \
+        if (!((h->smem_configured >> (BIT)) & 1u)) {                                                             \
+            MDPP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));    \
+            h->smem_configured |= 1u << (BIT);                                                                   \
+        }                                                                                                        \
+        LearnLaunch ll(h, grid, s, kEnvSmemThreads, (SMEM));                                                     \
+        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ra, control_of(h)));                           \
+        h->chain = true;                                                                                         \
+    } while (0)
+    if (h->cfg.n_cars == 1) {
+        ra.q = cur;
+        ra.bits_a = mark_region(h, P, 0);
+        MDPP_ROUND_K((q_round_kernel<1, 0>), round_smem_bytes(1, ra.map_bytes, 1), 28);
+        mk.cta_bits = mark_region(h, P, 0);
+        int rc = q_pull_launch(h, cur, alt, lp, s, &mk);
+        if (rc) return rc;
+        std::swap(cur, alt);
+        return MDPP_OK;
+    }
+    // K0: car 0 of every env, car 1 where it explores
+    ra.q = cur;
+    ra.bits_a = mark_region(h, P, 0);
+    ra.bits_b = mark_region(h, P, 1);
+    MDPP_ROUND_K((q_round_kernel<2, 0>), round_smem_bytes(2, ra.map_bytes, 2), 29);
+    mk.cta_bits = mark_region(h, P, 0);
+    int rc = q_pull_launch(h, cur, alt, lp, s, &mk);
+    if (rc) return rc;
+    std::swap(cur, alt);
+    // K1: the lanes whose car 1 acts greedily, against the table after the pull of sub-step 0
+    ra.q = cur;
+    ra.bits_a = mark_region(h, P, 2);
+    ra.bits_b = nullptr;
+    MDPP_ROUND_K((q_round_kernel<2, 1>), round_smem_bytes(2, ra.map_bytes, 1), 30);
+    mk.cta_bits = mark_region(h, P, 1);
+    mk.cta_bits2 = mark_region(h, P, 2);
+    mk.flags2 = ra.defer_flags;
+    rc = q_pull_launch(h, cur, alt, lp, s, &mk);
+    if (rc) return rc;
+    std::swap(cur, alt);
+#undef MDPP_ROUND_K
     return MDPP_OK;
 }
 
@@ -532,7 +672,13 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
     h->chain = false;
     float *cur = q, *alt = h->cv.dense ? (float *)(h->ws + h->cv.qalt) : q; // dense: the table ping-pongs
     const bool frozen = (lp->flags & MDPP_LEARN_FROZEN) != 0;
-    for (int r = 0; r < rounds; r++)
+    const bool fused = lp->flags == 0 && round_eligible(h);
+    for (int r = 0; r < rounds; r++) {
+        if (fused) { // training fast path: a whole round per launch (q_round.cuh)
+            int rc = q_round_launch(h, cur, alt, lp, first_round + (uint64_t)r, s);
+            if (rc) return rc;
+            continue;
+        }
         for (int c = 0; c < h->cfg.n_cars; c++) {
             int rc = q_env_launch(h, cur, lp, c, first_round + (uint64_t)r, nullptr, nullptr, nullptr, nullptr, s);
             if (rc) return rc;
@@ -544,6 +690,7 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
             if (rc) return rc;
             std::swap(cur, alt);
         }
+    }
     int rc = MDPP_OK;
     if (cur != q) rc = q_copy_launch(h, cur, q, s); // odd number of sub-steps: bring the table home
     h->chain = false;

@@ -273,6 +273,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
 // ------------------------------------------------------------------------------------------------
 } // namespace mdpp
 #include "q_learner.cuh" // needs Control / StatAcc / flush_stats_warp from above
+#include "q_round.cuh"
 namespace mdpp {
 
 // ------------------------------------------------------------------------------------------------

@@ -37,6 +37,8 @@ __device__ __forceinline__ uint32_t si_node(uint32_t i) { return (i >> 22) & 127
 
 struct Marks {
     uint32_t *cta_bits;  // dense: [n_ctas][words_per_cta] per-CTA touched bitmaps of the current parity
+    uint32_t *cta_bits2; // dense, fused round: bitmaps of the catch-up kernel (or NULL) ...
+    const uint32_t *flags2; // ... valid for the CTAs whose flag is set
     uint32_t n_ctas, words_per_cta;
     uint32_t *bits;      // list: [n_keys / 32] touched bitmap, parity of the current sub-step
     uint32_t *list;      // list: [capacity] touched keys
@@ -467,8 +469,12 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
     const uint32_t word = key >> 5; // warp-uniform
     uint32_t bits = 0;
-    if (word < mk.words_per_cta)
+    if (word < mk.words_per_cta) {
         for (uint32_t b = lane; b < mk.n_ctas; b += 32u) bits |= mk.cta_bits[(size_t)b * mk.words_per_cta + word];
+        if (mk.cta_bits2)
+            for (uint32_t b = lane; b < mk.n_ctas; b += 32u)
+                if (mk.flags2[b]) bits |= mk.cta_bits2[(size_t)b * mk.words_per_cta + word];
+    }
     bits = __reduce_or_sync(0xFFFFFFFFu, bits);
     uint32_t touched = 0;
     if (key < mk.n_keys) {

@@ -1,0 +1,290 @@
+// q_round.cuh -- training fast path for small tables: a whole round-robin round per launch (sm_100a).
+//
+// Same batch semantics as q_learner.cuh (the sub-step-by-sub-step kernels there remain the general
+// path and the one the parity tests drive step by step).  Two observations make a round cheaper:
+//
+// 1. An env only has to wait for the pull of sub-step c-1 before its car c acts if car c's coin says
+//    "greedy" -- an exploring car never reads the Q table.  So the round kernel K0 steps car 0 of every
+//    env (greedy reads see the table as the round began, which is the snapshot of sub-step 0) and goes
+//    straight on to car 1 when car 1 explores, marking into a second map.  A lane whose car 1 must act
+//    greedily is parked (pending bits in the record, decision word saved) and finished by the catch-up
+//    kernel K1 after the pull of sub-step 0.  While epsilon = 1 (40 % of the episodes, most of the
+//    steps) K1 finds nothing to do and its CTAs exit on one flag; later it does what the second
+//    sub-step kernel did.  The pull of sub-step 1 ORs the marks of both kernels.
+//
+// 2. The env arithmetic is bound by the integer ALU pipe (half issue rate on sm_100: ncu shows
+//    math_pipe_throttle and "wait" as the top stalls of the sub-step kernel at ~270 warp-instructions
+//    per car-step).  Everything the reference derives from a car's (node, destination_index) is a
+//    per-(car, node, destination_index) constant, so it is read from shared-memory tables instead:
+//    one 16-byte entry for the primary (state-index base, destination node, F successor, base legal
+//    mask, occupancy test masks, selective-block mask) and one 8-byte entry per other car (its listed
+//    (box, destination box) code and occupancy bits).
+//
+// Launch shape: one persistent CTA of 1024 threads per SM, tile assignment identical in K0 and K1.
+#pragma once
+#include "q_learner.cuh"
+
+namespace mdpp {
+
+// host-built table image (workspace); the kernels copy the first n_cars rows to shared memory
+struct FastTabs {
+    uint4 own[MDPP_MAX_CARS][256];  // index = node | destination_index << 7 (the low 8 bits of a car field)
+    uint2 oth[MDPP_MAX_CARS][256];  // same index, car seen as an "other"
+    uint2 ghost[MDPP_MAX_CARS];     // oth-format entry of the finished car's ghost
+    uint32_t nth[32];               // per 5-bit mask: positions of its set bits, 3 bits each, lowest first
+};
+// own.x: bits 0-9 dnidx * n_local_nodes + node_local | 10-16 destination node | 17-23 F successor (127 none)
+//        | 24-28 base legal mask | 29-31 destination-box index
+// own.y: bits 0-8 1 << (own box number - 1) | 9-17 1 << (number of the box ahead - 1) | 18 box ahead is in the
+//        selective-block list keyed by this car's current destination box
+// own.z: that selective-block list as an 18-bit box mask
+// oth.x: bits 0-17 1 << box18 | 18-25 others-code        oth.y: bits 0-8 1 << (box number - 1)
+
+template <int NC>
+struct RoundSmem {
+    uint4 own[NC][256];
+    uint2 oth[NC][256];
+    uint32_t nth[32];
+    CtaCounters cc;
+    uint32_t any_deferred;
+};
+
+struct RoundArgs {
+    uint4 *recs;
+    uint32_t n_envs;
+    uint32_t env_id_base;
+    uint64_t round;
+    const float *q;              // table a greedy car of THIS kernel reads (K0: car 0, K1: car 1)
+    uint32_t *rng_words;         // [3][n_envs] decision words of parked lanes
+    const FastTabs *tabs;
+    uint32_t *bits_a, *bits_b;   // K0: [n_ctas][words] bitmaps of map 0 / map 1; K1: bits_a = its own map-1 bitmap
+    uint32_t *defer_flags;       // [n_ctas] K0 writes, K1 reads: this CTA parked at least one lane
+    uint32_t words_per_cta, n_keys, map_bytes;
+    uint32_t rank_stride;        // n_dest_nodes * n_local_nodes
+};
+
+enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
+
+// One agent-step of car C on the unpacked record.  `cars` is committed (ghost counters of encodestate, the
+// move) unless the car is parked.  Returns kStepDone with `key` when a key was touched.
+template <int NC, int C>
+__device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
+                                              const RoundArgs &ra, uint64_t &cars, uint32_t word, uint32_t eps16,
+                                              bool allow_greedy, uint32_t &key, bool &moved, bool &explore) {
+    moved = false;
+    explore = false;
+    const uint32_t f = (uint32_t)(cars >> (12 * C)) & 0xFFFu;
+    if (f & 0x100u) return kStepSkip; // `if env.check_car_training(num): continue` (qlearning.py:216-217)
+    uint64_t nc = cars;
+    const uint4 own = S.own[C][f & 0xFFu];
+    // ---- encodestate (src/env_gym.py:281-329): the others, with the ghost side effect of finished cars ----
+    uint32_t occ9 = 0, occ18 = 0, codes[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        codes[i] = 0;
+        if (i == C) continue;
+        const uint32_t fi = (uint32_t)(cars >> (12 * i)) & 0xFFFu;
+        uint2 oe = make_uint2(0u, 0u);
+        if (!(fi & 0x100u)) {
+            oe = S.oth[i][fi & 0xFFu];
+        } else {
+            uint32_t g = fi >> 9;
+            if (g != 7u) {
+                if (g == 0u) g = 7u;                 // count went negative: the ghost vanishes for good
+                else { g -= 1u; oe = gt->ghost[i]; } // still shown (5 encodes in total)
+                nc = (nc & ~(0xE00ull << (12 * i))) | ((uint64_t)(g << 9) << (12 * i));
+            }
+        }
+        codes[i] = oe.x >> 18;
+        occ18 |= oe.x & 0x3FFFFu;
+        occ9 |= oe.y;
+    }
+    uint32_t rank = 0;
+    if constexpr (NC > 1) {
+        sort_codes<NC>(codes);
+        rank = codes[1];
+        if constexpr (NC > 2) rank += (codes[2] + 1u) * codes[2] / 2u;
+        if constexpr (NC > 3) rank += (codes[3] + 2u) * (codes[3] + 1u) * codes[3] / 6u;
+        if constexpr (NC > 4) rank += (codes[4] + 3u) * (codes[4] + 2u) * (codes[4] + 1u) * codes[4] / 24u;
+    }
+    const uint32_t sidx = rank * ra.rank_stride + (own.x & 0x3FFu);
+    // ---- getlegalactions_filtered (:143-224) ----
+    uint32_t lm = (own.x >> 24) & 31u;
+    const uint32_t hit = (occ9 * 0x201u) & own.y;
+    if (hit & 0x1FFu) lm &= 1u << MDPP_A_F;
+    if ((hit >> 9) || (((own.y >> 18) & 1u) && (own.z & occ18))) lm &= ~(1u << MDPP_A_F);
+    if (!lm) { // getaction returns None: nothing moves, the encode's side effects stay
+        cars = nc;
+        return kStepSkip;
+    }
+    // ---- getaction (src/algorithms/qlearning.py:74-105) ----
+    explore = (word >> 16) < eps16; // flipcoin (utils.py:255-265)
+    uint32_t a;
+    if (explore) { // random.choice(legal): low 16 bits scaled to the legal count
+        a = (S.nth[lm] >> (3u * (((word & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
+    } else {
+        if (!allow_greedy) return kStepDefer; // the snapshot of this sub-step does not exist yet
+        pdl_wait();
+        float qs[MDPP_Q_ROW];
+        ldg_row(ra.q + (size_t)sidx * MDPP_Q_ROW, qs);
+        float best = 0.f;
+        bool have = false;
+        a = 0;
+#pragma unroll
+        for (int k = 0; k < MDPP_N_ACT; k++) { // first maximum in S,L,R,F,T order (:659-667)
+            bool ok = (lm >> k) & 1u;
+            if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
+        }
+    }
+    key = sidx * MDPP_Q_ROW + a;
+    // ---- successor (src/env_gym.py:256-265) and update_car (:386-441) ----
+    const uint32_t pnode = f & 127u, dnode = (own.x >> 10) & 127u;
+    const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
+    uint32_t node = a == MDPP_A_F ? ((own.x >> 17) & 127u) : ((pnode & ~3u) | ((pnode + rot) & 3u));
+    uint32_t di = (f >> 7) & 1u, done = 0;
+    if (node == dnode) {
+        if ((int)di == cfg.tcdi) {
+            done = 0x100u;
+            node = (uint32_t)cfg.parking_node;
+        }
+        di ^= 1u;
+    }
+    const uint32_t nf = node | (di << 7) | done | (f & 0xE00u);
+    cars = (nc & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
+    moved = true;
+    return kStepDone;
+}
+
+// CSTART = 0: K0, every live env, cars 0..NC-1 while they explore.  CSTART = 1 (NC = 2): K1, parked lanes only.
+template <int NC, int CSTART>
+__global__ void __launch_bounds__(kEnvSmemThreads, 1)
+q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
+    static_assert(NC >= 1 && NC <= 2 && CSTART < NC, "the fused round is built for 1- and 2-car tables");
+    extern __shared__ uint4 smem_dyn[];
+    RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
+    constexpr uint32_t kTabBytes = (sizeof(RoundSmem<NC>) + 15u) & ~15u;
+    constexpr int kMaps = NC - CSTART;
+    uint8_t *maps = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes; // kMaps byte maps of map_bytes each
+    pdl_launch_dependents();
+    if (CSTART > 0) {
+        // nothing parked in this CTA's tiles (always the case while epsilon = 1): leave at once.  The flag was
+        // written by K0, which our predecessor (the pull of sub-step 0) waited for before it let us start.
+        pdl_wait();
+        if (ra.defer_flags[blockIdx.x] == 0u) return;
+    }
+    {   // tables and maps
+        const uint4 *src_own = &ra.tabs->own[0][0];
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.own[0][0])[i] = __ldg(src_own + i);
+        const uint2 *src_oth = &ra.tabs->oth[0][0];
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.oth[0][0])[i] = __ldg(src_oth + i);
+        if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&ra.tabs->nth[threadIdx.x]);
+        uint4 *m4 = reinterpret_cast<uint4 *>(maps);
+        const uint32_t n16 = (uint32_t)kMaps * (ra.map_bytes >> 4);
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0}; S.any_deferred = 0u; }
+    }
+    __syncthreads();
+    const uint32_t tiles = (ra.n_envs + 31u) >> 5;
+    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
+    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    StepCounts cnt;
+    bool deferred_any = false;
+    uint32_t t = t0 + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
+    while (t < t1) {
+        const uint32_t e = t * 32u + lane, tn = t + n_warps;
+        uint4 rec_next = make_uint4(0u, 0u, 0u, 0u); // the next tile's records are in flight during this tile's work
+        if (tn < t1 && tn * 32u + lane < ra.n_envs) rec_next = ra.recs[tn * 32u + lane];
+        const uint32_t pending = (rec.w >> 8) & 7u;
+        uint32_t episode = rec.z & 0xFFFFu;
+        const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
+        if (e < ra.n_envs && live && pending == (uint32_t)CSTART) {
+            uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            uint32_t steps = rec.z >> 16;
+            const uint32_t env = ra.env_id_base + e;
+            // epsilon schedule; the first segment (40 % of the episodes, most of the steps) costs one compare
+            uint32_t eps16 = lp.eps_q16[0];
+            if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
+            uint32_t w[NC];
+            if (CSTART == 0) { // one Philox block per env and round: word c belongs to car c
+                const uint4 p = philox4x32_10((uint32_t)ra.round, (uint32_t)(ra.round >> 32), 0, 0, lp.seed, env);
+                w[0] = p.x;
+                if (NC > 1) w[NC - 1] = p.y;
+            } else {
+                w[NC - 1] = ra.rng_words[e]; // saved by K0 when it parked the lane
+            }
+            uint32_t new_pending = 0;
+            uint32_t key;
+            bool moved, explore;
+            if (CSTART == 0) {
+                if (round_car_step<NC, 0>(S, cfg, ra.tabs, ra, cars, w[0], eps16, true, key, moved, explore) == kStepDone)
+                    maps[key] = 1;
+                steps += moved;
+                cnt.steps += moved;
+                cnt.explore += explore;
+            }
+            if (NC > 1) {
+                const int r = round_car_step<NC, NC - 1>(S, cfg, ra.tabs, ra, cars, w[NC - 1], eps16, CSTART > 0, key, moved, explore);
+                if (r == kStepDone) maps[(uint32_t)(kMaps - 1) * ra.map_bytes + key] = 1;
+                if (r == kStepDefer) { // park: K1 finishes this lane after the pull of sub-step 0
+                    new_pending = 1;
+                    ra.rng_words[e] = w[NC - 1];
+                    deferred_any = true;
+                }
+                steps += moved;
+                cnt.steps += moved;
+                cnt.explore += explore;
+            }
+            steps = steps > 0xFFFFu ? 0xFFFFu : steps;
+            if (!new_pending) { // end of the round-robin round (qlearning.py:233)
+                bool finished = all_done<NC>(cars);
+                bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+                if (finished || capped) {
+                    cnt.episodes += 1;
+                    cnt.capped += capped;
+                    episode = episode + 1;
+                    steps = 0;
+                    rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
+                    cars = initial_cars<NC>(cfg, heading_word(ra.round, 2, lp.seed, env));
+                }
+            }
+            rec.x = (uint32_t)cars;
+            rec.y = (uint32_t)(cars >> 32);
+            rec.z = (episode & 0xFFFFu) | (steps << 16);
+            rec.w = (rec.w & ~0x700u) | (new_pending << 8);
+            ra.recs[e] = rec;
+        }
+        rec = rec_next;
+        t = tn;
+    }
+    if (CSTART == 0 && NC > 1 && __any_sync(0xFFFFFFFFu, deferred_any) && lane == 0) S.any_deferred = 1u;
+    __syncthreads();
+    if (CSTART == 0 && NC > 1 && threadIdx.x == 0) ra.defer_flags[blockIdx.x] = S.any_deferred;
+    // bytes -> bits: 32 keys = two uint4 -> one word; (w * 0x01020408) >> 24 packs four 0/1 bytes into a nibble
+#pragma unroll
+    for (int m = 0; m < kMaps; m++) {
+        const uint4 *map4 = reinterpret_cast<const uint4 *>(maps + (uint32_t)m * ra.map_bytes);
+        const uint32_t n16 = ra.map_bytes >> 4;
+        uint32_t *out = (m == 0 ? ra.bits_a : ra.bits_b) + (size_t)blockIdx.x * ra.words_per_cta;
+        for (uint32_t wd = threadIdx.x; wd < ra.words_per_cta; wd += blockDim.x) {
+            uint32_t bits = 0;
+            if (2u * wd < n16) {
+                const uint4 lo = map4[2u * wd];
+                bits = ((lo.x * 0x01020408u) >> 24) | (((lo.y * 0x01020408u) >> 24) << 4) |
+                       (((lo.z * 0x01020408u) >> 24) << 8) | (((lo.w * 0x01020408u) >> 24) << 12);
+            }
+            if (2u * wd + 1u < n16) {
+                const uint4 hi = map4[2u * wd + 1u];
+                bits |= (((hi.x * 0x01020408u) >> 24) << 16) | (((hi.y * 0x01020408u) >> 24) << 20) |
+                        (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
+            }
+            out[wd] = bits;
+        }
+    }
+    flush_counts<true>(cnt, S.cc, 0u, ctl);
+    pdl_wait();
+}
+
+} // namespace mdpp

@@ -278,6 +278,62 @@ def test_batched_qlearning_matches_oracle(case):
         assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
 
 
+FUSED = [
+    ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 300, 1024, 10, 1400, 7),
+    ("b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 0, 777, 8, 900, 50),
+    ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 200, 1000, 12, 600, 3),
+]
+
+
+@pytest.mark.parametrize("case", FUSED, ids=[c[0] for c in FUSED])
+def test_train_rounds_fused_path_matches_oracle(case):
+    """mdpp_q_train_rounds on 1- and 2-car tables takes the fused round kernels (q_round.cuh: table-driven
+    steps, car 1 stepped in the same pass when it explores, parked and finished by the catch-up kernel
+    when it acts greedily).  The episode budget is small so that the run crosses every epsilon segment
+    (1, .8, .5, .3, .15, 0) and ends with frozen envs; table, records and counters must equal the
+    oracle's sub-step-by-sub-step restatement bit for bit."""
+    m, BatchedEnv, BatchedQLearner, orc = _mods()
+    name, block, boxes, idx, choose, bad, cap, n, episodes, rounds, chunk = case
+    badtxt = bad_states_text(block) if bad else None
+    sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
+    env = BatchedEnv(sc, n, seed=17)
+    lr = BatchedQLearner(env, episodes=episodes, seed=17)
+    ob = orc.Batch(orc.Config(m.layout_3[block]), n, boxes, idx, choose, badtxt, cap)
+    ob.reset(seed=17)
+    oq = orc.QTable(f32=True)
+    olp = orc.learner(episodes, seed=17)
+    done = 0
+    while done < rounds:
+        k = min(chunk, rounds - done)
+        lr.train_rounds(k)
+        for r in range(done, done + k):
+            ob.q_round(oq, olp, r)
+        done += k
+        if done in (chunk, rounds) or done % (chunk * 20) == 0:  # checkpoints along the way
+            q = lr.q.cpu().numpy()
+            items = [x for x in oq.items() if x[1] != "B"]
+            for s, a, v in items:
+                assert q[sc.encode(s), A5.index(a)] == np.float32(v), (done, s, a)
+            assert np.count_nonzero(q[:, :5]) == sum(1 for _, _, v in items if v != 0.0)
+    cars = {k: v.cpu().numpy() for k, v in env.cars().items()}
+    for e in range(0, n, 3):
+        oc = ob.env_cars(e)
+        assert [int(x) for x in cars["node"][e]] == [c[0] for c in oc], e
+        assert [int(x) for x in cars["dest_index"][e]] == [c[1] for c in oc]
+        assert [int(x) for x in cars["done"][e]] == [c[2] for c in oc]
+        assert [int(x) for x in cars["ghost"][e]] == [_ghost_of(c[2], c[3]) for c in oc]
+        assert (int(cars["episode"][e]), int(cars["steps"][e])) == ob.counters(e)
+    gs, ws = env.stats(), ob.stats()
+    for k in ("agent_steps", "episodes_done", "episodes_capped", "explore_steps"):
+        assert gs[k] == ws[k], k
+    assert gs["q_updates"] == gs["agent_steps"]
+    assert gs["touched_keys"] == ob.touched_keys()
+    assert 0 < gs["explore_steps"] < gs["agent_steps"]          # both kinds of decisions happened
+    assert int((cars["episode"] >= episodes).sum()) > 0           # some envs used up their budget
+    assert ob.disagreements() == 0
+    assert int((env.records[:, 3] & 0x700).sum()) == 0            # no lane is left parked
+
+
 def test_full_size_properties():
     """BASELINE size (2^20 envs, layout 3 block 2, 2 cars): determinism, shard invariance
     (env ids key the RNG, so two half-size shards equal one full batch) and counter identities."""
