@@ -95,6 +95,12 @@ struct mdpp_handle {
     bool chain;             // the previous launch on the stream was one of our learner kernels
     uint32_t smem_configured; // env-kernel variants whose dynamic shared-memory limit has been raised
     uint32_t round_parity;    // fused rounds alternate between two sets of mark regions
+    // Upper bound on every env's episode counter at the current point of the stream.  While it is below the
+    // end of an epsilon = 1 schedule segment no car can act greedily, so the fused round needs no catch-up
+    // kernel.  Grows by one per round launched; tightened to the device's own maximum at every stats fetch
+    // as long as only learner kernels (which maintain that maximum) have advanced episodes since the last reset.
+    int64_t ep_bound;
+    bool ep_device_max_valid;
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
 };
 
@@ -250,6 +256,8 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->chain = false;
     h->smem_configured = 0;
     h->round_parity = 0;
+    h->ep_bound = 0; // the workspace is zeroed below: every episode counter starts at 0
+    h->ep_device_max_valid = true;
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
     h->dev.bad_bitmap = (const uint32_t *)(h->ws + cv.bad);
     int devid = 0;
@@ -301,7 +309,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
     delete ft;
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, sizeof(mdpp_stats) * kStatSlots);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, (sizeof(mdpp_stats) + sizeof(uint32_t)) * kStatSlots);
     if (e != cudaSuccess) {
         delete h;
         return fail(MDPP_ECUDA, "workspace initialisation failed: %s", cudaGetErrorString(e));
@@ -340,7 +348,12 @@ int mdpp_reset(mdpp_handle *h, const uint8_t *env_mask, const uint8_t *headings,
     MDPP_DISPATCH_NC(h, reset_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
                      env_mask, headings, seed, zero_counters);
     MDPP_CUDA(cudaGetLastError());
-    if (zero_counters && !env_mask) MDPP_CUDA(cudaMemsetAsync(h->ws + h->cv.dl, 0xFF, (size_t)h->n_envs * 4, s));
+    if (zero_counters && !env_mask) {
+        MDPP_CUDA(cudaMemsetAsync(h->ws + h->cv.dl, 0xFF, (size_t)h->n_envs * 4, s));
+        MDPP_CUDA(cudaMemsetAsync(control_of(h)->max_episode, 0, sizeof(uint32_t) * kStatSlots, s));
+        h->ep_bound = 0;
+        h->ep_device_max_valid = true;
+    }
     return MDPP_OK;
 }
 
@@ -396,6 +409,8 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
                      h->env_id_base, rounds, first_round, seed, reward_kind, action, reward, done, next_idx,
                      control_of(h));
     MDPP_CUDA(cudaGetLastError());
+    h->ep_bound += rounds; // auto-reset starts at most one new episode per round
+    h->ep_device_max_valid = false;
     return MDPP_OK;
 }
 
@@ -527,6 +542,11 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
 #undef MDPP_QENV_K
 #undef MDPP_QENV_C
 #undef MDPP_QENV
+    if (car_slot == h->cfg.n_cars - 1) h->ep_bound += 1; // the end-of-round reset starts at most one new episode
+    if (lp->flags & MDPP_LEARN_DETECT) { // a flagged env jumps to the end of its episode budget
+        h->ep_bound = (int64_t)1 << 40;
+        h->ep_device_max_valid = false;
+    }
     h->chain = true;
     return MDPP_OK;
 }
@@ -572,6 +592,9 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
     const uint32_t P = h->round_parity;
     h->round_parity ^= 1u;
+    // every env still in an epsilon = 1 segment: every coin says "explore", no lane can be parked
+    const bool pure = lp->eps_q16[0] >= 65536u && h->ep_bound < (int64_t)lp->eps_threshold[0];
+    h->ep_bound += 1;
     RoundArgs ra{};
     ra.recs = recs_of(h);
     ra.n_envs = (uint32_t)h->n_envs;
@@ -616,14 +639,15 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     int rc = q_pull_launch(h, cur, alt, lp, s, &mk);
     if (rc) return rc;
     std::swap(cur, alt);
-    // K1: the lanes whose car 1 acts greedily, against the table after the pull of sub-step 0
-    ra.q = cur;
-    ra.bits_a = mark_region(h, P, 2);
-    ra.bits_b = nullptr;
-    MDPP_ROUND_K((q_round_kernel<2, 1>), round_smem_bytes(2, ra.map_bytes, 1), 30);
     mk.cta_bits = mark_region(h, P, 1);
-    mk.cta_bits2 = mark_region(h, P, 2);
-    mk.flags2 = ra.defer_flags;
+    if (!pure) { // K1: the lanes whose car 1 acts greedily, against the table after the pull of sub-step 0
+        ra.q = cur;
+        ra.bits_a = mark_region(h, P, 2);
+        ra.bits_b = nullptr;
+        MDPP_ROUND_K((q_round_kernel<2, 1>), round_smem_bytes(2, ra.map_bytes, 1), 30);
+        mk.cta_bits2 = mark_region(h, P, 2);
+        mk.flags2 = ra.defer_flags;
+    }
     rc = q_pull_launch(h, cur, alt, lp, s, &mk);
     if (rc) return rc;
     std::swap(cur, alt);
@@ -746,6 +770,10 @@ int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *a
                      reward_kind, actions, next_features, reward, next_legal, done, status, auto_reset, round, seed,
                      control_of(h));
     MDPP_CUDA(cudaGetLastError());
+    if (auto_reset && car_slot == h->cfg.n_cars - 1) {
+        h->ep_bound += 1;
+        h->ep_device_max_valid = false;
+    }
     return MDPP_OK;
 }
 
@@ -788,9 +816,16 @@ int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *s
     if (!h || !out_host) return fail(MDPP_EINVAL, "handle / out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     mdpp_stats *slots = h->stat_slots; // the device keeps kStatSlots privatised copies; summed here
+    uint32_t *max_ep = (uint32_t *)(slots + kStatSlots);
     MDPP_CUDA(cudaMemcpyAsync(slots, control_of(h)->stats, sizeof(mdpp_stats) * kStatSlots, cudaMemcpyDeviceToHost, s));
+    MDPP_CUDA(cudaMemcpyAsync(max_ep, control_of(h)->max_episode, sizeof(uint32_t) * kStatSlots, cudaMemcpyDeviceToHost, s));
     if (reset) MDPP_CUDA(cudaMemsetAsync(control_of(h)->stats, 0, sizeof(mdpp_stats) * kStatSlots, s));
     MDPP_CUDA(cudaStreamSynchronize(s));
+    if (h->ep_device_max_valid) { // everything launched so far has completed: the device's maximum is exact
+        uint32_t m = 0;
+        for (int i = 0; i < kStatSlots; i++) m = std::max(m, max_ep[i]);
+        h->ep_bound = std::min<int64_t>(h->ep_bound, (int64_t)m);
+    }
     mdpp_stats t;
     memset(&t, 0, sizeof t);
     for (int i = 0; i < kStatSlots; i++) {

@@ -21,6 +21,9 @@ struct Control {
     // zeroes [p^1] for the next sub-step -- no grid-wide fence or "last block" ticket is needed
     uint32_t touched_count[2];
     uint32_t pad[14];
+    // largest per-env episode counter the learner kernels have produced, privatised like the stats; the host
+    // uses it (mdpp_get_stats_host) to tighten its bound on "is any env past the epsilon = 1 segment?"
+    uint32_t max_episode[kStatSlots];
 };
 
 struct StatAcc {

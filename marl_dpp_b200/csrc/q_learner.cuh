@@ -138,6 +138,7 @@ struct EnvArgs {
 struct StepCounts {
     uint32_t steps = 0, explore = 0, episodes = 0, capped = 0;
     int32_t reward = 0;
+    uint32_t max_episode = 0; // largest episode counter this thread has written
 };
 
 // One agent-step of car C in env e (record `rec` already loaded).  Returns true and sets `key` when the env
@@ -271,6 +272,7 @@ __device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &
             cnt.episodes += 1;
             cnt.capped += capped;
             episode = episode + 1;
+            cnt.max_episode = max(cnt.max_episode, episode);
             steps = 0;
             rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
             cars = initial_cars<NC>(cfg, heading_word(ea.round, 2, lp.seed, env));
@@ -293,6 +295,7 @@ __device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &
 struct CtaCounters {
     uint32_t steps, explore, episodes, capped;
     int32_t reward;
+    uint32_t max_episode;
 };
 template <bool PLAIN>
 __device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &cc, uint32_t lflags, Control *ctl) {
@@ -307,6 +310,10 @@ __device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &c
         if (ep >> 16) atomicAdd(&cc.capped, ep >> 16);
         if (!PLAIN && rs) atomicAdd(&cc.reward, rs);
     }
+    if (ep) { // some lane of this warp started a new episode (rare)
+        const uint32_t me = __reduce_max_sync(0xFFFFFFFFu, c.max_episode);
+        if ((threadIdx.x & 31u) == 0) atomicMax(&cc.max_episode, me);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         mdpp_stats *slot = &ctl->stats[blockIdx.x & (kStatSlots - 1)];
@@ -315,6 +322,7 @@ __device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &c
         if (cc.explore) atomicAdd((unsigned long long *)&slot->explore_steps, (unsigned long long)cc.explore);
         if (cc.episodes) atomicAdd((unsigned long long *)&slot->episodes_done, (unsigned long long)cc.episodes);
         if (cc.capped) atomicAdd((unsigned long long *)&slot->episodes_capped, (unsigned long long)cc.capped);
+        if (cc.max_episode) atomicMax(&ctl->max_episode[blockIdx.x & (kStatSlots - 1)], cc.max_episode);
         if (!PLAIN && cc.reward) atomicAdd((unsigned long long *)&slot->reward_sum, (unsigned long long)(long long)cc.reward);
     }
 }
@@ -324,7 +332,7 @@ template <int NC, int C, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
 q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
     __shared__ CtaCounters cc;
-    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0};
+    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
     // PDL: the pull kernel that follows may be scheduled as SM slots free up (it waits for this grid to
     // complete before it looks at the marks)
     pdl_launch_dependents();
@@ -372,7 +380,7 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
     uint32_t *map32 = reinterpret_cast<uint32_t *>(smem_map4);
     const uint32_t n16 = BITS ? (mk.words_per_cta + 3u) >> 2 : (mk.n_keys + 15u) >> 4;
     for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) smem_map4[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0};
+    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
     pdl_launch_dependents();
     __syncthreads();
     const int64_t tiles = (ea.n_envs + 31) >> 5;

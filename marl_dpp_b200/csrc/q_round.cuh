@@ -181,7 +181,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
         uint4 *m4 = reinterpret_cast<uint4 *>(maps);
         const uint32_t n16 = (uint32_t)kMaps * (ra.map_bytes >> 4);
         for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0}; S.any_deferred = 0u; }
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
     }
     __syncthreads();
     const uint32_t tiles = (ra.n_envs + 31u) >> 5;
@@ -245,6 +245,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                     cnt.episodes += 1;
                     cnt.capped += capped;
                     episode = episode + 1;
+                    cnt.max_episode = max(cnt.max_episode, episode);
                     steps = 0;
                     rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
                     cars = initial_cars<NC>(cfg, heading_word(ra.round, 2, lp.seed, env));
