@@ -192,6 +192,11 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp
 int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp_host,
                              uint64_t first_round, int rounds, mdpp_stats *stats_host, void *stream);
 
+/* Profiling hook: launches ONLY the env-side kernel of one fused round (1- and 2-car tables, flags == 0) so
+ * that bench.py can time the dominant kernel alone with CUDA events.  The marks it leaves are never
+ * pulled: use it on a handle you do not train further. */
+int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t round, void *stream);
+
 /* ---- DQN feed: the env-facing half of the noisy double DQN's collection loop (reference
  * src/algorithms/dqn_open_source.py:490-526); the MLP stays in PyTorch.  observe = encodestate(car, 1)
  * (ghost side effect included) -> RL.convert(state) as 80 {0,1} bytes per env (:245-313) + give_mask

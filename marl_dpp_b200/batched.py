@@ -287,6 +287,13 @@ class BatchedQLearner:
         self.round += int(rounds)
         return s.as_dict()
 
+    def profile_env_kernel(self):
+        """Profiling hook: only the env-side kernel of one fused round (its marks are never pulled)."""
+        env = self.env
+        with torch.cuda.device(env.device):
+            _lib.check(env._L.mdpp_q_profile_env_kernel(env._h, _ptr(self.q), C.byref(self.params), self.round, _stream()))
+        self.round += 1
+
     def sync_replicas(self, group=None):
         """Average the per-GPU Q replicas: one NCCL all-reduce (AVG) over NVLink, in place."""
         from . import parallel

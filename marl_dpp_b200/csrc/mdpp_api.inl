@@ -841,6 +841,41 @@ int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *s
     return MDPP_OK;
 }
 
+int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64_t round, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
+    if (lp->flags != 0 || !round_eligible(h)) return fail(MDPP_EINVAL, "no fused round kernel for this table / these flags");
+    cudaStream_t s = (cudaStream_t)stream;
+    h->chain = false;
+    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
+    RoundArgs ra{};
+    ra.recs = recs_of(h);
+    ra.n_envs = (uint32_t)h->n_envs;
+    ra.env_id_base = h->env_id_base;
+    ra.round = round;
+    ra.q = q;
+    ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
+    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)h->round_parity * kMaxEnvCtas;
+    ra.bits_a = mark_region(h, h->round_parity, 0);
+    ra.bits_b = mark_region(h, h->round_parity, 1);
+    ra.words_per_cta = h->cv.words_per_cta;
+    ra.n_keys = (uint32_t)keys;
+    ra.map_bytes = (uint32_t)(((keys + 15) / 16) * 16);
+    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    const size_t smem = round_smem_bytes(h->cfg.n_cars, ra.map_bytes, h->cfg.n_cars);
+    LearnLaunch ll(h, env_ctas(h), s, kEnvSmemThreads, smem);
+    if (h->cfg.n_cars == 1) {
+        MDPP_CUDA(cudaFuncSetAttribute(q_round_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_round_kernel<1, 0>, h->dev, *lp, ra, control_of(h)));
+    } else {
+        MDPP_CUDA(cudaFuncSetAttribute(q_round_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_round_kernel<2, 0>, h->dev, *lp, ra, control_of(h)));
+    }
+    h->ep_bound += 1;
+    return MDPP_OK;
+}
+
 int mdpp_q_train_rounds_host(mdpp_handle *h, float *q, const mdpp_learner *lp_host, uint64_t first_round, int rounds,
                              mdpp_stats *stats_host, void *stream) {
     int rc = mdpp_q_train_rounds(h, q, lp_host, first_round, rounds, stream);
