@@ -201,6 +201,24 @@ static void build_fast_tabs(const mdpp_config &c, FastTabs &t) {
                 }
             }
         }
+        for (int di = 0; di < 2; di++) { // the move itself: successor + update_car, per action
+            const uint32_t dnode = c.dest_node[c.car_dest[car][di]];
+            for (int node = 0; node < MDPP_NODES; node++)
+                for (int a = 0; a < MDPP_N_ACT; a++) {
+                    static const int rot[MDPP_N_ACT] = {0, 3, 1, 0, 2}; // S, L (heading - 1), R (+ 1), F, T (- 2)
+                    uint32_t nn = a == MDPP_A_F ? c.fwd[node] : (uint32_t)((node & ~3) | ((node + rot[a]) & 3));
+                    uint32_t ndi = (uint32_t)di, done = 0;
+                    if (nn == MDPP_NONE) nn = (uint32_t)node; // F off the graph is never legal
+                    if (nn == dnode) {
+                        if (di == c.tcdi) {
+                            done = 1;
+                            nn = (uint32_t)c.parking_node;
+                        }
+                        ndi ^= 1u;
+                    }
+                    t.next[car][node | (di << 7)][a] = (uint16_t)((nn & 127u) | (ndi << 7) | (done << 8));
+                }
+        }
         // ghost of a finished car: [final box, final box] (reference src/env_gym.py:313-317)
         const uint32_t gdbox = c.dest_node_box[c.car_dest[car][c.tcdi]], gbox18 = c.dest_box[gdbox];
         if (c.src_box_idx[gbox18] != MDPP_NONE) {
@@ -553,12 +571,12 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
 
 // dense: qsrc -> qdst (whole table, marked keys substituted).  list: in place on qsrc, two passes.
 static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s,
-                         const Marks *marks = nullptr) {
+                         const Marks *marks = nullptr, int early_trigger = 0) {
     const Marks mk = marks ? *marks : marks_of(h);
     if (h->cv.dense) {
         LearnLaunch ll(h, grid_for(mk.n_keys), s);
         MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
-                                     lp->discount, control_of(h)));
+                                     lp->discount, early_trigger, control_of(h)));
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)mk.capacity + kThreads - 1) / kThreads,
                                                           (int64_t)h->sm_count * 8);
@@ -636,7 +654,7 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     ra.bits_b = mark_region(h, P, 1);
     MDPP_ROUND_K((q_round_kernel<2, 0>), round_smem_bytes(2, ra.map_bytes, 2), 29);
     mk.cta_bits = mark_region(h, P, 0);
-    int rc = q_pull_launch(h, cur, alt, lp, s, &mk);
+    int rc = q_pull_launch(h, cur, alt, lp, s, &mk, 1); // followed by K1 or the second pull: both wait first
     if (rc) return rc;
     std::swap(cur, alt);
     mk.cta_bits = mark_region(h, P, 1);

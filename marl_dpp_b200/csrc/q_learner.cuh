@@ -433,8 +433,7 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
 // pull side: the reference update of one key, from the snapshot table
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float td_value(const float *__restrict__ q, const uint32_t *__restrict__ sinfo, uint32_t s,
-                                          uint32_t a, float qa, float alpha, float discount) {
-    const uint32_t i = __ldg(sinfo + s);
+                                          uint32_t i /* = sinfo[s] */, uint32_t a, float qa, float alpha, float discount) {
     const uint32_t nl = si_node(i);
     const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
     const uint32_t nnl = a == MDPP_A_F ? si_fwd(i) : ((nl & ~3u) | ((nl + rot) & 3u));
@@ -471,11 +470,26 @@ __device__ __forceinline__ void mark_visited(uint32_t *__restrict__ visited, uin
 // key replaced by its update.
 __global__ void __launch_bounds__(kThreads)
 q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Marks mk, float alpha, float discount,
-                    Control *ctl) {
-    pdl_wait();              // the env kernel that wrote the bitmaps has completed
-    pdl_launch_dependents(); // the next env kernel may start; it waits for us before its first Q read
+                    int early_trigger, Control *ctl) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
     const uint32_t word = key >> 5; // warp-uniform
+    // This grid is resident (programmatic dependent launch) while its predecessor still runs: pull the lines it
+    // is going to read into L2 meanwhile.  A prefetch has no ordering requirement: L2 is the point of coherence,
+    // so lines the predecessor writes later are simply updated there.
+    if (key < mk.n_keys) {
+        if ((key & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(qold + key));
+        if ((key & 255u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(mk.sinfo + (key >> 3)));
+    }
+    // early_trigger: the kernel after this one waits (griddepcontrol.wait) before it touches anything this chain
+    // produces -- another pull or the catch-up kernel -- so it may be made resident right away and its launch
+    // latency disappears from the critical path.  The last pull of a round is followed by a round kernel, whose
+    // prologue reads records before waiting: that one is released only once the env kernel has completed.
+    if (early_trigger) pdl_launch_dependents();
+    pdl_wait();              // the env kernel that wrote the bitmaps has completed
+    if (!early_trigger) pdl_launch_dependents(); // the next env kernel may start; it waits for us before its first Q read
+    // the state's info word is requested together with the bitmap words (it does not depend on them): a marked
+    // key then needs one more round trip (successor row + info), not two
+    const uint32_t info = key < mk.n_keys ? __ldg(mk.sinfo + (key >> 3)) : 0u;
     uint32_t bits = 0;
     if (word < mk.words_per_cta) {
         for (uint32_t b = lane; b < mk.n_ctas; b += 32u) bits |= mk.cta_bits[(size_t)b * mk.words_per_cta + word];
@@ -488,7 +502,7 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
     if (key < mk.n_keys) {
         float v = qold[key];
         if ((bits >> lane) & 1u) {
-            v = td_value(qold, mk.sinfo, key >> 3, key & 7u, v, alpha, discount);
+            v = td_value(qold, mk.sinfo, key >> 3, info, key & 7u, v, alpha, discount);
             mark_visited(mk.visited, key);
             touched = 1;
         }
@@ -509,7 +523,7 @@ q_pull_list_compute_kernel(const float *__restrict__ q, Marks mk, float alpha, f
     if (blockIdx.x == 0 && threadIdx.x == 0) *mk.count_other = 0; // the next sub-step appends under the other parity
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t key = mk.list[i];
-        mk.vals[i] = td_value(q, mk.sinfo, key >> 3, key & 7u, __ldg(q + key), alpha, discount);
+        mk.vals[i] = td_value(q, mk.sinfo, key >> 3, __ldg(mk.sinfo + (key >> 3)), key & 7u, __ldg(q + key), alpha, discount);
     }
 }
 

@@ -32,6 +32,8 @@ struct FastTabs {
     uint2 oth[MDPP_MAX_CARS][256];  // same index, car seen as an "other"
     uint2 ghost[MDPP_MAX_CARS];     // oth-format entry of the finished car's ghost
     uint32_t nth[32];               // per 5-bit mask: positions of its set bits, 3 bits each, lowest first
+    alignas(16) uint16_t next[MDPP_MAX_CARS][256][8]; // [car][node | di << 7][action] -> node | di << 7 | done << 8 after the move:
+                                          // successor (src/env_gym.py:256-265) + update_car (:386-441) folded
 };
 // own.x: bits 0-9 dnidx * n_local_nodes + node_local | 10-16 destination node | 17-23 F successor (127 none)
 //        | 24-28 base legal mask | 29-31 destination-box index
@@ -44,6 +46,7 @@ template <int NC>
 struct RoundSmem {
     uint4 own[NC][256];
     uint2 oth[NC][256];
+    uint16_t next[NC][256][8];
     uint32_t nth[32];
     CtaCounters cc;
     uint32_t any_deferred;
@@ -137,19 +140,8 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
         }
     }
     key = sidx * MDPP_Q_ROW + a;
-    // ---- successor (src/env_gym.py:256-265) and update_car (:386-441) ----
-    const uint32_t pnode = f & 127u, dnode = (own.x >> 10) & 127u;
-    const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
-    uint32_t node = a == MDPP_A_F ? ((own.x >> 17) & 127u) : ((pnode & ~3u) | ((pnode + rot) & 3u));
-    uint32_t di = (f >> 7) & 1u, done = 0;
-    if (node == dnode) {
-        if ((int)di == cfg.tcdi) {
-            done = 0x100u;
-            node = (uint32_t)cfg.parking_node;
-        }
-        di ^= 1u;
-    }
-    const uint32_t nf = node | (di << 7) | done | (f & 0xE00u);
+    // ---- successor (src/env_gym.py:256-265) and update_car (:386-441): one table entry ----
+    const uint32_t nf = (uint32_t)S.next[C][f & 0xFFu][a] | (f & 0xE00u);
     cars = (nc & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
     moved = true;
     return kStepDone;
@@ -167,16 +159,28 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     uint8_t *maps = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes; // kMaps byte maps of map_bytes each
     pdl_launch_dependents();
     if (CSTART > 0) {
-        // nothing parked in this CTA's tiles (always the case while epsilon = 1): leave at once.  The flag was
-        // written by K0, which our predecessor (the pull of sub-step 0) waited for before it let us start.
+        // This grid may be resident while K0 still runs (the pull of sub-step 0 releases it early): wait for that
+        // pull -- and with it K0 -- to complete before looking at anything.  Then, if nothing was parked in this
+        // CTA's tiles, leave at once.
         pdl_wait();
         if (ra.defer_flags[blockIdx.x] == 0u) return;
     }
+    // the first tile's records are requested before the tables are staged (K0 reads them cold from HBM)
+    const uint32_t tiles = (ra.n_envs + 31u) >> 5;
+    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
+    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    uint32_t t = t0 + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
     {   // tables and maps
         const uint4 *src_own = &ra.tabs->own[0][0];
         for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.own[0][0])[i] = __ldg(src_own + i);
         const uint2 *src_oth = &ra.tabs->oth[0][0];
         for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.oth[0][0])[i] = __ldg(src_oth + i);
+        const uint4 *src_next = reinterpret_cast<const uint4 *>(&ra.tabs->next[0][0][0]); // 256 x 8 x u16 = 256 uint4 per car
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x)
+            reinterpret_cast<uint4 *>(&S.next[0][0][0])[i] = __ldg(src_next + i);
         if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&ra.tabs->nth[threadIdx.x]);
         uint4 *m4 = reinterpret_cast<uint4 *>(maps);
         const uint32_t n16 = (uint32_t)kMaps * (ra.map_bytes >> 4);
@@ -184,15 +188,8 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
         if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
     }
     __syncthreads();
-    const uint32_t tiles = (ra.n_envs + 31u) >> 5;
-    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
-    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     StepCounts cnt;
     bool deferred_any = false;
-    uint32_t t = t0 + warp;
-    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
     while (t < t1) {
         const uint32_t e = t * 32u + lane, tn = t + n_warps;
         uint4 rec_next = make_uint4(0u, 0u, 0u, 0u); // the next tile's records are in flight during this tile's work
