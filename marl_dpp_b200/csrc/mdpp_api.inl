@@ -26,15 +26,17 @@ static int fail(int code, const char *fmt, ...) {
                         "%s failed: %s", #call, cudaGetErrorString(err__));                     \
     } while (0)
 
-constexpr size_t kMaxByteMapKeys = 200 * 1024;    // shared-memory BYTE map of the persistent env kernel
-constexpr size_t kMaxDenseKeys = 8 * 200 * 1024;  // shared-memory BIT map (atomic OR) up to here; list mode beyond
-constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices reserved per parity (>= SM count)
-constexpr uint32_t kMarkRegions = 3;              // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1
+// marks of the dense modes are indexed by the compact key  state * 5 + action  (n_marks = n_states * 5)
+constexpr size_t kMaxByteMapMarks = 200 * 1024;   // shared-memory BYTE map of a persistent env CTA
+constexpr size_t kMaxDenseMarks = 8 * 200 * 1024; // shared-memory BIT map (atomic OR) up to here; list mode beyond
+constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices per region: sub-step kernels, one CTA per SM
+constexpr uint32_t kMaxRoundCtas = 320;           // ... fused round kernels, up to two CTAs per SM (byte-map tables only)
 
 struct Carve {
     size_t tables, nodetab, fast, rng, bad, recs, sinfo, qalt, marks, flags, bits, list, vals, visited, control, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
     uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
+    uint32_t cta_slots, regions; // layout of the bitmap array [parity][region][cta_slots][words_per_cta]
     bool dense;        // small table: byte marks + ping-pong pull; else bitmap + list + two-pass pull
 };
 
@@ -55,14 +57,17 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     // dense mode: the mark byte map of a persistent CTA lives in shared memory (one byte per key) and the pull
     // kernel sweeps the whole table once per sub-step (copy + substitute the marked keys) -- right while
     // the table is a few hundred KB.  Larger tables keep a touched bitmap + list in global memory.
-    c.dense = keys <= kMaxDenseKeys;
+    const size_t marks = (size_t)cfg.n_states * MDPP_N_ACT;
+    c.dense = marks <= kMaxDenseMarks;
     if (const char *env = getenv("MDPP_DENSE")) c.dense = c.dense && atoi(env) != 0;
     c.capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
-    c.words_per_cta = (uint32_t)(((keys + 31) / 32 + 3) & ~(size_t)3);
+    c.words_per_cta = (uint32_t)(((marks + 31) / 32 + 3) & ~(size_t)3);
+    c.cta_slots = marks <= kMaxByteMapMarks ? kMaxRoundCtas : kMaxEnvCtas;
+    c.regions = marks <= kMaxByteMapMarks ? 3 : 1; // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1
     if (c.dense) {
         c.qalt = take(keys * 4);
-        c.marks = take((size_t)2 * kMarkRegions * kMaxEnvCtas * c.words_per_cta * 4); // [parity][region][cta][word]
-        c.flags = take((size_t)2 * kMaxEnvCtas * 4);
+        c.marks = take((size_t)2 * c.regions * c.cta_slots * c.words_per_cta * 4); // [parity][region][cta][word]
+        c.flags = take((size_t)2 * c.cta_slots * 4);
         c.bits = c.list = c.vals = 0;
     } else {
         c.qalt = c.marks = c.flags = 0;
@@ -438,7 +443,12 @@ static unsigned env_ctas(mdpp_handle *h) { // persistent env CTAs (dense mode): 
 }
 
 static uint32_t *mark_region(mdpp_handle *h, uint32_t parity, uint32_t region) {
-    return (uint32_t *)(h->ws + h->cv.marks) + ((size_t)parity * kMarkRegions + region) * kMaxEnvCtas * h->cv.words_per_cta;
+    return (uint32_t *)(h->ws + h->cv.marks) + ((size_t)parity * h->cv.regions + region) * h->cv.cta_slots * h->cv.words_per_cta;
+}
+
+static unsigned round_ctas(mdpp_handle *h) { // persistent CTAs of the fused round kernels
+    const int64_t tiles = (h->n_envs + 31) / 32;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)h->sm_count * kRoundCtasPerSm, kMaxRoundCtas), tiles));
 }
 
 static Marks marks_of(mdpp_handle *h) {
@@ -462,6 +472,7 @@ static Marks marks_of(mdpp_handle *h) {
     m.sinfo = (const uint32_t *)(h->ws + h->cv.sinfo);
     m.capacity = h->cv.capacity;
     m.n_keys = (uint32_t)keys;
+    m.n_marks = (uint32_t)((size_t)h->cfg.n_states * MDPP_N_ACT);
     return m;
 }
 
@@ -515,8 +526,8 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     ea.reward_out = reward;
     ea.dl_state = (uint32_t *)(h->ws + h->cv.dl);
     const Marks mk = marks_of(h);
-    const bool bitmap = (size_t)mk.n_keys > kMaxByteMapKeys;
-    const size_t map_bytes = bitmap ? (size_t)mk.words_per_cta * 4 : (((size_t)mk.n_keys + 15) / 16) * 16;
+    const bool bitmap = (size_t)mk.n_marks > kMaxByteMapMarks;
+    const size_t map_bytes = bitmap ? (size_t)mk.words_per_cta * 4 : (((size_t)mk.n_marks + 15) / 16) * 16;
     LearnLaunch ll = h->cv.dense ? LearnLaunch(h, env_ctas(h), s, kEnvSmemThreads, map_bytes)
                                  : LearnLaunch(h, grid_for(h->n_envs), s);
     ll.cfg.attrs = &ll.attr; // the struct was copied: re-point at this copy's attribute
@@ -574,7 +585,7 @@ static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_le
                          const Marks *marks = nullptr, int early_trigger = 0) {
     const Marks mk = marks ? *marks : marks_of(h);
     if (h->cv.dense) {
-        LearnLaunch ll(h, grid_for(mk.n_keys), s);
+        LearnLaunch ll(h, grid_for(mk.n_marks), s);
         MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
                                      lp->discount, early_trigger, control_of(h)));
     } else {
@@ -598,9 +609,9 @@ static size_t round_smem_bytes(int n_cars, size_t map_bytes, int maps) {
 }
 static bool round_eligible(const mdpp_handle *h) {
     if (!h->cv.dense || h->cfg.n_cars > 2) return false;
-    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
-    if (keys > kMaxByteMapKeys) return false;
-    const size_t map_bytes = ((keys + 15) / 16) * 16;
+    const size_t marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
+    if (marks > kMaxByteMapMarks) return false;
+    const size_t map_bytes = ((marks + 15) / 16) * 16;
     const size_t need = h->cfg.n_cars == 1 ? round_smem_bytes(1, map_bytes, 1) : round_smem_bytes(2, map_bytes, 2);
     if (getenv("MDPP_FUSED") && atoi(getenv("MDPP_FUSED")) == 0) return false;
     return need <= (size_t)220 * 1024;
@@ -620,12 +631,12 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     ra.round = round;
     ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
     ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
-    ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)P * kMaxEnvCtas;
+    ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)P * h->cv.cta_slots;
     ra.words_per_cta = h->cv.words_per_cta;
     ra.n_keys = (uint32_t)keys;
-    ra.map_bytes = (uint32_t)(((keys + 15) / 16) * 16);
+    ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
-    const unsigned grid = env_ctas(h);
+    const unsigned grid = round_ctas(h);
     Marks mk = marks_of(h);
     mk.n_ctas = grid;
 #define MDPP_ROUND_K(KERNEL, SMEM, BIT)                                                                          \
@@ -634,7 +645,7 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
             MDPP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));    \
             h->smem_configured |= 1u << (BIT);                                                                   \
         }                                                                                                        \
-        LearnLaunch ll(h, grid, s, kEnvSmemThreads, (SMEM));                                                     \
+        LearnLaunch ll(h, grid, s, kRoundThreads, (SMEM));                                                       \
         MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ra, control_of(h)));                           \
         h->chain = true;                                                                                         \
     } while (0)
@@ -874,15 +885,15 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     ra.q = q;
     ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
     ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
-    ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)h->round_parity * kMaxEnvCtas;
+    ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)h->round_parity * h->cv.cta_slots;
     ra.bits_a = mark_region(h, h->round_parity, 0);
     ra.bits_b = mark_region(h, h->round_parity, 1);
     ra.words_per_cta = h->cv.words_per_cta;
     ra.n_keys = (uint32_t)keys;
-    ra.map_bytes = (uint32_t)(((keys + 15) / 16) * 16);
+    ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
     const size_t smem = round_smem_bytes(h->cfg.n_cars, ra.map_bytes, h->cfg.n_cars);
-    LearnLaunch ll(h, env_ctas(h), s, kEnvSmemThreads, smem);
+    LearnLaunch ll(h, round_ctas(h), s, kRoundThreads, smem);
     if (h->cfg.n_cars == 1) {
         MDPP_CUDA(cudaFuncSetAttribute(q_round_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_round_kernel<1, 0>, h->dev, *lp, ra, control_of(h)));

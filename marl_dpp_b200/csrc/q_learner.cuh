@@ -50,6 +50,7 @@ struct Marks {
     uint32_t capacity;
     uint32_t dense;
     uint32_t n_keys;
+    uint32_t n_marks; // dense: n_states * 5 -- marks are indexed by the compact key  state * 5 + action
 };
 
 // epsilon schedule (reference src/utils/utils.py:33-52, model 3) on the per-env episode counter
@@ -378,7 +379,7 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
     __shared__ CtaCounters cc;
     uint8_t *map = reinterpret_cast<uint8_t *>(smem_map4);
     uint32_t *map32 = reinterpret_cast<uint32_t *>(smem_map4);
-    const uint32_t n16 = BITS ? (mk.words_per_cta + 3u) >> 2 : (mk.n_keys + 15u) >> 4;
+    const uint32_t n16 = BITS ? (mk.words_per_cta + 3u) >> 2 : (mk.n_marks + 15u) >> 4;
     for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) smem_map4[i] = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
     pdl_launch_dependents();
@@ -397,8 +398,9 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
         if (e < ea.n_envs) {
             uint32_t key = 0;
             if (env_substep<NC, C, PLAIN>(cfg, lp, ea, e, rec, key, cnt)) {
-                if constexpr (BITS) atomicOr(map32 + (key >> 5), 1u << (key & 31u));
-                else map[key] = 1;
+                const uint32_t m = (key >> 3) * MDPP_N_ACT + (key & 7u); // compact key: no marks for the padding slots
+                if constexpr (BITS) atomicOr(map32 + (m >> 5), 1u << (m & 31u));
+                else map[m] = 1;
             }
         }
         rec = rec_next;
@@ -465,21 +467,15 @@ __device__ __forceinline__ void mark_visited(uint32_t *__restrict__ visited, uin
     if (!(*vis & vb)) atomicOr(vis, vb);
 }
 
-// dense mode: one thread per table word, one warp per 32 keys.  The warp ORs the per-CTA bitmaps of its
-// word (lane l reads CTAs l, l + 32, ...: all loads in flight at once), then qnew <- qold with every marked
-// key replaced by its update.
+// dense mode: one thread per compact key m = state * 5 + action (marks carry no padding slots), one warp per
+// bitmap word.  The warp ORs the per-CTA bitmaps of its word (lane l reads CTAs l, l + 32, ...: all loads in
+// flight at once), then qnew <- qold with every marked key replaced by its update (ping-pong: no in-place hazard).
 __global__ void __launch_bounds__(kThreads)
 q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Marks mk, float alpha, float discount,
                     int early_trigger, Control *ctl) {
-    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
-    const uint32_t word = key >> 5; // warp-uniform
-    // This grid is resident (programmatic dependent launch) while its predecessor still runs: pull the lines it
-    // is going to read into L2 meanwhile.  A prefetch has no ordering requirement: L2 is the point of coherence,
-    // so lines the predecessor writes later are simply updated there.
-    if (key < mk.n_keys) {
-        if ((key & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(qold + key));
-        if ((key & 255u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(mk.sinfo + (key >> 3)));
-    }
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const uint32_t word = m >> 5; // warp-uniform
+    const uint32_t s = m / MDPP_N_ACT, a = m - s * MDPP_N_ACT, key = s * MDPP_Q_ROW + a;
     // early_trigger: the kernel after this one waits (griddepcontrol.wait) before it touches anything this chain
     // produces -- another pull or the catch-up kernel -- so it may be made resident right away and its launch
     // latency disappears from the critical path.  The last pull of a round is followed by a round kernel, whose
@@ -489,7 +485,7 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
     if (!early_trigger) pdl_launch_dependents(); // the next env kernel may start; it waits for us before its first Q read
     // the state's info word is requested together with the bitmap words (it does not depend on them): a marked
     // key then needs one more round trip (successor row + info), not two
-    const uint32_t info = key < mk.n_keys ? __ldg(mk.sinfo + (key >> 3)) : 0u;
+    const uint32_t info = m < mk.n_marks ? __ldg(mk.sinfo + s) : 0u;
     uint32_t bits = 0;
     if (word < mk.words_per_cta) {
         for (uint32_t b = lane; b < mk.n_ctas; b += 32u) bits |= mk.cta_bits[(size_t)b * mk.words_per_cta + word];
@@ -499,14 +495,15 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
     }
     bits = __reduce_or_sync(0xFFFFFFFFu, bits);
     uint32_t touched = 0;
-    if (key < mk.n_keys) {
+    if (m < mk.n_marks) {
         float v = qold[key];
         if ((bits >> lane) & 1u) {
-            v = td_value(qold, mk.sinfo, key >> 3, info, key & 7u, v, alpha, discount);
+            v = td_value(qold, mk.sinfo, s, info, a, v, alpha, discount);
             mark_visited(mk.visited, key);
             touched = 1;
         }
         qnew[key] = v;
+        if (a < MDPP_Q_ROW - MDPP_N_ACT) qnew[key + MDPP_N_ACT] = qold[key + MDPP_N_ACT]; // padding slots 5..7 carried through
     }
     touched = __reduce_add_sync(0xFFFFFFFFu, touched);
     if (lane == 0 && touched)

@@ -69,7 +69,7 @@ struct RoundArgs {
 enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
 
 // One agent-step of car C on the unpacked record.  `cars` is committed (ghost counters of encodestate, the
-// move) unless the car is parked.  Returns kStepDone with `key` when a key was touched.
+// move) unless the car is parked.  Returns kStepDone with the compact key (state * 5 + action) when a key was touched.
 template <int NC, int C>
 __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
                                               const RoundArgs &ra, uint64_t &cars, uint32_t word, uint32_t eps16,
@@ -139,7 +139,7 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
             if (ok && (!have || qs[k] > best)) { best = qs[k]; a = k; have = true; }
         }
     }
-    key = sidx * MDPP_Q_ROW + a;
+    key = sidx * MDPP_N_ACT + a; // compact key (marks carry no padding slots)
     // ---- successor (src/env_gym.py:256-265) and update_car (:386-441): one table entry ----
     const uint32_t nf = (uint32_t)S.next[C][f & 0xFFu][a] | (f & 0xE00u);
     cars = (nc & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
@@ -148,8 +148,13 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
 }
 
 // CSTART = 0: K0, every live env, cars 0..NC-1 while they explore.  CSTART = 1 (NC = 2): K1, parked lanes only.
+#ifndef MDPP_ROUND_THREADS
+#define MDPP_ROUND_THREADS 1024
+#define MDPP_ROUND_CTAS_PER_SM 1
+#endif
+constexpr int kRoundThreads = MDPP_ROUND_THREADS, kRoundCtasPerSm = MDPP_ROUND_CTAS_PER_SM;
 template <int NC, int CSTART>
-__global__ void __launch_bounds__(kEnvSmemThreads, 1)
+__global__ void __launch_bounds__(kRoundThreads, kRoundCtasPerSm)
 q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     static_assert(NC >= 1 && NC <= 2 && CSTART < NC, "the fused round is built for 1- and 2-car tables");
     extern __shared__ uint4 smem_dyn[];
