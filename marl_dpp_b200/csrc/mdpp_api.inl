@@ -61,7 +61,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.dense = marks <= kMaxDenseMarks;
     if (const char *env = getenv("MDPP_DENSE")) c.dense = c.dense && atoi(env) != 0;
     c.capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
-    c.words_per_cta = (uint32_t)(((marks + 31) / 32 + 3) & ~(size_t)3);
+    c.words_per_cta = (uint32_t)(((marks + 31) / 32 + 7) & ~(size_t)7); // whole blocks of 8 words (slice_index)
     c.cta_slots = marks <= kMaxByteMapMarks ? kMaxRoundCtas : kMaxEnvCtas;
     c.regions = marks <= kMaxByteMapMarks ? 3 : 1; // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1
     if (c.dense) {
@@ -459,6 +459,7 @@ static Marks marks_of(mdpp_handle *h) {
     m.dense = h->cv.dense ? 1u : 0u;
     if (h->cv.dense) {
         m.words_per_cta = h->cv.words_per_cta;
+        m.cta_slots = h->cv.cta_slots;
         m.n_ctas = env_ctas(h);
         m.cta_bits = mark_region(h, p, 0);
     } else {
@@ -618,7 +619,6 @@ static bool round_eligible(const mdpp_handle *h) {
 }
 
 static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round, cudaStream_t s) {
-    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
     const uint32_t P = h->round_parity;
     h->round_parity ^= 1u;
     // every env still in an epsilon = 1 segment: every coin says "explore", no lane can be parked
@@ -633,7 +633,7 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
     ra.defer_flags = (uint32_t *)(h->ws + h->cv.flags) + (size_t)P * h->cv.cta_slots;
     ra.words_per_cta = h->cv.words_per_cta;
-    ra.n_keys = (uint32_t)keys;
+    ra.cta_slots = h->cv.cta_slots;
     ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
     const unsigned grid = round_ctas(h);
@@ -876,7 +876,6 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     if (lp->flags != 0 || !round_eligible(h)) return fail(MDPP_EINVAL, "no fused round kernel for this table / these flags");
     cudaStream_t s = (cudaStream_t)stream;
     h->chain = false;
-    const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
     RoundArgs ra{};
     ra.recs = recs_of(h);
     ra.n_envs = (uint32_t)h->n_envs;
@@ -889,7 +888,7 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     ra.bits_a = mark_region(h, h->round_parity, 0);
     ra.bits_b = mark_region(h, h->round_parity, 1);
     ra.words_per_cta = h->cv.words_per_cta;
-    ra.n_keys = (uint32_t)keys;
+    ra.cta_slots = h->cv.cta_slots;
     ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
     const size_t smem = round_smem_bytes(h->cfg.n_cars, ra.map_bytes, h->cfg.n_cars);

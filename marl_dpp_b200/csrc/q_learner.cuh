@@ -35,11 +35,19 @@ __device__ __forceinline__ uint32_t si_fwd(uint32_t i) { return (i >> 5) & 127u;
 __device__ __forceinline__ int32_t si_bfs(uint32_t i) { return (int32_t)((i >> 12) & 255u); }
 __device__ __forceinline__ uint32_t si_node(uint32_t i) { return (i >> 22) & 127u; }
 
+// Per-CTA touched bitmaps of one region are stored blocked: [word / 8][cta slot][8 words].  A CTA writes whole
+// 32-byte sectors; the pull kernel's CTA (256 threads = 8 words = one block) reads, for every env CTA, ONE sector
+// shared by its 8 warps instead of one sector per warp and env CTA (the [cta][word] layout cost 8x the L2
+// sectors and made the pull's first load phase 3 us long).
+__device__ __forceinline__ size_t slice_index(uint32_t word, uint32_t cta, uint32_t cta_slots) {
+    return ((size_t)(word >> 3) * cta_slots + cta) * 8u + (word & 7u);
+}
+
 struct Marks {
     uint32_t *cta_bits;  // dense: [n_ctas][words_per_cta] per-CTA touched bitmaps of the current parity
     uint32_t *cta_bits2; // dense, fused round: bitmaps of the catch-up kernel (or NULL) ...
     const uint32_t *flags2; // ... valid for the CTAs whose flag is set
-    uint32_t n_ctas, words_per_cta;
+    uint32_t n_ctas, words_per_cta, cta_slots;
     uint32_t *bits;      // list: [n_keys / 32] touched bitmap, parity of the current sub-step
     uint32_t *list;      // list: [capacity] touched keys
     uint32_t *count;     // list: number of listed keys (Control::touched_count[parity])
@@ -408,7 +416,7 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
     }
     __syncthreads();
     // bytes -> bits: 32 keys = two uint4 -> one word; (w * 0x01020408) >> 24 packs four 0/1 bytes into a nibble
-    uint32_t *out = mk.cta_bits + (size_t)blockIdx.x * mk.words_per_cta;
+    uint32_t *out = mk.cta_bits;
     for (uint32_t w = threadIdx.x; w < mk.words_per_cta; w += blockDim.x) {
         uint32_t bits = 0;
         if constexpr (BITS) {
@@ -425,7 +433,7 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
                         (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
             }
         }
-        out[w] = bits;
+        out[slice_index(w, blockIdx.x, mk.cta_slots)] = bits;
     }
     flush_counts<PLAIN>(cnt, cc, PLAIN ? 0u : lp.flags, ctl);
     pdl_wait();
@@ -470,6 +478,7 @@ __device__ __forceinline__ void mark_visited(uint32_t *__restrict__ visited, uin
 // dense mode: one thread per compact key m = state * 5 + action (marks carry no padding slots), one warp per
 // bitmap word.  The warp ORs the per-CTA bitmaps of its word (lane l reads CTAs l, l + 32, ...: all loads in
 // flight at once), then qnew <- qold with every marked key replaced by its update (ping-pong: no in-place hazard).
+constexpr int kPullUnroll = 5; // 5 x 32 lanes = 160 per-CTA bitmaps per pass
 __global__ void __launch_bounds__(kThreads)
 q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Marks mk, float alpha, float discount,
                     int early_trigger, Control *ctl) {
@@ -486,12 +495,33 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
     // the state's info word is requested together with the bitmap words (it does not depend on them): a marked
     // key then needs one more round trip (successor row + info), not two
     const uint32_t info = m < mk.n_marks ? __ldg(mk.sinfo + s) : 0u;
+    // All loads of a lane are issued before the first one is used: written as `bits |= load` in a loop, the
+    // in-order warp waited for every load in turn (5 L2 round trips, 3 us of the kernel's 4).
     uint32_t bits = 0;
     if (word < mk.words_per_cta) {
-        for (uint32_t b = lane; b < mk.n_ctas; b += 32u) bits |= mk.cta_bits[(size_t)b * mk.words_per_cta + word];
-        if (mk.cta_bits2)
-            for (uint32_t b = lane; b < mk.n_ctas; b += 32u)
-                if (mk.flags2[b]) bits |= mk.cta_bits2[(size_t)b * mk.words_per_cta + word];
+        for (uint32_t b0 = 0; b0 < mk.n_ctas; b0 += 32u * kPullUnroll) {
+            uint32_t v[kPullUnroll];
+#pragma unroll
+            for (int j = 0; j < kPullUnroll; j++) {
+                const uint32_t b = b0 + 32u * j + lane;
+                v[j] = b < mk.n_ctas ? mk.cta_bits[slice_index(word, b, mk.cta_slots)] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < kPullUnroll; j++) bits |= v[j];
+        }
+        if (mk.cta_bits2) {
+            for (uint32_t b0 = 0; b0 < mk.n_ctas; b0 += 32u * kPullUnroll) {
+                uint32_t v[kPullUnroll], f[kPullUnroll];
+#pragma unroll
+                for (int j = 0; j < kPullUnroll; j++) {
+                    const uint32_t b = b0 + 32u * j + lane;
+                    f[j] = b < mk.n_ctas ? mk.flags2[b] : 0u;
+                    v[j] = b < mk.n_ctas ? mk.cta_bits2[slice_index(word, b, mk.cta_slots)] : 0u; // a stale slice is masked below
+                }
+#pragma unroll
+                for (int j = 0; j < kPullUnroll; j++) bits |= f[j] ? v[j] : 0u;
+            }
+        }
     }
     bits = __reduce_or_sync(0xFFFFFFFFu, bits);
     uint32_t touched = 0;

@@ -62,7 +62,7 @@ struct RoundArgs {
     const FastTabs *tabs;
     uint32_t *bits_a, *bits_b;   // K0: [n_ctas][words] bitmaps of map 0 / map 1; K1: bits_a = its own map-1 bitmap
     uint32_t *defer_flags;       // [n_ctas] K0 writes, K1 reads: this CTA parked at least one lane
-    uint32_t words_per_cta, n_keys, map_bytes;
+    uint32_t words_per_cta, cta_slots, map_bytes;
     uint32_t rank_stride;        // n_dest_nodes * n_local_nodes
 };
 
@@ -270,7 +270,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     for (int m = 0; m < kMaps; m++) {
         const uint4 *map4 = reinterpret_cast<const uint4 *>(maps + (uint32_t)m * ra.map_bytes);
         const uint32_t n16 = ra.map_bytes >> 4;
-        uint32_t *out = (m == 0 ? ra.bits_a : ra.bits_b) + (size_t)blockIdx.x * ra.words_per_cta;
+        uint32_t *out = m == 0 ? ra.bits_a : ra.bits_b;
         for (uint32_t wd = threadIdx.x; wd < ra.words_per_cta; wd += blockDim.x) {
             uint32_t bits = 0;
             if (2u * wd < n16) {
@@ -283,7 +283,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                 bits |= (((hi.x * 0x01020408u) >> 24) << 16) | (((hi.y * 0x01020408u) >> 24) << 20) |
                         (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
             }
-            out[wd] = bits;
+            out[slice_index(wd, blockIdx.x, ra.cta_slots)] = bits;
         }
     }
     flush_counts<true>(cnt, S.cc, 0u, ctl);
