@@ -40,6 +40,8 @@ class BatchedEnv:
         self.n_envs = int(n_envs)
         self.n_cars = scenario.n_cars
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.seed = int(seed)
         self.env_id_base = int(env_id_base)
         L = _lib.lib()
@@ -281,9 +283,13 @@ class BatchedQLearner:
         """End-to-end call: learner parameters from host memory in, stats back, synchronised."""
         env = self.env
         s = MdppStats()
-        with torch.cuda.device(env.device):
+        if torch.cuda.current_device() == env.device.index:  # the common case: no device switch around the call
             _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self.q), C.byref(self.params), self.round,
                                                        int(rounds), C.byref(s), _stream()))
+        else:
+            with torch.cuda.device(env.device):
+                _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self.q), C.byref(self.params), self.round,
+                                                           int(rounds), C.byref(s), _stream()))
         self.round += int(rounds)
         return s.as_dict()
 

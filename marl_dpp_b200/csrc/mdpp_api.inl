@@ -332,7 +332,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
     delete ft;
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, (sizeof(mdpp_stats) + sizeof(uint32_t)) * kStatSlots);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, sizeof(Control));
     if (e != cudaSuccess) {
         delete h;
         return fail(MDPP_ECUDA, "workspace initialisation failed: %s", cudaGetErrorString(e));
@@ -844,12 +844,13 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *
 int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *stream) {
     if (!h || !out_host) return fail(MDPP_EINVAL, "handle / out is NULL");
     cudaStream_t s = (cudaStream_t)stream;
-    mdpp_stats *slots = h->stat_slots; // the device keeps kStatSlots privatised copies; summed here
-    uint32_t *max_ep = (uint32_t *)(slots + kStatSlots);
-    MDPP_CUDA(cudaMemcpyAsync(slots, control_of(h)->stats, sizeof(mdpp_stats) * kStatSlots, cudaMemcpyDeviceToHost, s));
-    MDPP_CUDA(cudaMemcpyAsync(max_ep, control_of(h)->max_episode, sizeof(uint32_t) * kStatSlots, cudaMemcpyDeviceToHost, s));
+    // one copy of the whole control block: kStatSlots privatised counter sets (summed here) + the episode maxima
+    Control *host_ctl = (Control *)h->stat_slots;
+    MDPP_CUDA(cudaMemcpyAsync(host_ctl, control_of(h), sizeof(Control), cudaMemcpyDeviceToHost, s));
     if (reset) MDPP_CUDA(cudaMemsetAsync(control_of(h)->stats, 0, sizeof(mdpp_stats) * kStatSlots, s));
     MDPP_CUDA(cudaStreamSynchronize(s));
+    const mdpp_stats *slots = host_ctl->stats;
+    const uint32_t *max_ep = host_ctl->max_episode;
     if (h->ep_device_max_valid) { // everything launched so far has completed: the device's maximum is exact
         uint32_t m = 0;
         for (int i = 0; i < kStatSlots; i++) m = std::max(m, max_ep[i]);
