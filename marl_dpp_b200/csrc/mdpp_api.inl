@@ -468,6 +468,7 @@ static Marks marks_of(mdpp_handle *h) {
         m.vals = (float *)(h->ws + h->cv.vals);
         m.count = &ctl->touched_count[p];
         m.count_other = &ctl->touched_count[p ^ 1u];
+        m.l1_check = keys / 8 <= ((size_t)4 << 20) ? 1u : 0u;
     }
     m.visited = (uint32_t *)(h->ws + h->cv.visited);
     m.sinfo = (const uint32_t *)(h->ws + h->cv.sinfo);
