@@ -98,6 +98,7 @@ struct mdpp_handle {
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool chain;             // the previous launch on the stream was one of our learner kernels
+    bool fast_rollout;      // the table-driven rollout kernel applies (BFS lengths fit its move table)
     uint32_t smem_configured; // env-kernel variants whose dynamic shared-memory limit has been raised
     uint32_t round_parity;    // fused rounds alternate between two sets of mark regions
     // Upper bound on every env's episode counter at the current point of the stream.  While it is below the
@@ -177,8 +178,9 @@ static void make_devcfg(const mdpp_config &c, DevCfg &d) {
 
 // Table image of the fused round kernel (q_round.cuh): everything the reference derives from a car's
 // (node, destination_index), per car, as the primary and as an "other".
-static void build_fast_tabs(const mdpp_config &c, FastTabs &t) {
+static bool build_fast_tabs(const mdpp_config &c, FastTabs &t) {
     memset(&t, 0, sizeof t);
+    bool ok = true; // every BFS length fits the 6 bits of the move table
     for (int car = 0; car < c.n_cars; car++) {
         for (int di = 0; di < 2; di++) {
             const uint32_t dn = c.car_dest[car][di], dnode = c.dest_node[dn], dbox = c.dest_node_box[dn];
@@ -198,6 +200,7 @@ static void build_fast_tabs(const mdpp_config &c, FastTabs &t) {
                                         (dbox << 29);
                     t.own[car][idx].y = y;
                     t.own[car][idx].z = sel;
+                    t.own[car][idx].w = c.bfs_len[dn][node];
                 }
                 if (c.src_box_idx[box18] != MDPP_NONE) { // as a listed other: (box, destination box)
                     const uint32_t code = 1u + (uint32_t)c.src_box_idx[box18] * (uint32_t)c.n_dest_boxes + dbox;
@@ -207,21 +210,24 @@ static void build_fast_tabs(const mdpp_config &c, FastTabs &t) {
             }
         }
         for (int di = 0; di < 2; di++) { // the move itself: successor + update_car, per action
-            const uint32_t dnode = c.dest_node[c.car_dest[car][di]];
+            const uint32_t dn = c.car_dest[car][di], dnode = c.dest_node[dn];
             for (int node = 0; node < MDPP_NODES; node++)
                 for (int a = 0; a < MDPP_N_ACT; a++) {
                     static const int rot[MDPP_N_ACT] = {0, 3, 1, 0, 2}; // S, L (heading - 1), R (+ 1), F, T (- 2)
                     uint32_t nn = a == MDPP_A_F ? c.fwd[node] : (uint32_t)((node & ~3) | ((node + rot[a]) & 3));
-                    uint32_t ndi = (uint32_t)di, done = 0;
+                    uint32_t ndi = (uint32_t)di, done = 0, reached = 0;
                     if (nn == MDPP_NONE) nn = (uint32_t)node; // F off the graph is never legal
+                    const uint32_t bfs = c.bfs_len[dn][nn];
+                    if (bfs > 63) ok = false;                  // does not fit the move table: rollout falls back
                     if (nn == dnode) {
+                        reached = 1;
                         if (di == c.tcdi) {
                             done = 1;
                             nn = (uint32_t)c.parking_node;
                         }
                         ndi ^= 1u;
                     }
-                    t.next[car][node | (di << 7)][a] = (uint16_t)((nn & 127u) | (ndi << 7) | (done << 8));
+                    t.next[car][node | (di << 7)][a] = (uint16_t)((nn & 127u) | (ndi << 7) | (done << 8) | (reached << 9) | ((bfs & 63u) << 10));
                 }
         }
         // ghost of a finished car: [final box, final box] (reference src/env_gym.py:313-317)
@@ -238,6 +244,7 @@ static void build_fast_tabs(const mdpp_config &c, FastTabs &t) {
             if ((m >> k) & 1) packed |= (uint32_t)k << (3 * n++);
         t.nth[m] = packed;
     }
+    return ok;
 }
 
 extern "C" {
@@ -309,7 +316,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     }
     FastTabs *ft = new (std::nothrow) FastTabs();
     if (!ft) { delete h; return fail(MDPP_EINVAL, "out of host memory"); }
-    build_fast_tabs(*cfg, *ft);
+    h->fast_rollout = build_fast_tabs(*cfg, *ft) && !(getenv("MDPP_FAST_ROLLOUT") && atoi(getenv("MDPP_FAST_ROLLOUT")) == 0);
     cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.fast, ft, sizeof(FastTabs), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.nodetab, nodeimg, sizeof nodeimg, cudaMemcpyHostToDevice, s);
@@ -428,9 +435,35 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
     if (rounds <= 0) return fail(MDPP_EINVAL, "rounds must be positive");
     if (reward_kind != MDPP_REWARD_Q && reward_kind != MDPP_REWARD_DQN) return fail(MDPP_EINVAL, "unknown reward kind");
     cudaStream_t s = (cudaStream_t)stream;
-    MDPP_DISPATCH_NC(h, rollout_random_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs,
-                     h->env_id_base, rounds, first_round, seed, reward_kind, action, reward, done, next_idx,
-                     control_of(h));
+    if (h->fast_rollout) { // table-driven, persistent CTAs (q_round.cuh)
+        const RolloutOut out{action, reward, done, next_idx};
+        const FastTabs *tabs = (const FastTabs *)(h->ws + h->cv.fast);
+        const uint32_t stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+        const int64_t tiles = (h->n_envs + 31) / 32;
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, (tiles + 7) / 8));
+#define MDPP_ROLL(NCV)                                                                                           \
+        do {                                                                                                     \
+            const size_t smem = sizeof(RoundSmem<NCV>);                                                          \
+            if (!((h->smem_configured >> 27) & 1u)) {                                                            \
+                MDPP_CUDA(cudaFuncSetAttribute(rollout_fast_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                h->smem_configured |= 1u << 27;                                                                  \
+            }                                                                                                    \
+            rollout_fast_kernel<NCV><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs,   \
+                    h->env_id_base, rounds, first_round, seed, reward_kind, out, tabs, stride, control_of(h));   \
+        } while (0)
+        switch (h->cfg.n_cars) {
+        case 1: MDPP_ROLL(1); break;
+        case 2: MDPP_ROLL(2); break;
+        case 3: MDPP_ROLL(3); break;
+        case 4: MDPP_ROLL(4); break;
+        default: MDPP_ROLL(5); break;
+        }
+#undef MDPP_ROLL
+    } else {
+        MDPP_DISPATCH_NC(h, rollout_random_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs,
+                         h->env_id_base, rounds, first_round, seed, reward_kind, action, reward, done, next_idx,
+                         control_of(h));
+    }
     MDPP_CUDA(cudaGetLastError());
     h->ep_bound += rounds; // auto-reset starts at most one new episode per round
     h->ep_device_max_valid = false;

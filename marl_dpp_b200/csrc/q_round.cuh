@@ -32,14 +32,15 @@ struct FastTabs {
     uint2 oth[MDPP_MAX_CARS][256];  // same index, car seen as an "other"
     uint2 ghost[MDPP_MAX_CARS];     // oth-format entry of the finished car's ghost
     uint32_t nth[32];               // per 5-bit mask: positions of its set bits, 3 bits each, lowest first
-    alignas(16) uint16_t next[MDPP_MAX_CARS][256][8]; // [car][node | di << 7][action] -> node | di << 7 | done << 8 after the move:
-                                          // successor (src/env_gym.py:256-265) + update_car (:386-441) folded
+    alignas(16) uint16_t next[MDPP_MAX_CARS][256][8]; // [car][node | di << 7][action]: successor (src/env_gym.py:256-265) +
+        // update_car (:386-441) folded: bits 0-8 = node | di << 7 | done << 8 after the move, bit 9 = the move reached
+        // the car's destination node, bits 10-15 = BFS length successor -> that destination (q_reward / dqn_reward)
 };
 // own.x: bits 0-9 dnidx * n_local_nodes + node_local | 10-16 destination node | 17-23 F successor (127 none)
 //        | 24-28 base legal mask | 29-31 destination-box index
 // own.y: bits 0-8 1 << (own box number - 1) | 9-17 1 << (number of the box ahead - 1) | 18 box ahead is in the
 //        selective-block list keyed by this car's current destination box
-// own.z: that selective-block list as an 18-bit box mask
+// own.z: that selective-block list as an 18-bit box mask        own.w: bits 0-7 BFS length node -> the car's destination
 // oth.x: bits 0-17 1 << box18 | 18-25 others-code        oth.y: bits 0-8 1 << (box number - 1)
 
 template <int NC>
@@ -141,7 +142,7 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
     }
     key = sidx * MDPP_N_ACT + a; // compact key (marks carry no padding slots)
     // ---- successor (src/env_gym.py:256-265) and update_car (:386-441): one table entry ----
-    const uint32_t nf = (uint32_t)S.next[C][f & 0xFFu][a] | (f & 0xE00u);
+    const uint32_t nf = ((uint32_t)S.next[C][f & 0xFFu][a] & 0x1FFu) | (f & 0xE00u);
     cars = (nc & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
     moved = true;
     return kStepDone;
@@ -288,6 +289,192 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     }
     flush_counts<true>(cnt, S.cc, 0u, ctl);
     pdl_wait();
+}
+
+// ------------------------------------------------------------------------------------------------
+// lockstep rollout under the uniform-random legal policy with auto-reset (config "random-policy sweep"),
+// table-driven like the round kernel: same semantics as rollout_random_kernel (mdpp_kernels.cu), which stays
+// as the fallback for layouts whose BFS lengths do not fit the 6 bits of the move table.
+// Persistent CTAs: the tables are staged once per CTA, each warp walks its tiles, a tile's records stay in
+// registers for all `rounds` rounds of the launch.
+// ------------------------------------------------------------------------------------------------
+template <int NC, int C>
+__device__ __forceinline__ bool rollout_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
+                                                 uint32_t rank_stride, int kind, uint64_t &cars, uint32_t word,
+                                                 uint32_t &a_out, int32_t &ri, uint32_t &nidx) {
+    const uint32_t f = (uint32_t)(cars >> (12 * C)) & 0xFFFu;
+    if (f & 0x100u) return false;
+    uint64_t nc = cars;
+    const uint4 own = S.own[C][f & 0xFFu];
+    uint32_t occ9 = 0, occ18 = 0, codes[NC], clash_boxes[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        codes[i] = 0;
+        clash_boxes[i] = 0xFFFFu;
+        if (i == C) continue;
+        const uint32_t fi = (uint32_t)(cars >> (12 * i)) & 0xFFFu;
+        clash_boxes[i] = (fi & 127u) >> 2; // real position, parked cars included (src/env_gym.py:613-619)
+        uint2 oe = make_uint2(0u, 0u);
+        if (!(fi & 0x100u)) {
+            oe = S.oth[i][fi & 0xFFu];
+        } else {
+            uint32_t g = fi >> 9;
+            if (g != 7u) {
+                if (g == 0u) g = 7u;
+                else { g -= 1u; oe = gt->ghost[i]; }
+                nc = (nc & ~(0xE00ull << (12 * i))) | ((uint64_t)(g << 9) << (12 * i));
+            }
+        }
+        codes[i] = oe.x >> 18;
+        occ18 |= oe.x & 0x3FFFFu;
+        occ9 |= oe.y;
+    }
+    cars = nc; // the encode's ghost side effects stay whether or not the car moves
+    uint32_t rank = 0;
+    if constexpr (NC > 1) {
+        sort_codes<NC>(codes);
+        rank = codes[1];
+        if constexpr (NC > 2) rank += (codes[2] + 1u) * codes[2] / 2u;
+        if constexpr (NC > 3) rank += (codes[3] + 2u) * (codes[3] + 1u) * codes[3] / 6u;
+        if constexpr (NC > 4) rank += (codes[4] + 3u) * (codes[4] + 2u) * (codes[4] + 1u) * codes[4] / 24u;
+    }
+    uint32_t lm = (own.x >> 24) & 31u;
+    const uint32_t hit = (occ9 * 0x201u) & own.y;
+    if (hit & 0x1FFu) lm &= 1u << MDPP_A_F;
+    if ((hit >> 9) || (((own.y >> 18) & 1u) && (own.z & occ18))) lm &= ~(1u << MDPP_A_F);
+    if (!lm) return false;
+    const uint32_t a = (S.nth[lm] >> (3u * (((word & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
+    const uint32_t mv = S.next[C][f & 0xFFu][a];
+    const uint32_t pnode = f & 127u, dnode = (own.x >> 10) & 127u;
+    const bool reached = (mv >> 9) & 1u;
+    const uint32_t nn = reached ? dnode : (mv & 127u); // the successor itself (a finished car is parked afterwards)
+    const uint32_t sidx = rank * rank_stride + (own.x & 0x3FFu);
+    nidx = sidx - pnode + nn;                           // same others, same destination: only the node term moves
+    // ---- q_reward / dqn_reward (src/env_gym.py:485-620), integer (dqn: before the /100) ----
+    bool bad_next = false, bad_prev = false;
+    if (kind == MDPP_REWARD_Q && cfg.bad_on) { // :568-577 on the heading-stripped strings
+        const uint32_t base = (rank * cfg.n_dest_boxes + (own.x >> 29)) * cfg.n_src_boxes;
+        const uint32_t idn = base + ((nn >> 2) - cfg.box_base), idp = base + ((pnode >> 2) - cfg.box_base);
+        bad_next = (__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u;
+        bad_prev = (__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u;
+    }
+    if (bad_next) ri = -10000;
+    else if (bad_prev) ri = 0;
+    else {
+        ri = -10 + 50 * ((int32_t)(own.w & 0xFFu) - (int32_t)(mv >> 10));
+        if (reached) ri += (kind == MDPP_REWARD_DQN) ? 110 : 10010;
+        int32_t clash = 0;
+#pragma unroll
+        for (int i = 0; i < NC; i++)
+            if (i != C) clash += (clash_boxes[i] == (nn >> 2));
+        ri -= clash * ((kind == MDPP_REWARD_DQN) ? 100 : 100000);
+    }
+    const uint32_t nf = (mv & 0x1FFu) | (f & 0xE00u);
+    cars = (cars & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
+    a_out = a;
+    return true;
+}
+
+struct RolloutOut {
+    uint8_t *action;
+    float *reward;
+    uint8_t *done;
+    uint32_t *next;
+};
+
+template <int NC, int C>
+__device__ __forceinline__ void rollout_chain(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
+                                              uint32_t rank_stride, int kind, uint64_t &cars, const uint32_t (&w)[NC],
+                                              uint32_t &steps, StepCounts &cnt, long long &rsum, const RolloutOut &out,
+                                              size_t o, size_t n_envs) {
+    uint32_t a = MDPP_ACT_SKIP, nidx = 0xFFFFFFFFu;
+    int32_t ri = 0;
+    float rw = 0.f;
+    if (rollout_car_step<NC, C>(S, cfg, gt, rank_stride, kind, cars, w[C], a, ri, nidx)) {
+        rw = reward_float(ri, kind);
+        steps = steps < 0xFFFFu ? steps + 1 : steps;
+        cnt.steps++;
+        rsum += ri;
+    } else {
+        a = MDPP_ACT_SKIP;
+        nidx = 0xFFFFFFFFu;
+    }
+    if (out.action) out.action[o] = (uint8_t)a;
+    if (out.reward) out.reward[o] = rw;
+    if (out.next) out.next[o] = nidx;
+    if (out.done) out.done[o] = (uint8_t)all_done<NC>(cars);
+    if constexpr (C + 1 < NC) rollout_chain<NC, C + 1>(S, cfg, gt, rank_stride, kind, cars, w, steps, cnt, rsum, out, o + n_envs, n_envs);
+}
+
+constexpr int kRolloutThreads = 256;
+template <int NC>
+__global__ void __launch_bounds__(kRolloutThreads, 4)
+rollout_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint32_t env_id_base, int rounds,
+                    uint64_t first_round, uint32_t seed, int kind, RolloutOut out, const FastTabs *__restrict__ tabs,
+                    uint32_t rank_stride, Control *ctl) {
+    extern __shared__ uint4 smem_dyn[]; // RoundSmem<NC> (50 KB for 5 cars: above the static limit)
+    RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
+    __shared__ long long cta_reward;
+    {
+        const uint4 *src_own = &tabs->own[0][0];
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.own[0][0])[i] = __ldg(src_own + i);
+        const uint2 *src_oth = &tabs->oth[0][0];
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.oth[0][0])[i] = __ldg(src_oth + i);
+        const uint4 *src_next = reinterpret_cast<const uint4 *>(&tabs->next[0][0][0]);
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x)
+            reinterpret_cast<uint4 *>(&S.next[0][0][0])[i] = __ldg(src_next + i);
+        if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&tabs->nth[threadIdx.x]);
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; cta_reward = 0ll; }
+    }
+    __syncthreads();
+    const uint32_t tiles = (n_envs + 31u) >> 5;
+    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
+    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    StepCounts cnt;
+    long long rsum = 0;
+    for (uint32_t t = t0 + warp; t < t1; t += n_warps) {
+        const uint32_t e = t * 32u + lane;
+        if (e >= n_envs) continue;
+        uint4 rec = recs[e];
+        uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        const uint32_t env = env_id_base + e;
+        for (int r = 0; r < rounds; r++) {
+            const uint64_t round = first_round + (uint64_t)r;
+            const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
+            uint32_t w[NC];
+            w[0] = p.x;
+            if (NC > 1) w[NC > 1 ? 1 : 0] = p.y;
+            if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
+            if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
+            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
+            rollout_chain<NC, 0>(S, cfg, tabs, rank_stride, kind, cars, w, steps, cnt, rsum, out,
+                                 (size_t)r * NC * (size_t)n_envs + e, (size_t)n_envs);
+            // end of round: is_game_ended (src/env_gym.py:622-638) or the step cap -> next episode
+            const bool finished = all_done<NC>(cars);
+            const bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                cnt.episodes++;
+                cnt.capped += capped;
+                episode = (episode + 1) & 0xFFFFu;
+                steps = 0;
+                cars = initial_cars<NC>(cfg, heading_word(round, 2, seed, env));
+            }
+        }
+        rec.x = (uint32_t)cars;
+        rec.y = (uint32_t)(cars >> 32);
+        rec.z = episode | (steps << 16);
+        recs[e] = rec;
+    }
+    // counters (every step of this kernel is an exploration step; rewards need 64 bits over many rounds)
+    cnt.explore = cnt.steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
+    if (lane == 0 && rsum) atomicAdd((unsigned long long *)&cta_reward, (unsigned long long)rsum);
+    flush_counts<true>(cnt, S.cc, MDPP_LEARN_FROZEN, ctl); // no Q-updates on this path
+    if (threadIdx.x == 0 && cta_reward)
+        atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].reward_sum, (unsigned long long)cta_reward);
 }
 
 } // namespace mdpp
