@@ -120,7 +120,9 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base,
 int mdpp_destroy(mdpp_handle *h);
 const char *mdpp_last_error_string(void);
 int mdpp_abi_version(void);
-/* device pointer to the packed env records, 16 bytes per env (see DESIGN.md "Data layout") */
+/* device pointer to the packed env records, 16 bytes per env (see DESIGN.md "Data layout").  Read-only for the
+ * caller: the library keeps a host-side bound on the episode counters (it decides whether a training round can
+ * skip its catch-up kernel); change records through mdpp_reset / the stepping entry points only. */
 void *mdpp_env_records(mdpp_handle *h);
 /* device pointer to [n_states] u32: bit a set = key (state, a) has been updated (qvalue file writer) */
 void *mdpp_visited_bits(mdpp_handle *h);

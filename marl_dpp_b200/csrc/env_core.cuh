@@ -51,33 +51,12 @@ struct SmemTables {
 };
 constexpr int kTableWords = (sizeof(SmemTables) + 3) / 4;
 
-// Two ways to read the tables: a shared-memory copy (one load + barrier per CTA; right for kernels that
-// run many steps per launch) or straight from global memory through the read-only L1 path (720 bytes,
-// always L1-resident; no barrier, no per-CTA copy: right for the one-step-per-launch learner kernel).
+// Table access of the parity / gym / string-API kernels: a shared-memory copy per CTA.
 struct SharedTab {
     const SmemTables *sm;
     __device__ __forceinline__ uint32_t info(uint32_t node) const { return sm->nodeinfo[node]; }
     __device__ __forceinline__ uint32_t bfs(uint32_t d, uint32_t node) const { return sm->bfs[d][node]; }
 };
-struct GlobalTab {
-    const SmemTables *g;
-    __device__ __forceinline__ uint32_t info(uint32_t node) const { return __ldg(&g->nodeinfo[node]); }
-    __device__ __forceinline__ uint32_t bfs(uint32_t d, uint32_t node) const { return __ldg(&g->bfs[d][node]); }
-};
-
-template <bool GT>
-struct AnyTab { // compile-time choice between the two
-    const SmemTables *p;
-    __device__ __forceinline__ uint32_t info(uint32_t node) const {
-        if constexpr (GT) return __ldg(&p->nodeinfo[node]);
-        else return p->nodeinfo[node];
-    }
-    __device__ __forceinline__ uint32_t bfs(uint32_t d, uint32_t node) const {
-        if constexpr (GT) return __ldg(&p->bfs[d][node]);
-        else return p->bfs[d][node];
-    }
-};
-
 __device__ __forceinline__ void load_tables(SmemTables &sm, const uint32_t *src) {
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sm);
     for (int i = threadIdx.x; i < kTableWords; i += blockDim.x) dst[i] = __ldg(src + i);

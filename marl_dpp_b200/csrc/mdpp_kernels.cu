@@ -87,27 +87,6 @@ __device__ __forceinline__ void flush_stats(const StatAcc &a, int64_t reward64, 
     }
 }
 
-// Barrier-free variant for one-step-per-thread kernels: one REDUX per warp, lane 0 adds straight to the
-// privatised global slot of its warp (3 atomics per warp spread over kStatSlots sectors).
-template <bool kQ>
-__device__ __forceinline__ void flush_stats_warp(const StatAcc &a, int64_t reward64, Control *ctl) {
-    uint32_t packed = a.steps | (a.explore << 8) | (a.episodes << 16) | (a.capped << 24);
-    packed = __reduce_add_sync(0xFFFFFFFFu, packed);
-    const int rs = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(int)reward64);
-    if ((threadIdx.x & 31u) == 0 && packed) {
-        const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        mdpp_stats *slot = &ctl->stats[w & (kStatSlots - 1)];
-        const unsigned long long steps = packed & 0xFFu, explore = (packed >> 8) & 0xFFu;
-        const unsigned long long episodes = (packed >> 16) & 0xFFu, capped = packed >> 24;
-        if (steps) atomicAdd((unsigned long long *)&slot->agent_steps, steps);
-        if (kQ && steps) atomicAdd((unsigned long long *)&slot->q_updates, steps);
-        if (explore) atomicAdd((unsigned long long *)&slot->explore_steps, explore);
-        if (episodes) atomicAdd((unsigned long long *)&slot->episodes_done, episodes);
-        if (capped) atomicAdd((unsigned long long *)&slot->episodes_capped, capped);
-        if (rs) atomicAdd((unsigned long long *)&slot->reward_sum, (unsigned long long)(long long)rs);
-    }
-}
-
 __device__ __forceinline__ void zero_stats(SmemStats &ss) {
     if (threadIdx.x == 0) ss = SmemStats{0ull, 0ull, 0u, 0u, 0u, 0u};
 }
@@ -275,7 +254,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
 // learner: epsilon-greedy select + env step + key marks, and the pull kernels that apply the update
 // ------------------------------------------------------------------------------------------------
 } // namespace mdpp
-#include "q_learner.cuh" // needs Control / StatAcc / flush_stats_warp from above
+#include "q_learner.cuh" // needs Control from above
 #include "q_round.cuh"
 namespace mdpp {
 
