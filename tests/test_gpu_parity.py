@@ -279,9 +279,13 @@ def test_batched_qlearning_matches_oracle(case):
 
 
 FUSED = [
-    ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 300, 1024, 10, 1400, 7),
-    ("b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 0, 777, 8, 900, 50),
-    ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 200, 1000, 12, 600, 3),
+    ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 300, 1024, 10, 1400, 7, 0),
+    ("b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 0, 777, 8, 900, 50, 0),
+    ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 200, 1000, 12, 600, 3, 0),
+    # 50 episodes: the epsilon = 1 segment ends at episode 20.  The host's bound on the episode counters reaches 20
+    # after 20 rounds although no env is near it (rounds then run with the catch-up kernel), every stats fetch
+    # tightens it again (rounds without), until envs really leave the segment.
+    ("b2_2car_bad_stats", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 40, 512, 50, 900, 11, 4),
 ]
 
 
@@ -293,7 +297,7 @@ def test_train_rounds_fused_path_matches_oracle(case):
     (1, .8, .5, .3, .15, 0) and ends with frozen envs; table, records and counters must equal the
     oracle's sub-step-by-sub-step restatement bit for bit."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
-    name, block, boxes, idx, choose, bad, cap, n, episodes, rounds, chunk = case
+    name, block, boxes, idx, choose, bad, cap, n, episodes, rounds, chunk, stats_every = case
     badtxt = bad_states_text(block) if bad else None
     sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
     env = BatchedEnv(sc, n, seed=17)
@@ -309,6 +313,8 @@ def test_train_rounds_fused_path_matches_oracle(case):
         for r in range(done, done + k):
             ob.q_round(oq, olp, r)
         done += k
+        if stats_every and (done // chunk) % stats_every == 0:
+            env.stats()  # synchronises and tightens the host-side episode bound
         if done in (chunk, rounds) or done % (chunk * 20) == 0:  # checkpoints along the way
             q = lr.q.cpu().numpy()
             items = [x for x in oq.items() if x[1] != "B"]
@@ -329,9 +335,48 @@ def test_train_rounds_fused_path_matches_oracle(case):
     assert gs["q_updates"] == gs["agent_steps"]
     assert gs["touched_keys"] == ob.touched_keys()
     assert 0 < gs["explore_steps"] < gs["agent_steps"]          # both kinds of decisions happened
-    assert int((cars["episode"] >= episodes).sum()) > 0           # some envs used up their budget
+    if not stats_every:
+        assert int((cars["episode"] >= episodes).sum()) > 0       # some envs used up their budget
     assert ob.disagreements() == 0
     assert int((env.records[:, 3] & 0x700).sum()) == 0            # no lane is left parked
+
+
+def test_training_after_other_episode_advancing_calls():
+    """A random rollout advances episode counters outside the learner kernels; training afterwards must still
+    equal the oracle (the host-side episode bound turns conservative), and the env-kernel profiling hook steps
+    every live env once."""
+    m, BatchedEnv, BatchedQLearner, orc = _mods()
+    boxes, idx, choose = ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]]
+    badtxt = bad_states_text(2)
+    sc = m.Scenario(m.layout_3[2], boxes, idx, choose, bad_states_text=badtxt, step_cap=60)
+    n, episodes = 600, 9
+    env = BatchedEnv(sc, n, seed=23)
+    ob = orc.Batch(orc.Config(m.layout_3[2]), n, boxes, idx, choose, badtxt, 60)
+    ob.reset(seed=23)
+    env.rollout_random(90, 0)                 # a few episodes per env, no learner involved
+    ob.rollout_random(90, 0, 23, False, threads=2, outputs=False)
+    lr = BatchedQLearner(env, episodes=episodes, seed=23)
+    oq = orc.QTable(f32=True)
+    olp = orc.learner(episodes, seed=23)
+    lr.round = 90
+    lr.train_rounds(260)
+    for r in range(90, 350):
+        ob.q_round(oq, olp, r)
+    q = lr.q.cpu().numpy()
+    for s, a, v in [x for x in oq.items() if x[1] != "B"]:
+        assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
+    cars = {k: v.cpu().numpy() for k, v in env.cars().items()}
+    for e in range(0, n, 5):
+        oc = ob.env_cars(e)
+        assert [int(x) for x in cars["node"][e]] == [c[0] for c in oc], e
+        assert (int(cars["episode"][e]), int(cars["steps"][e])) == ob.counters(e)
+    assert int((env.records[:, 3] & 0x700).sum()) == 0
+    # profiling hook: one launch of the round kernel alone
+    env2 = BatchedEnv(sc, 4096, seed=5)
+    lr2 = BatchedQLearner(env2, episodes=5000, seed=5)
+    lr2.profile_env_kernel()
+    st = env2.stats()
+    assert st["agent_steps"] == 2 * 4096 and st["q_updates"] == st["agent_steps"]
 
 
 def test_full_size_properties():
