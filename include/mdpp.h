@@ -128,6 +128,8 @@ void *mdpp_env_records(mdpp_handle *h);
 void *mdpp_visited_bits(mdpp_handle *h);
 /* device pointer to [n_envs] u32: state id at which MDPP_LEARN_DETECT flagged env e, 0xFFFFFFFF = none */
 void *mdpp_deadlock_states(mdpp_handle *h);
+/* number of learner kernels (env / round / pull / copy) launched through this handle so far */
+uint64_t mdpp_launch_count(mdpp_handle *h);
 
 /* ---- env: reset / initialize (reference src/env_gym.py:643-672,331-352) -------------------- */
 /* headings: [n_envs][n_cars] u8 in 0..3 (N,E,S,W) or NULL => Philox.  env_mask: [n_envs] u8, NULL = all.

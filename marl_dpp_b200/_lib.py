@@ -16,7 +16,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 # every symbol include/mdpp.h declares (tests check that the built library exports all of them)
 EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_error_string", "mdpp_abi_version",
-           "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_query_transitions",
+           "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_launch_count", "mdpp_query_transitions",
            "mdpp_update_car", "mdpp_dqn_observe", "mdpp_dqn_act", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
            "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
            "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
@@ -61,6 +61,7 @@ def lib():
         "mdpp_env_records": (P, [P]),
         "mdpp_visited_bits": (P, [P]),
         "mdpp_deadlock_states": (P, [P]),
+        "mdpp_launch_count": (U64, [P]),
         "mdpp_query_transitions": (I, [P, I, I, U32, U8, I64, U8, U32, F32, U8, P]),
         "mdpp_update_car": (I, [P, I, U8, P]),
         "mdpp_dqn_observe": (I, [P, I, U8, U8, U32, P]),

@@ -213,6 +213,10 @@ class BatchedEnv:
                 "next_state": torch.empty(shape, dtype=torch.int32, device=dev)}
 
     # -- inspection ----------------------------------------------------------------------------
+    def launch_count(self):
+        """Learner kernels launched through this handle so far."""
+        return int(self._L.mdpp_launch_count(self._h))
+
     def stats(self, reset=False):
         s = MdppStats()
         with torch.cuda.device(self.device):

@@ -32,6 +32,13 @@ constexpr size_t kMaxDenseMarks = 8 * 200 * 1024; // shared-memory BIT map (atom
 constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices per region: sub-step kernels, one CTA per SM
 constexpr uint32_t kMaxRoundCtas = 320;           // ... fused round kernels, up to two CTAs per SM (byte-map tables only)
 
+// a library kernel launch: counted per handle (mdpp_launch_count), error-checked
+#define MDPP_LAUNCH(h, call)                                                                     \
+    do {                                                                                        \
+        MDPP_CUDA(call);                                                                        \
+        (h)->launches += 1;                                                                     \
+    } while (0)
+
 struct Carve {
     size_t tables, nodetab, fast, rng, bad, recs, sinfo, qalt, marks, flags, bits, list, vals, visited, control, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
@@ -99,6 +106,7 @@ struct mdpp_handle {
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool chain;             // the previous launch on the stream was one of our learner kernels
     bool fast_rollout;      // the table-driven rollout kernel applies (BFS lengths fit its move table)
+    uint64_t launches;      // learner kernels launched through this handle (bench.py's gpu_launches)
     uint32_t smem_configured; // env-kernel variants whose dynamic shared-memory limit has been raised
     uint32_t round_parity;    // fused rounds alternate between two sets of mark regions
     // Upper bound on every env's episode counter at the current point of the stream.  While it is below the
@@ -286,6 +294,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->chain = false;
     h->smem_configured = 0;
     h->round_parity = 0;
+    h->launches = 0;
     h->ep_bound = 0; // the workspace is zeroed below: every episode counter starts at 0
     h->ep_device_max_valid = true;
     h->dev.tables = (const uint32_t *)(h->ws + cv.tables);
@@ -357,6 +366,7 @@ int mdpp_destroy(mdpp_handle *h) {
 void *mdpp_env_records(mdpp_handle *h) { return h ? h->ws + h->cv.recs : nullptr; }
 void *mdpp_visited_bits(mdpp_handle *h) { return h ? h->ws + h->cv.visited : nullptr; }
 void *mdpp_deadlock_states(mdpp_handle *h) { return h ? h->ws + h->cv.dl : nullptr; }
+uint64_t mdpp_launch_count(mdpp_handle *h) { return h ? h->launches : 0; }
 
 #define MDPP_DISPATCH_NC(h, KERNEL, grid, s, ...)                                               \
     switch ((h)->cfg.n_cars) {                                                                  \
@@ -573,7 +583,7 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
             MDPP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_bytes)); \
             h->smem_configured |= 1u << variant;                                                                 \
         }                                                                                                        \
-        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ea, mk, control_of(h)));                       \
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ea, mk, control_of(h)));                       \
     } while (0)
 #define MDPP_QENV_C(NCV, CV)                                                                                     \
     if (h->cv.dense) {                                                                                           \
@@ -621,16 +631,16 @@ static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_le
     const Marks mk = marks ? *marks : marks_of(h);
     if (h->cv.dense) {
         LearnLaunch ll(h, grid_for(mk.n_marks), s);
-        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
                                      lp->discount, early_trigger, control_of(h)));
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)mk.capacity + kThreads - 1) / kThreads,
                                                           (int64_t)h->sm_count * 8);
         LearnLaunch l1(h, grid, s);
-        MDPP_CUDA(cudaLaunchKernelEx(&l1.cfg, q_pull_list_compute_kernel, (const float *)qsrc, mk, lp->alpha, lp->discount));
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&l1.cfg, q_pull_list_compute_kernel, (const float *)qsrc, mk, lp->alpha, lp->discount));
         h->chain = true;
         LearnLaunch l2(h, grid, s);
-        MDPP_CUDA(cudaLaunchKernelEx(&l2.cfg, q_pull_list_apply_kernel, qsrc, mk, control_of(h)));
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&l2.cfg, q_pull_list_apply_kernel, qsrc, mk, control_of(h)));
     }
     h->chain = true;
     if (!marks) h->parity ^= 1u;
@@ -680,7 +690,7 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
             h->smem_configured |= 1u << (BIT);                                                                   \
         }                                                                                                        \
         LearnLaunch ll(h, grid, s, kRoundThreads, (SMEM));                                                       \
-        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ra, control_of(h)));                           \
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ra, control_of(h)));                           \
         h->chain = true;                                                                                         \
     } while (0)
     if (h->cfg.n_cars == 1) {
@@ -722,6 +732,7 @@ static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStrea
     const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
     MDPP_CUDA(cudaGetLastError());
+    h->launches += 1;
     h->chain = false;
     return MDPP_OK;
 }
@@ -930,10 +941,10 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     LearnLaunch ll(h, round_ctas(h), s, kRoundThreads, smem);
     if (h->cfg.n_cars == 1) {
         MDPP_CUDA(cudaFuncSetAttribute(q_round_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_round_kernel<1, 0>, h->dev, *lp, ra, control_of(h)));
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_round_kernel<1, 0>, h->dev, *lp, ra, control_of(h)));
     } else {
         MDPP_CUDA(cudaFuncSetAttribute(q_round_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MDPP_CUDA(cudaLaunchKernelEx(&ll.cfg, q_round_kernel<2, 0>, h->dev, *lp, ra, control_of(h)));
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_round_kernel<2, 0>, h->dev, *lp, ra, control_of(h)));
     }
     h->ep_bound += 1;
     return MDPP_OK;
