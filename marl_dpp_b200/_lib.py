@@ -19,7 +19,7 @@ EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_err
            "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_launch_count", "mdpp_query_transitions",
            "mdpp_update_car", "mdpp_dqn_observe", "mdpp_dqn_act", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
            "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
-           "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
+           "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
 
 
 def needs_build():
@@ -77,6 +77,7 @@ def lib():
         "mdpp_q_train_rounds": (I, [P, F32, P, U64, I, P]),
         "mdpp_q_train_rounds_host": (I, [P, F32, P, U64, I, P, P]),
         "mdpp_q_profile_env_kernel": (I, [P, F32, P, U64, P]),
+        "mdpp_fast_tables": (I64, [P, P, I64]),
         "mdpp_decode_state": (I, [P, I64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "mdpp_encode_state": (I64, [P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
         "mdpp_get_stats_host": (I, [P, P, I, P]),

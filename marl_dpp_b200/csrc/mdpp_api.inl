@@ -258,6 +258,13 @@ static bool build_fast_tabs(const mdpp_config &c, FastTabs &t) {
 extern "C" {
 
 int mdpp_abi_version(void) { return MDPP_ABI_VERSION; }
+
+int64_t mdpp_fast_tables(const mdpp_config *cfg, void *out_host, int64_t bytes) {
+    if (validate_config(cfg)) return -MDPP_EINVAL;
+    if (!out_host) return (int64_t)sizeof(FastTabs);
+    if (bytes < (int64_t)sizeof(FastTabs)) return -fail(MDPP_EINVAL, "buffer smaller than the table image");
+    return build_fast_tabs(*cfg, *(FastTabs *)out_host) ? (int64_t)sizeof(FastTabs) : 0;
+}
 const char *mdpp_last_error_string(void) { return g_err; }
 
 int64_t mdpp_workspace_bytes(const mdpp_config *cfg, int64_t n_envs) {

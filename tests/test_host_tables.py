@@ -157,3 +157,121 @@ def test_workspace_size_and_no_cpu_fallback():
         h = C.c_void_p()
         rc = L.mdpp_create(C.byref(sc.cfg), 16, 0, C.c_void_p(256), 1 << 30, None, None, C.byref(h))
         assert rc in (2, 3) and not h.value  # MDPP_ENODEVICE / MDPP_ECUDA: never a silent CPU path
+
+
+def _fast_tables(sc):
+    """Host-built table image of the table-driven kernels, decoded into numpy arrays."""
+    L = _lib.lib()
+    size = L.mdpp_fast_tables(C.byref(sc.cfg), None, 0)
+    buf = np.zeros(size, dtype=np.uint8)
+    assert L.mdpp_fast_tables(C.byref(sc.cfg), buf.ctypes.data_as(C.c_void_p), size) == size
+    off = 0
+    own = buf[off:off + 5 * 256 * 16].view(np.uint32).reshape(5, 256, 4); off += 5 * 256 * 16
+    oth = buf[off:off + 5 * 256 * 8].view(np.uint32).reshape(5, 256, 2); off += 5 * 256 * 8
+    ghost = buf[off:off + 5 * 8].view(np.uint32).reshape(5, 2); off += 5 * 8
+    nth = buf[off:off + 32 * 4].view(np.uint32); off += 32 * 4
+    off = (off + 15) & ~15
+    nxt = buf[off:off + 5 * 256 * 8 * 2].view(np.uint16).reshape(5, 256, 8)
+    return own, oth, ghost, nth, nxt
+
+
+@pytest.mark.parametrize("block,boxes,idx,choose", SCEN)
+def test_fast_tables_replay_the_oracle_env(block, boxes, idx, choose):
+    """The round / rollout kernels read everything the reference derives from a car's (node,
+    destination_index) from host-built tables.  Here the kernel's step (csrc/q_round.cuh round_car_step /
+    rollout_car_step) is restated in Python on those tables and replayed against the oracle env from random
+    joint states: state string, legal set, and for every legal action the successor, the car after
+    update_car and both rewards must agree -- ghosts of finished cars included."""
+    rng = np.random.default_rng(7)
+    sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=None)
+    own, oth, ghost, nth, nxt = _fast_tables(sc)
+    n = sc.n_cars
+    ocfg = orc.Config(m.layout_3[block])
+    env = orc.Env(ocfg)
+    env.reset()
+    env.initialize_cars(n)
+    env.initialize(idx, [b + "N" for b in boxes], choose)
+    nodes = [nd for nd in range(sc.node_base, sc.node_base + sc.n_local_nodes) if not ocfg.in_no_node_list(nd)]
+    A5TO6 = [0, 1, 2, 3, 5]
+    stride = len(sc.dest_nodes) * sc.n_local_nodes
+    checked = 0
+    for trial in range(300):
+        # a random joint state: distinct boxes for the cars still driving, some cars finished with a ghost count
+        fields = []
+        used = set()
+        for i in range(n):
+            done = trial % 3 == 0 and rng.random() < 0.3
+            if done:
+                cnt = int(rng.integers(-2, 6))
+                env.set_car(i, sc.parking, int(rng.integers(0, 2)), 1, cnt)
+                fields.append((sc.parking, 0, 1, cnt))
+                continue
+            while True:
+                nd = int(rng.choice(nodes))
+                if (nd >> 2) % 9 not in used:
+                    break
+            used.add((nd >> 2) % 9)
+            di = int(rng.integers(0, 2))
+            env.set_car(i, nd, di, 0, 5)
+            fields.append((nd, di, 0, 5))
+        c = int(rng.integers(0, n))
+        if fields[c][2]:
+            continue
+        node, di = fields[c][0], fields[c][1]
+        o = own[c][node | (di << 7)]
+        codes, occ9, occ18 = [], 0, 0
+        for i in range(n):
+            if i == c:
+                continue
+            nd_i, di_i, done_i, cnt_i = fields[i]
+            e = (0, 0)
+            if not done_i:
+                e = oth[i][nd_i | (di_i << 7)]
+            elif cnt_i > 0:          # training_done_count - 1 >= 0: the ghost is still listed (src/env_gym.py:307-318)
+                e = ghost[i]
+            codes.append(int(e[0]) >> 18)
+            occ18 |= int(e[0]) & 0x3FFFF
+            occ9 |= int(e[1])
+        codes.sort()
+        rank = sum(_comb_ref(cd + j, j + 1) for j, cd in enumerate(codes))
+        sidx = rank * stride + (int(o[0]) & 0x3FF)
+        st = env.encodestate(c, 1)
+        assert sc.decode(sidx) == orc.state_str(st), trial
+        lm = (int(o[0]) >> 24) & 31
+        hit = (occ9 * 0x201) & int(o[1])
+        if hit & 0x1FF:
+            lm &= 8
+        if (hit >> 9) or (((int(o[1]) >> 18) & 1) and (int(o[2]) & occ18)):
+            lm &= ~8
+        legal6 = env.legal(st)
+        assert lm == (legal6 & 0xF) | (((legal6 >> 5) & 1) << 4), (trial, orc.state_str(st))
+        dnode = (int(o[0]) >> 10) & 127
+        for a in range(5):
+            if not (lm >> a) & 1:
+                continue
+            mv = int(nxt[c][node | (di << 7)][a])
+            reached = (mv >> 9) & 1
+            nn = dnode if reached else mv & 127
+            ns = env.successor_state(st, A5TO6[a])
+            assert ns.pnode == nn
+            for dqn in (False, True):   # no bad-states file here: the arithmetic branch of q_reward / dqn_reward
+                r = -10 + 50 * ((int(o[3]) & 0xFF) - (mv >> 10)) + ((110 if dqn else 10010) if reached else 0)
+                want = env.reward(st, ns, c, dqn)
+                assert (r / 100.0 if dqn else float(r)) == want, (trial, a, dqn)
+            # update_car on a scratch copy of the car
+            env.update_car(c, nn)
+            got = env.car(c)
+            assert (got[0], got[1], got[2]) == (mv & 127, (mv >> 7) & 1, (mv >> 8) & 1), (trial, a)
+            env.set_car(c, node, di, 0, 5)
+            checked += 1
+        # encodestate(., 1) moved the ghost counters: put the finished cars back for the next trial
+    assert checked > 500
+    for mask in range(32):
+        bits = [k for k in range(5) if (mask >> k) & 1]
+        for j, k in enumerate(bits):
+            assert (int(nth[mask]) >> (3 * j)) & 7 == k
+
+
+def _comb_ref(n, k):
+    from math import comb
+    return comb(n, k) if n >= k else 0
