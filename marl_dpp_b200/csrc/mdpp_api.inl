@@ -688,6 +688,8 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
     const unsigned grid = round_ctas(h);
+    ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / grid);
+    ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
     Marks mk = marks_of(h);
     mk.n_ctas = grid;
 #define MDPP_ROUND_K(KERNEL, SMEM, BIT)                                                                          \
@@ -944,6 +946,8 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     ra.cta_slots = h->cv.cta_slots;
     ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / round_ctas(h));
+    ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % round_ctas(h));
     const size_t smem = round_smem_bytes(h->cfg.n_cars, ra.map_bytes, h->cfg.n_cars);
     LearnLaunch ll(h, round_ctas(h), s, kRoundThreads, smem);
     if (h->cfg.n_cars == 1) {

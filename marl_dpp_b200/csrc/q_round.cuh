@@ -65,6 +65,7 @@ struct RoundArgs {
     uint32_t *defer_flags;       // [n_ctas] K0 writes, K1 reads: this CTA parked at least one lane
     uint32_t words_per_cta, cta_slots, map_bytes;
     uint32_t rank_stride;        // n_dest_nodes * n_local_nodes
+    uint32_t tiles_q, tiles_r;   // CTA b owns tiles [b * q + min(b, r), ... + q + (b < r)): no division on the device
 };
 
 enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
@@ -172,25 +173,25 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
         if (ra.defer_flags[blockIdx.x] == 0u) return;
     }
     // the first tile's records are requested before the tables are staged (K0 reads them cold from HBM)
-    const uint32_t tiles = (ra.n_envs + 31u) >> 5;
-    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
-    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
+    const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
+    constexpr uint32_t kBlock = kRoundThreads, n_warps = kRoundThreads / 32; // compile-time trip counts
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t t = t0 + warp;
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
     {   // tables and maps
         const uint4 *src_own = &ra.tabs->own[0][0];
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.own[0][0])[i] = __ldg(src_own + i);
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += kBlock) (&S.own[0][0])[i] = __ldg(src_own + i);
         const uint2 *src_oth = &ra.tabs->oth[0][0];
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.oth[0][0])[i] = __ldg(src_oth + i);
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += kBlock) (&S.oth[0][0])[i] = __ldg(src_oth + i);
         const uint4 *src_next = reinterpret_cast<const uint4 *>(&ra.tabs->next[0][0][0]); // 256 x 8 x u16 = 256 uint4 per car
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x)
+        for (uint32_t i = threadIdx.x; i < NC * 256u; i += kBlock)
             reinterpret_cast<uint4 *>(&S.next[0][0][0])[i] = __ldg(src_next + i);
         if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&ra.tabs->nth[threadIdx.x]);
         uint4 *m4 = reinterpret_cast<uint4 *>(maps);
         const uint32_t n16 = (uint32_t)kMaps * (ra.map_bytes >> 4);
-        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = threadIdx.x; i < n16; i += kBlock) m4[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
     }
     __syncthreads();
@@ -272,7 +273,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
         const uint4 *map4 = reinterpret_cast<const uint4 *>(maps + (uint32_t)m * ra.map_bytes);
         const uint32_t n16 = ra.map_bytes >> 4;
         uint32_t *out = m == 0 ? ra.bits_a : ra.bits_b;
-        for (uint32_t wd = threadIdx.x; wd < ra.words_per_cta; wd += blockDim.x) {
+        for (uint32_t wd = threadIdx.x; wd < ra.words_per_cta; wd += kBlock) {
             uint32_t bits = 0;
             if (2u * wd < n16) {
                 const uint4 lo = map4[2u * wd];
