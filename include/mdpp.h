@@ -236,7 +236,7 @@ int64_t mdpp_encode_state(const mdpp_config *cfg, int32_t pnode, int32_t dnode, 
 /* ---- table image of the table-driven kernels (csrc/q_round.cuh FastTabs), built on the host: for tests and
  * inspection without a device.  out_host == NULL returns the image size; otherwise fills it and returns the size
  * (0 if a BFS length does not fit the move table: the rollout then uses its arithmetic kernel), negative on error.
- * Layout: own[5][256] x 16 B, oth[5][256] x 8 B, ghost[5] x 8 B, nth[32] x 4 B, (16-byte aligned) next[5][256][8] x 2 B. */
+ * Layout: own[5][256] x 16 B, oth[5][256] x 8 B, next[5][256][8] x 2 B, nth[32] x 4 B, ghost[5] x 8 B. */
 int64_t mdpp_fast_tables(const mdpp_config *cfg, void *out_host, int64_t bytes);
 
 /* ---- stats ---------------------------------------------------------------------------------- */

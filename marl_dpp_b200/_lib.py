@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libmdpp.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "q_learner.cuh", "q_round.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "fast_tabs.cuh", "q_learner.cuh", "q_round.cuh")] + \
           [os.path.join(ROOT, "include", "mdpp.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

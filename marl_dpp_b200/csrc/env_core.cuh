@@ -41,7 +41,6 @@ struct DevCfg {
     uint32_t dbox_sel[MDPP_MAX_DEST]; // destination-box index -> selective mask     constant reads)
     const uint32_t *tables;      // DEV: SmemTables image
     const uint32_t *bad_bitmap;  // DEV: n_box_states bits
-    uint16_t nth_lut[32];        // per 5-bit mask: positions of its set bits, 3 bits each, lowest first
 };
 
 // Divergently indexed tables live in shared memory (a constant-bank lookup would serialise).
@@ -298,12 +297,6 @@ __device__ __forceinline__ void ldg_row(const float *p, float (&r)[MDPP_Q_ROW]) 
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
                  : "l"(p));
-}
-
-// n-th (0-based) set bit of a 5-bit mask through the 32-entry table in the kernel-parameter block: one
-// indexed constant load (a warp rarely holds more than 3-4 distinct masks) instead of ~22 ALU instructions
-__device__ __forceinline__ uint32_t nth_set_bit_lut(const DevCfg &cfg, uint32_t mask, uint32_t n) {
-    return ((uint32_t)cfg.nth_lut[mask] >> (3u * n)) & 7u;
 }
 
 // n-th (0-based) set bit of a 5-bit mask

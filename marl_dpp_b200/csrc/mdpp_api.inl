@@ -40,7 +40,7 @@ constexpr uint32_t kMaxRoundCtas = 320;           // ... fused round kernels, up
     } while (0)
 
 struct Carve {
-    size_t tables, nodetab, fast, rng, bad, recs, sinfo, qalt, marks, flags, bits, list, vals, visited, control, stage, dl, total;
+    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, bits, list, vals, visited, control, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
     uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
     uint32_t cta_slots, regions; // layout of the bitmap array [parity][region][cta_slots][words_per_cta]
@@ -55,7 +55,6 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     const size_t keys = (size_t)cfg.n_states * MDPP_Q_ROW;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
     c.tables = take(sizeof(SmemTables));
-    c.nodetab = take((size_t)MDPP_NODES * 16);
     c.fast = take(sizeof(FastTabs));
     c.rng = take((size_t)n_envs * 4 * 3);
     c.bad = take((((size_t)cfg.n_box_states + 31) / 32) * 4 + 4);
@@ -176,12 +175,6 @@ static void make_devcfg(const mdpp_config &c, DevCfg &d) {
         d.dn_dbox[i] = c.dest_node_box[i];
     }
     for (int i = 0; i < c.n_dest_boxes; i++) d.dbox_sel[i] = c.sel_mask[i];
-    for (int m = 0; m < 32; m++) {
-        uint32_t packed = 0, n = 0;
-        for (int k = 0; k < 5; k++)
-            if ((m >> k) & 1) packed |= (uint32_t)k << (3 * n++);
-        d.nth_lut[m] = (uint16_t)packed;
-    }
 }
 
 // Table image of the fused round kernel (q_round.cuh): everything the reference derives from a car's
@@ -314,28 +307,11 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     memset(&img, 0, sizeof img);
     for (int n = 0; n < MDPP_NODES; n++) img.nodeinfo[n] = (uint16_t)(cfg->fwd[n] | (cfg->base_legal[n] << 8));
     memcpy(img.bfs, cfg->bfs_len, sizeof img.bfs);
-    uint8_t nodeimg[MDPP_NODES][16];
-    memset(nodeimg, 0, sizeof nodeimg);
-    for (int n = 0; n < MDPP_NODES; n++) {
-        for (int d = 0; d < MDPP_MAX_DEST; d++) nodeimg[n][d] = cfg->bfs_len[d][n];
-        nodeimg[n][8] = cfg->fwd[n];
-        nodeimg[n][9] = cfg->base_legal[n];
-        const uint32_t fwd = cfg->fwd[n];
-        uint32_t selbits = 0, w3 = 1u << ((n >> 2) % 9);
-        if (fwd != MDPP_NONE) {
-            w3 |= 1u << (9 + (fwd >> 2) % 9);
-            for (int d = 0; d < cfg->n_dest_boxes; d++)
-                if ((cfg->sel_mask[d] >> (fwd >> 2)) & 1u) selbits |= 1u << d;
-        }
-        nodeimg[n][10] = (uint8_t)selbits;
-        memcpy(&nodeimg[n][12], &w3, 4);
-    }
     FastTabs *ft = new (std::nothrow) FastTabs();
     if (!ft) { delete h; return fail(MDPP_EINVAL, "out of host memory"); }
     h->fast_rollout = build_fast_tabs(*cfg, *ft) && !(getenv("MDPP_FAST_ROLLOUT") && atoi(getenv("MDPP_FAST_ROLLOUT")) == 0);
     cudaError_t e = cudaMemsetAsync(h->ws, 0, cv.total, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.fast, ft, sizeof(FastTabs), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.nodetab, nodeimg, sizeof nodeimg, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->ws + cv.dl, 0xFF, (size_t)n_envs * 4, s); // no deadlock state yet
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->ws + cv.tables, &img, sizeof img, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && bad_bitmap_host)
@@ -548,6 +524,16 @@ struct LearnLaunch {
     }
 };
 
+static size_t step_tabs_bytes(int n_cars) {
+    switch (n_cars) {
+    case 1: return sizeof(StepTabs<1>);
+    case 2: return sizeof(StepTabs<2>);
+    case 3: return sizeof(StepTabs<3>);
+    case 4: return sizeof(StepTabs<4>);
+    default: return sizeof(StepTabs<5>);
+    }
+}
+
 static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
                         const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward,
                         cudaStream_t s) {
@@ -569,7 +555,8 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     ea.env_id_base = h->env_id_base;
     ea.round = round;
     ea.q = q;
-    ea.nodetab = (const uint4 *)(h->ws + h->cv.nodetab);
+    ea.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    ea.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
     ea.rng_words = (uint32_t *)(h->ws + h->cv.rng);
     ea.rng_mode = rng_mode;
     ea.forced = forced;
@@ -580,14 +567,16 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     const Marks mk = marks_of(h);
     const bool bitmap = (size_t)mk.n_marks > kMaxByteMapMarks;
     const size_t map_bytes = bitmap ? (size_t)mk.words_per_cta * 4 : (((size_t)mk.n_marks + 15) / 16) * 16;
-    LearnLaunch ll = h->cv.dense ? LearnLaunch(h, env_ctas(h), s, kEnvSmemThreads, map_bytes)
+    const size_t tab_bytes = (step_tabs_bytes(h->cfg.n_cars) + 15) & ~(size_t)15;
+    const size_t smem_bytes = h->cv.dense ? tab_bytes + map_bytes : 0; // list mode reads the tables in place
+    LearnLaunch ll = h->cv.dense ? LearnLaunch(h, env_ctas(h), s, kEnvSmemThreads, smem_bytes)
                                  : LearnLaunch(h, grid_for(h->n_envs), s);
     ll.cfg.attrs = &ll.attr; // the struct was copied: re-point at this copy's attribute
     const int variant = car_slot * 2 + (plain ? 1 : 0);
 #define MDPP_QENV_K(KERNEL)                                                                                      \
     do {                                                                                                         \
         if (h->cv.dense && !((h->smem_configured >> variant) & 1u)) {                                            \
-            MDPP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_bytes)); \
+            MDPP_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
             h->smem_configured |= 1u << variant;                                                                 \
         }                                                                                                        \
         MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, KERNEL, h->dev, *lp, ea, mk, control_of(h)));                       \

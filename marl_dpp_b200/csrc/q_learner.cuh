@@ -19,7 +19,7 @@
 // Marks / bitmaps / lists are double-buffered by sub-step parity so that the env kernel of sub-step
 // t+1 may overlap the finalize of sub-step t (programmatic dependent launch).
 #pragma once
-#include "env_core.cuh"
+#include "fast_tabs.cuh"
 
 namespace mdpp {
 
@@ -71,45 +71,6 @@ __device__ __forceinline__ uint32_t eps_q16_of(const LearnArgs &lp, int32_t epis
     return e;
 }
 
-// One 16-byte table entry per node, one LDG through L1 (the 36 entries of a block span 5 cache lines):
-//   bytes 0-7  BFS length to destination node 0..7
-//   byte 8     F successor            byte 9   base legal mask
-//   byte 10    bit d = the box ahead is in the selective-block list keyed by destination box d
-//   word 3     bits 0-8 = 1 << (own box number - 1), bits 9-17 = 1 << (number of the box ahead - 1), 0 if none
-// so that the legal filter (src/env_gym.py:143-224) is a handful of mask tests.
-struct NodeEnt {
-    uint4 v;
-    __device__ __forceinline__ uint32_t bfs(uint32_t d) const {
-        return (uint32_t)((((unsigned long long)v.y << 32) | v.x) >> (8u * d)) & 0xFFu;
-    }
-    __device__ __forceinline__ uint32_t fwd() const { return v.z & 0xFFu; }
-    __device__ __forceinline__ uint32_t base() const { return (v.z >> 8) & 0xFFu; }
-    __device__ __forceinline__ uint32_t selbits() const { return (v.z >> 16) & 0xFFu; }
-};
-__device__ __forceinline__ NodeEnt load_ent(const uint4 *__restrict__ tab, uint32_t node) {
-    NodeEnt e;
-    e.v = __ldg(tab + node);
-    return e;
-}
-// the half of the entry the legal filter and the successor need (training fast path: no BFS lengths)
-__device__ __forceinline__ NodeEnt load_ent_hi(const uint4 *__restrict__ tab, uint32_t node) {
-    NodeEnt e;
-    const uint2 hi = __ldg(reinterpret_cast<const uint2 *>(tab + node) + 1);
-    e.v = make_uint4(0u, 0u, hi.x, hi.y);
-    return e;
-}
-// getlegalactions_filtered for the primary standing on the entry's node: S,L,R,T keep the car in its own box,
-// so they die together when a listed car shares the box NUMBER (:211-217); F dies on the same test for the
-// box ahead or on the selective-block rule (:143-186)
-__device__ __forceinline__ uint32_t legal_mask_ent(const View &v, const NodeEnt &ent) {
-    uint32_t mask = ent.base();
-    const uint32_t hit = (v.occ9 * 0x201u) & ent.v.w; // occupancy against the own box (bits 0-8) and the box ahead (9-17)
-    if (hit & 0x1FFu) mask &= 1u << MDPP_A_F;
-    const bool sel_blocked = ((ent.selbits() >> v.dbox) & 1u) && (v.sel & v.occ18);
-    if ((hit >> 9) || sel_blocked) mask &= ~(1u << MDPP_A_F);
-    return mask;
-}
-
 // ------------------------------------------------------------------------------------------------
 // env side of one sub-step: car slot C of every env
 // ------------------------------------------------------------------------------------------------
@@ -135,7 +96,8 @@ struct EnvArgs {
     uint32_t env_id_base;
     uint64_t round;
     const float *q;
-    const uint4 *nodetab;
+    const FastTabs *tabs;
+    uint32_t rank_stride; // n_dest_nodes * n_local_nodes
     uint32_t *rng_words;
     int rng_mode;
     const uint8_t *forced;
@@ -153,9 +115,9 @@ struct StepCounts {
 
 // One agent-step of car C in env e (record `rec` already loaded).  Returns true and sets `key` when the env
 // updated a key; the caller owns the marking.  Writes the record back and the optional outputs.
-template <int NC, int C, bool PLAIN>
-__device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &lp, const EnvArgs &ea, int64_t e,
-                                            uint4 rec, uint32_t &key, StepCounts &cnt) {
+template <int NC, int C, bool PLAIN, class Tabs>
+__device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, const LearnArgs &lp,
+                                            const EnvArgs &ea, int64_t e, uint4 rec, uint32_t &key, StepCounts &cnt) {
     const uint32_t lflags = PLAIN ? 0u : lp.flags;
     const uint8_t *forced = PLAIN ? nullptr : ea.forced;
     uint8_t *action_out = PLAIN ? nullptr : ea.action_out;
@@ -183,10 +145,10 @@ __device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &
         word = ea.rng_words[(size_t)(C - 1) * ea.n_envs + e];
     }
     if (live && !f_done(car_field(cars, C))) {
-        View v = view_of<NC>(cars, C, mode, cfg);
-        const NodeEnt entP = PLAIN ? load_ent_hi(ea.nodetab, v.pnode) : load_ent(ea.nodetab, v.pnode);
-        const uint32_t lm = legal_mask_ent(v, entP);
-        const uint32_t sidx = state_index(v, v.pnode, cfg);
+        const FastView v = fast_view<NC, C>(S, ea.tabs, cars, mode, ea.rank_stride);
+        const uint64_t before = cars; // the reward's clash term reads the cars before update_car
+        cars = v.cars;                // the encode's ghost side effects stay whether or not the car moves
+        const uint32_t lm = v.lm, sidx = v.sidx;
         s_out = sidx;
         uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
         const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
@@ -207,7 +169,7 @@ __device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &
                 const uint32_t w = ea.rng_mode ? word : decision_word(ea.round, C, lp.seed, env);
                 explore = (w >> 16) < eps16; // flipcoin (utils.py:255-265)
                 // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
-                a = nth_set_bit_lut(cfg, lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
+                a = (S.nth[lm] >> (3u * (((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
             }
             if (!explore) { // computeactionfromqvalues: first maximum in S,L,R,F,T order (:659-667)
                 pdl_wait();  // the only Q read of this kernel: the preceding pull must be complete
@@ -241,34 +203,15 @@ __device__ __forceinline__ bool env_substep(const DevCfg &cfg, const LearnArgs &
                     key = sidx * MDPP_Q_ROW + a;
                     touched = true;
                 }
-                // ---- env step: successor (src/env_gym.py:256-265), update_car (:386-441) ----
-                const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
-                const uint32_t nn = a == MDPP_A_F ? entP.fwd() : ((v.pnode & ~3u) | ((v.pnode + rot) & 3u));
+                // ---- env step: successor (src/env_gym.py:256-265) + update_car (:386-441) = one table entry ----
+                const uint32_t mv = S.next[C][v.f & 0xFFu][a];
                 if constexpr (!PLAIN) { // q_reward (:555-620) for reward_out / reward_sum
-                    int32_t ri;
-                    bool bad_next = false, bad_prev = false;
-                    if (cfg.bad_on) { // :568-577 on the heading-stripped strings
-                        const uint32_t base = (v.rank * cfg.n_dest_boxes + v.dbox) * cfg.n_src_boxes;
-                        const uint32_t idn = base + ((nn >> 2) - cfg.box_base), idp = base + ((v.pnode >> 2) - cfg.box_base);
-                        bad_next = (__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u;
-                        bad_prev = (__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u;
-                    }
-                    if (bad_next) ri = -10000;
-                    else if (bad_prev) ri = 0;
-                    else {
-                        const NodeEnt entN = load_ent(ea.nodetab, nn);
-                        ri = -10 + 50 * ((int32_t)entP.bfs(v.dnidx) - (int32_t)entN.bfs(v.dnidx));
-                        if (nn == v.dnode) ri += 10010;
-                        int32_t clash = 0;
-#pragma unroll
-                        for (int i = 0; i < NC; i++)
-                            if (i != C) clash += ((f_node(car_field(cars, i)) >> 2) == (nn >> 2));
-                        ri -= clash * 100000;
-                    }
+                    const int32_t ri = fast_reward<NC, C>(v, mv, before, MDPP_REWARD_Q, cfg);
                     cnt.reward += ri;
                     r_out = (float)ri;
                 }
-                cars = advance_car(cars, C, v, nn, cfg);
+                const uint32_t nf = (mv & 0x1FFu) | (v.f & 0xE00u);
+                cars = (cars & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
                 steps = steps < 0xFFFFu ? steps + 1 : steps;
                 cnt.steps += 1;
             }
@@ -337,11 +280,14 @@ __device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &c
     }
 }
 
-// list mode (large tables): one CTA per 256-env tile, touched bitmap + key list in global memory
+// list mode (large tables): one CTA per 256-env tile, touched bitmap + key list in global memory.  The step tables
+// are read in place through L1 (a 256-env CTA cannot amortise staging 40 KB; a persistent variant with staged
+// tables measured 10-40 % slower: fewer warps to hide the returning atomic).
 template <int NC, int C, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
 q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
     __shared__ CtaCounters cc;
+    const StepTabs<MDPP_MAX_CARS> &S = *reinterpret_cast<const StepTabs<MDPP_MAX_CARS> *>(ea.tabs);
     if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
     // PDL: the pull kernel that follows may be scheduled as SM slots free up (it waits for this grid to
     // complete before it looks at the marks)
@@ -352,7 +298,7 @@ q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
     bool first = false; // this lane is the first toucher of its key in this sub-step
     uint32_t key = 0;
     if (e < ea.n_envs) {
-        if (env_substep<NC, C, PLAIN>(cfg, lp, ea, e, ea.recs[e], key, cnt)) {
+        if (env_substep<NC, C, PLAIN>(S, cfg, lp, ea, e, ea.recs[e], key, cnt)) {
             // Check through L1 first: the returning atomic on a hot bitmap word is what this kernel waits for
             // (ncu, 4 cars: 80 us with 1.3 M atomic sectors for the car slot whose envs share states, 21 us with
             // 0.4 M for the one whose envs are spread).  L1 is not coherent, but the word can only be stale
@@ -391,10 +337,13 @@ constexpr int kEnvSmemThreads = 1024;
 template <int NC, int C, bool PLAIN, bool BITS>
 __global__ void __launch_bounds__(kEnvSmemThreads, 1)
 q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
-    extern __shared__ uint4 smem_map4[];          // bytes: 16 keys per uint4; bits: 128 keys per uint4
+    extern __shared__ uint4 smem_dyn[];           // step tables, then the map (bytes: 16 keys per uint4; bits: 128)
     __shared__ CtaCounters cc;
+    StepTabs<NC> &S = *reinterpret_cast<StepTabs<NC> *>(smem_dyn);
+    uint4 *smem_map4 = smem_dyn + (sizeof(StepTabs<NC>) + 15) / 16;
     uint8_t *map = reinterpret_cast<uint8_t *>(smem_map4);
     uint32_t *map32 = reinterpret_cast<uint32_t *>(smem_map4);
+    stage_step_tabs<NC, kEnvSmemThreads>(S, ea.tabs);
     const uint32_t n16 = BITS ? (mk.words_per_cta + 3u) >> 2 : (mk.n_marks + 15u) >> 4;
     for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) smem_map4[i] = make_uint4(0u, 0u, 0u, 0u);
     if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
@@ -413,7 +362,7 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
         if (tn < t1 && tn * 32 + lane < ea.n_envs) rec_next = ea.recs[tn * 32 + lane];
         if (e < ea.n_envs) {
             uint32_t key = 0;
-            if (env_substep<NC, C, PLAIN>(cfg, lp, ea, e, rec, key, cnt)) {
+            if (env_substep<NC, C, PLAIN>(S, cfg, lp, ea, e, rec, key, cnt)) {
                 const uint32_t m = (key >> 3) * MDPP_N_ACT + (key & 7u); // compact key: no marks for the padding slots
                 if constexpr (BITS) atomicOr(map32 + (m >> 5), 1u << (m & 31u));
                 else map[m] = 1;

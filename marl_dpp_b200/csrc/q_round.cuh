@@ -26,29 +26,8 @@
 
 namespace mdpp {
 
-// host-built table image (workspace); the kernels copy the first n_cars rows to shared memory
-struct FastTabs {
-    uint4 own[MDPP_MAX_CARS][256];  // index = node | destination_index << 7 (the low 8 bits of a car field)
-    uint2 oth[MDPP_MAX_CARS][256];  // same index, car seen as an "other"
-    uint2 ghost[MDPP_MAX_CARS];     // oth-format entry of the finished car's ghost
-    uint32_t nth[32];               // per 5-bit mask: positions of its set bits, 3 bits each, lowest first
-    alignas(16) uint16_t next[MDPP_MAX_CARS][256][8]; // [car][node | di << 7][action]: successor (src/env_gym.py:256-265) +
-        // update_car (:386-441) folded: bits 0-8 = node | di << 7 | done << 8 after the move, bit 9 = the move reached
-        // the car's destination node, bits 10-15 = BFS length successor -> that destination (q_reward / dqn_reward)
-};
-// own.x: bits 0-9 dnidx * n_local_nodes + node_local | 10-16 destination node | 17-23 F successor (127 none)
-//        | 24-28 base legal mask | 29-31 destination-box index
-// own.y: bits 0-8 1 << (own box number - 1) | 9-17 1 << (number of the box ahead - 1) | 18 box ahead is in the
-//        selective-block list keyed by this car's current destination box
-// own.z: that selective-block list as an 18-bit box mask        own.w: bits 0-7 BFS length node -> the car's destination
-// oth.x: bits 0-17 1 << box18 | 18-25 others-code        oth.y: bits 0-8 1 << (box number - 1)
-
 template <int NC>
-struct RoundSmem {
-    uint4 own[NC][256];
-    uint2 oth[NC][256];
-    uint16_t next[NC][256][8];
-    uint32_t nth[32];
+struct RoundSmem : StepTabs<NC> {
     CtaCounters cc;
     uint32_t any_deferred;
 };
@@ -181,14 +160,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
     {   // tables and maps
-        const uint4 *src_own = &ra.tabs->own[0][0];
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += kBlock) (&S.own[0][0])[i] = __ldg(src_own + i);
-        const uint2 *src_oth = &ra.tabs->oth[0][0];
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += kBlock) (&S.oth[0][0])[i] = __ldg(src_oth + i);
-        const uint4 *src_next = reinterpret_cast<const uint4 *>(&ra.tabs->next[0][0][0]); // 256 x 8 x u16 = 256 uint4 per car
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += kBlock)
-            reinterpret_cast<uint4 *>(&S.next[0][0][0])[i] = __ldg(src_next + i);
-        if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&ra.tabs->nth[threadIdx.x]);
+        stage_step_tabs<NC, kBlock>(S, ra.tabs);
         uint4 *m4 = reinterpret_cast<uint4 *>(maps);
         const uint32_t n16 = (uint32_t)kMaps * (ra.map_bytes >> 4);
         for (uint32_t i = threadIdx.x; i < n16; i += kBlock) m4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -417,14 +389,7 @@ rollout_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
     RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
     __shared__ long long cta_reward;
     {
-        const uint4 *src_own = &tabs->own[0][0];
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.own[0][0])[i] = __ldg(src_own + i);
-        const uint2 *src_oth = &tabs->oth[0][0];
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x) (&S.oth[0][0])[i] = __ldg(src_oth + i);
-        const uint4 *src_next = reinterpret_cast<const uint4 *>(&tabs->next[0][0][0]);
-        for (uint32_t i = threadIdx.x; i < NC * 256u; i += blockDim.x)
-            reinterpret_cast<uint4 *>(&S.next[0][0][0])[i] = __ldg(src_next + i);
-        if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&tabs->nth[threadIdx.x]);
+        stage_step_tabs<NC, kRolloutThreads>(S, tabs);
         if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; cta_reward = 0ll; }
     }
     __syncthreads();

@@ -168,10 +168,9 @@ def _fast_tables(sc):
     off = 0
     own = buf[off:off + 5 * 256 * 16].view(np.uint32).reshape(5, 256, 4); off += 5 * 256 * 16
     oth = buf[off:off + 5 * 256 * 8].view(np.uint32).reshape(5, 256, 2); off += 5 * 256 * 8
-    ghost = buf[off:off + 5 * 8].view(np.uint32).reshape(5, 2); off += 5 * 8
+    nxt = buf[off:off + 5 * 256 * 8 * 2].view(np.uint16).reshape(5, 256, 8); off += 5 * 256 * 8 * 2
     nth = buf[off:off + 32 * 4].view(np.uint32); off += 32 * 4
-    off = (off + 15) & ~15
-    nxt = buf[off:off + 5 * 256 * 8 * 2].view(np.uint16).reshape(5, 256, 8)
+    ghost = buf[off:off + 5 * 8].view(np.uint32).reshape(5, 2)
     return own, oth, ghost, nth, nxt
 
 
