@@ -129,13 +129,12 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
 }
 
 // CSTART = 0: K0, every live env, cars 0..NC-1 while they explore.  CSTART = 1 (NC = 2): K1, parked lanes only.
-#ifndef MDPP_ROUND_THREADS
-#define MDPP_ROUND_THREADS 1024
-#define MDPP_ROUND_CTAS_PER_SM 1
-#endif
-constexpr int kRoundThreads = MDPP_ROUND_THREADS, kRoundCtasPerSm = MDPP_ROUND_CTAS_PER_SM;
+constexpr int kRoundThreads = 1024, kRoundCtasPerSm = 1; // 2 x 768 (40 registers, spills) and 2 x 512 measured slower
+// 54 registers x 1024 threads leave room for one CTA of the pull kernel (34 x 256) per SM: the pull of sub-step 0
+// is then resident while this kernel runs instead of being launched as it drains (isolated round 27.1 -> 26.5 us;
+// at 46 registers, room for both pulls, the kernel spills and loses 2 us).
 template <int NC, int CSTART>
-__global__ void __launch_bounds__(kRoundThreads, kRoundCtasPerSm)
+__global__ void __maxnreg__(54)
 q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     static_assert(NC >= 1 && NC <= 2 && CSTART < NC, "the fused round is built for 1- and 2-car tables");
     extern __shared__ uint4 smem_dyn[];
