@@ -62,8 +62,18 @@ struct FastView {
     uint4 own;       // the primary's table entry
     uint32_t f;      // its 12-bit field
     uint32_t rank, sidx, lm;
+    uint32_t occ9, occ18; // boxes the listed others occupy: by box number, by floor + box
     uint64_t cars;   // records after the encode's side effects
 };
+
+// getlegalactions_filtered (src/env_gym.py:143-224) for a primary whose table entry is `own`
+__device__ __forceinline__ uint32_t fast_legal(const uint4 &own, uint32_t occ9, uint32_t occ18) {
+    uint32_t lm = (own.x >> 24) & 31u;
+    const uint32_t hit = (occ9 * 0x201u) & own.y; // occupancy against the own box (bits 0-8) and the box ahead (9-17)
+    if (hit & 0x1FFu) lm &= 1u << MDPP_A_F;
+    if ((hit >> 9) || (((own.y >> 18) & 1u) && (own.z & occ18))) lm &= ~(1u << MDPP_A_F);
+    return lm;
+}
 
 template <int NC, int C, class Tabs>
 __device__ __forceinline__ FastView fast_view(const Tabs &S, const FastTabs *__restrict__ gt, uint64_t cars,
@@ -105,10 +115,9 @@ __device__ __forceinline__ FastView fast_view(const Tabs &S, const FastTabs *__r
     }
     v.rank = rank;
     v.sidx = rank * rank_stride + (v.own.x & 0x3FFu);
-    uint32_t lm = (v.own.x >> 24) & 31u;
-    const uint32_t hit = (occ9 * 0x201u) & v.own.y; // occupancy against the own box (bits 0-8) and the box ahead (9-17)
-    if (hit & 0x1FFu) lm &= 1u << MDPP_A_F;
-    if ((hit >> 9) || (((v.own.y >> 18) & 1u) && (v.own.z & occ18))) lm &= ~(1u << MDPP_A_F);
+    const uint32_t lm = fast_legal(v.own, occ9, occ18);
+    v.occ9 = occ9;
+    v.occ18 = occ18;
     v.lm = lm;
     return v;
 }

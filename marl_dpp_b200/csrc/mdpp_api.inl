@@ -360,6 +360,24 @@ uint64_t mdpp_launch_count(mdpp_handle *h) { return h ? h->launches : 0; }
     default: KERNEL<5><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                           \
     }
 
+// kernels templated on <n_cars, car slot>
+#define MDPP_DISPATCH_C(NCV, c, KERNEL, grid, s, ...)                                             \
+    switch (c) {                                                                                \
+    case 0: KERNEL<NCV, 0><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;                       \
+    case 1: KERNEL<NCV, (NCV > 1 ? 1 : 0)><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;       \
+    case 2: KERNEL<NCV, (NCV > 2 ? 2 : 0)><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;       \
+    case 3: KERNEL<NCV, (NCV > 3 ? 3 : 0)><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;       \
+    default: KERNEL<NCV, (NCV > 4 ? 4 : 0)><<<grid, kThreads, 0, s>>>(__VA_ARGS__); break;      \
+    }
+#define MDPP_DISPATCH_NC_C(h, c, KERNEL, grid, s, ...)                                            \
+    switch ((h)->cfg.n_cars) {                                                                  \
+    case 1: MDPP_DISPATCH_C(1, c, KERNEL, grid, s, __VA_ARGS__) break;                          \
+    case 2: MDPP_DISPATCH_C(2, c, KERNEL, grid, s, __VA_ARGS__) break;                          \
+    case 3: MDPP_DISPATCH_C(3, c, KERNEL, grid, s, __VA_ARGS__) break;                          \
+    case 4: MDPP_DISPATCH_C(4, c, KERNEL, grid, s, __VA_ARGS__) break;                          \
+    default: MDPP_DISPATCH_C(5, c, KERNEL, grid, s, __VA_ARGS__) break;                         \
+    }
+
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 static inline Control *control_of(mdpp_handle *h) { return (Control *)(h->ws + h->cv.control); }
 static inline uint4 *recs_of(mdpp_handle *h) { return (uint4 *)(h->ws + h->cv.recs); }
@@ -823,8 +841,10 @@ int mdpp_dqn_observe(mdpp_handle *h, int car_slot, uint8_t *features, uint8_t *l
     if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
     if (features && ((uintptr_t)features & 15)) return fail(MDPP_EINVAL, "features must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    MDPP_DISPATCH_NC(h, dqn_observe_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, car_slot, features,
-                     legal, state_idx);
+    const FastTabs *tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    const uint32_t stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    MDPP_DISPATCH_NC_C(h, car_slot, dqn_observe_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, tabs, stride,
+                       features, legal, state_idx);
     MDPP_CUDA(cudaGetLastError());
     return MDPP_OK;
 }
@@ -838,9 +858,11 @@ int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *a
     if (reward_kind != MDPP_REWARD_Q && reward_kind != MDPP_REWARD_DQN) return fail(MDPP_EINVAL, "unknown reward kind");
     if (next_features && ((uintptr_t)next_features & 15)) return fail(MDPP_EINVAL, "next_features must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    MDPP_DISPATCH_NC(h, dqn_act_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base, car_slot,
-                     reward_kind, actions, next_features, reward, next_legal, done, status, auto_reset, round, seed,
-                     control_of(h));
+    const FastTabs *tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    const uint32_t stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    MDPP_DISPATCH_NC_C(h, car_slot, dqn_act_kernel, grid_for(h->n_envs), s, h->dev, recs_of(h), h->n_envs, h->env_id_base,
+                       reward_kind, tabs, stride, actions, next_features, reward, next_legal, done, status, auto_reset, round,
+                       seed, control_of(h));
     MDPP_CUDA(cudaGetLastError());
     if (auto_reset && car_slot == h->cfg.n_cars - 1) {
         h->ep_bound += 1;

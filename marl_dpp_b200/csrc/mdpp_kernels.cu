@@ -426,13 +426,24 @@ __device__ __forceinline__ void listed_others(uint64_t cars, int c, int mode, co
     if constexpr (NC > 1) sort_codes<NC>(keys);
 }
 
-// writes the 80 feature bytes of (primary node, destination node, others) to dst (16-byte aligned)
+// Both kernels step through the shared step tables (fast_tabs.cuh), read in place through L1, and take the 8
+// feature bytes of a (box number, heading) pair from a 256-entry shared-memory table instead of recomputing the
+// bit spread per entry: ncu had dqn_act at 683 warp-instructions per 32 envs, issue slots 80 % busy and DRAM
+// at 60 %, i.e. bound by instructions, next to dqn_observe at 79 % of DRAM.
+struct FeatLut {
+    unsigned long long e[256]; // index = number << 3 | dir
+};
+__device__ __forceinline__ void build_feat_lut(FeatLut &lut) {
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) lut.e[i] = feat_entry(i >> 3, i & 7u);
+}
+
 template <int NC>
-__device__ __forceinline__ void write_features(uint4 *dst, uint32_t pnode, uint32_t dnode, const uint32_t (&keys)[NC]) {
+__device__ __forceinline__ void write_features_lut(const FeatLut &lut, uint4 *dst, uint32_t pnode, uint32_t dnode,
+                                                   const uint32_t (&keys)[NC]) {
     const uint32_t dirmap = 0x1320u; // our N,E,S,W (0..3) -> the reference's N=0 W=1 E=2 S=3, one nibble each
     unsigned long long src[MDPP_MAX_CARS], dstv[MDPP_MAX_CARS];
-    src[0] = feat_entry(boxnum0(pnode >> 2) + 1u, (dirmap >> (4u * (pnode & 3u))) & 7u);
-    dstv[0] = feat_entry(boxnum0(dnode >> 2) + 1u, (dirmap >> (4u * (dnode & 3u))) & 7u);
+    src[0] = lut.e[((boxnum0(pnode >> 2) + 1u) << 3) | ((dirmap >> (4u * (pnode & 3u))) & 7u)];
+    dstv[0] = lut.e[((boxnum0(dnode >> 2) + 1u) << 3) | ((dirmap >> (4u * (dnode & 3u))) & 7u)];
 #pragma unroll
     for (int i = 1; i < MDPP_MAX_CARS; i++) {
         src[i] = 0x0101010101010101ull; // missing cars: all ones (:303)
@@ -441,8 +452,8 @@ __device__ __forceinline__ void write_features(uint4 *dst, uint32_t pnode, uint3
             const uint32_t k = keys[i - 1];
             if (k != 0xFFFFFFFFu) {
                 const uint32_t sb = k & 31u, db = (k >> 5) & 31u; // after the rotation: bits 0-4 src, 5-9 dst
-                src[i] = feat_entry(boxnum0(sb) + 1u, 7u);
-                dstv[i] = feat_entry(boxnum0(db) + 1u, 7u);
+                src[i] = lut.e[((boxnum0(sb) + 1u) << 3) | 7u];
+                dstv[i] = lut.e[((boxnum0(db) + 1u) << 3) | 7u];
             }
         }
     }
@@ -457,12 +468,12 @@ __device__ __forceinline__ void write_features(uint4 *dst, uint32_t pnode, uint3
 // 512-byte rows (a lane's own 80 bytes are 80 apart from its neighbour's: direct stores would touch
 // 32 different sectors per instruction).
 template <int NC>
-__device__ __forceinline__ void store_features_coalesced(uint8_t *__restrict__ out, int64_t warp_first_env, int64_t n_envs,
-                                                         uint4 *stage, bool valid, uint32_t pnode, uint32_t dnode,
-                                                         const uint32_t (&keys)[NC]) {
+__device__ __forceinline__ void store_features_lut(const FeatLut &lut, uint8_t *__restrict__ out, int64_t warp_first_env,
+                                                   int64_t n_envs, uint4 *stage, bool valid, uint32_t pnode,
+                                                   uint32_t dnode, const uint32_t (&keys)[NC]) {
     const uint32_t lane = threadIdx.x & 31u;
     uint4 *mine = stage + lane * 5; // 80 bytes per lane
-    if (valid) write_features<NC>(mine, pnode, dnode, keys);
+    if (valid) write_features_lut<NC>(lut, mine, pnode, dnode, keys);
     else {
 #pragma unroll
         for (int j = 0; j < 5; j++) mine[j] = make_uint4(0, 0, 0, 0);
@@ -480,14 +491,16 @@ __device__ __forceinline__ void store_features_coalesced(uint8_t *__restrict__ o
 }
 
 // observe: encodestate(car, 1) with its ghost side effect -> convert(state), give_mask(state), state id
-template <int NC>
+template <int NC, int C>
 __global__ void __launch_bounds__(kThreads)
-dqn_observe_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, uint8_t *__restrict__ features,
-                   uint8_t *__restrict__ legal, uint32_t *__restrict__ state_idx) {
-    __shared__ SmemTables sm;
+dqn_observe_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, const FastTabs *__restrict__ tabs,
+                   uint32_t rank_stride, uint8_t *__restrict__ features, uint8_t *__restrict__ legal,
+                   uint32_t *__restrict__ state_idx) {
+    __shared__ FeatLut lut;
     __shared__ uint4 stage[kThreads * 5];
-    load_tables(sm, cfg.tables);
-    const SharedTab tab{&sm};
+    build_feat_lut(lut);
+    __syncthreads();
+    const StepTabs<MDPP_MAX_CARS> &S = *reinterpret_cast<const StepTabs<MDPP_MAX_CARS> *>(tabs);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t warp_first = e - (threadIdx.x & 31);
     uint32_t keys[NC], pnode = 0, dnode = 0, lm = 0, sidx = 0xFFFFFFFFu;
@@ -495,17 +508,19 @@ dqn_observe_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, 
     if (e < n_envs) {
         uint4 rec = recs[e];
         uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
-        if (!f_done(car_field(cars, c))) {
-            const View v = view_of<NC>(cars, c, 1, cfg);
-            lm = legal_mask(v, v.pnode, tab);
-            sidx = state_index(v, v.pnode, cfg);
-            listed_others<NC>(cars, c, 2, cfg, keys);
-            pnode = v.pnode;
-            dnode = v.dnode;
+        if (!f_done(car_field(cars, C))) {
+            const FastView v = fast_view<NC, C>(S, tabs, cars, 1, rank_stride);
+            lm = v.lm;
+            sidx = v.sidx;
+            listed_others<NC>(v.cars, C, 2, cfg, keys);
+            pnode = v.f & 127u;
+            dnode = (v.own.x >> 10) & 127u;
             valid = true;
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
-            recs[e] = rec;
+            if (v.cars != cars) { // only a ghost counter can have moved: most records are not written back (16 B/env)
+                rec.x = (uint32_t)v.cars;
+                rec.y = (uint32_t)(v.cars >> 32);
+                recs[e] = rec;
+            }
         }
         if (legal) legal[e] = (uint8_t)lm;
         if (state_idx) state_idx[e] = sidx;
@@ -515,30 +530,31 @@ dqn_observe_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, int c, 
         for (int i = 0; i < NC; i++) keys[i] = 0xFFFFFFFFu;
     }
     if (warp_first < n_envs && features)
-        store_features_coalesced<NC>(features, warp_first, n_envs, stage + (threadIdx.x & ~31) * 5, valid, pnode, dnode, keys);
+        store_features_lut<NC>(lut, features, warp_first, n_envs, stage + (threadIdx.x & ~31) * 5, valid, pnode, dnode, keys);
 }
 
 // act: env.step(state, action, num) for the state the observe kernel produced (ghost counters are NOT
 // advanced again) -> convert(next_state), reward, give_mask(next_state), env-done flag; optional
 // end-of-round auto-reset with Philox headings when c is the last slot.
-template <int NC>
+template <int NC, int C>
 __global__ void __launch_bounds__(kThreads)
-dqn_act_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int c, int kind,
-               const uint8_t *__restrict__ actions, uint8_t *__restrict__ next_features, float *__restrict__ reward,
-               uint8_t *__restrict__ next_legal, uint8_t *__restrict__ done_out, uint8_t *__restrict__ status,
-               int auto_reset, uint64_t round, uint32_t seed, Control *ctl) {
-    __shared__ SmemTables sm;
-    __shared__ SmemStats ss;
+dqn_act_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t env_id_base, int kind,
+               const FastTabs *__restrict__ tabs, uint32_t rank_stride, const uint8_t *__restrict__ actions,
+               uint8_t *__restrict__ next_features, float *__restrict__ reward, uint8_t *__restrict__ next_legal,
+               uint8_t *__restrict__ done_out, uint8_t *__restrict__ status, int auto_reset, uint64_t round,
+               uint32_t seed, Control *ctl) {
+    __shared__ FeatLut lut;
+    __shared__ CtaCounters cc;
     __shared__ uint4 stage[kThreads * 5];
-    zero_stats(ss);
-    load_tables(sm, cfg.tables);
-    const SharedTab tab{&sm};
+    build_feat_lut(lut);
+    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
+    __syncthreads();
+    const StepTabs<MDPP_MAX_CARS> &S = *reinterpret_cast<const StepTabs<MDPP_MAX_CARS> *>(tabs);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t warp_first = e - (threadIdx.x & 31);
     uint32_t keys[NC], pnode = 0, dnode = 0;
     bool valid = false;
-    StatAcc acc;
-    int64_t rsum = 0;
+    StepCounts cnt;
     if (e < n_envs) {
         uint4 rec = recs[e];
         uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
@@ -546,34 +562,34 @@ dqn_act_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t en
         uint32_t st = 1, lm2 = 0;
         float rw = 0.f;
         const uint32_t a = actions[e];
-        if (!f_done(car_field(cars, c)) && a != MDPP_ACT_SKIP) {
-            uint64_t tmp = cars;
-            const View v = view_of<NC>(tmp, c, 2, cfg); // mode 2: counters as the observe kernel left them
-            const uint32_t lm = legal_mask(v, v.pnode, tab);
+        if (!f_done(car_field(cars, C)) && a != MDPP_ACT_SKIP) {
+            const FastView v = fast_view<NC, C>(S, tabs, cars, 2, rank_stride); // mode 2: counters as the observe kernel left them
             st = 2;
-            if (a < MDPP_N_ACT && ((lm >> a) & 1u)) {
+            if (a < MDPP_N_ACT && ((v.lm >> a) & 1u)) {
                 st = 0;
-                const uint32_t nn = next_node(v.pnode, a, tab);
-                const int32_t ri = reward_int<NC>(v, nn, cars, c, kind, cfg, tab);
+                const uint32_t mv = S.next[C][v.f & 0xFFu][a];
+                const int32_t ri = fast_reward<NC, C>(v, mv, cars, kind, cfg);
                 rw = reward_float(ri, kind);
-                lm2 = legal_mask(v, nn, tab);
-                listed_others<NC>(cars, c, 2, cfg, keys);
-                pnode = nn;
-                dnode = v.dnode;
+                dnode = (v.own.x >> 10) & 127u;
+                pnode = ((mv >> 9) & 1u) ? dnode : (mv & 127u); // the successor itself (a finished car is parked afterwards)
+                // give_mask(next_state): the successor STATE STRING keeps the others and the destination
+                lm2 = fast_legal(S.own[C][pnode | (v.f & 0x80u)], v.occ9, v.occ18);
+                listed_others<NC>(cars, C, 2, cfg, keys);
                 valid = true;
-                cars = advance_car(cars, c, v, nn, cfg);
+                const uint32_t nf = (mv & 0x1FFu) | (v.f & 0xE00u);
+                cars = (cars & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
                 steps = steps < 0xFFFFu ? steps + 1 : steps;
-                acc.steps = 1;
-                rsum = ri;
+                cnt.steps = 1;
+                cnt.reward = ri;
             }
         }
         const bool finished = all_done<NC>(cars);
         if (done_out) done_out[e] = (uint8_t)finished;
-        if (auto_reset && c == NC - 1) {
+        if (auto_reset && C == NC - 1) {
             const bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
             if (finished || capped) {
-                acc.episodes = 1;
-                acc.capped = capped;
+                cnt.episodes = 1;
+                cnt.capped = capped;
                 episode = (episode + 1) & 0xFFFFu;
                 steps = 0;
                 cars = initial_cars<NC>(cfg, heading_word(round, 2, seed, env_id_base + (uint32_t)e));
@@ -592,8 +608,8 @@ dqn_act_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t en
         for (int i = 0; i < NC; i++) keys[i] = 0xFFFFFFFFu;
     }
     if (warp_first < n_envs && next_features)
-        store_features_coalesced<NC>(next_features, warp_first, n_envs, stage + (threadIdx.x & ~31) * 5, valid, pnode, dnode, keys);
-    flush_stats<true, false>(acc, rsum, ctl, ss);
+        store_features_lut<NC>(lut, next_features, warp_first, n_envs, stage + (threadIdx.x & ~31) * 5, valid, pnode, dnode, keys);
+    flush_counts<false>(cnt, cc, MDPP_LEARN_FROZEN, ctl); // steps + reward_sum, no Q-updates
 }
 
 // ------------------------------------------------------------------------------------------------
