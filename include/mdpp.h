@@ -105,7 +105,7 @@ typedef struct {
     int64_t reward_sum;         /* sum of integer q_rewards (dqn: x100) */
     uint64_t explore_steps;
     uint64_t touched_keys;      /* distinct (state, action) keys finalised */
-    uint64_t reserved;
+    uint64_t internal_errors;   /* index guards tripped inside the kernels (a key or state id out of range): always 0 */
 } mdpp_stats;
 
 typedef struct mdpp_handle mdpp_handle;

@@ -575,6 +575,8 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     ea.q = q;
     ea.tabs = (const FastTabs *)(h->ws + h->cv.fast);
     ea.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ea.n_states = (uint32_t)h->cfg.n_states;
+    ea.ctl = control_of(h);
     ea.rng_words = (uint32_t *)(h->ws + h->cv.rng);
     ea.rng_mode = rng_mode;
     ea.forced = forced;
@@ -651,7 +653,7 @@ static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_le
         const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)mk.capacity + kThreads - 1) / kThreads,
                                                           (int64_t)h->sm_count * 8);
         LearnLaunch l1(h, grid, s);
-        MDPP_LAUNCH(h, cudaLaunchKernelEx(&l1.cfg, q_pull_list_compute_kernel, (const float *)qsrc, mk, lp->alpha, lp->discount));
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&l1.cfg, q_pull_list_compute_kernel, (const float *)qsrc, mk, lp->alpha, lp->discount, control_of(h)));
         h->chain = true;
         LearnLaunch l2(h, grid, s);
         MDPP_LAUNCH(h, cudaLaunchKernelEx(&l2.cfg, q_pull_list_apply_kernel, qsrc, mk, control_of(h)));
@@ -694,6 +696,7 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     ra.cta_slots = h->cv.cta_slots;
     ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.n_states = (uint32_t)h->cfg.n_states;
     const unsigned grid = round_ctas(h);
     ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / grid);
     ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
@@ -931,6 +934,7 @@ int mdpp_get_stats_host(mdpp_handle *h, mdpp_stats *out_host, int reset, void *s
         t.reward_sum += slots[i].reward_sum;
         t.explore_steps += slots[i].explore_steps;
         t.touched_keys += slots[i].touched_keys;
+        t.internal_errors += slots[i].internal_errors;
     }
     *out_host = t;
     return MDPP_OK;
@@ -957,6 +961,7 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     ra.cta_slots = h->cv.cta_slots;
     ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
     ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.n_states = (uint32_t)h->cfg.n_states;
     ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / round_ctas(h));
     ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % round_ctas(h));
     const size_t smem = round_smem_bytes(h->cfg.n_cars, ra.map_bytes, h->cfg.n_cars);

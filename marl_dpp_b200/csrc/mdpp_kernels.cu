@@ -26,6 +26,13 @@ struct Control {
     uint32_t max_episode[kStatSlots];
 };
 
+// Index guards: compute-sanitizer is closed on this GPU pool, so data-dependent indices that are not masked by
+// construction are range-checked before use.  The sub-step and list kernels skip the access and count the event
+// (mdpp_stats.internal_errors, asserted 0 by the tests, which drive the same tables and state encoding as the
+// fused kernels); the round kernel and the dense pull, where a counted guard measurably costs time, clamp
+// branch-free instead.
+__device__ __forceinline__ void guard_tripped(Control *ctl) { atomicAdd((unsigned long long *)&ctl->stats[0].internal_errors, 1ull); }
+
 struct StatAcc {
     uint32_t steps = 0, episodes = 0, capped = 0, explore = 0;
     int32_t reward = 0;

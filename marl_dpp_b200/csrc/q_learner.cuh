@@ -98,6 +98,8 @@ struct EnvArgs {
     const float *q;
     const FastTabs *tabs;
     uint32_t rank_stride; // n_dest_nodes * n_local_nodes
+    uint32_t n_states;    // rows of the Q table (index guard)
+    Control *ctl;
     uint32_t *rng_words;
     int rng_mode;
     const uint8_t *forced;
@@ -148,7 +150,12 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
         const FastView v = fast_view<NC, C>(S, ea.tabs, cars, mode, ea.rank_stride);
         const uint64_t before = cars; // the reward's clash term reads the cars before update_car
         cars = v.cars;                // the encode's ghost side effects stay whether or not the car moves
-        const uint32_t lm = v.lm, sidx = v.sidx;
+        uint32_t lm = v.lm;
+        const uint32_t sidx = v.sidx;
+        if (sidx >= ea.n_states) { // guard: the encoded state is off the table -- the car does not act
+            guard_tripped(ea.ctl);
+            lm = 0;
+        }
         s_out = sidx;
         uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
         const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
@@ -400,11 +407,14 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
 // pull side: the reference update of one key, from the snapshot table
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float td_value(const float *__restrict__ q, const uint32_t *__restrict__ sinfo, uint32_t s,
-                                          uint32_t i /* = sinfo[s] */, uint32_t a, float qa, float alpha, float discount) {
+                                          uint32_t i /* = sinfo[s] */, uint32_t a, float qa, float alpha, float discount,
+                                          uint32_t n_states) {
     const uint32_t nl = si_node(i);
     const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
     const uint32_t nnl = a == MDPP_A_F ? si_fwd(i) : ((nl & ~3u) | ((nl + rot) & 3u));
-    const uint32_t s2 = s - nl + nnl; // same others, same destination: only the node term moves
+    // same others, same destination: only the node term moves.  In range for every key an env can mark; clamped
+    // branch-free (a counted guard here cost the latency-bound pull 1 us per round)
+    const uint32_t s2 = min(s - nl + nnl, n_states - 1u);
     const uint32_t i2 = __ldg(sinfo + s2);
     float ns[MDPP_Q_ROW];
     ldg_row(q + (size_t)s2 * MDPP_Q_ROW, ns);
@@ -485,7 +495,7 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
     if (m < mk.n_marks) {
         float v = qold[key];
         if ((bits >> lane) & 1u) {
-            v = td_value(qold, mk.sinfo, s, info, a, v, alpha, discount);
+            v = td_value(qold, mk.sinfo, s, info, a, v, alpha, discount, mk.n_keys / MDPP_Q_ROW);
             mark_visited(mk.visited, key);
             touched = 1;
         }
@@ -500,14 +510,20 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
 
 // list mode, pass 1: new value of every listed key into vals[] (the table is read-only here)
 __global__ void __launch_bounds__(kThreads)
-q_pull_list_compute_kernel(const float *__restrict__ q, Marks mk, float alpha, float discount) {
+q_pull_list_compute_kernel(const float *__restrict__ q, Marks mk, float alpha, float discount, Control *ctl) {
     pdl_wait();
     pdl_launch_dependents();
     const uint32_t n = min(*mk.count, mk.capacity);
     if (blockIdx.x == 0 && threadIdx.x == 0) *mk.count_other = 0; // the next sub-step appends under the other parity
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t key = mk.list[i];
-        mk.vals[i] = td_value(q, mk.sinfo, key >> 3, __ldg(mk.sinfo + (key >> 3)), key & 7u, __ldg(q + key), alpha, discount);
+        if (key >= mk.n_keys) { // guard
+            guard_tripped(ctl);
+            mk.vals[i] = 0.f;
+            continue;
+        }
+        mk.vals[i] = td_value(q, mk.sinfo, key >> 3, __ldg(mk.sinfo + (key >> 3)), key & 7u, __ldg(q + key), alpha, discount,
+                              mk.n_keys / MDPP_Q_ROW);
     }
 }
 
@@ -519,6 +535,7 @@ q_pull_list_apply_kernel(float *__restrict__ q, Marks mk, Control *ctl) {
     const uint32_t n = min(*mk.count, mk.capacity);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t key = mk.list[i];
+        if (key >= mk.n_keys) continue; // guard (counted by the compute pass)
         q[key] = mk.vals[i];
         mk.bits[key >> 5] = 0;
         mark_visited(mk.visited, key);

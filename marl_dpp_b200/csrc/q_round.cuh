@@ -44,6 +44,7 @@ struct RoundArgs {
     uint32_t *defer_flags;       // [n_ctas] K0 writes, K1 reads: this CTA parked at least one lane
     uint32_t words_per_cta, cta_slots, map_bytes;
     uint32_t rank_stride;        // n_dest_nodes * n_local_nodes
+    uint32_t n_states;           // rows of the Q table (index clamp)
     uint32_t tiles_q, tiles_r;   // CTA b owns tiles [b * q + min(b, r), ... + q + (b < r)): no division on the device
 };
 
@@ -91,7 +92,9 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
         if constexpr (NC > 3) rank += (codes[3] + 2u) * (codes[3] + 1u) * codes[3] / 6u;
         if constexpr (NC > 4) rank += (codes[4] + 3u) * (codes[4] + 2u) * (codes[4] + 1u) * codes[4] / 24u;
     }
-    const uint32_t sidx = rank * ra.rank_stride + (own.x & 0x3FFu);
+    // in range by construction (codes and bases come from the tables); clamped all the same, branch-free: the mark
+    // below is a shared-memory store (a counted guard like the sub-step kernels' costs this kernel 0.3 us)
+    const uint32_t sidx = min(rank * ra.rank_stride + (own.x & 0x3FFu), ra.n_states - 1u);
     // ---- getlegalactions_filtered (:143-224) ----
     uint32_t lm = (own.x >> 24) & 31u;
     const uint32_t hit = (occ9 * 0x201u) & own.y;

@@ -162,10 +162,10 @@ class MdppLearner(C.Structure):
 class MdppStats(C.Structure):
     _fields_ = [("agent_steps", C.c_uint64), ("q_updates", C.c_uint64), ("episodes_done", C.c_uint64),
                 ("episodes_capped", C.c_uint64), ("reward_sum", C.c_int64), ("explore_steps", C.c_uint64),
-                ("touched_keys", C.c_uint64), ("reserved", C.c_uint64)]
+                ("touched_keys", C.c_uint64), ("internal_errors", C.c_uint64)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
 def _comb(n, k):

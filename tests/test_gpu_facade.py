@@ -161,6 +161,7 @@ def test_learner_flags_match_oracle(scratch):
     for s, a, v in [x for x in oq.items() if x[1] != "B"]:
         assert q[sc.encode(s), A5.index(a)] == np.float32(v)
     gs, ws = env.stats(), ob.stats()
+    assert gs["internal_errors"] == 0
     for k in ("agent_steps", "episodes_done", "episodes_capped", "explore_steps"):
         assert gs[k] == ws[k], k
     # frozen: same decisions, table untouched

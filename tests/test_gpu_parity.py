@@ -148,6 +148,7 @@ def test_random_rollout_matches_oracle(case, dqn):
         assert [int(x) for x in cars["ghost"][e]] == [_ghost_of(c[2], c[3]) for c in oc]
         assert (int(cars["episode"][e]), int(cars["steps"][e])) == ob.counters(e)
     gs, ws = env.stats(), ob.stats()
+    assert gs["internal_errors"] == 0
     for k in ("agent_steps", "episodes_done", "episodes_capped", "reward_sum"):
         assert gs[k] == ws[k], k
     assert gs["agent_steps"] == int((got["action"] != 0xFF).sum())
@@ -263,6 +264,7 @@ def test_batched_qlearning_matches_oracle(case):
         assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
     assert np.count_nonzero(q[:, :5]) == sum(1 for _, _, v in items if v != 0.0)
     gs, ws = env.stats(), ob.stats()
+    assert gs["internal_errors"] == 0
     for k in ("agent_steps", "episodes_done", "episodes_capped", "reward_sum", "explore_steps"):
         assert gs[k] == ws[k], k
     assert gs["q_updates"] == gs["agent_steps"]
@@ -330,6 +332,7 @@ def test_train_rounds_fused_path_matches_oracle(case):
         assert [int(x) for x in cars["ghost"][e]] == [_ghost_of(c[2], c[3]) for c in oc]
         assert (int(cars["episode"][e]), int(cars["steps"][e])) == ob.counters(e)
     gs, ws = env.stats(), ob.stats()
+    assert gs["internal_errors"] == 0
     for k in ("agent_steps", "episodes_done", "episodes_capped", "explore_steps"):
         assert gs[k] == ws[k], k
     assert gs["q_updates"] == gs["agent_steps"]
@@ -406,7 +409,7 @@ def test_full_size_properties():
         lr = BatchedQLearner(env, episodes=1000, seed=9)
         lr.train_rounds(24)
         st = env.stats()
-        assert st["q_updates"] == st["agent_steps"] > 0
+        assert st["q_updates"] == st["agent_steps"] > 0 and st["internal_errors"] == 0
         tables.append(lr.q.clone())
     assert torch.equal(tables[0], tables[1])
     assert torch.isfinite(tables[0]).all()
