@@ -95,6 +95,14 @@ typedef struct {
 #define MDPP_LEARN_DETECT 4u /* stall heuristic of detect_deadlocks_v0 (qlearning.py:347-360) */
 #define MDPP_LEARN_OBSERVED 8u /* the state was already encoded for this agent-step (mdpp_step_car peek or
                                   mdpp_dqn_observe): do not advance the ghost counters a second time */
+#define MDPP_LEARN_RANDOM_ORDER 16u /* train_given_state_random_order (qlearning.py:241-295): in every sub-step each
+                                  env draws the car that acts (random.randint, :267; a finished car = no agent-step,
+                                  :268-269) and the episode may end after any agent-step (:291).  `car` of
+                                  mdpp_q_substep is then the index of the sub-step within the round (a round is
+                                  n_cars sub-steps; Philox stream 4 + index: word 0 car, word 1 decision, word 2
+                                  headings of the next episode).  The forced byte carries the car in its high
+                                  nibble (0xF = own draw) and the action in the low one (0..4, 0xE greedy, 0xF own
+                                  decision), so MDPP_ACT_SKIP / MDPP_ACT_GREEDY keep their meaning. */
 
 /* counters accumulated on the device, fetched with mdpp_get_stats_host */
 typedef struct {

@@ -16,7 +16,8 @@ from ..batched import BatchedEnv, BatchedQLearner
 from ..configuration import Configuration
 import random
 
-from ..tables import ACTIONS5, HEADS, LEARN_DETECT, LEARN_FROZEN, LEARN_MODE0, LEARN_OBSERVED, Scenario, epsilon_schedule
+from ..tables import (ACTIONS5, HEADS, LEARN_DETECT, LEARN_FROZEN, LEARN_MODE0, LEARN_OBSERVED, LEARN_RANDOM_ORDER,
+                      Scenario, epsilon_schedule)
 
 
 class RL:
@@ -215,6 +216,96 @@ class RL:
         self.last_stats = learner.env.stats()
         self.save_qvalues(outputfile_number)
         self._pull()
+
+    # ---- training, random car order (reference :241-295) ---------------------------------------------
+    def _train_random_order_reference_rng(self, episodes, outputfile_number, boxes, n, idx, choose):
+        """The reference's loop (qlearning.py:245-293) on the host, one env: random.randint picks the car
+        (a finished car consumes the draw and nothing else), then the decisions of getaction in the
+        reference's order; env step, greedy argmax and TD update on the GPU.  Returns (learner, ok): ok is
+        False when an episode ran past 10 000 actions (the reference's `return 0`, :274-277)."""
+        learner = self._make(episodes, boxes, n, idx, choose, flags=LEARN_OBSERVED | LEARN_RANDOM_ORDER)
+        env = learner.env
+        th, eps_values = epsilon_schedule(episodes, self.probability_model)
+        peek = torch.tensor([0xFE], dtype=torch.uint8)
+        self.trace = []
+        for episode in range(episodes):
+            if episode == 30:
+                self.save_qvalues(outputfile_number)
+            self.epsilon = next((v for t, v in zip(th, eps_values) if episode < t), eps_values[5])
+            heads = []
+            for num in range(n):
+                nodes = list("NESW")
+                random.shuffle(nodes)
+                heads.append(HEADS.index(nodes[0]))
+            env.reset(headings=torch.tensor([heads], dtype=torch.uint8), zero_counters=False)
+            done = [False] * n
+            actions = 0
+            ep0 = int(env.cars()["episode"][0])
+            while True:
+                num = random.randint(0, n - 1)
+                if done[num]:
+                    continue
+                o = env.step_car(num, peek)              # encodestate(num, 1) + getlegalactions
+                legal = int(o["legal"][0])
+                legal_actions = [a for a in range(5) if (legal >> a) & 1]
+                low = 0xF
+                if legal_actions:
+                    if random.random() < self.epsilon:
+                        low = random.choice(legal_actions)
+                    else:
+                        low = 0xE
+                actions += 1
+                if actions > 10000:
+                    return learner, False
+                out = learner.substep(0, forced=torch.tensor([(num << 4) | low], dtype=torch.uint8), outputs=True)
+                learner.finalize()
+                learner.round += 1
+                self.trace.append((num, int(out["state"][0]), int(out["action"][0])))
+                cars = env.cars()
+                if int(cars["episode"][0]) != ep0:       # every car finished: the launch started the next episode
+                    break
+                done = [bool(x) for x in cars["done"][0].tolist()]
+        return learner, True
+
+    def train_given_state_random_order(self, episodes, inputfile_number, outputfile_number, input_car_states=None,
+                                       no_of_cars=1, destination_index_array=[0, 0, 0, 0],
+                                       destination_choose_arrays=[0, 0, 0]):
+        """Like train_given_state, but every agent-step is taken by a randomly drawn car and an episode
+        that runs past 10 000 actions aborts the training with 0 (a state without a path, :274-277).
+        Batched (n_envs > 1): every env draws its own car in every sub-step (MDPP_LEARN_RANDOM_ORDER); the
+        cap is the learner's step_cap, and the call returns 0 after the run if any episode hit it."""
+        self.load_qvalues(inputfile_number)
+        if self.reference_rng:
+            learner, ok = self._train_random_order_reference_rng(episodes, outputfile_number, input_car_states,
+                                                                 no_of_cars, destination_index_array,
+                                                                 destination_choose_arrays)
+            self.last_stats = learner.env.stats()
+            self._pull()
+            if not ok:
+                print('\nSkipping! The state cannot be trained as it has no paths possible.')
+                return 0
+            self.save_qvalues(outputfile_number)
+            return
+        cap = self.step_cap
+        self.step_cap = 10000 if cap == 0 else min(cap, 10000)  # this variant always has the cap (:274)
+        try:
+            learner = self._make(episodes, input_car_states, no_of_cars, destination_index_array,
+                                 destination_choose_arrays, flags=LEARN_RANDOM_ORDER)
+        finally:
+            self.step_cap = cap
+        saved = []
+
+        def snapshot(min_episode):
+            if not saved and min_episode >= 30:
+                saved.append(True)
+                self.save_qvalues(outputfile_number)
+        self._run(learner, episodes, on_episode=snapshot)
+        self.last_stats = learner.env.stats()
+        self._pull()
+        if self.last_stats["episodes_capped"]:
+            print('\nSkipping! The state cannot be trained as it has no paths possible.')
+            return 0
+        self.save_qvalues(outputfile_number)
 
     # ---- deadlock detection (reference :297-382) -----------------------------------------------------
     def detect_deadlocks_v0(self, episodes=40, inputfile_number=0, outputfile_number=0, input_car_states=None,

@@ -557,7 +557,10 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
                         cudaStream_t s) {
     // Philox hand-over: the car-0 launch of a round publishes the decision words of cars 1..3
     int rng_mode = 0;
-    if (h->cfg.n_cars > 1) {
+    const uint32_t order_slot = (uint32_t)car_slot;
+    if (lp->flags & MDPP_LEARN_RANDOM_ORDER) {
+        car_slot = 0; // every env draws its own car: the slot-0 kernels carry that dispatch
+    } else if (h->cfg.n_cars > 1) {
         if (car_slot == 0) {
             rng_mode = 1;
             h->rng_round = round;
@@ -579,6 +582,7 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     ea.ctl = control_of(h);
     ea.rng_words = (uint32_t *)(h->ws + h->cv.rng);
     ea.rng_mode = rng_mode;
+    ea.order_slot = order_slot;
     ea.forced = forced;
     ea.action_out = action_out;
     ea.state_out = state_idx;

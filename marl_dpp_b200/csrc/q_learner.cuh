@@ -102,6 +102,7 @@ struct EnvArgs {
     Control *ctl;
     uint32_t *rng_words;
     int rng_mode;
+    uint32_t order_slot;  // MDPP_LEARN_RANDOM_ORDER: index of the sub-step within the round
     const uint8_t *forced;
     uint8_t *action_out;
     uint32_t *state_out;
@@ -117,9 +118,12 @@ struct StepCounts {
 
 // One agent-step of car C in env e (record `rec` already loaded).  Returns true and sets `key` when the env
 // updated a key; the caller owns the marking.  Writes the record back and the optional outputs.
-template <int NC, int C, bool PLAIN, class Tabs>
-__device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, const LearnArgs &lp,
-                                            const EnvArgs &ea, int64_t e, uint4 rec, uint32_t &key, StepCounts &cnt) {
+// ANY: random car order (MDPP_LEARN_RANDOM_ORDER) -- C is the car this env drew, the forced byte, the decision
+// word and the heading word of a reset come from the caller, and the episode may end after any agent-step.
+template <int NC, int C, bool PLAIN, bool ANY, class Tabs>
+__device__ __forceinline__ bool env_substep_car(const Tabs &S, const DevCfg &cfg, const LearnArgs &lp,
+                                                const EnvArgs &ea, int64_t e, uint4 rec, uint32_t &key, StepCounts &cnt,
+                                                uint32_t any_forced, uint32_t any_word, uint32_t any_heading) {
     const uint32_t lflags = PLAIN ? 0u : lp.flags;
     const uint8_t *forced = PLAIN ? nullptr : ea.forced;
     uint8_t *action_out = PLAIN ? nullptr : ea.action_out;
@@ -135,7 +139,9 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
     // detect_deadlocks_v0 encodes with deadlock_id 0 (qlearning.py:342), training with 1 (:218)
     const int mode = (lflags & MDPP_LEARN_MODE0) ? 0 : (lflags & MDPP_LEARN_OBSERVED) ? 2 : 1;
     uint32_t word = 0;
-    if (C == 0 && ea.rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
+    if (ANY) {
+        word = any_word;
+    } else if (C == 0 && ea.rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
         if (live) {
             const uint4 p = philox4x32_10((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 0, 0, lp.seed, env);
             word = p.x;
@@ -157,7 +163,7 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
             lm = 0;
         }
         s_out = sidx;
-        uint32_t f = forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
+        uint32_t f = ANY ? any_forced : forced ? forced[e] : (uint32_t)MDPP_ACT_SKIP;
         const bool forced_ok = f >= MDPP_ACT_GREEDY || (f < MDPP_N_ACT && ((lm >> f) & 1u));
         if (lm && forced_ok) {
             // ---- getaction (reference src/algorithms/qlearning.py:74-105) ----
@@ -173,7 +179,7 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
                 a = f;
                 explore = true;
             } else {
-                const uint32_t w = ea.rng_mode ? word : decision_word(ea.round, C, lp.seed, env);
+                const uint32_t w = (ANY || ea.rng_mode) ? word : decision_word(ea.round, C, lp.seed, env);
                 explore = (w >> 16) < eps16; // flipcoin (utils.py:255-265)
                 // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
                 a = (S.nth[lm] >> (3u * (((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
@@ -225,7 +231,7 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
             a_out = a;
         }
     }
-    if (live && C == NC - 1) { // end of the round-robin round (qlearning.py:233)
+    if (live && (ANY || C == NC - 1)) { // end of the round-robin round (qlearning.py:233); any order: :291
         bool finished = all_done<NC>(cars);
         bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
         if (finished || capped) {
@@ -235,7 +241,7 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
             cnt.max_episode = max(cnt.max_episode, episode);
             steps = 0;
             rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
-            cars = initial_cars<NC>(cfg, heading_word(ea.round, 2, lp.seed, env));
+            cars = initial_cars<NC>(cfg, ANY ? any_heading : heading_word(ea.round, 2, lp.seed, env));
         }
     }
     if (live) {
@@ -248,6 +254,35 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
     if (state_out) state_out[e] = s_out;
     if (reward_out) reward_out[e] = r_out;
     return touched;
+}
+
+// The sub-step of car slot C -- or, under MDPP_LEARN_RANDOM_ORDER (train_given_state_random_order,
+// qlearning.py:241-295; the host always launches slot 0 then), of the car each env draws for itself:
+// random.randint(0, n - 1) (:267) = the high half of word 0 of the Philox block (round, stream 4 + order_slot)
+// scaled to n_cars; a finished car means no agent-step (:268-269); word 1 is the decision word, word 2 the
+// headings of the next episode.  The forced byte then carries the car in its high nibble (0xF = own draw) and
+// the action in the low one (0..4, 0xE greedy, 0xF own decision): 0xFF / 0xFE keep their meaning.
+template <int NC, int C, bool PLAIN, class Tabs>
+__device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, const LearnArgs &lp,
+                                            const EnvArgs &ea, int64_t e, uint4 rec, uint32_t &key, StepCounts &cnt) {
+    if constexpr (!PLAIN && C == 0) {
+        if (lp.flags & MDPP_LEARN_RANDOM_ORDER) {
+            const uint4 p = philox4x32_10((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 4u + ea.order_slot, 0, lp.seed,
+                                          ea.env_id_base + (uint32_t)e);
+            uint32_t f = ea.forced ? ea.forced[e] : 0xFFu;
+            uint32_t c = ((p.x >> 16) * (uint32_t)NC) >> 16;
+            if ((f >> 4) != 0xFu) c = min(f >> 4, (uint32_t)NC - 1u);
+            f = (f & 0xFu) == 0xFu ? (uint32_t)MDPP_ACT_SKIP : (f & 0xFu) == 0xEu ? (uint32_t)MDPP_ACT_GREEDY : (f & 0xFu);
+            switch (c) {
+            case 0: return env_substep_car<NC, 0, false, true>(S, cfg, lp, ea, e, rec, key, cnt, f, p.y, p.z);
+            case 1: return env_substep_car<NC, (NC > 1 ? 1 : 0), false, true>(S, cfg, lp, ea, e, rec, key, cnt, f, p.y, p.z);
+            case 2: return env_substep_car<NC, (NC > 2 ? 2 : 0), false, true>(S, cfg, lp, ea, e, rec, key, cnt, f, p.y, p.z);
+            case 3: return env_substep_car<NC, (NC > 3 ? 3 : 0), false, true>(S, cfg, lp, ea, e, rec, key, cnt, f, p.y, p.z);
+            default: return env_substep_car<NC, (NC > 4 ? 4 : 0), false, true>(S, cfg, lp, ea, e, rec, key, cnt, f, p.y, p.z);
+            }
+        }
+    }
+    return env_substep_car<NC, C, PLAIN, false>(S, cfg, lp, ea, e, rec, key, cnt, 0u, 0u, 0u);
 }
 
 // counters of a CTA: warp REDUX -> one shared-memory atomic per warp -> one thread adds the CTA's totals to a

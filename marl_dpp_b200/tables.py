@@ -345,7 +345,7 @@ def epsilon_schedule(episodes, model=3):
     raise ValueError("unknown probability model %r" % (model,))
 
 
-LEARN_FROZEN, LEARN_MODE0, LEARN_DETECT, LEARN_OBSERVED = 1, 2, 4, 8
+LEARN_FROZEN, LEARN_MODE0, LEARN_DETECT, LEARN_OBSERVED, LEARN_RANDOM_ORDER = 1, 2, 4, 8, 16
 
 
 def learner_params(episodes, alpha=0.9, discount=0.15, model=3, seed=3, flags=0):

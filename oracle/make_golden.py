@@ -15,6 +15,8 @@ What is recorded (all produced by reference code, none by this repo's implementa
   qrun_*.json.gz          RL.train_given_state / detect-style runs with the coin / choice /
                           heading decisions recorded and the final Counter (insertion order kept)
                           (reference src/algorithms/qlearning.py:74-116,187-239)
+  qrand_*.json.gz         RL.train_given_state_random_order runs, the drawn car recorded as well
+                          (reference src/algorithms/qlearning.py:241-295)
   known_answers.json.gz   the SURVEY 8c known-answer probes re-derived live.
 """
 import gzip
@@ -194,6 +196,85 @@ def gen_qrun(ref, name, block, boxes, idx, choose, bad, episodes, max_steps, see
         "alpha": 0.9, "discount": 0.15, "log": log["episodes"], "qvals": qv})
 
 
+def gen_qrand(ref, name, block, boxes, idx, choose, bad, episodes, max_steps, seed):
+    """Real RL.train_given_state_random_order (reference src/algorithms/qlearning.py:241-295) with every
+    random decision recorded: the car drawn by random.randint before each agent-step (draws that hit a
+    finished car are logged too -- they consume the stream and nothing else), coin, choice, headings."""
+    rl, env = ref.make_rl(block, bad_states=bad)
+    Q = ref.qlearning
+    random.seed(seed)
+    log = {"episodes": []}
+    cur = {}
+    state = {"n": 0}
+    real_flip = ref.utils.flipcoin
+    real_choice = random.choice
+    real_randint = random.randint
+    real_init = env.initialize
+    real_update = rl.update
+
+    def flip(p):
+        r = real_flip(p)
+        cur["pending_coin"] = bool(r)
+        return r
+
+    class RandomProxy:
+        def __getattr__(self, k):
+            return getattr(random, k)
+
+        @staticmethod
+        def choice(seq):
+            c = real_choice(seq)
+            cur["pending_choice"] = c
+            return c
+
+        @staticmethod
+        def randint(a, b):
+            c = real_randint(a, b)
+            cur["ep"]["draws"].append(c)
+            cur["pending_car"] = c
+            return c
+
+    def init(a, b, c):
+        real_init(a, b, c)
+        cur.clear()
+        ep = {"headings": list(env.given_nodes), "eps": rl.epsilon, "steps": [], "draws": []}
+        log["episodes"].append(ep)
+        cur["ep"] = ep
+
+    def update(s, a, ns, r):
+        real_update(s, a, ns, r)
+        coin = cur.pop("pending_coin")
+        ch = cur.pop("pending_choice", None)
+        # [car, state, explore?, action, next_state, reward, Q(s,a) after update]
+        cur["ep"]["steps"].append([cur["pending_car"], s, int(coin), a, ns, r, repr(rl.qvals[(s, a)])])
+        if coin:
+            assert ch == a
+        state["n"] += 1
+        if state["n"] >= max_steps:
+            raise _Abort()
+
+    Q.flipcoin = flip
+    Q.random = RandomProxy()
+    env.initialize = init
+    rl.update = update
+    aborted = False
+    result = None
+    try:
+        with ref_harness.quiet():
+            result = rl.train_given_state_random_order(episodes, "0", "0", boxes, len(boxes), idx, choose)
+    except _Abort:
+        aborted = True
+    finally:
+        Q.flipcoin = real_flip
+        Q.random = random
+        env.initialize = real_init
+    qv = [[s, a, repr(v)] for (s, a), v in rl.qvals.items()]
+    dump("qrand_" + name, {
+        "block": block, "boxes": boxes, "idx": idx, "choose": choose, "bad_states": bool(bad),
+        "episodes_total": episodes, "aborted": aborted, "n_steps": state["n"], "seed": seed, "result": result,
+        "alpha": 0.9, "discount": 0.15, "log": log["episodes"], "qvals": qv})
+
+
 # ------------------------------------------------------------------------------------------
 def gen_known_answers(ref):
     out = {}
@@ -276,8 +357,18 @@ def gen_convert(ref):
     dump("dqn_convert", out)
 
 
+def gen_all_qrand(ref):
+    R = gen_qrand
+    R(ref, "b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 60, 40000, 6)
+    R(ref, "b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 40, 30000, 7)
+
+
 def main():
     ref = ref_harness.load()
+    if "--only-qrand" in sys.argv:  # the other fixtures are unchanged
+        gen_all_qrand(ref)
+        ref.close()
+        return
     for b in (0, 2):
         dump("tables_b%d" % b, gen_tables(ref, b))
     gen_known_answers(ref)
@@ -304,6 +395,7 @@ def main():
     G(ref, "b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 60, 40000, 3)
     G(ref, "b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 60, 40000, 4)
     G(ref, "b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 40, 30000, 5)
+    gen_all_qrand(ref)
     gen_convert(ref)
     ref.close()
 

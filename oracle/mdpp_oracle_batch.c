@@ -144,7 +144,7 @@ static int nth_set_bit(int mask, int n) {
 /* 6-action oracle mask -> 5-bit S,L,R,F,T mask of the ABI */
 static int mask5(int m6) { return (m6 & 0xF) | (((m6 >> 5) & 1) << 4); }
 
-static void end_of_round(orc_batch *b, int64_t e, uint64_t round, uint32_t seed, uint64_t *episodes, uint64_t *capped) {
+static void end_of_episode_check(orc_batch *b, int64_t e, uint32_t heading_word, uint64_t *episodes, uint64_t *capped) {
     int finished = orc_env_is_game_ended(b->envs[e]);
     int cap = !finished && b->step_cap > 0 && b->steps[e] >= b->step_cap;
     if (finished || cap) {
@@ -153,8 +153,12 @@ static void end_of_round(orc_batch *b, int64_t e, uint64_t round, uint32_t seed,
         b->episode[e] += 1;
         b->steps[e] = 0;
         b->stall[e] = 0; /* deadlock_count = 0 per episode, qlearning.py:331 */
-        init_env(b, e, philox_word(round, 2, seed, b->env_id_base + (uint32_t)e, 0));
+        init_env(b, e, heading_word);
     }
+}
+static void end_of_round(orc_batch *b, int64_t e, uint64_t round, uint32_t seed, uint64_t *episodes, uint64_t *capped) {
+    /* the heading word is only drawn when it is used; it is a pure function of (round, env) */
+    end_of_episode_check(b, e, philox_word(round, 2, seed, b->env_id_base + (uint32_t)e, 0), episodes, capped);
 }
 
 /* ---- random-policy rollout (the reference's epsilon = 1 behaviour, qlearning.py:99-102) -------- */
@@ -254,7 +258,7 @@ typedef struct {
     int32_t eps_threshold[5];
     uint32_t eps_q16[6];
     uint32_t seed;
-    uint32_t flags; /* 1 frozen (no update), 2 encodestate(.,0), 4 stall detection */
+    uint32_t flags; /* 1 frozen (no update), 2 encodestate(.,0), 4 stall detection, 16 random car order */
 } orc_learner;
 
 static uint32_t eps_q16_of(const orc_learner *lp, int32_t episode) {
@@ -270,10 +274,19 @@ typedef struct {
 } pending;
 
 /* One sub-step for car slot c.  q must have been created with f32 = 1.  forced: NULL or [n_envs]
- * (ACT_SKIP = own decision, else take that action as exploration).  Outputs optional. */
-void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, uint64_t round, const uint8_t *forced,
+ * (ACT_SKIP = own decision, else take that action as exploration).  Outputs optional.
+ *
+ * flags & 16: random car order (train_given_state_random_order, qlearning.py:241-295).  `slot` is then only the
+ * index of the sub-step within the round (a round is n_cars sub-steps): every env draws its own car --
+ * random.randint(0, n - 1) (:267) = the high half of word 0 of the Philox block (round, stream 4 + slot) scaled to
+ * n_cars; a finished car means no agent-step (:268-269); the decision word is word 1 of that block; the end of the
+ * episode is checked after every agent-step (:291), the headings of the next one come from word 2.  forced then
+ * carries the car in its high nibble (0xF = the env's own draw) and the action in the low one (0..4, 0xE greedy,
+ * 0xF own decision), so 0xFF / 0xFE keep their meaning. */
+void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot, uint64_t round, const uint8_t *forced,
                          uint8_t *action_out, orc_state *state_out, float *reward_out) {
     const int nc = b->n_cars;
+    const int any_order = (lp->flags & 16u) != 0;
     pending *pend = (pending *)malloc(sizeof(pending) * (size_t)b->n_envs);
     /* phase 1: every env decides and steps against the Q table as it stands (no writes yet) */
     for (int64_t e = 0; e < b->n_envs; e++) {
@@ -286,10 +299,19 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
         memset(&st, 0, sizeof st);
         st.pnode = ORC_NONE;
         int live = b->episode[e] < lp->episodes;
+        int c = slot, f = forced ? forced[e] : ACT_SKIP;
+        uint32_t blk[4] = {0, 0, 0, 0};
+        if (any_order) {
+            uint32_t ctr[4] = {(uint32_t)round, (uint32_t)(round >> 32), 4u + (uint32_t)slot, 0}, key[2] = {lp->seed, envid};
+            orc_philox4x32_10(ctr, key, blk);
+            c = (int)(((blk[0] >> 16) * (uint32_t)nc) >> 16);
+            if ((f >> 4) != 0xF) c = f >> 4;
+            f = (f & 0xF) == 0xF ? ACT_SKIP : (f & 0xF) == 0xE ? ACT_GREEDY : (f & 0xF);
+            if (c >= nc) c = nc - 1;
+        }
         if (live && !orc_env_car_done(env, c)) {
             orc_env_encodestate(env, c, (lp->flags & 2u) ? 0 : 1, &st);
             int lm = mask5(orc_env_legal(env, &st));
-            int f = forced ? forced[e] : ACT_SKIP;
             int forced_ok = f >= ACT_GREEDY || (f < 5 && ((lm >> f) & 1));
             if (lm && forced_ok) {
                 int a5, explore;
@@ -300,7 +322,7 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
                     a5 = f;
                     explore = 1;
                 } else {
-                    uint32_t w = decision_word(round, c, lp->seed, envid);
+                    uint32_t w = any_order ? blk[1] : decision_word(round, c, lp->seed, envid);
                     explore = (w >> 16) < eps_q16_of(lp, b->episode[e]);
                     a5 = nth_set_bit(lm, (int)(((w & 0xFFFFu) * (uint32_t)__builtin_popcount((unsigned)lm)) >> 16));
                 }
@@ -355,7 +377,8 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int c, u
             }
         }
         live = b->episode[e] < lp->episodes || live;
-        if (live && c == nc - 1) end_of_round(b, e, round, lp->seed, &b->episodes_done, &b->episodes_capped);
+        if (live && any_order) end_of_episode_check(b, e, blk[2], &b->episodes_done, &b->episodes_capped);
+        else if (live && c == nc - 1) end_of_round(b, e, round, lp->seed, &b->episodes_done, &b->episodes_capped);
         if (action_out) action_out[e] = (uint8_t)a_out;
         if (state_out) state_out[e] = st;
         if (reward_out) reward_out[e] = r_out;

@@ -211,3 +211,50 @@ def test_rl_plugin_reproduces_reference_run_from_the_same_seed(scratch, name):
     assert set(rl.qvals) == updated
     for k, v in rl.qvals.items():
         assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
+
+
+@pytest.mark.parametrize("name", ["qrand_b2_2car", "qrand_b2_3car_bad"])
+def test_rl_plugin_reproduces_reference_random_order_run(scratch, name):
+    """train_given_state_random_order seeded like the reference's recorded run (one env, reference_rng): the
+    same cars are drawn, the same (state, action) sequence is visited and the same table is learnt (float32
+    vs float64: <= 1e-5 relative)."""
+    import random
+    import marl_dpp_b200 as m
+    from marl_dpp_b200 import settings
+    from marl_dpp_b200.algorithms.qlearning import RL
+    g = load_golden(name)
+    bad_file = scratch / "data" / "bad_states_files" / "layout-3" / "down_right.txt"
+    if not g["bad_states"]:
+        os.remove(bad_file)
+    rl = RL(**settings.params, sess=None, env_config=m.layout_3[g["block"]], n_envs=1, step_cap=0, reference_rng=True)
+    random.seed(g["seed"])
+    res = rl.train_given_state_random_order(g["episodes_total"], '0', '0', g["boxes"], len(g["boxes"]), g["idx"],
+                                            g["choose"])
+    assert res is None and g["result"] is None
+    sc = rl.learner.env.scenario
+    want_trace = [(s[0], s[1], s[3]) for ep in g["log"] for s in ep["steps"]]
+    got_trace = [(c, sc.decode(s), A5[a]) for c, s, a in rl.trace]
+    assert got_trace == want_trace
+    want = {(s, a): float(v) for s, a, v in g["qvals"]}
+    assert set(rl.qvals) == {(s, a) for _, s, a in want_trace}
+    for k, v in rl.qvals.items():
+        assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
+
+
+def test_rl_plugin_random_order_batched(scratch):
+    """The batched form: 256 envs, every env draws its own car; the run ends with every env through its
+    episode budget, a table over the same states as the reference's run, and the file written."""
+    import marl_dpp_b200 as m
+    from marl_dpp_b200 import settings, formats
+    from marl_dpp_b200.algorithms.qlearning import RL
+    g = load_golden("qrand_b2_2car")
+    os.remove(scratch / "data" / "bad_states_files" / "layout-3" / "down_right.txt")
+    rl = RL(**settings.params, sess=None, env_config=m.layout_3[2], n_envs=256)
+    res = rl.train_given_state_random_order(40, '0', '7', g["boxes"], 2, g["idx"], g["choose"])
+    st = rl.last_stats
+    assert st["episodes_done"] >= 256 * 40 and st["internal_errors"] == 0
+    assert res is None and st["episodes_capped"] == 0
+    ref_states = {s for s, a, v in g["qvals"]}
+    got_states = {s for (s, a) in rl.qvals}
+    assert len(ref_states & got_states) > 0.6 * len(ref_states)
+    assert os.path.exists(formats.qvalue_path('7', rl.qvalue_dir))

@@ -215,6 +215,11 @@ def test_reference_qlearning_runs(name):
     assert {(s, a) for s, a, _ in lr.qvalue_items()} == updated
 
 
+def torch_u8(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8))
+
+
 QBATCH = [
     ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 400, 512, 40, 300),
     ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 0, 256, 30, 200),
@@ -278,6 +283,79 @@ def test_batched_qlearning_matches_oracle(case):
     q = lr.q.cpu().numpy()
     for s, a, v in [x for x in oq.items() if x[1] != "B"]:
         assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
+
+
+RANDOM_ORDER = [
+    ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 400, 512, 40, 300),
+    ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 0, 256, 30, 120),
+    ("b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 300, 384, 30, 150),
+    ("b2_4car_bad_list", 2, ["D2", "D6", "D4", "D8"], [0, 0, 0, 0], [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]],
+     True, 300, 320, 20, 60),
+]
+
+
+@pytest.mark.parametrize("case", RANDOM_ORDER, ids=[c[0] for c in RANDOM_ORDER])
+def test_batched_random_order_matches_oracle(case):
+    """MDPP_LEARN_RANDOM_ORDER (train_given_state_random_order, qlearning.py:241-295): every env draws the
+    car that acts, a finished car means no agent-step, the episode may end after any agent-step.  Per
+    sub-step the encoded state, action and reward of every env, then the table and the counters, are
+    bit-identical to the oracle's restatement; every third round the car and/or the action are forced
+    through the high / low nibble of the forced byte."""
+    m, BatchedEnv, BatchedQLearner, orc = _mods()
+    from marl_dpp_b200.tables import LEARN_RANDOM_ORDER
+    name, block, boxes, idx, choose, bad, cap, n, episodes, rounds = case
+    badtxt = bad_states_text(block) if bad else None
+    sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
+    env = BatchedEnv(sc, n, seed=9)
+    lr = BatchedQLearner(env, episodes=episodes, seed=9, flags=LEARN_RANDOM_ORDER)
+    ob = orc.Batch(orc.Config(m.layout_3[block]), n, boxes, idx, choose, badtxt, cap)
+    ob.reset(seed=9)
+    oq = orc.QTable(f32=True)
+    olp = orc.learner(episodes, seed=9, flags=LEARN_RANDOM_ORDER)
+    nc = len(boxes)
+    rng = np.random.default_rng(1)
+    cars_seen = set()
+    for r in range(rounds):
+        for c in range(nc):
+            forced = None
+            if r % 3 == 2:  # high nibble: car or 0xF = own draw; low nibble: action, 0xE greedy, 0xF own decision
+                hi = rng.choice(np.array(list(range(nc)) + [0xF, 0xF], dtype=np.uint8), size=n)
+                lo = rng.choice(np.array([0, 1, 2, 3, 4, 0xE, 0xF, 0xF], dtype=np.uint8), size=n)
+                forced = ((hi.astype(np.uint8) << 4) | lo).astype(np.uint8)
+            out = lr.substep(c, forced=None if forced is None else torch_u8(forced), outputs=True)
+            lr.finalize()
+            want = ob.q_substep(oq, olp, c, r, forced=forced)
+            assert np.array_equal(out["action"].cpu().numpy(), want["action"]), (r, c)
+            assert np.array_equal(out["reward"].cpu().numpy(), want["reward"]), (r, c)
+            got_state = out["state"].cpu().numpy()
+            for e in range(0, n, 37):
+                if want["action"][e] != 0xFF:
+                    st = orc.state_str(want["state"][e])
+                    assert got_state[e] == sc.encode(st), (r, c, e)
+                    cars_seen.add(st.split("x")[1].split("z")[0])
+        lr.round += 1
+    if nc > 1:
+        assert len(cars_seen) > 1  # different cars (different destinations) took agent-steps
+    q = lr.q.cpu().numpy()
+    items = [x for x in oq.items() if x[1] != "B"]
+    for s, a, v in items:
+        assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
+    assert np.count_nonzero(q[:, :5]) == sum(1 for _, _, v in items if v != 0.0)
+    gs, ws = env.stats(), ob.stats()
+    assert gs["internal_errors"] == 0
+    for k in ("agent_steps", "episodes_done", "episodes_capped", "reward_sum", "explore_steps"):
+        assert gs[k] == ws[k], k
+    assert gs["episodes_done"] > 0
+    assert ob.disagreements() == 0
+    assert gs["touched_keys"] == ob.touched_keys()
+    # the multi-round entry point continues identically (n_cars sub-steps per round)
+    lr.train_rounds(5)
+    for r in range(rounds, rounds + 5):
+        ob.q_round(oq, olp, r)
+    q = lr.q.cpu().numpy()
+    for s, a, v in [x for x in oq.items() if x[1] != "B"]:
+        assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
+    assert env.stats()["agent_steps"] == ob.stats()["agent_steps"]
 
 
 FUSED = [

@@ -9,6 +9,7 @@ from oracle import oracle as orc
 
 TRAJ = sorted(os.path.basename(p)[:-8] for p in glob.glob(os.path.join(GOLDEN, "traj_*.json.gz")))
 QRUN = sorted(os.path.basename(p)[:-8] for p in glob.glob(os.path.join(GOLDEN, "qrun_*.json.gz")))
+QRAND = sorted(os.path.basename(p)[:-8] for p in glob.glob(os.path.join(GOLDEN, "qrand_*.json.gz")))
 
 
 def cfg_for(block):
@@ -127,6 +128,95 @@ def test_qlearning_run_bit_exact(name):
     assert got == want
 
 
+@pytest.mark.parametrize("name", QRAND)
+def test_qlearning_random_order_run_bit_exact(name):
+    """train_given_state_random_order (reference src/algorithms/qlearning.py:241-295) replayed with the
+    recorded car draws, coins, choices and headings: a draw that hits a finished car does nothing, every
+    other draw is one agent-step of that car; states, greedy actions, rewards, every updated Q value
+    (float64, exact) and the final Counter incl. its insertion order must match the reference."""
+    g = load_golden(name)
+    cfg = cfg_for(g["block"])
+    env = orc.Env(cfg, bad_states_text(g["block"]) if g["bad_states"] else None)
+    q = orc.QTable(f32=False, alpha=g["alpha"], discount=g["discount"])
+    n = len(g["boxes"])
+    for e, ep in enumerate(g["log"]):
+        assert orc.epsilon(g["episodes_total"], e, 3) == ep["eps"]
+        env.reset()
+        env.initialize_cars(n)
+        env.initialize(g["idx"], ep["headings"], g["choose"])
+        it = iter(ep["steps"])
+        for car in ep["draws"]:
+            assert not env.is_game_ended()
+            if env.car_done(car):
+                continue
+            num, state, explore, action, nxt, reward, qafter = next(it)
+            assert num == car
+            st = env.encodestate(car, 1)
+            assert orc.state_str(st) == state
+            if explore:
+                a = orc.ACTIONS.index(action)
+            else:
+                a = q.greedy(env, st)
+                assert orc.ACTIONS[a] == action, (e, state)
+            ns = env.successor_state(st, a)
+            assert orc.state_str(ns) == nxt
+            r = env.reward(st, ns, car, False)
+            assert r == reward
+            q.update(env, st, a, ns, r)
+            assert q.get(st, a) == float(qafter)
+            env.update_car(car, ns.pnode)
+        assert next(it, None) is None
+        assert env.is_game_ended()
+    got = q.items()
+    want = [(s, a, float(v)) for s, a, v in g["qvals"]]
+    assert got == want
+
+
+@pytest.mark.parametrize("name", QRAND)
+def test_batch_oracle_random_order_reproduces_reference_run(name):
+    """The batch restatement's random-order mode (flags & 16) with ONE env, the reference's recorded car draws and
+    decisions fed through the forced byte (high nibble car, low nibble action / 0xE greedy): it visits the
+    reference's (car, state, action, reward) sequence and learns its table (float32 vs float64: 1e-5)."""
+    np = pytest.importorskip("numpy")
+    g = load_golden(name)
+    cfg = cfg_for(g["block"])
+    n = len(g["boxes"])
+    ob = orc.Batch(cfg, 1, g["boxes"], g["idx"], g["choose"], bad_states_text(g["block"]) if g["bad_states"] else None, 0)
+    ob.reset(seed=1)
+    q = orc.QTable(f32=True)
+    lp = orc.learner(g["episodes_total"], seed=1, flags=16)
+    A5 = "SLRFT"
+    rnd = 0
+    for ep in g["log"]:
+        heads = [[orc.HEADS.index(h[-1]) for h in ep["headings"]]]
+        ob.reset(headings=np.array(heads, dtype=np.uint8), zero_counters=False)
+        it = iter(ep["steps"])
+        for car in ep["draws"]:
+            if ob.env_cars(0)[car][2]:  # a finished car consumes the draw, nothing else (qlearning.py:268-269)
+                out = ob.q_substep(q, lp, 0, rnd, forced=np.array([(car << 4) | 0xF], dtype=np.uint8))
+                assert out["action"][0] == 0xFF
+                rnd += 1
+                continue
+            num, state, explore, action, nxt, reward, qafter = next(it)
+            assert num == car
+            low = A5.index(action) if explore else 0xE
+            out = ob.q_substep(q, lp, 0, rnd, forced=np.array([(car << 4) | low], dtype=np.uint8))
+            rnd += 1
+            assert orc.state_str(out["state"][0]) == state
+            assert A5[out["action"][0]] == action
+            assert out["reward"][0] == reward
+            got = q.get(orc.state_from_str(state), orc.ACTIONS.index(action))
+            assert abs(got - float(qafter)) <= 1e-5 * max(abs(float(qafter)), 1.0)
+        assert next(it, None) is None
+    assert ob.stats()["episodes_done"] == len(g["log"])
+    want = {(s, a): float(v) for s, a, v in g["qvals"]}
+    got = {(s, a): v for s, a, v in q.items()}
+    # the reference's Counter also holds the keys it only read (0.0); the batch table the updated ones
+    assert set(got) == {(s[1], s[3]) for ep in g["log"] for s in ep["steps"]}
+    for k, v in want.items():
+        assert abs(got.get(k, 0.0) - v) <= 1e-5 * max(abs(v), 1.0), k
+
+
 def test_known_answers():
     g = load_golden("known_answers")
     cfg = cfg_for(2)
@@ -222,6 +312,9 @@ BATCH_CLAIM = [
     (2, ["D2", "D6", "D4", "D8"], [0, 0, 0, 0], [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 512, 120, 0),
     (0, ["U4", "U8", "U5", "U7"], [0, 1, 0, 0], [[0, 0, 0]] * 4, False, 512, 120, 0),
     (2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 512, 150, 2 | 4),  # encodestate(.,0) + stall detection
+    # random car order: different cars of different envs write the same table in one sub-step
+    (2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 512, 150, 16),
+    (2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 1024, 150, 16),
 ]
 
 
