@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
-    ap.add_argument("--sync-interval", type=int, default=16, help="rounds between Q-replica all-reduces (N>1)")
+    ap.add_argument("--sync-interval", type=int, default=64, help="rounds between Q-replica all-reduces (N>1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary (random-rollout, gym e2e) lines")
     args = ap.parse_args()

@@ -120,6 +120,52 @@ class RL:
 
     getpolicy = computeactionfromqvalues
 
+    def _legal_of(self, state):
+        if self.learner is None:
+            raise RuntimeError("no scenario yet: call prepare(...) or one of the train/validate methods first")
+        env = self.learner.env
+        idx = env.scenario.encode(state)
+        return idx, int(env.query(0, [idx])["legal"][0])
+
+    def computevaluefromqvalues(self, state):
+        """max over the legal actions of Q(state, .), 0.0 without legal actions (reference :45-58)."""
+        idx, legal = self._legal_of(state)
+        row = self.learner.q[idx].tolist()
+        vals = [row[a] for a in range(5) if (legal >> a) & 1]
+        return max(vals) if vals else 0.0
+
+    getvalue = computevaluefromqvalues
+
+    def getaction(self, state, epsilon):
+        """One random.random() draw always; below epsilon -> random.choice(legal), else the greedy action;
+        None without legal actions (reference :74-105, flipcoin src/utils/utils.py:255-265)."""
+        idx, legal = self._legal_of(state)
+        legal_actions = [ACTIONS5[a] for a in range(5) if (legal >> a) & 1]
+        if not legal_actions:
+            return None
+        if random.random() < epsilon:
+            return random.choice(legal_actions)
+        return self.computeactionfromqvalues(state)
+
+    def update(self, state, action, nextState, reward):
+        """Q[s,a] += alpha * (r + discount * max_a' Q[s',a'] - Q[s,a]) on the device table (reference :107-116),
+        float32 with the kernels' operation order."""
+        idx, _ = self._legal_of(state)
+        a = ACTIONS5.index(action)
+        q = self.learner.q
+        f32 = torch.float32
+        nv = torch.tensor(self.computevaluefromqvalues(nextState), dtype=f32)
+        qa = q[idx, a].cpu()
+        target = torch.tensor(float(reward), dtype=f32) + torch.tensor(self.discount, dtype=f32) * nv
+        q[idx, a] = (qa + torch.tensor(self.alpha, dtype=f32) * (target - qa)).to(q.device)
+        self.learner.visited[idx] |= 1 << a
+
+    def prepare(self, input_car_states, no_of_cars=1, destination_index_array=[0, 0, 0, 0],
+                destination_choose_arrays=[0, 0, 0], episodes=1):
+        """Build the device table for a scenario without training (the reference's methods above lean on
+        the module-global env having been initialised, qlearning.py:17-18,197-205)."""
+        return self._make(episodes, input_car_states, no_of_cars, destination_index_array, destination_choose_arrays)
+
     # ---- training (reference :187-239) -----------------------------------------------------------
     def _make(self, episodes, boxes, n, idx, choose, flags=0, model=None):
         sc = Scenario(self.env_config.layout, list(boxes[:n]), list(idx[:n]), [list(c) for c in choose[:n]],

@@ -258,3 +258,37 @@ def test_rl_plugin_random_order_batched(scratch):
     got_states = {s for (s, a) in rl.qvals}
     assert len(ref_states & got_states) > 0.6 * len(ref_states)
     assert os.path.exists(formats.qvalue_path('7', rl.qvalue_dir))
+
+
+def test_rl_counter_style_methods_match_oracle(scratch):
+    """getaction / update / computevaluefromqvalues / getvalue / getpolicy on state strings (reference
+    qlearning.py:34-121) against the float32 oracle table, on the (state, action, next, reward) tuples of a
+    recorded reference run."""
+    import random
+    import marl_dpp_b200 as m
+    from marl_dpp_b200 import settings
+    from marl_dpp_b200.algorithms.qlearning import RL
+    from oracle import oracle as orc
+    g = load_golden("qrun_b2_2car_bad")
+    rl = RL(**settings.params, sess=None, env_config=m.layout_3[2], n_envs=1)
+    with pytest.raises(RuntimeError):
+        rl.getaction("D2NxD6NzD3xD6", 0.0)
+    rl.prepare(g["boxes"], 2, g["idx"], g["choose"])
+    cfg = orc.Config(m.layout_3[2])
+    env = orc.Env(cfg, bad_states_text(2))
+    env.initialize_cars(2)
+    oq = orc.QTable(f32=True)
+    steps = [s for ep in g["log"][:6] for s in ep["steps"]][:400]
+    for state, explore, action, nxt, reward, qafter in steps:
+        st, ns = orc.state_from_str(state), orc.state_from_str(nxt)
+        assert rl.computevaluefromqvalues(nxt) == oq.value(env, ns)
+        rl.update(state, action, nxt, reward)
+        oq.update(env, st, orc.ACTIONS.index(action), ns, reward)
+        assert rl.getqvalue(state, action) == oq.get(st, orc.ACTIONS.index(action))
+        assert rl.getpolicy(state) == orc.ACTIONS[oq.greedy(env, st)]
+        assert rl.getvalue(state) == oq.value(env, st)
+    assert rl.getaction(steps[0][0], 0.0) == rl.computeactionfromqvalues(steps[0][0])
+    random.seed(5)
+    legal = orc.mask_str(env.legal(orc.state_from_str(steps[0][0])))
+    picks = {rl.getaction(steps[0][0], 1.0) for _ in range(60)}
+    assert picks == set(legal) - {"B"}
