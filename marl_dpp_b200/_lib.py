@@ -7,7 +7,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libmdpp.so")
+LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp.so")  # MDPP_LIB: A/B builds of experiments
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "fast_tabs.cuh", "q_learner.cuh", "q_round.cuh")] + \
           [os.path.join(ROOT, "include", "mdpp.h")]
 

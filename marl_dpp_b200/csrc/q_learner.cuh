@@ -441,18 +441,17 @@ q_env_smem_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) 
 // ------------------------------------------------------------------------------------------------
 // pull side: the reference update of one key, from the snapshot table
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float td_value(const float *__restrict__ q, const uint32_t *__restrict__ sinfo, uint32_t s,
-                                          uint32_t i /* = sinfo[s] */, uint32_t a, float qa, float alpha, float discount,
-                                          uint32_t n_states) {
+// row of the state the action leads to: same others, same destination, only the node term moves.  In range for
+// every key an env can mark; clamped branch-free (a counted guard here cost the latency-bound pull 1 us per round)
+__device__ __forceinline__ uint32_t td_successor(uint32_t s, uint32_t i /* = sinfo[s] */, uint32_t a, uint32_t n_states) {
     const uint32_t nl = si_node(i);
     const uint32_t rot = (0x20130u >> (4u * a)) & 3u;
     const uint32_t nnl = a == MDPP_A_F ? si_fwd(i) : ((nl & ~3u) | ((nl + rot) & 3u));
-    // same others, same destination: only the node term moves.  In range for every key an env can mark; clamped
-    // branch-free (a counted guard here cost the latency-bound pull 1 us per round)
-    const uint32_t s2 = min(s - nl + nnl, n_states - 1u);
-    const uint32_t i2 = __ldg(sinfo + s2);
-    float ns[MDPP_Q_ROW];
-    ldg_row(q + (size_t)s2 * MDPP_Q_ROW, ns);
+    return min(s - nl + nnl, n_states - 1u);
+}
+// the new value of a key from its state's info word, the successor's info word and table row
+__device__ __forceinline__ float td_update(uint32_t i, uint32_t i2, const float (&ns)[MDPP_Q_ROW], float qa, float alpha,
+                                           float discount) {
     // q_reward (src/env_gym.py:555-620); clash term = 0 under legal actions
     int32_t ri;
     if (i2 & kSiBad) ri = -10000;
@@ -469,6 +468,15 @@ __device__ __forceinline__ float td_value(const float *__restrict__ q, const uin
     // explicit roundings: the same operation order as the reference expression, no FMA contraction
     const float target = __fadd_rn((float)ri, __fmul_rn(discount, nv));
     return __fadd_rn(qa, __fmul_rn(alpha, __fsub_rn(target, qa)));
+}
+__device__ __forceinline__ float td_value(const float *__restrict__ q, const uint32_t *__restrict__ sinfo, uint32_t s,
+                                          uint32_t i /* = sinfo[s] */, uint32_t a, float qa, float alpha, float discount,
+                                          uint32_t n_states) {
+    const uint32_t s2 = td_successor(s, i, a, n_states);
+    const uint32_t i2 = __ldg(sinfo + s2);
+    float ns[MDPP_Q_ROW];
+    ldg_row(q + (size_t)s2 * MDPP_Q_ROW, ns);
+    return td_update(i, i2, ns, qa, alpha, discount);
 }
 
 __device__ __forceinline__ void mark_visited(uint32_t *__restrict__ visited, uint32_t key) {

@@ -68,6 +68,18 @@ for _ in range(100):
     ts.append((a, b))
 torch.cuda.synchronize()
 print("whole round, L2 flushed before each: %.2f us" % (sum(x.elapsed_time(y) for x, y in ts) / len(ts) * 1e3))
+# the same with the L2 left full of CLEAN lines (write flush, then a read pass over another 256 MiB)
+flush2 = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+flush2.zero_()
+ts = []
+for _ in range(100):
+    flush.zero_()
+    sink = flush2.sum()
+    a, b = ev(), ev()
+    a.record(); lr.train_rounds(1); b.record()
+    ts.append((a, b))
+torch.cuda.synchronize()
+print("whole round, L2 flushed (write pass then read pass: clean lines) before each: %.2f us" % (sum(x.elapsed_time(y) for x, y in ts) / len(ts) * 1e3))
 a, b = ev(), ev()
 torch.cuda.synchronize()
 a.record(); b.record(); torch.cuda.synchronize()
