@@ -31,6 +31,7 @@ constexpr size_t kMaxByteMapMarks = 200 * 1024;   // shared-memory BYTE map of a
 constexpr size_t kMaxDenseMarks = 8 * 200 * 1024; // shared-memory BIT map (atomic OR) up to here; list mode beyond
 constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices per region: sub-step kernels, one CTA per SM
 constexpr uint32_t kMaxRoundCtas = 320;           // ... fused round kernels, up to two CTAs per SM (byte-map tables only)
+constexpr int kMaxPureRounds = 8;                 // pure-exploration rounds per q_rounds_pure_kernel launch
 
 // a library kernel launch: counted per handle (mdpp_launch_count), error-checked
 #define MDPP_LAUNCH(h, call)                                                                     \
@@ -69,7 +70,9 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
     c.words_per_cta = (uint32_t)(((marks + 31) / 32 + 7) & ~(size_t)7); // whole blocks of 8 words (slice_index)
     c.cta_slots = marks <= kMaxByteMapMarks ? kMaxRoundCtas : kMaxEnvCtas;
-    c.regions = marks <= kMaxByteMapMarks ? 3 : 1; // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1
+    // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1; several pure-exploration rounds per
+    // launch (1-2 cars): region r * n_cars + c for sub-step (r, c)
+    c.regions = marks <= kMaxByteMapMarks ? (cfg.n_cars <= 2 ? (uint32_t)std::max(3, kMaxPureRounds * cfg.n_cars) : 3u) : 1u;
     if (c.dense) {
         c.qalt = take(keys * 4);
         c.marks = take((size_t)2 * c.regions * c.cta_slots * c.words_per_cta * 4); // [parity][region][cta][word]
@@ -103,6 +106,7 @@ struct mdpp_handle {
     uint64_t rng_round;     // round whose Philox words the car-0 launch published
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
+    bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
     bool chain;             // the previous launch on the stream was one of our learner kernels
     bool fast_rollout;      // the table-driven rollout kernel applies (BFS lengths fit its move table)
     uint64_t launches;      // learner kernels launched through this handle (bench.py's gpu_launches)
@@ -291,6 +295,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     make_devcfg(*cfg, h->dev);
     h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
+    h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->chain = false;
     h->smem_configured = 0;
     h->round_parity = 0;
@@ -751,6 +756,73 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     return MDPP_OK;
 }
 
+// n pure-exploration rounds in one launch (q_rounds_pure_kernel), then the pulls of their 2n (n) sub-steps in order.
+// Returns the number of rounds it ran: 0 when the next n rounds are not certainly inside the epsilon = 1 segment.
+static int pure_rounds_fit(const mdpp_handle *h, const mdpp_learner *lp, int want) {
+    if (!h->multi_round || lp->eps_q16[0] < 65536u) return 0;
+    const int64_t room = (int64_t)lp->eps_threshold[0] - h->ep_bound; // rounds before the bound leaves the segment
+    int n = (int)std::min<int64_t>(std::min<int64_t>(want, kMaxPureRounds), room);
+    const size_t map_bytes = (((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16;
+    const size_t tabs = ((h->cfg.n_cars == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>)) + 15) & ~(size_t)15;
+    if (tabs + 2 * (size_t)h->cfg.n_cars * map_bytes > (size_t)220 * 1024) return 0;
+    return n >= 2 ? n : 0;
+}
+static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round, int n,
+                                cudaStream_t s) {
+    const uint32_t P = h->round_parity;
+    h->round_parity ^= 1u;
+    h->ep_bound += n;
+    const int nc = h->cfg.n_cars;
+    RoundArgs ra{};
+    ra.recs = recs_of(h);
+    ra.n_envs = (uint32_t)h->n_envs;
+    ra.env_id_base = h->env_id_base;
+    ra.round = round;
+    ra.q = cur;
+    ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
+    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    ra.words_per_cta = h->cv.words_per_cta;
+    ra.cta_slots = h->cv.cta_slots;
+    ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
+    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.n_states = (uint32_t)h->cfg.n_states;
+    const unsigned grid = round_ctas(h);
+    ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / grid);
+    ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
+    ra.n_rounds = (uint32_t)n;
+    ra.region_words = h->cv.cta_slots * h->cv.words_per_cta;
+    ra.bits_a = mark_region(h, P, 0);
+    const size_t tabs = ((nc == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>)) + 15) & ~(size_t)15;
+    const size_t smem = tabs + 2 * (size_t)nc * ra.map_bytes;
+    {
+        LearnLaunch ll(h, grid, s, kRoundThreads, smem);
+        if (nc == 1) {
+            if (!((h->smem_configured >> 25) & 1u)) {
+                MDPP_CUDA(cudaFuncSetAttribute(q_rounds_pure_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                h->smem_configured |= 1u << 25;
+            }
+            MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_rounds_pure_kernel<1>, h->dev, *lp, ra, control_of(h)));
+        } else {
+            if (!((h->smem_configured >> 26) & 1u)) {
+                MDPP_CUDA(cudaFuncSetAttribute(q_rounds_pure_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                h->smem_configured |= 1u << 26;
+            }
+            MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_rounds_pure_kernel<2>, h->dev, *lp, ra, control_of(h)));
+        }
+        h->chain = true;
+    }
+    Marks mk = marks_of(h);
+    mk.n_ctas = grid;
+    for (int i = 0; i < n * nc; i++) {
+        mk.cta_bits = mark_region(h, P, (uint32_t)i);
+        // every pull but the last is followed by another pull, which waits before it touches anything
+        int rc = q_pull_launch(h, cur, alt, lp, s, &mk, i + 1 < n * nc ? 1 : 0);
+        if (rc) return rc;
+        std::swap(cur, alt);
+    }
+    return MDPP_OK;
+}
+
 static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStream_t s) {
     const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
@@ -795,7 +867,13 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
     const bool frozen = (lp->flags & MDPP_LEARN_FROZEN) != 0;
     const bool fused = lp->flags == 0 && round_eligible(h);
     for (int r = 0; r < rounds; r++) {
-        if (fused) { // training fast path: a whole round per launch (q_round.cuh)
+        if (fused) { // training fast path: a whole round per launch (q_round.cuh), several while every env explores
+            if (const int n = pure_rounds_fit(h, lp, rounds - r)) {
+                int rc = q_pure_rounds_launch(h, cur, alt, lp, first_round + (uint64_t)r, n, s);
+                if (rc) return rc;
+                r += n - 1;
+                continue;
+            }
             int rc = q_round_launch(h, cur, alt, lp, first_round + (uint64_t)r, s);
             if (rc) return rc;
             continue;

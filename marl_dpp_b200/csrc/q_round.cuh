@@ -46,6 +46,8 @@ struct RoundArgs {
     uint32_t rank_stride;        // n_dest_nodes * n_local_nodes
     uint32_t n_states;           // rows of the Q table (index clamp)
     uint32_t tiles_q, tiles_r;   // CTA b owns tiles [b * q + min(b, r), ... + q + (b < r)): no division on the device
+    uint32_t n_rounds;           // q_rounds_pure_kernel: rounds of this launch; sub-step (r, c) flushes into the mark
+    uint32_t region_words;       // region r * NC + c, regions region_words apart starting at bits_a
 };
 
 enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
@@ -262,6 +264,139 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
             out[slice_index(wd, blockIdx.x, ra.cta_slots)] = bits;
         }
     }
+    flush_counts<true>(cnt, S.cc, 0u, ctl);
+    pdl_wait();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Several pure-exploration rounds per launch.
+//
+// At 2^20 envs half of a round is fixed cost: 1 us of table staging and map clearing, 1.9 us of bitmap
+// compaction behind the last tile (the first map alone costs 1.1 us: first execution of that code), a kernel
+// boundary -- for 10 us of stepping (globaltimer stamps).  While every env explores nothing an
+// env does depends on the table, so the rounds of one mdpp_q_train_rounds call need no pull between them: this
+// kernel keeps the CTA (tables staged once) and runs n_rounds rounds, each warp over its own tiles, with one
+// __syncthreads per round.  The byte maps are double-buffered: while round r + 1 marks into the other pair,
+// every thread compacts its two words of round r's maps into the CTA's bitmap slices of mark regions r * NC + c
+// and clears them.  The pulls of all sub-steps follow the launch in order (the dense pull, one per region).
+// Same per-round arithmetic as q_round_kernel<NC, 0>; no lane can be parked (epsilon = 1: every coin explores;
+// the host launches this kernel only while its bound on the episode counters stays inside the first segment
+// for all n_rounds rounds).
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void flush_round_maps(const uint8_t *maps, uint32_t *bits0, const RoundArgs &ra) {
+    constexpr uint32_t kBlock = kRoundThreads;
+#pragma unroll
+    for (int m = 0; m < NC; m++) {
+        uint4 *map4 = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(maps) + (uint32_t)m * ra.map_bytes);
+        const uint32_t n16 = ra.map_bytes >> 4;
+        uint32_t *out = bits0 + (size_t)m * ra.region_words;
+        for (uint32_t wd = threadIdx.x; wd < ra.words_per_cta; wd += kBlock) {
+            uint32_t bits = 0;
+            if (2u * wd < n16) {
+                const uint4 lo = map4[2u * wd];
+                bits = ((lo.x * 0x01020408u) >> 24) | (((lo.y * 0x01020408u) >> 24) << 4) |
+                       (((lo.z * 0x01020408u) >> 24) << 8) | (((lo.w * 0x01020408u) >> 24) << 12);
+                map4[2u * wd] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (2u * wd + 1u < n16) {
+                const uint4 hi = map4[2u * wd + 1u];
+                bits |= (((hi.x * 0x01020408u) >> 24) << 16) | (((hi.y * 0x01020408u) >> 24) << 20) |
+                        (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
+                map4[2u * wd + 1u] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            out[slice_index(wd, blockIdx.x, ra.cta_slots)] = bits;
+        }
+    }
+}
+
+template <int NC>
+__global__ void __maxnreg__(56)
+q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
+    static_assert(NC >= 1 && NC <= 2, "the fused rounds are built for 1- and 2-car tables");
+    extern __shared__ uint4 smem_dyn[];
+    RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
+    constexpr uint32_t kTabBytes = (sizeof(RoundSmem<NC>) + 15u) & ~15u;
+    uint8_t *maps = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes; // [2 buffers][NC maps] of map_bytes each
+    pdl_launch_dependents(); // the pulls that follow wait for this grid to complete
+    const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
+    const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
+    constexpr uint32_t kBlock = kRoundThreads, n_warps = kRoundThreads / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t t = t0 + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
+    {
+        stage_step_tabs<NC, kBlock>(S, ra.tabs);
+        uint4 *m4 = reinterpret_cast<uint4 *>(maps);
+        const uint32_t n16 = 2u * NC * (ra.map_bytes >> 4);
+        for (uint32_t i = threadIdx.x; i < n16; i += kBlock) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
+    }
+    __syncthreads();
+    StepCounts cnt;
+    uint32_t parked = 0; // must stay 0 (see above); counted as an internal error otherwise
+    for (uint32_t r = 0; r < ra.n_rounds; r++) {
+        const uint64_t round = ra.round + r;
+        uint8_t *rmaps = maps + (size_t)(r & 1u) * NC * ra.map_bytes;
+        while (t < t1) {
+            const uint32_t e = t * 32u + lane, tn = t + n_warps;
+            uint4 rec_next = make_uint4(0u, 0u, 0u, 0u);
+            if (tn < t1 && tn * 32u + lane < ra.n_envs) rec_next = ra.recs[tn * 32u + lane];
+            uint32_t episode = rec.z & 0xFFFFu;
+            const bool live = (int32_t)episode < lp.episodes;
+            if (e < ra.n_envs && live && ((rec.w >> 8) & 7u) == 0u) {
+                uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+                uint32_t steps = rec.z >> 16;
+                const uint32_t env = ra.env_id_base + e;
+                uint32_t eps16 = lp.eps_q16[0];
+                if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
+                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+                uint32_t key;
+                bool moved, explore;
+                int st = round_car_step<NC, 0>(S, cfg, ra.tabs, ra, cars, p.x, eps16, false, key, moved, explore);
+                if (st == kStepDone) rmaps[key] = 1;
+                parked += st == kStepDefer;
+                steps += moved;
+                cnt.steps += moved;
+                cnt.explore += explore;
+                if (NC > 1) {
+                    st = round_car_step<NC, NC - 1>(S, cfg, ra.tabs, ra, cars, p.y, eps16, false, key, moved, explore);
+                    if (st == kStepDone) rmaps[(uint32_t)(NC - 1) * ra.map_bytes + key] = 1;
+                    parked += st == kStepDefer;
+                    steps += moved;
+                    cnt.steps += moved;
+                    cnt.explore += explore;
+                }
+                steps = steps > 0xFFFFu ? 0xFFFFu : steps;
+                { // end of the round-robin round (qlearning.py:233)
+                    bool finished = all_done<NC>(cars);
+                    bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+                    if (finished || capped) {
+                        cnt.episodes += 1;
+                        cnt.capped += capped;
+                        episode = episode + 1;
+                        cnt.max_episode = max(cnt.max_episode, episode);
+                        steps = 0;
+                        rec.w &= ~0xFFu;
+                        cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+                    }
+                }
+                rec.x = (uint32_t)cars;
+                rec.y = (uint32_t)(cars >> 32);
+                rec.z = (episode & 0xFFFFu) | (steps << 16);
+                ra.recs[e] = rec;
+            }
+            rec = rec_next;
+            t = tn;
+        }
+        // this thread's first tile of the next round: the record it wrote above, requested before the flush work
+        t = t0 + warp;
+        if (r + 1u < ra.n_rounds && t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
+        __syncthreads(); // every mark of round r is in its maps; the other pair (round r - 1) was cleared before the previous barrier
+        flush_round_maps<NC>(rmaps, ra.bits_a + (size_t)r * NC * ra.region_words, ra);
+    }
+    if (__any_sync(0xFFFFFFFFu, parked != 0u) && lane == 0) guard_tripped(ctl);
     flush_counts<true>(cnt, S.cc, 0u, ctl);
     pdl_wait();
 }
