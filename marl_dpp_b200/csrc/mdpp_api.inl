@@ -41,7 +41,7 @@ constexpr int kMaxPureRounds = 8;                 // pure-exploration rounds per
     } while (0)
 
 struct Carve {
-    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, bits, list, vals, visited, control, stage, dl, total;
+    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, gbits, bits, list, vals, visited, control, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
     uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
     uint32_t cta_slots, regions; // layout of the bitmap array [parity][region][cta_slots][words_per_cta]
@@ -77,9 +77,10 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
         c.qalt = take(keys * 4);
         c.marks = take((size_t)2 * c.regions * c.cta_slots * c.words_per_cta * 4); // [parity][region][cta][word]
         c.flags = take((size_t)2 * c.cta_slots * 4);
+        c.gbits = take((size_t)c.regions * c.words_per_cta * 4); // reduced marks of a multi-round launch, one bitmap per sub-step
         c.bits = c.list = c.vals = 0;
     } else {
-        c.qalt = c.marks = c.flags = 0;
+        c.qalt = c.marks = c.flags = c.gbits = 0;
         c.bits = take(2 * (keys / 8 + 4));
         c.list = take(2 * (size_t)c.capacity * 4);
         c.vals = take((size_t)c.capacity * 4);
@@ -107,6 +108,7 @@ struct mdpp_handle {
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
+    bool multi_pull;        // ... followed by one reduce + one cluster pull launch (MDPP_MULTI_PULL=0: dense pulls)
     bool chain;             // the previous launch on the stream was one of our learner kernels
     bool fast_rollout;      // the table-driven rollout kernel applies (BFS lengths fit its move table)
     uint64_t launches;      // learner kernels launched through this handle (bench.py's gpu_launches)
@@ -296,6 +298,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
+    h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
     h->chain = false;
     h->smem_configured = 0;
     h->round_parity = 0;
@@ -813,6 +816,46 @@ static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const 
     }
     Marks mk = marks_of(h);
     mk.n_ctas = grid;
+    // the pulls of all n * nc sub-steps in two launches when one cluster can hold the table (q_round.cuh)
+    if (h->multi_pull && (size_t)h->cfg.n_states <= (size_t)kMultiPullThreads * kMultiPullCtas) {
+        const uint32_t n_sub = (uint32_t)(n * nc), words = h->cv.words_per_cta;
+        uint32_t *gbits = (uint32_t *)(h->ws + h->cv.gbits);
+        {
+            const unsigned items = n_sub * words;
+            LearnLaunch ll(h, (items + kThreads / 32 - 1) / (kThreads / 32), s);
+            MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_marks_reduce_kernel, (const uint32_t *)mark_region(h, P, 0),
+                                              ra.region_words, n_sub, words, words, h->cv.cta_slots, (uint32_t)grid, gbits));
+        }
+        MultiPullArgs pa{};
+        pa.q = cur;
+        pa.sinfo = mk.sinfo;
+        pa.visited = mk.visited;
+        pa.gbits = gbits;
+        pa.n_substeps = n_sub;
+        pa.words = words;
+        pa.n_states = (uint32_t)h->cfg.n_states;
+        pa.alpha = lp->alpha;
+        pa.discount = lp->discount;
+        if (!((h->smem_configured >> 24) & 1u)) {
+            MDPP_CUDA(cudaFuncSetAttribute(q_multi_pull_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            h->smem_configured |= 1u << 24;
+        }
+        cudaLaunchAttribute attrs[2];
+        attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+        attrs[1].id = cudaLaunchAttributeClusterDimension;
+        attrs[1].val.clusterDim.x = kMultiPullCtas;
+        attrs[1].val.clusterDim.y = 1;
+        attrs[1].val.clusterDim.z = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(kMultiPullCtas);
+        cfg.blockDim = dim3(kMultiPullThreads);
+        cfg.stream = s;
+        cfg.attrs = attrs;
+        cfg.numAttrs = 2;
+        MDPP_LAUNCH(h, cudaLaunchKernelEx(&cfg, q_multi_pull_kernel, pa, control_of(h)));
+        return MDPP_OK;
+    }
     for (int i = 0; i < n * nc; i++) {
         mk.cta_bits = mark_region(h, P, (uint32_t)i);
         // every pull but the last is followed by another pull, which waits before it touches anything

@@ -402,6 +402,142 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The pulls of all sub-steps of a q_rounds_pure_kernel launch: two launches instead of one dense pull (a kernel
+// boundary and ~3 us) per sub-step.
+//   q_marks_reduce_kernel  one warp per (sub-step, bitmap word): ORs the env CTAs' slices into one bitmap per
+//                          sub-step (all sub-steps in parallel);
+//   q_multi_pull_kernel    ONE thread-block cluster (16 CTAs x 512 threads) holds the table in distributed shared
+//                          memory, one state row per thread, and applies the sub-steps in order.  Per sub-step a
+//                          thread takes its row's 5 mark bits (prefetched a sub-step ahead), gathers the
+//                          successor row of every marked action from the owning CTA's shared memory
+//                          (ld.shared::cluster) and writes the new row into the other of two row buffers; one
+//                          cluster barrier per sub-step separates the generations.  Successor ids and their info
+//                          words do not change: computed once.  The rows go back to global memory at the end.
+// Same arithmetic as the dense pull (td_update), so the table stays bit-identical.  (One CTA with the whole
+// table in its shared memory was tried first: 4.8 us per sub-step -- 2400 updates are 13 k warp-instructions,
+// too many for the issue slots of a single SM.)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+q_marks_reduce_kernel(const uint32_t *__restrict__ regions, uint32_t region_words, uint32_t n_regions, uint32_t words,
+                      uint32_t words_per_cta, uint32_t cta_slots, uint32_t n_ctas, uint32_t *__restrict__ gbits) {
+    pdl_launch_dependents();
+    pdl_wait(); // the round kernel has completed
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t item = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); // region * words + word
+    if (item >= n_regions * words) return;
+    const uint32_t region = item / words, word = item - region * words;
+    const uint32_t *src = regions + (size_t)region * region_words;
+    uint32_t bits = 0;
+    if (word < words_per_cta) {
+        for (uint32_t b0 = 0; b0 < n_ctas; b0 += 32u * kPullUnroll) {
+            uint32_t v[kPullUnroll];
+#pragma unroll
+            for (int j = 0; j < kPullUnroll; j++) {
+                const uint32_t b = b0 + 32u * j + lane;
+                v[j] = b < n_ctas ? src[slice_index(word, b, cta_slots)] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < kPullUnroll; j++) bits |= v[j];
+        }
+    }
+    bits = __reduce_or_sync(0xFFFFFFFFu, bits);
+    if (lane == 0) gbits[item] = bits;
+}
+
+constexpr int kMultiPullThreads = 512, kMultiPullCtas = 16; // 8192 states; 16 CTAs = the non-portable cluster size of sm_100
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ld_cluster_row(const void *local_smem, uint32_t rank, float (&r)[MDPP_Q_ROW]) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(ra) : "memory");
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4+16];"
+                 : "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "r"(ra) : "memory");
+}
+struct MultiPullArgs {
+    float *q;                 // the table, rows of MDPP_Q_ROW floats, updated in place at the end
+    const uint32_t *sinfo;
+    uint32_t *visited;
+    const uint32_t *gbits;    // [n_substeps][words] reduced marks (compact keys)
+    uint32_t n_substeps, words, n_states;
+    float alpha, discount;
+};
+// this state's 5 mark bits of one sub-step's bitmap (compact keys s * 5 .. s * 5 + 4: at most two words)
+__device__ __forceinline__ uint2 row_bit_words(const uint32_t *__restrict__ g, uint32_t s, uint32_t words) {
+    const uint32_t w = (s * MDPP_N_ACT) >> 5;
+    return make_uint2(w < words ? g[w] : 0u, w + 1u < words ? g[w + 1u] : 0u);
+}
+__global__ void __launch_bounds__(kMultiPullThreads, 1)
+q_multi_pull_kernel(MultiPullArgs pa, Control *ctl) {
+    __shared__ __align__(16) float rows[2][kMultiPullThreads][MDPP_Q_ROW]; // two generations of this CTA's rows
+    const uint32_t rank = cluster_ctarank(), lane = threadIdx.x & 31u;
+    const uint32_t s = rank * kMultiPullThreads + threadIdx.x;
+    const bool valid = s < pa.n_states;
+    const uint32_t sc = valid ? s : 0u, sh = (sc * MDPP_N_ACT) & 31u;
+    float *row_ptr = pa.q + (size_t)sc * MDPP_Q_ROW;
+    pdl_wait();              // the reduce kernel (and with it the round kernel and everything before) has completed
+    pdl_launch_dependents(); // the next round kernel waits for this grid before it reads the table or exits
+    const uint32_t info = pa.sinfo[sc];
+    float q[MDPP_Q_ROW];
+    {
+        const float4 lo = reinterpret_cast<const float4 *>(row_ptr)[0], hi = reinterpret_cast<const float4 *>(row_ptr)[1];
+        q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = lo.w; q[4] = hi.x; q[5] = hi.y; q[6] = hi.z; q[7] = hi.w;
+    }
+    uint2 nb = row_bit_words(pa.gbits, sc, pa.words);
+    uint32_t s2[MDPP_N_ACT], i2[MDPP_N_ACT]; // successor rows and their info words: fixed for the whole launch
+#pragma unroll
+    for (int a = 0; a < MDPP_N_ACT; a++) {
+        s2[a] = td_successor(sc, info, (uint32_t)a, pa.n_states);
+        i2[a] = pa.sinfo[s2[a]];
+    }
+    reinterpret_cast<float4 *>(rows[0][threadIdx.x])[0] = make_float4(q[0], q[1], q[2], q[3]);
+    reinterpret_cast<float4 *>(rows[0][threadIdx.x])[1] = make_float4(q[4], q[5], q[6], q[7]);
+    cluster_arrive();
+    uint32_t touched_bits = 0, touched = 0;
+    for (uint32_t i = 0; i < pa.n_substeps; i++) {
+        uint32_t mb = valid ? (__funnelshift_r(nb.x, nb.y, sh) & 31u) : 0u;
+        if (i + 1u < pa.n_substeps) nb = row_bit_words(pa.gbits + (size_t)(i + 1u) * pa.words, sc, pa.words);
+        cluster_wait(); // generation i is complete in every CTA
+        float nq[MDPP_Q_ROW];
+#pragma unroll
+        for (int k = 0; k < MDPP_Q_ROW; k++) nq[k] = q[k];
+#pragma unroll
+        for (int a = 0; a < MDPP_N_ACT; a++) {
+            if ((mb >> a) & 1u) {
+                float ns[MDPP_Q_ROW];
+                ld_cluster_row(rows[i & 1u][s2[a] % kMultiPullThreads], s2[a] / kMultiPullThreads, ns);
+                nq[a] = td_update(info, i2[a], ns, q[a], pa.alpha, pa.discount);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < MDPP_Q_ROW; k++) q[k] = nq[k];
+        // generation i + 1 goes to the other buffer: nobody reads that one before the next barrier completes
+        reinterpret_cast<float4 *>(rows[(i + 1u) & 1u][threadIdx.x])[0] = make_float4(q[0], q[1], q[2], q[3]);
+        reinterpret_cast<float4 *>(rows[(i + 1u) & 1u][threadIdx.x])[1] = make_float4(q[4], q[5], q[6], q[7]);
+        cluster_arrive();
+        touched_bits |= mb;
+        touched += (uint32_t)__popc(mb);
+    }
+    if (touched_bits) {
+        reinterpret_cast<float4 *>(row_ptr)[0] = make_float4(q[0], q[1], q[2], q[3]);
+        reinterpret_cast<float4 *>(row_ptr)[1] = make_float4(q[4], q[5], q[6], q[7]);
+        uint32_t *vis = pa.visited + s;
+        if ((*vis & touched_bits) != touched_bits) atomicOr(vis, touched_bits);
+    }
+    touched = __reduce_add_sync(0xFFFFFFFFu, touched);
+    if (lane == 0 && touched)
+        atomicAdd((unsigned long long *)&ctl->stats[(rank * (kMultiPullThreads / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1)].touched_keys,
+                  (unsigned long long)touched);
+    cluster_wait(); // no CTA leaves while its shared memory may still be read
+}
+
+// ------------------------------------------------------------------------------------------------
 // lockstep rollout under the uniform-random legal policy with auto-reset (config "random-policy sweep"),
 // table-driven like the round kernel: same semantics as rollout_random_kernel (mdpp_kernels.cu), which stays
 // as the fallback for layouts whose BFS lengths do not fit the 6 bits of the move table.

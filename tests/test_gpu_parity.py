@@ -424,47 +424,55 @@ def test_train_rounds_fused_path_matches_oracle(case):
 
 def test_pure_exploration_rounds_share_a_launch():
     """While every env is certainly in the epsilon = 1 segment, mdpp_q_train_rounds runs up to 8 rounds per
-    env-kernel launch (q_rounds_pure_kernel) and the pulls of their sub-steps afterwards: fewer launches, the
-    same table, records and counters as round-by-round launches (MDPP_MULTI_ROUND=0) -- and as the oracle."""
+    env-kernel launch (q_rounds_pure_kernel) and then all their pulls in two launches (bitmap reduce + one
+    cluster that holds the table in distributed shared memory): far fewer launches, the same table, records,
+    visited bits and counters as round-by-round launches -- and as the oracle.  Variant: the dense pulls after
+    the multi-round kernel (MDPP_MULTI_PULL=0)."""
     import torch
     m, BatchedEnv, BatchedQLearner, orc = _mods()
+    variants = [("default", {}), ("round by round", {"MDPP_MULTI_ROUND": "0"}), ("dense pulls", {"MDPP_MULTI_PULL": "0"})]
     for boxes, idx, choose, block, per_round in ((["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], 2, 3), (["U4"], [1], [[0, 0, 0]], 0, 2)):
         nc = len(boxes)
         badtxt = bad_states_text(block)
         sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=300)
-        runs = []
-        for multi in ("1", "0"):
-            os.environ["MDPP_MULTI_ROUND"] = multi
+        runs = {}
+        for name, envvars in variants:
+            os.environ.update(envvars)
             try:
                 env = BatchedEnv(sc, 4000, seed=23)
             finally:
-                os.environ.pop("MDPP_MULTI_ROUND", None)
+                for k in envvars:
+                    os.environ.pop(k, None)
             lr = BatchedQLearner(env, episodes=5000, seed=23)
             l0 = env.launch_count()
             lr.train_rounds(19)   # 8 + 8 + 3
             lr.train_rounds(1)    # a single round takes the one-round kernels
             lr.train_rounds(2)
             torch.cuda.synchronize()
-            runs.append((env.launch_count() - l0, lr.q.clone(), env.records.clone(), env.stats(), lr.visited.clone()))
-        want_multi = 3 * 1 + 19 * nc + per_round + (1 + 2 * nc) + (nc % 2)   # + the copy home after an odd number of pulls
-        assert runs[1][0] >= 22 * per_round
-        assert runs[0][0] < runs[1][0] and runs[0][0] <= want_multi + 3
-        assert torch.equal(runs[0][1], runs[1][1])
-        assert torch.equal(runs[0][2], runs[1][2])
-        assert torch.equal(runs[0][4], runs[1][4])
-        for k in ("agent_steps", "episodes_done", "explore_steps", "touched_keys", "q_updates", "internal_errors"):
-            assert runs[0][3][k] == runs[1][3][k], k
-        assert runs[0][3]["internal_errors"] == 0
+            runs[name] = (env.launch_count() - l0, lr.q.clone(), env.records.clone(), env.stats(), lr.visited.clone())
+        assert runs["round by round"][0] >= 22 * per_round
+        assert runs["default"][0] <= 16                       # 4 multi-round groups x 3 launches + one single round
+        assert runs["default"][0] < runs["dense pulls"][0] < runs["round by round"][0]
+        ref = runs["round by round"]
+        for name in ("default", "dense pulls"):
+            got = runs[name]
+            assert torch.equal(got[1], ref[1]), name
+            assert torch.equal(got[2], ref[2]), name
+            assert torch.equal(got[4], ref[4]), name
+            for k in ("agent_steps", "episodes_done", "explore_steps", "touched_keys", "q_updates", "internal_errors"):
+                assert got[3][k] == ref[3][k], (name, k)
+        assert ref[3]["internal_errors"] == 0
         ob = orc.Batch(orc.Config(m.layout_3[block]), 4000, boxes, idx, choose, badtxt, 300)
         ob.reset(seed=23)
         oq = orc.QTable(f32=True)
         olp = orc.learner(5000, seed=23)
         for r in range(22):
             ob.q_round(oq, olp, r)
-        q = runs[0][1].cpu().numpy()
+        q = runs["default"][1].cpu().numpy()
         for s_, a, v in [x for x in oq.items() if x[1] != "B"]:
             assert q[sc.encode(s_), A5.index(a)] == np.float32(v), (s_, a)
-        assert runs[0][3]["agent_steps"] == ob.stats()["agent_steps"]
+        assert runs["default"][3]["agent_steps"] == ob.stats()["agent_steps"]
+        assert runs["default"][3]["touched_keys"] == ob.touched_keys()
 
 
 def test_training_after_other_episode_advancing_calls():
