@@ -197,7 +197,10 @@ int mdpp_q_substep(mdpp_handle *h, float *q /*DEV [n_states][8]*/, const mdpp_le
 int mdpp_q_finalize(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, void *stream);
 /* `rounds` full rounds (n_cars x (sub-step + finalize)) starting at round index first_round.  The kernels of
  * consecutive sub-steps overlap through programmatic dependent launch; small tables ping-pong between q and a
- * workspace copy and are back in q when the call's work completes. */
+ * workspace copy and are back in q when the call's work completes.  With flags == 0 on 1- and 2-car tables a
+ * whole round is one env-kernel launch; while every env is certainly in an epsilon = 1 segment (a host-side
+ * bound on the episode counters, tightened at every mdpp_get_stats_host) up to 8 rounds share one launch and
+ * their updates follow in two launches.  The result does not depend on how the rounds are grouped into calls. */
 int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t first_round,
                         int rounds, void *stream);
 /* end-to-end variant: learner parameters from host memory, stats copied back, synchronised */
