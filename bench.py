@@ -339,6 +339,35 @@ def main():
         aux["qlearning_rounds_back_to_back"] = {"value": s["agent_steps"] / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
                                                 "us_per_round": a.elapsed_time(b) / 500 * 1e3,
                                                 "note": "500 rounds in one call, L2 warm, epsilon = 1 segment"}
+        # the library's own granularity while every env explores: 8 rounds per env-kernel launch, their pulls in two
+        # more launches (q_round.cuh); L2 flushed before every call like the headline, per-call events
+        evg = []
+        for _ in range(60):
+            flush.zero_()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            lra.train_rounds(8)
+            eb.record()
+            evg.append((ea, eb))
+        torch.cuda.synchronize()
+        s = enva.stats(reset=True)
+        gms = sum(x.elapsed_time(y) for x, y in evg)
+        aux["qlearning_8_rounds_per_call_l2_flushed"] = {
+            "value": s["agent_steps"] / (gms * 1e-3), "unit": UNIT, "us_per_round": gms / (60 * 8) * 1e3,
+            "frac_of_hbm_roofline": FUSED_Q_BYTES_PER_STEP(k) * s["agent_steps"] / (gms * 1e-3) / 1e9 / measured_peak()[0],
+            "note": "train_rounds(8) per timed call, 256 MiB L2 flush before each call (outside the event pair)"}
+        # ... and the same granularity end to end: parameters from host memory, counters back, synchronised
+        t_e2e = 0.0
+        for _ in range(60):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lra.train_rounds_host(8)
+            t_e2e += time.perf_counter() - t0
+        s = enva.stats(reset=True)
+        aux["e2e_8_rounds_per_call_l2_flushed"] = {
+            "value": s["agent_steps"] / t_e2e, "unit": UNIT, "us_per_round": t_e2e / (60 * 8) * 1e6,
+            "call": "BatchedQLearner.train_rounds_host(8) (host wall clock, sync + counter read-back every call)"}
         # a later training phase: epsilon pinned to 0.5, so half of the decisions are greedy (Q-row gathers,
         # parked lanes finished by the catch-up kernel)
         for i in range(6):
