@@ -302,6 +302,17 @@ def main():
         torch.cuda.synchronize()
         k0_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
         del lrp, envp
+        # what an event pair measures with NOTHING between the records, after the same flush: every per-step number
+        # above contains this much launch / event latency (chained rounds hide it, see aux)
+        eev = []
+        for i in range(100):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            b.record()
+            eev.append((a, b))
+        torch.cuda.synchronize()
+        empty_ms = sum(a.elapsed_time(b) for a, b in eev) / len(eev)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
@@ -312,7 +323,7 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "kernel": "one round = q_round_kernel<%d,0> + %d x q_pull_dense_kernel" % (k, k),
-                "avg_launch_ms": step_ms, "units_per_launch": units,
+                "avg_launch_ms": step_ms, "units_per_launch": units, "empty_event_pair_ms": empty_ms,
                 "algorithmic_bytes_per_unit": FUSED_Q_BYTES_PER_STEP(k), "peak_source": how,
                 "dominant_kernel": {"name": "q_round_kernel<%d,0>" % k, "avg_launch_ms": k0_ms,
                                     "share_of_step": k0_ms / step_ms,

@@ -20,6 +20,10 @@
 //    mask, occupancy test masks, selective-block mask) and one 8-byte entry per other car (its listed
 //    (box, destination box) code and occupancy bits).
 //
+// 3. At 2^20 envs half of a round is fixed cost (staging, map flush, three kernel boundaries).  While every
+//    env explores, q_rounds_pure_kernel runs up to 8 rounds per launch and q_marks_reduce_kernel +
+//    q_multi_pull_kernel (one cluster, table in distributed shared memory) apply all their sub-steps.
+//
 // Launch shape: one persistent CTA of 1024 threads per SM, tile assignment identical in K0 and K1.
 #pragma once
 #include "q_learner.cuh"
