@@ -184,6 +184,9 @@ class RL:
         while True:
             learner.train_rounds(chunk)
             rounds += chunk
+            # a counter fetch lets the library tighten its bound on the episode counters (it grows by one per
+            # round otherwise) and so keep the cheap pure-exploration kernels for the whole epsilon = 1 segment
+            learner.env.stats()
             ep = learner.env.cars()["episode"]
             lo = int(ep.min())
             if on_episode is not None:

@@ -276,7 +276,10 @@ class BatchedQLearner:
             _lib.check(self.env._L.mdpp_q_finalize(self.env._h, _ptr(self.q), C.byref(self.params), _stream()))
 
     def train_rounds(self, rounds):
-        """`rounds` full round-robin rounds (n_cars x (sub-step + finalize)); asynchronous."""
+        """`rounds` full round-robin rounds (n_cars x (sub-step + finalize)); asynchronous.
+        On 1- and 2-car tables the library runs up to 8 rounds per launch while every env is certainly in an
+        epsilon = 1 segment; it knows that from a host-side bound on the episode counters that grows by one per
+        round and is tightened whenever `env.stats()` is fetched -- fetch the counters every few hundred rounds."""
         env = self.env
         with torch.cuda.device(env.device):
             _lib.check(env._L.mdpp_q_train_rounds(env._h, _ptr(self.q), C.byref(self.params), self.round,

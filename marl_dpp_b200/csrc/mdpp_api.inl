@@ -107,6 +107,7 @@ struct mdpp_handle {
     uint64_t rng_round;     // round whose Philox words the car-0 launch published
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
+    bool k1_rounds;         // MDPP_K1_ROUNDS=1: rounds with greedy decisions through the fused K0 / K1 pair as well
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
     bool multi_pull;        // ... followed by one reduce + one cluster pull launch (MDPP_MULTI_PULL=0: dense pulls)
     bool chain;             // the previous launch on the stream was one of our learner kernels
@@ -297,6 +298,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     make_devcfg(*cfg, h->dev);
     h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
+    h->k1_rounds = getenv("MDPP_K1_ROUNDS") && atoi(getenv("MDPP_K1_ROUNDS")) != 0;
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
     h->chain = false;
@@ -644,7 +646,8 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
 #undef MDPP_QENV_K
 #undef MDPP_QENV_C
 #undef MDPP_QENV
-    if (car_slot == h->cfg.n_cars - 1) h->ep_bound += 1; // the end-of-round reset starts at most one new episode
+    // the end-of-round reset starts at most one new episode; in random car order any sub-step may end one
+    if (car_slot == h->cfg.n_cars - 1 || (lp->flags & MDPP_LEARN_RANDOM_ORDER)) h->ep_bound += 1;
     if (lp->flags & MDPP_LEARN_DETECT) { // a flagged env jumps to the end of its episode budget
         h->ep_bound = (int64_t)1 << 40;
         h->ep_device_max_valid = false;
@@ -917,9 +920,16 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
                 r += n - 1;
                 continue;
             }
-            int rc = q_round_launch(h, cur, alt, lp, first_round + (uint64_t)r, s);
-            if (rc) return rc;
-            continue;
+            // A round with greedy decisions needs two env passes either way.  The fused pair K0 / K1 steps car 1
+            // in both (explorers in K0, parked lanes in K1): 35-39 us per round at 2^20 envs for every epsilon
+            // < 1 of the schedule, against 31-32 us for one sub-step kernel + pull per car (tools/exp_mixed.py).
+            // So the round kernel is taken while every env certainly explores, the sub-step kernels otherwise.
+            const bool pure = lp->eps_q16[0] >= 65536u && h->ep_bound < (int64_t)lp->eps_threshold[0];
+            if (pure || h->k1_rounds) {
+                int rc = q_round_launch(h, cur, alt, lp, first_round + (uint64_t)r, s);
+                if (rc) return rc;
+                continue;
+            }
         }
         for (int c = 0; c < h->cfg.n_cars; c++) {
             int rc = q_env_launch(h, cur, lp, c, first_round + (uint64_t)r, nullptr, nullptr, nullptr, nullptr, s);

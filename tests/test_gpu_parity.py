@@ -356,6 +356,20 @@ def test_batched_random_order_matches_oracle(case):
     for s, a, v in [x for x in oq.items() if x[1] != "B"]:
         assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
     assert env.stats()["agent_steps"] == ob.stats()["agent_steps"]
+    # back to round-robin rounds on the same handle: the host's bound on the episode counters must have followed
+    # the random-order sub-steps (any of them may end an episode), or greedy lanes would be taken for explorers
+    lr.params.flags = 0
+    olp.flags = 0
+    lr.train_rounds(6)
+    for r in range(rounds + 5, rounds + 11):
+        ob.q_round(oq, olp, r)
+    q = lr.q.cpu().numpy()
+    for s, a, v in [x for x in oq.items() if x[1] != "B"]:
+        assert q[sc.encode(s), A5.index(a)] == np.float32(v), (s, a)
+    gs, ws = env.stats(), ob.stats()
+    for k in ("agent_steps", "episodes_done", "explore_steps"):
+        assert gs[k] == ws[k], k
+    assert int((env.records[:, 3] & 0x700).sum()) == 0
 
 
 FUSED = [
@@ -369,18 +383,25 @@ FUSED = [
 ]
 
 
+@pytest.mark.parametrize("k1", [False, True], ids=["default", "k1_rounds"])
 @pytest.mark.parametrize("case", FUSED, ids=[c[0] for c in FUSED])
-def test_train_rounds_fused_path_matches_oracle(case):
+def test_train_rounds_fused_path_matches_oracle(case, k1):
     """mdpp_q_train_rounds on 1- and 2-car tables takes the fused round kernels (q_round.cuh: table-driven
-    steps, car 1 stepped in the same pass when it explores, parked and finished by the catch-up kernel
-    when it acts greedily).  The episode budget is small so that the run crosses every epsilon segment
+    steps, car 1 stepped in the same pass when it explores; several rounds per launch while every env
+    explores) and, once greedy decisions appear, the sub-step kernels -- or, with MDPP_K1_ROUNDS=1, the fused
+    pair K0 / K1 (car 1 parked and finished by the catch-up kernel when it acts greedily).  The episode budget is small so that the run crosses every epsilon segment
     (1, .8, .5, .3, .15, 0) and ends with frozen envs; table, records and counters must equal the
     oracle's sub-step-by-sub-step restatement bit for bit."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
     name, block, boxes, idx, choose, bad, cap, n, episodes, rounds, chunk, stats_every = case
     badtxt = bad_states_text(block) if bad else None
     sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
-    env = BatchedEnv(sc, n, seed=17)
+    if k1:  # rounds with greedy decisions through the fused K0 / K1 pair too (default: the sub-step kernels)
+        os.environ["MDPP_K1_ROUNDS"] = "1"
+    try:
+        env = BatchedEnv(sc, n, seed=17)
+    finally:
+        os.environ.pop("MDPP_K1_ROUNDS", None)
     lr = BatchedQLearner(env, episodes=episodes, seed=17)
     ob = orc.Batch(orc.Config(m.layout_3[block]), n, boxes, idx, choose, badtxt, cap)
     ob.reset(seed=17)
