@@ -198,9 +198,10 @@ int mdpp_q_finalize(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, vo
 /* `rounds` full rounds (n_cars x (sub-step + finalize)) starting at round index first_round.  The kernels of
  * consecutive sub-steps overlap through programmatic dependent launch; small tables ping-pong between q and a
  * workspace copy and are back in q when the call's work completes.  With flags == 0 on 1- and 2-car tables a
- * whole round is one env-kernel launch; while every env is certainly in an epsilon = 1 segment (a host-side
- * bound on the episode counters, tightened at every mdpp_get_stats_host) up to 8 rounds share one launch and
- * their updates follow in two launches.  The result does not depend on how the rounds are grouped into calls. */
+ * whole round is one env-kernel launch while every env is certainly in an epsilon = 1 segment (a host-side
+ * bound on the episode counters, tightened at every mdpp_get_stats_host: fetch the counters now and then), and
+ * up to 8 such rounds share one launch, their updates following in two more.  The result does not depend on how
+ * the rounds are grouped into calls. */
 int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t first_round,
                         int rounds, void *stream);
 /* end-to-end variant: learner parameters from host memory, stats copied back, synchronised */
