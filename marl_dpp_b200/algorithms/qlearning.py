@@ -179,7 +179,7 @@ class RL:
 
     def _run(self, learner, episodes, on_episode=None, max_rounds=None):
         """Rounds until every env used its episode budget.  Returns rounds run."""
-        chunk = 1 if self.n_envs == 1 else 64
+        chunk = 1 if self.n_envs == 1 else 256
         rounds = 0
         while True:
             learner.train_rounds(chunk)

@@ -41,7 +41,7 @@ constexpr int kMaxPureRounds = 8;                 // pure-exploration rounds per
     } while (0)
 
 struct Carve {
-    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, gbits, bits, list, vals, visited, control, stage, dl, total;
+    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, gbits, bits, list, vals, visited, control, barrier, stage, dl, total;
     uint32_t capacity; // touched-list entries per parity (list mode)
     uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
     uint32_t cta_slots, regions; // layout of the bitmap array [parity][region][cta_slots][words_per_cta]
@@ -87,6 +87,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     }
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
+    c.barrier = take(64); // arrival counter of the cooperative kernels' grid barrier: zero at create, only ever grows
     c.stage = take((size_t)n_envs * 16);
     c.dl = take((size_t)n_envs * 4);
     c.total = off;
@@ -108,6 +109,9 @@ struct mdpp_handle {
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool k1_rounds;         // MDPP_K1_ROUNDS=1: rounds with greedy decisions through the fused K0 / K1 pair as well
+    bool mixed_rounds;      // rounds with greedy decisions: several per cooperative launch (MDPP_MIXED_ROUNDS=0: sub-step kernels)
+    int coop_ok;            // -1 unknown, 0 no cooperative launch / not co-resident, 1 ok
+    uint32_t barrier_base;  // value of the grid barrier's counter once everything launched so far has run
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
     bool multi_pull;        // ... followed by one reduce + one cluster pull launch (MDPP_MULTI_PULL=0: dense pulls)
     bool chain;             // the previous launch on the stream was one of our learner kernels
@@ -299,6 +303,9 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->rng_round = ~0ull;
     h->pdl = !(getenv("MDPP_PDL") && atoi(getenv("MDPP_PDL")) == 0);
     h->k1_rounds = getenv("MDPP_K1_ROUNDS") && atoi(getenv("MDPP_K1_ROUNDS")) != 0;
+    h->mixed_rounds = !(getenv("MDPP_MIXED_ROUNDS") && atoi(getenv("MDPP_MIXED_ROUNDS")) == 0);
+    h->coop_ok = -1;
+    h->barrier_base = 0;
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
     h->chain = false;
@@ -869,6 +876,74 @@ static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const 
     return MDPP_OK;
 }
 
+// n rounds WITH greedy decisions in one cooperative launch (q_rounds_mixed_kernel).  The table ends where it began
+// for 2 cars (an even number of pulls); for 1 car and an odd n it ends in the other copy.
+static size_t mixed_smem_bytes(const mdpp_handle *h) {
+    const size_t tabs = ((h->cfg.n_cars == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>)) + 15) & ~(size_t)15;
+    return tabs + (((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16;
+}
+static int mixed_rounds_fit(mdpp_handle *h, int want) {
+    if (!h->mixed_rounds || want < 1) return 0;
+    if (h->coop_ok < 0) { // first use: cooperative launch available, and the whole grid co-resident?
+        h->coop_ok = 0;
+        int dev = 0, coop = 0, per_sm = 0;
+        const void *fn = h->cfg.n_cars == 1 ? (const void *)q_rounds_mixed_kernel<1> : (const void *)q_rounds_mixed_kernel<2>;
+        const size_t smem = mixed_smem_bytes(h);
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess &&
+            coop && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kRoundThreads, smem) == cudaSuccess &&
+            (int64_t)per_sm * h->sm_count >= (int64_t)round_ctas(h))
+            h->coop_ok = 1;
+        else
+            cudaGetLastError(); // clear: the sub-step kernels take over
+    }
+    return h->coop_ok == 1 ? std::min(want, 16) : 0;
+}
+static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round, int n,
+                                 cudaStream_t s) {
+    const int nc = h->cfg.n_cars;
+    h->ep_bound += n;
+    RoundArgs ra{};
+    ra.recs = recs_of(h);
+    ra.n_envs = (uint32_t)h->n_envs;
+    ra.env_id_base = h->env_id_base;
+    ra.round = round;
+    ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
+    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    ra.words_per_cta = h->cv.words_per_cta;
+    ra.cta_slots = h->cv.cta_slots;
+    ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
+    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.n_states = (uint32_t)h->cfg.n_states;
+    const unsigned grid = round_ctas(h);
+    ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / grid);
+    ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
+    ra.n_rounds = (uint32_t)n;
+    ra.bits_a = mark_region(h, 0, 0);
+    MixedArgs mx{};
+    mx.barrier = (uint32_t *)(h->ws + h->cv.barrier);
+    mx.barrier_base = h->barrier_base;
+    mx.q0 = cur;
+    mx.q1 = alt;
+    const Marks mk = marks_of(h);
+    mx.sinfo = mk.sinfo;
+    mx.visited = mk.visited;
+    mx.n_marks = (uint32_t)((size_t)h->cfg.n_states * MDPP_N_ACT);
+    mx.n_ctas = grid;
+    mx.alpha = lp->alpha;
+    mx.discount = lp->discount;
+    const size_t smem = mixed_smem_bytes(h);
+    mdpp_learner lpv = *lp;
+    Control *ctl = control_of(h);
+    void *args[] = {(void *)&h->dev, (void *)&lpv, (void *)&ra, (void *)&mx, (void *)&ctl};
+    const void *fn = nc == 1 ? (const void *)q_rounds_mixed_kernel<1> : (const void *)q_rounds_mixed_kernel<2>;
+    MDPP_LAUNCH(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRoundThreads), args, smem, s));
+    h->barrier_base += (uint32_t)(2 * n * nc) * grid; // two barriers per sub-step, one arrival per CTA
+    h->chain = false; // launched in plain stream order; what follows must not overlap it either
+    if ((n * nc) & 1) std::swap(cur, alt);
+    return MDPP_OK;
+}
+
 static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStream_t s) {
     const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
@@ -928,6 +1003,12 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
             if (pure || h->k1_rounds) {
                 int rc = q_round_launch(h, cur, alt, lp, first_round + (uint64_t)r, s);
                 if (rc) return rc;
+                continue;
+            }
+            if (const int n = mixed_rounds_fit(h, rounds - r)) { // several such rounds in one cooperative launch
+                int rc = q_mixed_rounds_launch(h, cur, alt, lp, first_round + (uint64_t)r, n, s);
+                if (rc) return rc;
+                r += n - 1;
                 continue;
             }
         }

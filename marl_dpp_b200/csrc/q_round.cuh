@@ -54,14 +54,25 @@ struct RoundArgs {
     uint32_t region_words;       // region r * NC + c, regions region_words apart starting at bits_a
 };
 
+// A table row for kernels under which the table changes (q_rounds_mixed_kernel): plain coherent loads, not the
+// non-coherent path of ldg_row.  They may be served by L1 -- hot rows are read by thousands of lanes, and past L1
+// (ld.global.cg) the same-address loads serialise in L2: 75 instead of 32 us per round -- and the acquire side of
+// the grid barrier between sub-steps makes the table written before it visible to them.
+__device__ __forceinline__ void ldcg_row(const float *p, float (&r)[MDPP_Q_ROW]) {
+    const float4 lo = reinterpret_cast<const float4 *>(p)[0], hi = reinterpret_cast<const float4 *>(p)[1];
+    r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w; r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
+}
+
 enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
 
 // One agent-step of car C on the unpacked record.  `cars` is committed (ghost counters of encodestate, the
 // move) unless the car is parked.  Returns kStepDone with the compact key (state * 5 + action) when a key was touched.
-template <int NC, int C>
+// CG: the table changes while the kernel runs (q_rounds_mixed_kernel): coherent greedy reads (ldcg_row).
+template <int NC, int C, bool CG = false>
 __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
                                               const RoundArgs &ra, uint64_t &cars, uint32_t word, uint32_t eps16,
-                                              bool allow_greedy, uint32_t &key, bool &moved, bool &explore) {
+                                              bool allow_greedy, uint32_t &key, bool &moved, bool &explore,
+                                              const float *q_now = nullptr) {
     moved = false;
     explore = false;
     const uint32_t f = (uint32_t)(cars >> (12 * C)) & 0xFFFu;
@@ -117,9 +128,13 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
         a = (S.nth[lm] >> (3u * (((word & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
     } else {
         if (!allow_greedy) return kStepDefer; // the snapshot of this sub-step does not exist yet
-        pdl_wait();
         float qs[MDPP_Q_ROW];
-        ldg_row(ra.q + (size_t)sidx * MDPP_Q_ROW, qs);
+        if constexpr (CG) {
+            ldcg_row(q_now + (size_t)sidx * MDPP_Q_ROW, qs);
+        } else {
+            pdl_wait();
+            ldg_row(ra.q + (size_t)sidx * MDPP_Q_ROW, qs);
+        }
         float best = 0.f;
         bool have = false;
         a = 0;
@@ -539,6 +554,189 @@ q_multi_pull_kernel(MultiPullArgs pa, Control *ctl) {
         atomicAdd((unsigned long long *)&ctl->stats[(rank * (kMultiPullThreads / 32) + (threadIdx.x >> 5)) & (kStatSlots - 1)].touched_keys,
                   (unsigned long long)touched);
     cluster_wait(); // no CTA leaves while its shared memory may still be read
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rounds WITH greedy decisions, several per launch: a cooperative persistent kernel.
+//
+// Once greedy decisions appear every sub-step needs the table of the sub-step before it, so a round is
+// env pass -> pull -> env pass -> pull.  As separate launches that is 4 kernels and ~32 us per round at 2^20 envs,
+// of which the stepping itself is ~12 (tools/exp_mixed.py; 80 % of a full training run is spent in such rounds).
+// Here ONE cooperative grid (a CTA per SM, co-resident by construction) keeps its tables staged and runs
+// n_rounds x n_cars sub-steps with grid-wide barriers (grid_barrier below) instead of kernel boundaries:
+//   env pass of car c over the CTA's tiles (greedy reads by plain coherent loads: the table changes under the kernel), marks in
+//   a shared-memory byte map, compacted into the CTA's bitmap slice and cleared;   grid barrier;
+//   pull: warp w < 8 of CTA b owns bitmap word 8 b + w -- ORs the slices of all CTAs, then one thread per key writes
+//   the other copy of the table (ping-pong, as q_pull_dense_kernel);                grid barrier.
+// The decision word of car 1 travels through rng_words (same thread writes and reads it).  Same arithmetic,
+// same order as the sub-step kernels: bit-identical tables, records and counters.
+// ------------------------------------------------------------------------------------------------
+// Grid-wide barrier of a cooperative launch (every CTA co-resident by construction): one arrival per CTA on a
+// counter that only ever grows -- the host passes the value it had when the kernel started -- and a spin of one
+// thread per CTA.  Release / acquire through the two fences and the acquiring load, like cooperative groups'
+// grid.sync(), which measured ~4 us per barrier here against ~1 us for this one.
+__device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while ((int32_t)(v - target) < 0);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct MixedArgs {
+    uint32_t *barrier;        // the grid barrier's counter and its value at kernel start
+    uint32_t barrier_base;
+    float *q0, *q1;           // the table and its other copy: sub-step i reads q(i & 1), its pull writes q((i + 1) & 1)
+    const uint32_t *sinfo;
+    uint32_t *visited;
+    uint32_t n_marks, n_ctas;
+    float alpha, discount;
+};
+
+template <int NC, int C>
+__device__ __forceinline__ void mixed_env_pass(const RoundSmem<NC> &S, const DevCfg &cfg, const LearnArgs &lp,
+                                               const RoundArgs &ra, const float *q_now, uint64_t round, uint8_t *map,
+                                               uint32_t t0, uint32_t t1, StepCounts &cnt) {
+    constexpr uint32_t n_warps = kRoundThreads / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t t = t0 + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
+    while (t < t1) {
+        const uint32_t e = t * 32u + lane, tn = t + n_warps;
+        uint4 rec_next = make_uint4(0u, 0u, 0u, 0u);
+        if (tn < t1 && tn * 32u + lane < ra.n_envs) rec_next = ra.recs[tn * 32u + lane];
+        uint32_t episode = rec.z & 0xFFFFu;
+        const bool live = (int32_t)episode < lp.episodes;
+        if (e < ra.n_envs && live) {
+            uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            uint32_t steps = rec.z >> 16;
+            const uint32_t env = ra.env_id_base + e;
+            uint32_t eps16 = lp.eps_q16[0];
+            if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
+            uint32_t word;
+            if (C == 0) { // one Philox block per env and round: word c belongs to car c
+                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+                word = p.x;
+                if (NC > 1) ra.rng_words[e] = p.y;
+            } else {
+                word = ra.rng_words[e];
+            }
+            uint32_t key;
+            bool moved, explore;
+            if (round_car_step<NC, C, true>(S, cfg, ra.tabs, ra, cars, word, eps16, true, key, moved, explore, q_now) == kStepDone)
+                map[key] = 1;
+            steps += moved;
+            cnt.steps += moved;
+            cnt.explore += explore;
+            steps = steps > 0xFFFFu ? 0xFFFFu : steps;
+            if (C == NC - 1) { // end of the round-robin round (qlearning.py:233)
+                bool finished = all_done<NC>(cars);
+                bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+                if (finished || capped) {
+                    cnt.episodes += 1;
+                    cnt.capped += capped;
+                    episode = episode + 1;
+                    cnt.max_episode = max(cnt.max_episode, episode);
+                    steps = 0;
+                    rec.w &= ~0xFFu;
+                    cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+                }
+            }
+            rec.x = (uint32_t)cars;
+            rec.y = (uint32_t)(cars >> 32);
+            rec.z = (episode & 0xFFFFu) | (steps << 16);
+            ra.recs[e] = rec;
+        }
+        rec = rec_next;
+        t = tn;
+    }
+}
+
+// the pull of one sub-step by the whole grid: warp w < 8 of CTA b owns bitmap word 8 b + w
+__device__ __forceinline__ void mixed_pull(const RoundArgs &ra, const MixedArgs &mx, const float *qold, float *qnew,
+                                           uint32_t &touched_total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (warp >= 8u) return;
+    for (uint32_t word = blockIdx.x * 8u + warp; word < ra.words_per_cta; word += gridDim.x * 8u) {
+    const uint32_t m = word * 32u + lane, s = m / MDPP_N_ACT, a = m - s * MDPP_N_ACT, key = s * MDPP_Q_ROW + a;
+    const uint32_t info = m < mx.n_marks ? __ldg(mx.sinfo + s) : 0u;
+    uint32_t bits = 0;
+    for (uint32_t b0 = 0; b0 < mx.n_ctas; b0 += 32u * kPullUnroll) {
+        uint32_t v[kPullUnroll];
+#pragma unroll
+        for (int j = 0; j < kPullUnroll; j++) {
+            const uint32_t b = b0 + 32u * j + lane;
+            v[j] = b < mx.n_ctas ? ra.bits_a[slice_index(word, b, ra.cta_slots)] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kPullUnroll; j++) bits |= v[j];
+    }
+    bits = __reduce_or_sync(0xFFFFFFFFu, bits);
+    uint32_t touched = 0;
+    if (m < mx.n_marks) {
+        float v = qold[key];
+        if ((bits >> lane) & 1u) {
+            const uint32_t s2 = td_successor(s, info, a, ra.n_states);
+            const uint32_t i2 = __ldg(mx.sinfo + s2);
+            float ns[MDPP_Q_ROW];
+            ldcg_row(qold + (size_t)s2 * MDPP_Q_ROW, ns);
+            v = td_update(info, i2, ns, v, mx.alpha, mx.discount);
+            mark_visited(mx.visited, key);
+            touched = 1;
+        }
+        qnew[key] = v;
+        if (a < MDPP_Q_ROW - MDPP_N_ACT) qnew[key + MDPP_N_ACT] = qold[key + MDPP_N_ACT]; // padding slots carried through
+    }
+    touched = __reduce_add_sync(0xFFFFFFFFu, touched);
+    if (lane == 0) touched_total += touched;
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kRoundThreads, 1)
+q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Control *ctl) {
+    static_assert(NC >= 1 && NC <= 2, "built for 1- and 2-car tables");
+    extern __shared__ uint4 smem_dyn[];
+    RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
+    constexpr uint32_t kTabBytes = (sizeof(RoundSmem<NC>) + 15u) & ~15u;
+    uint8_t *map = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes;
+    const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
+    const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
+    {
+        stage_step_tabs<NC, kRoundThreads>(S, ra.tabs);
+        uint4 *m4 = reinterpret_cast<uint4 *>(map);
+        for (uint32_t i = threadIdx.x; i < (ra.map_bytes >> 4); i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
+    }
+    __syncthreads();
+    StepCounts cnt;
+    uint32_t touched_total = 0, sub = 0, bar = mx.barrier_base;
+    for (uint32_t r = 0; r < ra.n_rounds; r++) {
+        const uint64_t round = ra.round + r;
+#pragma unroll
+        for (int c = 0; c < NC; c++, sub++) {
+            const float *q_now = (sub & 1u) ? mx.q1 : mx.q0;
+            float *q_next = (sub & 1u) ? mx.q0 : mx.q1;
+            if (c == 0) mixed_env_pass<NC, 0>(S, cfg, lp, ra, q_now, round, map, t0, t1, cnt);
+            else mixed_env_pass<NC, (NC > 1 ? 1 : 0)>(S, cfg, lp, ra, q_now, round, map, t0, t1, cnt);
+            __syncthreads();
+            flush_round_maps<1>(map, ra.bits_a, ra); // compacts the map into this CTA's slice and clears it
+            grid_barrier(mx.barrier, bar += gridDim.x);
+            mixed_pull(ra, mx, q_now, q_next, touched_total);
+            grid_barrier(mx.barrier, bar += gridDim.x);
+        }
+    }
+    if ((threadIdx.x & 31u) == 0 && touched_total)
+        atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
+                  (unsigned long long)touched_total);
+    flush_counts<true>(cnt, S.cc, 0u, ctl);
 }
 
 // ------------------------------------------------------------------------------------------------

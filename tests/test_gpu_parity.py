@@ -383,25 +383,31 @@ FUSED = [
 ]
 
 
-@pytest.mark.parametrize("k1", [False, True], ids=["default", "k1_rounds"])
+@pytest.mark.parametrize("k1", [False, True, "substep"], ids=["default", "k1_rounds", "substep_kernels"])
 @pytest.mark.parametrize("case", FUSED, ids=[c[0] for c in FUSED])
 def test_train_rounds_fused_path_matches_oracle(case, k1):
     """mdpp_q_train_rounds on 1- and 2-car tables takes the fused round kernels (q_round.cuh: table-driven
     steps, car 1 stepped in the same pass when it explores; several rounds per launch while every env
-    explores) and, once greedy decisions appear, the sub-step kernels -- or, with MDPP_K1_ROUNDS=1, the fused
-    pair K0 / K1 (car 1 parked and finished by the catch-up kernel when it acts greedily).  The episode budget is small so that the run crosses every epsilon segment
+    explores) and, once greedy decisions appear, the cooperative multi-round kernel (env pass / grid barrier / pull
+    per sub-step) -- or, with MDPP_K1_ROUNDS=1, the fused pair K0 / K1 (car 1 parked and finished by the catch-up
+    kernel when it acts greedily), or, with MDPP_MIXED_ROUNDS=0, one sub-step kernel + pull per car.  The episode budget is small so that the run crosses every epsilon segment
     (1, .8, .5, .3, .15, 0) and ends with frozen envs; table, records and counters must equal the
     oracle's sub-step-by-sub-step restatement bit for bit."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
     name, block, boxes, idx, choose, bad, cap, n, episodes, rounds, chunk, stats_every = case
     badtxt = bad_states_text(block) if bad else None
     sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
-    if k1:  # rounds with greedy decisions through the fused K0 / K1 pair too (default: the sub-step kernels)
+    # rounds with greedy decisions: default = the cooperative multi-round kernel; the fused K0 / K1 pair; the
+    # sub-step kernels
+    if k1 is True:
         os.environ["MDPP_K1_ROUNDS"] = "1"
+    elif k1 == "substep":
+        os.environ["MDPP_MIXED_ROUNDS"] = "0"
     try:
         env = BatchedEnv(sc, n, seed=17)
     finally:
         os.environ.pop("MDPP_K1_ROUNDS", None)
+        os.environ.pop("MDPP_MIXED_ROUNDS", None)
     lr = BatchedQLearner(env, episodes=episodes, seed=17)
     ob = orc.Batch(orc.Config(m.layout_3[block]), n, boxes, idx, choose, badtxt, cap)
     ob.reset(seed=17)
