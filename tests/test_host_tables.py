@@ -141,6 +141,21 @@ def test_c_abi_exports_every_declared_symbol():
     assert _lib.lib().mdpp_abi_version() == 1
 
 
+def test_python_constants_match_the_header():
+    """The learner flags, forced-action codes and reward kinds the Python layer passes are the header's."""
+    from marl_dpp_b200 import batched
+    hdr = open(os.path.join(ROOT, "include", "mdpp.h")).read()
+    defs = {k: int(v.rstrip("u"), 0) for k, v in re.findall(r"#define\s+(MDPP_[A-Z_0-9]+)\s+(0x[0-9A-Fa-f]+u?|\d+u?)\b", hdr)}
+    assert (defs["MDPP_LEARN_FROZEN"], defs["MDPP_LEARN_MODE0"], defs["MDPP_LEARN_DETECT"], defs["MDPP_LEARN_OBSERVED"],
+            defs["MDPP_LEARN_RANDOM_ORDER"]) == (T.LEARN_FROZEN, T.LEARN_MODE0, T.LEARN_DETECT, T.LEARN_OBSERVED,
+                                                 T.LEARN_RANDOM_ORDER)
+    assert defs["MDPP_ACT_SKIP"] == batched.ACT_SKIP and defs["MDPP_ACT_GREEDY"] == batched.ACT_GREEDY
+    enums = dict(re.findall(r"\b(MDPP_REWARD_[A-Z]+)\s*=\s*(\d+)", hdr))
+    assert int(enums["MDPP_REWARD_Q"]) == batched.REWARD_KINDS["q_reward"]
+    assert int(enums["MDPP_REWARD_DQN"]) == batched.REWARD_KINDS["dqn_reward"]
+    assert defs["MDPP_ABI_VERSION"] == _lib.lib().mdpp_abi_version()
+
+
 def test_workspace_size_and_no_cpu_fallback():
     import torch
     sc = T.Scenario(m.layout_3[2], ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]])
