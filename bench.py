@@ -15,6 +15,12 @@ Prints ONE JSON line on rank 0 (contract in the task statement): value = device-
 throughput, e2e = the same metric through the public host-facing call (parameters from host
 memory in, counters back, synchronised every step), roofline = the dominant kernel against the
 measured HBM peak, cpu_baseline = the CPU oracle port on this box's host cores.
+
+Before anything is timed the batch is rolled forward (untimed) to its stationary mix of active and
+finished cars: a round costs the same whether or not a car still moves, so a window that starts at a
+fresh reset (99 % of the car slots active) over-reports the long-run rate (72 % active).  With N > 1
+the replicas are averaged INSIDE the timed region (at least four times) by the library's own
+peer-memory kernel, and the sync-interval sweep of BASELINE config 4 is reported in aux.
 """
 import argparse
 import json
@@ -35,6 +41,21 @@ STEP_CAP = 10000
 EPISODES = 5000
 WORKLOAD = "qlearning-layout3-block2-2car-badstates-1Mi-envs-per-gpu"
 FUSED_Q_BYTES_PER_STEP = lambda k: 44.0 + 16.0 / k  # fused Q-learning, per agent-step
+PREROLL_ROUNDS = 1024        # untimed rounds before any timed region: the active-car fraction is stationary by then
+# The UNMODIFIED Python reference cannot run on the GPU box (/root/reference is absent there).  Its rate was
+# measured in the build container (SURVEY.md section 6 [probe]): src/algorithms/qlearning.py train_given_state,
+# layout 3 block 2, 2 cars, Display stubbed, stdout discarded, Python 3.12, ONE core (the reference is single-threaded).
+PYTHON_REFERENCE = {"value": 1.28e4, "unit": UNIT, "cores": 1, "kind": "labelled constant, not measured in this run",
+                    "provenance": "SURVEY.md section 6 [probe]: 84 532 agent-steps of the unmodified reference's "
+                                  "RL.train_given_state in 6.6 s (300 episodes, block 2, 2 cars, cv2 Display stubbed) "
+                                  "in the build container; 7.2e2 /s as shipped (Display rebuilt at every reset)"}
+
+
+def workload_config():
+    """The workload both arms run (BASELINE.json configs[1]); arm-specific keys are added by each arm."""
+    return {"workload": WORKLOAD, "layout": 3, "block": BLOCK, "n_cars": 2, "envs_per_gpu": 1 << 20,
+            "bad_states": True, "episodes_per_env": EPISODES, "step_cap": STEP_CAP,
+            "alpha": 0.9, "discount": 0.15, "epsilon_model": 3}
 
 
 def bad_text():
@@ -106,38 +127,48 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(seconds, threads=None, envs_per_thread=2048, rounds_per_chunk=20):
-    """The CPU arm: oracle port (the reference is pure Python and cannot travel to the GPU box; its
-    measured rate here is quoted in DESIGN.md).  One independent learner replica per host thread."""
+CPU_ENVS_PER_THREAD = 2048   # the same sample in both CPU legs (cpu_baseline of our arm, --impl reference)
+CPU_PREROLL_ROUNDS = 512     # the CPU envs are rolled to their stationary mix first as well (untimed)
+
+
+def _cpu_bench(threads):
     from oracle import oracle as orc
     import marl_dpp_b200 as m
-    threads = threads or os.cpu_count() or 1
     boxes, idx, choose = m.layout_3[BLOCK]["initial_states"][0]
     lp = orc.learner(EPISODES, seed=3)
-    b = orc.CpuBench(orc.Config(m.layout_3[BLOCK]), threads, envs_per_thread, boxes, idx, choose, bad_text(),
+    b = orc.CpuBench(orc.Config(m.layout_3[BLOCK]), threads, CPU_ENVS_PER_THREAD, boxes, idx, choose, bad_text(),
                      STEP_CAP, lp)
-    b.run(2)  # warm the tables
+    b.run(CPU_PREROLL_ROUNDS)
+    return b
+
+
+def cpu_reference(seconds, threads=None, rounds_per_chunk=100):
+    """The CPU arm: oracle port (the reference is pure Python and cannot travel to the GPU box; its
+    measured rate is carried as a labelled constant).  One independent learner replica per host thread."""
+    threads = threads or os.cpu_count() or 1
+    b = _cpu_bench(threads)
     steps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         steps += b.run(rounds_per_chunk)
     dt = time.perf_counter() - t0
     b.close()
     return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d independent oracle learners x %d envs, %.1f s, same scenario/hyper-parameters"
-                      % (threads, envs_per_thread, dt)}
+            "sample": "%d independent oracle learners x %d envs, %d untimed pre-roll rounds, then %.1f s timed, same "
+                      "scenario/hyper-parameters" % (threads, CPU_ENVS_PER_THREAD, CPU_PREROLL_ROUNDS, dt),
+            "python_reference": PYTHON_REFERENCE}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    from oracle import oracle as orc
-    import marl_dpp_b200 as m
     threads = os.cpu_count() or 1
-    envs_per_thread, rounds_per_step = 512, 4   # bounded sample: the whole K-step run ends within minutes
-    boxes, idx, choose = m.layout_3[BLOCK]["initial_states"][0]
-    lp = orc.learner(EPISODES, seed=3)
-    b = orc.CpuBench(orc.Config(m.layout_3[BLOCK]), threads, envs_per_thread, boxes, idx, choose, bad_text(),
-                     STEP_CAP, lp)
+    b = _cpu_bench(threads)
+    # a step = enough rounds for ~0.5 s of CPU work (calibrated once, untimed): the per-step thread fan-out of the
+    # oracle driver is then noise, and the whole --steps K --warmup W run ends within a minute or two
+    t0 = time.perf_counter()
+    b.run(20)
+    per_round = (time.perf_counter() - t0) / 20
+    rounds_per_step = max(20, min(2000, int(0.5 / max(per_round, 1e-6))))
     for _ in range(args.warmup):
         b.run(rounds_per_step)
     steps, t0 = 0, time.perf_counter()
@@ -146,14 +177,17 @@ def run_reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     b.close()
     v = steps / dt
-    sample = ("each step = %d rounds of %d independent oracle learners x %d envs (bounded sample of the workload)"
-              % (rounds_per_step, threads, envs_per_thread))
+    sample = ("each step = %d rounds of %d independent oracle learners x %d envs after %d untimed pre-roll rounds "
+              "(bounded sample of the workload; same sample as cpu_baseline of the GPU arm)"
+              % (rounds_per_step, threads, CPU_ENVS_PER_THREAD, CPU_PREROLL_ROUNDS))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "arm": "CPU oracle port on host cores (reference is pure Python)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": dict(workload_config(), arm="CPU oracle port on host cores (the reference is pure Python): every "
+                                              "step is a bounded sample of the workload, see cpu_baseline.sample"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "python_reference": PYTHON_REFERENCE},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -166,9 +200,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
-    ap.add_argument("--sync-interval", type=int, default=64, help="rounds between Q-replica all-reduces (N>1)")
+    ap.add_argument("--sync-interval", type=int, default=-1,
+                    help="rounds between Q-replica averagings (N>1); default min(64, max(1, steps // 4)): at least four "
+                         "inside the timed region; 0 = never")
+    ap.add_argument("--preroll", type=int, default=PREROLL_ROUNDS, help="untimed rounds before the timed region")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary (random-rollout, gym e2e) lines")
+    ap.add_argument("--full-training", type=int, default=1,
+                    help="aux: also run the whole 5000-episode training job once (~20 s on one B200); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -205,7 +244,20 @@ def main():
     sc = m.Scenario(m.layout_3[BLOCK], boxes, idx, choose, bad_states_text=bad_text(), step_cap=STEP_CAP)
     n, k = args.envs, sc.n_cars
     env = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=3)
-    lr = BatchedQLearner(env, episodes=EPISODES, seed=3)
+    # N > 1: the table lives in a peer-mapped exchange buffer and the library averages the replicas with its own
+    # kernel inside train_rounds (csrc/q_sync.cuh); a table too large for that would use NCCL (not this workload)
+    interval = args.sync_interval if args.sync_interval >= 0 else min(64, max(1, args.steps // 4))
+    exchange, sync_kind = None, None
+    if world > 1:
+        from marl_dpp_b200.parallel import PeerExchange
+        try:
+            exchange = PeerExchange(sc, device=dev)
+            sync_kind = "q_sync_kernel: one-shot peer-memory exchange over NVLink (CUDA IPC), fused 1/N"
+        except Exception as e:  # noqa: BLE001 -- reported in the line, never silent
+            exchange, sync_kind = None, "ncclAllReduce(AVG) fallback: %s" % (str(e)[:120],)
+    lr = BatchedQLearner(env, episodes=EPISODES, seed=3, q=exchange.q if exchange else None)
+    if exchange:
+        exchange.attach(lr, interval)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -213,13 +265,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i):
-        lr.train_rounds(1)
-        if world > 1 and args.sync_interval > 0 and (i + 1) % args.sync_interval == 0:
-            lr.sync_replicas()
+    nccl_syncs = [0]
 
+    def after_step():
+        """NCCL fallback only: the library's own exchange happens inside train_rounds."""
+        if world > 1 and not exchange and interval > 0 and lr.round % interval == 0:
+            lr.sync_replicas()
+            nccl_syncs[0] += 1
+
+    # ---- untimed pre-roll to the stationary mix of active / finished cars --------------------------------
+    done = 0
+    while done < args.preroll:
+        c = min(256, args.preroll - done)
+        if world > 1 and not exchange and interval > 0:
+            for _ in range(c):
+                lr.train_rounds(1)
+                after_step()
+        else:
+            lr.train_rounds(c)
+        done += c
+        env.stats()   # lets the library tighten its bound on the episode counters
     for i in range(args.warmup):
-        one_step(i)
+        lr.train_rounds(1)
+        after_step()
     barrier()
     env.stats(reset=True)
 
@@ -231,16 +299,19 @@ def main():
     barrier()
     wall0 = time.perf_counter()
     launches0 = env.launch_count()
+    syncs0 = lr.sync_count() + nccl_syncs[0]
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
-        one_step(args.warmup + i)
+        lr.train_rounds(1)
+        after_step()
         ev[i][1].record()
         if (i + 1) % 256 == 0:
             # outside the event pair: a counter fetch (synchronises) lets the library tighten its bound on the
             # envs' episode counters, i.e. keep skipping the catch-up kernel while every env explores
             st_mid = env.stats()
     gpu_launches = env.launch_count() - launches0
+    syncs_timed = lr.sync_count() + nccl_syncs[0] - syncs0
     barrier()
     wall = time.perf_counter() - wall0
     clk = clocks.stop() if rank == 0 else None
@@ -254,6 +325,21 @@ def main():
         dev_ms = float(tmax[0])
     total_steps, total_upd = float(t[1]), float(t[2])
     value = total_steps / (dev_ms * 1e-3)
+    active_fraction = total_steps / (float(args.steps) * n * k * world)
+
+    # the exchange alone, in this run: back-to-back explicit averagings, device-timed, max over ranks
+    sync_us = None
+    if world > 1:
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(50):
+            lr.sync_replicas()
+        b.record()
+        torch.cuda.synchronize()
+        ts = torch.tensor([a.elapsed_time(b) / 50 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sync_us = float(ts[0])
 
     # ---- e2e: the public host-facing call, one round per call, counters read back every step ----
     barrier()
@@ -264,7 +350,7 @@ def main():
         torch.cuda.synchronize()           # the L2 flush is outside the timed window
         t0 = time.perf_counter()
         lr.train_rounds_host(1)  # learner params from host memory in, mdpp_stats back, stream synchronised
-        if world > 1 and args.sync_interval > 0 and (i + 1) % args.sync_interval == 0:
+        if world > 1 and not exchange and interval > 0 and lr.round % interval == 0:
             lr.sync_replicas()
             torch.cuda.synchronize()
         e2e_dt += time.perf_counter() - t0
@@ -290,6 +376,9 @@ def main():
         achieved = FUSED_Q_BYTES_PER_STEP(k) * units / (step_ms * 1e-3) / 1e9
         envp = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=3)
         lrp = BatchedQLearner(envp, episodes=EPISODES, seed=3)
+        for _ in range(0, args.preroll, 256):   # the same stationary mix as the timed region
+            lrp.train_rounds(min(256, args.preroll))
+            envp.stats()
         lrp.train_rounds(args.warmup)
         kev = []
         for i in range(min(args.steps, 200)):
@@ -313,15 +402,18 @@ def main():
             eev.append((a, b))
         torch.cuda.synchronize()
         empty_ms = sum(a.elapsed_time(b) for a, b in eev) / len(eev)
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        # DRAM bytes of the round's kernels from this round's committed `ncu --set full` capture of this command
+        # (per launch, stationary mix); null when no capture of the current kernels is tracked
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic_r02.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("round_dram_bytes")
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj.get("round_dram_bytes"), tj.get("source")
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "one round = q_round_kernel<%d,0> + %d x q_pull_dense_kernel" % (k, k),
                 "avg_launch_ms": step_ms, "units_per_launch": units, "empty_event_pair_ms": empty_ms,
                 "algorithmic_bytes_per_unit": FUSED_Q_BYTES_PER_STEP(k), "peak_source": how,
@@ -334,11 +426,43 @@ def main():
 
     # ---- secondary lines (not the headline): random-policy rollout and gym-style host stepping ----
     aux = {}
-    if rank == 0 and not args.no_aux:
+    if world > 1 and exchange and not args.no_aux:
+        # BASELINE config 4: sync-interval sweep, every rank takes part (the exchange is collective).  256 rounds
+        # per point, launched back to back in calls of 64 (so that interval 64 averages inside the library's
+        # kernel chain), device-timed, max over ranks.
+        sweep = {}
+        for iv in (1, 4, 16, 64, 0):
+            exchange.attach(lr, iv)
+            lr.round = ((lr.round + 63) // 64) * 64      # the same phase of the interval at every point
+            barrier()
+            env.stats(reset=True)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0 = lr.sync_count()
+            a.record()
+            for _ in range(4):
+                lr.train_rounds(64)
+            b.record()
+            torch.cuda.synchronize()
+            sv = env.stats(reset=True)
+            tt = torch.tensor([a.elapsed_time(b), float(sv["agent_steps"])], dtype=torch.float64, device=dev)
+            tm = tt.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            sweep["never" if iv == 0 else str(iv)] = {
+                "value": float(tt[1]) / (float(tm[0]) * 1e-3), "us_per_round": float(tm[0]) / 256 * 1e3,
+                "exchanges": lr.sync_count() - c0}
+        exchange.attach(lr, interval)
+        if rank == 0:
+            aux["sync_interval_sweep"] = {"unit": UNIT, "rounds_per_point": 256, "points": sweep,
+                                          "note": "rounds back to back (L2 warm), replicas averaged by q_sync_kernel "
+                                                  "before every round R with R % interval == 0"}
+    if rank == 0 and world == 1 and not args.no_aux:
         # the same learner, rounds launched back to back (no flush, no per-round events): training throughput
         enva = BatchedEnv(sc, n, device=dev, seed=3)
         lra = BatchedQLearner(enva, episodes=EPISODES, seed=3)
-        lra.train_rounds(200)
+        for _ in range(0, args.preroll, 256):
+            lra.train_rounds(min(256, args.preroll))
+            enva.stats()
         torch.cuda.synchronize()
         enva.stats(reset=True)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,6 +473,7 @@ def main():
         s = enva.stats(reset=True)
         aux["qlearning_rounds_back_to_back"] = {"value": s["agent_steps"] / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
                                                 "us_per_round": a.elapsed_time(b) / 500 * 1e3,
+                                                "active_fraction": s["agent_steps"] / (500.0 * n * k),
                                                 "note": "500 rounds in one call, L2 warm, epsilon = 1 segment"}
         # the library's own granularity while every env explores: 8 rounds per env-kernel launch, their pulls in two
         # more launches (q_round.cuh); L2 flushed before every call like the headline, per-call events
@@ -395,6 +520,25 @@ def main():
                                                "us_per_round": a.elapsed_time(b) / 300 * 1e3,
                                                "greedy_fraction": 1.0 - s["explore_steps"] / max(s["agent_steps"], 1)}
         del lra, enva
+        if args.full_training:
+            # the whole BASELINE training job: 2^20 envs x 5000 episodes each, epsilon schedule 1 -> 0, through the
+            # public call sequence of RL._run (256 rounds per call, a counter fetch between calls)
+            envf = BatchedEnv(sc, n, device=dev, seed=3)
+            lrf = BatchedQLearner(envf, episodes=EPISODES, seed=3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rounds_f = 0
+            while True:
+                lrf.train_rounds(256)
+                rounds_f += 256
+                sf = envf.stats()
+                if int((envf.records[:, 2] & 0xFFFF).min()) >= EPISODES or rounds_f > 4_000_000:
+                    break
+            dt = time.perf_counter() - t0
+            aux["full_training_run"] = {"wall_s": dt, "rounds": rounds_f, "agent_steps": sf["agent_steps"],
+                                        "episodes": sf["episodes_done"], "value": sf["agent_steps"] / dt, "unit": UNIT,
+                                        "note": "2^20 envs x 5000 episodes per env, every epsilon segment, host wall clock"}
+            del lrf, envf
         rounds = 16
         env2 = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=4)
         for w in range(3):
@@ -522,13 +666,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "layout": 3, "block": BLOCK, "n_cars": k, "envs_per_gpu": n,
-                       "bad_states": True, "episodes_per_env": EPISODES, "step_cap": STEP_CAP,
-                       "alpha": 0.9, "discount": 0.15, "epsilon_model": 3,
+            "config": dict(workload_config(), n_cars=k, envs_per_gpu=n, **{
                        "step": "one round-robin round over every env = q_round_kernel (all cars) + one q_pull_dense_kernel per car slot",
                        "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
-                       "sync_interval_rounds": args.sync_interval if world > 1 else None,
-                       "parallelism": "dp%d: env shards + per-GPU Q replicas, NCCL all-reduce(AVG)" % world},
+                       "preroll_rounds": args.preroll, "active_fraction": active_fraction,
+                       "sync_interval_rounds": interval if world > 1 else None,
+                       "allreduces_in_timed_region": syncs_timed if world > 1 else None,
+                       "allreduce_us": sync_us, "allreduce": sync_kind,
+                       "parallelism": "dp%d: env shards + per-GPU Q replicas averaged every sync_interval_rounds" % world}),
             "q_updates_per_s": total_upd / (dev_ms * 1e-3),
             "wall_s_timed_region": wall,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(lr.params),

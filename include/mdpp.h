@@ -83,7 +83,8 @@ typedef struct {
 /* Learner parameters (reference src/algorithms/qlearning.py:20-27 and src/utils/utils.py:33-52). */
 typedef struct {
     float alpha, discount;      /* 0.9, 0.15 */
-    int32_t episodes;           /* per-env episode budget; an env that finished it is frozen */
+    int32_t episodes;           /* per-env episode budget, 0..65535 (the per-env counter is 16 bits of the record;
+                                   larger values are rejected with MDPP_EINVAL); an env that finished it is frozen */
     int32_t eps_threshold[5];   /* int(episodes*{0.4,0.6,0.7,0.85,0.99}) */
     uint32_t eps_q16[6];        /* epsilon * 65536 per schedule segment: {1,.8,.5,.3,.15,0} */
     uint32_t seed;
@@ -212,6 +213,40 @@ int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learne
  * that bench.py can time the dominant kernel alone with CUDA events.  The marks it leaves are never
  * pulled: use it on a handle you do not train further. */
 int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t round, void *stream);
+
+/* ---- multi-GPU: Q-replica averaging over NVLink peer memory ------------------------------------------
+ * No reference counterpart (the reference is one process): every GPU of a node trains its own
+ * replica on its env shard (env_id_base keys the RNG) and every `interval` rounds the replicas are averaged --
+ * sum in rank order / world, the same bits on every rank -- by ONE kernel that reads every rank's table through
+ * peer-mapped memory (csrc/q_sync.cuh).  The table must therefore live in an exchange buffer:
+ *   mdpp_sync_buffer_bytes   bytes of the buffer for a scenario: the Q table [n_states][8] floats at offset 0,
+ *                            then MDPP_SYNC_FLAG_BYTES of flags (zero-initialised by mdpp_sync_alloc);
+ *   mdpp_sync_alloc          cudaMalloc on the current device (the ONE device allocation this library makes:
+ *                            legacy CUDA IPC needs memory it allocated itself) + the 64-byte IPC handle the other
+ *                            ranks open; mdpp_sync_free releases it;
+ *   mdpp_sync_open / _close  map / unmap a peer's buffer (cudaIpcOpenMemHandle with lazy peer access);
+ *   mdpp_sync_attach         bufs[r] = rank r's buffer as seen from this process (bufs[rank] = the own one; in a
+ *                            single process plain device pointers do).  interval > 0: mdpp_q_train_rounds[_host]
+ *                            averages before every round R > 0 with R % interval == 0 -- `q` must then be
+ *                            bufs[rank] -- as a member of its kernel chain: a pure-exploration round runs while
+ *                            the replicas are exchanged.  Every rank must make the same calls in the same order.
+ *   mdpp_q_sync_replicas     one averaging now (all ranks call it; asynchronous on `stream`).
+ * One-shot exchange, for tables up to MDPP_SYNC_MAX_TABLE_BYTES (1-2 cars, 3 cars on block 0); mdpp_sync_attach
+ * fails with MDPP_EINVAL beyond that and the caller falls back to a library all-reduce. */
+#define MDPP_SYNC_MAX_RANKS 8
+#define MDPP_SYNC_FLAG_BYTES (2 * 148 * MDPP_SYNC_MAX_RANKS * 4)
+#define MDPP_SYNC_MAX_TABLE_BYTES (148 * 512 * 2 * 16)
+#define MDPP_IPC_HANDLE_BYTES 64
+int64_t mdpp_sync_buffer_bytes(const mdpp_config *cfg);
+int mdpp_sync_alloc(int64_t bytes, void **dev_ptr_out, uint8_t *ipc_handle_out /*[MDPP_IPC_HANDLE_BYTES]*/);
+int mdpp_sync_free(void *dev_ptr);
+int mdpp_sync_open(const uint8_t *ipc_handle /*[MDPP_IPC_HANDLE_BYTES]*/, void **peer_ptr_out);
+int mdpp_sync_close(void *peer_ptr);
+int mdpp_sync_attach(mdpp_handle *h, int rank, int world, void *const *bufs /*HOST array [world] of DEV pointers*/,
+                     int interval);
+int mdpp_q_sync_replicas(mdpp_handle *h, float *q /*DEV, == bufs[rank]*/, void *stream);
+/* number of replica averagings launched through this handle so far */
+uint64_t mdpp_sync_count(mdpp_handle *h);
 
 /* ---- DQN feed: the env-facing half of the noisy double DQN's collection loop (reference
  * src/algorithms/dqn_open_source.py:490-526); the MLP stays in PyTorch.  observe = encodestate(car, 1)

@@ -1,5 +1,5 @@
 """ctypes binding of libmdpp.so (include/mdpp.h).  The library is built in-tree by
-`python -m marl_dpp_b200.build` / __graft_entry__.build() with nvcc for sm_100a.  There is no
+__graft_entry__.build() (`python -c 'import __graft_entry__ as g; g.build()'`) with nvcc for sm_100a.  There is no
 fallback: if the shared library is missing, importing the compute API raises."""
 import ctypes as C
 import os
@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp.so")  # MDPP_LIB: A/B builds of experiments
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "fast_tabs.cuh", "q_learner.cuh", "q_round.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "fast_tabs.cuh", "q_learner.cuh", "q_round.cuh", "q_sync.cuh")] + \
           [os.path.join(ROOT, "include", "mdpp.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -19,7 +19,9 @@ EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_err
            "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_launch_count", "mdpp_query_transitions",
            "mdpp_update_car", "mdpp_dqn_observe", "mdpp_dqn_act", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
            "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
-           "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host"]
+           "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host",
+           "mdpp_sync_buffer_bytes", "mdpp_sync_alloc", "mdpp_sync_free", "mdpp_sync_open", "mdpp_sync_close", "mdpp_sync_attach",
+           "mdpp_q_sync_replicas", "mdpp_sync_count"]
 
 
 def needs_build():
@@ -81,6 +83,14 @@ def lib():
         "mdpp_decode_state": (I, [P, I64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "mdpp_encode_state": (I64, [P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
         "mdpp_get_stats_host": (I, [P, P, I, P]),
+        "mdpp_sync_buffer_bytes": (I64, [P]),
+        "mdpp_sync_alloc": (I, [I64, C.POINTER(P), P]),
+        "mdpp_sync_free": (I, [P]),
+        "mdpp_sync_open": (I, [P, C.POINTER(P)]),
+        "mdpp_sync_close": (I, [P]),
+        "mdpp_sync_attach": (I, [P, I, I, C.POINTER(P), I]),
+        "mdpp_q_sync_replicas": (I, [P, F32, P]),
+        "mdpp_sync_count": (U64, [P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

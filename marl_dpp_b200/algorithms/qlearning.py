@@ -8,6 +8,8 @@ CUDA learner over `n_envs` lockstep copies of the initial state (marl_dpp_b200.b
 n_envs = 1 it performs the reference's update sequence.  File arguments keep the reference's
 meaning: strings, '0' = none, files under ./src/data/qvalue_files/layout-3/.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -72,6 +74,35 @@ class RL:
         self._pull()
         formats.write_qvalues(formats.qvalue_path(outputfile_number, self.qvalue_dir),
                               [(s, a, v) for (s, a), v in self.qvals.items()])
+
+    # ---- file conversions (reference :439-597) ----------------------------------------------------------
+    def convert_textfile_in_ascending_order(self, inputfile_number, outputfile_number):
+        """Re-key the loaded table with every state's others in ascend_array order into `qvals_new`,
+        then save_qvalues(outputfile_number).  Like the reference, save_qvalues writes `self.qvals`
+        -- the table as loaded -- so the file on disk is a re-serialisation of the input and the
+        ascended table only lives in `qvals_new` (reference :446-455)."""
+        self.learner = None          # the file, not a device table from an earlier run, is the source
+        self.load_qvalues(inputfile_number)
+        self.qvals_new = {}
+        for (state, action), value in self.qvals.items():
+            self.qvals_new[(formats.ascend_state(state), action)] = value
+        self.save_qvalues(outputfile_number)
+
+    def convert_textfile(self, input_textfile, output_textfile, block_number):
+        """Rename a block's boxes to whole-floor ("MSV") boxes in a qvalue file (reference :457-542)."""
+        formats.convert_textfile(input_textfile, output_textfile, block_number,
+                                 directory=self._qvalue_root())
+
+    def reverse_convert_textfile(self, input_textfile, output_textfile, block_number):
+        """The inverse renaming (reference :544-597)."""
+        formats.convert_textfile(input_textfile, output_textfile, block_number,
+                                 directory=self._qvalue_root(), reverse=True)
+
+    def _qvalue_root(self):
+        # the reference hard-codes ./src/data/qvalue_files/ here and .../layout-3/ for load/save
+        if self.qvalue_dir == formats.QVALUE_DIR:
+            return formats.QVALUE_ROOT
+        return self.qvalue_dir
 
     def _push(self, learner):
         """Loaded Counter -> dense device table (keys outside this scenario's state space are kept
@@ -361,10 +392,13 @@ class RL:
                             no_of_cars=1, destination_index_array=[0, 0, 0, 0], destination_choose_arrays=[0, 0, 0],
                             max_cars=6):
         """Stall heuristic: Q-learning episodes with encodestate(., 0); in the epsilon = 0 episodes an
-        env whose greedy policy emits 3*n_cars consecutive 'S' flags that state.  Every flagged state
-        that is not already in the bad-states file is expanded and written (utils.py:159-199).
-        Returns like the reference: the last episode index, or False when a flagged state was
-        already known (the reference's `skip`)."""
+        env whose greedy policy emits 3*n_cars consecutive 'S' flags that state and stops.
+        Return value as in the reference (:350-382): the EPISODE at which a not-yet-known state was
+        flagged -- the state is expanded and written to the bad-states file (utils.py:159-199) and
+        the Q values are NOT saved (the reference returns before save_qvalues); False when a
+        flagged state is already in the file (the reference's `skip`); else the last episode index,
+        after save_qvalues.  Batched: every env runs the heuristic; the smallest flagging episode
+        over the envs is returned and every distinct new state is written."""
         self.env_config.no_of_cars = no_of_cars
         self.load_qvalues(inputfile_number)
         learner = self._make(episodes, input_car_states, no_of_cars, destination_index_array,
@@ -372,22 +406,36 @@ class RL:
         self._run(learner, episodes)
         sc = learner.env.scenario
         flagged = learner.env.deadlock_states().cpu().numpy()
-        states = sorted({sc.decode(int(i)) for i in np.unique(flagged[flagged >= 0])})
+        hit = flagged >= 0
+        states = sorted({sc.decode(int(i)) for i in np.unique(flagged[hit])})
         self.detected_deadlocks = states
-        known = set(formats.read_bad_states(self.env_config.environment_bad_states_file)) \
-            if self.bad_states_text is not None else set()
-        result = episodes - 1
-        for state in states:
-            if state in known:  # reference :350,357-366 compares the full string (with headings)
-                result = False
-                continue
+        bad_file = self.env_config.environment_bad_states_file
+        known = set()
+        if self.bad_states_text is not None:
+            try:
+                known = set(formats.read_bad_states(bad_file))
+            except OSError:   # bad_states was passed as text and the layout's file does not exist yet
+                known = {x for x in self.bad_states_text.split("\n") if x != ""}
+        fresh = [s for s in states if s not in known]  # the reference compares the full string, headings included (:350)
+        if len(fresh) < len(states):
+            self._pull()
+            return False
+        if fresh:
             if self.bad_states_text is not None:
-                formats.save_deadlock_state(state, self.env_config.station_box_list,
-                                            self.env_config.environment_bad_states_file,
-                                            state.count('z') + 1, max_cars)
+                if not os.path.exists(bad_file):
+                    os.makedirs(os.path.dirname(bad_file) or ".", exist_ok=True)
+                    with open(bad_file, "w") as f:
+                        f.write(self.bad_states_text)
+                for state in fresh:
+                    formats.save_deadlock_state(state, self.env_config.station_box_list, bad_file,
+                                                state.count('z') + 1, max_cars)
+            # the episode in which each env was flagged rides in the high half of record word 3
+            ep = (learner.env.records[:, 3].cpu().numpy().astype(np.int64) >> 16) & 0xFFFF
+            self._pull()
+            return int(ep[hit].min())
         self.save_qvalues(outputfile_number)
         self._pull()
-        return result
+        return episodes - 1
 
     # ---- validation (reference :384-437, minus the cv2 key-press UI) -----------------------------------
     def validate_given_state(self, episodes, inputfile_number, outputfile_number, input_car_states=None, no_of_cars=1,

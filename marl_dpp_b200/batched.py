@@ -308,9 +308,25 @@ class BatchedQLearner:
         self.round += 1
 
     def sync_replicas(self, group=None):
-        """Average the per-GPU Q replicas: one NCCL all-reduce (AVG) over NVLink, in place."""
+        """Average the per-GPU Q replicas now.  With a PeerExchange attached (parallel.PeerExchange.attach):
+        the library's own one-kernel exchange over NVLink peer memory; otherwise one library all-reduce
+        (NCCL AVG, or SUM + scale on gloo)."""
+        if getattr(self, "exchange", None) is not None:
+            env = self.env
+            with torch.cuda.device(env.device):
+                _lib.check(env._L.mdpp_q_sync_replicas(env._h, _ptr(self.q), _stream()))
+            return
         from . import parallel
         parallel.average_(self.q, group)
+
+    def sync_count(self):
+        """Replica averagings launched by the library through this handle (explicit + inside train_rounds)."""
+        return int(self.env._L.mdpp_sync_count(self.env._h))
+
+    def merge_visited(self, group=None):
+        """OR the ranks' updated-key bits (call before qvalue_items / save on a multi-GPU run)."""
+        from . import parallel
+        parallel.merge_visited_(self.visited, group)
 
     # -- qvalue .txt format (reference src/algorithms/qlearning.py:159-185) --------------------------
     def qvalue_items(self):

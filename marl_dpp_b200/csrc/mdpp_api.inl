@@ -126,6 +126,11 @@ struct mdpp_handle {
     int64_t ep_bound;
     bool ep_device_max_valid;
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
+    // replica averaging (q_sync.cuh): every rank's exchange buffer as seen from this process
+    int sync_world, sync_rank, sync_interval;
+    uint32_t sync_epoch;    // calls so far; the flags of call k carry k (every rank makes the same calls)
+    uint64_t sync_count;
+    void *sync_bufs[MDPP_SYNC_MAX_RANKS];
 };
 
 using namespace mdpp;
@@ -143,6 +148,15 @@ static int validate_config(const mdpp_config *cfg) {
     if (cfg->n_states <= 0 || cfg->n_states * MDPP_Q_ROW >= (int64_t)1 << 32)
         return fail(MDPP_EINVAL, "n_states %lld does not fit 32-bit keys", (long long)cfg->n_states);
     if (cfg->step_cap < 0 || cfg->step_cap > 65535) return fail(MDPP_EINVAL, "step_cap out of 0..65535");
+    return MDPP_OK;
+}
+
+// The per-env episode counter is 16 bits of the record (rec.z & 0xFFFF): a larger budget would wrap it, restart
+// the epsilon schedule and never freeze the env.
+static int validate_learner(const mdpp_learner *lp) {
+    if (!lp) return fail(MDPP_EINVAL, "learner is NULL");
+    if (lp->episodes < 0 || lp->episodes > 65535)
+        return fail(MDPP_EINVAL, "learner.episodes %d out of 0..65535 (16-bit per-env episode counter)", lp->episodes);
     return MDPP_OK;
 }
 
@@ -953,12 +967,120 @@ static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStrea
     return MDPP_OK;
 }
 
+// ---- replica averaging (q_sync.cuh) -----------------------------------------------------------------------
+static size_t sync_table_bytes(const mdpp_config &c) { return align_up((size_t)c.n_states * MDPP_Q_ROW * 4); }
+static bool sync_due(const mdpp_handle *h, uint64_t round) {
+    return h->sync_world > 1 && h->sync_interval > 0 && round > 0 && round % (uint64_t)h->sync_interval == 0;
+}
+// rounds that may share a launch from `round` on without crossing an averaging point
+static int sync_room(const mdpp_handle *h, uint64_t round, int want) {
+    if (h->sync_world <= 1 || h->sync_interval <= 0) return want;
+    const uint64_t left = (uint64_t)h->sync_interval - round % (uint64_t)h->sync_interval;
+    return (int)std::min<uint64_t>((uint64_t)want, left);
+}
+static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
+    if (h->sync_world <= 1) return MDPP_OK;
+    if ((void *)q != h->sync_bufs[h->sync_rank])
+        return fail(MDPP_EINVAL, "replica averaging: q must be the table of this rank's exchange buffer");
+    SyncArgs a{};
+    const size_t tb = sync_table_bytes(h->cfg);
+    for (int r = 0; r < h->sync_world; r++) {
+        a.table[r] = (float *)h->sync_bufs[r];
+        a.flags[r] = (uint32_t *)((char *)h->sync_bufs[r] + tb);
+    }
+    a.rank = (uint32_t)h->sync_rank;
+    a.world = (uint32_t)h->sync_world;
+    a.epoch = ++h->sync_epoch;
+    a.n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
+    a.timeout_ns = 2000000000ull;
+    a.errors = (unsigned long long *)&control_of(h)->stats[0].internal_errors;
+    const unsigned grid = (a.n4 + kSyncThreads * kSyncPer - 1) / (kSyncThreads * kSyncPer);
+    LearnLaunch ll(h, grid, s, kSyncThreads);
+    switch (h->sync_world) {
+    case 2: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<2>, a)); break;
+    case 3: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<3>, a)); break;
+    case 4: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<4>, a)); break;
+    case 5: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<5>, a)); break;
+    case 6: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<6>, a)); break;
+    case 7: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<7>, a)); break;
+    default: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<8>, a)); break;
+    }
+    h->sync_count += 1;
+    h->chain = true;
+    return MDPP_OK;
+}
+
+int64_t mdpp_sync_buffer_bytes(const mdpp_config *cfg) {
+    if (validate_config(cfg) != MDPP_OK) return -1;
+    return (int64_t)(sync_table_bytes(*cfg) + align_up(kSyncFlagBytes));
+}
+int mdpp_sync_alloc(int64_t bytes, void **dev_ptr_out, uint8_t *ipc_handle_out) {
+    if (!dev_ptr_out || bytes <= 0) return fail(MDPP_EINVAL, "mdpp_sync_alloc: bad arguments");
+    void *p = nullptr;
+    MDPP_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess && ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == MDPP_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t hd;
+        e = cudaIpcGetMemHandle(&hd, p);
+        if (e == cudaSuccess) memcpy(ipc_handle_out, &hd, sizeof hd);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(MDPP_ECUDA, "mdpp_sync_alloc: %s", cudaGetErrorString(e));
+    }
+    *dev_ptr_out = p;
+    return MDPP_OK;
+}
+int mdpp_sync_free(void *dev_ptr) {
+    if (dev_ptr) MDPP_CUDA(cudaFree(dev_ptr));
+    return MDPP_OK;
+}
+int mdpp_sync_open(const uint8_t *ipc_handle, void **peer_ptr_out) {
+    if (!ipc_handle || !peer_ptr_out) return fail(MDPP_EINVAL, "mdpp_sync_open: bad arguments");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle, sizeof hd);
+    MDPP_CUDA(cudaIpcOpenMemHandle(peer_ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return MDPP_OK;
+}
+int mdpp_sync_close(void *peer_ptr) {
+    if (peer_ptr) MDPP_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return MDPP_OK;
+}
+int mdpp_sync_attach(mdpp_handle *h, int rank, int world, void *const *bufs, int interval) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (world < 1 || world > MDPP_SYNC_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(MDPP_EINVAL, "rank %d / world %d out of range (at most %d ranks)", rank, world, MDPP_SYNC_MAX_RANKS);
+    if (interval < 0) return fail(MDPP_EINVAL, "interval must be >= 0");
+    if ((size_t)h->cfg.n_states * MDPP_Q_ROW * 4 > (size_t)MDPP_SYNC_MAX_TABLE_BYTES)
+        return fail(MDPP_EINVAL, "table of %lld states is too large for the one-shot exchange", (long long)h->cfg.n_states);
+    if (world > 1 && !bufs) return fail(MDPP_EINVAL, "bufs is NULL");
+    for (int r = 0; r < world; r++) {
+        if (world > 1 && (!bufs[r] || ((uintptr_t)bufs[r] & 255))) return fail(MDPP_EINVAL, "bufs[%d] is NULL or not 256-byte aligned", r);
+        h->sync_bufs[r] = world > 1 ? bufs[r] : nullptr;
+    }
+    h->sync_world = world;
+    h->sync_rank = rank;
+    h->sync_interval = interval;
+    return MDPP_OK;
+}
+int mdpp_q_sync_replicas(mdpp_handle *h, float *q, void *stream) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q) return fail(MDPP_EINVAL, "q is NULL");
+    h->chain = false; // the caller may have put anything on the stream since our last launch
+    int rc = q_sync_launch(h, q, (cudaStream_t)stream);
+    h->chain = false;
+    return rc;
+}
+uint64_t mdpp_sync_count(mdpp_handle *h) { return h ? h->sync_count : 0; }
+
 int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
                    const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward, void *stream) {
     if (!h) return fail(MDPP_EINVAL, "handle is NULL");
     if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
     if (car_slot < 0 || car_slot >= h->cfg.n_cars) return fail(MDPP_EINVAL, "car_slot %d out of range", car_slot);
     if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
+    if (int rc = validate_learner(lp)) return rc;
     h->chain = false; // the caller may have put anything on the stream since our last launch
     return q_env_launch(h, q, lp, car_slot, round, forced, action_out, state_idx, reward, (cudaStream_t)stream);
 }
@@ -982,14 +1104,25 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
     if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
     if ((uintptr_t)q & 31) return fail(MDPP_EINVAL, "q must be 32-byte aligned");
     if (lp->flags & MDPP_LEARN_OBSERVED) return fail(MDPP_EINVAL, "MDPP_LEARN_OBSERVED is a per-sub-step flag");
+    if (int rc = validate_learner(lp)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     h->chain = false;
     float *cur = q, *alt = h->cv.dense ? (float *)(h->ws + h->cv.qalt) : q; // dense: the table ping-pongs
     const bool frozen = (lp->flags & MDPP_LEARN_FROZEN) != 0;
     const bool fused = lp->flags == 0 && round_eligible(h);
     for (int r = 0; r < rounds; r++) {
+        if (sync_due(h, first_round + (uint64_t)r)) { // replica averaging before this round (q_sync.cuh)
+            if (cur != q) { // an odd number of pulls so far: the exchange runs on the caller's table
+                int rc = q_copy_launch(h, cur, q, s);
+                if (rc) return rc;
+                std::swap(cur, alt);
+            }
+            int rc = q_sync_launch(h, q, s);
+            if (rc) return rc;
+        }
+        const int room = sync_room(h, first_round + (uint64_t)r, rounds - r); // rounds up to the next averaging
         if (fused) { // training fast path: a whole round per launch (q_round.cuh), several while every env explores
-            if (const int n = pure_rounds_fit(h, lp, rounds - r)) {
+            if (const int n = pure_rounds_fit(h, lp, room)) {
                 int rc = q_pure_rounds_launch(h, cur, alt, lp, first_round + (uint64_t)r, n, s);
                 if (rc) return rc;
                 r += n - 1;
@@ -1005,7 +1138,7 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
                 if (rc) return rc;
                 continue;
             }
-            if (const int n = mixed_rounds_fit(h, rounds - r)) { // several such rounds in one cooperative launch
+            if (const int n = mixed_rounds_fit(h, room)) { // several such rounds in one cooperative launch
                 int rc = q_mixed_rounds_launch(h, cur, alt, lp, first_round + (uint64_t)r, n, s);
                 if (rc) return rc;
                 r += n - 1;

@@ -263,6 +263,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
 } // namespace mdpp
 #include "q_learner.cuh" // needs Control from above
 #include "q_round.cuh"
+#include "q_sync.cuh"
 namespace mdpp {
 
 // ------------------------------------------------------------------------------------------------

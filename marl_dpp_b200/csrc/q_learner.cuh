@@ -207,6 +207,7 @@ __device__ __forceinline__ bool env_substep_car(const Tabs &S, const DevCfg &cfg
                 rec.w = (rec.w & ~0xFFu) | (stalled ? 0u : run);
                 if (stalled) {
                     ea.dl_state[e] = sidx;
+                    rec.w = (rec.w & 0xFFFFu) | (episode << 16); // the episode of the detection (the reference returns it, :379-380)
                     episode = (uint32_t)lp.episodes; // frozen from now on
                 }
             }

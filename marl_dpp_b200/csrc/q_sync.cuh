@@ -1,0 +1,122 @@
+// q_sync.cuh -- Q-replica averaging across the GPUs of one node, one kernel over NVLink peer memory (sm_100a).
+//
+// every GPU trains its own replica of the Q table on its env shard; every `interval` rounds the
+// replicas are averaged.  The reference has no counterpart (one process).  For the tables of the headline
+// scenario (208 KiB) a library all-reduce is pure latency -- ncclAllReduce(AVG) measured 33 us, two whole
+// rounds -- so the exchange is ONE kernel of our own, a member of the learner's kernel chain:
+//
+//   * every rank's table lives in a peer-mapped exchange buffer (CUDA IPC; mdpp_sync_alloc / mdpp_sync_open),
+//     followed by a small flag area;
+//   * CTA b of every rank owns the same slice of the table.  It tells CTA b of every peer "my table is final"
+//     (a release store into the peer's flag area), waits for the same word from every peer, reads the slice from
+//     ALL ranks' buffers -- every load of a thread in flight at once: one NVLink round trip -- adds them in rank
+//     order and divides by the rank count, so that every rank computes the same bits;
+//   * a second handshake ("I have read your slice") precedes the only write: the slice of the own table.  Nobody
+//     overwrites data a peer may still be reading, no second buffer and no copy back.
+//
+// Flags only ever grow (the epoch of the call), so nothing is reset between calls.  One-shot: each rank pulls
+// world x table bytes, right for tables of a few MB at NVLink bandwidth; larger tables (4-5 cars) take the
+// caller's NCCL path.
+//
+// Chain membership: the kernel waits for its predecessor (the last pull: the local table is final) with
+// griddepcontrol.wait and releases its successor at once.  The next env kernel never reads the table before its
+// own griddepcontrol.wait, so a pure-exploration round runs WHILE the replicas are exchanged and the exchange
+// disappears from the critical path; the pulls of that round start after the env kernel, hence after this one.
+#pragma once
+#include "env_core.cuh"
+
+namespace mdpp {
+
+constexpr int kSyncThreads = 512, kSyncPer = 2, kSyncMaxCtas = 148, kSyncMaxRanks = MDPP_SYNC_MAX_RANKS;
+constexpr size_t kSyncFlagWords = 2u * kSyncMaxCtas * kSyncMaxRanks; // [phase][cta][rank]
+constexpr size_t kSyncFlagBytes = kSyncFlagWords * 4u;
+
+struct SyncArgs {
+    float *table[kSyncMaxRanks];    // every rank's table; [rank] is the own one
+    uint32_t *flags[kSyncMaxRanks]; // every rank's flag area
+    uint32_t rank, world, epoch;
+    uint32_t n4;                    // float4 elements of the table
+    unsigned long long timeout_ns;  // a peer that never arrives must not hang the GPU: give up, count an error
+    unsigned long long *errors;     // Control::stats[0].internal_errors
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// one phase of the handshake between the CTAs `b` of all ranks: thread t < world signals rank t and waits for it
+__device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase, uint32_t b) {
+    __syncthreads(); // everything this CTA did before (its reads of the peers' slices) is ordered before the signal
+    if (threadIdx.x < a.world) {
+        const uint32_t t = threadIdx.x;
+        const size_t slot = ((size_t)phase * kSyncMaxCtas + b) * kSyncMaxRanks;
+        __threadfence_system();
+        st_release_sys(a.flags[t] + slot + a.rank, a.epoch);
+        const uint32_t *mine = a.flags[a.rank] + slot + t;
+        const unsigned long long t0 = global_ns();
+        while ((int32_t)(ld_acquire_sys(mine) - a.epoch) < 0) {
+            if (global_ns() - t0 > a.timeout_ns) {
+                atomicAdd(a.errors, 1ull);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(kSyncThreads)
+q_sync_kernel(SyncArgs a) {
+    pdl_wait();              // the last pull has completed: the own table is final
+    pdl_launch_dependents(); // the next env kernel may run beside the exchange (it waits before it reads the table)
+    const uint32_t b = blockIdx.x;
+    sync_handshake(a, 0u, b); // every rank's table is final
+    const uint32_t base = b * (kSyncThreads * kSyncPer) + threadIdx.x;
+    float4 v[kSyncPer][WORLD];
+#pragma unroll
+    for (int k = 0; k < kSyncPer; k++) {
+        const uint32_t i = base + (uint32_t)k * kSyncThreads;
+#pragma unroll
+        for (int r = 0; r < WORLD; r++)
+            v[k][r] = i < a.n4 ? ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(a.table[r]) + i)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 m[kSyncPer];
+    const float w = (float)WORLD;
+#pragma unroll
+    for (int k = 0; k < kSyncPer; k++) { // rank order, explicit roundings: the same bits on every rank
+        float4 s = v[k][0];
+#pragma unroll
+        for (int r = 1; r < WORLD; r++) {
+            s.x = __fadd_rn(s.x, v[k][r].x);
+            s.y = __fadd_rn(s.y, v[k][r].y);
+            s.z = __fadd_rn(s.z, v[k][r].z);
+            s.w = __fadd_rn(s.w, v[k][r].w);
+        }
+        m[k] = make_float4(__fdiv_rn(s.x, w), __fdiv_rn(s.y, w), __fdiv_rn(s.z, w), __fdiv_rn(s.w, w));
+    }
+    sync_handshake(a, 1u, b); // every rank has read this slice of every table
+#pragma unroll
+    for (int k = 0; k < kSyncPer; k++) {
+        const uint32_t i = base + (uint32_t)k * kSyncThreads;
+        if (i < a.n4) reinterpret_cast<float4 *>(a.table[a.rank])[i] = m[k];
+    }
+}
+
+} // namespace mdpp

@@ -3,9 +3,17 @@
 Envs are independent, so a batch shards by contiguous env-id ranges with no data-path
 collective; the RNG is keyed by GLOBAL env id, so a shard computes exactly what the same envs
 would compute inside one big batch.  The only exchange step is the periodic averaging of the
-per-GPU Q replicas: one all-reduce over NCCL/NVLink (AVG), or SUM + scale where the backend has
-no AVG (gloo, used by the CPU tests).  The reference has no counterpart (single process).
+per-GPU Q replicas.  On one node that is ONE hand-written kernel reading every rank's table
+through NVLink peer memory (csrc/q_sync.cuh, PeerExchange below: CUDA IPC is the plumbing, the
+kernel is the product) -- a member of the learner's kernel chain, so a pure-exploration round runs
+while the replicas are exchanged.  Tables too large for the one-shot exchange, and the CPU tests
+(gloo), use a library all-reduce instead (average_).  The reference has no counterpart (single
+process).  Averaging semantics: plain mean over ALL ranks per key -- a key only some ranks have
+updated since the last exchange is pulled towards the others' value; at the batch sizes this is
+built for every rank touches every reachable key between two exchanges.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -57,3 +65,111 @@ class ReplicaSync:
             self.syncs += 1
             return True
         return False
+
+
+def merge_visited_(visited, group=None):
+    """Bitwise OR of the per-rank `visited` words (which keys have ever been updated: what the qvalue
+    file lists).  A key updated only on other ranks arrives here through the averaging with its bit
+    clear; without this merge save_qvalues would drop it.  all-gather + OR (no backend has a BOR)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return visited
+    parts = [torch.empty_like(visited) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, visited, group=group)
+    for p in parts:
+        visited |= p
+    return visited
+
+
+class _DevView:
+    """A raw device pointer as something torch.as_tensor understands (no ownership)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerExchange:
+    """This rank's exchange buffer (the Q table + the handshake flags of csrc/q_sync.cuh) and every
+    peer's buffer mapped into this process.  `q` is the table as a torch tensor [n_states, 8] float32
+    -- pass it to BatchedQLearner(q=...) and call attach(learner, interval).
+
+    PeerExchange(scenario, group)    one process per GPU: buffers exchanged as CUDA IPC handles
+                                     over the process group (all_gather_object);
+    PeerExchange.local(scenario, n)  n buffers in THIS process on the current device (tests: several
+                                     "ranks" on one GPU, each with its own handle and stream)."""
+
+    def __init__(self, scenario, group=None, device=None, _local=None):
+        from . import _lib
+        self._L = L = _lib.lib()
+        self.scenario = scenario
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        nbytes = L.mdpp_sync_buffer_bytes(C.byref(scenario.cfg))
+        if nbytes <= 0:
+            raise _lib.MdppError("invalid scenario: " + _lib.last_error())
+        if scenario.n_states * 32 > self.max_table_bytes():
+            raise _lib.MdppError("table too large for the one-shot exchange: use a library all-reduce (average_)")
+        self._own, self._opened = [], []
+        with torch.cuda.device(self.device):
+            if _local:
+                self.rank, self.world = 0, int(_local)
+                for _ in range(self.world):
+                    p = C.c_void_p()
+                    _lib.check(L.mdpp_sync_alloc(nbytes, C.byref(p), None))
+                    self._own.append(p.value)
+                self.ptrs = list(self._own)
+            else:
+                self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+                p, hd = C.c_void_p(), (C.c_uint8 * 64)()
+                _lib.check(L.mdpp_sync_alloc(nbytes, C.byref(p), hd))
+                self._own.append(p.value)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(hd), group=group)
+                self.ptrs = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.ptrs.append(p.value)
+                        continue
+                    q = C.c_void_p()
+                    _lib.check(L.mdpp_sync_open((C.c_uint8 * 64).from_buffer_copy(handles[r]), C.byref(q)))
+                    self._opened.append(q.value)
+                    self.ptrs.append(q.value)
+                dist.barrier(group=group)  # every rank has mapped every buffer before anyone uses or frees one
+        self.tables = [self._table(p) for p in (self.ptrs if _local else [self.ptrs[self.rank]])]
+        self.q = self.tables[0]
+
+    @staticmethod
+    def max_table_bytes():
+        return 148 * 512 * 2 * 16   # MDPP_SYNC_MAX_TABLE_BYTES
+
+    @classmethod
+    def local(cls, scenario, world, device=None):
+        return cls(scenario, device=device, _local=world)
+
+    def _table(self, ptr):
+        return torch.as_tensor(_DevView(ptr, (self.scenario.n_states, 8)), device=self.device)
+
+    def attach(self, learner, interval, rank=None):
+        """Bind a learner's handle: replicas are averaged before every round R > 0 with R % interval == 0
+        inside train_rounds (0 = only when sync_replicas() is called)."""
+        from . import _lib
+        rank = self.rank if rank is None else int(rank)
+        if learner.q.data_ptr() != self.ptrs[rank]:
+            raise ValueError("the learner's q must be this exchange's table (BatchedQLearner(..., q=exchange.q))")
+        arr = (C.c_void_p * self.world)(*self.ptrs)
+        _lib.check(self._L.mdpp_sync_attach(learner.env._h, rank, self.world, arr, int(interval)))
+        learner.exchange = self
+
+    def close(self):
+        for p in self._opened:
+            self._L.mdpp_sync_close(C.c_void_p(p))
+        for p in self._own:
+            self._L.mdpp_sync_free(C.c_void_p(p))
+        self._opened, self._own = [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -349,6 +349,8 @@ LEARN_FROZEN, LEARN_MODE0, LEARN_DETECT, LEARN_OBSERVED, LEARN_RANDOM_ORDER = 1,
 
 
 def learner_params(episodes, alpha=0.9, discount=0.15, model=3, seed=3, flags=0):
+    if not 0 <= int(episodes) <= 65535:
+        raise ValueError("episodes must be in 0..65535 (the per-env episode counter is 16 bits), got %r" % (episodes,))
     th, eps = epsilon_schedule(episodes, model)
     lp = MdppLearner()
     lp.alpha, lp.discount, lp.episodes, lp.seed, lp.flags = alpha, discount, episodes, seed, flags

@@ -18,6 +18,9 @@ What is recorded (all produced by reference code, none by this repo's implementa
   qrand_*.json.gz         RL.train_given_state_random_order runs, the drawn car recorded as well
                           (reference src/algorithms/qlearning.py:241-295)
   known_answers.json.gz   the SURVEY 8c known-answer probes re-derived live.
+  textfile_convert.json.gz  RL.convert_textfile / reverse_convert_textfile on qvalue files of all four
+                          block numbers and RL.convert_textfile_in_ascending_order (file written and
+                          the qvals_new it builds) (reference src/algorithms/qlearning.py:439-597)
 """
 import gzip
 import json
@@ -357,6 +360,42 @@ def gen_convert(ref):
     dump("dqn_convert", out)
 
 
+def gen_textfile_conversions(ref):
+    """The three file-conversion methods of RL (reference src/algorithms/qlearning.py:439-597), run
+    unmodified in the harness' scratch cwd on qvalue files written in the reference's own format."""
+    root = os.path.join(ref.scratch, "src/data/qvalue_files")
+    rl, _env = ref.make_rl(2)
+    out = {"cases": []}
+
+    def lines_of(golden, limit):
+        with gzip.open(os.path.join(OUT, golden + ".json.gz")) as f:
+            q = json.load(f)["qvals"]
+        return "".join("%s|%s|%s\n" % (s, a, v) for s, a, v in q[:limit])
+
+    d_text = lines_of("qrun_b2_3car_bad", 70) + lines_of("qrun_b2_2car", 50)
+    u_text = lines_of("qrun_b0_1car", 60) + "U4NxU2WzU8xU1zU5xU4|F|1.5\nU9WxU1N|T|-2.25\n"
+    odd = "D1NxD6N|S|0.5\n\nD10xD2|F|1.0\nXD3xD4zD5S|L|2.0"   # blank line, no trailing newline, near misses
+    for block, text in ((0, u_text), (1, d_text), (2, d_text), (3, u_text), (2, odd), (1, "")):
+        with open(os.path.join(root, "cv_in.txt"), "w") as f:
+            f.write(text)
+        with ref_harness.quiet():
+            rl.convert_textfile("cv_in", "cv_out", block)
+            rl.reverse_convert_textfile("cv_out", "cv_back", block)
+        out["cases"].append({"block": block, "input": text,
+                             "converted": open(os.path.join(root, "cv_out.txt")).read(),
+                             "reversed": open(os.path.join(root, "cv_back.txt")).read()})
+    # convert_textfile_in_ascending_order: others of some keys deliberately out of order, one duplicate key
+    asc_in = ("D5ExD6NzD8xD8zD1xD6|F|1.25\nD5ExD6NzD1xD6zD8xD8|F|-3.5\nD2NxD6NzD3xD6|S|0.1\n"
+              "D2NxD6NzD7xD4zD3xD6zD5xD8|L|7.0\nD2NxD6NzD3xD8zD3xD6|R|-0.75\nD2NxD6NzD3xD6|S|0.30000000000000004\n")
+    with open(os.path.join(root, "layout-3", "asc_in.txt"), "w") as f:
+        f.write(asc_in)
+    with ref_harness.quiet():
+        rl.convert_textfile_in_ascending_order("asc_in", "asc_out")
+    out["ascending"] = {"input": asc_in, "output": open(os.path.join(root, "layout-3", "asc_out.txt")).read(),
+                        "qvals_new": [[s, a, repr(v)] for (s, a), v in rl.qvals_new.items()]}
+    dump("textfile_convert", out)
+
+
 def gen_all_qrand(ref):
     R = gen_qrand
     R(ref, "b2_2car", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], False, 60, 40000, 6)
@@ -367,6 +406,10 @@ def main():
     ref = ref_harness.load()
     if "--only-qrand" in sys.argv:  # the other fixtures are unchanged
         gen_all_qrand(ref)
+        ref.close()
+        return
+    if "--only-textfiles" in sys.argv:
+        gen_textfile_conversions(ref)
         ref.close()
         return
     for b in (0, 2):
@@ -397,6 +440,7 @@ def main():
     G(ref, "b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 40, 30000, 5)
     gen_all_qrand(ref)
     gen_convert(ref)
+    gen_textfile_conversions(ref)
     ref.close()
 
 

@@ -175,6 +175,7 @@ struct orc_env {
     char **bad_tab;
     uint32_t bad_cap;
     char *bad_text;
+    int bad_shared; /* the set belongs to another env of the same batch (orc_env_share_bad_states) */
 };
 
 static uint32_t str_hash(const char *s) {
@@ -189,15 +190,32 @@ orc_env *orc_env_create(const orc_cfg *c) {
     return e;
 }
 void orc_env_destroy(orc_env *e) {
-    free(e->bad_tab);
-    free(e->bad_text);
+    if (!e->bad_shared) {
+        free(e->bad_tab);
+        free(e->bad_text);
+    }
     free(e);
 }
 
 /* reference src/env_gym.py:71-83: file lines, '' skipped; failure to open => flag False */
+/* a batch of envs reads ONE parsed bad-states set: env `e` borrows `owner`'s (which must outlive it) */
+void orc_env_share_bad_states(orc_env *e, const orc_env *owner) {
+    if (!e->bad_shared) {
+        free(e->bad_tab);
+        free(e->bad_text);
+    }
+    e->bad_on = owner->bad_on;
+    e->bad_tab = owner->bad_tab;
+    e->bad_cap = owner->bad_cap;
+    e->bad_text = owner->bad_text;
+    e->bad_shared = 1;
+}
 void orc_env_set_bad_states(orc_env *e, const char *text) {
-    free(e->bad_tab);
-    free(e->bad_text);
+    if (!e->bad_shared) {
+        free(e->bad_tab);
+        free(e->bad_text);
+    }
+    e->bad_shared = 0;
     e->bad_tab = NULL;
     e->bad_text = NULL;
     e->bad_on = 0;

@@ -24,6 +24,7 @@
 #include "mdpp_oracle.h"
 
 /* from mdpp_oracle.c */
+void orc_env_share_bad_states(orc_env *e, const orc_env *owner);
 int64_t orc_q_index(orc_q *q, const orc_state *s, int action);
 double orc_q_at(const orc_q *q, int64_t i);
 void orc_q_set_at(orc_q *q, int64_t i, double v);
@@ -43,6 +44,7 @@ typedef struct {
     int32_t *episode, *steps;
     int32_t *stall;      /* consecutive greedy 'S' at epsilon 0 (detect_deadlocks_v0, qlearning.py:347-360) */
     orc_state *dl_state; /* state flagged by the stall heuristic; pnode == ORC_NONE: none */
+    int32_t *dl_episode; /* episode in which it was flagged (the reference returns it, qlearning.py:379-380); -1: none */
     /* stats */
     uint64_t agent_steps, episodes_done, episodes_capped, explore_steps;
     int64_t reward_sum;
@@ -75,28 +77,49 @@ orc_batch *orc_batch_create(const orc_cfg *cfg, int64_t n_envs, int n_cars, cons
     b->steps = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
     b->stall = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
     b->dl_state = (orc_state *)calloc((size_t)n_envs, sizeof(orc_state));
+    b->dl_episode = (int32_t *)calloc((size_t)n_envs, sizeof(int32_t));
     for (int64_t e = 0; e < n_envs; e++) b->dl_state[e].pnode = ORC_NONE;
+    for (int64_t e = 0; e < n_envs; e++) b->dl_episode[e] = -1;
     for (int64_t e = 0; e < n_envs; e++) {
         b->envs[e] = orc_env_create(cfg);
-        orc_env_set_bad_states(b->envs[e], bad_text);
+        if (e == 0) orc_env_set_bad_states(b->envs[0], bad_text); /* parsed once, read by every env of the batch */
+        else orc_env_share_bad_states(b->envs[e], b->envs[0]);
     }
     return b;
 }
 void orc_batch_destroy(orc_batch *b) {
-    for (int64_t e = 0; e < b->n_envs; e++) orc_env_destroy(b->envs[e]);
+    for (int64_t e = b->n_envs - 1; e >= 0; e--) orc_env_destroy(b->envs[e]); /* env 0 owns the shared set: last */
     free(b->envs);
     free(b->episode);
     free(b->steps);
     free(b->stall);
     free(b->dl_state);
+    free(b->dl_episode);
     free(b);
 }
 orc_env *orc_batch_env(orc_batch *b, int64_t e) { return b->envs[e]; }
 int32_t orc_batch_episode(const orc_batch *b, int64_t e) { return b->episode[e]; }
 int32_t orc_batch_steps(const orc_batch *b, int64_t e) { return b->steps[e]; }
 const orc_state *orc_batch_deadlock_state(const orc_batch *b, int64_t e) { return &b->dl_state[e]; }
+int32_t orc_batch_deadlock_episode(const orc_batch *b, int64_t e) { return b->dl_episode[e]; }
 uint64_t orc_batch_disagreements(const orc_batch *b) { return b->disagreements; }
 uint64_t orc_batch_touched_keys(const orc_batch *b) { return b->touched_keys; }
+/* bulk view of every env for the full-size parity tests: per car (node, destination_index, done, done_count clamped
+ * to -1), then the episode and step counters */
+void orc_batch_export(const orc_batch *b, int16_t *cars4 /* [n_envs][n_cars][4] */, int32_t *episode, int32_t *steps) {
+    for (int64_t e = 0; e < b->n_envs; e++) {
+        for (int c = 0; c < b->n_cars; c++) {
+            int16_t *o = cars4 + ((size_t)e * (size_t)b->n_cars + (size_t)c) * 4;
+            int cnt = orc_env_car_done_count(b->envs[e], c);
+            o[0] = (int16_t)orc_env_car_node(b->envs[e], c);
+            o[1] = (int16_t)orc_env_car_dest_index(b->envs[e], c);
+            o[2] = (int16_t)orc_env_car_done(b->envs[e], c);
+            o[3] = (int16_t)(cnt < -1 ? -1 : cnt);
+        }
+        if (episode) episode[e] = b->episode[e];
+        if (steps) steps[e] = b->steps[e];
+    }
+}
 void orc_batch_stats(const orc_batch *b, uint64_t *out5) {
     out5[0] = b->agent_steps;
     out5[1] = b->episodes_done;
@@ -129,6 +152,7 @@ void orc_batch_reset(orc_batch *b, const uint8_t *headings, uint32_t seed, int z
         if (zero_counters) {
             b->episode[e] = 0;
             b->dl_state[e].pnode = ORC_NONE;
+            b->dl_episode[e] = -1;
         }
     }
 }
@@ -269,30 +293,46 @@ static uint32_t eps_q16_of(const orc_learner *lp, int32_t episode) {
 }
 
 typedef struct {
-    int64_t key; /* index into the oracle Q map, -1 = no update */
+    int valid;       /* this env updates a key in this sub-step */
+    int action;      /* oracle action number of the key */
+    orc_state st;    /* its state */
     float newv;
 } pending;
 
-/* One sub-step for car slot c.  q must have been created with f32 = 1.  forced: NULL or [n_envs]
- * (ACT_SKIP = own decision, else take that action as exploration).  Outputs optional.
- *
- * flags & 16: random car order (train_given_state_random_order, qlearning.py:241-295).  `slot` is then only the
- * index of the sub-step within the round (a round is n_cars sub-steps): every env draws its own car --
- * random.randint(0, n - 1) (:267) = the high half of word 0 of the Philox block (round, stream 4 + slot) scaled to
- * n_cars; a finished car means no agent-step (:268-269); the decision word is word 1 of that block; the end of the
- * episode is checked after every agent-step (:291), the headings of the next one come from word 2.  forced then
- * carries the car in its high nibble (0xF = the env's own draw) and the action in the low one (0..4, 0xE greedy,
- * 0xF own decision), so 0xFF / 0xFE keep their meaning. */
-void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot, uint64_t round, const uint8_t *forced,
-                         uint8_t *action_out, orc_state *state_out, float *reward_out) {
+/* phase 1 of a sub-step over the envs [lo, hi): every env decides and steps against the Q table as it stands.
+ * Reads the table only (orc_q_peek: no inserts), touches only its own envs and its own counters, so disjoint
+ * ranges may run on different host threads (the BFS memo of the graph must have been filled before). */
+typedef struct {
+    orc_batch *b;
+    const orc_q *q;
+    const orc_learner *lp;
+    int slot;
+    uint64_t round;
+    const uint8_t *forced;
+    uint8_t *action_out;
+    orc_state *state_out;
+    float *reward_out;
+    pending *pend;
+    int64_t lo, hi;
+    uint64_t agent_steps, explore_steps, episodes_done, episodes_capped;
+    int64_t reward_sum;
+} substep_job;
+
+static void *substep_worker(void *arg) {
+    substep_job *j = (substep_job *)arg;
+    orc_batch *b = j->b;
+    const orc_q *q = j->q;
+    const orc_learner *lp = j->lp;
+    const int slot = j->slot;
+    const uint64_t round = j->round;
+    const uint8_t *forced = j->forced;
+    pending *pend = j->pend;
     const int nc = b->n_cars;
     const int any_order = (lp->flags & 16u) != 0;
-    pending *pend = (pending *)malloc(sizeof(pending) * (size_t)b->n_envs);
-    /* phase 1: every env decides and steps against the Q table as it stands (no writes yet) */
-    for (int64_t e = 0; e < b->n_envs; e++) {
+    for (int64_t e = j->lo; e < j->hi; e++) {
         orc_env *env = b->envs[e];
         uint32_t envid = b->env_id_base + (uint32_t)e;
-        pend[e].key = -1;
+        pend[e].valid = 0;
         int a_out = ACT_SKIP;
         float r_out = 0.f;
         orc_state st;
@@ -335,7 +375,7 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot
                         if (!have || v > best) { best = v; a5 = k; have = 1; }
                     }
                 }
-                b->explore_steps += (uint64_t)explore;
+                j->explore_steps += (uint64_t)explore;
                 int stalled = 0;
                 if (lp->flags & 4u) { /* qlearning.py:347-360 */
                     if (a5 == 0 && eps_q16_of(lp, b->episode[e]) == 0) b->stall[e] += 1;
@@ -344,6 +384,7 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot
                         stalled = 1;
                         b->stall[e] = 0;
                         b->dl_state[e] = st;
+                        b->dl_episode[e] = b->episode[e];
                         b->episode[e] = lp->episodes;
                     }
                 }
@@ -365,33 +406,84 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot
                 float diff = target - qa;
                 float newv = qa + lp->alpha * diff;
                 if (!(lp->flags & 1u)) {
-                    pend[e].key = orc_q_index(q, &st, ACT5[a5]);
+                    pend[e].valid = 1;
+                    pend[e].action = ACT5[a5];
+                    pend[e].st = st;
                     pend[e].newv = newv;
                 }
                 orc_env_update_car(env, c, ns.pnode);
                 if (b->steps[e] < 0xFFFF) b->steps[e]++;
-                b->agent_steps++;
-                b->reward_sum += (int64_t)rw;
+                j->agent_steps++;
+                j->reward_sum += (int64_t)rw;
                 r_out = (float)rw;
             after_step:;
             }
         }
         live = b->episode[e] < lp->episodes || live;
-        if (live && any_order) end_of_episode_check(b, e, blk[2], &b->episodes_done, &b->episodes_capped);
-        else if (live && c == nc - 1) end_of_round(b, e, round, lp->seed, &b->episodes_done, &b->episodes_capped);
-        if (action_out) action_out[e] = (uint8_t)a_out;
-        if (state_out) state_out[e] = st;
-        if (reward_out) reward_out[e] = r_out;
+        if (live && any_order) end_of_episode_check(b, e, blk[2], &j->episodes_done, &j->episodes_capped);
+        else if (live && c == nc - 1) end_of_round(b, e, round, lp->seed, &j->episodes_done, &j->episodes_capped);
+        if (j->action_out) j->action_out[e] = (uint8_t)a_out;
+        if (j->state_out) j->state_out[e] = st;
+        if (j->reward_out) j->reward_out[e] = r_out;
+    }
+    return NULL;
+}
+
+/* host threads of phase 1 (full-size parity tests: 2^20 envs); 1 = everything on the calling thread */
+static int g_substep_threads = 1;
+void orc_batch_set_threads(int n) { g_substep_threads = n < 1 ? 1 : n > 256 ? 256 : n; }
+
+/* One sub-step for car slot c.  q must have been created with f32 = 1.  forced: NULL or [n_envs]
+ * (ACT_SKIP = own decision, else take that action as exploration).  Outputs optional.
+ *
+ * flags & 16: random car order (train_given_state_random_order, qlearning.py:241-295).  `slot` is then only the
+ * index of the sub-step within the round (a round is n_cars sub-steps): every env draws its own car --
+ * random.randint(0, n - 1) (:267) = the high half of word 0 of the Philox block (round, stream 4 + slot) scaled to
+ * n_cars; a finished car means no agent-step (:268-269); the decision word is word 1 of that block; the end of the
+ * episode is checked after every agent-step (:291), the headings of the next one come from word 2.  forced then
+ * carries the car in its high nibble (0xF = the env's own draw) and the action in the low one (0..4, 0xE greedy,
+ * 0xF own decision), so 0xFF / 0xFE keep their meaning. */
+void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot, uint64_t round, const uint8_t *forced,
+                         uint8_t *action_out, orc_state *state_out, float *reward_out) {
+    pending *pend = (pending *)malloc(sizeof(pending) * (size_t)b->n_envs);
+    /* phase 1: every env decides and steps against the Q table as it stands (no writes yet) */
+    int T = g_substep_threads;
+    if (b->n_envs < 4096) T = 1;
+    if (T > 1) /* fill the BFS memo up front: the workers only read it */
+        for (int s = 0; s < ORC_NODES; s++)
+            for (int d = 0; d < ORC_NODES; d++) orc_cfg_bfs_len(b->cfg, s, d);
+    substep_job jobs[256];
+    pthread_t tid[256];
+    for (int t = 0; t < T; t++) {
+        substep_job *j = &jobs[t];
+        memset(j, 0, sizeof *j);
+        j->b = b; j->q = q; j->lp = lp; j->slot = slot; j->round = round; j->forced = forced;
+        j->action_out = action_out; j->state_out = state_out; j->reward_out = reward_out; j->pend = pend;
+        j->lo = b->n_envs * t / T;
+        j->hi = b->n_envs * (t + 1) / T;
+        if (T == 1) substep_worker(j);
+        else pthread_create(&tid[t], NULL, substep_worker, j);
+    }
+    for (int t = 0; t < T; t++) {
+        if (T > 1) pthread_join(tid[t], NULL);
+        b->agent_steps += jobs[t].agent_steps;
+        b->explore_steps += jobs[t].explore_steps;
+        b->episodes_done += jobs[t].episodes_done;
+        b->episodes_capped += jobs[t].episodes_capped;
+        b->reward_sum += jobs[t].reward_sum;
     }
     /* phase 2: per key, the value the contributing envs computed (identical for all of them;
-     * formally the maximum) */
+     * formally the maximum).  Keys enter the map in env order, as if the envs had run one after another. */
+    int64_t *keyidx = (int64_t *)malloc(sizeof(int64_t) * (size_t)b->n_envs);
+    for (int64_t e = 0; e < b->n_envs; e++)
+        keyidx[e] = pend[e].valid ? orc_q_index(q, &pend[e].st, pend[e].action) : -1;
     int64_t nq = orc_q_size(q);
-    uint32_t *cnt = (uint32_t *)calloc((size_t)nq, sizeof(uint32_t));
-    float *val = (float *)calloc((size_t)nq, sizeof(float));
-    uint8_t *differ = (uint8_t *)calloc((size_t)nq, 1);
+    uint32_t *cnt = (uint32_t *)calloc((size_t)nq + 1, sizeof(uint32_t));
+    float *val = (float *)calloc((size_t)nq + 1, sizeof(float));
+    uint8_t *differ = (uint8_t *)calloc((size_t)nq + 1, 1);
     for (int64_t e = 0; e < b->n_envs; e++) {
-        if (pend[e].key < 0) continue;
-        const int64_t k = pend[e].key;
+        if (keyidx[e] < 0) continue;
+        const int64_t k = keyidx[e];
         if (cnt[k] == 0) val[k] = pend[e].newv;
         else if (pend[e].newv != val[k]) {
             differ[k] = 1;
@@ -408,6 +500,7 @@ void orc_batch_q_substep(orc_batch *b, orc_q *q, const orc_learner *lp, int slot
     free(cnt);
     free(val);
     free(differ);
+    free(keyidx);
     free(pend);
 }
 
@@ -496,22 +589,29 @@ uint64_t orc_bench_run(orc_bench *o, int rounds) {
  * state; live iff all-finished is reachable.  Joint index = sum_c v_c * V^c, v_c = node_local*2 + di,
  * V - 1 = finished.  Forward successors are enumerated once through the scalar env functions, then a
  * backward closure runs over the reverse adjacency.  Returns the number of live states. */
-int64_t orc_reachability(const orc_cfg *cfg, int n_cars, const int32_t *choose3, int n_local_nodes, int node_base,
-                         uint32_t *bitmap_out) {
-    const uint64_t V = 2ull * (uint64_t)n_local_nodes + 1ull;
-    uint64_t n = 1, pw[ORC_MAX_CARS];
-    for (int c = 0; c < n_cars; c++) { pw[c] = n; n *= V; }
-    const int maxs = n_cars * 5;
-    uint32_t *succ = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n * (size_t)maxs);
-    uint8_t *nsucc = (uint8_t *)calloc((size_t)n, 1);
-    orc_env *env = orc_env_create(cfg);
+typedef struct {
+    const orc_cfg *cfg;
+    int n_cars, n_local_nodes, node_base;
+    const int32_t *choose3;
+    uint64_t lo, hi, V;
+    const uint64_t *pw;
+    uint32_t *succ;
+    uint8_t *nsucc;
+} reach_job;
+
+/* forward successors of the joint states [lo, hi), through the scalar env functions */
+static void *reach_worker(void *arg) {
+    reach_job *j = (reach_job *)arg;
+    const int n_cars = j->n_cars, node_base = j->node_base, maxs = n_cars * 5;
+    const uint64_t V = j->V;
+    orc_env *env = orc_env_create(j->cfg);
     int32_t di0[ORC_MAX_CARS] = {0}, nodes0[ORC_MAX_CARS] = {0};
-    for (uint64_t idx = 0; idx < n; idx++) {
+    for (uint64_t idx = j->lo; idx < j->hi; idx++) {
         uint64_t rest = idx;
         int digit[ORC_MAX_CARS];
         orc_env_reset(env);
         orc_env_initialize_cars(env, n_cars);
-        orc_env_initialize(env, di0, nodes0, choose3);
+        orc_env_initialize(env, di0, nodes0, j->choose3);
         for (int c = 0; c < n_cars; c++) {
             digit[c] = (int)(rest % V);
             rest /= V;
@@ -529,12 +629,40 @@ int64_t orc_reachability(const orc_cfg *cfg, int n_cars, const int32_t *choose3,
                 orc_env_update_car(env, c, ns.pnode);
                 int nd = orc_env_car_done(env, c) ? (int)V - 1
                                                   : (orc_env_car_node(env, c) - node_base) * 2 + orc_env_car_dest_index(env, c);
-                succ[idx * (uint64_t)maxs + nsucc[idx]++] = (uint32_t)(idx - (uint64_t)digit[c] * pw[c] + (uint64_t)nd * pw[c]);
+                j->succ[idx * (uint64_t)maxs + j->nsucc[idx]++] =
+                    (uint32_t)(idx - (uint64_t)digit[c] * j->pw[c] + (uint64_t)nd * j->pw[c]);
                 orc_env_set_car(env, c, digit[c] / 2 + node_base, digit[c] & 1, 0, 5); /* undo */
             }
         }
     }
     orc_env_destroy(env);
+    return NULL;
+}
+
+int64_t orc_reachability(const orc_cfg *cfg, int n_cars, const int32_t *choose3, int n_local_nodes, int node_base,
+                         uint32_t *bitmap_out) {
+    const uint64_t V = 2ull * (uint64_t)n_local_nodes + 1ull;
+    uint64_t n = 1, pw[ORC_MAX_CARS];
+    for (int c = 0; c < n_cars; c++) { pw[c] = n; n *= V; }
+    const int maxs = n_cars * 5;
+    uint32_t *succ = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n * (size_t)maxs);
+    uint8_t *nsucc = (uint8_t *)calloc((size_t)n, 1);
+    {
+        int T = n < 100000 ? 1 : g_substep_threads;
+        reach_job jobs[256];
+        pthread_t tid[256];
+        for (int t = 0; t < T; t++) {
+            reach_job *j = &jobs[t];
+            j->cfg = cfg; j->n_cars = n_cars; j->n_local_nodes = n_local_nodes; j->node_base = node_base;
+            j->choose3 = choose3; j->V = V; j->pw = pw; j->succ = succ; j->nsucc = nsucc;
+            j->lo = n * (uint64_t)t / (uint64_t)T;
+            j->hi = n * (uint64_t)(t + 1) / (uint64_t)T;
+            if (T == 1) reach_worker(j);
+            else pthread_create(&tid[t], NULL, reach_worker, j);
+        }
+        if (T > 1)
+            for (int t = 0; t < T; t++) pthread_join(tid[t], NULL);
+    }
     /* reverse adjacency (CSR) + backward BFS from the all-finished state */
     uint64_t *start = (uint64_t *)calloc((size_t)n + 2, sizeof(uint64_t));
     for (uint64_t i = 0; i < n; i++)

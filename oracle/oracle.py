@@ -352,6 +352,15 @@ def _batch_lib():
     return L
 
 
+def set_threads(n=None):
+    """Host threads of the batched learner's per-env phase and of the reachability enumeration (the
+    full-size parity tests use every core; results do not depend on the thread count)."""
+    L = _batch_lib()
+    L.orc_batch_set_threads.restype = None
+    L.orc_batch_set_threads.argtypes = [C.c_int]
+    L.orc_batch_set_threads(int(n or os.cpu_count() or 1))
+
+
 class Batch:
     """N scalar oracle envs driven with the batch semantics of DESIGN.md (CPU, for checking)."""
 
@@ -426,6 +435,19 @@ class Batch:
         h = _batch_lib().orc_batch_env(self.h, e)
         return [(L.orc_env_car_node(h, i), L.orc_env_car_dest_index(h, i), L.orc_env_car_done(h, i),
                  L.orc_env_car_done_count(h, i)) for i in range(self.n_cars)]
+
+    def export(self):
+        """Every env at once: cars int16 [n_envs, n_cars, 4] = (node, destination_index, done,
+        done_count clamped to -1), episode int32 [n_envs], steps int32 [n_envs]."""
+        np = self.np
+        L = _batch_lib()
+        L.orc_batch_export.restype = None
+        L.orc_batch_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        cars = np.empty((self.n_envs, self.n_cars, 4), np.int16)
+        episode, steps = np.empty(self.n_envs, np.int32), np.empty(self.n_envs, np.int32)
+        L.orc_batch_export(self.h, cars.ctypes.data_as(C.c_void_p), episode.ctypes.data_as(C.c_void_p),
+                           steps.ctypes.data_as(C.c_void_p))
+        return cars, episode, steps
 
     def counters(self, e):
         L = _batch_lib()

@@ -78,3 +78,40 @@ def test_configuration_accepts_the_references_object():
     assert c.action_dictionary == Configuration(d).action_dictionary
     assert c.no_node_list == ["D9N", "D9E", "D9S", "D9W"] and c.initial_states == d["initial_states"]
     assert Configuration.coerce(c) is c and Configuration.coerce(d).layout["no_box_list"] == ["D9"]
+
+
+def test_block_renaming_matches_reference(tmp_path):
+    """convert_textfile / reverse_convert_textfile (reference src/algorithms/qlearning.py:457-597):
+    byte-identical files on every block number, incl. blank lines and a missing final newline."""
+    g = load_golden("textfile_convert")
+    assert sorted({c["block"] for c in g["cases"]}) == [0, 1, 2, 3]
+    for c in g["cases"]:
+        (tmp_path / "in.txt").write_text(c["input"])
+        formats.convert_textfile("in", "out", c["block"], directory=str(tmp_path))
+        assert (tmp_path / "out.txt").read_text() == c["converted"]
+        formats.convert_textfile("out", "back", c["block"], directory=str(tmp_path), reverse=True)
+        assert (tmp_path / "back.txt").read_text() == c["reversed"]
+        # the renaming is a bijection on box names: undoing it restores every line
+        assert c["reversed"].split("\n")[:len(c["input"].split("\n"))] == c["input"].split("\n")
+    with pytest.raises(KeyError):
+        formats.block_box_map(4)
+
+
+def test_plugin_file_conversions_match_reference(tmp_path):
+    """The same three methods through the RL plugin (they need no device)."""
+    from marl_dpp_b200.algorithms.qlearning import RL
+    g = load_golden("textfile_convert")
+    rl = RL(input_dim=80, output_dim=5, cars=5, sess=None, env_config=layout_3[2], qvalue_dir=str(tmp_path),
+            bad_states="")
+    a = g["ascending"]
+    (tmp_path / "asc_in.txt").write_text(a["input"])
+    rl.convert_textfile_in_ascending_order("asc_in", "asc_out")
+    assert (tmp_path / "asc_out.txt").read_text() == a["output"]
+    assert [[s, act, repr(v)] for (s, act), v in rl.qvals_new.items()] == a["qvals_new"]
+    c = g["cases"][2]
+    (tmp_path / "cv_in.txt").write_text(c["input"])
+    rl.convert_textfile("cv_in", "cv_out", c["block"])
+    rl.reverse_convert_textfile("cv_out", "cv_back", c["block"])
+    assert (tmp_path / "cv_out.txt").read_text() == c["converted"]
+    assert (tmp_path / "cv_back.txt").read_text() == c["reversed"]
+    assert formats.ascend_state("D5ExD6NzD8xD8zD1xD6") == load_golden("known_answers")["ascend"]

@@ -149,13 +149,17 @@ def test_learner_flags_match_oracle(scratch):
     L = orc._batch_lib()
     L.orc_batch_deadlock_state.restype = orc.C.POINTER(orc.State)
     L.orc_batch_deadlock_state.argtypes = [orc.C.c_void_p, orc.C.c_int64]
+    L.orc_batch_deadlock_episode.restype = orc.C.c_int32
+    L.orc_batch_deadlock_episode.argtypes = [orc.C.c_void_p, orc.C.c_int64]
+    flag_episode = (env.records[:, 3].cpu().numpy().astype(np.int64) >> 16) & 0xFFFF
     n_flagged = 0
     for e in range(n):
         st = L.orc_batch_deadlock_state(ob.h, e).contents
         if st.pnode == orc.ORC_NONE:
-            assert flagged[e] == -1
+            assert flagged[e] == -1 and L.orc_batch_deadlock_episode(ob.h, e) == -1
         else:
             assert sc.decode(int(flagged[e])) == orc.state_str(st)
+            assert flag_episode[e] == L.orc_batch_deadlock_episode(ob.h, e)   # the value detect_deadlocks_v0 returns
             n_flagged += 1
     q = lr.q.cpu().numpy()
     for s, a, v in [x for x in oq.items() if x[1] != "B"]:
@@ -182,9 +186,17 @@ def test_rl_detect_deadlocks_writes_bad_states(scratch):
     rl = RL(**settings.params, sess=None, env_config=ed, n_envs=512, step_cap=300)
     res = rl.detect_deadlocks_v0(20, '0', '0', ["D5", "D6", "D8"], 3, [0, 0, 0], [[2, 1, 0], [0, 2, 0], [2, 1, 0]])
     after = set(formats.read_bad_states(path))
-    assert res in (19, False) and before <= after
+    assert before <= after
     for s in rl.detected_deadlocks:
         assert formats.strip_headings(s) in after
+    # reference return value (qlearning.py:350-382): the detection episode (epsilon is 0 only in the last
+    # 1 % of the episodes: 19 of 20) when a new state was flagged, the last episode index otherwise
+    assert res == 19 and (rl.detected_deadlocks or after == before)
+    # bad_states passed as TEXT with no file on disk: the file is created instead of raising
+    os.remove(path)
+    rl = RL(**settings.params, sess=None, env_config=ed, n_envs=512, step_cap=300, bad_states="\n".join(sorted(before)) + "\n")
+    res = rl.detect_deadlocks_v0(20, '0', '0', ["D5", "D6", "D8"], 3, [0, 0, 0], [[2, 1, 0], [0, 2, 0], [2, 1, 0]])
+    assert res == 19 and (not rl.detected_deadlocks or before <= set(formats.read_bad_states(path)))
 
 
 @pytest.mark.parametrize("name", ["qrun_b0_1car", "qrun_b2_2car"])

@@ -336,3 +336,42 @@ def test_batch_contributors_of_a_key_agree(case):
     assert b.stats()["agent_steps"] > 10000
     assert b.touched_keys() > 0
     assert b.disagreements() == 0
+
+
+def test_batch_oracle_is_thread_count_invariant():
+    """The full-size GPU parity tests run the oracle's per-env phase on every host core: the table (values AND
+    insertion order), the envs, the counters and the reachability bitmap must not depend on the thread count."""
+    import marl_dpp_b200 as m
+    from oracle import oracle as orc
+    boxes, idx, choose = m.layout_3[2]["initial_states"][0]
+    bad = bad_states_text(2)
+    runs = []
+    try:
+        for threads in (1, 4):
+            orc.set_threads(threads)
+            ob = orc.Batch(orc.Config(m.layout_3[2]), 6000, boxes, idx, choose, bad, 30)
+            ob.reset(seed=13)
+            oq = orc.QTable(f32=True)
+            olp = orc.learner(3, seed=13)          # greedy decisions from episode 1 on
+            for r in range(60):
+                ob.q_round(oq, olp, r)
+            cars, ep, steps = ob.export()
+            runs.append((oq.items(), cars.copy(), ep.copy(), steps.copy(), ob.stats(), ob.touched_keys(),
+                         ob.disagreements()))
+        a, b = runs
+        assert a[0] == b[0] and a[4] == b[4] and a[5] == b[5] and a[6] == b[6] == 0
+        for i in (1, 2, 3):
+            assert (a[i] == b[i]).all()
+        assert 0 < a[4]["explore_steps"] < a[4]["agent_steps"] and a[4]["episodes_done"] > 6000
+        # export agrees with the per-env accessors
+        for e in (0, 17, 5999):
+            assert [tuple(int(x) for x in c[:3]) for c in a[1][e]] == [c[:3] for c in ob.env_cars(e)]
+            assert (int(a[2][e]), int(a[3][e])) == ob.counters(e)
+        choose3 = [[0, 1, 0], [1, 0, 0], [2, 1, 0]]
+        orc.set_threads(1)
+        w1, l1 = orc.reachability(orc.Config(m.layout_3[2]), 3, choose3)
+        orc.set_threads(3)
+        w3, l3 = orc.reachability(orc.Config(m.layout_3[2]), 3, choose3)
+        assert l1 == l3 and (w1 == w3).all()
+    finally:
+        orc.set_threads(1)

@@ -32,6 +32,9 @@ def _worker(rank, world, port, out_dir):
             q += 0.01 * (rank + 1)              # stands in for a round of local learning
             if sync.step(q, rounds_done):
                 history.append(rounds_done)
+        vis = torch.tensor([1 << rank, 0, 3 * rank, 16], dtype=torch.int32)   # updated-key bits of this rank
+        parallel.merge_visited_(vis)
+        np.save(os.path.join(out_dir, "vis%d.npy" % rank), vis.numpy())
         base, n = parallel.shard_env_ids(1 << 10, rank, world)
         np.save(os.path.join(out_dir, "q%d.npy" % rank), q.numpy())
         np.save(os.path.join(out_dir, "meta%d.npy" % rank), np.array(history + [base, n, sync.syncs]))
@@ -57,6 +60,8 @@ def test_replica_averaging_two_ranks(tmp_path):
         assert list(meta[r][:3]) == [4, 8, 12] and meta[r][-1] == 3
         assert (meta[r][3], meta[r][4]) == (r * 1024, 1024)
     np.testing.assert_array_equal(q[0], q[1])
+    for r in range(world):   # bitwise OR over the ranks
+        assert np.load(tmp_path / ("vis%d.npy" % r)).tolist() == [3, 0, 3, 16]
 
 
 def test_env_id_partitions_cover_exactly_once():
