@@ -612,18 +612,26 @@ def main():
         # -dd precompute of the headline scenario (2 cars) and of the 4-car scenario: reachability bitmap
         for tag, scn in (("2car", sc), ("4car", sc4)):
             envd = BatchedEnv(scn, 1024, device=dev, seed=7)
-            envd.deadlock_reachability()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            bm, sweeps = envd.deadlock_reachability()
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
             joint = (2 * scn.n_local_nodes + 1) ** scn.n_cars
+            entry = {"joint_states": joint}
+            for method in ("bfs", "sweep"):
+                envd.deadlock_reachability(method=method)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                bm, count = envd.deadlock_reachability(method=method)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                entry[method] = {"ms": dt * 1e3, "levels" if method == "bfs" else "sweeps": count}
             live = int(sum(int((bm[i:i + (1 << 22)].view(torch.uint8).to(torch.int16).unsqueeze(1)
                                 >> torch.arange(8, device=dev, dtype=torch.int16) & 1).sum())
                            for i in range(0, bm.numel(), 1 << 22)))
-            aux["dd_reachability_" + tag] = {"joint_states": joint, "live_states": live, "sweeps": sweeps,
-                                             "ms": dt * 1e3, "joint_states_per_s": joint * sweeps / dt}
+            entry["live_states"] = live
+            # roofline of the search: per live state one bit set in the result and one in a frontier, per examined
+            # predecessor one result-bit probe (4-byte sector reads in L2); reported as states and probes per second
+            entry["bfs_live_states_per_s"] = live / (entry["bfs"]["ms"] * 1e-3)
+            entry["note"] = ("bfs = backward breadth-first search, one cooperative launch, host wall clock incl. the "
+                             "scratch memset and the final 8-byte read-back; sweep = forward sweeps to the fixpoint")
+            aux["dd_reachability_" + tag] = entry
             del envd, bm
         # config 5 point: DQN feed, 2^24 envs, (convert(s), action, convert(s'), reward, mask(s')) per agent-step
         n5 = 1 << 24

@@ -247,6 +247,10 @@ int mdpp_sync_attach(mdpp_handle *h, int rank, int world, void *const *bufs /*HO
 int mdpp_q_sync_replicas(mdpp_handle *h, float *q /*DEV, == bufs[rank]*/, void *stream);
 /* number of replica averagings launched through this handle so far */
 uint64_t mdpp_sync_count(mdpp_handle *h);
+/* Fewer GPUs than ranks (tests): the averaging of ALL ranks of a group whose handles live in this process, as one
+ * cooperative launch that runs every rank's slices with the same code, handshakes included.  (Kernels that wait
+ * on one another must never be separate launches on one GPU.)  handles[r] must be attached as rank r of `world`. */
+int mdpp_sync_emulate(mdpp_handle *const *handles, int world, void *stream);
 
 /* ---- DQN feed: the env-facing half of the noisy double DQN's collection loop (reference
  * src/algorithms/dqn_open_source.py:490-526); the MLP stays in PyTorch.  observe = encodestate(car, 1)
@@ -271,6 +275,15 @@ int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *a
  * sweeps until a fixpoint; *sweeps_out (host) receives the sweep count. */
 int64_t mdpp_joint_state_count(const mdpp_config *cfg);
 int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap /*DEV*/, int32_t *sweeps_out, void *stream);
+/* The same bitmap, found backwards: a level-synchronous breadth-first search from "all cars finished" over reverse
+ * moves, each candidate predecessor checked with the legal filter, in ONE cooperative launch with a device-side
+ * end test (csrc/reach.cuh).  Every live state is expanded once, so the whole search costs about one sweep of the
+ * function above.  For joint spaces below 2^32 states (mdpp_deadlock_scratch_bytes returns 0 otherwise); scratch:
+ * caller-owned device memory of mdpp_deadlock_scratch_bytes(cfg) bytes, 16-byte aligned.  Synchronous;
+ * *levels_out (host) receives the number of search levels. */
+int64_t mdpp_deadlock_scratch_bytes(const mdpp_config *cfg);
+int mdpp_deadlock_reachability_bfs(mdpp_handle *h, uint32_t *reach_bitmap /*DEV*/, void *scratch /*DEV*/,
+                                   int64_t scratch_bytes, int32_t *levels_out, void *stream);
 
 /* ---- state-id codec (for the qvalue .txt format, reference src/algorithms/qlearning.py:159-185) */
 /* decode: state id -> primary node, destination node, others as (src box18, dst box18) pairs in the

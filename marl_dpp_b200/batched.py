@@ -133,18 +133,31 @@ class BatchedEnv:
         with torch.cuda.device(self.device):
             _lib.check(self._L.mdpp_update_car(self._h, car, _ptr(nodes), _stream()))
 
-    def deadlock_reachability(self):
+    def deadlock_reachability(self, method="auto"):
         """-dd precompute: bitmap (int32 words, bit j = joint state j can still reach "all cars
-        finished") over the joint state space, and the number of sweeps the fixpoint took.
-        Joint index = sum_c v_c * V^c, v_c = node_local*2 + destination_index, V-1 = finished."""
+        finished") over the joint state space, and the number of sweeps / search levels it took.
+        Joint index = sum_c v_c * V^c, v_c = node_local*2 + destination_index, V-1 = finished.
+        method: "bfs" = backward breadth-first search in one cooperative launch (csrc/reach.cuh),
+        "sweep" = forward sweeps to a fixpoint (the direct restatement of the definition),
+        "auto" = bfs wherever joint indices fit 32 bits."""
         n = self._L.mdpp_joint_state_count(C.byref(self.scenario.cfg))
         if n <= 0:
             raise _lib.MdppError("joint state space too large: " + _lib.last_error())
         bitmap = torch.empty((n + 31) // 32, dtype=torch.int32, device=self.device)
-        sweeps = C.c_int32()
+        count = C.c_int32()
+        nscratch = self._L.mdpp_deadlock_scratch_bytes(C.byref(self.scenario.cfg))
+        if method == "auto":
+            method = "bfs" if nscratch > 0 else "sweep"
         with torch.cuda.device(self.device):
-            _lib.check(self._L.mdpp_deadlock_reachability(self._h, _ptr(bitmap), C.byref(sweeps), _stream()))
-        return bitmap, int(sweeps.value)
+            if method == "bfs":
+                scratch = torch.empty(nscratch, dtype=torch.uint8, device=self.device)
+                _lib.check(self._L.mdpp_deadlock_reachability_bfs(self._h, _ptr(bitmap), _ptr(scratch), nscratch,
+                                                                  C.byref(count), _stream()))
+            elif method == "sweep":
+                _lib.check(self._L.mdpp_deadlock_reachability(self._h, _ptr(bitmap), C.byref(count), _stream()))
+            else:
+                raise ValueError("unknown method %r" % (method,))
+        return bitmap, int(count.value)
 
     def joint_index(self, cars):
         """cars: [(node name or None for finished, destination_index)] -> joint state index."""

@@ -110,6 +110,8 @@ struct mdpp_handle {
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool k1_rounds;         // MDPP_K1_ROUNDS=1: rounds with greedy decisions through the fused K0 / K1 pair as well
     bool mixed_rounds;      // rounds with greedy decisions: several per cooperative launch (MDPP_MIXED_ROUNDS=0: sub-step kernels)
+    bool resident_rounds;   // ... with the table resident in every CTA's shared memory (MDPP_RESIDENT_ROUNDS=0: q_rounds_mixed_kernel)
+    int resident_ok;        // -1 unknown, 0 does not fit / not co-resident, 1 ok
     int coop_ok;            // -1 unknown, 0 no cooperative launch / not co-resident, 1 ok
     uint32_t barrier_base;  // value of the grid barrier's counter once everything launched so far has run
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
@@ -319,6 +321,8 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->k1_rounds = getenv("MDPP_K1_ROUNDS") && atoi(getenv("MDPP_K1_ROUNDS")) != 0;
     h->mixed_rounds = !(getenv("MDPP_MIXED_ROUNDS") && atoi(getenv("MDPP_MIXED_ROUNDS")) == 0);
     h->coop_ok = -1;
+    h->resident_rounds = !(getenv("MDPP_RESIDENT_ROUNDS") && atoi(getenv("MDPP_RESIDENT_ROUNDS")) == 0);
+    h->resident_ok = -1;
     h->barrier_base = 0;
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
@@ -958,6 +962,78 @@ static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const
     return MDPP_OK;
 }
 
+// n rounds WITH greedy decisions, the table resident in shared memory (q_rounds_resident_kernel): updated in place.
+static size_t resident_smem_bytes(const mdpp_handle *h) {
+    const size_t tabs = ((h->cfg.n_cars == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>)) + 15) & ~(size_t)15;
+    const size_t marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
+    return tabs + ((marks + 15) / 16) * 16 + ((marks * 4 + 15) / 16) * 16;
+}
+static int resident_rounds_fit(mdpp_handle *h, int want) {
+    if (!h->mixed_rounds || !h->resident_rounds || want < 1) return 0;
+    if (h->resident_ok < 0) {
+        h->resident_ok = 0;
+        int dev = 0, coop = 0, per_sm = 0;
+        const void *fn = h->cfg.n_cars == 1 ? (const void *)q_rounds_resident_kernel<1> : (const void *)q_rounds_resident_kernel<2>;
+        const size_t smem = resident_smem_bytes(h), marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
+        if (marks < 65536 && smem <= (size_t)227 * 1024 && h->cv.regions * (size_t)h->cv.words_per_cta >= 3 * (size_t)h->cv.words_per_cta &&
+            cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess &&
+            coop && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kRoundThreads, smem) == cudaSuccess &&
+            (int64_t)per_sm * h->sm_count >= (int64_t)round_ctas(h))
+            h->resident_ok = 1;
+        else
+            cudaGetLastError(); // clear: q_rounds_mixed_kernel or the sub-step kernels take over
+    }
+    return h->resident_ok == 1 ? std::min(want, 16) : 0;
+}
+static int q_resident_rounds_launch(mdpp_handle *h, float *cur, const mdpp_learner *lp, uint64_t round, int n, cudaStream_t s) {
+    const int nc = h->cfg.n_cars;
+    h->ep_bound += n;
+    RoundArgs ra{};
+    ra.recs = recs_of(h);
+    ra.n_envs = (uint32_t)h->n_envs;
+    ra.env_id_base = h->env_id_base;
+    ra.round = round;
+    ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
+    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    ra.words_per_cta = h->cv.words_per_cta;
+    ra.cta_slots = h->cv.cta_slots;
+    ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
+    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.n_states = (uint32_t)h->cfg.n_states;
+    const unsigned grid = round_ctas(h);
+    ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / grid);
+    ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
+    ra.n_rounds = (uint32_t)n;
+    ResidentArgs rx{};
+    rx.barrier = (uint32_t *)(h->ws + h->cv.barrier);
+    rx.barrier_base = h->barrier_base;
+    rx.q = cur;
+    rx.scratch = (float *)(h->ws + h->cv.qalt);
+    rx.gbits = (uint32_t *)(h->ws + h->cv.gbits);
+    const Marks mk = marks_of(h);
+    rx.sinfo = mk.sinfo;
+    rx.visited = mk.visited;
+    rx.n_marks = (uint32_t)((size_t)h->cfg.n_states * MDPP_N_ACT);
+    rx.words = h->cv.words_per_cta;
+    rx.list_cap = (ra.map_bytes / 6u) & ~3u;
+    if (const char *e = getenv("MDPP_RESIDENT_LIST_CAP")) rx.list_cap = std::min<uint32_t>(rx.list_cap, (uint32_t)atoi(e) & ~3u); // tests: force the overflow path
+    rx.alpha = lp->alpha;
+    rx.discount = lp->discount;
+    MDPP_CUDA(cudaMemsetAsync(rx.gbits, 0, (size_t)3 * rx.words * 4, s)); // the three mark bitmaps start clear
+    const size_t smem = resident_smem_bytes(h);
+    mdpp_learner lpv = *lp;
+    Control *ctl = control_of(h);
+    void *args[] = {(void *)&h->dev, (void *)&lpv, (void *)&ra, (void *)&rx, (void *)&ctl};
+    const void *fn = nc == 1 ? (const void *)q_rounds_resident_kernel<1> : (const void *)q_rounds_resident_kernel<2>;
+    MDPP_LAUNCH(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRoundThreads), args, smem, s));
+    // one barrier per sub-step, one more whenever a sub-step overflows the list: the host cannot know how many there
+    // were, so the kernel is told its base and the next launch gets a base beyond anything this one can have used
+    h->barrier_base += (uint32_t)(2 * n * nc) * grid;
+    h->chain = false; // launched in plain stream order; what follows must not overlap it either
+    return MDPP_OK;
+}
+
 static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStream_t s) {
     const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
@@ -978,10 +1054,7 @@ static int sync_room(const mdpp_handle *h, uint64_t round, int want) {
     const uint64_t left = (uint64_t)h->sync_interval - round % (uint64_t)h->sync_interval;
     return (int)std::min<uint64_t>((uint64_t)want, left);
 }
-static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
-    if (h->sync_world <= 1) return MDPP_OK;
-    if ((void *)q != h->sync_bufs[h->sync_rank])
-        return fail(MDPP_EINVAL, "replica averaging: q must be the table of this rank's exchange buffer");
+static SyncArgs sync_args(mdpp_handle *h, uint32_t epoch) {
     SyncArgs a{};
     const size_t tb = sync_table_bytes(h->cfg);
     for (int r = 0; r < h->sync_world; r++) {
@@ -990,12 +1063,22 @@ static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
     }
     a.rank = (uint32_t)h->sync_rank;
     a.world = (uint32_t)h->sync_world;
-    a.epoch = ++h->sync_epoch;
+    a.epoch = epoch;
     a.n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     a.timeout_ns = 2000000000ull;
     a.errors = (unsigned long long *)&control_of(h)->stats[0].internal_errors;
-    const unsigned grid = (a.n4 + kSyncThreads * kSyncPer - 1) / (kSyncThreads * kSyncPer);
-    LearnLaunch ll(h, grid, s, kSyncThreads);
+    return a;
+}
+static unsigned sync_ctas(const mdpp_handle *h) {
+    const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
+    return (n4 + kSyncThreads * kSyncPer - 1) / (kSyncThreads * kSyncPer);
+}
+static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
+    if (h->sync_world <= 1) return MDPP_OK;
+    if ((void *)q != h->sync_bufs[h->sync_rank])
+        return fail(MDPP_EINVAL, "replica averaging: q must be the table of this rank's exchange buffer");
+    const SyncArgs a = sync_args(h, ++h->sync_epoch);
+    LearnLaunch ll(h, sync_ctas(h), s, kSyncThreads);
     switch (h->sync_world) {
     case 2: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<2>, a)); break;
     case 3: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<3>, a)); break;
@@ -1007,6 +1090,41 @@ static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
     }
     h->sync_count += 1;
     h->chain = true;
+    return MDPP_OK;
+}
+
+// All ranks of a group attached in this process: one cooperative launch (q_sync_group_kernel).
+int mdpp_sync_emulate(mdpp_handle *const *handles, int world, void *stream) {
+    if (!handles || world < 2 || world > MDPP_SYNC_MAX_RANKS) return fail(MDPP_EINVAL, "mdpp_sync_emulate: bad arguments");
+    SyncGroupArgs g{};
+    for (int r = 0; r < world; r++) {
+        mdpp_handle *h = handles[r];
+        if (!h || h->sync_world != world || h->sync_rank != r) return fail(MDPP_EINVAL, "handle %d is not attached as rank %d of %d", r, r, world);
+        if (h->cfg.n_states != handles[0]->cfg.n_states) return fail(MDPP_EINVAL, "the ranks' tables differ in size");
+        g.r[r] = sync_args(h, ++h->sync_epoch);
+        h->sync_count += 1;
+        h->launches += 1;
+        h->chain = false;
+    }
+    g.ctas_per_rank = sync_ctas(handles[0]);
+    const unsigned grid = g.ctas_per_rank * (unsigned)world;
+    const void *fn = nullptr;
+    switch (world) {
+    case 2: fn = (const void *)q_sync_group_kernel<2>; break;
+    case 3: fn = (const void *)q_sync_group_kernel<3>; break;
+    case 4: fn = (const void *)q_sync_group_kernel<4>; break;
+    case 5: fn = (const void *)q_sync_group_kernel<5>; break;
+    case 6: fn = (const void *)q_sync_group_kernel<6>; break;
+    case 7: fn = (const void *)q_sync_group_kernel<7>; break;
+    default: fn = (const void *)q_sync_group_kernel<8>; break;
+    }
+    int dev = 0, per_sm = 0, sms = 0;
+    MDPP_CUDA(cudaGetDevice(&dev));
+    MDPP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MDPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSyncThreads, 0));
+    if ((unsigned)(per_sm * sms) < grid) return fail(MDPP_EINVAL, "the group's %u CTAs cannot be co-resident on this device", grid);
+    void *args[] = {(void *)&g};
+    MDPP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kSyncThreads), args, 0, (cudaStream_t)stream));
     return MDPP_OK;
 }
 
@@ -1138,6 +1256,17 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
                 if (rc) return rc;
                 continue;
             }
+            if (const int n = resident_rounds_fit(h, room)) { // several such rounds in one cooperative launch, table in shared memory
+                if (cur != q) { // the kernel updates the caller's table in place
+                    int rc = q_copy_launch(h, cur, q, s);
+                    if (rc) return rc;
+                    std::swap(cur, alt);
+                }
+                int rc = q_resident_rounds_launch(h, cur, lp, first_round + (uint64_t)r, n, s);
+                if (rc) return rc;
+                r += n - 1;
+                continue;
+            }
             if (const int n = mixed_rounds_fit(h, room)) { // several such rounds in one cooperative launch
                 int rc = q_mixed_rounds_launch(h, cur, alt, lp, first_round + (uint64_t)r, n, s);
                 if (rc) return rc;
@@ -1255,6 +1384,83 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *
         if (sweeps > 100000) return fail(MDPP_ECUDA, "reachability did not converge");
     }
     if (sweeps_out) *sweeps_out = sweeps;
+    return MDPP_OK;
+}
+
+// ---- the same bitmap by a backward breadth-first search in one cooperative launch (reach.cuh) ------------------
+int64_t mdpp_deadlock_scratch_bytes(const mdpp_config *cfg) {
+    const int64_t n = mdpp_joint_state_count(cfg);
+    if (n <= 0 || n >= (int64_t)1 << 32) return 0; // 32-bit joint indices only: the sweeps cover the rest
+    return (int64_t)(2 * (((size_t)n + 31) / 32) * 4 + 256);
+}
+
+extern "C++" {
+template <int NC>
+static int reach_bfs_launch(mdpp_handle *h, ReachArgs &ra, cudaStream_t s, unsigned *grid_out) {
+    const size_t smem = sizeof(ReachSmem<NC>);
+    const void *fn = (const void *)reach_bfs_kernel<NC>;
+    int per_sm = 0, coop = 0, dev = 0;
+    MDPP_CUDA(cudaGetDevice(&dev));
+    MDPP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return fail(MDPP_ECUDA, "cooperative launch is not available on this device");
+    MDPP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MDPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kReachThreads, smem));
+    if (per_sm < 1) return fail(MDPP_ECUDA, "reach_bfs_kernel does not fit an SM");
+    const unsigned chunks = (ra.words + kReachChunkWords - 1) / kReachChunkWords;
+    const unsigned grid = std::max(1u, std::min((unsigned)(per_sm * h->sm_count), chunks));
+    void *args[] = {(void *)&ra};
+    MDPP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kReachThreads), args, smem, s));
+    *grid_out = grid;
+    return MDPP_OK;
+}
+} // extern "C++"
+
+int mdpp_deadlock_reachability_bfs(mdpp_handle *h, uint32_t *reach_bitmap, void *scratch, int64_t scratch_bytes,
+                                   int32_t *levels_out, void *stream) {
+    if (!h || !reach_bitmap || !scratch) return fail(MDPP_EINVAL, "handle / bitmap / scratch is NULL");
+    const int64_t need = mdpp_deadlock_scratch_bytes(&h->cfg);
+    if (need == 0) return fail(MDPP_EINVAL, "joint state space too large for 32-bit indices: use mdpp_deadlock_reachability");
+    if (scratch_bytes < need || ((uintptr_t)scratch & 15)) return fail(MDPP_EWORKSPACE, "scratch of %lld B (16-byte aligned) required", (long long)need);
+    const int64_t n = mdpp_joint_state_count(&h->cfg);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t words = ((size_t)n + 31) / 32;
+    ReachArgs ra{};
+    ra.reach = reach_bitmap;
+    ra.front[0] = (uint32_t *)scratch;
+    ra.front[1] = ra.front[0] + words;
+    ra.counts = ra.front[1] + words;
+    ra.levels_out = ra.counts + 4;
+    ra.errors = ra.counts + 5;
+    ra.barrier = (uint32_t *)(h->ws + h->cv.barrier);
+    ra.barrier_base = h->barrier_base;
+    ra.words = (uint32_t)words;
+    ra.n_joint = (uint32_t)n;
+    ra.V = 2u * (uint32_t)h->cfg.n_local_nodes + 1u;
+    ra.node_base = (uint32_t)h->dev.node_base;
+    ra.parking_node = (uint32_t)h->cfg.parking_node;
+    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    MDPP_CUDA(cudaMemsetAsync(reach_bitmap, 0, words * 4, s));
+    MDPP_CUDA(cudaMemsetAsync(scratch, 0, (size_t)need, s));
+    reach_seed_kernel<<<1, 32, 0, s>>>(reach_bitmap, ra.front[0], (uint32_t)(n - 1));
+    MDPP_CUDA(cudaGetLastError());
+    unsigned grid = 0;
+    int rc;
+    switch (h->cfg.n_cars) {
+    case 1: rc = reach_bfs_launch<1>(h, ra, s, &grid); break;
+    case 2: rc = reach_bfs_launch<2>(h, ra, s, &grid); break;
+    case 3: rc = reach_bfs_launch<3>(h, ra, s, &grid); break;
+    case 4: rc = reach_bfs_launch<4>(h, ra, s, &grid); break;
+    default: rc = reach_bfs_launch<5>(h, ra, s, &grid); break;
+    }
+    if (rc) return rc;
+    uint32_t res[2] = {0u, 0u}; // levels, reverse-table overflows
+    MDPP_CUDA(cudaMemcpyAsync(res, ra.levels_out, 8, cudaMemcpyDeviceToHost, s));
+    MDPP_CUDA(cudaStreamSynchronize(s));
+    h->barrier_base += res[0] * grid; // one grid barrier per level
+    h->chain = false;
+    if (res[1]) return fail(MDPP_ECUDA, "reverse move table overflow (%u values): raise kRevSlots", res[1]);
+    if (levels_out) *levels_out = (int32_t)res[0];
     return MDPP_OK;
 }
 

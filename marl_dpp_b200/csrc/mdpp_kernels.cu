@@ -681,4 +681,5 @@ reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t n_joint, u
 
 } // namespace mdpp
 
+#include "reach.cuh"
 #include "mdpp_api.inl"

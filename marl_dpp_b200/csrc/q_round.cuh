@@ -68,7 +68,8 @@ enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
 // One agent-step of car C on the unpacked record.  `cars` is committed (ghost counters of encodestate, the
 // move) unless the car is parked.  Returns kStepDone with the compact key (state * 5 + action) when a key was touched.
 // CG: the table changes while the kernel runs (q_rounds_mixed_kernel): coherent greedy reads (ldcg_row).
-template <int NC, int C, bool CG = false>
+// TQ: the table is resident in shared memory as compact keys (q_now[state * 5 + action], q_rounds_resident_kernel).
+template <int NC, int C, bool CG = false, bool TQ = false>
 __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
                                               const RoundArgs &ra, uint64_t &cars, uint32_t word, uint32_t eps16,
                                               bool allow_greedy, uint32_t &key, bool &moved, bool &explore,
@@ -129,7 +130,10 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
     } else {
         if (!allow_greedy) return kStepDefer; // the snapshot of this sub-step does not exist yet
         float qs[MDPP_Q_ROW];
-        if constexpr (CG) {
+        if constexpr (TQ) {
+#pragma unroll
+            for (int k = 0; k < MDPP_N_ACT; k++) qs[k] = q_now[sidx * MDPP_N_ACT + k];
+        } else if constexpr (CG) {
             ldcg_row(q_now + (size_t)sidx * MDPP_Q_ROW, qs);
         } else {
             pdl_wait();
@@ -734,6 +738,268 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
         }
     }
     if ((threadIdx.x & 31u) == 0 && touched_total)
+        atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
+                  (unsigned long long)touched_total);
+    flush_counts<true>(cnt, S.cc, 0u, ctl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rounds WITH greedy decisions, the table RESIDENT in every CTA's shared memory (replaces q_rounds_mixed_kernel
+// wherever the table fits; that kernel stays as the fallback and for A/B runs, MDPP_RESIDENT_ROUNDS=0).
+//
+// ncu on q_rounds_mixed_kernel: 30.5 us per round at epsilon 0.5, top stall "barrier"; ~4 us of every sub-step went
+// into flush -> grid barrier -> pull by 8 warps per CTA (148-slice OR + L2 round trips) -> grid barrier, and the
+// greedy lanes gathered hot table rows through L1/L2.  Here every CTA keeps its own copy of the table, compact
+// (state * 5 + action, 133 KB for the headline scenario), so
+//   * a greedy lane reads its row from shared memory;
+//   * the marks of a sub-step are OR-ed by every CTA into ONE global bitmap (RED.OR of its non-zero words: a few
+//     hundred per CTA), followed by the ONLY grid barrier of the sub-step;
+//   * every CTA then applies the whole pull to its own copy (redundantly: ~2400 updates over 1024 threads): new
+//     values are computed from the untouched copy into a list -- which lives in the byte map's storage, free at
+//     that point -- and written after a CTA barrier, so every update sees the snapshot;
+//   * the global table is written once, at the end of the launch (each CTA a slice of its copy).
+// The bitmap is triple-buffered: sub-step i ORs into buffer i % 3 and, after its barrier, CTA 0 clears buffer
+// (i + 2) % 3 -- last read before every CTA arrived at that barrier, next written after the following one.
+// Overflow of the list (more marked keys in one sub-step than fit the map's storage; never at the headline
+// scenario's ~2400) is handled exactly: every CTA sees the same count, and all of them switch to a pull through
+// global memory for that sub-step (each CTA its share of the bitmap words, values to a scratch table, one more
+// grid barrier, copies refreshed from the scratch).
+// Same arithmetic in the same order as the sub-step kernels: bit-identical tables, records and counters.
+// ------------------------------------------------------------------------------------------------
+struct ResidentArgs {
+    uint32_t *barrier;        // the grid barrier's counter and its value at kernel start
+    uint32_t barrier_base;
+    float *q;                 // the table: rows of MDPP_Q_ROW floats, read at the start, written at the end
+    float *scratch;           // [n_marks] floats: new values of the overflow path
+    uint32_t *gbits;          // [3][words] global mark bitmaps (compact keys), zero at kernel start
+    const uint32_t *sinfo;
+    uint32_t *visited;
+    uint32_t n_marks, words, list_cap;
+    float alpha, discount;
+};
+
+template <int NC, int C>
+__device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const DevCfg &cfg, const LearnArgs &lp,
+                                                  const RoundArgs &ra, const float *tq, uint64_t round, uint8_t *map,
+                                                  uint32_t t0, uint32_t t1, StepCounts &cnt) {
+    constexpr uint32_t n_warps = kRoundThreads / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t t = t0 + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
+    while (t < t1) {
+        const uint32_t e = t * 32u + lane, tn = t + n_warps;
+        uint4 rec_next = make_uint4(0u, 0u, 0u, 0u);
+        if (tn < t1 && tn * 32u + lane < ra.n_envs) rec_next = ra.recs[tn * 32u + lane];
+        uint32_t episode = rec.z & 0xFFFFu;
+        const bool live = (int32_t)episode < lp.episodes;
+        if (e < ra.n_envs && live) {
+            uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            uint32_t steps = rec.z >> 16;
+            const uint32_t env = ra.env_id_base + e;
+            uint32_t eps16 = lp.eps_q16[0];
+            if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
+            uint32_t word;
+            if (C == 0) { // one Philox block per env and round: word c belongs to car c
+                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+                word = p.x;
+                if (NC > 1) ra.rng_words[e] = p.y;
+            } else {
+                word = ra.rng_words[e];
+            }
+            uint32_t key;
+            bool moved, explore;
+            if (round_car_step<NC, C, false, true>(S, cfg, ra.tabs, ra, cars, word, eps16, true, key, moved, explore, tq) == kStepDone)
+                map[key] = 1;
+            steps += moved;
+            cnt.steps += moved;
+            cnt.explore += explore;
+            steps = steps > 0xFFFFu ? 0xFFFFu : steps;
+            if (C == NC - 1) { // end of the round-robin round (qlearning.py:233)
+                bool finished = all_done<NC>(cars);
+                bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+                if (finished || capped) {
+                    cnt.episodes += 1;
+                    cnt.capped += capped;
+                    episode = episode + 1;
+                    cnt.max_episode = max(cnt.max_episode, episode);
+                    steps = 0;
+                    rec.w &= ~0xFFu;
+                    cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+                }
+            }
+            rec.x = (uint32_t)cars;
+            rec.y = (uint32_t)(cars >> 32);
+            rec.z = (episode & 0xFFFFu) | (steps << 16);
+            ra.recs[e] = rec;
+        }
+        rec = rec_next;
+        t = tn;
+    }
+}
+
+// bytes -> bits of the CTA's map, OR-ed into the global bitmap (non-zero words only); the map is cleared
+__device__ __forceinline__ void resident_flush(uint8_t *map, uint32_t map_bytes, uint32_t words, uint32_t *gbits) {
+    uint4 *map4 = reinterpret_cast<uint4 *>(map);
+    const uint32_t n16 = map_bytes >> 4;
+    for (uint32_t wd = threadIdx.x; wd < words; wd += kRoundThreads) {
+        uint32_t bits = 0;
+        if (2u * wd < n16) {
+            const uint4 lo = map4[2u * wd];
+            bits = ((lo.x * 0x01020408u) >> 24) | (((lo.y * 0x01020408u) >> 24) << 4) |
+                   (((lo.z * 0x01020408u) >> 24) << 8) | (((lo.w * 0x01020408u) >> 24) << 12);
+            map4[2u * wd] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (2u * wd + 1u < n16) {
+            const uint4 hi = map4[2u * wd + 1u];
+            bits |= (((hi.x * 0x01020408u) >> 24) << 16) | (((hi.y * 0x01020408u) >> 24) << 20) |
+                    (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
+            map4[2u * wd + 1u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (bits) atomicOr(gbits + wd, bits);
+    }
+}
+
+// the new value of compact key m from the CTA's copy of the table (the snapshot of this sub-step)
+__device__ __forceinline__ float resident_value(const float *tq, const uint32_t *__restrict__ sinfo, uint32_t m,
+                                                uint32_t n_states, float alpha, float discount, uint32_t &key8) {
+    const uint32_t s = m / MDPP_N_ACT, a = m - s * MDPP_N_ACT;
+    const uint32_t info = __ldg(sinfo + s);
+    const uint32_t s2 = td_successor(s, info, a, n_states);
+    const uint32_t i2 = __ldg(sinfo + s2);
+    float ns[MDPP_Q_ROW];
+#pragma unroll
+    for (int k = 0; k < MDPP_N_ACT; k++) ns[k] = tq[s2 * MDPP_N_ACT + k];
+#pragma unroll
+    for (int k = MDPP_N_ACT; k < MDPP_Q_ROW; k++) ns[k] = 0.f;
+    key8 = s * MDPP_Q_ROW + a;
+    return td_update(info, i2, ns, tq[m], alpha, discount);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kRoundThreads, 1)
+q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx, Control *ctl) {
+    static_assert(NC >= 1 && NC <= 2, "built for 1- and 2-car tables");
+    extern __shared__ uint4 smem_dyn[];
+    RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
+    constexpr uint32_t kTabBytes = (sizeof(RoundSmem<NC>) + 15u) & ~15u;
+    uint8_t *map = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes;
+    float *tq = reinterpret_cast<float *>(map + ra.map_bytes);       // [n_marks] the table, compact keys
+    // the pull's list of (key, new value) reuses the map's storage: values first (4-byte aligned), then 16-bit keys
+    float *lvals = reinterpret_cast<float *>(map);
+    uint16_t *lkeys = reinterpret_cast<uint16_t *>(map + 4u * rx.list_cap);
+    __shared__ uint32_t list_count;
+    const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
+    const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
+    {
+        stage_step_tabs<NC, kRoundThreads>(S, ra.tabs);
+        uint4 *m4 = reinterpret_cast<uint4 *>(map);
+        for (uint32_t i = threadIdx.x; i < (ra.map_bytes >> 4); i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t m = threadIdx.x; m < rx.n_marks; m += kRoundThreads) {
+            const uint32_t s = m / MDPP_N_ACT;
+            tq[m] = rx.q[(size_t)s * MDPP_Q_ROW + (m - s * MDPP_N_ACT)];
+        }
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; list_count = 0u; }
+    }
+    __syncthreads();
+    StepCounts cnt;
+    uint32_t touched_total = 0, sub = 0, bar = rx.barrier_base;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t r = 0; r < ra.n_rounds; r++) {
+        const uint64_t round = ra.round + r;
+#pragma unroll
+        for (int c = 0; c < NC; c++, sub++) {
+            uint32_t *gb = rx.gbits + (size_t)(sub % 3u) * rx.words;
+            if (c == 0) resident_env_pass<NC, 0>(S, cfg, lp, ra, tq, round, map, t0, t1, cnt);
+            else resident_env_pass<NC, (NC > 1 ? 1 : 0)>(S, cfg, lp, ra, tq, round, map, t0, t1, cnt);
+            __syncthreads();
+            resident_flush(map, ra.map_bytes, rx.words, gb);
+            grid_barrier(rx.barrier, bar += gridDim.x);
+            // ---- the pull of this sub-step, applied to the CTA's own copy ----
+            if (blockIdx.x == 0) { // the buffer of the previous sub-step: everybody finished reading it before this barrier
+                uint32_t *old = rx.gbits + (size_t)((sub + 2u) % 3u) * rx.words;
+                for (uint32_t wd = threadIdx.x; wd < rx.words; wd += kRoundThreads) old[wd] = 0u;
+            }
+            for (uint32_t w0 = 0; w0 < rx.words; w0 += kRoundThreads) {
+                const uint32_t wd = w0 + threadIdx.x;
+                uint32_t bits = wd < rx.words ? __ldcg(gb + wd) : 0u;
+                const bool mine = wd % gridDim.x == blockIdx.x; // visited bits and the touched count: once per word
+                if (mine) touched_total += (uint32_t)__popc(bits);
+                while (__any_sync(0xFFFFFFFFu, bits != 0u)) {
+                    const bool have = bits != 0u;
+                    uint32_t m = 0, key8 = 0;
+                    float v = 0.f;
+                    if (have) {
+                        const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u;
+                        bits &= bits - 1u;
+                        m = wd * 32u + bit;
+                        v = resident_value(tq, rx.sinfo, min(m, rx.n_marks - 1u), ra.n_states, rx.alpha, rx.discount, key8);
+                        if (mine) mark_visited(rx.visited, key8);
+                    }
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, have);
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&list_count, (uint32_t)__popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    if (have && slot < rx.list_cap) {
+                        lvals[slot] = v;
+                        lkeys[slot] = (uint16_t)m;
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t n_list = list_count;
+            if (n_list <= rx.list_cap) {
+                for (uint32_t i = threadIdx.x; i < n_list; i += kRoundThreads) tq[lkeys[i]] = lvals[i];
+                __syncthreads();
+            } else {
+                // overflow (the same count in every CTA): this sub-step's pull through global memory.  CTA b owns the
+                // words w with w % G == b, computes their keys' values from its intact copy into the scratch table,
+                // and after one more grid barrier every CTA refreshes the marked keys of its copy from there.
+                for (uint32_t wd = blockIdx.x; wd < rx.words; wd += gridDim.x) {
+                    const uint32_t bits = __ldcg(gb + wd);
+                    if ((bits >> lane) & 1u) {
+                        if (threadIdx.x < 32u) {
+                            uint32_t key8;
+                            const uint32_t m = wd * 32u + lane;
+                            rx.scratch[m] = resident_value(tq, rx.sinfo, min(m, rx.n_marks - 1u), ra.n_states, rx.alpha, rx.discount, key8);
+                        }
+                    }
+                }
+                grid_barrier(rx.barrier, bar += gridDim.x);
+                for (uint32_t wd = threadIdx.x; wd < rx.words; wd += kRoundThreads) {
+                    uint32_t bits = __ldcg(gb + wd);
+                    while (bits) {
+                        const uint32_t m = wd * 32u + (uint32_t)__ffs((int)bits) - 1u;
+                        bits &= bits - 1u;
+                        if (m < rx.n_marks) tq[m] = __ldcg(rx.scratch + m);
+                    }
+                }
+                __syncthreads();
+            }
+            // the list overwrote the map's storage: clear what it used before the next pass marks again
+            {
+                uint4 *m4 = reinterpret_cast<uint4 *>(map);
+                const uint32_t used = min(n_list, rx.list_cap);
+                const uint32_t v16 = (used * 4u + 15u) >> 4, k0 = (4u * rx.list_cap) >> 4, k16 = (used * 2u + 15u) >> 4;
+                for (uint32_t i = threadIdx.x; i < v16; i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+                for (uint32_t i = threadIdx.x; i < k16; i += kRoundThreads) m4[k0 + i] = make_uint4(0u, 0u, 0u, 0u);
+                if (threadIdx.x == 0) list_count = 0u;
+            }
+            __syncthreads();
+        }
+    }
+    // the table goes home: CTA b writes the b-th slice of its copy (all copies are identical)
+    {
+        const uint32_t per = (rx.n_marks + gridDim.x - 1u) / gridDim.x;
+        const uint32_t m0 = blockIdx.x * per, m1 = min(m0 + per, rx.n_marks);
+        for (uint32_t m = m0 + threadIdx.x; m < m1; m += kRoundThreads) {
+            const uint32_t s = m / MDPP_N_ACT;
+            rx.q[(size_t)s * MDPP_Q_ROW + (m - s * MDPP_N_ACT)] = tq[m];
+        }
+    }
+    touched_total = __reduce_add_sync(0xFFFFFFFFu, touched_total);
+    if (lane == 0 && touched_total)
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
                   (unsigned long long)touched_total);
     flush_counts<true>(cnt, S.cc, 0u, ctl);

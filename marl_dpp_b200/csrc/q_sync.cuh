@@ -80,12 +80,9 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
     __syncthreads();
 }
 
+// the exchange of slice `b` as rank a.rank
 template <int WORLD>
-__global__ void __launch_bounds__(kSyncThreads)
-q_sync_kernel(SyncArgs a) {
-    pdl_wait();              // the last pull has completed: the own table is final
-    pdl_launch_dependents(); // the next env kernel may run beside the exchange (it waits before it reads the table)
-    const uint32_t b = blockIdx.x;
+__device__ __forceinline__ void sync_slice(const SyncArgs &a, uint32_t b) {
     sync_handshake(a, 0u, b); // every rank's table is final
     const uint32_t base = b * (kSyncThreads * kSyncPer) + threadIdx.x;
     float4 v[kSyncPer][WORLD];
@@ -117,6 +114,29 @@ q_sync_kernel(SyncArgs a) {
         const uint32_t i = base + (uint32_t)k * kSyncThreads;
         if (i < a.n4) reinterpret_cast<float4 *>(a.table[a.rank])[i] = m[k];
     }
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(kSyncThreads)
+q_sync_kernel(SyncArgs a) {
+    pdl_wait();              // the last pull has completed: the own table is final
+    pdl_launch_dependents(); // the next env kernel may run beside the exchange (it waits before it reads the table)
+    sync_slice<WORLD>(a, blockIdx.x);
+}
+
+// Every rank of a group that lives in ONE process on ONE GPU, as a single cooperative launch (all CTAs co-resident
+// by construction): CTA x is slice x % ctas_per_rank of rank x / ctas_per_rank and runs the very code a rank's own
+// kernel runs, handshakes included.  Kernels that wait on one another must not be separate launches on one GPU
+// (nothing guarantees that they run at the same time), so this is how the protocol is exercised where there are
+// fewer GPUs than ranks (mdpp_sync_emulate; tests/test_gpu_sync.py).
+struct SyncGroupArgs {
+    SyncArgs r[kSyncMaxRanks];
+    uint32_t ctas_per_rank;
+};
+template <int WORLD>
+__global__ void __launch_bounds__(kSyncThreads)
+q_sync_group_kernel(SyncGroupArgs g) {
+    sync_slice<WORLD>(g.r[blockIdx.x / g.ctas_per_rank], blockIdx.x % g.ctas_per_rank);
 }
 
 } // namespace mdpp

@@ -95,8 +95,10 @@ class PeerExchange:
 
     PeerExchange(scenario, group)    one process per GPU: buffers exchanged as CUDA IPC handles
                                      over the process group (all_gather_object);
-    PeerExchange.local(scenario, n)  n buffers in THIS process on the current device (tests: several
-                                     "ranks" on one GPU, each with its own handle and stream)."""
+    PeerExchange.local(scenario, n)  n buffers in THIS process on the current device (tests with fewer
+                                     GPUs than ranks: emulate() runs the exchange of all n ranks as ONE
+                                     cooperative launch; saturate_flags() turns a buffer into a peer that
+                                     never has to be waited for)."""
 
     def __init__(self, scenario, group=None, device=None, _local=None):
         from . import _lib
@@ -160,6 +162,19 @@ class PeerExchange:
         arr = (C.c_void_p * self.world)(*self.ptrs)
         _lib.check(self._L.mdpp_sync_attach(learner.env._h, rank, self.world, arr, int(interval)))
         learner.exchange = self
+
+    def flags(self, r):
+        """The handshake flag words of local buffer r as an int32 tensor (tests)."""
+        off = ((self.scenario.n_states * 32 + 255) // 256) * 256
+        return torch.as_tensor(_DevView(self.ptrs[r] + off, (2 * 148 * 8,), "<i4"), device=self.device)
+
+    def emulate(self, learners):
+        """One exchange of ALL ranks of a local group as a single cooperative launch on the current
+        stream (learners[r] attached as rank r)."""
+        from . import _lib
+        arr = (C.c_void_p * self.world)(*[lr.env._h.value for lr in learners])
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_sync_emulate(arr, self.world, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def close(self):
         for p in self._opened:

@@ -24,11 +24,13 @@ def test_reachability_bitmap_bit_exact(block, boxes, idx, choose):
     from oracle import oracle as orc
     sc = m.Scenario(m.layout_3[block], boxes, idx, choose)
     env = BatchedEnv(sc, 32)
-    bitmap, sweeps = env.deadlock_reachability()
-    got = bitmap.cpu().numpy().view(np.uint32)
     want, live = orc.reachability(orc.Config(m.layout_3[block]), len(boxes), choose, sc.n_local_nodes, sc.node_base)
-    assert np.array_equal(got, want)
-    assert int(sum(bin(int(w)).count("1") for w in got)) == live and sweeps >= 2
+    # both implementations: the backward breadth-first search (one cooperative launch) and the forward sweeps
+    for method in ("bfs", "sweep", "bfs"):
+        bitmap, sweeps = env.deadlock_reachability(method=method)
+        got = bitmap.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), method
+        assert int(sum(bin(int(w)).count("1") for w in got)) == live and sweeps >= 2
     V = 2 * sc.n_local_nodes + 1
     goal = V ** len(boxes) - 1
     assert (int(got[goal >> 5]) >> (goal & 31)) & 1
@@ -47,9 +49,9 @@ def test_reachability_four_cars_properties_and_bad_states_cross_report():
     choose = [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]]
     sc = m.Scenario(m.layout_3[2], boxes, idx, choose)
     env = BatchedEnv(sc, 32)
-    b1, s1 = env.deadlock_reachability()
-    b2, s2 = env.deadlock_reachability()
-    assert torch.equal(b1, b2)       # the fixpoint is unique; the sweep count depends on propagation order
+    b1, s1 = env.deadlock_reachability(method="sweep")
+    b2, s2 = env.deadlock_reachability(method="bfs")
+    assert torch.equal(b1, b2)       # the fixpoint is unique: forward sweeps == backward search
     assert 2 <= s1 <= 200 and 2 <= s2 <= 200
     words = b1.cpu().numpy().view(np.uint32)
     live = int(np.unpackbits(words.view(np.uint8)).sum())

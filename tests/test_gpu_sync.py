@@ -1,11 +1,16 @@
 """GPU: Q-replica averaging by the library's own peer-memory kernel (csrc/q_sync.cuh).
 
 No reference counterpart, so the oracle is the NumPy restatement of the definition: float32 sum of the
-ranks' tables in rank order, divided by the rank count -- the same bits on every rank.  The kernel only
-needs device pointers to every rank's exchange buffer, so on ONE GPU several "ranks" (one handle, one
-stream each) of one process exercise the complete protocol: handshake flags, epochs, slice ownership,
-the averaging points inside mdpp_q_train_rounds and the copy home of an odd ping-pong parity.  The
-multi-process form (CUDA IPC between one process per GPU) runs when the box has 2+ GPUs.
+ranks' tables in rank order, divided by the rank count -- the same bits on every rank.
+
+Kernels that wait on one another must never be separate launches on one GPU, so with ONE GPU:
+  * the protocol between ranks (both handshakes, epochs, slice ownership, arithmetic) runs as the
+    library's cooperative group launch, every rank's slices with the code its own kernel runs
+    (mdpp_sync_emulate);
+  * the exchange INSIDE mdpp_q_train_rounds (averaging points, multi-round launches that stop at them,
+    the copy home of an odd ping-pong parity, the overlap with the next env kernel) runs with real
+    rank kernels against peers whose flags are saturated, i.e. peers that never have to be waited for.
+One process per GPU with CUDA IPC between them runs when the box has 2+ GPUs.
 """
 import os
 import socket
@@ -39,36 +44,36 @@ def _scenario(m, block=2, cap=300):
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_explicit_exchange_equals_mean_in_rank_order(world):
-    """`world` replicas trained on different env shards, then two exchanges: every table equals the float32
-    mean in rank order, bit for bit and on every rank; the second exchange (equal inputs) is the identity."""
+def test_exchange_protocol_equals_mean_in_rank_order(world):
+    """`world` replicas trained on different env shards, then two exchanges (one cooperative launch each): every
+    table equals the float32 mean in rank order, bit for bit and on every rank; the second exchange (equal
+    inputs, next epoch of the flags) is the identity."""
     m, BatchedEnv, BatchedQLearner, PeerExchange = _mods()
     sc = _scenario(m)
-    n = 512                                         # 16 tiles per rank: all ranks' kernels are co-resident on one GPU
+    n = 2048
     ex = PeerExchange.local(sc, world)
-    streams = [torch.cuda.Stream() for _ in range(world)]
     lrs = []
     for r in range(world):
-        with torch.cuda.stream(streams[r]):
-            env = BatchedEnv(sc, n, env_id_base=r * n, seed=3)
-            lr = BatchedQLearner(env, episodes=5000, seed=3, q=ex.tables[r])
-            ex.attach(lr, 0, rank=r)
-            lr.train_rounds(6 + r)                  # different amounts of learning per rank
-            lrs.append(lr)
+        env = BatchedEnv(sc, n, env_id_base=r * n, seed=3)
+        lr = BatchedQLearner(env, episodes=5000, seed=3, q=ex.tables[r])
+        ex.attach(lr, 0, rank=r)
+        lr.train_rounds(6 + r)                  # different amounts of learning per rank
+        lrs.append(lr)
     torch.cuda.synchronize()
     before = [t.cpu().numpy().copy() for t in ex.tables]
     assert any(not np.array_equal(before[0], b) for b in before[1:])
     for rep in range(2):
-        for r in range(world):                      # every rank's kernel is enqueued before anyone waits
-            with torch.cuda.stream(streams[r]):
-                lrs[r].sync_replicas()
+        ex.emulate(lrs)
         torch.cuda.synchronize()
         want = _mean_in_rank_order(before)
         for r in range(world):
             assert np.array_equal(ex.tables[r].cpu().numpy(), want), (rep, r)
         before = [want] * world
-    for lr in lrs:
+    for r, lr in enumerate(lrs):
         assert lr.env.stats()["internal_errors"] == 0 and lr.sync_count() == 2
+        fl = ex.flags(r).cpu().numpy().reshape(2, 148, 8)
+        ctas = (sc.n_states * 2 + 1023) // 1024
+        assert (fl[:, :ctas, :world] == 2).all() and (fl[:, ctas:, :] == 0).all()   # both phases, every slice, epoch 2
     ex2 = PeerExchange.local(sc, 2)
     with pytest.raises(ValueError):                 # a learner whose table is not the exchange's
         ex2.attach(BatchedQLearner(BatchedEnv(sc, 64)), 4, rank=0)
@@ -77,59 +82,54 @@ def test_explicit_exchange_equals_mean_in_rank_order(world):
     ex2.close()
 
 
-@pytest.mark.parametrize("block,interval,chunks", [(2, 4, (10, 1, 5)), (0, 3, (7, 4)), (2, 1, (6,)), (0, 1, (5,))])
-def test_interval_exchange_inside_train_rounds(block, interval, chunks):
-    """mdpp_q_train_rounds averages before every round R > 0 with R % interval == 0, inside its kernel chain
-    (multi-round launches stop at the averaging points; the 1-car table is copied home when its ping-pong
-    parity is odd).  Against the same shards trained round by round on plain handles with the NumPy mean
-    applied at the same rounds: tables, records and counters bit-identical."""
+@pytest.mark.parametrize("block,interval,chunks,rank,world",
+                         [(2, 4, (10, 1, 5), 0, 2), (0, 3, (7, 4), 1, 3), (2, 1, (6,), 2, 3), (0, 1, (5,), 0, 2),
+                          (2, 64, (64, 64, 8), 1, 2)])
+def test_interval_exchange_inside_train_rounds(block, interval, chunks, rank, world):
+    """mdpp_q_train_rounds averages before every round R > 0 with R % interval == 0 as a member of its kernel
+    chain (multi-round launches stop at the averaging points; the 1-car table is copied home when its ping-pong
+    parity is odd; the next env kernel is released while the exchange runs).  One real rank at the BASELINE-like
+    launch shape (148 CTAs) among peers that hold constant tables and never have to be waited for, against a
+    plain handle trained round by round with the NumPy mean applied at the same rounds: bit-identical."""
     m, BatchedEnv, BatchedQLearner, PeerExchange = _mods()
     sc = _scenario(m, block)
-    # Two "ranks" share ONE GPU here: a rank's env kernel, resident and waiting for its exchange, holds SMs the
-    # other rank's kernels (incl. a 16-CTA cluster, which needs 16 free SMs in one GPC) must still find.  8 tiles per
-    # rank keep that always possible; one process per GPU has no such coupling.
-    world, n = 2, 256
+    n = 1 << 15
     ex = PeerExchange.local(sc, world)
-    streams = [torch.cuda.Stream() for _ in range(world)]
-    lrs = []
+    g = torch.Generator().manual_seed(11)
     for r in range(world):
-        with torch.cuda.stream(streams[r]):
-            env = BatchedEnv(sc, n, env_id_base=r * n, seed=5)
-            lr = BatchedQLearner(env, episodes=5000, seed=5, q=ex.tables[r])
-            ex.attach(lr, interval, rank=r)
-            lrs.append(lr)
-    torch.cuda.synchronize()
+        ex.flags(r).fill_(0x7FFFFFFF)              # saturated: no rank ever waits for another
+        if r != rank:
+            t = torch.randn((sc.n_states, 8), generator=g) * 50.0
+            t[:, 5:] = 0.0
+            ex.tables[r].copy_(t)
+    env = BatchedEnv(sc, n, env_id_base=rank * n, seed=5)
+    lr = BatchedQLearner(env, episodes=5000, seed=5, q=ex.tables[rank])
+    ex.attach(lr, interval, rank=rank)
     for k in chunks:
-        for r in range(world):
-            with torch.cuda.stream(streams[r]):
-                lrs[r].train_rounds(k)
-        torch.cuda.synchronize()
+        lr.train_rounds(k)
+    torch.cuda.synchronize()
     total = sum(chunks)
-    # restatement: plain handles, one round at a time, NumPy mean at the averaging points
-    refs = []
-    for r in range(world):
-        env = BatchedEnv(sc, n, env_id_base=r * n, seed=5)
-        refs.append(BatchedQLearner(env, episodes=5000, seed=5))
+    ref = BatchedQLearner(BatchedEnv(sc, n, env_id_base=rank * n, seed=5), episodes=5000, seed=5)
+    peers = [t.cpu().numpy() for t in ex.tables]
     n_sync = 0
     for R in range(total):
         if R > 0 and R % interval == 0:
-            mean = torch.from_numpy(_mean_in_rank_order([x.q.cpu().numpy() for x in refs])).cuda()
-            for x in refs:
-                x.q.copy_(mean)
+            tabs = [ref.q.cpu().numpy() if r == rank else peers[r] for r in range(world)]
+            ref.q.copy_(torch.from_numpy(_mean_in_rank_order(tabs)).cuda())
             n_sync += 1
-        for x in refs:
-            x.train_rounds(1)
+        ref.train_rounds(1)
     torch.cuda.synchronize()
-    for r in range(world):
-        assert torch.equal(lrs[r].q, refs[r].q), r
-        assert torch.equal(lrs[r].env.records, refs[r].env.records), r
-        a, b = lrs[r].env.stats(), refs[r].env.stats()
-        assert a["internal_errors"] == 0
-        for key in ("agent_steps", "q_updates", "episodes_done", "touched_keys"):
-            assert a[key] == b[key], key
-        assert lrs[r].sync_count() == n_sync
-    assert n_sync == (total - 1) // interval
-    del lrs, refs
+    assert torch.equal(lr.q, ref.q)
+    assert torch.equal(lr.env.records, ref.env.records)
+    a, b = lr.env.stats(), ref.env.stats()
+    assert a["internal_errors"] == 0
+    for key in ("agent_steps", "q_updates", "episodes_done", "touched_keys"):
+        assert a[key] == b[key], key
+    assert lr.sync_count() == n_sync == (total - 1) // interval
+    for r in range(world):                          # the peers' tables were only read
+        if r != rank:
+            assert np.array_equal(ex.tables[r].cpu().numpy(), peers[r])
+    del lr, ref
     ex.close()
 
 
