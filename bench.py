@@ -685,8 +685,10 @@ def main():
             "q_updates_per_s": total_upd / (dev_ms * 1e-3),
             "wall_s_timed_region": wall,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(lr.params),
-                    "d2h_bytes_per_step": 64 * 128,
-                    "call": "BatchedQLearner.train_rounds_host(1) -> mdpp_q_train_rounds_host (sync each step)"},
+                    "d2h_bytes_per_step": 80,
+                    "call": "BatchedQLearner.train_rounds_host(1) -> mdpp_q_train_rounds_host: learner parameters from "
+                            "host memory in, the counters of the step back in host memory (stored there by the "
+                            "device, the host waits for them) before the call returns, every step"},
             "gpu_launches": gpu_launches * world,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "aux": aux,
         }

@@ -267,6 +267,40 @@ int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *a
                  uint8_t *done /*DEV*/, uint8_t *status /*DEV*/, int auto_reset, uint64_t round, uint32_t seed,
                  void *stream);
 
+/* ---- DQN replay memory and Double-DQN target (reference src/algorithms/dqn_open_source.py:315-394) -----------
+ * remember() + the `deque(OrderedSet(self.memory))` de-duplication of replay() (:322,:343): the memory is a SET of
+ * samples (state, action, next state, reward).  Batched, the compact key  state id * 5 + action  enumerates the
+ * samples (next state and reward follow from the key under legal actions), so the set is one presence bit per key
+ * plus a per-key payload, all caller-owned device arrays: present [n_keys/32] u32 (zeroed by the caller), m_next
+ * [n_keys] u32, m_reward [n_keys] f32, m_mask [n_keys] u8 (give_mask of the next state as a bit mask), m_features
+ * [n_keys][160] u8 = convert(state) | convert(next_state) or NULL, counters [3] u64 (zeroed by the caller): samples
+ * offered, new keys, duplicates whose stored (next state, reward) differ (distinct tuples in the reference; none
+ * occur under legal actions).  n_keys = n_states * 5 rounded up to a multiple of 32.
+ *   mdpp_replay_insert   one sub-step's samples (the outputs of mdpp_dqn_observe / mdpp_dqn_act; status[i] != 0 = no
+ *                        sample) into the set: one atomic OR per sample, the first of a key stores the payload;
+ *   mdpp_replay_compact  list[rank] = the keys of the set in ascending order, *count = its size (the minibatch
+ *                        of :347-350 is `count choose batch_size` positions of that list);
+ *   mdpp_dqn_target      Double-DQN target (:360-379) of a minibatch: a* = argmax of the ONLINE network's Q(s', .)
+ *                        over the valid actions, target = reward + discount * Q_target(s', a*) in float64 like the
+ *                        reference's NumPy arithmetic, y = prediction with y[i][action[i]] = target.  index_mode 0
+ *                        reproduces the reference line for line: it takes a* as the POSITION inside the masked
+ *                        sub-array (`np.argmax(qvalues[masks[i]])`) and uses that position as the action index;
+ *                        index_mode 1 maps the position back to the action.  counters [2] u64 or NULL: invalid_count
+ *                        (:367), empty masks (the reference raises there; index 0 is used).
+ * All arrays [n][5] float32 row-major; action int64 (the dtype torch indexes with). */
+int mdpp_replay_insert(int64_t n, const uint32_t *state_idx /*DEV*/, const uint8_t *action /*DEV*/,
+                       const uint32_t *next_idx /*DEV*/, const float *reward /*DEV*/, const uint8_t *next_mask /*DEV*/,
+                       const uint8_t *status /*DEV or NULL*/, const uint8_t *features /*DEV [n][80] or NULL*/,
+                       const uint8_t *next_features /*DEV [n][80] or NULL*/, int64_t n_keys, uint32_t *present /*DEV*/,
+                       uint32_t *m_next /*DEV*/, float *m_reward /*DEV*/, uint8_t *m_mask /*DEV*/,
+                       uint8_t *m_features /*DEV or NULL*/, uint64_t *counters /*DEV [3]*/, void *stream);
+int mdpp_replay_compact(int64_t n_keys, const uint32_t *present /*DEV*/, uint32_t *list /*DEV [n_keys]*/,
+                        uint32_t *count /*DEV*/, void *stream);
+int mdpp_dqn_target(int64_t n, const float *q_online_next /*DEV*/, const float *q_target_next /*DEV*/,
+                    const uint8_t *next_mask /*DEV*/, const float *reward /*DEV*/, const int64_t *action /*DEV*/,
+                    const float *prediction /*DEV*/, double discount, int index_mode, float *y /*DEV*/,
+                    float *target_out /*DEV or NULL*/, uint64_t *counters /*DEV [2] or NULL*/, void *stream);
+
 /* ---- deadlock precompute (-dd): backward reachability bitmap over the joint state space -------------
  * NEW definition next to the reference's stall heuristic: joint state = per car
  * (node, destination_index) or FINISHED, index = sum_c v_c * V^c with v_c = node_local*2 + di and

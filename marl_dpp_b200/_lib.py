@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("MDPP_LIB") or os.path.join(HERE, "libmdpp.so")  # MDPP_LIB: A/B builds of experiments
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "fast_tabs.cuh", "q_learner.cuh", "q_round.cuh", "q_sync.cuh", "reach.cuh")] + \
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("mdpp_kernels.cu", "mdpp_api.inl", "env_core.cuh", "fast_tabs.cuh", "q_learner.cuh", "q_round.cuh", "q_sync.cuh", "reach.cuh", "dqn_replay.cuh")] + \
           [os.path.join(ROOT, "include", "mdpp.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -22,7 +22,7 @@ EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_err
            "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host",
            "mdpp_sync_buffer_bytes", "mdpp_sync_alloc", "mdpp_sync_free", "mdpp_sync_open", "mdpp_sync_close", "mdpp_sync_attach",
            "mdpp_q_sync_replicas", "mdpp_sync_count", "mdpp_sync_emulate", "mdpp_deadlock_scratch_bytes",
-           "mdpp_deadlock_reachability_bfs"]
+           "mdpp_deadlock_reachability_bfs", "mdpp_replay_insert", "mdpp_replay_compact", "mdpp_dqn_target"]
 
 
 def needs_build():
@@ -94,6 +94,9 @@ def lib():
         "mdpp_sync_count": (U64, [P]),
         "mdpp_sync_emulate": (I, [C.POINTER(P), I, P]),
         "mdpp_deadlock_scratch_bytes": (I64, [P]),
+        "mdpp_replay_insert": (I, [I64, U32, U8, U32, F32, U8, U8, U8, U8, I64, U32, U32, F32, U8, U8, P, P]),
+        "mdpp_replay_compact": (I, [I64, U32, U32, U32, P]),
+        "mdpp_dqn_target": (I, [I64, F32, F32, U8, F32, P, F32, C.c_double, I, F32, F32, P, P]),
         "mdpp_deadlock_reachability_bfs": (I, [P, U32, P, I64, C.POINTER(C.c_int32), P]),
     }
     for name, (res, args) in sig.items():

@@ -267,7 +267,10 @@ __device__ __forceinline__ int32_t reward_int(const View &v, uint32_t nnode, uin
 }
 
 __device__ __forceinline__ float reward_float(int32_t r, int kind) {
-    return kind == MDPP_REWARD_DQN ? (float)((double)r / 100.0) : (float)r; // reference :553 `reward/100`
+    // reference :553 `reward/100` (float64, stored as float32 here).  For every integer |r| <= 2e6 the correctly
+    // rounded SINGLE-precision quotient equals the float64 quotient rounded to float32 (checked exhaustively on the
+    // host, tests/test_host_tables.py), so no FP64 instruction is needed
+    return kind == MDPP_REWARD_DQN ? __fdiv_rn((float)r, 100.0f) : (float)r;
 }
 
 // update_car (reference src/env_gym.py:386-441): move; on reaching the current destination either

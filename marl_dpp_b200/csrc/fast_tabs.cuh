@@ -144,4 +144,93 @@ __device__ __forceinline__ int32_t fast_reward(const FastView &v, uint32_t mv, u
     return r - clash * ((kind == MDPP_REWARD_DQN) ? 100 : 100000);
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Lean" form of the same step for the kernels that keep a tile's cars in registers across a whole round
+// (rollout_fast_kernel; ncu on the previous form: 1101 warp-instructions per tile and round for 4 cars, a quarter
+// of them 64-bit shifts / masks on the packed car word and branches around finished cars):
+//   * the cars live UNPACKED, one 12-bit field per 32-bit register, for all car-steps of a round;
+//   * an "other" is looked up with 9 index bits (node | destination_index << 7 | done << 8): the upper half of the
+//     table is zero, so a finished car is simply not listed -- no branch;
+//   * the ghost of a finished car (listed for 5 encodes by the others, src/env_gym.py:307-318) is branch-free: its
+//     counter steps through a nibble table, its entry is OR-ed in under a mask;
+//   * only the others are sorted, and the combinatorial rank comes from three small tables C(c+1,2), C(c+2,3),
+//     C(c+3,4) instead of multiplications and constant divisions.
+// Mode 1 (training / rollout: ghosts listed, counters move) only.  Bit-identical to fast_view by the oracle tests.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLeanCodes = 160; // others-codes are <= 1 + 18 * 8
+template <int NC>
+struct LeanTabs {
+    uint4 own[NC][256];
+    uint2 oth[NC][512];           // [256, 512): done cars -> {0, 0}
+    uint16_t next[NC][256][8];
+    uint32_t nth[32];
+    uint2 ghost[NC];
+    uint32_t tri[kLeanCodes], tet[kLeanCodes], quad[kLeanCodes];
+};
+
+template <int NC, int BLOCK>
+__device__ __forceinline__ void stage_lean_tabs(LeanTabs<NC> &S, const FastTabs *__restrict__ g) {
+    const uint4 *src_own = &g->own[0][0];
+    for (uint32_t i = threadIdx.x; i < NC * 256u; i += BLOCK) (&S.own[0][0])[i] = __ldg(src_own + i);
+    for (uint32_t i = threadIdx.x; i < NC * 512u; i += BLOCK) {
+        const uint32_t car = i >> 9, e = i & 511u;
+        S.oth[car][e] = e < 256u ? __ldg(&g->oth[car][e]) : make_uint2(0u, 0u);
+    }
+    const uint4 *src_next = reinterpret_cast<const uint4 *>(&g->next[0][0][0]);
+    for (uint32_t i = threadIdx.x; i < NC * 256u; i += BLOCK)
+        reinterpret_cast<uint4 *>(&S.next[0][0][0])[i] = __ldg(src_next + i);
+    if (threadIdx.x < 32) S.nth[threadIdx.x] = __ldg(&g->nth[threadIdx.x]);
+    if (threadIdx.x < NC) S.ghost[threadIdx.x] = __ldg(&g->ghost[threadIdx.x]);
+    for (uint32_t c = threadIdx.x; c < (uint32_t)kLeanCodes; c += BLOCK) {
+        const unsigned long long x = c;
+        S.tri[c] = (uint32_t)((x + 1) * x / 2);
+        S.tet[c] = (uint32_t)((x + 2) * (x + 1) * x / 6);
+        S.quad[c] = (uint32_t)((x + 3) * (x + 2) * (x + 1) * x / 24);
+    }
+}
+
+struct LeanView {
+    uint4 own;
+    uint32_t rank, sidx, lm;
+};
+
+// encodestate(car C, 1) + getlegalactions_filtered on the unpacked fields f[]; the ghost side effects land in f[].
+template <int NC, int C>
+__device__ __forceinline__ LeanView lean_view(const LeanTabs<NC> &S, uint32_t (&f)[NC], uint32_t rank_stride) {
+    LeanView v;
+    v.own = S.own[C][f[C] & 0xFFu];
+    uint32_t occ9 = 0, occ18 = 0, codes[NC > 1 ? NC - 1 : 1];
+    codes[0] = 0;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        if (i == C) continue;
+        const uint32_t fi = f[i], g = fi >> 9;
+        uint2 oe = S.oth[i][fi & 0x1FFu]; // zero for a finished car
+        // ghost of a finished car: counter 5..1 -> shown, then one lower; 0 -> 7 (gone for good); 7 stays
+        const uint32_t done = (fi >> 8) & 1u;
+        const uint32_t show = done & (0x7Eu >> g);                  // g in 1..6
+        const uint32_t ng = done ? ((0x75432107u >> (4u * g)) & 7u) : g;
+        const uint32_t mask = 0u - show;
+        oe.x |= S.ghost[i].x & mask;
+        oe.y |= S.ghost[i].y & mask;
+        f[i] = (fi & 0x1FFu) | (ng << 9);
+        codes[k++] = oe.x >> 18;
+        occ18 |= oe.x & 0x3FFFFu;
+        occ9 |= oe.y;
+    }
+    uint32_t rank = 0;
+    if constexpr (NC == 2) rank = codes[0];
+    if constexpr (NC > 2) {
+        sort_codes<NC - 1>(codes);
+        rank = codes[0] + S.tri[codes[1]];
+        if constexpr (NC > 3) rank += S.tet[codes[2]];
+        if constexpr (NC > 4) rank += S.quad[codes[3]];
+    }
+    v.rank = rank;
+    v.sidx = rank * rank_stride + (v.own.x & 0x3FFu);
+    v.lm = fast_legal(v.own, occ9, occ18);
+    return v;
+}
+
 } // namespace mdpp

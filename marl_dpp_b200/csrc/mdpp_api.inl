@@ -1,5 +1,6 @@
 // mdpp_api.inl -- host side of the C ABI declared in include/mdpp.h (included by mdpp_kernels.cu).
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -87,7 +88,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     }
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
-    c.barrier = take(64); // arrival counter of the cooperative kernels' grid barrier: zero at create, only ever grows
+    c.barrier = take(64); // grid barrier of the cooperative kernels: [0] arrival counter (only ever grows), [1] its value at the next kernel's start; zero at create
     c.stage = take((size_t)n_envs * 16);
     c.dl = take((size_t)n_envs * 4);
     c.total = off;
@@ -113,7 +114,6 @@ struct mdpp_handle {
     bool resident_rounds;   // ... with the table resident in every CTA's shared memory (MDPP_RESIDENT_ROUNDS=0: q_rounds_mixed_kernel)
     int resident_ok;        // -1 unknown, 0 does not fit / not co-resident, 1 ok
     int coop_ok;            // -1 unknown, 0 no cooperative launch / not co-resident, 1 ok
-    uint32_t barrier_base;  // value of the grid barrier's counter once everything launched so far has run
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
     bool multi_pull;        // ... followed by one reduce + one cluster pull launch (MDPP_MULTI_PULL=0: dense pulls)
     bool chain;             // the previous launch on the stream was one of our learner kernels
@@ -128,6 +128,8 @@ struct mdpp_handle {
     int64_t ep_bound;
     bool ep_device_max_valid;
     mdpp_stats *stat_slots; // pinned host staging for the privatised device counters
+    mdpp::HostStats *host_stats;  // pinned, device-visible: totals published by stats_publish_kernel (end-to-end calls)
+    unsigned long long host_seq;
     // replica averaging (q_sync.cuh): every rank's exchange buffer as seen from this process
     int sync_world, sync_rank, sync_interval;
     uint32_t sync_epoch;    // calls so far; the flags of call k carry k (every rank makes the same calls)
@@ -323,7 +325,6 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->coop_ok = -1;
     h->resident_rounds = !(getenv("MDPP_RESIDENT_ROUNDS") && atoi(getenv("MDPP_RESIDENT_ROUNDS")) == 0);
     h->resident_ok = -1;
-    h->barrier_base = 0;
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
     h->chain = false;
@@ -367,6 +368,8 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     if (e == cudaSuccess) e = cudaStreamSynchronize(s); // host images go out of scope
     delete ft;
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->stat_slots, sizeof(Control));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->host_stats, sizeof(HostStats), cudaHostAllocMapped);
+    if (e == cudaSuccess) memset(h->host_stats, 0, sizeof(HostStats));
     if (e != cudaSuccess) {
         delete h;
         return fail(MDPP_ECUDA, "workspace initialisation failed: %s", cudaGetErrorString(e));
@@ -377,6 +380,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
 
 int mdpp_destroy(mdpp_handle *h) {
     if (h && h->stat_slots) cudaFreeHost(h->stat_slots);
+    if (h && h->host_stats) cudaFreeHost(h->host_stats);
     delete h;
     return MDPP_OK;
 }
@@ -487,15 +491,21 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
         const uint32_t stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
         const int64_t tiles = (h->n_envs + 31) / 32;
         const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, (tiles + 7) / 8));
+        const bool lean = !(getenv("MDPP_LEAN_ROLLOUT") && atoi(getenv("MDPP_LEAN_ROLLOUT")) == 0);
 #define MDPP_ROLL(NCV)                                                                                           \
         do {                                                                                                     \
-            const size_t smem = sizeof(RoundSmem<NCV>);                                                          \
+            const size_t smem = lean ? sizeof(LeanTabs<NCV>) : sizeof(RoundSmem<NCV>);                           \
             if (!((h->smem_configured >> 27) & 1u)) {                                                            \
-                MDPP_CUDA(cudaFuncSetAttribute(rollout_fast_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                MDPP_CUDA(cudaFuncSetAttribute(rollout_fast_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem<NCV>))); \
+                MDPP_CUDA(cudaFuncSetAttribute(rollout_lean_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanTabs<NCV>))); \
                 h->smem_configured |= 1u << 27;                                                                  \
             }                                                                                                    \
-            rollout_fast_kernel<NCV><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs,   \
-                    h->env_id_base, rounds, first_round, seed, reward_kind, out, tabs, stride, control_of(h));   \
+            if (lean)                                                                                            \
+                rollout_lean_kernel<NCV><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs, \
+                        h->env_id_base, rounds, first_round, seed, reward_kind, out, tabs, stride, control_of(h)); \
+            else                                                                                                 \
+                rollout_fast_kernel<NCV><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs, \
+                        h->env_id_base, rounds, first_round, seed, reward_kind, out, tabs, stride, control_of(h)); \
         } while (0)
         switch (h->cfg.n_cars) {
         case 1: MDPP_ROLL(1); break;
@@ -940,7 +950,6 @@ static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const
     ra.bits_a = mark_region(h, 0, 0);
     MixedArgs mx{};
     mx.barrier = (uint32_t *)(h->ws + h->cv.barrier);
-    mx.barrier_base = h->barrier_base;
     mx.q0 = cur;
     mx.q1 = alt;
     const Marks mk = marks_of(h);
@@ -956,7 +965,6 @@ static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const
     void *args[] = {(void *)&h->dev, (void *)&lpv, (void *)&ra, (void *)&mx, (void *)&ctl};
     const void *fn = nc == 1 ? (const void *)q_rounds_mixed_kernel<1> : (const void *)q_rounds_mixed_kernel<2>;
     MDPP_LAUNCH(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRoundThreads), args, smem, s));
-    h->barrier_base += (uint32_t)(2 * n * nc) * grid; // two barriers per sub-step, one arrival per CTA
     h->chain = false; // launched in plain stream order; what follows must not overlap it either
     if ((n * nc) & 1) std::swap(cur, alt);
     return MDPP_OK;
@@ -1007,7 +1015,6 @@ static int q_resident_rounds_launch(mdpp_handle *h, float *cur, const mdpp_learn
     ra.n_rounds = (uint32_t)n;
     ResidentArgs rx{};
     rx.barrier = (uint32_t *)(h->ws + h->cv.barrier);
-    rx.barrier_base = h->barrier_base;
     rx.q = cur;
     rx.scratch = (float *)(h->ws + h->cv.qalt);
     rx.gbits = (uint32_t *)(h->ws + h->cv.gbits);
@@ -1027,9 +1034,6 @@ static int q_resident_rounds_launch(mdpp_handle *h, float *cur, const mdpp_learn
     void *args[] = {(void *)&h->dev, (void *)&lpv, (void *)&ra, (void *)&rx, (void *)&ctl};
     const void *fn = nc == 1 ? (const void *)q_rounds_resident_kernel<1> : (const void *)q_rounds_resident_kernel<2>;
     MDPP_LAUNCH(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRoundThreads), args, smem, s));
-    // one barrier per sub-step, one more whenever a sub-step overflows the list: the host cannot know how many there
-    // were, so the kernel is told its base and the next launch gets a base beyond anything this one can have used
-    h->barrier_base += (uint32_t)(2 * n * nc) * grid;
     h->chain = false; // launched in plain stream order; what follows must not overlap it either
     return MDPP_OK;
 }
@@ -1432,7 +1436,6 @@ int mdpp_deadlock_reachability_bfs(mdpp_handle *h, uint32_t *reach_bitmap, void 
     ra.levels_out = ra.counts + 4;
     ra.errors = ra.counts + 5;
     ra.barrier = (uint32_t *)(h->ws + h->cv.barrier);
-    ra.barrier_base = h->barrier_base;
     ra.words = (uint32_t)words;
     ra.n_joint = (uint32_t)n;
     ra.V = 2u * (uint32_t)h->cfg.n_local_nodes + 1u;
@@ -1457,10 +1460,64 @@ int mdpp_deadlock_reachability_bfs(mdpp_handle *h, uint32_t *reach_bitmap, void 
     uint32_t res[2] = {0u, 0u}; // levels, reverse-table overflows
     MDPP_CUDA(cudaMemcpyAsync(res, ra.levels_out, 8, cudaMemcpyDeviceToHost, s));
     MDPP_CUDA(cudaStreamSynchronize(s));
-    h->barrier_base += res[0] * grid; // one grid barrier per level
     h->chain = false;
     if (res[1]) return fail(MDPP_ECUDA, "reverse move table overflow (%u values): raise kRevSlots", res[1]);
     if (levels_out) *levels_out = (int32_t)res[0];
+    return MDPP_OK;
+}
+
+// ---- DQN replay memory and Double-DQN target (dqn_replay.cuh); no handle: plain device arrays ------------------
+static ReplayMem replay_mem(int64_t n_keys, uint32_t *present, uint32_t *m_next, float *m_reward, uint8_t *m_mask,
+                            uint8_t *m_features, uint64_t *counters) {
+    ReplayMem m{};
+    m.present = present;
+    m.next = m_next;
+    m.reward = m_reward;
+    m.mask = m_mask;
+    m.features = m_features;
+    m.counters = (unsigned long long *)counters;
+    m.n_keys = (uint32_t)n_keys;
+    return m;
+}
+int mdpp_replay_insert(int64_t n, const uint32_t *state_idx, const uint8_t *action, const uint32_t *next_idx,
+                       const float *reward, const uint8_t *next_mask, const uint8_t *status, const uint8_t *features,
+                       const uint8_t *next_features, int64_t n_keys, uint32_t *present, uint32_t *m_next, float *m_reward,
+                       uint8_t *m_mask, uint8_t *m_features, uint64_t *counters, void *stream) {
+    if (n <= 0) return MDPP_OK;
+    if (!state_idx || !action || !next_idx || !reward || !next_mask || !present || !m_next || !m_reward || !m_mask || !counters)
+        return fail(MDPP_EINVAL, "mdpp_replay_insert: NULL argument");
+    if (n_keys <= 0 || n_keys >= (int64_t)1 << 32 || (n_keys & 31)) return fail(MDPP_EINVAL, "n_keys must be a positive multiple of 32 below 2^32");
+    if (m_features && (!features || !next_features)) return fail(MDPP_EINVAL, "feature memory without feature rows");
+    if (m_features && (((uintptr_t)m_features | (uintptr_t)features | (uintptr_t)next_features) & 15))
+        return fail(MDPP_EINVAL, "feature arrays must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const ReplayMem m = replay_mem(n_keys, present, m_next, m_reward, m_mask, m_features, counters);
+    // duplicates of keys stored by earlier calls are compared with the stored payload first (the payload of a key this
+    // call stores is only complete when the call's kernel has finished)
+    replay_check_kernel<<<grid_for(n), kThreads, 0, s>>>(n, state_idx, action, next_idx, reward, status, m);
+    replay_insert_kernel<<<grid_for(n), kThreads, 0, s>>>(n, state_idx, action, next_idx, reward, next_mask, status,
+                                                         features, next_features, m);
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+int mdpp_replay_compact(int64_t n_keys, const uint32_t *present, uint32_t *list, uint32_t *count, void *stream) {
+    if (!present || !list || !count) return fail(MDPP_EINVAL, "mdpp_replay_compact: NULL argument");
+    if (n_keys <= 0 || n_keys >= (int64_t)1 << 32 || (n_keys & 31)) return fail(MDPP_EINVAL, "n_keys must be a positive multiple of 32 below 2^32");
+    replay_compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(present, (uint32_t)(n_keys / 32), (uint32_t)n_keys, list, count);
+    MDPP_CUDA(cudaGetLastError());
+    return MDPP_OK;
+}
+int mdpp_dqn_target(int64_t n, const float *q_online_next, const float *q_target_next, const uint8_t *next_mask,
+                    const float *reward, const int64_t *action, const float *prediction, double discount, int index_mode,
+                    float *y, float *target_out, uint64_t *counters, void *stream) {
+    if (n <= 0) return MDPP_OK;
+    if (!q_online_next || !q_target_next || !next_mask || !reward || !action || !prediction || !y)
+        return fail(MDPP_EINVAL, "mdpp_dqn_target: NULL argument");
+    if (index_mode != 0 && index_mode != 1) return fail(MDPP_EINVAL, "index_mode must be 0 (reference) or 1 (action index)");
+    dqn_target_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(n, q_online_next, q_target_next, next_mask, reward,
+                                                                         action, prediction, discount, index_mode, y,
+                                                                         target_out, (unsigned long long *)counters);
+    MDPP_CUDA(cudaGetLastError());
     return MDPP_OK;
 }
 
@@ -1536,7 +1593,31 @@ int mdpp_q_train_rounds_host(mdpp_handle *h, float *q, const mdpp_learner *lp_ho
                              mdpp_stats *stats_host, void *stream) {
     int rc = mdpp_q_train_rounds(h, q, lp_host, first_round, rounds, stream);
     if (rc) return rc;
-    return mdpp_get_stats_host(h, stats_host, 0, stream);
+    if (!stats_host) return fail(MDPP_EINVAL, "stats_host is NULL");
+    if (getenv("MDPP_HOST_STATS_COPY") && atoi(getenv("MDPP_HOST_STATS_COPY")) != 0)
+        return mdpp_get_stats_host(h, stats_host, 0, stream); // the copy + synchronise form (A/B runs)
+    // totals + sequence number stored into pinned host memory by one small kernel; this thread polls the word
+    cudaStream_t s = (cudaStream_t)stream;
+    HostStats *dev_view = nullptr;
+    MDPP_CUDA(cudaHostGetDevicePointer((void **)&dev_view, h->host_stats, 0));
+    const unsigned long long seq = ++h->host_seq;
+    stats_publish_kernel<<<1, 128, 0, s>>>(control_of(h), dev_view, seq);
+    MDPP_CUDA(cudaGetLastError());
+    unsigned spins = 0;
+    while (h->host_stats->seq != seq) {
+        if ((++spins & 0xFFFFu) == 0u) { // a failed launch must not turn into an endless poll
+            cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(MDPP_ECUDA, "stream failed while waiting for the counters: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && h->host_stats->seq != seq)
+                return fail(MDPP_ECUDA, "the counters never arrived in host memory");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *stats_host = h->host_stats->totals;
+    if (h->ep_device_max_valid) // everything launched so far has completed: the device's maximum is exact
+        h->ep_bound = std::min<int64_t>(h->ep_bound, (int64_t)h->host_stats->max_episode);
+    return MDPP_OK;
 }
 
 // ---- state-id codec: pure host arithmetic, usable without a device --------------------------------

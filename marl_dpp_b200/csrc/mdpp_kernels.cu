@@ -33,6 +33,52 @@ struct Control {
 // branch-free instead.
 __device__ __forceinline__ void guard_tripped(Control *ctl) { atomicAdd((unsigned long long *)&ctl->stats[0].internal_errors, 1ull); }
 
+// End-to-end calls (mdpp_q_train_rounds_host): the counters go to the host WITHOUT a copy command and without a
+// stream synchronisation.  One small kernel after the round's kernels sums the privatised slots and stores the
+// totals, then a sequence number, straight into pinned host memory (zero-copy over PCIe); the host thread polls that
+// word.  Against cudaMemcpyAsync(8 KB) + cudaStreamSynchronize this takes ~15 us out of every host-facing call.
+struct HostStats {
+    mdpp_stats totals;
+    uint32_t max_episode;
+    uint32_t pad;
+    volatile unsigned long long seq; // written last
+};
+__global__ void __launch_bounds__(128)
+stats_publish_kernel(const Control *__restrict__ ctl, HostStats *host, unsigned long long seq) {
+    static_assert(kStatSlots == 128, "one thread per slot");
+    __shared__ unsigned long long acc[8];
+    __shared__ uint32_t mx;
+    if (threadIdx.x < 8) acc[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) mx = 0u;
+    __syncthreads();
+    const mdpp_stats s = ctl->stats[threadIdx.x];
+    const unsigned long long v[8] = {s.agent_steps, s.q_updates, s.episodes_done, s.episodes_capped,
+                                     (unsigned long long)s.reward_sum, s.explore_steps, s.touched_keys, s.internal_errors};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if ((threadIdx.x & 31u) == 0 && x) atomicAdd(&acc[k], x);
+    }
+    const uint32_t me = __reduce_max_sync(0xFFFFFFFFu, ctl->max_episode[threadIdx.x]);
+    if ((threadIdx.x & 31u) == 0) atomicMax(&mx, me);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        host->totals.agent_steps = acc[0];
+        host->totals.q_updates = acc[1];
+        host->totals.episodes_done = acc[2];
+        host->totals.episodes_capped = acc[3];
+        host->totals.reward_sum = (int64_t)acc[4];
+        host->totals.explore_steps = acc[5];
+        host->totals.touched_keys = acc[6];
+        host->totals.internal_errors = acc[7];
+        host->max_episode = mx;
+        __threadfence_system();
+        host->seq = seq;
+    }
+}
+
 struct StatAcc {
     uint32_t steps = 0, episodes = 0, capped = 0, explore = 0;
     int32_t reward = 0;
@@ -682,4 +728,5 @@ reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t n_joint, u
 } // namespace mdpp
 
 #include "reach.cuh"
+#include "dqn_replay.cuh"
 #include "mdpp_api.inl"

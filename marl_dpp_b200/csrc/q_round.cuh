@@ -30,8 +30,10 @@
 
 namespace mdpp {
 
+// LeanTabs (fast_tabs.cuh): the step tables with a 9-bit "other" index (finished cars read a zero entry: no branch),
+// the ghost entries and the rank tables staged in shared memory as well.
 template <int NC>
-struct RoundSmem : StepTabs<NC> {
+struct RoundSmem : LeanTabs<NC> {
     CtaCounters cc;
     uint32_t any_deferred;
 };
@@ -69,35 +71,36 @@ enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
 // move) unless the car is parked.  Returns kStepDone with the compact key (state * 5 + action) when a key was touched.
 // CG: the table changes while the kernel runs (q_rounds_mixed_kernel): coherent greedy reads (ldcg_row).
 // TQ: the table is resident in shared memory as compact keys (q_now[state * 5 + action], q_rounds_resident_kernel).
-template <int NC, int C, bool CG = false, bool TQ = false>
+// CarsT: uint32_t for 1- and 2-car tables (both 12-bit fields live in the record's first word: no 64-bit shifts).
+template <int NC, int C, bool CG = false, bool TQ = false, class CarsT = uint64_t>
 __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
-                                              const RoundArgs &ra, uint64_t &cars, uint32_t word, uint32_t eps16,
+                                              const RoundArgs &ra, CarsT &cars, uint32_t word, uint32_t eps16,
                                               bool allow_greedy, uint32_t &key, bool &moved, bool &explore,
                                               const float *q_now = nullptr) {
+    static_assert(sizeof(CarsT) * 8 >= 12 * NC, "the cars do not fit the word");
     moved = false;
     explore = false;
     const uint32_t f = (uint32_t)(cars >> (12 * C)) & 0xFFFu;
     if (f & 0x100u) return kStepSkip; // `if env.check_car_training(num): continue` (qlearning.py:216-217)
-    uint64_t nc = cars;
+    CarsT nc = cars;
     const uint4 own = S.own[C][f & 0xFFu];
     // ---- encodestate (src/env_gym.py:281-329): the others, with the ghost side effect of finished cars ----
+    // branch-free (lean_view, fast_tabs.cuh): a finished car reads a zero entry; its ghost counter steps through a
+    // nibble table (5..1 -> shown and one lower, 0 -> 7 = gone, 7 stays) and its entry is OR-ed in under a mask
     uint32_t occ9 = 0, occ18 = 0, codes[NC];
 #pragma unroll
     for (int i = 0; i < NC; i++) {
         codes[i] = 0;
         if (i == C) continue;
-        const uint32_t fi = (uint32_t)(cars >> (12 * i)) & 0xFFFu;
-        uint2 oe = make_uint2(0u, 0u);
-        if (!(fi & 0x100u)) {
-            oe = S.oth[i][fi & 0xFFu];
-        } else {
-            uint32_t g = fi >> 9;
-            if (g != 7u) {
-                if (g == 0u) g = 7u;                 // count went negative: the ghost vanishes for good
-                else { g -= 1u; oe = gt->ghost[i]; } // still shown (5 encodes in total)
-                nc = (nc & ~(0xE00ull << (12 * i))) | ((uint64_t)(g << 9) << (12 * i));
-            }
-        }
+        const uint32_t fi = (uint32_t)(cars >> (12 * i)) & 0xFFFu, g = fi >> 9;
+        uint2 oe = S.oth[i][fi & 0x1FFu];
+        const uint32_t done = (fi >> 8) & 1u;
+        const uint32_t show = done & (0x7Eu >> g);
+        const uint32_t ng = done ? ((0x75432107u >> (4u * g)) & 7u) : g;
+        const uint32_t mask = 0u - show;
+        oe.x |= S.ghost[i].x & mask;
+        oe.y |= S.ghost[i].y & mask;
+        nc = (nc & ~((CarsT)0xE00u << (12 * i))) | ((CarsT)(ng << 9) << (12 * i));
         codes[i] = oe.x >> 18;
         occ18 |= oe.x & 0x3FFFFu;
         occ9 |= oe.y;
@@ -151,9 +154,16 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
     key = sidx * MDPP_N_ACT + a; // compact key (marks carry no padding slots)
     // ---- successor (src/env_gym.py:256-265) and update_car (:386-441): one table entry ----
     const uint32_t nf = ((uint32_t)S.next[C][f & 0xFFu][a] & 0x1FFu) | (f & 0xE00u);
-    cars = (nc & ~(0xFFFull << (12 * C))) | ((uint64_t)nf << (12 * C));
+    cars = (nc & ~((CarsT)0xFFFu << (12 * C))) | ((CarsT)nf << (12 * C));
     moved = true;
     return kStepDone;
+}
+
+// end-of-round test and reset on 32-bit cars (1- and 2-car tables)
+template <int NC>
+__device__ __forceinline__ bool all_done32(uint32_t cars) {
+    constexpr uint32_t kDoneBits = NC == 1 ? 0x100u : 0x100100u;
+    return (cars & kDoneBits) == kDoneBits;
 }
 
 // CSTART = 0: K0, every live env, cars 0..NC-1 while they explore.  CSTART = 1 (NC = 2): K1, parked lanes only.
@@ -187,7 +197,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
     {   // tables and maps
-        stage_step_tabs<NC, kBlock>(S, ra.tabs);
+        stage_lean_tabs<NC, kBlock>(S, ra.tabs);
         uint4 *m4 = reinterpret_cast<uint4 *>(maps);
         const uint32_t n16 = (uint32_t)kMaps * (ra.map_bytes >> 4);
         for (uint32_t i = threadIdx.x; i < n16; i += kBlock) m4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -204,7 +214,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
         uint32_t episode = rec.z & 0xFFFFu;
         const bool live = (int32_t)episode < lp.episodes; // an env that used its episode budget is frozen
         if (e < ra.n_envs && live && pending == (uint32_t)CSTART) {
-            uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            uint32_t cars = rec.x; // 1-2 cars: both 12-bit fields live in the first word
             uint32_t steps = rec.z >> 16;
             const uint32_t env = ra.env_id_base + e;
             // epsilon schedule; the first segment (40 % of the episodes, most of the steps) costs one compare
@@ -242,7 +252,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
             }
             steps = steps > 0xFFFFu ? 0xFFFFu : steps;
             if (!new_pending) { // end of the round-robin round (qlearning.py:233)
-                bool finished = all_done<NC>(cars);
+                bool finished = all_done32<NC>(cars);
                 bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
                 if (finished || capped) {
                     cnt.episodes += 1;
@@ -251,11 +261,10 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                     cnt.max_episode = max(cnt.max_episode, episode);
                     steps = 0;
                     rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
-                    cars = initial_cars<NC>(cfg, heading_word(ra.round, 2, lp.seed, env));
+                    cars = (uint32_t)initial_cars<NC>(cfg, heading_word(ra.round, 2, lp.seed, env));
                 }
             }
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
+            rec.x = cars;
             rec.z = (episode & 0xFFFFu) | (steps << 16);
             rec.w = (rec.w & ~0x700u) | (new_pending << 8);
             ra.recs[e] = rec;
@@ -350,7 +359,7 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
     {
-        stage_step_tabs<NC, kBlock>(S, ra.tabs);
+        stage_lean_tabs<NC, kBlock>(S, ra.tabs);
         uint4 *m4 = reinterpret_cast<uint4 *>(maps);
         const uint32_t n16 = 2u * NC * (ra.map_bytes >> 4);
         for (uint32_t i = threadIdx.x; i < n16; i += kBlock) m4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -369,7 +378,7 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
             uint32_t episode = rec.z & 0xFFFFu;
             const bool live = (int32_t)episode < lp.episodes;
             if (e < ra.n_envs && live && ((rec.w >> 8) & 7u) == 0u) {
-                uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+                uint32_t cars = rec.x; // 1-2 cars: both 12-bit fields live in the first word
                 uint32_t steps = rec.z >> 16;
                 const uint32_t env = ra.env_id_base + e;
                 uint32_t eps16 = lp.eps_q16[0];
@@ -393,7 +402,7 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                 }
                 steps = steps > 0xFFFFu ? 0xFFFFu : steps;
                 { // end of the round-robin round (qlearning.py:233)
-                    bool finished = all_done<NC>(cars);
+                    bool finished = all_done32<NC>(cars);
                     bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
                     if (finished || capped) {
                         cnt.episodes += 1;
@@ -402,11 +411,10 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                         cnt.max_episode = max(cnt.max_episode, episode);
                         steps = 0;
                         rec.w &= ~0xFFu;
-                        cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+                        cars = (uint32_t)initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
                     }
                 }
-                rec.x = (uint32_t)cars;
-                rec.y = (uint32_t)(cars >> 32);
+                rec.x = cars;
                 rec.z = (episode & 0xFFFFu) | (steps << 16);
                 ra.recs[e] = rec;
             }
@@ -576,26 +584,43 @@ q_multi_pull_kernel(MultiPullArgs pa, Control *ctl) {
 // same order as the sub-step kernels: bit-identical tables, records and counters.
 // ------------------------------------------------------------------------------------------------
 // Grid-wide barrier of a cooperative launch (every CTA co-resident by construction): one arrival per CTA on a
-// counter that only ever grows -- the host passes the value it had when the kernel started -- and a spin of one
-// thread per CTA.  Release / acquire through the two fences and the acquiring load, like cooperative groups'
+// counter that only ever grows and a spin of one thread per CTA.  The value the counter has when a kernel starts
+// lives next to it (word 1 of the barrier area): every cooperative kernel reads it first and its CTA 0 stores the
+// value after its last barrier on the way out, so kernels whose number of barriers depends on the data (the
+// overflow path of q_rounds_resident_kernel, the levels of reach_bfs_kernel) need no host bookkeeping -- a host
+// count that disagrees with the arrivals would leave the next kernel waiting for ever.  Release / acquire through the two fences and the acquiring load, like cooperative groups'
 // grid.sync(), which measured ~4 us per barrier here against ~1 us for this one.
 __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
-        uint32_t v;
+        uint32_t v, spins = 0;
+        unsigned long long t0 = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            // A barrier that cannot complete (a CTA missing, a base that disagrees with the arrivals) must end in an
+            // error the host sees, not in a GPU that spins until somebody resets it: after 4 s the kernel traps.
+            if ((++spins & 0x3FFFu) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) __trap();
+            }
         } while ((int32_t)(v - target) < 0);
         __threadfence();
     }
     __syncthreads();
 }
 
+__device__ __forceinline__ uint32_t barrier_base_load(const uint32_t *area) { return __ldcg(area + 1); }
+// on the way out, after the kernel's last barrier (every CTA read the base before its first one)
+__device__ __forceinline__ void barrier_base_store(uint32_t *area, uint32_t bar) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) area[1] = bar;
+}
+
 struct MixedArgs {
-    uint32_t *barrier;        // the grid barrier's counter and its value at kernel start
-    uint32_t barrier_base;
+    uint32_t *barrier;        // the grid barrier's area: [0] arrival counter, [1] its value when a kernel starts
     float *q0, *q1;           // the table and its other copy: sub-step i reads q(i & 1), its pull writes q((i + 1) & 1)
     const uint32_t *sinfo;
     uint32_t *visited;
@@ -619,7 +644,7 @@ __device__ __forceinline__ void mixed_env_pass(const RoundSmem<NC> &S, const Dev
         uint32_t episode = rec.z & 0xFFFFu;
         const bool live = (int32_t)episode < lp.episodes;
         if (e < ra.n_envs && live) {
-            uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            uint32_t cars = rec.x; // 1-2 cars: both 12-bit fields live in the first word
             uint32_t steps = rec.z >> 16;
             const uint32_t env = ra.env_id_base + e;
             uint32_t eps16 = lp.eps_q16[0];
@@ -641,7 +666,7 @@ __device__ __forceinline__ void mixed_env_pass(const RoundSmem<NC> &S, const Dev
             cnt.explore += explore;
             steps = steps > 0xFFFFu ? 0xFFFFu : steps;
             if (C == NC - 1) { // end of the round-robin round (qlearning.py:233)
-                bool finished = all_done<NC>(cars);
+                bool finished = all_done32<NC>(cars);
                 bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
                 if (finished || capped) {
                     cnt.episodes += 1;
@@ -650,11 +675,10 @@ __device__ __forceinline__ void mixed_env_pass(const RoundSmem<NC> &S, const Dev
                     cnt.max_episode = max(cnt.max_episode, episode);
                     steps = 0;
                     rec.w &= ~0xFFu;
-                    cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+                    cars = (uint32_t)initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
                 }
             }
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
+            rec.x = cars;
             rec.z = (episode & 0xFFFFu) | (steps << 16);
             ra.recs[e] = rec;
         }
@@ -714,14 +738,14 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
     const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
     const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
     {
-        stage_step_tabs<NC, kRoundThreads>(S, ra.tabs);
+        stage_lean_tabs<NC, kRoundThreads>(S, ra.tabs);
         uint4 *m4 = reinterpret_cast<uint4 *>(map);
         for (uint32_t i = threadIdx.x; i < (ra.map_bytes >> 4); i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
     }
     __syncthreads();
     StepCounts cnt;
-    uint32_t touched_total = 0, sub = 0, bar = mx.barrier_base;
+    uint32_t touched_total = 0, sub = 0, bar = barrier_base_load(mx.barrier);
     for (uint32_t r = 0; r < ra.n_rounds; r++) {
         const uint64_t round = ra.round + r;
 #pragma unroll
@@ -740,6 +764,7 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
     if ((threadIdx.x & 31u) == 0 && touched_total)
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
                   (unsigned long long)touched_total);
+    barrier_base_store(mx.barrier, bar);
     flush_counts<true>(cnt, S.cc, 0u, ctl);
 }
 
@@ -767,8 +792,7 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
 // Same arithmetic in the same order as the sub-step kernels: bit-identical tables, records and counters.
 // ------------------------------------------------------------------------------------------------
 struct ResidentArgs {
-    uint32_t *barrier;        // the grid barrier's counter and its value at kernel start
-    uint32_t barrier_base;
+    uint32_t *barrier;        // the grid barrier's area: [0] arrival counter, [1] its value when a kernel starts
     float *q;                 // the table: rows of MDPP_Q_ROW floats, read at the start, written at the end
     float *scratch;           // [n_marks] floats: new values of the overflow path
     uint32_t *gbits;          // [3][words] global mark bitmaps (compact keys), zero at kernel start
@@ -794,7 +818,7 @@ __device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const 
         uint32_t episode = rec.z & 0xFFFFu;
         const bool live = (int32_t)episode < lp.episodes;
         if (e < ra.n_envs && live) {
-            uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+            uint32_t cars = rec.x; // 1-2 cars: both 12-bit fields live in the first word
             uint32_t steps = rec.z >> 16;
             const uint32_t env = ra.env_id_base + e;
             uint32_t eps16 = lp.eps_q16[0];
@@ -816,7 +840,7 @@ __device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const 
             cnt.explore += explore;
             steps = steps > 0xFFFFu ? 0xFFFFu : steps;
             if (C == NC - 1) { // end of the round-robin round (qlearning.py:233)
-                bool finished = all_done<NC>(cars);
+                bool finished = all_done32<NC>(cars);
                 bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
                 if (finished || capped) {
                     cnt.episodes += 1;
@@ -825,11 +849,10 @@ __device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const 
                     cnt.max_episode = max(cnt.max_episode, episode);
                     steps = 0;
                     rec.w &= ~0xFFu;
-                    cars = initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
+                    cars = (uint32_t)initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
                 }
             }
-            rec.x = (uint32_t)cars;
-            rec.y = (uint32_t)(cars >> 32);
+            rec.x = cars;
             rec.z = (episode & 0xFFFFu) | (steps << 16);
             ra.recs[e] = rec;
         }
@@ -892,7 +915,7 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
     const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
     const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
     {
-        stage_step_tabs<NC, kRoundThreads>(S, ra.tabs);
+        stage_lean_tabs<NC, kRoundThreads>(S, ra.tabs);
         uint4 *m4 = reinterpret_cast<uint4 *>(map);
         for (uint32_t i = threadIdx.x; i < (ra.map_bytes >> 4); i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
         for (uint32_t m = threadIdx.x; m < rx.n_marks; m += kRoundThreads) {
@@ -903,7 +926,7 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
     }
     __syncthreads();
     StepCounts cnt;
-    uint32_t touched_total = 0, sub = 0, bar = rx.barrier_base;
+    uint32_t touched_total = 0, sub = 0, bar = barrier_base_load(rx.barrier);
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t r = 0; r < ra.n_rounds; r++) {
         const uint64_t round = ra.round + r;
@@ -1002,6 +1025,7 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
     if (lane == 0 && touched_total)
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
                   (unsigned long long)touched_total);
+    barrier_base_store(rx.barrier, bar);
     flush_counts<true>(cnt, S.cc, 0u, ctl);
 }
 
@@ -1130,7 +1154,7 @@ rollout_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
     RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
     __shared__ long long cta_reward;
     {
-        stage_step_tabs<NC, kRolloutThreads>(S, tabs);
+        stage_lean_tabs<NC, kRolloutThreads>(S, tabs);
         if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; cta_reward = 0ll; }
     }
     __syncthreads();
@@ -1180,6 +1204,138 @@ rollout_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
     if (lane == 0 && rsum) atomicAdd((unsigned long long *)&cta_reward, (unsigned long long)rsum);
     flush_counts<true>(cnt, S.cc, MDPP_LEARN_FROZEN, ctl); // no Q-updates on this path
+    if (threadIdx.x == 0 && cta_reward)
+        atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].reward_sum, (unsigned long long)cta_reward);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same rollout on the lean step (fast_tabs.cuh, LeanTabs): cars unpacked in registers for the whole launch,
+// branch-free others / ghosts, table-driven rank, and no clash term in the reward -- under LEGAL actions it is
+// always 0 (a listed car blocks its box number, a finished car stands on the parking node, which is no box), which
+// is what the learner's pull relies on too; the oracle comparison of every reward (1-5 cars) pins it.
+// ------------------------------------------------------------------------------------------------
+template <int NC, int C>
+__device__ __forceinline__ void lean_rollout_chain(const LeanTabs<NC> &S, const DevCfg &cfg, uint32_t rank_stride, int kind,
+                                                   uint32_t (&f)[NC], const uint32_t (&w)[NC], uint32_t &steps, uint32_t &n_steps,
+                                                   int32_t &rsum, const RolloutOut &out, size_t o, size_t n_envs) {
+    uint32_t a = MDPP_ACT_SKIP, nidx = 0xFFFFFFFFu;
+    float rw = 0.f;
+    const uint32_t fc = f[C];
+    if (!(fc & 0x100u)) {
+        const LeanView v = lean_view<NC, C>(S, f, rank_stride);
+        if (v.lm) {
+            a = (S.nth[v.lm] >> (3u * (((w[C] & 0xFFFFu) * (uint32_t)__popc(v.lm)) >> 16))) & 7u;
+            const uint32_t mv = S.next[C][fc & 0xFFu][a];
+            const uint32_t pnode = fc & 127u, dnode = (v.own.x >> 10) & 127u;
+            const bool reached = (mv >> 9) & 1u;
+            const uint32_t nn = reached ? dnode : (mv & 127u); // the successor itself (a finished car is parked afterwards)
+            nidx = v.sidx - pnode + nn;                         // same others, same destination: only the node term moves
+            // ---- q_reward / dqn_reward (src/env_gym.py:485-620), integer (dqn: before the /100) ----
+            int32_t ri = -10 + 50 * ((int32_t)(v.own.w & 0xFFu) - (int32_t)(mv >> 10));
+            if (reached) ri += (kind == MDPP_REWARD_DQN) ? 110 : 10010;
+            if (kind == MDPP_REWARD_Q && cfg.bad_on) { // :568-577 on the heading-stripped strings
+                const uint32_t base = (v.rank * cfg.n_dest_boxes + (v.own.x >> 29)) * cfg.n_src_boxes - cfg.box_base;
+                const uint32_t idn = base + (nn >> 2), idp = base + (pnode >> 2);
+                const uint32_t bn = (__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u;
+                const uint32_t bp = (__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u;
+                ri = bn ? -10000 : (bp ? 0 : ri);
+            }
+            rw = reward_float(ri, kind);
+            f[C] = (mv & 0x1FFu) | (fc & 0xE00u);
+            steps += 1;
+            n_steps += 1;
+            rsum += ri;
+        }
+    }
+    if (out.action) out.action[o] = (uint8_t)a;
+    if (out.reward) out.reward[o] = rw;
+    if (out.next) out.next[o] = nidx;
+    if (out.done) {
+        uint32_t d = f[0];
+#pragma unroll
+        for (int i = 1; i < NC; i++) d &= f[i];
+        out.done[o] = (uint8_t)((d >> 8) & 1u);
+    }
+    if constexpr (C + 1 < NC) lean_rollout_chain<NC, C + 1>(S, cfg, rank_stride, kind, f, w, steps, n_steps, rsum, out, o + n_envs, n_envs);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kRolloutThreads, 4)
+rollout_lean_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint32_t env_id_base, int rounds,
+                    uint64_t first_round, uint32_t seed, int kind, RolloutOut out, const FastTabs *__restrict__ tabs,
+                    uint32_t rank_stride, Control *ctl) {
+    extern __shared__ uint4 smem_dyn[];
+    LeanTabs<NC> &S = *reinterpret_cast<LeanTabs<NC> *>(smem_dyn);
+    __shared__ long long cta_reward;
+    __shared__ CtaCounters cc;
+    stage_lean_tabs<NC, kRolloutThreads>(S, tabs);
+    if (threadIdx.x == 0) { cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; cta_reward = 0ll; }
+    __syncthreads();
+    const uint32_t tiles = (n_envs + 31u) >> 5;
+    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
+    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    StepCounts cnt;
+    long long rsum = 0;
+    for (uint32_t t = t0 + warp; t < t1; t += n_warps) {
+        const uint32_t e = t * 32u + lane;
+        if (e >= n_envs) continue;
+        uint4 rec = recs[e];
+        uint32_t f[NC];
+        {
+            const uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+#pragma unroll
+            for (int i = 0; i < NC; i++) f[i] = (uint32_t)(cars >> (12 * i)) & 0xFFFu;
+        }
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        const uint32_t env = env_id_base + e;
+        int32_t rtile = 0;
+        for (int r = 0; r < rounds; r++) {
+            const uint64_t round = first_round + (uint64_t)r;
+            const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
+            uint32_t w[NC];
+            w[0] = p.x;
+            if (NC > 1) w[NC > 1 ? 1 : 0] = p.y;
+            if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
+            if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
+            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
+            int32_t rr = 0;
+            lean_rollout_chain<NC, 0>(S, cfg, rank_stride, kind, f, w, steps, cnt.steps, rr, out,
+                                      (size_t)r * NC * (size_t)n_envs + e, (size_t)n_envs);
+            rtile += rr;
+            if ((r & 63) == 63) { rsum += rtile; rtile = 0; } // |reward| <= 1e5 per step: 64 rounds x 5 cars fit 32 bits
+            steps = min(steps, 0xFFFFu);
+            // end of round: is_game_ended (src/env_gym.py:622-638) or the step cap -> next episode
+            uint32_t d = f[0];
+#pragma unroll
+            for (int i = 1; i < NC; i++) d &= f[i];
+            const bool finished = (d >> 8) & 1u;
+            const bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                cnt.episodes++;
+                cnt.capped += capped;
+                episode = (episode + 1) & 0xFFFFu;
+                steps = 0;
+                const uint32_t hb = heading_word(round, 2, seed, env);
+#pragma unroll
+                for (int i = 0; i < NC; i++)
+                    f[i] = make_field(cfg.start_box18[i] * 4 + ((hb >> (2 * i)) & 3u), cfg.start_di[i], 0, 5);
+            }
+        }
+        rsum += rtile;
+        uint64_t cars = 0;
+#pragma unroll
+        for (int i = 0; i < NC; i++) cars |= (uint64_t)f[i] << (12 * i);
+        rec.x = (uint32_t)cars;
+        rec.y = (uint32_t)(cars >> 32);
+        rec.z = episode | (steps << 16);
+        recs[e] = rec;
+    }
+    cnt.explore = cnt.steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xFFFFFFFFu, rsum, o);
+    if (lane == 0 && rsum) atomicAdd((unsigned long long *)&cta_reward, (unsigned long long)rsum);
+    flush_counts<true>(cnt, cc, MDPP_LEARN_FROZEN, ctl); // no Q-updates on this path
     if (threadIdx.x == 0 && cta_reward)
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].reward_sum, (unsigned long long)cta_reward);
 }

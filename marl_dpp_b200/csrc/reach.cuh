@@ -33,8 +33,7 @@ struct ReachArgs {
     uint32_t *counts;         // [3] states found per level (rotating)
     uint32_t *levels_out;     // number of levels the search ran
     uint32_t *errors;         // reverse-table overflow (never): counted, the search result would be incomplete
-    uint32_t *barrier;
-    uint32_t barrier_base;
+    uint32_t *barrier;        // the grid barrier's area (q_round.cuh grid_barrier)
     uint32_t words, n_joint, V, node_base, parking_node, rank_stride;
     const FastTabs *tabs;
 };
@@ -111,7 +110,7 @@ reach_bfs_kernel(ReachArgs ra) {
     }
     __syncthreads();
     const uint32_t n_chunks = (ra.words + kReachChunkWords - 1) / kReachChunkWords;
-    uint32_t bar = ra.barrier_base;
+    uint32_t bar = barrier_base_load(ra.barrier);
     uint32_t *cur = ra.front[0], *nxt = ra.front[1];
     ReachArgs la = ra; // front[1] of this copy is always "the next frontier" for reach_expand_car
     for (uint32_t level = 0;; level++) {
@@ -175,6 +174,7 @@ reach_bfs_kernel(ReachArgs ra) {
         const uint32_t n_new = __ldcg(ra.counts + level % 3u);
         if (n_new == 0u) {
             if (blockIdx.x == 0 && threadIdx.x == 0) *ra.levels_out = level + 1u;
+            barrier_base_store(ra.barrier, bar);
             break;
         }
         uint32_t *t2 = cur;

@@ -112,3 +112,114 @@ def test_collector_fills_ring_and_feeds_a_torch_model():
     before = env.stats()["agent_steps"]
     col2.collect_round()
     assert env.stats()["agent_steps"] > before
+
+
+def test_unique_replay_equals_the_references_ordered_set():
+    """remember() + `deque(OrderedSet(self.memory))` (reference dqn_open_source.py:322,343) on the device: after a
+    few thousand envs x rounds the de-duplicated memory holds exactly the distinct (state, action, next_state,
+    reward) tuples a Python set of the same samples holds, its key list is sorted, every payload is the tuple's,
+    and a minibatch is `batch_size` distinct members (None while the set is smaller than the batch, :344-345)."""
+    import marl_dpp_b200 as m
+    from marl_dpp_b200.batched import BatchedEnv
+    from marl_dpp_b200.dqn_feed import DQNCollector, ReplayRing, UniqueReplay, random_legal_policy
+    sc = m.Scenario(m.layout_3[2], ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], step_cap=500)
+    n = 4096
+    env = BatchedEnv(sc, n, seed=2)
+    ring = ReplayRing(2 * n, "cuda")
+    mem = UniqueReplay(sc, "cuda")
+    assert mem.sample(32) is None and len(mem) == 0
+    g = torch.Generator(device="cuda").manual_seed(5)
+    col = DQNCollector(env, ring, random_legal_policy(g), memory=mem)
+    seen = {}
+    offered = 0
+    for _ in range(40):
+        # replay the collector's sub-steps by hand so that every sample can also go into a Python set
+        for c in range(env.n_cars):
+            sl = ring.reserve(n)
+            feats, legal, state = env.dqn_observe(c, features=ring.state[sl])
+            actions = col.policy(feats, legal)
+            actions = torch.where(legal != 0, actions, torch.full_like(actions, 0xFF))
+            out = env.dqn_act(c, actions, next_features=ring.next_state[sl], auto_reset=True, round=col.round)
+            ok = out["status"] == 0
+            nxt = env.query(c, torch.where(ok, state, torch.zeros_like(state)),
+                            torch.where(ok, actions, torch.full_like(actions, 0xFF)), reward="dqn_reward")["next_state"]
+            mem.insert(state, actions, nxt, out["reward"], out["next_legal"], out["status"], ring.state[sl], ring.next_state[sl])
+            okc = ok.cpu().numpy()
+            tup = zip(state.cpu().numpy()[okc].tolist(), actions.cpu().numpy()[okc].tolist(),
+                      nxt.cpu().numpy()[okc].tolist(), out["reward"].cpu().numpy()[okc].tolist(),
+                      out["next_legal"].cpu().numpy()[okc].tolist(),
+                      [bytes(r) for r in ring.state[sl].cpu().numpy()[okc]],
+                      [bytes(r) for r in ring.next_state[sl].cpu().numpy()[okc]])
+            for s_, a_, n_, r_, mk, f1, f2 in tup:
+                offered += 1
+                seen.setdefault((s_, a_, n_, r_), (mk, f1, f2))
+        col.round += 1
+    st = mem.stats()
+    assert st["offered"] == offered and st["differing_duplicates"] == 0
+    assert len(mem) == st["unique"] == len(seen) > 1000
+    assert len({(s_, a_) for s_, a_, _, _ in seen}) == len(seen)        # next state and reward follow from the key
+    keys = mem.keys[:len(mem)].cpu().numpy()
+    assert np.array_equal(keys, np.array(sorted(s_ * 5 + a_ for s_, a_, _, _ in seen)))
+    nxt_all, rew_all, mask_all = mem.next.cpu().numpy(), mem.reward.cpu().numpy(), mem.mask.cpu().numpy()
+    feat_all = mem.features.cpu().numpy()
+    for (s_, a_, n_, r_), (mk, f1, f2) in seen.items():
+        k = s_ * 5 + a_
+        assert (nxt_all[k], rew_all[k], mask_all[k]) == (n_, np.float32(r_), mk)
+        assert bytes(feat_all[k, :80]) == f1 and bytes(feat_all[k, 80:]) == f2
+    # the same set as strings, the way the reference's OrderedSet sees it
+    strings = {(sc.decode(s_), "SLRFT"[a_], sc.decode(n_), r_) for s_, a_, n_, r_ in seen}
+    assert len(strings) == len(seen)
+    batch = mem.sample(32, generator=g)
+    assert len(set(batch["key"].tolist())) == 32
+    for k, s_, a_, n_, r_ in zip(batch["key"].tolist(), batch["state"].tolist(), batch["action"].tolist(),
+                                 batch["next_state"].tolist(), batch["reward"].tolist()):
+        assert k == s_ * 5 + a_ and (s_, a_, n_, r_) in seen
+    assert batch["features"].shape == (32, 80) and batch["next_features"].shape == (32, 80)
+    assert mem.sample(len(mem) + 1) is None
+
+
+@pytest.mark.parametrize("index_mode", ["reference", "action"])
+def test_double_dqn_target_matches_numpy_restatement(index_mode):
+    """The Double-DQN target (reference dqn_open_source.py:360-379) against its NumPy statement, line for line
+    (TensorFlow is absent, so the two networks' outputs are random float32 arrays): bit-identical y and target,
+    the same invalid_count.  index_mode "reference" keeps the reference's use of the POSITION inside the masked
+    sub-array as the action index; "action" maps it back."""
+    from marl_dpp_b200.dqn_feed import double_dqn_target
+    rng = np.random.default_rng(3)
+    n, discount = 4096, 0.99
+    model_predictions = rng.normal(size=(n, 5)).astype(np.float32)       # self.predict(next_states)
+    model_predictions[::7, 1] = model_predictions[::7, 3]                # ties: np.argmax takes the first
+    target_predictions = rng.normal(size=(n, 5)).astype(np.float32)      # self.target_predict(next_states)
+    predictions = rng.normal(size=(n, 5)).astype(np.float32)             # self.predict(states)
+    bits = rng.integers(1, 32, size=n).astype(np.uint8)
+    masks = [np.nonzero([(b >> k) & 1 for k in range(5)])[0] for b in bits]   # self.masks[next_state]
+    rewards = rng.choice(np.array([-1.1, -0.6, -0.1, 0.4, 1.0]), size=n)      # float64, like np.asarray(.., float)
+    actions = rng.integers(0, 5, size=n)
+    # ---- the reference's lines ----
+    max_actions, invalid_count = [], 0
+    for i, qvalues in enumerate(model_predictions):
+        overall_max_action = np.argmax(qvalues)
+        max_action = np.argmax(qvalues[masks[i]])
+        max_actions.append(max_action if index_mode == "reference" else masks[i][max_action])
+        if overall_max_action != max_action:
+            invalid_count += 1
+    max_actions = np.array(max_actions)
+    max_qvalues = np.choose(max_actions, target_predictions.T)
+    true = rewards + discount * max_qvalues
+    want = predictions.copy()
+    for i in range(len(want)):
+        want[i][actions[i]] = true[i]
+    # ---- the kernel ----
+    counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+    dev = lambda a: torch.from_numpy(a).cuda()
+    y, t = double_dqn_target(dev(model_predictions), dev(target_predictions), dev(bits), dev(rewards.astype(np.float32)),
+                             dev(actions), dev(predictions), discount, index_mode=index_mode, counters=counters)
+    # float32(-1.1) != -1.1: the kernel sees float32 rewards (what the env kernels emit); restate with the same values
+    true32 = rewards.astype(np.float32).astype(np.float64) + discount * max_qvalues
+    want32 = predictions.copy()
+    for i in range(len(want32)):
+        want32[i][actions[i]] = true32[i]
+    assert np.array_equal(y.cpu().numpy(), want32)
+    assert np.array_equal(t.cpu().numpy(), true32.astype(np.float32))
+    assert np.abs(want32 - want).max() <= 1e-6                            # vs float64 rewards: float32 storage only
+    assert counters.tolist() == [invalid_count, 0]

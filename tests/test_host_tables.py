@@ -289,3 +289,13 @@ def test_fast_tables_replay_the_oracle_env(block, boxes, idx, choose):
 def _comb_ref(n, k):
     from math import comb
     return comb(n, k) if n >= k else 0
+
+
+def test_dqn_reward_division_needs_no_float64():
+    """dqn_reward returns reward/100 in float64 (reference src/env_gym.py:553); the kernels store float32 and
+    divide in single precision.  Exhaustively: for every integer reward the kernels can produce (and far beyond)
+    the correctly rounded float32 quotient equals the float64 quotient rounded to float32."""
+    r = np.arange(-2_000_000, 2_000_001, dtype=np.int64)
+    via_f64 = (r.astype(np.float64) / 100.0).astype(np.float32)
+    via_f32 = r.astype(np.float32) / np.float32(100.0)
+    assert via_f32.dtype == np.float32 and np.array_equal(via_f64, via_f32)
