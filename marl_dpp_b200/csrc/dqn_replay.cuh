@@ -83,7 +83,8 @@ replay_check_kernel(int64_t n, const uint32_t *__restrict__ state_idx, const uin
     uint32_t differ = 0;
     if (i < n && (!status || status[i] == 0) && action[i] < MDPP_N_ACT) {
         const uint64_t k64 = (uint64_t)state_idx[i] * MDPP_N_ACT + action[i];
-        if (k64 < mem.n_keys) differ = mem.next[k64] != next_idx[i] || mem.reward[k64] != reward[i];
+        if (k64 < mem.n_keys && ((mem.present[k64 >> 5] >> (k64 & 31u)) & 1u)) // only keys an EARLIER call stored
+            differ = mem.next[k64] != next_idx[i] || mem.reward[k64] != reward[i];
     }
     differ = __reduce_add_sync(0xFFFFFFFFu, differ);
     if ((threadIdx.x & 31u) == 0 && differ) atomicAdd(mem.counters + 2, (unsigned long long)differ);

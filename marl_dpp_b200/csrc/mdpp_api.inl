@@ -974,7 +974,7 @@ static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const
 static size_t resident_smem_bytes(const mdpp_handle *h) {
     const size_t tabs = ((h->cfg.n_cars == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>)) + 15) & ~(size_t)15;
     const size_t marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
-    return tabs + ((marks + 15) / 16) * 16 + ((marks * 4 + 15) / 16) * 16;
+    return tabs + ((marks + 15) / 16) * 16 + ((marks * 4 + 15) / 16) * 16 + (((size_t)h->cfg.n_states * 4 + 15) / 16) * 16;
 }
 static int resident_rounds_fit(mdpp_handle *h, int want) {
     if (!h->mixed_rounds || !h->resident_rounds || want < 1) return 0;
@@ -983,7 +983,7 @@ static int resident_rounds_fit(mdpp_handle *h, int want) {
         int dev = 0, coop = 0, per_sm = 0;
         const void *fn = h->cfg.n_cars == 1 ? (const void *)q_rounds_resident_kernel<1> : (const void *)q_rounds_resident_kernel<2>;
         const size_t smem = resident_smem_bytes(h), marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
-        if (marks < 65536 && smem <= (size_t)227 * 1024 && h->cv.regions * (size_t)h->cv.words_per_cta >= 3 * (size_t)h->cv.words_per_cta &&
+        if (marks < 65536 && smem <= (size_t)227 * 1024 && h->cv.words_per_cta <= 2u * kRoundThreads && h->cv.regions * (size_t)h->cv.words_per_cta >= 3 * (size_t)h->cv.words_per_cta &&
             cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess &&
             coop && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kRoundThreads, smem) == cudaSuccess &&

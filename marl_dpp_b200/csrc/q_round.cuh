@@ -791,6 +791,7 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
 // grid barrier, copies refreshed from the scratch).
 // Same arithmetic in the same order as the sub-step kernels: bit-identical tables, records and counters.
 // ------------------------------------------------------------------------------------------------
+constexpr __host__ __device__ uint32_t n_warps_of(int threads) { return (uint32_t)threads / 32u; }
 struct ResidentArgs {
     uint32_t *barrier;        // the grid barrier's area: [0] arrival counter, [1] its value when a kernel starts
     float *q;                 // the table: rows of MDPP_Q_ROW floats, read at the start, written at the end
@@ -802,6 +803,11 @@ struct ResidentArgs {
     float alpha, discount;
 };
 
+// One sub-step (car slot C) over the CTA's tiles.  The decision word of car 1 travels in the record itself: with
+// 1-2 cars both car fields live in word 0, so pass 0 parks Philox word 1 in word 1 of the record and pass 1 -- which
+// gets the record through the same one-lap-ahead prefetch -- takes it from there and writes the 0 back that every
+// other kernel expects.  (Through the rng_words side array the load sat, unprefetched, at the head of every lap: an
+// exposed L2 round trip per tile.)
 template <int NC, int C>
 __device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const DevCfg &cfg, const LearnArgs &lp,
                                                   const RoundArgs &ra, const float *tq, uint64_t round, uint8_t *map,
@@ -827,9 +833,10 @@ __device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const 
             if (C == 0) { // one Philox block per env and round: word c belongs to car c
                 const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
                 word = p.x;
-                if (NC > 1) ra.rng_words[e] = p.y;
+                if (NC > 1) rec.y = p.y;
             } else {
-                word = ra.rng_words[e];
+                word = rec.y;
+                rec.y = 0u;
             }
             uint32_t key;
             bool moved, explore;
@@ -883,13 +890,14 @@ __device__ __forceinline__ void resident_flush(uint8_t *map, uint32_t map_bytes,
     }
 }
 
-// the new value of compact key m from the CTA's copy of the table (the snapshot of this sub-step)
-__device__ __forceinline__ float resident_value(const float *tq, const uint32_t *__restrict__ sinfo, uint32_t m,
-                                                uint32_t n_states, float alpha, float discount, uint32_t &key8) {
+// the new value of compact key m from the CTA's copies of the table and of the state info words (the snapshot of
+// this sub-step): shared memory only
+__device__ __forceinline__ float resident_value(const float *tq, const uint32_t *sinfo, uint32_t m, uint32_t n_states,
+                                                float alpha, float discount, uint32_t &key8) {
     const uint32_t s = m / MDPP_N_ACT, a = m - s * MDPP_N_ACT;
-    const uint32_t info = __ldg(sinfo + s);
+    const uint32_t info = sinfo[s];
     const uint32_t s2 = td_successor(s, info, a, n_states);
-    const uint32_t i2 = __ldg(sinfo + s2);
+    const uint32_t i2 = sinfo[s2];
     float ns[MDPP_Q_ROW];
 #pragma unroll
     for (int k = 0; k < MDPP_N_ACT; k++) ns[k] = tq[s2 * MDPP_N_ACT + k];
@@ -908,10 +916,12 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
     constexpr uint32_t kTabBytes = (sizeof(RoundSmem<NC>) + 15u) & ~15u;
     uint8_t *map = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes;
     float *tq = reinterpret_cast<float *>(map + ra.map_bytes);       // [n_marks] the table, compact keys
+    uint32_t *sinfo = reinterpret_cast<uint32_t *>(tq + ((rx.n_marks + 3u) & ~3u)); // [n_states] state info words
     // the pull's list of (key, new value) reuses the map's storage: values first (4-byte aligned), then 16-bit keys
     float *lvals = reinterpret_cast<float *>(map);
     uint16_t *lkeys = reinterpret_cast<uint16_t *>(map + 4u * rx.list_cap);
-    __shared__ uint32_t list_count;
+    __shared__ uint32_t warp_excl[32];
+    __shared__ uint32_t list_total;
     const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
     const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
     {
@@ -922,12 +932,13 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
             const uint32_t s = m / MDPP_N_ACT;
             tq[m] = rx.q[(size_t)s * MDPP_Q_ROW + (m - s * MDPP_N_ACT)];
         }
-        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; list_count = 0u; }
+        for (uint32_t i = threadIdx.x; i < ra.n_states; i += kRoundThreads) sinfo[i] = __ldg(rx.sinfo + i);
+        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
     }
     __syncthreads();
     StepCounts cnt;
     uint32_t touched_total = 0, sub = 0, bar = barrier_base_load(rx.barrier);
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t r = 0; r < ra.n_rounds; r++) {
         const uint64_t round = ra.round + r;
 #pragma unroll
@@ -943,50 +954,64 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
                 uint32_t *old = rx.gbits + (size_t)((sub + 2u) % 3u) * rx.words;
                 for (uint32_t wd = threadIdx.x; wd < rx.words; wd += kRoundThreads) old[wd] = 0u;
             }
-            for (uint32_t w0 = 0; w0 < rx.words; w0 += kRoundThreads) {
-                const uint32_t wd = w0 + threadIdx.x;
-                uint32_t bits = wd < rx.words ? __ldcg(gb + wd) : 0u;
-                const bool mine = wd % gridDim.x == blockIdx.x; // visited bits and the touched count: once per word
-                if (mine) touched_total += (uint32_t)__popc(bits);
-                while (__any_sync(0xFFFFFFFFu, bits != 0u)) {
-                    const bool have = bits != 0u;
-                    uint32_t m = 0, key8 = 0;
-                    float v = 0.f;
-                    if (have) {
-                        const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u;
-                        bits &= bits - 1u;
-                        m = wd * 32u + bit;
-                        v = resident_value(tq, rx.sinfo, min(m, rx.n_marks - 1u), ra.n_states, rx.alpha, rx.discount, key8);
-                        if (mine) mark_visited(rx.visited, key8);
-                    }
-                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, have);
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&list_count, (uint32_t)__popc(bal));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                    if (have && slot < rx.list_cap) {
-                        lvals[slot] = v;
-                        lkeys[slot] = (uint16_t)m;
-                    }
+            // (a) the marked keys, in ascending order, into the list: thread t owns words 2t and 2t + 1 (block scan of
+            //     the popcounts; no atomics, the same list in every CTA)
+            const uint32_t w0 = 2u * threadIdx.x, w1 = w0 + 1u;
+            uint32_t b0 = w0 < rx.words ? __ldcg(gb + w0) : 0u, b1 = w1 < rx.words ? __ldcg(gb + w1) : 0u;
+            const uint32_t cntk = (uint32_t)(__popc(b0) + __popc(b1));
+            uint32_t incl = cntk;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += y;
+            }
+            if (lane == 31u) warp_excl[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t sw = warp_excl[lane];
+                uint32_t tw = sw;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw, o);
+                    if (lane >= (uint32_t)o) tw += y;
                 }
+                warp_excl[lane] = tw - sw;
+                if (lane == 31u) list_total = tw;
             }
             __syncthreads();
-            const uint32_t n_list = list_count;
+            const uint32_t n_list = list_total;
             if (n_list <= rx.list_cap) {
-                for (uint32_t i = threadIdx.x; i < n_list; i += kRoundThreads) tq[lkeys[i]] = lvals[i];
+                uint32_t slot = warp_excl[warp] + incl - cntk;
+                while (b0) { lkeys[slot++] = (uint16_t)(w0 * 32u + (uint32_t)__ffs((int)b0) - 1u); b0 &= b0 - 1u; }
+                while (b1) { lkeys[slot++] = (uint16_t)(w1 * 32u + (uint32_t)__ffs((int)b1) - 1u); b1 &= b1 - 1u; }
+                __syncthreads();
+                // (b) one key per thread: its new value from the untouched copy; visited bits and the touched count
+                //     once per key (entry i belongs to CTA i % G)
+                for (uint32_t i = threadIdx.x; i < n_list; i += kRoundThreads) {
+                    uint32_t key8;
+                    const uint32_t m = min((uint32_t)lkeys[i], rx.n_marks - 1u);
+                    lvals[i] = resident_value(tq, sinfo, m, ra.n_states, rx.alpha, rx.discount, key8);
+                    if (i % gridDim.x == blockIdx.x) {
+                        mark_visited(rx.visited, key8);
+                        touched_total++;
+                    }
+                }
+                __syncthreads();
+                // (c) every value was computed from the snapshot: write them
+                for (uint32_t i = threadIdx.x; i < n_list; i += kRoundThreads) tq[min((uint32_t)lkeys[i], rx.n_marks - 1u)] = lvals[i];
                 __syncthreads();
             } else {
                 // overflow (the same count in every CTA): this sub-step's pull through global memory.  CTA b owns the
                 // words w with w % G == b, computes their keys' values from its intact copy into the scratch table,
                 // and after one more grid barrier every CTA refreshes the marked keys of its copy from there.
-                for (uint32_t wd = blockIdx.x; wd < rx.words; wd += gridDim.x) {
+                for (uint32_t wd = blockIdx.x * n_warps_of(kRoundThreads) + warp; wd < rx.words; wd += gridDim.x * n_warps_of(kRoundThreads)) {
                     const uint32_t bits = __ldcg(gb + wd);
                     if ((bits >> lane) & 1u) {
-                        if (threadIdx.x < 32u) {
-                            uint32_t key8;
-                            const uint32_t m = wd * 32u + lane;
-                            rx.scratch[m] = resident_value(tq, rx.sinfo, min(m, rx.n_marks - 1u), ra.n_states, rx.alpha, rx.discount, key8);
-                        }
+                        uint32_t key8;
+                        const uint32_t m = min(wd * 32u + lane, rx.n_marks - 1u);
+                        rx.scratch[m] = resident_value(tq, sinfo, m, ra.n_states, rx.alpha, rx.discount, key8);
+                        mark_visited(rx.visited, key8);
+                        touched_total++;
                     }
                 }
                 grid_barrier(rx.barrier, bar += gridDim.x);
@@ -1007,7 +1032,6 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
                 const uint32_t v16 = (used * 4u + 15u) >> 4, k0 = (4u * rx.list_cap) >> 4, k16 = (used * 2u + 15u) >> 4;
                 for (uint32_t i = threadIdx.x; i < v16; i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
                 for (uint32_t i = threadIdx.x; i < k16; i += kRoundThreads) m4[k0 + i] = make_uint4(0u, 0u, 0u, 0u);
-                if (threadIdx.x == 0) list_count = 0u;
             }
             __syncthreads();
         }
