@@ -213,6 +213,9 @@ int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learne
  * that bench.py can time the dominant kernel alone with CUDA events.  The marks it leaves are never
  * pulled: use it on a handle you do not train further. */
 int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t round, void *stream);
+/* the same for the multi-round launch: ONLY the env kernel of `rounds` (2..8) pure-exploration rounds */
+int mdpp_q_profile_env_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t round, int rounds,
+                              void *stream);
 
 /* ---- multi-GPU: Q-replica averaging over NVLink peer memory ------------------------------------------
  * No reference counterpart (the reference is one process): every GPU of a node trains its own
@@ -251,6 +254,10 @@ uint64_t mdpp_sync_count(mdpp_handle *h);
  * cooperative launch that runs every rank's slices with the same code, handshakes included.  (Kernels that wait
  * on one another must never be separate launches on one GPU.)  handles[r] must be attached as rank r of `world`. */
 int mdpp_sync_emulate(mdpp_handle *const *handles, int world, void *stream);
+
+/* Profiling hook: with MDPP_STAMPS=1 in the environment q_rounds_resident_kernel records %globaltimer at its phase
+ * boundaries in three of its CTAs; this copies the first n (<= 96) 64-bit words back (synchronises the device). */
+int mdpp_debug_stamps(uint64_t *out_host, int n);
 
 /* ---- DQN feed: the env-facing half of the noisy double DQN's collection loop (reference
  * src/algorithms/dqn_open_source.py:490-526); the MLP stays in PyTorch.  observe = encodestate(car, 1)

@@ -313,12 +313,14 @@ class BatchedQLearner:
         self.round += int(rounds)
         return s.as_dict()
 
-    def profile_env_kernel(self):
-        """Profiling hook: only the env-side kernel of one fused round (its marks are never pulled)."""
+    def profile_env_kernel(self, rounds=1):
+        """Profiling hook: only the env-side kernel of `rounds` fused rounds (1: the round kernel; 2..8: the
+        multi-round pure-exploration kernel); its marks are never pulled."""
         env = self.env
         with torch.cuda.device(env.device):
-            _lib.check(env._L.mdpp_q_profile_env_kernel(env._h, _ptr(self.q), C.byref(self.params), self.round, _stream()))
-        self.round += 1
+            _lib.check(env._L.mdpp_q_profile_env_rounds(env._h, _ptr(self.q), C.byref(self.params), self.round,
+                                                        int(rounds), _stream()))
+        self.round += int(rounds)
 
     def sync_replicas(self, group=None):
         """Average the per-GPU Q replicas now.  With a PeerExchange attached (parallel.PeerExchange.attach):

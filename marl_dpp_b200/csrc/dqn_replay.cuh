@@ -163,7 +163,8 @@ dqn_target_kernel(int64_t n, const float *__restrict__ q_online_next, const floa
         if (best_pos < 0) { empty = 1; best_pos = 0; best_act = 0; } // the reference raises on an empty mask
         invalid = overall != best_pos;                              // `overall_max_action != max_action` (:367)
         const int idx = index_mode == 0 ? best_pos : best_act;
-        const float t = (float)((double)reward[i] + discount * (double)qt[idx]);
+        // NumPy rounds the product and the sum separately: no fused multiply-add
+        const float t = (float)__dadd_rn((double)reward[i], __dmul_rn(discount, (double)qt[idx]));
 #pragma unroll
         for (int k = 0; k < MDPP_N_ACT; k++) y[i * MDPP_N_ACT + k] = prediction[i * MDPP_N_ACT + k];
         const int64_t a = action[i];

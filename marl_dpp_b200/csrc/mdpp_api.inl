@@ -497,11 +497,15 @@ int mdpp_rollout_random(mdpp_handle *h, int rounds, uint64_t first_round, uint32
             const size_t smem = lean ? sizeof(LeanTabs<NCV>) : sizeof(RoundSmem<NCV>);                           \
             if (!((h->smem_configured >> 27) & 1u)) {                                                            \
                 MDPP_CUDA(cudaFuncSetAttribute(rollout_fast_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem<NCV>))); \
-                MDPP_CUDA(cudaFuncSetAttribute(rollout_lean_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanTabs<NCV>))); \
+                MDPP_CUDA(cudaFuncSetAttribute(rollout_lean_kernel<NCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanTabs<NCV>))); \
+                MDPP_CUDA(cudaFuncSetAttribute(rollout_lean_kernel<NCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeanTabs<NCV>))); \
                 h->smem_configured |= 1u << 27;                                                                  \
             }                                                                                                    \
-            if (lean)                                                                                            \
-                rollout_lean_kernel<NCV><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs, \
+            if (lean && action && reward && done && next_idx)                                                    \
+                rollout_lean_kernel<NCV, true><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs, \
+                        h->env_id_base, rounds, first_round, seed, reward_kind, out, tabs, stride, control_of(h)); \
+            else if (lean)                                                                                       \
+                rollout_lean_kernel<NCV, false><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs, \
                         h->env_id_base, rounds, first_round, seed, reward_kind, out, tabs, stride, control_of(h)); \
             else                                                                                                 \
                 rollout_fast_kernel<NCV><<<grid, kRolloutThreads, smem, s>>>(h->dev, recs_of(h), (uint32_t)h->n_envs, \
@@ -809,7 +813,7 @@ static int pure_rounds_fit(const mdpp_handle *h, const mdpp_learner *lp, int wan
     return n >= 2 ? n : 0;
 }
 static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round, int n,
-                                cudaStream_t s) {
+                                cudaStream_t s, bool env_only = false) {
     const uint32_t P = h->round_parity;
     h->round_parity ^= 1u;
     h->ep_bound += n;
@@ -852,6 +856,7 @@ static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const 
         }
         h->chain = true;
     }
+    if (env_only) return MDPP_OK; // profiling hook: the marks are never pulled
     Marks mk = marks_of(h);
     mk.n_ctas = grid;
     // the pulls of all n * nc sub-steps in two launches when one cluster can hold the table (q_round.cuh)
@@ -1027,6 +1032,7 @@ static int q_resident_rounds_launch(mdpp_handle *h, float *cur, const mdpp_learn
     if (const char *e = getenv("MDPP_RESIDENT_LIST_CAP")) rx.list_cap = std::min<uint32_t>(rx.list_cap, (uint32_t)atoi(e) & ~3u); // tests: force the overflow path
     rx.alpha = lp->alpha;
     rx.discount = lp->discount;
+    rx.stamps = getenv("MDPP_STAMPS") && atoi(getenv("MDPP_STAMPS")) != 0 ? 1u : 0u;
     MDPP_CUDA(cudaMemsetAsync(rx.gbits, 0, (size_t)3 * rx.words * 4, s)); // the three mark bitmaps start clear
     const size_t smem = resident_smem_bytes(h);
     mdpp_learner lpv = *lp;
@@ -1587,6 +1593,27 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
     }
     h->ep_bound += 1;
     return MDPP_OK;
+}
+
+int mdpp_debug_stamps(uint64_t *out_host, int n) {
+    if (!out_host || n <= 0 || n > 3 * kStampSlots) return fail(MDPP_EINVAL, "mdpp_debug_stamps: 1..%d words", 3 * kStampSlots);
+    MDPP_CUDA(cudaDeviceSynchronize());
+    MDPP_CUDA(cudaMemcpyFromSymbol(out_host, g_stamps, (size_t)n * 8));
+    return MDPP_OK;
+}
+
+int mdpp_q_profile_env_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64_t round, int rounds, void *stream) {
+    if (rounds == 1) return mdpp_q_profile_env_kernel(h, q, lp, round, stream);
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
+    if (lp->flags != 0 || !round_eligible(h)) return fail(MDPP_EINVAL, "no fused round kernel for this table / these flags");
+    if (pure_rounds_fit(h, lp, rounds) != rounds)
+        return fail(MDPP_EINVAL, "%d rounds do not fit one pure-exploration launch here (2..%d, every env in the epsilon = 1 segment)", rounds, kMaxPureRounds);
+    h->chain = false;
+    float *cur = q, *alt = q;
+    int rc = q_pure_rounds_launch(h, cur, alt, lp, round, rounds, (cudaStream_t)stream, true);
+    h->chain = false;
+    return rc;
 }
 
 int mdpp_q_train_rounds_host(mdpp_handle *h, float *q, const mdpp_learner *lp_host, uint64_t first_round, int rounds,

@@ -792,6 +792,19 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
 // Same arithmetic in the same order as the sub-step kernels: bit-identical tables, records and counters.
 // ------------------------------------------------------------------------------------------------
 constexpr __host__ __device__ uint32_t n_warps_of(int threads) { return (uint32_t)threads / 32u; }
+// Phase timestamps of q_rounds_resident_kernel (MDPP_STAMPS=1; read back with mdpp_debug_stamps): CTAs 0, G/2 and
+// G-1 store %globaltimer after staging and, for the first 6 sub-steps, after the env pass, the map flush, the grid
+// barrier, the pull and the list clean-up.  Temporary-instrumentation style of DESIGN.md 4.2, kept as a hook.
+constexpr int kStampSlots = 32;
+__device__ unsigned long long g_stamps[3][kStampSlots];
+__device__ __forceinline__ void stamp(uint32_t enabled, uint32_t slot) {
+    if (!enabled || threadIdx.x != 0 || slot >= (uint32_t)kStampSlots) return;
+    const int which = blockIdx.x == 0 ? 0 : blockIdx.x == gridDim.x / 2 ? 1 : blockIdx.x == gridDim.x - 1 ? 2 : -1;
+    if (which < 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_stamps[which][slot] = t;
+}
 struct ResidentArgs {
     uint32_t *barrier;        // the grid barrier's area: [0] arrival counter, [1] its value when a kernel starts
     float *q;                 // the table: rows of MDPP_Q_ROW floats, read at the start, written at the end
@@ -801,6 +814,7 @@ struct ResidentArgs {
     uint32_t *visited;
     uint32_t n_marks, words, list_cap;
     float alpha, discount;
+    uint32_t stamps;          // MDPP_STAMPS=1: phase timestamps into g_stamps
 };
 
 // One sub-step (car slot C) over the CTA's tiles.  The decision word of car 1 travels in the record itself: with
@@ -936,6 +950,7 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
         if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
     }
     __syncthreads();
+    stamp(rx.stamps, 0u);
     StepCounts cnt;
     uint32_t touched_total = 0, sub = 0, bar = barrier_base_load(rx.barrier);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -947,8 +962,11 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
             if (c == 0) resident_env_pass<NC, 0>(S, cfg, lp, ra, tq, round, map, t0, t1, cnt);
             else resident_env_pass<NC, (NC > 1 ? 1 : 0)>(S, cfg, lp, ra, tq, round, map, t0, t1, cnt);
             __syncthreads();
+            stamp(rx.stamps, 1u + 5u * sub);
             resident_flush(map, ra.map_bytes, rx.words, gb);
+            stamp(rx.stamps, 2u + 5u * sub);
             grid_barrier(rx.barrier, bar += gridDim.x);
+            stamp(rx.stamps, 3u + 5u * sub);
             // ---- the pull of this sub-step, applied to the CTA's own copy ----
             if (blockIdx.x == 0) { // the buffer of the previous sub-step: everybody finished reading it before this barrier
                 uint32_t *old = rx.gbits + (size_t)((sub + 2u) % 3u) * rx.words;
@@ -1025,6 +1043,7 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
                 }
                 __syncthreads();
             }
+            stamp(rx.stamps, 4u + 5u * sub);
             // the list overwrote the map's storage: clear what it used before the next pass marks again
             {
                 uint4 *m4 = reinterpret_cast<uint4 *>(map);
@@ -1034,6 +1053,7 @@ q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx
                 for (uint32_t i = threadIdx.x; i < k16; i += kRoundThreads) m4[k0 + i] = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncthreads();
+            stamp(rx.stamps, 5u + 5u * sub);
         }
     }
     // the table goes home: CTA b writes the b-th slice of its copy (all copies are identical)
@@ -1238,10 +1258,12 @@ rollout_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
 // always 0 (a listed car blocks its box number, a finished car stands on the parking node, which is no box), which
 // is what the learner's pull relies on too; the oracle comparison of every reward (1-5 cars) pins it.
 // ------------------------------------------------------------------------------------------------
-template <int NC, int C>
+// ALL: every output array is present (the sweep's configuration): no per-store null tests, and the four addresses
+// advance by pointer increments instead of being rebuilt from a 64-bit index.
+template <int NC, int C, bool ALL>
 __device__ __forceinline__ void lean_rollout_chain(const LeanTabs<NC> &S, const DevCfg &cfg, uint32_t rank_stride, int kind,
                                                    uint32_t (&f)[NC], const uint32_t (&w)[NC], uint32_t &steps, uint32_t &n_steps,
-                                                   int32_t &rsum, const RolloutOut &out, size_t o, size_t n_envs) {
+                                                   int32_t &rsum, RolloutOut &out, size_t n_envs) {
     uint32_t a = MDPP_ACT_SKIP, nidx = 0xFFFFFFFFu;
     float rw = 0.f;
     const uint32_t fc = f[C];
@@ -1271,19 +1293,24 @@ __device__ __forceinline__ void lean_rollout_chain(const LeanTabs<NC> &S, const 
             rsum += ri;
         }
     }
-    if (out.action) out.action[o] = (uint8_t)a;
-    if (out.reward) out.reward[o] = rw;
-    if (out.next) out.next[o] = nidx;
-    if (out.done) {
+    if (ALL || out.action) *out.action = (uint8_t)a;
+    if (ALL || out.reward) *out.reward = rw;
+    if (ALL || out.next) *out.next = nidx;
+    if (ALL || out.done) {
         uint32_t d = f[0];
 #pragma unroll
         for (int i = 1; i < NC; i++) d &= f[i];
-        out.done[o] = (uint8_t)((d >> 8) & 1u);
+        *out.done = (uint8_t)((d >> 8) & 1u);
     }
-    if constexpr (C + 1 < NC) lean_rollout_chain<NC, C + 1>(S, cfg, rank_stride, kind, f, w, steps, n_steps, rsum, out, o + n_envs, n_envs);
+    // the next car-step's slot of every output: one row of n_envs further
+    if (ALL || out.action) out.action += n_envs;
+    if (ALL || out.reward) out.reward += n_envs;
+    if (ALL || out.next) out.next += n_envs;
+    if (ALL || out.done) out.done += n_envs;
+    if constexpr (C + 1 < NC) lean_rollout_chain<NC, C + 1, ALL>(S, cfg, rank_stride, kind, f, w, steps, n_steps, rsum, out, n_envs);
 }
 
-template <int NC>
+template <int NC, bool ALL>
 __global__ void __launch_bounds__(kRolloutThreads, 4)
 rollout_lean_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint32_t env_id_base, int rounds,
                     uint64_t first_round, uint32_t seed, int kind, RolloutOut out, const FastTabs *__restrict__ tabs,
@@ -1301,10 +1328,13 @@ rollout_lean_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     StepCounts cnt;
     long long rsum = 0;
+    uint4 rec_next = make_uint4(0u, 0u, 0u, 0u); // the next tile's records are in flight during this tile's work
+    if (t0 + warp < t1 && (t0 + warp) * 32u + lane < n_envs) rec_next = recs[(t0 + warp) * 32u + lane];
     for (uint32_t t = t0 + warp; t < t1; t += n_warps) {
         const uint32_t e = t * 32u + lane;
+        uint4 rec = rec_next;
+        if (t + n_warps < t1 && (t + n_warps) * 32u + lane < n_envs) rec_next = recs[(t + n_warps) * 32u + lane];
         if (e >= n_envs) continue;
-        uint4 rec = recs[e];
         uint32_t f[NC];
         {
             const uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
@@ -1324,8 +1354,13 @@ rollout_lean_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
             if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
             if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
             int32_t rr = 0;
-            lean_rollout_chain<NC, 0>(S, cfg, rank_stride, kind, f, w, steps, cnt.steps, rr, out,
-                                      (size_t)r * NC * (size_t)n_envs + e, (size_t)n_envs);
+            RolloutOut o = out; // this env's slot of car 0 in round r
+            const size_t off = (size_t)r * NC * (size_t)n_envs + e;
+            if (ALL || o.action) o.action += off;
+            if (ALL || o.reward) o.reward += off;
+            if (ALL || o.next) o.next += off;
+            if (ALL || o.done) o.done += off;
+            lean_rollout_chain<NC, 0, ALL>(S, cfg, rank_stride, kind, f, w, steps, cnt.steps, rr, o, (size_t)n_envs);
             rtile += rr;
             if ((r & 63) == 63) { rsum += rtile; rtile = 0; } // |reward| <= 1e5 per step: 64 rounds x 5 cars fit 32 bits
             steps = min(steps, 0xFFFFu);
