@@ -4,9 +4,13 @@
 Workload (BASELINE.json configs[1]): tabular Q-learning on layout 3 block 2 (down_right), the
 layout's live initial state (2 cars), bad-states ON, 2^20 lockstep envs per GPU, reference
 hyper-parameters (alpha 0.9, gamma 0.15, epsilon model 3, 5000 episodes per env, step cap
-10000).  One "step" = one round-robin round over every env of the batch: the round kernel (every
-car of every env: select, step, mark the touched keys) + one pull kernel per car slot (the
-reference TD update, once per touched key).  Metric: agent-env-steps/s (== Q-updates/s on this path).
+10000).  One "step" = one call of the library's training entry point at the granularity it launches
+at while every env explores: 8 round-robin rounds over every env of the batch = ONE env-kernel launch
+(q_rounds_pure_kernel: every car of every env, 8 rounds: select, step, mark the touched keys) + the
+pulls of its 16 sub-steps in two more launches (bitmap reduce + cluster pull: the reference TD update,
+once per touched key).  The former definition -- one round per step, round kernel + two dense pulls --
+is measured the same way and reported as aux.one_round_per_step.  Metric: agent-env-steps/s
+(== Q-updates/s on this path).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -204,6 +208,7 @@ def main():
                     help="rounds between Q-replica averagings (N>1); default min(64, max(1, steps // 4)): at least four "
                          "inside the timed region; 0 = never")
     ap.add_argument("--preroll", type=int, default=PREROLL_ROUNDS, help="untimed rounds before the timed region")
+    ap.add_argument("--rounds-per-step", type=int, default=8, help="rounds per timed step (one train_rounds call); 1..8")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary (random-rollout, gym e2e) lines")
     ap.add_argument("--full-training", type=int, default=1,
@@ -246,7 +251,9 @@ def main():
     env = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=3)
     # N > 1: the table lives in a peer-mapped exchange buffer and the library averages the replicas with its own
     # kernel inside train_rounds (csrc/q_sync.cuh); a table too large for that would use NCCL (not this workload)
-    interval = args.sync_interval if args.sync_interval >= 0 else min(64, max(1, args.steps // 4))
+    RPS = max(1, min(8, args.rounds_per_step))
+    # default: at least four exchanges inside the timed region, at most every 64 rounds, on step boundaries
+    interval = args.sync_interval if args.sync_interval >= 0 else min(64, max(RPS, (args.steps * RPS // 4) // RPS * RPS))
     exchange, sync_kind = None, None
     if world > 1:
         from marl_dpp_b200.parallel import PeerExchange
@@ -286,7 +293,7 @@ def main():
         done += c
         env.stats()   # lets the library tighten its bound on the episode counters
     for i in range(args.warmup):
-        lr.train_rounds(1)
+        lr.train_rounds(RPS)
         after_step()
     barrier()
     env.stats(reset=True)
@@ -303,10 +310,10 @@ def main():
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
-        lr.train_rounds(1)
+        lr.train_rounds(RPS)
         after_step()
         ev[i][1].record()
-        if (i + 1) % 256 == 0:
+        if (i + 1) % 32 == 0:
             # outside the event pair: a counter fetch (synchronises) lets the library tighten its bound on the
             # envs' episode counters, i.e. keep skipping the catch-up kernel while every env explores
             st_mid = env.stats()
@@ -325,7 +332,7 @@ def main():
         dev_ms = float(tmax[0])
     total_steps, total_upd = float(t[1]), float(t[2])
     value = total_steps / (dev_ms * 1e-3)
-    active_fraction = total_steps / (float(args.steps) * n * k * world)
+    active_fraction = total_steps / (float(args.steps) * RPS * n * k * world)
 
     # the exchange alone, in this run: back-to-back explicit averagings, device-timed, max over ranks
     sync_us = None
@@ -349,7 +356,7 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()           # the L2 flush is outside the timed window
         t0 = time.perf_counter()
-        lr.train_rounds_host(1)  # learner params from host memory in, mdpp_stats back, stream synchronised
+        lr.train_rounds_host(RPS)  # learner params from host memory in, the counters back in host memory
         if world > 1 and not exchange and interval > 0 and lr.round % interval == 0:
             lr.sync_replicas()
             torch.cuda.synchronize()
@@ -374,23 +381,27 @@ def main():
         units = total_steps / world / args.steps
         step_ms = dev_ms / args.steps
         achieved = FUSED_Q_BYTES_PER_STEP(k) * units / (step_ms * 1e-3) / 1e9
-        envp = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=3)
-        lrp = BatchedQLearner(envp, episodes=EPISODES, seed=3)
-        for _ in range(0, args.preroll, 256):   # the same stationary mix as the timed region
-            lrp.train_rounds(min(256, args.preroll))
-            envp.stats()
-        lrp.train_rounds(args.warmup)
-        kev = []
-        for i in range(min(args.steps, 200)):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            lrp.profile_env_kernel()
-            b.record()
-            kev.append((a, b))
-        torch.cuda.synchronize()
-        k0_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
-        del lrp, envp
+        def env_kernel_alone(rounds, reps):
+            """The env kernel of `rounds` rounds alone (profiling hook: its marks are never pulled), on a batch
+            rolled to the same stationary mix, CUDA events, L2 flushed before every launch -> ms per launch."""
+            envp = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=3)
+            lrp = BatchedQLearner(envp, episodes=EPISODES, seed=3)
+            for _ in range(0, args.preroll, 256):
+                lrp.train_rounds(min(256, args.preroll))
+                envp.stats()
+            kev = []
+            for i in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                lrp.profile_env_kernel(rounds)
+                b.record()
+                kev.append((a, b))
+                if (i + 1) % 32 == 0:
+                    envp.stats()
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+        k0_ms = env_kernel_alone(RPS, min(args.steps, 200))
         # what an event pair measures with NOTHING between the records, after the same flush: every per-step number
         # above contains this much launch / event latency (chained rounds hide it, see aux)
         eev = []
@@ -414,14 +425,17 @@ def main():
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "one round = q_round_kernel<%d,0> + %d x q_pull_dense_kernel" % (k, k),
+                "kernel": ("one step = %d rounds = q_rounds_pure_kernel<%d> + q_marks_reduce_kernel + q_multi_pull_kernel"
+                           % (RPS, k)) if RPS > 1 else
+                          "one round = q_round_kernel<%d,0> + %d x q_pull_dense_kernel" % (k, k),
                 "avg_launch_ms": step_ms, "units_per_launch": units, "empty_event_pair_ms": empty_ms,
                 "algorithmic_bytes_per_unit": FUSED_Q_BYTES_PER_STEP(k), "peak_source": how,
-                "dominant_kernel": {"name": "q_round_kernel<%d,0>" % k, "avg_launch_ms": k0_ms,
+                "dominant_kernel": {"name": ("q_rounds_pure_kernel<%d>" if RPS > 1 else "q_round_kernel<%d,0>") % k,
+                                    "avg_launch_ms": k0_ms,
                                     "share_of_step": k0_ms / step_ms,
                                     "how": "timed alone with CUDA events, L2 flushed before every launch"},
-                "note": "frac counts the whole round (round kernel + pulls) against the algorithmic bytes of fused "
-                        "Q-learning; the round kernel is bound by the integer ALU pipe (ncu: math_pipe_throttle), "
+                "note": "frac counts the whole step (env kernel + pulls) against the algorithmic bytes of fused "
+                        "Q-learning; the env kernel is bound by instruction issue / the integer ALU pipe (ncu), "
                         "records and table are L2-resident at this size, so DRAM traffic is below the algorithmic bytes"}
 
     # ---- secondary lines (not the headline): random-policy rollout and gym-style host stepping ----
@@ -456,6 +470,36 @@ def main():
             aux["sync_interval_sweep"] = {"unit": UNIT, "rounds_per_point": 256, "points": sweep,
                                           "note": "rounds back to back (L2 warm), replicas averaged by q_sync_kernel "
                                                   "before every round R with R % interval == 0"}
+    if rank == 0 and world == 1 and not args.no_aux and RPS > 1:
+        # the former headline definition, measured the same way: ONE round per step = round kernel + two dense pulls
+        env1 = BatchedEnv(sc, n, device=dev, seed=3)
+        lr1 = BatchedQLearner(env1, episodes=EPISODES, seed=3)
+        for _ in range(0, args.preroll, 256):
+            lr1.train_rounds(min(256, args.preroll))
+            env1.stats()
+        env1.stats(reset=True)
+        ev1 = []
+        for i in range(min(args.steps * RPS, 400)):
+            flush.zero_()
+            a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a1.record()
+            lr1.train_rounds(1)
+            b1.record()
+            ev1.append((a1, b1))
+            if (i + 1) % 128 == 0:
+                env1.stats()
+        torch.cuda.synchronize()
+        s1 = env1.stats(reset=True)
+        ms1 = sum(x.elapsed_time(y) for x, y in ev1)
+        k1_ms = env_kernel_alone(1, 200)
+        aux["one_round_per_step"] = {
+            "value": s1["agent_steps"] / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / len(ev1),
+            "frac_of_hbm_roofline": FUSED_Q_BYTES_PER_STEP(k) * s1["agent_steps"] / (ms1 * 1e-3) / 1e9 / measured_peak()[0],
+            "dominant_kernel": {"name": "q_round_kernel<%d,0>" % k, "avg_launch_ms": k1_ms,
+                                "share_of_step": k1_ms / (ms1 / len(ev1))},
+            "note": "round 1's headline definition: one round per timed step (q_round_kernel + two q_pull_dense_kernel), "
+                    "L2 flushed before every step, per-step events, stationary mix"}
+        del lr1, env1
     if rank == 0 and world == 1 and not args.no_aux:
         # the same learner, rounds launched back to back (no flush, no per-round events): training throughput
         enva = BatchedEnv(sc, n, device=dev, seed=3)
@@ -675,7 +719,12 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(), n_cars=k, envs_per_gpu=n, **{
-                       "step": "one round-robin round over every env = q_round_kernel (all cars) + one q_pull_dense_kernel per car slot",
+                       "rounds_per_step": RPS,
+                       "step": ("one train_rounds(%d) call = %d round-robin rounds over every env = one q_rounds_pure_kernel "
+                                "launch (all cars, all rounds) + q_marks_reduce_kernel + q_multi_pull_kernel (the %d sub-steps' "
+                                "updates); aux.one_round_per_step holds the one-round-per-step figures" % (RPS, RPS, RPS * k))
+                               if RPS > 1 else
+                               "one round-robin round over every env = q_round_kernel (all cars) + one q_pull_dense_kernel per car slot",
                        "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
                        "preroll_rounds": args.preroll, "active_fraction": active_fraction,
                        "sync_interval_rounds": interval if world > 1 else None,

@@ -255,10 +255,6 @@ uint64_t mdpp_sync_count(mdpp_handle *h);
  * on one another must never be separate launches on one GPU.)  handles[r] must be attached as rank r of `world`. */
 int mdpp_sync_emulate(mdpp_handle *const *handles, int world, void *stream);
 
-/* Profiling hook: with MDPP_STAMPS=1 in the environment q_rounds_resident_kernel records %globaltimer at its phase
- * boundaries in three of its CTAs; this copies the first n (<= 96) 64-bit words back (synchronises the device). */
-int mdpp_debug_stamps(uint64_t *out_host, int n);
-
 /* ---- DQN feed: the env-facing half of the noisy double DQN's collection loop (reference
  * src/algorithms/dqn_open_source.py:490-526); the MLP stays in PyTorch.  observe = encodestate(car, 1)
  * (ghost side effect included) -> RL.convert(state) as 80 {0,1} bytes per env (:245-313) + give_mask

@@ -19,7 +19,7 @@ EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_err
            "mdpp_env_records", "mdpp_visited_bits", "mdpp_deadlock_states", "mdpp_launch_count", "mdpp_query_transitions",
            "mdpp_update_car", "mdpp_dqn_observe", "mdpp_dqn_act", "mdpp_joint_state_count", "mdpp_deadlock_reachability", "mdpp_reset", "mdpp_step_car", "mdpp_step_car_host",
            "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
-           "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_q_profile_env_rounds", "mdpp_debug_stamps", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host",
+           "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_q_profile_env_rounds", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host",
            "mdpp_sync_buffer_bytes", "mdpp_sync_alloc", "mdpp_sync_free", "mdpp_sync_open", "mdpp_sync_close", "mdpp_sync_attach",
            "mdpp_q_sync_replicas", "mdpp_sync_count", "mdpp_sync_emulate", "mdpp_deadlock_scratch_bytes",
            "mdpp_deadlock_reachability_bfs", "mdpp_replay_insert", "mdpp_replay_compact", "mdpp_dqn_target"]
@@ -81,7 +81,6 @@ def lib():
         "mdpp_q_train_rounds_host": (I, [P, F32, P, U64, I, P, P]),
         "mdpp_q_profile_env_kernel": (I, [P, F32, P, U64, P]),
         "mdpp_q_profile_env_rounds": (I, [P, F32, P, U64, I, P]),
-        "mdpp_debug_stamps": (I, [P, I]),
         "mdpp_fast_tables": (I64, [P, P, I64]),
         "mdpp_decode_state": (I, [P, I64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "mdpp_encode_state": (I64, [P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),

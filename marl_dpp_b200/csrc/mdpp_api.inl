@@ -88,7 +88,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     }
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
-    c.barrier = take(64); // grid barrier of the cooperative kernels: [0] arrival counter (only ever grows), [1] its value at the next kernel's start; zero at create
+    c.barrier = take(512); // grid barrier of the cooperative kernels: word 0 arrival counter (only ever grows), word 1 its value at the next kernel's start, word 64 the release flag; zero at create
     c.stage = take((size_t)n_envs * 16);
     c.dl = take((size_t)n_envs * 4);
     c.total = off;
@@ -111,8 +111,6 @@ struct mdpp_handle {
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
     bool k1_rounds;         // MDPP_K1_ROUNDS=1: rounds with greedy decisions through the fused K0 / K1 pair as well
     bool mixed_rounds;      // rounds with greedy decisions: several per cooperative launch (MDPP_MIXED_ROUNDS=0: sub-step kernels)
-    bool resident_rounds;   // ... with the table resident in every CTA's shared memory (MDPP_RESIDENT_ROUNDS=0: q_rounds_mixed_kernel)
-    int resident_ok;        // -1 unknown, 0 does not fit / not co-resident, 1 ok
     int coop_ok;            // -1 unknown, 0 no cooperative launch / not co-resident, 1 ok
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
     bool multi_pull;        // ... followed by one reduce + one cluster pull launch (MDPP_MULTI_PULL=0: dense pulls)
@@ -323,8 +321,6 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->k1_rounds = getenv("MDPP_K1_ROUNDS") && atoi(getenv("MDPP_K1_ROUNDS")) != 0;
     h->mixed_rounds = !(getenv("MDPP_MIXED_ROUNDS") && atoi(getenv("MDPP_MIXED_ROUNDS")) == 0);
     h->coop_ok = -1;
-    h->resident_rounds = !(getenv("MDPP_RESIDENT_ROUNDS") && atoi(getenv("MDPP_RESIDENT_ROUNDS")) == 0);
-    h->resident_ok = -1;
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
     h->chain = false;
@@ -975,75 +971,6 @@ static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const
     return MDPP_OK;
 }
 
-// n rounds WITH greedy decisions, the table resident in shared memory (q_rounds_resident_kernel): updated in place.
-static size_t resident_smem_bytes(const mdpp_handle *h) {
-    const size_t tabs = ((h->cfg.n_cars == 1 ? sizeof(RoundSmem<1>) : sizeof(RoundSmem<2>)) + 15) & ~(size_t)15;
-    const size_t marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
-    return tabs + ((marks + 15) / 16) * 16 + ((marks * 4 + 15) / 16) * 16 + (((size_t)h->cfg.n_states * 4 + 15) / 16) * 16;
-}
-static int resident_rounds_fit(mdpp_handle *h, int want) {
-    if (!h->mixed_rounds || !h->resident_rounds || want < 1) return 0;
-    if (h->resident_ok < 0) {
-        h->resident_ok = 0;
-        int dev = 0, coop = 0, per_sm = 0;
-        const void *fn = h->cfg.n_cars == 1 ? (const void *)q_rounds_resident_kernel<1> : (const void *)q_rounds_resident_kernel<2>;
-        const size_t smem = resident_smem_bytes(h), marks = (size_t)h->cfg.n_states * MDPP_N_ACT;
-        if (marks < 65536 && smem <= (size_t)227 * 1024 && h->cv.words_per_cta <= 2u * kRoundThreads && h->cv.regions * (size_t)h->cv.words_per_cta >= 3 * (size_t)h->cv.words_per_cta &&
-            cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess &&
-            coop && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kRoundThreads, smem) == cudaSuccess &&
-            (int64_t)per_sm * h->sm_count >= (int64_t)round_ctas(h))
-            h->resident_ok = 1;
-        else
-            cudaGetLastError(); // clear: q_rounds_mixed_kernel or the sub-step kernels take over
-    }
-    return h->resident_ok == 1 ? std::min(want, 16) : 0;
-}
-static int q_resident_rounds_launch(mdpp_handle *h, float *cur, const mdpp_learner *lp, uint64_t round, int n, cudaStream_t s) {
-    const int nc = h->cfg.n_cars;
-    h->ep_bound += n;
-    RoundArgs ra{};
-    ra.recs = recs_of(h);
-    ra.n_envs = (uint32_t)h->n_envs;
-    ra.env_id_base = h->env_id_base;
-    ra.round = round;
-    ra.rng_words = (uint32_t *)(h->ws + h->cv.rng);
-    ra.tabs = (const FastTabs *)(h->ws + h->cv.fast);
-    ra.words_per_cta = h->cv.words_per_cta;
-    ra.cta_slots = h->cv.cta_slots;
-    ra.map_bytes = (uint32_t)((((size_t)h->cfg.n_states * MDPP_N_ACT + 15) / 16) * 16);
-    ra.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
-    ra.n_states = (uint32_t)h->cfg.n_states;
-    const unsigned grid = round_ctas(h);
-    ra.tiles_q = (uint32_t)(((h->n_envs + 31) / 32) / grid);
-    ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
-    ra.n_rounds = (uint32_t)n;
-    ResidentArgs rx{};
-    rx.barrier = (uint32_t *)(h->ws + h->cv.barrier);
-    rx.q = cur;
-    rx.scratch = (float *)(h->ws + h->cv.qalt);
-    rx.gbits = (uint32_t *)(h->ws + h->cv.gbits);
-    const Marks mk = marks_of(h);
-    rx.sinfo = mk.sinfo;
-    rx.visited = mk.visited;
-    rx.n_marks = (uint32_t)((size_t)h->cfg.n_states * MDPP_N_ACT);
-    rx.words = h->cv.words_per_cta;
-    rx.list_cap = (ra.map_bytes / 6u) & ~3u;
-    if (const char *e = getenv("MDPP_RESIDENT_LIST_CAP")) rx.list_cap = std::min<uint32_t>(rx.list_cap, (uint32_t)atoi(e) & ~3u); // tests: force the overflow path
-    rx.alpha = lp->alpha;
-    rx.discount = lp->discount;
-    rx.stamps = getenv("MDPP_STAMPS") && atoi(getenv("MDPP_STAMPS")) != 0 ? 1u : 0u;
-    MDPP_CUDA(cudaMemsetAsync(rx.gbits, 0, (size_t)3 * rx.words * 4, s)); // the three mark bitmaps start clear
-    const size_t smem = resident_smem_bytes(h);
-    mdpp_learner lpv = *lp;
-    Control *ctl = control_of(h);
-    void *args[] = {(void *)&h->dev, (void *)&lpv, (void *)&ra, (void *)&rx, (void *)&ctl};
-    const void *fn = nc == 1 ? (const void *)q_rounds_resident_kernel<1> : (const void *)q_rounds_resident_kernel<2>;
-    MDPP_LAUNCH(h, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kRoundThreads), args, smem, s));
-    h->chain = false; // launched in plain stream order; what follows must not overlap it either
-    return MDPP_OK;
-}
-
 static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStream_t s) {
     const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
@@ -1264,17 +1191,6 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
             if (pure || h->k1_rounds) {
                 int rc = q_round_launch(h, cur, alt, lp, first_round + (uint64_t)r, s);
                 if (rc) return rc;
-                continue;
-            }
-            if (const int n = resident_rounds_fit(h, room)) { // several such rounds in one cooperative launch, table in shared memory
-                if (cur != q) { // the kernel updates the caller's table in place
-                    int rc = q_copy_launch(h, cur, q, s);
-                    if (rc) return rc;
-                    std::swap(cur, alt);
-                }
-                int rc = q_resident_rounds_launch(h, cur, lp, first_round + (uint64_t)r, n, s);
-                if (rc) return rc;
-                r += n - 1;
                 continue;
             }
             if (const int n = mixed_rounds_fit(h, room)) { // several such rounds in one cooperative launch
@@ -1592,13 +1508,6 @@ int mdpp_q_profile_env_kernel(mdpp_handle *h, float *q, const mdpp_learner *lp, 
         MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_round_kernel<2, 0>, h->dev, *lp, ra, control_of(h)));
     }
     h->ep_bound += 1;
-    return MDPP_OK;
-}
-
-int mdpp_debug_stamps(uint64_t *out_host, int n) {
-    if (!out_host || n <= 0 || n > 3 * kStampSlots) return fail(MDPP_EINVAL, "mdpp_debug_stamps: 1..%d words", 3 * kStampSlots);
-    MDPP_CUDA(cudaDeviceSynchronize());
-    MDPP_CUDA(cudaMemcpyFromSymbol(out_host, g_stamps, (size_t)n * 8));
     return MDPP_OK;
 }
 

@@ -70,9 +70,8 @@ enum { kStepSkip = 0, kStepDone = 1, kStepDefer = 2 };
 // One agent-step of car C on the unpacked record.  `cars` is committed (ghost counters of encodestate, the
 // move) unless the car is parked.  Returns kStepDone with the compact key (state * 5 + action) when a key was touched.
 // CG: the table changes while the kernel runs (q_rounds_mixed_kernel): coherent greedy reads (ldcg_row).
-// TQ: the table is resident in shared memory as compact keys (q_now[state * 5 + action], q_rounds_resident_kernel).
 // CarsT: uint32_t for 1- and 2-car tables (both 12-bit fields live in the record's first word: no 64-bit shifts).
-template <int NC, int C, bool CG = false, bool TQ = false, class CarsT = uint64_t>
+template <int NC, int C, bool CG = false, class CarsT = uint64_t>
 __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevCfg &cfg, const FastTabs *gt,
                                               const RoundArgs &ra, CarsT &cars, uint32_t word, uint32_t eps16,
                                               bool allow_greedy, uint32_t &key, bool &moved, bool &explore,
@@ -133,10 +132,7 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
     } else {
         if (!allow_greedy) return kStepDefer; // the snapshot of this sub-step does not exist yet
         float qs[MDPP_Q_ROW];
-        if constexpr (TQ) {
-#pragma unroll
-            for (int k = 0; k < MDPP_N_ACT; k++) qs[k] = q_now[sidx * MDPP_N_ACT + k];
-        } else if constexpr (CG) {
+        if constexpr (CG) {
             ldcg_row(q_now + (size_t)sidx * MDPP_Q_ROW, qs);
         } else {
             pdl_wait();
@@ -584,35 +580,42 @@ q_multi_pull_kernel(MultiPullArgs pa, Control *ctl) {
 // same order as the sub-step kernels: bit-identical tables, records and counters.
 // ------------------------------------------------------------------------------------------------
 // Grid-wide barrier of a cooperative launch (every CTA co-resident by construction): one arrival per CTA on a
-// counter that only ever grows and a spin of one thread per CTA.  The value the counter has when a kernel starts
+// counter that only ever grows; the last arrival releases the others through a flag word they spin on.  The value the counter has when a kernel starts
 // lives next to it (word 1 of the barrier area): every cooperative kernel reads it first and its CTA 0 stores the
-// value after its last barrier on the way out, so kernels whose number of barriers depends on the data (the
-// overflow path of q_rounds_resident_kernel, the levels of reach_bfs_kernel) need no host bookkeeping -- a host
-// count that disagrees with the arrivals would leave the next kernel waiting for ever.  Release / acquire through the two fences and the acquiring load, like cooperative groups'
+// value after its last barrier on the way out, so a kernel whose number of barriers depends on the data (the
+// levels of reach_bfs_kernel) needs no host bookkeeping -- a host count that disagrees with the arrivals would
+// leave the next kernel waiting for ever.  Release / acquire through the two fences and the acquiring load, like cooperative groups'
 // grid.sync(), which measured ~4 us per barrier here against ~1 us for this one.
+constexpr uint32_t kBarrierFlagWord = 64; // word 64 of the barrier area (256 bytes on): the release flag's own line
 __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(ctr, 1u);
-        uint32_t v, spins = 0;
-        unsigned long long t0 = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-            // A barrier that cannot complete (a CTA missing, a base that disagrees with the arrivals) must end in an
-            // error the host sees, not in a GPU that spins until somebody resets it: after 4 s the kernel traps.
-            if ((++spins & 0x3FFFu) == 0u) {
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 4000000000ull) __trap();
-            }
-        } while ((int32_t)(v - target) < 0);
+        // The LAST arrival publishes the target in a word of its own cache line and everybody else polls that word:
+        // 148 pollers on the counter itself queue up in L2 behind the 148 atomics they are waiting for (phase
+        // stamps inside the kernel: ~2 us per barrier that way).
+        uint32_t *flag = ctr + kBarrierFlagWord;
+        if (atomicAdd(ctr, 1u) + 1u == target) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(target) : "memory");
+        } else {
+            uint32_t v, spins = 0;
+            unsigned long long t0 = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                // A barrier that cannot complete (a CTA missing, a base that disagrees with the arrivals) must end in
+                // an error the host sees, not in a GPU that spins until somebody resets it: after 4 s the kernel traps.
+                if ((++spins & 0x3FFFu) == 0u) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 4000000000ull) __trap();
+                }
+            } while ((int32_t)(v - target) < 0);
+        }
         __threadfence();
     }
     __syncthreads();
 }
-
 __device__ __forceinline__ uint32_t barrier_base_load(const uint32_t *area) { return __ldcg(area + 1); }
 // on the way out, after the kernel's last barrier (every CTA read the base before its first one)
 __device__ __forceinline__ void barrier_base_store(uint32_t *area, uint32_t bar) {
@@ -765,311 +768,6 @@ q_rounds_mixed_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, MixedArgs mx, Cont
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
                   (unsigned long long)touched_total);
     barrier_base_store(mx.barrier, bar);
-    flush_counts<true>(cnt, S.cc, 0u, ctl);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Rounds WITH greedy decisions, the table RESIDENT in every CTA's shared memory (replaces q_rounds_mixed_kernel
-// wherever the table fits; that kernel stays as the fallback and for A/B runs, MDPP_RESIDENT_ROUNDS=0).
-//
-// ncu on q_rounds_mixed_kernel: 30.5 us per round at epsilon 0.5, top stall "barrier"; ~4 us of every sub-step went
-// into flush -> grid barrier -> pull by 8 warps per CTA (148-slice OR + L2 round trips) -> grid barrier, and the
-// greedy lanes gathered hot table rows through L1/L2.  Here every CTA keeps its own copy of the table, compact
-// (state * 5 + action, 133 KB for the headline scenario), so
-//   * a greedy lane reads its row from shared memory;
-//   * the marks of a sub-step are OR-ed by every CTA into ONE global bitmap (RED.OR of its non-zero words: a few
-//     hundred per CTA), followed by the ONLY grid barrier of the sub-step;
-//   * every CTA then applies the whole pull to its own copy (redundantly: ~2400 updates over 1024 threads): new
-//     values are computed from the untouched copy into a list -- which lives in the byte map's storage, free at
-//     that point -- and written after a CTA barrier, so every update sees the snapshot;
-//   * the global table is written once, at the end of the launch (each CTA a slice of its copy).
-// The bitmap is triple-buffered: sub-step i ORs into buffer i % 3 and, after its barrier, CTA 0 clears buffer
-// (i + 2) % 3 -- last read before every CTA arrived at that barrier, next written after the following one.
-// Overflow of the list (more marked keys in one sub-step than fit the map's storage; never at the headline
-// scenario's ~2400) is handled exactly: every CTA sees the same count, and all of them switch to a pull through
-// global memory for that sub-step (each CTA its share of the bitmap words, values to a scratch table, one more
-// grid barrier, copies refreshed from the scratch).
-// Same arithmetic in the same order as the sub-step kernels: bit-identical tables, records and counters.
-// ------------------------------------------------------------------------------------------------
-constexpr __host__ __device__ uint32_t n_warps_of(int threads) { return (uint32_t)threads / 32u; }
-// Phase timestamps of q_rounds_resident_kernel (MDPP_STAMPS=1; read back with mdpp_debug_stamps): CTAs 0, G/2 and
-// G-1 store %globaltimer after staging and, for the first 6 sub-steps, after the env pass, the map flush, the grid
-// barrier, the pull and the list clean-up.  Temporary-instrumentation style of DESIGN.md 4.2, kept as a hook.
-constexpr int kStampSlots = 32;
-__device__ unsigned long long g_stamps[3][kStampSlots];
-__device__ __forceinline__ void stamp(uint32_t enabled, uint32_t slot) {
-    if (!enabled || threadIdx.x != 0 || slot >= (uint32_t)kStampSlots) return;
-    const int which = blockIdx.x == 0 ? 0 : blockIdx.x == gridDim.x / 2 ? 1 : blockIdx.x == gridDim.x - 1 ? 2 : -1;
-    if (which < 0) return;
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_stamps[which][slot] = t;
-}
-struct ResidentArgs {
-    uint32_t *barrier;        // the grid barrier's area: [0] arrival counter, [1] its value when a kernel starts
-    float *q;                 // the table: rows of MDPP_Q_ROW floats, read at the start, written at the end
-    float *scratch;           // [n_marks] floats: new values of the overflow path
-    uint32_t *gbits;          // [3][words] global mark bitmaps (compact keys), zero at kernel start
-    const uint32_t *sinfo;
-    uint32_t *visited;
-    uint32_t n_marks, words, list_cap;
-    float alpha, discount;
-    uint32_t stamps;          // MDPP_STAMPS=1: phase timestamps into g_stamps
-};
-
-// One sub-step (car slot C) over the CTA's tiles.  The decision word of car 1 travels in the record itself: with
-// 1-2 cars both car fields live in word 0, so pass 0 parks Philox word 1 in word 1 of the record and pass 1 -- which
-// gets the record through the same one-lap-ahead prefetch -- takes it from there and writes the 0 back that every
-// other kernel expects.  (Through the rng_words side array the load sat, unprefetched, at the head of every lap: an
-// exposed L2 round trip per tile.)
-template <int NC, int C>
-__device__ __forceinline__ void resident_env_pass(const RoundSmem<NC> &S, const DevCfg &cfg, const LearnArgs &lp,
-                                                  const RoundArgs &ra, const float *tq, uint64_t round, uint8_t *map,
-                                                  uint32_t t0, uint32_t t1, StepCounts &cnt) {
-    constexpr uint32_t n_warps = kRoundThreads / 32;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t t = t0 + warp;
-    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-    if (t < t1 && t * 32u + lane < ra.n_envs) rec = ra.recs[t * 32u + lane];
-    while (t < t1) {
-        const uint32_t e = t * 32u + lane, tn = t + n_warps;
-        uint4 rec_next = make_uint4(0u, 0u, 0u, 0u);
-        if (tn < t1 && tn * 32u + lane < ra.n_envs) rec_next = ra.recs[tn * 32u + lane];
-        uint32_t episode = rec.z & 0xFFFFu;
-        const bool live = (int32_t)episode < lp.episodes;
-        if (e < ra.n_envs && live) {
-            uint32_t cars = rec.x; // 1-2 cars: both 12-bit fields live in the first word
-            uint32_t steps = rec.z >> 16;
-            const uint32_t env = ra.env_id_base + e;
-            uint32_t eps16 = lp.eps_q16[0];
-            if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
-            uint32_t word;
-            if (C == 0) { // one Philox block per env and round: word c belongs to car c
-                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
-                word = p.x;
-                if (NC > 1) rec.y = p.y;
-            } else {
-                word = rec.y;
-                rec.y = 0u;
-            }
-            uint32_t key;
-            bool moved, explore;
-            if (round_car_step<NC, C, false, true>(S, cfg, ra.tabs, ra, cars, word, eps16, true, key, moved, explore, tq) == kStepDone)
-                map[key] = 1;
-            steps += moved;
-            cnt.steps += moved;
-            cnt.explore += explore;
-            steps = steps > 0xFFFFu ? 0xFFFFu : steps;
-            if (C == NC - 1) { // end of the round-robin round (qlearning.py:233)
-                bool finished = all_done32<NC>(cars);
-                bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
-                if (finished || capped) {
-                    cnt.episodes += 1;
-                    cnt.capped += capped;
-                    episode = episode + 1;
-                    cnt.max_episode = max(cnt.max_episode, episode);
-                    steps = 0;
-                    rec.w &= ~0xFFu;
-                    cars = (uint32_t)initial_cars<NC>(cfg, heading_word(round, 2, lp.seed, env));
-                }
-            }
-            rec.x = cars;
-            rec.z = (episode & 0xFFFFu) | (steps << 16);
-            ra.recs[e] = rec;
-        }
-        rec = rec_next;
-        t = tn;
-    }
-}
-
-// bytes -> bits of the CTA's map, OR-ed into the global bitmap (non-zero words only); the map is cleared
-__device__ __forceinline__ void resident_flush(uint8_t *map, uint32_t map_bytes, uint32_t words, uint32_t *gbits) {
-    uint4 *map4 = reinterpret_cast<uint4 *>(map);
-    const uint32_t n16 = map_bytes >> 4;
-    for (uint32_t wd = threadIdx.x; wd < words; wd += kRoundThreads) {
-        uint32_t bits = 0;
-        if (2u * wd < n16) {
-            const uint4 lo = map4[2u * wd];
-            bits = ((lo.x * 0x01020408u) >> 24) | (((lo.y * 0x01020408u) >> 24) << 4) |
-                   (((lo.z * 0x01020408u) >> 24) << 8) | (((lo.w * 0x01020408u) >> 24) << 12);
-            map4[2u * wd] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (2u * wd + 1u < n16) {
-            const uint4 hi = map4[2u * wd + 1u];
-            bits |= (((hi.x * 0x01020408u) >> 24) << 16) | (((hi.y * 0x01020408u) >> 24) << 20) |
-                    (((hi.z * 0x01020408u) >> 24) << 24) | (((hi.w * 0x01020408u) >> 24) << 28);
-            map4[2u * wd + 1u] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (bits) atomicOr(gbits + wd, bits);
-    }
-}
-
-// the new value of compact key m from the CTA's copies of the table and of the state info words (the snapshot of
-// this sub-step): shared memory only
-__device__ __forceinline__ float resident_value(const float *tq, const uint32_t *sinfo, uint32_t m, uint32_t n_states,
-                                                float alpha, float discount, uint32_t &key8) {
-    const uint32_t s = m / MDPP_N_ACT, a = m - s * MDPP_N_ACT;
-    const uint32_t info = sinfo[s];
-    const uint32_t s2 = td_successor(s, info, a, n_states);
-    const uint32_t i2 = sinfo[s2];
-    float ns[MDPP_Q_ROW];
-#pragma unroll
-    for (int k = 0; k < MDPP_N_ACT; k++) ns[k] = tq[s2 * MDPP_N_ACT + k];
-#pragma unroll
-    for (int k = MDPP_N_ACT; k < MDPP_Q_ROW; k++) ns[k] = 0.f;
-    key8 = s * MDPP_Q_ROW + a;
-    return td_update(info, i2, ns, tq[m], alpha, discount);
-}
-
-template <int NC>
-__global__ void __launch_bounds__(kRoundThreads, 1)
-q_rounds_resident_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, ResidentArgs rx, Control *ctl) {
-    static_assert(NC >= 1 && NC <= 2, "built for 1- and 2-car tables");
-    extern __shared__ uint4 smem_dyn[];
-    RoundSmem<NC> &S = *reinterpret_cast<RoundSmem<NC> *>(smem_dyn);
-    constexpr uint32_t kTabBytes = (sizeof(RoundSmem<NC>) + 15u) & ~15u;
-    uint8_t *map = reinterpret_cast<uint8_t *>(smem_dyn) + kTabBytes;
-    float *tq = reinterpret_cast<float *>(map + ra.map_bytes);       // [n_marks] the table, compact keys
-    uint32_t *sinfo = reinterpret_cast<uint32_t *>(tq + ((rx.n_marks + 3u) & ~3u)); // [n_states] state info words
-    // the pull's list of (key, new value) reuses the map's storage: values first (4-byte aligned), then 16-bit keys
-    float *lvals = reinterpret_cast<float *>(map);
-    uint16_t *lkeys = reinterpret_cast<uint16_t *>(map + 4u * rx.list_cap);
-    __shared__ uint32_t warp_excl[32];
-    __shared__ uint32_t list_total;
-    const uint32_t t0 = blockIdx.x * ra.tiles_q + min(blockIdx.x, ra.tiles_r);
-    const uint32_t t1 = t0 + ra.tiles_q + (blockIdx.x < ra.tiles_r ? 1u : 0u);
-    {
-        stage_lean_tabs<NC, kRoundThreads>(S, ra.tabs);
-        uint4 *m4 = reinterpret_cast<uint4 *>(map);
-        for (uint32_t i = threadIdx.x; i < (ra.map_bytes >> 4); i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (uint32_t m = threadIdx.x; m < rx.n_marks; m += kRoundThreads) {
-            const uint32_t s = m / MDPP_N_ACT;
-            tq[m] = rx.q[(size_t)s * MDPP_Q_ROW + (m - s * MDPP_N_ACT)];
-        }
-        for (uint32_t i = threadIdx.x; i < ra.n_states; i += kRoundThreads) sinfo[i] = __ldg(rx.sinfo + i);
-        if (threadIdx.x == 0) { S.cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u}; S.any_deferred = 0u; }
-    }
-    __syncthreads();
-    stamp(rx.stamps, 0u);
-    StepCounts cnt;
-    uint32_t touched_total = 0, sub = 0, bar = barrier_base_load(rx.barrier);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t r = 0; r < ra.n_rounds; r++) {
-        const uint64_t round = ra.round + r;
-#pragma unroll
-        for (int c = 0; c < NC; c++, sub++) {
-            uint32_t *gb = rx.gbits + (size_t)(sub % 3u) * rx.words;
-            if (c == 0) resident_env_pass<NC, 0>(S, cfg, lp, ra, tq, round, map, t0, t1, cnt);
-            else resident_env_pass<NC, (NC > 1 ? 1 : 0)>(S, cfg, lp, ra, tq, round, map, t0, t1, cnt);
-            __syncthreads();
-            stamp(rx.stamps, 1u + 5u * sub);
-            resident_flush(map, ra.map_bytes, rx.words, gb);
-            stamp(rx.stamps, 2u + 5u * sub);
-            grid_barrier(rx.barrier, bar += gridDim.x);
-            stamp(rx.stamps, 3u + 5u * sub);
-            // ---- the pull of this sub-step, applied to the CTA's own copy ----
-            if (blockIdx.x == 0) { // the buffer of the previous sub-step: everybody finished reading it before this barrier
-                uint32_t *old = rx.gbits + (size_t)((sub + 2u) % 3u) * rx.words;
-                for (uint32_t wd = threadIdx.x; wd < rx.words; wd += kRoundThreads) old[wd] = 0u;
-            }
-            // (a) the marked keys, in ascending order, into the list: thread t owns words 2t and 2t + 1 (block scan of
-            //     the popcounts; no atomics, the same list in every CTA)
-            const uint32_t w0 = 2u * threadIdx.x, w1 = w0 + 1u;
-            uint32_t b0 = w0 < rx.words ? __ldcg(gb + w0) : 0u, b1 = w1 < rx.words ? __ldcg(gb + w1) : 0u;
-            const uint32_t cntk = (uint32_t)(__popc(b0) + __popc(b1));
-            uint32_t incl = cntk;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= (uint32_t)o) incl += y;
-            }
-            if (lane == 31u) warp_excl[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t sw = warp_excl[lane];
-                uint32_t tw = sw;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tw, o);
-                    if (lane >= (uint32_t)o) tw += y;
-                }
-                warp_excl[lane] = tw - sw;
-                if (lane == 31u) list_total = tw;
-            }
-            __syncthreads();
-            const uint32_t n_list = list_total;
-            if (n_list <= rx.list_cap) {
-                uint32_t slot = warp_excl[warp] + incl - cntk;
-                while (b0) { lkeys[slot++] = (uint16_t)(w0 * 32u + (uint32_t)__ffs((int)b0) - 1u); b0 &= b0 - 1u; }
-                while (b1) { lkeys[slot++] = (uint16_t)(w1 * 32u + (uint32_t)__ffs((int)b1) - 1u); b1 &= b1 - 1u; }
-                __syncthreads();
-                // (b) one key per thread: its new value from the untouched copy; visited bits and the touched count
-                //     once per key (entry i belongs to CTA i % G)
-                for (uint32_t i = threadIdx.x; i < n_list; i += kRoundThreads) {
-                    uint32_t key8;
-                    const uint32_t m = min((uint32_t)lkeys[i], rx.n_marks - 1u);
-                    lvals[i] = resident_value(tq, sinfo, m, ra.n_states, rx.alpha, rx.discount, key8);
-                    if (i % gridDim.x == blockIdx.x) {
-                        mark_visited(rx.visited, key8);
-                        touched_total++;
-                    }
-                }
-                __syncthreads();
-                // (c) every value was computed from the snapshot: write them
-                for (uint32_t i = threadIdx.x; i < n_list; i += kRoundThreads) tq[min((uint32_t)lkeys[i], rx.n_marks - 1u)] = lvals[i];
-                __syncthreads();
-            } else {
-                // overflow (the same count in every CTA): this sub-step's pull through global memory.  CTA b owns the
-                // words w with w % G == b, computes their keys' values from its intact copy into the scratch table,
-                // and after one more grid barrier every CTA refreshes the marked keys of its copy from there.
-                for (uint32_t wd = blockIdx.x * n_warps_of(kRoundThreads) + warp; wd < rx.words; wd += gridDim.x * n_warps_of(kRoundThreads)) {
-                    const uint32_t bits = __ldcg(gb + wd);
-                    if ((bits >> lane) & 1u) {
-                        uint32_t key8;
-                        const uint32_t m = min(wd * 32u + lane, rx.n_marks - 1u);
-                        rx.scratch[m] = resident_value(tq, sinfo, m, ra.n_states, rx.alpha, rx.discount, key8);
-                        mark_visited(rx.visited, key8);
-                        touched_total++;
-                    }
-                }
-                grid_barrier(rx.barrier, bar += gridDim.x);
-                for (uint32_t wd = threadIdx.x; wd < rx.words; wd += kRoundThreads) {
-                    uint32_t bits = __ldcg(gb + wd);
-                    while (bits) {
-                        const uint32_t m = wd * 32u + (uint32_t)__ffs((int)bits) - 1u;
-                        bits &= bits - 1u;
-                        if (m < rx.n_marks) tq[m] = __ldcg(rx.scratch + m);
-                    }
-                }
-                __syncthreads();
-            }
-            stamp(rx.stamps, 4u + 5u * sub);
-            // the list overwrote the map's storage: clear what it used before the next pass marks again
-            {
-                uint4 *m4 = reinterpret_cast<uint4 *>(map);
-                const uint32_t used = min(n_list, rx.list_cap);
-                const uint32_t v16 = (used * 4u + 15u) >> 4, k0 = (4u * rx.list_cap) >> 4, k16 = (used * 2u + 15u) >> 4;
-                for (uint32_t i = threadIdx.x; i < v16; i += kRoundThreads) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-                for (uint32_t i = threadIdx.x; i < k16; i += kRoundThreads) m4[k0 + i] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            __syncthreads();
-            stamp(rx.stamps, 5u + 5u * sub);
-        }
-    }
-    // the table goes home: CTA b writes the b-th slice of its copy (all copies are identical)
-    {
-        const uint32_t per = (rx.n_marks + gridDim.x - 1u) / gridDim.x;
-        const uint32_t m0 = blockIdx.x * per, m1 = min(m0 + per, rx.n_marks);
-        for (uint32_t m = m0 + threadIdx.x; m < m1; m += kRoundThreads) {
-            const uint32_t s = m / MDPP_N_ACT;
-            rx.q[(size_t)s * MDPP_Q_ROW + (m - s * MDPP_N_ACT)] = tq[m];
-        }
-    }
-    touched_total = __reduce_add_sync(0xFFFFFFFFu, touched_total);
-    if (lane == 0 && touched_total)
-        atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys,
-                  (unsigned long long)touched_total);
-    barrier_base_store(rx.barrier, bar);
     flush_counts<true>(cnt, S.cc, 0u, ctl);
 }
 

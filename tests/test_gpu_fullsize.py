@@ -91,22 +91,19 @@ def test_fullsize_pure_exploration_rounds_bit_exact():
     assert int((env.records[:, 3] & 0x700).sum()) == 0
 
 
-@pytest.mark.parametrize("variant", ["default", "mixed_kernel", "resident_list_overflow", "substep_kernels", "k1_rounds"])
+@pytest.mark.parametrize("variant", ["default", "substep_kernels", "k1_rounds"])
 def test_fullsize_greedy_rounds_bit_exact(variant):
     """Rounds WITH greedy decisions at full size: an episode budget of 2 puts episode 0 at epsilon 0.8 and
     episode 1 at epsilon 0, a step cap of 24 ends episodes quickly, so 40 rounds cross both segments and
-    finish with every env frozen.  default = q_rounds_resident_kernel (table resident in shared memory, 148 CTAs,
-    one grid barrier per sub-step); MDPP_RESIDENT_ROUNDS=0 = q_rounds_mixed_kernel; MDPP_RESIDENT_LIST_CAP=64 = the
-    resident kernel's overflow pull; MDPP_MIXED_ROUNDS=0 = one sub-step kernel + dense pull per car;
-    MDPP_K1_ROUNDS=1 = the fused K0 / K1 pair."""
+    finish with every env frozen.  default = q_rounds_mixed_kernel (cooperative, 148 CTAs, grid barriers between
+    env passes and pulls); MDPP_MIXED_ROUNDS=0 = one sub-step kernel + dense pull per car; MDPP_K1_ROUNDS=1 = the
+    fused K0 / K1 pair."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
     boxes, idx, choose = m.layout_3[2]["initial_states"][0]
     bad = bad_states_text(2)
     cap, episodes, rounds = 24, 2, 40
     sc = m.Scenario(m.layout_3[2], boxes, idx, choose, bad_states_text=bad, step_cap=cap)
-    envvars = {"substep_kernels": {"MDPP_MIXED_ROUNDS": "0"}, "k1_rounds": {"MDPP_K1_ROUNDS": "1"},
-               "mixed_kernel": {"MDPP_RESIDENT_ROUNDS": "0"},
-               "resident_list_overflow": {"MDPP_RESIDENT_LIST_CAP": "64"}}.get(variant, {})
+    envvars = {"substep_kernels": {"MDPP_MIXED_ROUNDS": "0"}, "k1_rounds": {"MDPP_K1_ROUNDS": "1"}}.get(variant, {})
     os.environ.update(envvars)
     try:
         env = BatchedEnv(sc, N_FULL, seed=37)

@@ -383,8 +383,7 @@ FUSED = [
 ]
 
 
-@pytest.mark.parametrize("k1", [False, True, "substep", "mixed", "overflow"],
-                         ids=["default", "k1_rounds", "substep_kernels", "mixed_kernel", "resident_list_overflow"])
+@pytest.mark.parametrize("k1", [False, True, "substep"], ids=["default", "k1_rounds", "substep_kernels"])
 @pytest.mark.parametrize("case", FUSED, ids=[c[0] for c in FUSED])
 def test_train_rounds_fused_path_matches_oracle(case, k1):
     """mdpp_q_train_rounds on 1- and 2-car tables takes the fused round kernels (q_round.cuh: table-driven
@@ -393,17 +392,14 @@ def test_train_rounds_fused_path_matches_oracle(case, k1):
     per sub-step) -- or, with MDPP_K1_ROUNDS=1, the fused pair K0 / K1 (car 1 parked and finished by the catch-up
     kernel when it acts greedily), or, with MDPP_MIXED_ROUNDS=0, one sub-step kernel + pull per car.  The episode budget is small so that the run crosses every epsilon segment
     (1, .8, .5, .3, .15, 0) and ends with frozen envs; table, records and counters must equal the
-    oracle's sub-step-by-sub-step restatement bit for bit.  default = q_rounds_resident_kernel (the table in every
-    CTA's shared memory, one grid barrier per sub-step); MDPP_RESIDENT_ROUNDS=0 = q_rounds_mixed_kernel;
-    MDPP_RESIDENT_LIST_CAP=64 forces the resident kernel's pull through its overflow path (global scratch)."""
+    oracle's sub-step-by-sub-step restatement bit for bit."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
     name, block, boxes, idx, choose, bad, cap, n, episodes, rounds, chunk, stats_every = case
     badtxt = bad_states_text(block) if bad else None
     sc = m.Scenario(m.layout_3[block], boxes, idx, choose, bad_states_text=badtxt, step_cap=cap)
     # rounds with greedy decisions: default = the cooperative multi-round kernel; the fused K0 / K1 pair; the
     # sub-step kernels
-    envvars = {True: {"MDPP_K1_ROUNDS": "1"}, "substep": {"MDPP_MIXED_ROUNDS": "0"},
-               "mixed": {"MDPP_RESIDENT_ROUNDS": "0"}, "overflow": {"MDPP_RESIDENT_LIST_CAP": "64"}}.get(k1, {})
+    envvars = {True: {"MDPP_K1_ROUNDS": "1"}, "substep": {"MDPP_MIXED_ROUNDS": "0"}}.get(k1, {})
     os.environ.update(envvars)
     try:
         _fused_path_body(m, BatchedEnv, BatchedQLearner, orc, sc, case, badtxt)

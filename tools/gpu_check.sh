@@ -7,9 +7,7 @@ mkdir -p $out
 echo "pytest rc=$?"; tail -12 $out/pytest.log
 for e in 0.8 0.5 0.0; do
   timeout 120 python tools/exp_mixed.py $e
-  MDPP_RESIDENT_ROUNDS=0 timeout 120 python tools/exp_mixed.py $e
 done 2>&1 | tee $out/mixed.log
-(timeout 120 python tools/exp_stamps.py 0.5; timeout 120 python tools/exp_stamps.py 0.0) 2>&1 | tee $out/stamps.log
 (timeout 120 python tools/exp_rollout.py 4 24 10; MDPP_LEAN_ROLLOUT=0 timeout 120 python tools/exp_rollout.py 4 24 10;
  timeout 120 python tools/exp_rollout.py 2 20 20; MDPP_LEAN_ROLLOUT=0 timeout 120 python tools/exp_rollout.py 2 20 20) 2>&1 | tee $out/rollout.log
 timeout 900 python bench.py --steps 300 --warmup 5 > $out/bench.json 2> $out/bench.err
