@@ -335,7 +335,7 @@ def main():
     active_fraction = total_steps / (float(args.steps) * RPS * n * k * world)
 
     # the exchange alone, in this run: back-to-back explicit averagings, device-timed, max over ranks
-    sync_us = None
+    sync_us, nccl_us = None, None
     if world > 1:
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -347,6 +347,20 @@ def main():
         ts = torch.tensor([a.elapsed_time(b) / 50 * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         sync_us = float(ts[0])
+        # the library all-reduce of the same table, for comparison (what round 1 used: ncclAllReduce AVG)
+        qc = lr.q.clone()
+        for _ in range(5):
+            dist.all_reduce(qc, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(50):
+            dist.all_reduce(qc, op=dist.ReduceOp.AVG)
+        b.record()
+        torch.cuda.synchronize()
+        ts = torch.tensor([a.elapsed_time(b) / 50 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        nccl_us = float(ts[0])
+        del qc
 
     # ---- e2e: the public host-facing call, one round per call, counters read back every step ----
     barrier()
@@ -729,7 +743,7 @@ def main():
                        "preroll_rounds": args.preroll, "active_fraction": active_fraction,
                        "sync_interval_rounds": interval if world > 1 else None,
                        "allreduces_in_timed_region": syncs_timed if world > 1 else None,
-                       "allreduce_us": sync_us, "allreduce": sync_kind,
+                       "allreduce_us": sync_us, "allreduce": sync_kind, "nccl_allreduce_avg_us_same_table": nccl_us,
                        "parallelism": "dp%d: env shards + per-GPU Q replicas averaged every sync_interval_rounds" % world}),
             "q_updates_per_s": total_upd / (dev_ms * 1e-3),
             "wall_s_timed_region": wall,

@@ -284,8 +284,8 @@ int mdpp_dqn_act(mdpp_handle *h, int car_slot, int reward_kind, const uint8_t *a
  *   mdpp_replay_compact  list[rank] = the keys of the set in ascending order, *count = its size (the minibatch
  *                        of :347-350 is `count choose batch_size` positions of that list);
  *   mdpp_dqn_target      Double-DQN target (:360-379) of a minibatch: a* = argmax of the ONLINE network's Q(s', .)
- *                        over the valid actions, target = reward + discount * Q_target(s', a*) in float64 like the
- *                        reference's NumPy arithmetic, y = prediction with y[i][action[i]] = target.  index_mode 0
+ *                        over the valid actions, target = reward + discount * Q_target(s', a*) with the reference's NumPy
+ *                        arithmetic (float32 product, float64 sum with the float64 reward k/100, float32 store), y = prediction with y[i][action[i]] = target.  index_mode 0
  *                        reproduces the reference line for line: it takes a* as the POSITION inside the masked
  *                        sub-array (`np.argmax(qvalues[masks[i]])`) and uses that position as the action index;
  *                        index_mode 1 maps the position back to the action.  counters [2] u64 or NULL: invalid_count

@@ -19,8 +19,9 @@
 // The reference computes a* as `np.argmax(qvalues[masks[i]])`, i.e. the POSITION inside the masked sub-array, and
 // then uses that position as the action index in `np.choose(max_actions, target.T)`.  index_mode 0 reproduces
 // that line exactly (positions == actions whenever no action below the best one is masked); index_mode 1 maps
-// the position back to the action.  Arithmetic as in the reference: float64 product and sum (NumPy promotes the
-// float32 network outputs), rounded to float32 when stored into the prediction array.
+// the position back to the action.  Arithmetic as in the reference's NumPy expression: float32 product (scalar
+// discount x float32 network output), float64 sum with the float64 reward, rounded to float32 when stored into the
+// prediction array.
 #pragma once
 #include "env_core.cuh"
 
@@ -163,8 +164,14 @@ dqn_target_kernel(int64_t n, const float *__restrict__ q_online_next, const floa
         if (best_pos < 0) { empty = 1; best_pos = 0; best_act = 0; } // the reference raises on an empty mask
         invalid = overall != best_pos;                              // `overall_max_action != max_action` (:367)
         const int idx = index_mode == 0 ? best_pos : best_act;
-        // NumPy rounds the product and the sum separately: no fused multiply-add
-        const float t = (float)__dadd_rn((double)reward[i], __dmul_rn(discount, (double)qt[idx]));
+        // NumPy's arithmetic for `rewards + self.discount * max_qvalues`: the Python float scalar times a float32
+        // array is a FLOAT32 product (the scalar is cast to the array's type); adding the float64 reward array
+        // promotes to float64; storing into the float32 prediction array rounds once more.  The reference's rewards
+        // are float64 k / 100 (dqn_reward, src/env_gym.py:553) or integers; the env kernels emit float32(k / 100), so
+        // k is recovered and divided again in float64.
+        const float prod = __fmul_rn((float)discount, qt[idx]);
+        const double r64 = (double)lrintf(__fmul_rn(reward[i], 100.0f)) / 100.0;
+        const float t = (float)__dadd_rn(r64, (double)prod);
 #pragma unroll
         for (int k = 0; k < MDPP_N_ACT; k++) y[i * MDPP_N_ACT + k] = prediction[i * MDPP_N_ACT + k];
         const int64_t a = action[i];

@@ -88,7 +88,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     }
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
-    c.barrier = take(512); // grid barrier of the cooperative kernels: word 0 arrival counter (only ever grows), word 1 its value at the next kernel's start, word 64 the release flag; zero at create
+    c.barrier = take(64); // grid barrier of the cooperative kernels: word 0 arrival counter (only ever grows), word 1 its value at the next kernel's start; zero at create
     c.stage = take((size_t)n_envs * 16);
     c.dl = take((size_t)n_envs * 4);
     c.total = off;

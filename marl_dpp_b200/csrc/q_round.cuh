@@ -580,38 +580,33 @@ q_multi_pull_kernel(MultiPullArgs pa, Control *ctl) {
 // same order as the sub-step kernels: bit-identical tables, records and counters.
 // ------------------------------------------------------------------------------------------------
 // Grid-wide barrier of a cooperative launch (every CTA co-resident by construction): one arrival per CTA on a
-// counter that only ever grows; the last arrival releases the others through a flag word they spin on.  The value the counter has when a kernel starts
+// counter that only ever grows and a spin of one thread per CTA.  The value the counter has when a kernel starts
 // lives next to it (word 1 of the barrier area): every cooperative kernel reads it first and its CTA 0 stores the
 // value after its last barrier on the way out, so a kernel whose number of barriers depends on the data (the
 // levels of reach_bfs_kernel) needs no host bookkeeping -- a host count that disagrees with the arrivals would
 // leave the next kernel waiting for ever.  Release / acquire through the two fences and the acquiring load, like cooperative groups'
 // grid.sync(), which measured ~4 us per barrier here against ~1 us for this one.
-constexpr uint32_t kBarrierFlagWord = 64; // word 64 of the barrier area (256 bytes on): the release flag's own line
 __device__ __forceinline__ void grid_barrier(uint32_t *ctr, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        // The LAST arrival publishes the target in a word of its own cache line and everybody else polls that word:
-        // 148 pollers on the counter itself queue up in L2 behind the 148 atomics they are waiting for (phase
-        // stamps inside the kernel: ~2 us per barrier that way).
-        uint32_t *flag = ctr + kBarrierFlagWord;
-        if (atomicAdd(ctr, 1u) + 1u == target) {
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(target) : "memory");
-        } else {
-            uint32_t v, spins = 0;
-            unsigned long long t0 = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                // A barrier that cannot complete (a CTA missing, a base that disagrees with the arrivals) must end in
-                // an error the host sees, not in a GPU that spins until somebody resets it: after 4 s the kernel traps.
-                if ((++spins & 0x3FFFu) == 0u) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > 4000000000ull) __trap();
-                }
-            } while ((int32_t)(v - target) < 0);
-        }
+        atomicAdd(ctr, 1u);
+        // Everybody polls the counter itself.  (Releasing through a separate flag word written by the last arrival --
+        // so that the pollers do not queue up in L2 with the atomics -- measured SLOWER: 34.0 vs 30.5 us per round of
+        // q_rounds_mixed_kernel; the extra store is one more serial L2 round trip on the critical path.)
+        uint32_t v, spins = 0;
+        unsigned long long t0 = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            // A barrier that cannot complete (a CTA missing, a base that disagrees with the arrivals) must end in an
+            // error the host sees, not in a GPU that spins until somebody resets it: after 4 s the kernel traps.
+            if ((++spins & 0x3FFFu) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) __trap();
+            }
+        } while ((int32_t)(v - target) < 0);
         __threadfence();
     }
     __syncthreads();
