@@ -18,8 +18,8 @@
 // world x table bytes, right for tables of a few MB at NVLink bandwidth; larger tables (4-5 cars) take the
 // caller's NCCL path.
 //
-// Chain membership: the kernel waits for its predecessor (the last pull: the local table is final) with
-// griddepcontrol.wait and releases its successor at once.  The next env kernel never reads the table before its
+// Chain membership: the kernel releases its successor at once and then waits for its predecessor (the last pull:
+// the local table is final) with griddepcontrol.wait.  The next env kernel never reads the table before its
 // own griddepcontrol.wait, so a pure-exploration round runs WHILE the replicas are exchanged and the exchange
 // disappears from the critical path; the pulls of that round start after the env kernel, hence after this one.
 #pragma once
@@ -119,8 +119,13 @@ __device__ __forceinline__ void sync_slice(const SyncArgs &a, uint32_t b) {
 template <int WORLD>
 __global__ void __launch_bounds__(kSyncThreads)
 q_sync_kernel(SyncArgs a) {
+    // Release the successor FIRST: the next env kernel then starts as early as it does in an unsynchronised chain --
+    // while the last pull still runs -- and overlaps the pull AND the exchange (it touches records and its own
+    // parity of the mark regions only, and waits for this grid before it reads the table or exits).  With the
+    // release after the wait the env kernel could not start before the pull had completed: +20 us per exchange on
+    // 2 GPUs, the pull's overlap lost and a launch latency exposed.
+    pdl_launch_dependents();
     pdl_wait();              // the last pull has completed: the own table is final
-    pdl_launch_dependents(); // the next env kernel may run beside the exchange (it waits before it reads the table)
     sync_slice<WORLD>(a, blockIdx.x);
 }
 
