@@ -1004,6 +1004,7 @@ static SyncArgs sync_args(mdpp_handle *h, uint32_t epoch) {
     a.n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     a.timeout_ns = 2000000000ull;
     a.errors = (unsigned long long *)&control_of(h)->stats[0].internal_errors;
+    a.mode = getenv("MDPP_SYNC_MODE") ? (uint32_t)atoi(getenv("MDPP_SYNC_MODE")) : 0u;
     return a;
 }
 static unsigned sync_ctas(const mdpp_handle *h) {

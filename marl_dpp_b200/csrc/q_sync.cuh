@@ -38,6 +38,8 @@ struct SyncArgs {
     uint32_t n4;                    // float4 elements of the table
     unsigned long long timeout_ns;  // a peer that never arrives must not hang the GPU: give up, count an error
     unsigned long long *errors;     // Control::stats[0].internal_errors
+    uint32_t mode;                  // experiments (MDPP_SYNC_MODE): 0 = acquire polling, 1 = relaxed polling + one fence,
+                                    // 2 = 1 without waiting in the second handshake (UNSAFE, timing only)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -66,14 +68,36 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
     if (threadIdx.x < a.world) {
         const uint32_t t = threadIdx.x;
         const size_t slot = ((size_t)phase * kSyncMaxCtas + b) * kSyncMaxRanks;
-        __threadfence_system();
-        st_release_sys(a.flags[t] + slot + a.rank, a.epoch);
         const uint32_t *mine = a.flags[a.rank] + slot + t;
-        const unsigned long long t0 = global_ns();
-        while ((int32_t)(ld_acquire_sys(mine) - a.epoch) < 0) {
-            if (global_ns() - t0 > a.timeout_ns) {
-                atomicAdd(a.errors, 1ull);
-                break;
+        if (a.mode == 0u) {
+            __threadfence_system();
+            st_release_sys(a.flags[t] + slot + a.rank, a.epoch);
+            const unsigned long long t0 = global_ns();
+            while ((int32_t)(ld_acquire_sys(mine) - a.epoch) < 0) {
+                if (global_ns() - t0 > a.timeout_ns) {
+                    atomicAdd(a.errors, 1ull);
+                    break;
+                }
+            }
+        } else {
+            // one release fence, a relaxed store; poll with relaxed loads and fence once after the flag arrived
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + slot + a.rank), "r"(a.epoch) : "memory");
+            if (!(a.mode == 2u && phase == 1u)) {
+                uint32_t v, spins = 0;
+                unsigned long long t0 = 0;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+                    if ((++spins & 0xFFFu) == 0u) {
+                        const unsigned long long now = global_ns();
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > a.timeout_ns) {
+                            atomicAdd(a.errors, 1ull);
+                            break;
+                        }
+                    }
+                } while ((int32_t)(v - a.epoch) < 0);
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
             }
         }
     }
