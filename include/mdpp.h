@@ -234,11 +234,11 @@ int mdpp_q_profile_env_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learn
  *                            bufs[rank] -- as a member of its kernel chain: a pure-exploration round runs while
  *                            the replicas are exchanged.  Every rank must make the same calls in the same order.
  *   mdpp_q_sync_replicas     one averaging now (all ranks call it; asynchronous on `stream`).
- * One-shot exchange, for tables up to MDPP_SYNC_MAX_TABLE_BYTES (1-2 cars, 3 cars on block 0); mdpp_sync_attach
+ * One-shot exchange, for tables up to MDPP_SYNC_MAX_TABLE_BYTES (1-2 cars); mdpp_sync_attach
  * fails with MDPP_EINVAL beyond that and the caller falls back to a library all-reduce. */
 #define MDPP_SYNC_MAX_RANKS 8
 #define MDPP_SYNC_FLAG_BYTES (2 * 148 * MDPP_SYNC_MAX_RANKS * 4)
-#define MDPP_SYNC_MAX_TABLE_BYTES (148 * 512 * 2 * 16)
+#define MDPP_SYNC_MAX_TABLE_BYTES (148 * 128 * 4 * 16)
 #define MDPP_IPC_HANDLE_BYTES 64
 int64_t mdpp_sync_buffer_bytes(const mdpp_config *cfg);
 int mdpp_sync_alloc(int64_t bytes, void **dev_ptr_out, uint8_t *ipc_handle_out /*[MDPP_IPC_HANDLE_BYTES]*/);

@@ -991,6 +991,16 @@ static int sync_room(const mdpp_handle *h, uint64_t round, int want) {
     const uint64_t left = (uint64_t)h->sync_interval - round % (uint64_t)h->sync_interval;
     return (int)std::min<uint64_t>((uint64_t)want, left);
 }
+// chunks per CTA: one while the table fits 148 CTAs that way (every float4 one NVLink round trip), up to kSyncPer
+static uint32_t sync_per(const mdpp_handle *h) {
+    const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
+    const uint32_t per = (n4 + kSyncThreads * kSyncMaxCtas - 1) / (kSyncThreads * kSyncMaxCtas);
+    return std::max(1u, std::min(per, (uint32_t)kSyncPer));
+}
+static unsigned sync_ctas(const mdpp_handle *h) {
+    const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4), chunk = kSyncThreads * sync_per(h);
+    return (n4 + chunk - 1) / chunk;
+}
 static SyncArgs sync_args(mdpp_handle *h, uint32_t epoch) {
     SyncArgs a{};
     const size_t tb = sync_table_bytes(h->cfg);
@@ -1002,14 +1012,11 @@ static SyncArgs sync_args(mdpp_handle *h, uint32_t epoch) {
     a.world = (uint32_t)h->sync_world;
     a.epoch = epoch;
     a.n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
+    a.per = sync_per(h);
     a.timeout_ns = 2000000000ull;
     a.errors = (unsigned long long *)&control_of(h)->stats[0].internal_errors;
     a.mode = getenv("MDPP_SYNC_MODE") ? (uint32_t)atoi(getenv("MDPP_SYNC_MODE")) : 0u;
     return a;
-}
-static unsigned sync_ctas(const mdpp_handle *h) {
-    const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
-    return (n4 + kSyncThreads * kSyncPer - 1) / (kSyncThreads * kSyncPer);
 }
 static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
     if (h->sync_world <= 1) return MDPP_OK;

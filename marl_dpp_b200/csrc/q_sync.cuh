@@ -27,7 +27,11 @@
 
 namespace mdpp {
 
-constexpr int kSyncThreads = 512, kSyncPer = 2, kSyncMaxCtas = 148, kSyncMaxRanks = MDPP_SYNC_MAX_RANKS;
+// CTA shape: the exchange must be RESIDENT BESIDE the env kernel it overlaps.  A round-kernel CTA holds 1024 threads
+// x 54-56 registers of its SM, i.e. 8192 registers stay free: 128 threads x 64 registers.  (The first version used
+// 512-thread CTAs of 52 registers: on the SMs that hosted one, the env kernel's CTA could not start before the
+// exchange had finished, and every exchange sat on the critical path -- +25 us per round at interval 1.)
+constexpr int kSyncThreads = 128, kSyncPer = 4, kSyncMaxCtas = 148, kSyncMaxRanks = MDPP_SYNC_MAX_RANKS;
 constexpr size_t kSyncFlagWords = 2u * kSyncMaxCtas * kSyncMaxRanks; // [phase][cta][rank]
 constexpr size_t kSyncFlagBytes = kSyncFlagWords * 4u;
 
@@ -36,6 +40,7 @@ struct SyncArgs {
     uint32_t *flags[kSyncMaxRanks]; // every rank's flag area
     uint32_t rank, world, epoch;
     uint32_t n4;                    // float4 elements of the table
+    uint32_t per;                   // chunks of kSyncThreads float4 per CTA (1..kSyncPer)
     unsigned long long timeout_ns;  // a peer that never arrives must not hang the GPU: give up, count an error
     unsigned long long *errors;     // Control::stats[0].internal_errors
     uint32_t mode;                  // experiments (MDPP_SYNC_MODE): 0 = acquire polling, 1 = relaxed polling + one fence,
@@ -104,31 +109,27 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
     __syncthreads();
 }
 
-// the exchange of slice `b` as rank a.rank
+// the exchange of slice `b` as rank a.rank: a.per (<= kSyncPer) chunks of kSyncThreads float4 per CTA
 template <int WORLD>
 __device__ __forceinline__ void sync_slice(const SyncArgs &a, uint32_t b) {
     sync_handshake(a, 0u, b); // every rank's table is final
-    const uint32_t base = b * (kSyncThreads * kSyncPer) + threadIdx.x;
-    float4 v[kSyncPer][WORLD];
-#pragma unroll
-    for (int k = 0; k < kSyncPer; k++) {
-        const uint32_t i = base + (uint32_t)k * kSyncThreads;
-#pragma unroll
-        for (int r = 0; r < WORLD; r++)
-            v[k][r] = i < a.n4 ? ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(a.table[r]) + i)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    const uint32_t base = b * (kSyncThreads * a.per) + threadIdx.x;
     float4 m[kSyncPer];
     const float w = (float)WORLD;
 #pragma unroll
-    for (int k = 0; k < kSyncPer; k++) { // rank order, explicit roundings: the same bits on every rank
-        float4 s = v[k][0];
+    for (int k = 0; k < kSyncPer; k++) {
+        const uint32_t i = base + (uint32_t)k * kSyncThreads;
+        if ((uint32_t)k >= a.per || i >= a.n4) continue;
+        float4 v[WORLD]; // every rank's copy of this float4: all loads in flight at once (one NVLink round trip)
+#pragma unroll
+        for (int r = 0; r < WORLD; r++) v[r] = ld_relaxed_sys_f4(reinterpret_cast<const float4 *>(a.table[r]) + i);
+        float4 s = v[0]; // rank order, explicit roundings: the same bits on every rank
 #pragma unroll
         for (int r = 1; r < WORLD; r++) {
-            s.x = __fadd_rn(s.x, v[k][r].x);
-            s.y = __fadd_rn(s.y, v[k][r].y);
-            s.z = __fadd_rn(s.z, v[k][r].z);
-            s.w = __fadd_rn(s.w, v[k][r].w);
+            s.x = __fadd_rn(s.x, v[r].x);
+            s.y = __fadd_rn(s.y, v[r].y);
+            s.z = __fadd_rn(s.z, v[r].z);
+            s.w = __fadd_rn(s.w, v[r].w);
         }
         m[k] = make_float4(__fdiv_rn(s.x, w), __fdiv_rn(s.y, w), __fdiv_rn(s.z, w), __fdiv_rn(s.w, w));
     }
@@ -136,7 +137,7 @@ __device__ __forceinline__ void sync_slice(const SyncArgs &a, uint32_t b) {
 #pragma unroll
     for (int k = 0; k < kSyncPer; k++) {
         const uint32_t i = base + (uint32_t)k * kSyncThreads;
-        if (i < a.n4) reinterpret_cast<float4 *>(a.table[a.rank])[i] = m[k];
+        if ((uint32_t)k < a.per && i < a.n4) reinterpret_cast<float4 *>(a.table[a.rank])[i] = m[k];
     }
 }
 

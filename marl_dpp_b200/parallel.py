@@ -143,7 +143,7 @@ class PeerExchange:
 
     @staticmethod
     def max_table_bytes():
-        return 148 * 512 * 2 * 16   # MDPP_SYNC_MAX_TABLE_BYTES
+        return 148 * 128 * 4 * 16   # MDPP_SYNC_MAX_TABLE_BYTES
 
     @classmethod
     def local(cls, scenario, world, device=None):
