@@ -1023,6 +1023,8 @@ static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
     if ((void *)q != h->sync_bufs[h->sync_rank])
         return fail(MDPP_EINVAL, "replica averaging: q must be the table of this rank's exchange buffer");
     const SyncArgs a = sync_args(h, ++h->sync_epoch);
+    const bool no_pdl = (a.mode & 16u) != 0; // experiment: plain stream order around the exchange
+    if (no_pdl) h->chain = false;
     LearnLaunch ll(h, sync_ctas(h), s, kSyncThreads);
     switch (h->sync_world) {
     case 2: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<2>, a)); break;
@@ -1034,7 +1036,7 @@ static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
     default: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<8>, a)); break;
     }
     h->sync_count += 1;
-    h->chain = true;
+    h->chain = !no_pdl;
     return MDPP_OK;
 }
 

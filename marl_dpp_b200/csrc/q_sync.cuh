@@ -74,7 +74,7 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
         const uint32_t t = threadIdx.x;
         const size_t slot = ((size_t)phase * kSyncMaxCtas + b) * kSyncMaxRanks;
         const uint32_t *mine = a.flags[a.rank] + slot + t;
-        if (a.mode == 0u) {
+        if ((a.mode & 3u) == 0u) {
             __threadfence_system();
             st_release_sys(a.flags[t] + slot + a.rank, a.epoch);
             const unsigned long long t0 = global_ns();
@@ -88,7 +88,7 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
             // one release fence, a relaxed store; poll with relaxed loads and fence once after the flag arrived
             asm volatile("fence.acq_rel.sys;" ::: "memory");
             asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + slot + a.rank), "r"(a.epoch) : "memory");
-            if (!(a.mode == 2u && phase == 1u)) {
+            if (!((a.mode & 3u) == 2u && phase == 1u)) {
                 uint32_t v, spins = 0;
                 unsigned long long t0 = 0;
                 do {
@@ -149,8 +149,14 @@ q_sync_kernel(SyncArgs a) {
     // parity of the mark regions only, and waits for this grid before it reads the table or exits).  With the
     // release after the wait the env kernel could not start before the pull had completed: +20 us per exchange on
     // 2 GPUs, the pull's overlap lost and a launch latency exposed.
-    pdl_launch_dependents();
-    pdl_wait();              // the last pull has completed: the own table is final
+    if (a.mode & 8u) { // experiment: wait first, release after (the first version's order)
+        pdl_wait();
+        pdl_launch_dependents();
+    } else {
+        pdl_launch_dependents();
+        pdl_wait();          // the last pull has completed: the own table is final
+    }
+    if (a.mode & 4u) return; // experiment: no exchange at all, only the chain membership
     sync_slice<WORLD>(a, blockIdx.x);
 }
 

@@ -21,6 +21,20 @@ ex.attach(lr, 0, rank=0)
 lr.train_rounds(256)
 env.stats()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for mode, what in ((0, "as shipped"), (4, "no exchange body, chain membership only"), (8, "wait before release"),
+                   (12, "no body, wait before release"), (16, "plain stream order around the exchange"), (20, "plain order, no body")):
+    os.environ["MDPP_SYNC_MODE"] = str(mode)
+    ex.attach(lr, 1, rank=0)
+    lr.round = ((lr.round + 63) // 64) * 64
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(4):
+        lr.train_rounds(64)
+    b.record()
+    torch.cuda.synchronize()
+    env.stats()
+    print("interval 1, mode %2d (%s): %.2f us per round" % (mode, what, a.elapsed_time(b) / 256 * 1e3))
+os.environ["MDPP_SYNC_MODE"] = "0"
 for iv in (0, 1, 4, 64, 0):
     ex.attach(lr, iv, rank=0)
     lr.round = ((lr.round + 63) // 64) * 64
