@@ -133,6 +133,10 @@ struct mdpp_handle {
     uint32_t sync_epoch;    // calls so far; the flags of call k carry k (every rank makes the same calls)
     uint64_t sync_count;
     void *sync_bufs[MDPP_SYNC_MAX_RANKS];
+    // the exchange runs on a stream of its own, beside the env kernel that follows it on the caller's stream
+    cudaStream_t sync_stream;
+    cudaEvent_t sync_fork, sync_join;
+    bool sync_pending;      // an exchange is in flight: the caller's stream must wait for sync_join before the table is touched
 };
 
 using namespace mdpp;
@@ -377,6 +381,12 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
 int mdpp_destroy(mdpp_handle *h) {
     if (h && h->stat_slots) cudaFreeHost(h->stat_slots);
     if (h && h->host_stats) cudaFreeHost(h->host_stats);
+    if (h && h->sync_stream) {
+        cudaStreamSynchronize(h->sync_stream);
+        cudaEventDestroy(h->sync_fork);
+        cudaEventDestroy(h->sync_join);
+        cudaStreamDestroy(h->sync_stream);
+    }
     delete h;
     return MDPP_OK;
 }
@@ -587,6 +597,17 @@ struct LearnLaunch {
     }
 };
 
+// An exchange of the replicas may be running on the handle's side stream (q_sync_launch): whatever reads or writes
+// the table next on the caller's stream waits for it first.  Kernels that touch records and marks only (the env
+// kernels of pure-exploration rounds) do not call this: they run beside the exchange.
+static int sync_join(mdpp_handle *h, cudaStream_t s) {
+    if (!h->sync_pending) return MDPP_OK;
+    MDPP_CUDA(cudaStreamWaitEvent(s, h->sync_join, 0));
+    h->sync_pending = false;
+    h->chain = false; // the event wait sits between this launch and its predecessor
+    return MDPP_OK;
+}
+
 static size_t step_tabs_bytes(int n_cars) {
     switch (n_cars) {
     case 1: return sizeof(StepTabs<1>);
@@ -600,6 +621,7 @@ static size_t step_tabs_bytes(int n_cars) {
 static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
                         const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward,
                         cudaStream_t s) {
+    if (int rc = sync_join(h, s)) return rc; // a sub-step kernel may read the table (greedy lanes)
     // Philox hand-over: the car-0 launch of a round publishes the decision words of cars 1..3
     int rng_mode = 0;
     const uint32_t order_slot = (uint32_t)car_slot;
@@ -695,6 +717,7 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
 static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s,
                          const Marks *marks = nullptr, int early_trigger = 0) {
     const Marks mk = marks ? *marks : marks_of(h);
+    if (int rc = sync_join(h, s)) return rc;
     if (h->cv.dense) {
         LearnLaunch ll(h, grid_for(mk.n_marks), s);
         MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
@@ -752,6 +775,8 @@ static int q_round_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_l
     ra.tiles_r = (uint32_t)(((h->n_envs + 31) / 32) % grid);
     Marks mk = marks_of(h);
     mk.n_ctas = grid;
+    if (!pure) // greedy lanes of the round kernel read the table: an exchange in flight comes first
+        if (int rc = sync_join(h, s)) return rc;
 #define MDPP_ROUND_K(KERNEL, SMEM, BIT)                                                                          \
     do {                                                                                                         \
         if (!((h->smem_configured >> (BIT)) & 1u)) {                                                             \
@@ -865,6 +890,7 @@ static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const 
             MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_marks_reduce_kernel, (const uint32_t *)mark_region(h, P, 0),
                                               ra.region_words, n_sub, words, words, h->cv.cta_slots, (uint32_t)grid, gbits));
         }
+        if (int rc = sync_join(h, s)) return rc; // the cluster pull reads the table (the reduce above only marks)
         MultiPullArgs pa{};
         pa.q = cur;
         pa.sinfo = mk.sinfo;
@@ -881,7 +907,7 @@ static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const 
         }
         cudaLaunchAttribute attrs[2];
         attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attrs[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+        attrs[0].val.programmaticStreamSerializationAllowed = (h->pdl && h->chain) ? 1 : 0;
         attrs[1].id = cudaLaunchAttributeClusterDimension;
         attrs[1].val.clusterDim.x = kMultiPullCtas;
         attrs[1].val.clusterDim.y = 1;
@@ -930,6 +956,7 @@ static int mixed_rounds_fit(mdpp_handle *h, int want) {
 }
 static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round, int n,
                                  cudaStream_t s) {
+    if (int rc = sync_join(h, s)) return rc;
     const int nc = h->cfg.n_cars;
     h->ep_bound += n;
     RoundArgs ra{};
@@ -972,6 +999,7 @@ static int q_mixed_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const
 }
 
 static int q_copy_launch(mdpp_handle *h, const float *src, float *dst, cudaStream_t s) {
+    if (int rc = sync_join(h, s)) return rc;
     const uint32_t n4 = (uint32_t)((size_t)h->cfg.n_states * MDPP_Q_ROW / 4);
     q_copy_kernel<<<grid_for(n4), kThreads, 0, s>>>((const float4 *)src, (float4 *)dst, n4);
     MDPP_CUDA(cudaGetLastError());
@@ -1018,12 +1046,31 @@ static SyncArgs sync_args(mdpp_handle *h, uint32_t epoch) {
     a.mode = getenv("MDPP_SYNC_MODE") ? (uint32_t)atoi(getenv("MDPP_SYNC_MODE")) : 0u;
     return a;
 }
-static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
+// beside: the exchange goes to the handle's side stream, forked from and later joined into the caller's stream
+// (sync_join), so that the env kernel launched next on the caller's stream runs beside it.  As a member of the
+// caller's stream -- even with programmatic dependent launch on both sides -- the env kernel did not start before
+// the exchange had finished (one GPU, no peer to wait for: 31.1 us per round at interval 1 against 21.9 with an
+// empty exchange kernel and 20.1 without any).
+static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s, bool beside = false) {
     if (h->sync_world <= 1) return MDPP_OK;
     if ((void *)q != h->sync_bufs[h->sync_rank])
         return fail(MDPP_EINVAL, "replica averaging: q must be the table of this rank's exchange buffer");
+    if (int rc = sync_join(h, s)) return rc; // (never pending here: every round's pulls join first)
     const SyncArgs a = sync_args(h, ++h->sync_epoch);
-    const bool no_pdl = (a.mode & 16u) != 0; // experiment: plain stream order around the exchange
+    if (getenv("MDPP_SYNC_BESIDE") && atoi(getenv("MDPP_SYNC_BESIDE")) == 0) beside = false; // A/B runs
+    cudaStream_t main_stream = s;
+    if (beside) {
+        if (!h->sync_stream) {
+            MDPP_CUDA(cudaStreamCreateWithFlags(&h->sync_stream, cudaStreamNonBlocking));
+            MDPP_CUDA(cudaEventCreateWithFlags(&h->sync_fork, cudaEventDisableTiming));
+            MDPP_CUDA(cudaEventCreateWithFlags(&h->sync_join, cudaEventDisableTiming));
+        }
+        MDPP_CUDA(cudaEventRecord(h->sync_fork, main_stream)); // after the last pull: the own table is final
+        MDPP_CUDA(cudaStreamWaitEvent(h->sync_stream, h->sync_fork, 0));
+        s = h->sync_stream;
+    }
+    const bool saved_chain = h->chain;
+    const bool no_pdl = beside || (a.mode & 16u) != 0; // plain launch on the side stream
     if (no_pdl) h->chain = false;
     LearnLaunch ll(h, sync_ctas(h), s, kSyncThreads);
     switch (h->sync_world) {
@@ -1036,7 +1083,13 @@ static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s) {
     default: MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_sync_kernel<8>, a)); break;
     }
     h->sync_count += 1;
-    h->chain = !no_pdl;
+    if (beside) {
+        MDPP_CUDA(cudaEventRecord(h->sync_join, h->sync_stream));
+        h->sync_pending = true;
+        h->chain = saved_chain; // the caller's stream goes on where it was
+    } else {
+        h->chain = !no_pdl;
+    }
     return MDPP_OK;
 }
 
@@ -1182,7 +1235,7 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
                 if (rc) return rc;
                 std::swap(cur, alt);
             }
-            int rc = q_sync_launch(h, q, s);
+            int rc = q_sync_launch(h, q, s, true);
             if (rc) return rc;
         }
         const int room = sync_room(h, first_round + (uint64_t)r, rounds - r); // rounds up to the next averaging
@@ -1224,6 +1277,7 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
     }
     int rc = MDPP_OK;
     if (cur != q) rc = q_copy_launch(h, cur, q, s); // odd number of sub-steps: bring the table home
+    if (!rc) rc = sync_join(h, s); // (a frozen learner has no pull that would have joined)
     h->chain = false;
     return rc;
 }
