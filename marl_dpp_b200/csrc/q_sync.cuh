@@ -86,7 +86,10 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
             }
         } else {
             // one release fence, a relaxed store; poll with relaxed loads and fence once after the flag arrived
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            // (variant 3: no fence at all -- the tables were written by kernels that completed before this one started,
+            // and the second signal follows instructions that consumed every loaded value)
+            const bool fences = (a.mode & 3u) != 3u;
+            if (fences) asm volatile("fence.acq_rel.sys;" ::: "memory");
             asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + slot + a.rank), "r"(a.epoch) : "memory");
             if (!((a.mode & 3u) == 2u && phase == 1u)) {
                 uint32_t v, spins = 0;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase
                         }
                     }
                 } while ((int32_t)(v - a.epoch) < 0);
-                asm volatile("fence.acq_rel.sys;" ::: "memory");
+                if (fences) asm volatile("fence.acq_rel.sys;" ::: "memory");
             }
         }
     }

@@ -37,7 +37,7 @@ def timed(fn, reps=200):
     return float(t[0])
 
 
-for mode in ("0", "1", "2"):
+for mode in ("0", "1", "2", "3"):
     os.environ["MDPP_SYNC_MODE"] = mode
     us = timed(lr.sync_replicas)
     if rank == 0:

@@ -21,8 +21,9 @@ ex.attach(lr, 0, rank=0)
 lr.train_rounds(256)
 env.stats()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for mode, what in ((0, "as shipped"), (4, "no exchange body, chain membership only"), (8, "wait before release"),
-                   (12, "no body, wait before release"), (16, "plain stream order around the exchange"), (20, "plain order, no body")):
+os.environ["MDPP_SYNC_BESIDE"] = "0"   # the protocol variants are timed in plain stream order: their own duration
+for mode, what in ((16, "acquire polling, fences"), (17, "relaxed polling, one fence per signal and per wait"),
+                   (19, "relaxed, no fences"), (20, "no exchange body")):
     os.environ["MDPP_SYNC_MODE"] = str(mode)
     ex.attach(lr, 1, rank=0)
     lr.round = ((lr.round + 63) // 64) * 64
@@ -35,6 +36,7 @@ for mode, what in ((0, "as shipped"), (4, "no exchange body, chain membership on
     env.stats()
     print("interval 1, mode %2d (%s): %.2f us per round" % (mode, what, a.elapsed_time(b) / 256 * 1e3))
 os.environ["MDPP_SYNC_MODE"] = "0"
+os.environ["MDPP_SYNC_BESIDE"] = "1"
 for iv in (0, 1, 4, 64, 0):
     ex.attach(lr, iv, rank=0)
     lr.round = ((lr.round + 63) // 64) * 64
