@@ -1070,7 +1070,7 @@ static int q_sync_launch(mdpp_handle *h, float *q, cudaStream_t s, bool beside =
         s = h->sync_stream;
     }
     const bool saved_chain = h->chain;
-    const bool no_pdl = beside || (a.mode & 16u) != 0; // plain launch on the side stream
+    const bool no_pdl = beside; // plain launch on the side stream
     if (no_pdl) h->chain = false;
     LearnLaunch ll(h, sync_ctas(h), s, kSyncThreads);
     switch (h->sync_world) {

@@ -8,7 +8,7 @@
 //   * every rank's table lives in a peer-mapped exchange buffer (CUDA IPC; mdpp_sync_alloc / mdpp_sync_open),
 //     followed by a small flag area;
 //   * CTA b of every rank owns the same slice of the table.  It tells CTA b of every peer "my table is final"
-//     (a release store into the peer's flag area), waits for the same word from every peer, reads the slice from
+//     (a store into the peer's flag area), waits for the same word from every peer, reads the slice from
 //     ALL ranks' buffers -- every load of a thread in flight at once: one NVLink round trip -- adds them in rank
 //     order and divides by the rank count, so that every rank computes the same bits;
 //   * a second handshake ("I have read your slice") precedes the only write: the slice of the own table.  Nobody
@@ -18,10 +18,11 @@
 // world x table bytes, right for tables of a few MB at NVLink bandwidth; larger tables (4-5 cars) take the
 // caller's NCCL path.
 //
-// Chain membership: the kernel releases its successor at once and then waits for its predecessor (the last pull:
-// the local table is final) with griddepcontrol.wait.  The next env kernel never reads the table before its
-// own griddepcontrol.wait, so a pure-exploration round runs WHILE the replicas are exchanged and the exchange
-// disappears from the critical path; the pulls of that round start after the env kernel, hence after this one.
+// Overlap: inside mdpp_q_train_rounds the kernel runs on a stream of its own, forked from the caller's stream after
+// the last pull and joined again before the next kernel that touches the table (mdpp_api.inl q_sync_launch /
+// sync_join).  The next env kernel never reads the table while every env explores, so a pure-exploration round runs
+// WHILE the replicas are exchanged; the pulls of that round wait for the join.  Its CTAs are small enough (128
+// threads, <= 56 registers) to be resident beside the env kernel's 1024-thread CTA on the same SM.
 #pragma once
 #include "env_core.cuh"
 
@@ -43,18 +44,9 @@ struct SyncArgs {
     uint32_t per;                   // chunks of kSyncThreads float4 per CTA (1..kSyncPer)
     unsigned long long timeout_ns;  // a peer that never arrives must not hang the GPU: give up, count an error
     unsigned long long *errors;     // Control::stats[0].internal_errors
-    uint32_t mode;                  // experiments (MDPP_SYNC_MODE): 0 = acquire polling, 1 = relaxed polling + one fence,
-                                    // 2 = 1 without waiting in the second handshake (UNSAFE, timing only)
+    uint32_t mode;                  // MDPP_SYNC_MODE bit 0: system-scope fences around every flag (comparison runs)
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4 *p) {
     float4 v;
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -67,47 +59,41 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-// one phase of the handshake between the CTAs `b` of all ranks: thread t < world signals rank t and waits for it
+// One phase of the handshake between the CTAs `b` of all ranks: thread t < world signals rank t and waits for it.
+//
+// Flags travel as relaxed system-scope stores and are polled with relaxed system-scope loads, WITHOUT fences:
+//   * "my table is final": the table was written by kernels that completed before this one started; a peer reads it
+//     through NVLink from the owner's L2, the point of coherence, where those writes are;
+//   * "I have read your slice": every thread consumed the values it loaded (the sums are formed) before the CTA
+//     barrier in front of the signal, so the loads have completed; the waiting side writes its slice only after its
+//     poll loop has exited (stores are not speculated).
+// This is the established shape of latency-critical all-reduce barriers over NVLink peer memory (volatile flag
+// stores / loads at the start barrier, no fence before a kernel's final barrier).  System-scope fences made each
+// phase ~5 us more expensive: 20.4 us per exchange on 2 GPUs against 9.8 without (ncclAllReduce of the same table:
+// 18.1).  MDPP_SYNC_MODE=1 selects the fenced form (release / acquire around every flag) for comparison.
 __device__ __forceinline__ void sync_handshake(const SyncArgs &a, uint32_t phase, uint32_t b) {
     __syncthreads(); // everything this CTA did before (its reads of the peers' slices) is ordered before the signal
     if (threadIdx.x < a.world) {
         const uint32_t t = threadIdx.x;
         const size_t slot = ((size_t)phase * kSyncMaxCtas + b) * kSyncMaxRanks;
         const uint32_t *mine = a.flags[a.rank] + slot + t;
-        if ((a.mode & 3u) == 0u) {
-            __threadfence_system();
-            st_release_sys(a.flags[t] + slot + a.rank, a.epoch);
-            const unsigned long long t0 = global_ns();
-            while ((int32_t)(ld_acquire_sys(mine) - a.epoch) < 0) {
-                if (global_ns() - t0 > a.timeout_ns) {
+        const bool fences = (a.mode & 1u) != 0u;
+        if (fences) asm volatile("fence.acq_rel.sys;" ::: "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + slot + a.rank), "r"(a.epoch) : "memory");
+        uint32_t v, spins = 0;
+        unsigned long long t0 = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((++spins & 0xFFFu) == 0u) { // a peer that never arrives: give up after timeout_ns, count an error
+                const unsigned long long now = global_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > a.timeout_ns) {
                     atomicAdd(a.errors, 1ull);
                     break;
                 }
             }
-        } else {
-            // one release fence, a relaxed store; poll with relaxed loads and fence once after the flag arrived
-            // (variant 3: no fence at all -- the tables were written by kernels that completed before this one started,
-            // and the second signal follows instructions that consumed every loaded value)
-            const bool fences = (a.mode & 3u) != 3u;
-            if (fences) asm volatile("fence.acq_rel.sys;" ::: "memory");
-            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.flags[t] + slot + a.rank), "r"(a.epoch) : "memory");
-            if (!((a.mode & 3u) == 2u && phase == 1u)) {
-                uint32_t v, spins = 0;
-                unsigned long long t0 = 0;
-                do {
-                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-                    if ((++spins & 0xFFFu) == 0u) {
-                        const unsigned long long now = global_ns();
-                        if (t0 == 0) t0 = now;
-                        else if (now - t0 > a.timeout_ns) {
-                            atomicAdd(a.errors, 1ull);
-                            break;
-                        }
-                    }
-                } while ((int32_t)(v - a.epoch) < 0);
-                if (fences) asm volatile("fence.acq_rel.sys;" ::: "memory");
-            }
-        }
+        } while ((int32_t)(v - a.epoch) < 0);
+        if (fences) asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
     __syncthreads();
 }
@@ -152,14 +138,8 @@ q_sync_kernel(SyncArgs a) {
     // parity of the mark regions only, and waits for this grid before it reads the table or exits).  With the
     // release after the wait the env kernel could not start before the pull had completed: +20 us per exchange on
     // 2 GPUs, the pull's overlap lost and a launch latency exposed.
-    if (a.mode & 8u) { // experiment: wait first, release after (the first version's order)
-        pdl_wait();
-        pdl_launch_dependents();
-    } else {
-        pdl_launch_dependents();
-        pdl_wait();          // the last pull has completed: the own table is final
-    }
-    if (a.mode & 4u) return; // experiment: no exchange at all, only the chain membership
+    pdl_launch_dependents();
+    pdl_wait();              // launched in a kernel chain (mdpp_q_sync_replicas): the last pull has completed
     sync_slice<WORLD>(a, blockIdx.x);
 }
 

@@ -21,23 +21,10 @@ ex.attach(lr, 0, rank=0)
 lr.train_rounds(256)
 env.stats()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-os.environ["MDPP_SYNC_BESIDE"] = "0"   # the protocol variants are timed in plain stream order: their own duration
-for mode, what in ((16, "acquire polling, fences"), (17, "relaxed polling, one fence per signal and per wait"),
-                   (19, "relaxed, no fences"), (20, "no exchange body")):
-    os.environ["MDPP_SYNC_MODE"] = str(mode)
-    ex.attach(lr, 1, rank=0)
-    lr.round = ((lr.round + 63) // 64) * 64
-    torch.cuda.synchronize()
-    a.record()
-    for _ in range(4):
-        lr.train_rounds(64)
-    b.record()
-    torch.cuda.synchronize()
-    env.stats()
-    print("interval 1, mode %2d (%s): %.2f us per round" % (mode, what, a.elapsed_time(b) / 256 * 1e3))
-os.environ["MDPP_SYNC_MODE"] = "0"
-os.environ["MDPP_SYNC_BESIDE"] = "1"
-for iv in (0, 1, 4, 64, 0):
+for beside in ("1", "0"):
+  os.environ["MDPP_SYNC_BESIDE"] = beside
+  print("exchange %s" % ("on its own stream beside the env kernel (default)" if beside == "1" else "in the caller's stream (MDPP_SYNC_BESIDE=0)"))
+  for iv in (0, 1, 4, 64):
     ex.attach(lr, iv, rank=0)
     lr.round = ((lr.round + 63) // 64) * 64
     torch.cuda.synchronize()
@@ -48,7 +35,7 @@ for iv in (0, 1, 4, 64, 0):
     b.record()
     torch.cuda.synchronize()
     env.stats()
-    print("interval %3d: %.2f us per round (%d exchanges)" % (iv, a.elapsed_time(b) / 256 * 1e3, lr.sync_count() - c0))
+    print("  interval %3d: %.2f us per round (%d exchanges)" % (iv, a.elapsed_time(b) / 256 * 1e3, lr.sync_count() - c0))
 os.environ["MDPP_MULTI_ROUND"] = "0"
 env2 = BatchedEnv(sc, 1 << 20, seed=3)
 lr2 = BatchedQLearner(env2, episodes=5000, seed=3)
