@@ -9,6 +9,12 @@ cap() { # name regex skip count cmd...
   timeout 300 "$@" > $out/${name}_plain.log 2>&1 && \
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -o $out/$name "$@" > $out/${name}_ncu.log 2>&1
   echo "$name rc=$?"
+  # gpurun_out/ may carry 64 MiB back: export the two pages the summaries are made from, drop the report
+  if [ -f $out/$name.ncu-rep ]; then
+    ncu -i $out/$name.ncu-rep --page raw --csv > $out/${name}_raw.csv 2>/dev/null
+    ncu -i $out/$name.ncu-rep --page source --csv --print-source sass > $out/${name}_src.csv 2>/dev/null
+    [ "$name" = "pure" ] || rm -f $out/$name.ncu-rep
+  fi
 }
 timeout 300 $B > $out/bench_plain.json 2> $out/bench_plain.err && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $out/launches_bench.csv $B > $out/launches_ncu.log 2>&1
