@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    extra = os.environ.get("MDPP_NVCC_EXTRA", "").split()  # e.g. -DMDPP_GHOST_BRANCH=1 for A/B builds (with MDPP_LIB)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
     subprocess.check_call(cmd)
     return LIB_PATH
 

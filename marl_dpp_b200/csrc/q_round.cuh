@@ -28,6 +28,10 @@
 #pragma once
 #include "q_learner.cuh"
 
+#ifndef MDPP_GHOST_BRANCH
+#define MDPP_GHOST_BRANCH 0 // 1: the ghost of a finished car behind a (rarely taken) branch instead of branch-free
+#endif
+
 namespace mdpp {
 
 // LeanTabs (fast_tabs.cuh): the step tables with a 9-bit "other" index (finished cars read a zero entry: no branch),
@@ -93,6 +97,13 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
         if (i == C) continue;
         const uint32_t fi = (uint32_t)(cars >> (12 * i)) & 0xFFFu, g = fi >> 9;
         uint2 oe = S.oth[i][fi & 0x1FFu];
+#if MDPP_GHOST_BRANCH
+        if ((fi & 0x100u) && g != 7u) { // a finished car whose ghost is still counted: rare
+            const uint32_t ng = g == 0u ? 7u : g - 1u;
+            if (g != 0u) oe = S.ghost[i];
+            nc = (nc & ~((CarsT)0xE00u << (12 * i))) | ((CarsT)(ng << 9) << (12 * i));
+        }
+#else
         const uint32_t done = (fi >> 8) & 1u;
         const uint32_t show = done & (0x7Eu >> g);
         const uint32_t ng = done ? ((0x75432107u >> (4u * g)) & 7u) : g;
@@ -100,6 +111,7 @@ __device__ __forceinline__ int round_car_step(const RoundSmem<NC> &S, const DevC
         oe.x |= S.ghost[i].x & mask;
         oe.y |= S.ghost[i].y & mask;
         nc = (nc & ~((CarsT)0xE00u << (12 * i))) | ((CarsT)(ng << 9) << (12 * i));
+#endif
         codes[i] = oe.x >> 18;
         occ18 |= oe.x & 0x3FFFFu;
         occ9 |= oe.y;
