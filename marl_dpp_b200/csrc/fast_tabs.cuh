@@ -157,6 +157,9 @@ __device__ __forceinline__ int32_t fast_reward(const FastView &v, uint32_t mv, u
 //     C(c+3,4) instead of multiplications and constant divisions.
 // Mode 1 (training / rollout: ghosts listed, counters move) only.  Bit-identical to fast_view by the oracle tests.
 // ------------------------------------------------------------------------------------------------
+#ifndef MDPP_LEAN_GHOST_BRANCH
+#define MDPP_LEAN_GHOST_BRANCH 0 // rollout (lean_view): 1 = ghost behind a branch, 0 = branch-free
+#endif
 constexpr int kLeanCodes = 160; // others-codes are <= 1 + 18 * 8
 template <int NC>
 struct LeanTabs {
@@ -208,6 +211,12 @@ __device__ __forceinline__ LeanView lean_view(const LeanTabs<NC> &S, uint32_t (&
         const uint32_t fi = f[i], g = fi >> 9;
         uint2 oe = S.oth[i][fi & 0x1FFu]; // zero for a finished car
         // ghost of a finished car: counter 5..1 -> shown, then one lower; 0 -> 7 (gone for good); 7 stays
+#if MDPP_LEAN_GHOST_BRANCH
+        if ((fi & 0x100u) && g != 7u) {
+            if (g != 0u) oe = S.ghost[i];
+            f[i] = (fi & 0x1FFu) | ((g == 0u ? 7u : g - 1u) << 9);
+        }
+#else
         const uint32_t done = (fi >> 8) & 1u;
         const uint32_t show = done & (0x7Eu >> g);                  // g in 1..6
         const uint32_t ng = done ? ((0x75432107u >> (4u * g)) & 7u) : g;
@@ -215,6 +224,7 @@ __device__ __forceinline__ LeanView lean_view(const LeanTabs<NC> &S, uint32_t (&
         oe.x |= S.ghost[i].x & mask;
         oe.y |= S.ghost[i].y & mask;
         f[i] = (fi & 0x1FFu) | (ng << 9);
+#endif
         codes[k++] = oe.x >> 18;
         occ18 |= oe.x & 0x3FFFFu;
         occ9 |= oe.y;

@@ -28,8 +28,12 @@
 #pragma once
 #include "q_learner.cuh"
 
+// The ghost of a finished car (listed for 5 encodes by the others) behind a rarely taken branch (1) or branch-free
+// (0: nibble table + masked OR).  Same-box A/B of the round kernels: the branch is faster -- chained rounds 14.98 vs
+// 15.81 us, one flushed round 25.7 vs 27.5, rounds with greedy decisions 30.2 vs 31.1 (the branch-free form costs
+// ~25 more instructions per tile and round, and ghosts are rare).
 #ifndef MDPP_GHOST_BRANCH
-#define MDPP_GHOST_BRANCH 0 // 1: the ghost of a finished car behind a (rarely taken) branch instead of branch-free
+#define MDPP_GHOST_BRANCH 1
 #endif
 
 namespace mdpp {
