@@ -158,7 +158,7 @@ __device__ __forceinline__ int32_t fast_reward(const FastView &v, uint32_t mv, u
 // Mode 1 (training / rollout: ghosts listed, counters move) only.  Bit-identical to fast_view by the oracle tests.
 // ------------------------------------------------------------------------------------------------
 #ifndef MDPP_LEAN_GHOST_BRANCH
-#define MDPP_LEAN_GHOST_BRANCH 0 // rollout (lean_view): 1 = ghost behind a branch, 0 = branch-free
+#define MDPP_LEAN_GHOST_BRANCH 1 // rollout (lean_view): 1 = ghost behind a branch (4 cars, 2^24 envs: 9.41e10 against 8.80e10 steps/s), 0 = branch-free
 #endif
 constexpr int kLeanCodes = 160; // others-codes are <= 1 + 18 * 8
 template <int NC>

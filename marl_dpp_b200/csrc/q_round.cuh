@@ -978,6 +978,16 @@ __device__ __forceinline__ void lean_rollout_chain(const LeanTabs<NC> &S, const 
     const uint32_t fc = f[C];
     if (!(fc & 0x100u)) {
         const LeanView v = lean_view<NC, C>(S, f, rank_stride);
+        // bad-state bits of this state's (others, destination box) for EVERY primary box: n_src_boxes (<= 18)
+        // consecutive bits.  The two words are requested here, as soon as the rank is known, and used after the
+        // action has been chosen: issued next to their use they were the kernel's hottest stall (4 x 4 % of the
+        // samples on the first use of each loaded word).
+        uint32_t bad_window = 0;
+        if (kind == MDPP_REWARD_Q && cfg.bad_on) {
+            const uint32_t base = (v.rank * cfg.n_dest_boxes + (v.own.x >> 29)) * cfg.n_src_boxes;
+            const uint32_t *wp = cfg.bad_bitmap + (base >> 5); // the bitmap carries one word of padding
+            bad_window = __funnelshift_r(__ldg(wp), __ldg(wp + 1), base & 31u);
+        }
         if (v.lm) {
             a = (S.nth[v.lm] >> (3u * (((w[C] & 0xFFFFu) * (uint32_t)__popc(v.lm)) >> 16))) & 7u;
             const uint32_t mv = S.next[C][fc & 0xFFu][a];
@@ -989,10 +999,8 @@ __device__ __forceinline__ void lean_rollout_chain(const LeanTabs<NC> &S, const 
             int32_t ri = -10 + 50 * ((int32_t)(v.own.w & 0xFFu) - (int32_t)(mv >> 10));
             if (reached) ri += (kind == MDPP_REWARD_DQN) ? 110 : 10010;
             if (kind == MDPP_REWARD_Q && cfg.bad_on) { // :568-577 on the heading-stripped strings
-                const uint32_t base = (v.rank * cfg.n_dest_boxes + (v.own.x >> 29)) * cfg.n_src_boxes - cfg.box_base;
-                const uint32_t idn = base + (nn >> 2), idp = base + (pnode >> 2);
-                const uint32_t bn = (__ldg(cfg.bad_bitmap + (idn >> 5)) >> (idn & 31u)) & 1u;
-                const uint32_t bp = (__ldg(cfg.bad_bitmap + (idp >> 5)) >> (idp & 31u)) & 1u;
+                const uint32_t bn = (bad_window >> ((nn >> 2) - cfg.box_base)) & 1u;
+                const uint32_t bp = (bad_window >> ((pnode >> 2) - cfg.box_base)) & 1u;
                 ri = bn ? -10000 : (bp ? 0 : ri);
             }
             rw = reward_float(ri, kind);
