@@ -597,10 +597,14 @@ def main():
                                         "episodes": sf["episodes_done"], "value": sf["agent_steps"] / dt, "unit": UNIT,
                                         "note": "2^20 envs x 5000 episodes per env, every epsilon segment, host wall clock"}
             del lrf, envf
+        # random-policy rollouts (BASELINE config 3).  Like the learner, every batch is first rolled (untimed) to its
+        # stationary mix of active and finished cars -- a round costs the same whether or not a car still moves --
+        # and the active fraction of the timed rounds is printed next to the rate.
         rounds = 16
         env2 = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=4)
-        for w in range(3):
+        for w in range(args.preroll // rounds):
             env2.rollout_random(rounds, w * rounds)
+        r0 = (args.preroll // rounds) * rounds
         torch.cuda.synchronize()
         env2.stats(reset=True)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -608,22 +612,25 @@ def main():
         flush.zero_()
         a.record()
         for w in range(reps):
-            env2.rollout_random(rounds, (3 + w) * rounds)
+            env2.rollout_random(rounds, r0 + w * rounds)
         b.record()
         torch.cuda.synchronize()
         s = env2.stats(reset=True)
         aux["random_rollout_no_outputs"] = {"value": s["agent_steps"] / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
-                                            "rounds_per_launch": rounds}
+                                            "rounds_per_launch": rounds,
+                                            "active_fraction": s["agent_steps"] / float(reps * rounds * n * k)}
+        r0 += reps * rounds
         outs = env2.alloc_rollout_outputs(1)
         a.record()
         for w in range(reps * 4):
-            env2.rollout_random(1, 1000 + w, outputs=outs)
+            env2.rollout_random(1, r0 + w, outputs=outs)
         b.record()
         torch.cuda.synchronize()
         s = env2.stats(reset=True)
         ms = a.elapsed_time(b)
         aux["random_rollout_outputs_materialised"] = {
             "value": s["agent_steps"] / (ms * 1e-3), "unit": UNIT, "rounds_per_launch": 1,
+            "active_fraction": s["agent_steps"] / float(reps * 4 * n * k),
             "algorithmic_GBps": (10.0 + 16.0 / k) * s["agent_steps"] / (ms * 1e-3) / 1e9}
         # gym-style e2e: host actions in, host (state, next, reward, legal, status, done) out, per car slot
         acts = torch.zeros(n, dtype=torch.uint8).pin_memory()
@@ -651,21 +658,28 @@ def main():
         n4 = 1 << 24
         env4 = BatchedEnv(sc4, n4, device=dev, seed=5)
         outs4 = env4.alloc_rollout_outputs(1)
+        for w in range(args.preroll // 16):            # untimed: to the stationary mix (see above)
+            env4.rollout_random(16, w * 16)
+        r4 = (args.preroll // 16) * 16
         for w in range(3):
-            env4.rollout_random(1, w, outputs=outs4)
+            env4.rollout_random(1, r4 + w, outputs=outs4)
         torch.cuda.synchronize()
         env4.stats(reset=True)
         a.record()
         for w in range(10):
-            env4.rollout_random(1, 3 + w, outputs=outs4)
+            env4.rollout_random(1, r4 + 3 + w, outputs=outs4)
         b.record()
         torch.cuda.synchronize()
         s = env4.stats(reset=True)
         ms = a.elapsed_time(b)
         aux["random_rollout_4car_16Mi_envs_outputs"] = {
             "value": s["agent_steps"] / (ms * 1e-3), "unit": UNIT, "rounds_per_launch": 1,
+            "active_fraction": s["agent_steps"] / float(10 * n4 * 4),
+            "car_slots_per_s": 10 * n4 * 4 / (ms * 1e-3),
             "algorithmic_GBps": (10.0 + 16.0 / 4) * s["agent_steps"] / (ms * 1e-3) / 1e9,
-            "note": "records (256 MiB) + outputs (640 MiB) exceed L2: HBM-streaming regime"}
+            "slot_GBps": (10.0 + 16.0 / 4) * 10 * n4 * 4 / (ms * 1e-3) / 1e9,
+            "note": "records (256 MiB) + outputs (640 MiB) exceed L2: HBM-streaming regime; every car slot of every env "
+                    "writes its 10 output bytes whether or not the car still moves (slot_GBps counts those)"}
         del env4, outs4
         # -dd precompute of the headline scenario (2 cars) and of the 4-car scenario: reachability bitmap
         for tag, scn in (("2car", sc), ("4car", sc4)):
