@@ -201,10 +201,18 @@ int mdpp_q_finalize(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, vo
  * workspace copy and are back in q when the call's work completes.  With flags == 0 on 1- and 2-car tables a
  * whole round is one env-kernel launch while every env is certainly in an epsilon = 1 segment (a host-side
  * bound on the episode counters, tightened at every mdpp_get_stats_host: fetch the counters now and then), and
- * up to 8 such rounds share one launch, their updates following in two more.  The result does not depend on how
- * the rounds are grouped into calls. */
+ * up to 8 such rounds share one launch, their updates following in two more.  Large tables (3-5 cars) keep one
+ * touched bitmap per sub-step and a MIRROR of the table in the workspace; a pull writes the keys marked in its own
+ * and in the previous sub-step from one copy into the other, and while every env explores all cars of several
+ * rounds are stepped in one pass over the batch.  The result does not depend on how the rounds are grouped into
+ * calls.  Every learner call leaves the current table in q. */
 int mdpp_q_train_rounds(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp, uint64_t first_round,
                         int rounds, void *stream);
+/* Large tables only (a no-op otherwise): between learner calls the mirror is a complete copy of q, which saves
+ * copying the table at the start of every call.  A caller that WRITES q itself between two learner calls (loads a
+ * qvalue file, averages replicas with a library all-reduce) says so before its next learner call; the library then
+ * copies the table once.  Passing a different q pointer than the previous call has the same effect. */
+int mdpp_q_table_written(mdpp_handle *h);
 /* end-to-end variant: learner parameters from host memory, stats copied back, synchronised */
 int mdpp_q_train_rounds_host(mdpp_handle *h, float *q /*DEV*/, const mdpp_learner *lp_host,
                              uint64_t first_round, int rounds, mdpp_stats *stats_host, void *stream);

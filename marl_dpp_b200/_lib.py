@@ -21,7 +21,7 @@ EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_err
            "mdpp_rollout_random", "mdpp_q_substep", "mdpp_q_finalize", "mdpp_q_train_rounds",
            "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_q_profile_env_rounds", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host",
            "mdpp_sync_buffer_bytes", "mdpp_sync_alloc", "mdpp_sync_free", "mdpp_sync_open", "mdpp_sync_close", "mdpp_sync_attach",
-           "mdpp_q_sync_replicas", "mdpp_sync_count", "mdpp_sync_emulate", "mdpp_deadlock_scratch_bytes",
+           "mdpp_q_sync_replicas", "mdpp_sync_count", "mdpp_q_table_written", "mdpp_sync_emulate", "mdpp_deadlock_scratch_bytes",
            "mdpp_deadlock_reachability_bfs", "mdpp_replay_insert", "mdpp_replay_compact", "mdpp_dqn_target"]
 
 
@@ -94,6 +94,7 @@ def lib():
         "mdpp_sync_attach": (I, [P, I, I, C.POINTER(P), I]),
         "mdpp_q_sync_replicas": (I, [P, F32, P]),
         "mdpp_sync_count": (U64, [P]),
+        "mdpp_q_table_written": (I, [P]),
         "mdpp_sync_emulate": (I, [C.POINTER(P), I, P]),
         "mdpp_deadlock_scratch_bytes": (I64, [P]),
         "mdpp_replay_insert": (I, [I64, U32, U8, U32, F32, U8, U8, U8, U8, I64, U32, U32, F32, U8, U8, P, P]),
@@ -102,6 +103,8 @@ def lib():
         "mdpp_deadlock_reachability_bfs": (I, [P, U32, P, I64, C.POINTER(C.c_int32), P]),
     }
     for name, (res, args) in sig.items():
+        if os.environ.get("MDPP_LIB") and not hasattr(L, name):
+            continue  # an older build in an A/B run
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args

@@ -261,12 +261,26 @@ class BatchedQLearner:
         self.params = learner_params(episodes, alpha, discount, probability_model,
                                      env.seed if seed is None else seed, flags)
         n_states = env.scenario.n_states
-        self.q = q if q is not None else torch.zeros((n_states, 8), dtype=torch.float32, device=env.device)
-        assert self.q.shape == (n_states, 8) and self.q.dtype == torch.float32 and self.q.is_contiguous()
+        self._q = q if q is not None else torch.zeros((n_states, 8), dtype=torch.float32, device=env.device)
+        assert self._q.shape == (n_states, 8) and self._q.dtype == torch.float32 and self._q.is_contiguous()
         self.round = 0
         L, h = env._L, env._h
         off = L.mdpp_visited_bits(h) - env.workspace.data_ptr()
         self.visited = env.workspace[off:off + 4 * n_states].view(torch.int32)
+
+    @property
+    def q(self):
+        """The Q table [n_states, 8] (slots 0..4 = S, L, R, F, T), current after every learner call.  Whoever takes
+        the tensor may write it (load a file, average replicas): large tables keep a mirror copy in the workspace,
+        so the library is told (mdpp_q_table_written) and copies the table once at its next learner call."""
+        self.env._L.mdpp_q_table_written(self.env._h)
+        return self._q
+
+    @q.setter
+    def q(self, t):
+        assert t.shape == self._q.shape and t.dtype == torch.float32 and t.is_contiguous()
+        self._q = t
+        self.env._L.mdpp_q_table_written(self.env._h)
 
     def substep(self, car, forced=None, outputs=False):
         env = self.env
@@ -279,14 +293,14 @@ class BatchedQLearner:
                    "state": torch.empty(n, dtype=torch.int32, device=dev),
                    "reward": torch.empty(n, dtype=torch.float32, device=dev)}
         with torch.cuda.device(dev):
-            _lib.check(env._L.mdpp_q_substep(env._h, _ptr(self.q), C.byref(self.params), car, self.round,
+            _lib.check(env._L.mdpp_q_substep(env._h, _ptr(self._q), C.byref(self.params), car, self.round,
                                              _ptr(forced), _ptr(out.get("action")), _ptr(out.get("state")),
                                              _ptr(out.get("reward")), _stream()))
         return out
 
     def finalize(self):
         with torch.cuda.device(self.env.device):
-            _lib.check(self.env._L.mdpp_q_finalize(self.env._h, _ptr(self.q), C.byref(self.params), _stream()))
+            _lib.check(self.env._L.mdpp_q_finalize(self.env._h, _ptr(self._q), C.byref(self.params), _stream()))
 
     def train_rounds(self, rounds):
         """`rounds` full round-robin rounds (n_cars x (sub-step + finalize)); asynchronous.
@@ -295,7 +309,7 @@ class BatchedQLearner:
         round and is tightened whenever `env.stats()` is fetched -- fetch the counters every few hundred rounds."""
         env = self.env
         with torch.cuda.device(env.device):
-            _lib.check(env._L.mdpp_q_train_rounds(env._h, _ptr(self.q), C.byref(self.params), self.round,
+            _lib.check(env._L.mdpp_q_train_rounds(env._h, _ptr(self._q), C.byref(self.params), self.round,
                                                   int(rounds), _stream()))
         self.round += int(rounds)
 
@@ -304,11 +318,11 @@ class BatchedQLearner:
         env = self.env
         s = MdppStats()
         if torch.cuda.current_device() == env.device.index:  # the common case: no device switch around the call
-            _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self.q), C.byref(self.params), self.round,
+            _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self._q), C.byref(self.params), self.round,
                                                        int(rounds), C.byref(s), _stream()))
         else:
             with torch.cuda.device(env.device):
-                _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self.q), C.byref(self.params), self.round,
+                _lib.check(env._L.mdpp_q_train_rounds_host(env._h, _ptr(self._q), C.byref(self.params), self.round,
                                                            int(rounds), C.byref(s), _stream()))
         self.round += int(rounds)
         return s.as_dict()
@@ -318,7 +332,7 @@ class BatchedQLearner:
         multi-round pure-exploration kernel); its marks are never pulled."""
         env = self.env
         with torch.cuda.device(env.device):
-            _lib.check(env._L.mdpp_q_profile_env_rounds(env._h, _ptr(self.q), C.byref(self.params), self.round,
+            _lib.check(env._L.mdpp_q_profile_env_rounds(env._h, _ptr(self._q), C.byref(self.params), self.round,
                                                         int(rounds), _stream()))
         self.round += int(rounds)
 
@@ -329,7 +343,7 @@ class BatchedQLearner:
         if getattr(self, "exchange", None) is not None:
             env = self.env
             with torch.cuda.device(env.device):
-                _lib.check(env._L.mdpp_q_sync_replicas(env._h, _ptr(self.q), _stream()))
+                _lib.check(env._L.mdpp_q_sync_replicas(env._h, _ptr(self._q), _stream()))
             return
         from . import parallel
         parallel.average_(self.q, group)

@@ -42,11 +42,16 @@ constexpr int kMaxPureRounds = 8;                 // pure-exploration rounds per
     } while (0)
 
 struct Carve {
-    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, gbits, bits, list, vals, visited, control, barrier, stage, dl, total;
-    uint32_t capacity; // touched-list entries per parity (list mode)
+    size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, gbits, bits, visited, control, barrier, stage, dl, total;
+    uint32_t scan_words;    // scan mode: words of one touched bitmap (a multiple of 4; bit = key = state * 8 + action)
+    uint32_t scan_regions;  // ... bitmaps per bank: sub-step i of a launch marks region i of the launch's bank.  THREE banks in
+                            // rotation: the pull of a sub-step clears the bitmap of the sub-step BEFORE it (its last reader)
+                            // while the next env kernel, which may already run, marks into the third
     uint32_t words_per_cta; // words of one per-CTA touched bitmap (dense mode)
     uint32_t cta_slots, regions; // layout of the bitmap array [parity][region][cta_slots][words_per_cta]
-    bool dense;        // small table: byte marks + ping-pong pull; else bitmap + list + two-pass pull
+    bool dense;        // small table: shared-memory marks + whole-table ping-pong pull; else global bitmaps + mirror table + scanning pull
+    bool scan;         // the global touched bitmaps of the scan mode exist: every non-dense table, and the mid-size dense ones
+                       // (shared-memory BIT maps, 3 cars), whose pure-exploration rounds take the scan mode's fused env pass
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -64,11 +69,11 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.sinfo = take((size_t)cfg.n_states * 4);
     // dense mode: the mark byte map of a persistent CTA lives in shared memory (one byte per key) and the pull
     // kernel sweeps the whole table once per sub-step (copy + substitute the marked keys) -- right while
-    // the table is a few hundred KB.  Larger tables keep a touched bitmap + list in global memory.
+    // the table is a few hundred KB.  Larger tables keep touched bitmaps in global memory and a mirror of the table
+    // (scan mode, q_pull_scan_kernel).
     const size_t marks = (size_t)cfg.n_states * MDPP_N_ACT;
     c.dense = marks <= kMaxDenseMarks;
     if (const char *env = getenv("MDPP_DENSE")) c.dense = c.dense && atoi(env) != 0;
-    c.capacity = (uint32_t)std::min<size_t>((size_t)n_envs, keys);
     c.words_per_cta = (uint32_t)(((marks + 31) / 32 + 7) & ~(size_t)7); // whole blocks of 8 words (slice_index)
     c.cta_slots = marks <= kMaxByteMapMarks ? kMaxRoundCtas : kMaxEnvCtas;
     // sub-step kernels use region 0; fused round: K0 map 0, K0 map 1, K1 map 1; several pure-exploration rounds per
@@ -79,12 +84,20 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
         c.marks = take((size_t)2 * c.regions * c.cta_slots * c.words_per_cta * 4); // [parity][region][cta][word]
         c.flags = take((size_t)2 * c.cta_slots * 4);
         c.gbits = take((size_t)c.regions * c.words_per_cta * 4); // reduced marks of a multi-round launch, one bitmap per sub-step
-        c.bits = c.list = c.vals = 0;
+        c.bits = 0;
     } else {
-        c.qalt = c.marks = c.flags = c.gbits = 0;
-        c.bits = take(2 * (keys / 8 + 4));
-        c.list = take(2 * (size_t)c.capacity * 4);
-        c.vals = take((size_t)c.capacity * 4);
+        c.marks = c.flags = c.gbits = 0;
+        c.qalt = take(keys * 4); // the mirror table
+    }
+    c.scan = !c.dense || marks > kMaxByteMapMarks;
+    if (const char *env = getenv("MDPP_HYBRID")) c.scan = c.scan && (!c.dense || atoi(env) != 0);
+    if (c.scan) {
+        c.scan_words = (uint32_t)(((keys + 31) / 32 + 3) & ~(size_t)3);
+        // pure-exploration rounds share a launch (q_rounds_pure_scan_kernel): as many rounds as fit 16 MB of bitmaps per bank
+        const size_t per_round = (size_t)cfg.n_cars * c.scan_words * 4;
+        const int rounds = (int)std::max<size_t>(1, std::min<size_t>((size_t)kMaxPureRounds, ((size_t)16 << 20) / per_round));
+        c.scan_regions = (uint32_t)(rounds * cfg.n_cars);
+        c.bits = take((size_t)3 * c.scan_regions * c.scan_words * 4);
     }
     c.visited = take((size_t)cfg.n_states * 4);
     c.control = take(sizeof(Control));
@@ -105,7 +118,13 @@ struct mdpp_handle {
     uint32_t env_id_base;
     char *ws;
     int sm_count;
-    uint32_t parity;        // sub-step parity of the marks / touched lists
+    uint32_t parity;        // sub-step parity of the marks (dense mode)
+    // scan mode: the mirror table (workspace) equals the caller's table except on the keys of one bitmap, where it is
+    // one update behind (q_pull_scan_kernel); between API calls it is either a complete copy or invalid
+    uint32_t *scan_stale;   // that bitmap, or NULL
+    uint32_t scan_bank;     // bank 0..2 the next scan-mode launch marks into
+    bool mirror_ok;         // the workspace copy and the caller's table mirror_q are such a pair (see mdpp_q_table_written)
+    const float *mirror_q;
     uint64_t rng_round;     // round whose Philox words the car-0 launch published
     uint32_t rng_seed;
     bool pdl;               // programmatic dependent launch between learner kernels (MDPP_PDL=0 disables)
@@ -114,6 +133,7 @@ struct mdpp_handle {
     int coop_ok;            // -1 unknown, 0 no cooperative launch / not co-resident, 1 ok
     bool multi_round;       // several pure-exploration rounds per launch (MDPP_MULTI_ROUND=0 disables)
     bool multi_pull;        // ... followed by one reduce + one cluster pull launch (MDPP_MULTI_PULL=0: dense pulls)
+    bool pure_scan;         // large tables: all cars of pure-exploration rounds in one env pass (MDPP_PURE_SCAN=0: sub-step kernels)
     bool chain;             // the previous launch on the stream was one of our learner kernels
     bool fast_rollout;      // the table-driven rollout kernel applies (BFS lengths fit its move table)
     uint64_t launches;      // learner kernels launched through this handle (bench.py's gpu_launches)
@@ -327,6 +347,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->coop_ok = -1;
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
+    h->pure_scan = !(getenv("MDPP_PURE_SCAN") && atoi(getenv("MDPP_PURE_SCAN")) == 0);
     h->chain = false;
     h->smem_configured = 0;
     h->round_parity = 0;
@@ -545,6 +566,10 @@ static uint32_t *mark_region(mdpp_handle *h, uint32_t parity, uint32_t region) {
     return (uint32_t *)(h->ws + h->cv.marks) + ((size_t)parity * h->cv.regions + region) * h->cv.cta_slots * h->cv.words_per_cta;
 }
 
+static uint32_t *scan_region(mdpp_handle *h, uint32_t bank, uint32_t region) { // scan mode: touched bitmap `region` of `bank`
+    return (uint32_t *)(h->ws + h->cv.bits) + ((size_t)bank * h->cv.scan_regions + region) * h->cv.scan_words;
+}
+
 static unsigned round_ctas(mdpp_handle *h) { // persistent CTAs of the fused round kernels
     const int64_t tiles = (h->n_envs + 31) / 32;
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((int64_t)h->sm_count * kRoundCtasPerSm, kMaxRoundCtas), tiles));
@@ -554,7 +579,6 @@ static Marks marks_of(mdpp_handle *h) {
     Marks m{};
     const size_t keys = (size_t)h->cfg.n_states * MDPP_Q_ROW;
     const uint32_t p = h->parity;
-    Control *ctl = (Control *)(h->ws + h->cv.control);
     m.dense = h->cv.dense ? 1u : 0u;
     if (h->cv.dense) {
         m.words_per_cta = h->cv.words_per_cta;
@@ -562,16 +586,15 @@ static Marks marks_of(mdpp_handle *h) {
         m.n_ctas = env_ctas(h);
         m.cta_bits = mark_region(h, p, 0);
     } else {
-        m.bits = (uint32_t *)(h->ws + h->cv.bits) + (size_t)p * (keys / 32 + 1);
-        m.list = (uint32_t *)(h->ws + h->cv.list) + (size_t)p * h->cv.capacity;
-        m.vals = (float *)(h->ws + h->cv.vals);
-        m.count = &ctl->touched_count[p];
-        m.count_other = &ctl->touched_count[p ^ 1u];
+        m.bits = scan_region(h, h->scan_bank, 0);
+        m.bits_prev = h->scan_stale;
+    }
+    if (h->cv.scan) {
+        m.scan_words = h->cv.scan_words;
         m.l1_check = keys / 8 <= ((size_t)4 << 20) ? 1u : 0u;
     }
     m.visited = (uint32_t *)(h->ws + h->cv.visited);
     m.sinfo = (const uint32_t *)(h->ws + h->cv.sinfo);
-    m.capacity = h->cv.capacity;
     m.n_keys = (uint32_t)keys;
     m.n_marks = (uint32_t)((size_t)h->cfg.n_states * MDPP_N_ACT);
     return m;
@@ -713,7 +736,18 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     return MDPP_OK;
 }
 
-// dense: qsrc -> qdst (whole table, marked keys substituted).  list: in place on qsrc, two passes.
+// qsrc -> qdst.  dense: the whole table, marked keys substituted.  scan: the keys marked in this and in the previous
+// sub-step (q_pull_scan_kernel); the caller swaps the tables afterwards in both modes.
+static unsigned scan_grid(const mdpp_handle *h) {
+    return (unsigned)(((int64_t)h->cv.scan_words + kThreads - 1) / kThreads); // a bitmap word per thread
+}
+static int q_scan_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s, const Marks &mk) {
+    LearnLaunch ll(h, scan_grid(h), s);
+    MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_pull_scan_kernel, (const float *)qsrc, qdst, mk, lp->alpha, lp->discount, control_of(h)));
+    h->scan_stale = mk.bits; // qsrc is now one update behind on these keys
+    h->chain = true;
+    return MDPP_OK;
+}
 static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_learner *lp, cudaStream_t s,
                          const Marks *marks = nullptr, int early_trigger = 0) {
     const Marks mk = marks ? *marks : marks_of(h);
@@ -722,17 +756,43 @@ static int q_pull_launch(mdpp_handle *h, float *qsrc, float *qdst, const mdpp_le
         LearnLaunch ll(h, grid_for(mk.n_marks), s);
         MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_pull_dense_kernel, (const float *)qsrc, qdst, mk, lp->alpha,
                                      lp->discount, early_trigger, control_of(h)));
+        h->mirror_ok = false; // (mid-size tables) qsrc is behind on keys no bitmap of the scan mode describes
+        if (!marks) h->parity ^= 1u;
     } else {
-        const unsigned grid = (unsigned)std::min<int64_t>(((int64_t)mk.capacity + kThreads - 1) / kThreads,
-                                                          (int64_t)h->sm_count * 8);
-        LearnLaunch l1(h, grid, s);
-        MDPP_LAUNCH(h, cudaLaunchKernelEx(&l1.cfg, q_pull_list_compute_kernel, (const float *)qsrc, mk, lp->alpha, lp->discount, control_of(h)));
-        h->chain = true;
-        LearnLaunch l2(h, grid, s);
-        MDPP_LAUNCH(h, cudaLaunchKernelEx(&l2.cfg, q_pull_list_apply_kernel, qsrc, mk, control_of(h)));
+        if (int rc = q_scan_pull_launch(h, qsrc, qdst, lp, s, mk)) return rc;
+        if (!marks) h->scan_bank = (h->scan_bank + 1u) % 3u;
     }
     h->chain = true;
-    if (!marks) h->parity ^= 1u;
+    return MDPP_OK;
+}
+
+// scan mode, before its first pull: `alt` must equal `cur` except on the keys of h->scan_stale.  The pair (caller's
+// table, workspace copy) stays like that from one learner call to the next (scan_settle) unless the caller has
+// written the table since (mdpp_q_table_written), passes another table, or a dense pull ran in between (mid-size
+// tables): then `cur` is copied once.
+static int scan_begin(mdpp_handle *h, const float *q, const float *cur, float *alt, cudaStream_t s) {
+    if (!h->cv.scan || (h->mirror_ok && h->mirror_q == q)) return MDPP_OK;
+    MDPP_CUDA(cudaMemcpyAsync(alt, cur, (size_t)h->cfg.n_states * MDPP_Q_ROW * 4, cudaMemcpyDeviceToDevice, s));
+    h->mirror_ok = true;
+    h->mirror_q = q;
+    h->scan_stale = nullptr; // (never set here: every path that leaves the scan mode settles first)
+    h->chain = false;
+    return MDPP_OK;
+}
+// scan mode: `cur` holds the table; the other copy is behind on the keys of the last sub-step's bitmap.  One
+// copy-only pass makes both complete (and clears that bitmap), after which either may be taken as the table: the
+// caller's pointers are reset to (q, workspace copy).
+static int scan_settle(mdpp_handle *h, float *q, float *&cur, float *&alt, cudaStream_t s) {
+    if (!h->scan_stale) return MDPP_OK;
+    Marks mk = marks_of(h);
+    mk.bits = nullptr;
+    mk.bits_prev = h->scan_stale;
+    LearnLaunch ll(h, scan_grid(h), s);
+    MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_pull_scan_kernel, (const float *)cur, alt, mk, 0.f, 0.f, control_of(h)));
+    h->scan_stale = nullptr;
+    h->chain = true;
+    cur = q;
+    alt = (float *)(h->ws + h->cv.qalt);
     return MDPP_OK;
 }
 
@@ -926,6 +986,70 @@ static int q_pure_rounds_launch(mdpp_handle *h, float *&cur, float *&alt, const 
         // every pull but the last is followed by another pull, which waits before it touches anything
         int rc = q_pull_launch(h, cur, alt, lp, s, &mk, i + 1 < n * nc ? 1 : 0);
         if (rc) return rc;
+        std::swap(cur, alt);
+    }
+    return MDPP_OK;
+}
+
+// scan mode (large tables): n pure-exploration rounds, all cars, in one env pass (q_rounds_pure_scan_kernel), then the
+// pulls of their n * n_cars sub-steps in order.  0 when the next rounds are not certainly inside the epsilon = 1 segment.
+static int pure_scan_rounds_fit(const mdpp_handle *h, const mdpp_learner *lp, int want) {
+    if (!h->cv.scan || !h->multi_round || !h->pure_scan || lp->eps_q16[0] < 65536u) return 0;
+    const int64_t room = (int64_t)lp->eps_threshold[0] - h->ep_bound; // rounds before the bound leaves the segment
+    const int cap = (int)(h->cv.scan_regions / (uint32_t)h->cfg.n_cars);
+    const int n = (int)std::min<int64_t>(std::min<int64_t>(want, cap), room);
+    return n >= 1 ? n : 0;
+}
+extern "C++" {
+template <int NC>
+static int pure_scan_kernel_launch(mdpp_handle *h, const mdpp_learner *lp, const PureScanArgs &pa, cudaStream_t s) {
+    const size_t smem = sizeof(LeanTabs<NC>);
+    if (!((h->smem_configured >> 31) & 1u)) {
+        MDPP_CUDA(cudaFuncSetAttribute(q_rounds_pure_scan_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->smem_configured |= 1u << 31;
+    }
+    const int64_t tiles = (h->n_envs + 31) / 32;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, (tiles + 7) / 8));
+    LearnLaunch ll(h, grid, s, kRolloutThreads, smem);
+    MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_rounds_pure_scan_kernel<NC>, h->dev, *lp, pa, control_of(h)));
+    h->chain = true;
+    return MDPP_OK;
+}
+} // extern "C++"
+static int q_pure_scan_rounds_launch(mdpp_handle *h, float *q, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round,
+                                     int n, cudaStream_t s) {
+    const int nc = h->cfg.n_cars;
+    if (int rc = scan_begin(h, q, cur, alt, s)) return rc; // (mid-size tables after a dense pull: one copy)
+    const uint32_t bank = h->scan_bank;
+    h->scan_bank = (h->scan_bank + 1u) % 3u;
+    h->ep_bound += n;
+    PureScanArgs pa{};
+    pa.recs = recs_of(h);
+    pa.n_envs = (uint32_t)h->n_envs;
+    pa.env_id_base = h->env_id_base;
+    pa.rounds = (uint32_t)n;
+    pa.first_round = round;
+    pa.tabs = (const FastTabs *)(h->ws + h->cv.fast);
+    pa.rank_stride = (uint32_t)(h->cfg.n_dest_nodes * h->cfg.n_local_nodes);
+    pa.n_states = (uint32_t)h->cfg.n_states;
+    pa.bits0 = scan_region(h, bank, 0);
+    pa.region_words = h->cv.scan_words;
+    Marks mk = marks_of(h);
+    pa.l1_check = mk.l1_check;
+    int rc;
+    switch (nc) { // (the env pass touches records and marks only: an exchange in flight need not be joined first)
+    case 1: rc = pure_scan_kernel_launch<1>(h, lp, pa, s); break;
+    case 2: rc = pure_scan_kernel_launch<2>(h, lp, pa, s); break;
+    case 3: rc = pure_scan_kernel_launch<3>(h, lp, pa, s); break;
+    case 4: rc = pure_scan_kernel_launch<4>(h, lp, pa, s); break;
+    default: rc = pure_scan_kernel_launch<5>(h, lp, pa, s); break;
+    }
+    if (rc) return rc;
+    for (int i = 0; i < n * nc; i++) {
+        mk.bits = scan_region(h, bank, (uint32_t)i);
+        mk.bits_prev = h->scan_stale;
+        if ((rc = sync_join(h, s))) return rc;
+        if ((rc = q_scan_pull_launch(h, cur, alt, lp, s, mk))) return rc;
         std::swap(cur, alt);
     }
     return MDPP_OK;
@@ -1188,9 +1312,16 @@ int mdpp_q_sync_replicas(mdpp_handle *h, float *q, void *stream) {
     h->chain = false; // the caller may have put anything on the stream since our last launch
     int rc = q_sync_launch(h, q, (cudaStream_t)stream);
     h->chain = false;
+    h->mirror_ok = false; // (scan mode) the exchange rewrites the table
     return rc;
 }
 uint64_t mdpp_sync_count(mdpp_handle *h) { return h ? h->sync_count : 0; }
+
+int mdpp_q_table_written(mdpp_handle *h) {
+    if (!h) return fail(MDPP_EINVAL, "handle is NULL");
+    h->mirror_ok = false; // scan mode: the next learner call copies the table into the mirror first
+    return MDPP_OK;
+}
 
 int mdpp_q_substep(mdpp_handle *h, float *q, const mdpp_learner *lp, int car_slot, uint64_t round,
                    const uint8_t *forced, uint8_t *action_out, uint32_t *state_idx, float *reward, void *stream) {
@@ -1208,10 +1339,12 @@ int mdpp_q_finalize(mdpp_handle *h, float *q, const mdpp_learner *lp, void *stre
     if (!q || !lp) return fail(MDPP_EINVAL, "q / learner is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     h->chain = false;
-    float *alt = h->cv.dense ? (float *)(h->ws + h->cv.qalt) : q;
-    int rc = q_pull_launch(h, q, alt, lp, s);
+    float *alt = (float *)(h->ws + h->cv.qalt);
+    int rc = h->cv.dense ? MDPP_OK : scan_begin(h, q, q, alt, s);
+    if (!rc) rc = q_pull_launch(h, q, alt, lp, s);
     if (rc) return rc;
-    if (h->cv.dense) rc = q_copy_launch(h, alt, q, s);
+    float *cur = alt, *other = q;
+    rc = h->cv.dense ? q_copy_launch(h, alt, q, s) : scan_settle(h, q, cur, other, s);
     h->chain = false;
     return rc;
 }
@@ -1225,20 +1358,40 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
     if (int rc = validate_learner(lp)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     h->chain = false;
-    float *cur = q, *alt = h->cv.dense ? (float *)(h->ws + h->cv.qalt) : q; // dense: the table ping-pongs
+    float *cur = q, *alt = (float *)(h->ws + h->cv.qalt); // the table ping-pongs (dense: whole copies; scan: a mirror)
     const bool frozen = (lp->flags & MDPP_LEARN_FROZEN) != 0;
     const bool fused = lp->flags == 0 && round_eligible(h);
+    if (!frozen && !h->cv.dense)
+        if (int rc = scan_begin(h, q, cur, alt, s)) return rc;
     for (int r = 0; r < rounds; r++) {
         if (sync_due(h, first_round + (uint64_t)r)) { // replica averaging before this round (q_sync.cuh)
-            if (cur != q) { // an odd number of pulls so far: the exchange runs on the caller's table
+            if (h->scan_stale) { // scan mode: both copies complete, the caller's table current
+                int rc = scan_settle(h, q, cur, alt, s);
+                if (rc) return rc;
+            } else if (cur != q) { // an odd number of pulls so far: the exchange runs on the caller's table
                 int rc = q_copy_launch(h, cur, q, s);
                 if (rc) return rc;
                 std::swap(cur, alt);
             }
-            int rc = q_sync_launch(h, q, s, true);
+            int rc = q_sync_launch(h, q, s, h->cv.dense);
             if (rc) return rc;
+            if (h->sync_world > 1) h->mirror_ok = false; // the exchange rewrites the table
+            if (!h->cv.dense && h->sync_world > 1 && !frozen) { // ... and the mirror follows
+                if ((rc = sync_join(h, s))) return rc;
+                if ((rc = scan_begin(h, q, cur, alt, s))) return rc;
+            }
         }
         const int room = sync_room(h, first_round + (uint64_t)r, rounds - r); // rounds up to the next averaging
+        if (h->cv.scan && lp->flags == 0) { // 3-5 cars: all cars of several pure-exploration rounds in one env pass
+            if (const int n = pure_scan_rounds_fit(h, lp, room)) {
+                int rc = q_pure_scan_rounds_launch(h, q, cur, alt, lp, first_round + (uint64_t)r, n, s);
+                if (rc) return rc;
+                r += n - 1;
+                continue;
+            }
+        }
+        if (h->cv.dense && h->scan_stale) // mid-size tables leaving the scan mode: the dense pulls know nothing of its bitmaps
+            if (int rc = scan_settle(h, q, cur, alt, s)) return rc;
         if (fused) { // training fast path: a whole round per launch (q_round.cuh), several while every env explores
             if (const int n = pure_rounds_fit(h, lp, room)) {
                 int rc = q_pure_rounds_launch(h, cur, alt, lp, first_round + (uint64_t)r, n, s);
@@ -1276,7 +1429,8 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
         }
     }
     int rc = MDPP_OK;
-    if (cur != q) rc = q_copy_launch(h, cur, q, s); // odd number of sub-steps: bring the table home
+    if (h->scan_stale) rc = scan_settle(h, q, cur, alt, s); // both copies complete: the caller's table is current
+    else if (cur != q) rc = q_copy_launch(h, cur, q, s); // odd number of sub-steps: bring the table home
     if (!rc) rc = sync_join(h, s); // (a frozen learner has no pull that would have joined)
     h->chain = false;
     return rc;

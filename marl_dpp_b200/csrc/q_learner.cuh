@@ -15,9 +15,13 @@
 //                       snapshot ("pull") and write it; ~10^3-10^4 keys instead of ~10^6 envs.
 // Small tables (dense mode) ping-pong between two table buffers: the pull kernel copies the whole
 // table and substitutes the marked keys, so there is no in-place hazard and no second pass.
-// Large tables (list mode) keep a touched bitmap + list and finalize in two passes (compute, apply).
-// Marks / bitmaps / lists are double-buffered by sub-step parity so that the env kernel of sub-step
-// t+1 may overlap the finalize of sub-step t (programmatic dependent launch).
+// Large tables (scan mode) keep one touched bitmap per sub-step in global memory (a fire-and-forget
+// atomic OR per env) and a MIRROR of the table: the pull of sub-step c scans the bitmaps of sub-steps
+// c-1 and c, reads table X and writes table Y -- the update for keys marked in c, a plain copy for keys
+// marked only in c-1 (where Y was left stale by the previous pull) -- and the two tables swap roles.
+// One pass per sub-step, no in-place hazard, nothing proportional to the table size.
+// Marks are double-buffered (by sub-step parity / by bank) so that the env kernel of sub-step
+// t+1 may overlap the pull of sub-step t (programmatic dependent launch).
 #pragma once
 #include "fast_tabs.cuh"
 
@@ -48,18 +52,15 @@ struct Marks {
     uint32_t *cta_bits2; // dense, fused round: bitmaps of the catch-up kernel (or NULL) ...
     const uint32_t *flags2; // ... valid for the CTAs whose flag is set
     uint32_t n_ctas, words_per_cta, cta_slots;
-    uint32_t *bits;      // list: [n_keys / 32] touched bitmap, parity of the current sub-step
-    uint32_t *list;      // list: [capacity] touched keys
-    uint32_t *count;     // list: number of listed keys (Control::touched_count[parity])
-    uint32_t *count_other; // list: the other parity's counter (zeroed by the compute pass)
-    float *vals;         // list: [capacity] new values between the compute and the apply pass
+    uint32_t *bits;      // scan: [n_keys / 32] touched bitmap of the current sub-step (bit = key = state * 8 + action)
+    uint32_t *bits_prev; // scan: bitmap of the previous sub-step (keys where the pull's destination table is stale) or NULL
+    uint32_t scan_words; // scan: words of one bitmap (a multiple of 4)
     uint32_t *visited;   // [n_states] bit a = (state, a) has been updated at least once (qvalue file writer)
     const uint32_t *sinfo; // [n_states] per-state info words
-    uint32_t capacity;
     uint32_t dense;
     uint32_t n_keys;
     uint32_t n_marks; // dense: n_states * 5 -- marks are indexed by the compact key  state * 5 + action
-    uint32_t l1_check; // list: test the bitmap word through L1 before the returning atomic
+    uint32_t l1_check; // scan: test the bitmap word through L1 before the atomic
 };
 
 // epsilon schedule (reference src/utils/utils.py:33-52, model 3) on the per-env episode counter
@@ -323,9 +324,21 @@ __device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &c
     }
 }
 
-// list mode (large tables): one CTA per 256-env tile, touched bitmap + key list in global memory.  The step tables
-// are read in place through L1 (a 256-env CTA cannot amortise staging 40 KB; a persistent variant with staged
-// tables measured 10-40 % slower: fewer warps to hide the returning atomic).
+// scan mode (large tables): one CTA per 256-env tile, one touched bitmap per sub-step in global memory.  The step
+// tables are read in place through L1 (a 256-env CTA cannot amortise staging 40 KB; a persistent variant with
+// staged tables measured 10-40 % slower when the atomic still returned a value).
+__device__ __forceinline__ void scan_mark(uint32_t *__restrict__ bits, uint32_t key, uint32_t l1_check) {
+    // Check through L1 first: atomics on a hot bitmap word are what L2 serialises (ncu, 4 cars: 80 us with 1.3 M
+    // atomic sectors for the car slot whose envs share states, 21 us with 0.4 M for the one whose envs are spread).
+    // L1 is not coherent, but the word can only be stale towards "clear" -- bits are set during this launch and were
+    // cleared by a pull that completed before it -- and a stale clear bit just costs the atomic.  Only for
+    // bitmaps of a few MB: on the 5-car table (16 MB bitmap, 1e5 keys per sub-step) the extra load misses.
+    // The result of the atomic is not used: a reduction (RED), nothing for the lane to wait for.
+    const uint32_t bit = 1u << (key & 31u);
+    uint32_t *w = bits + (key >> 5);
+    if (!l1_check || !(*w & bit)) atomicOr(w, bit);
+}
+
 template <int NC, int C, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
 q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
@@ -338,32 +351,9 @@ q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StepCounts cnt;
-    bool first = false; // this lane is the first toucher of its key in this sub-step
     uint32_t key = 0;
-    if (e < ea.n_envs) {
-        if (env_substep<NC, C, PLAIN>(S, cfg, lp, ea, e, ea.recs[e], key, cnt)) {
-            // Check through L1 first: the returning atomic on a hot bitmap word is what this kernel waits for
-            // (ncu, 4 cars: 80 us with 1.3 M atomic sectors for the car slot whose envs share states, 21 us with
-            // 0.4 M for the one whose envs are spread).  L1 is not coherent, but the word can only be stale
-            // towards "clear" -- bits are set during this launch and were cleared by an apply kernel that
-            // completed before it -- and a stale clear bit just costs the atomic.  Only for bitmaps of a few MB:
-            // on the 5-car table (16 MB bitmap, 1e5 keys per sub-step) the extra load misses and costs 25 %.
-            const uint32_t bit = 1u << (key & 31u);
-            uint32_t *w = mk.bits + (key >> 5);
-            if (!mk.l1_check || !(*w & bit)) first = !(atomicOr(w, bit) & bit);
-        }
-    }
-    { // first touchers append their key, one counter atomic per warp
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, first);
-        if (bal) {
-            const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)bal) - 1u;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(mk.count, (uint32_t)__popc(bal));
-            base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
-            const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-            if (first && slot < mk.capacity) mk.list[slot] = key;
-        }
-    }
+    if (e < ea.n_envs)
+        if (env_substep<NC, C, PLAIN>(S, cfg, lp, ea, e, ea.recs[e], key, cnt)) scan_mark(mk.bits, key, mk.l1_check);
     flush_counts<PLAIN>(cnt, cc, PLAIN ? 0u : lp.flags, ctl);
     // every kernel of the chain waits for its predecessor before it exits, so that "my predecessor has
     // completed" implies "everything before it has completed" (lanes that explored never waited above)
@@ -552,40 +542,73 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
                   (unsigned long long)touched);
 }
 
-// list mode, pass 1: new value of every listed key into vals[] (the table is read-only here)
+// scan mode: the pull of one sub-step in ONE pass.  X = the table as the sub-step began (complete), Y = the other
+// table, equal to X except on the keys of `bits_prev` (marked in the previous sub-step: Y is one update behind there).
+// Every key marked now receives its update computed from X; every key marked only before is copied; afterwards Y is
+// the complete new table and X is one update behind on the keys of `bits` -- the next pull's `bits_prev`.  X is never
+// written and Y never read: no in-place hazard, no second pass, and nothing proportional to the table size except
+// the scan of two bitmaps.  bits == NULL: settle (copy only; both tables equal afterwards).
+// Work is balanced per KEY, not per bitmap word: hot states cluster (the 36-72 states that share the others and the
+// destination are neighbours, and a popular configuration marks most of their 5 actions), and a thread that walked
+// the bits of its own words one dependent load chain after the other made the first version of this kernel 60 us
+// long for 20 k keys.  Each thread takes one word of each bitmap, the CTA queues the set bits in shared memory, and
+// the queue is processed one key per thread, every load chain of a pass in flight at once.  (Measured and dropped:
+// persistent CTAs walking four words per thread with a batched queue -- contiguous ranges 82 us per 4-car round
+// against 62, round-robin 32-word groups 72: fewer CTAs in flight, the same per-key latency chain.)
+// The table is read past L1 (ld.global.cg): these pulls may run BESIDE a long env kernel on the same SM
+// (mdpp_api.inl, q_pure_scan_rounds_launch), where a line cached by the pull before last must not be trusted.
+constexpr uint32_t kScanQueue = kThreads * 4 * MDPP_N_ACT; // a word covers 4 states x 5 actions
 __global__ void __launch_bounds__(kThreads)
-q_pull_list_compute_kernel(const float *__restrict__ q, Marks mk, float alpha, float discount, Control *ctl) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const uint32_t n = min(*mk.count, mk.capacity);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *mk.count_other = 0; // the next sub-step appends under the other parity
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = mk.list[i];
-        if (key >= mk.n_keys) { // guard
+q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk, float alpha, float discount, Control *ctl) {
+    __shared__ uint32_t queue[kScanQueue]; // key << 1 | marked in this sub-step
+    __shared__ uint32_t n_queued;
+    if (threadIdx.x == 0) n_queued = 0;
+    pdl_wait();              // the env kernel that set the marks (and, by the chain rule, the previous pull) has completed
+    pdl_launch_dependents(); // the next env kernel may start; it waits for us before its first Q read
+    __syncthreads();
+    const uint32_t n_states = mk.n_keys / MDPP_Q_ROW;
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0, p = 0;
+    if (w < mk.scan_words) {
+        if (mk.bits) c = __ldcg(mk.bits + w);
+        if (mk.bits_prev) {
+            p = __ldcg(mk.bits_prev + w);
+            if (p) mk.bits_prev[w] = 0; // last reader
+        }
+    }
+    uint32_t m = (c | p) & 0x1F1F1F1Fu; // (the padding slots 5..7 of a row are never marked)
+    if (m) {
+        uint32_t at = atomicAdd(&n_queued, (uint32_t)__popc(m));
+        while (m) {
+            const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            queue[at++] = ((w * 32u + b) << 1) | ((c >> b) & 1u);
+        }
+    }
+    const uint32_t touched = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(c & 0x1F1F1F1Fu));
+    if ((threadIdx.x & 31u) == 0 && touched)
+        atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys, (unsigned long long)touched);
+    __syncthreads();
+    const uint32_t n = n_queued;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t item = queue[i], key = item >> 1;
+        if (key >= mk.n_keys) { // guard: no env can mark beyond the table
             guard_tripped(ctl);
-            mk.vals[i] = 0.f;
             continue;
         }
-        mk.vals[i] = td_value(q, mk.sinfo, key >> 3, __ldg(mk.sinfo + (key >> 3)), key & 7u, __ldg(q + key), alpha, discount,
-                              mk.n_keys / MDPP_Q_ROW);
+        float v = __ldcg(X + key);
+        if (item & 1u) {
+            const uint32_t s = key >> 3, i1 = __ldg(mk.sinfo + s);
+            const uint32_t s2 = td_successor(s, i1, key & 7u, n_states);
+            const uint32_t i2 = __ldg(mk.sinfo + s2);
+            const float4 lo = __ldcg(reinterpret_cast<const float4 *>(X + (size_t)s2 * MDPP_Q_ROW));
+            const float4 hi = __ldcg(reinterpret_cast<const float4 *>(X + (size_t)s2 * MDPP_Q_ROW) + 1);
+            const float ns[MDPP_Q_ROW] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            v = td_update(i1, i2, ns, v, alpha, discount);
+            mark_visited(mk.visited, key);
+        }
+        Y[key] = v;
     }
-}
-
-// list mode, pass 2: write the values, clear the bitmap words (every set bit of a word is a listed key)
-__global__ void __launch_bounds__(kThreads)
-q_pull_list_apply_kernel(float *__restrict__ q, Marks mk, Control *ctl) {
-    pdl_wait();
-    pdl_launch_dependents();
-    const uint32_t n = min(*mk.count, mk.capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = mk.list[i];
-        if (key >= mk.n_keys) continue; // guard (counted by the compute pass)
-        q[key] = mk.vals[i];
-        mk.bits[key >> 5] = 0;
-        mark_visited(mk.visited, key);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n)
-        atomicAdd((unsigned long long *)&ctl->stats[0].touched_keys, (unsigned long long)n);
 }
 
 __global__ void __launch_bounds__(kThreads)

@@ -1116,4 +1116,126 @@ rollout_lean_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].reward_sum, (unsigned long long)cta_reward);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pure-exploration rounds of LARGE tables (scan mode, 3-5 cars): all cars of up to `rounds` rounds in one pass over
+// the batch.  While every env explores nothing an env does depends on the table, so the per-car sub-step kernels
+// (each a full pass over the records: 4 cars = 4 x 15 us at 2^20 envs) collapse into the lean step of the rollout
+// kernel -- cars unpacked in registers for the whole launch, tables in shared memory -- plus one fire-and-forget
+// atomic OR per agent-step into the touched bitmap of its sub-step (region r * NC + c).  The pulls of those
+// sub-steps follow in order (q_pull_scan_kernel).  The host launches this kernel only while its bound on the
+// episode counters keeps every env inside the epsilon = 1 segment for all `rounds` rounds.
+// ------------------------------------------------------------------------------------------------
+struct PureScanArgs {
+    uint4 *recs;
+    uint32_t n_envs, env_id_base;
+    uint32_t rounds;
+    uint64_t first_round;
+    const FastTabs *tabs;
+    uint32_t rank_stride, n_states;
+    uint32_t *bits0;       // bitmap of sub-step (0, 0); sub-step (r, c) = bits0 + (r * NC + c) * region_words
+    uint32_t region_words;
+    uint32_t l1_check;
+};
+
+template <int NC, int C>
+__device__ __forceinline__ void lean_mark_chain(const LeanTabs<NC> &S, const PureScanArgs &pa, uint32_t (&f)[NC],
+                                                const uint32_t (&w)[NC], uint32_t &steps, uint32_t &n_steps,
+                                                uint32_t *__restrict__ bits, Control *ctl) {
+    const uint32_t fc = f[C];
+    if (!(fc & 0x100u)) { // `if env.check_car_training(num): continue` (qlearning.py:216-217)
+        const LeanView v = lean_view<NC, C>(S, f, pa.rank_stride); // the encode's ghost side effects stay in f[]
+        uint32_t lm = v.lm;
+        if (v.sidx >= pa.n_states) { // guard: the encoded state is off the table -- the car does not act
+            guard_tripped(ctl);
+            lm = 0;
+        }
+        if (lm) {
+            // random.choice(legal) (qlearning.py:102): low 16 bits of the decision word scaled to the legal count
+            const uint32_t a = (S.nth[lm] >> (3u * (((w[C] & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
+            scan_mark(bits, v.sidx * MDPP_Q_ROW + a, pa.l1_check);
+            const uint32_t mv = S.next[C][fc & 0xFFu][a]; // successor + update_car
+            f[C] = (mv & 0x1FFu) | (fc & 0xE00u);
+            steps += 1;
+            n_steps += 1;
+        }
+    }
+    if constexpr (C + 1 < NC) lean_mark_chain<NC, C + 1>(S, pa, f, w, steps, n_steps, bits + pa.region_words, ctl);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kRolloutThreads, 4)
+q_rounds_pure_scan_kernel(DevCfg cfg, LearnArgs lp, PureScanArgs pa, Control *ctl) {
+    extern __shared__ uint4 smem_dyn[];
+    LeanTabs<NC> &S = *reinterpret_cast<LeanTabs<NC> *>(smem_dyn);
+    __shared__ CtaCounters cc;
+    pdl_launch_dependents(); // the pulls that follow wait for this grid to complete
+    stage_lean_tabs<NC, kRolloutThreads>(S, pa.tabs);
+    if (threadIdx.x == 0) cc = CtaCounters{0u, 0u, 0u, 0u, 0, 0u};
+    __syncthreads();
+    const uint32_t tiles = (pa.n_envs + 31u) >> 5;
+    const uint32_t t0 = (uint32_t)((uint64_t)tiles * blockIdx.x / gridDim.x);
+    const uint32_t t1 = (uint32_t)((uint64_t)tiles * (blockIdx.x + 1u) / gridDim.x);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    StepCounts cnt;
+    uint4 rec_next = make_uint4(0u, 0u, 0u, 0u); // the next tile's records are in flight during this tile's work
+    if (t0 + warp < t1 && (t0 + warp) * 32u + lane < pa.n_envs) rec_next = pa.recs[(t0 + warp) * 32u + lane];
+    for (uint32_t t = t0 + warp; t < t1; t += n_warps) {
+        const uint32_t e = t * 32u + lane;
+        uint4 rec = rec_next;
+        if (t + n_warps < t1 && (t + n_warps) * 32u + lane < pa.n_envs) rec_next = pa.recs[(t + n_warps) * 32u + lane];
+        uint32_t episode = rec.z & 0xFFFFu, steps = rec.z >> 16;
+        if (e >= pa.n_envs || (int32_t)episode >= lp.episodes) continue; // an env that used its episode budget is frozen
+        uint32_t f[NC];
+        {
+            const uint64_t cars = (uint64_t)rec.x | ((uint64_t)rec.y << 32);
+#pragma unroll
+            for (int i = 0; i < NC; i++) f[i] = (uint32_t)(cars >> (12 * i)) & 0xFFFu;
+        }
+        const uint32_t env = pa.env_id_base + e;
+        uint32_t *bits = pa.bits0;
+        for (uint32_t r = 0; r < pa.rounds; r++) {
+            const uint64_t round = pa.first_round + (uint64_t)r;
+            const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+            uint32_t w[NC];
+            w[0] = p.x;
+            if (NC > 1) w[NC > 1 ? 1 : 0] = p.y;
+            if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
+            if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
+            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, lp.seed, env).x;
+            lean_mark_chain<NC, 0>(S, pa, f, w, steps, cnt.steps, bits, ctl);
+            bits += (size_t)NC * pa.region_words;
+            steps = min(steps, 0xFFFFu);
+            // end of the round-robin round (qlearning.py:233): is_game_ended or the step cap -> next episode
+            uint32_t d = f[0];
+#pragma unroll
+            for (int i = 1; i < NC; i++) d &= f[i];
+            const bool finished = (d >> 8) & 1u;
+            const bool capped = !finished && cfg.step_cap > 0 && steps >= (uint32_t)cfg.step_cap;
+            if (finished || capped) {
+                cnt.episodes++;
+                cnt.capped += capped;
+                episode = episode + 1;
+                cnt.max_episode = max(cnt.max_episode, episode);
+                steps = 0;
+                rec.w &= ~0xFFu; // deadlock_count = 0 per episode (qlearning.py:331)
+                const uint32_t hb = heading_word(round, 2, lp.seed, env);
+#pragma unroll
+                for (int i = 0; i < NC; i++)
+                    f[i] = make_field(cfg.start_box18[i] * 4 + ((hb >> (2 * i)) & 3u), cfg.start_di[i], 0, 5);
+                if ((int32_t)episode >= lp.episodes) break; // budget used up: frozen from here on
+            }
+        }
+        uint64_t cars = 0;
+#pragma unroll
+        for (int i = 0; i < NC; i++) cars |= (uint64_t)f[i] << (12 * i);
+        rec.x = (uint32_t)cars;
+        rec.y = (uint32_t)(cars >> 32);
+        rec.z = (episode & 0xFFFFu) | (steps << 16);
+        pa.recs[e] = rec;
+    }
+    cnt.explore = cnt.steps; // every decision of this kernel explores
+    flush_counts<true>(cnt, cc, 0u, ctl);
+    pdl_wait();
+}
+
 } // namespace mdpp
