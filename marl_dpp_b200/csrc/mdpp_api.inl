@@ -157,6 +157,13 @@ struct mdpp_handle {
     cudaStream_t sync_stream;
     cudaEvent_t sync_fork, sync_join;
     bool sync_pending;      // an exchange is in flight: the caller's stream must wait for sync_join before the table is touched
+    // scan mode, pure-exploration rounds: the pulls of a group of rounds run on a stream of the handle's own, BESIDE the
+    // env pass of the next group on the caller's stream (q_pure_scan_rounds_launch)
+    bool scan_overlap;      // MDPP_SCAN_OVERLAP=0 keeps everything on the caller's stream
+    cudaStream_t pull_stream;
+    cudaEvent_t ev_env[2], ev_pull[2];
+    uint32_t ov_groups;     // groups launched since the streams last joined
+    bool pulls_pending;     // pulls are in flight on pull_stream: the caller's stream waits for ev_pull[(ov_groups - 1) & 1] first
 };
 
 using namespace mdpp;
@@ -348,6 +355,7 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
     h->multi_round = !(getenv("MDPP_MULTI_ROUND") && atoi(getenv("MDPP_MULTI_ROUND")) == 0);
     h->multi_pull = !(getenv("MDPP_MULTI_PULL") && atoi(getenv("MDPP_MULTI_PULL")) == 0);
     h->pure_scan = !(getenv("MDPP_PURE_SCAN") && atoi(getenv("MDPP_PURE_SCAN")) == 0);
+    h->scan_overlap = !(getenv("MDPP_SCAN_OVERLAP") && atoi(getenv("MDPP_SCAN_OVERLAP")) == 0);
     h->chain = false;
     h->smem_configured = 0;
     h->round_parity = 0;
@@ -402,6 +410,14 @@ int mdpp_create(const mdpp_config *cfg, int64_t n_envs, int64_t env_id_base, voi
 int mdpp_destroy(mdpp_handle *h) {
     if (h && h->stat_slots) cudaFreeHost(h->stat_slots);
     if (h && h->host_stats) cudaFreeHost(h->host_stats);
+    if (h && h->pull_stream) {
+        cudaStreamSynchronize(h->pull_stream);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(h->ev_env[i]);
+            cudaEventDestroy(h->ev_pull[i]);
+        }
+        cudaStreamDestroy(h->pull_stream);
+    }
     if (h && h->sync_stream) {
         cudaStreamSynchronize(h->sync_stream);
         cudaEventDestroy(h->sync_fork);
@@ -1002,24 +1018,66 @@ static int pure_scan_rounds_fit(const mdpp_handle *h, const mdpp_learner *lp, in
 }
 extern "C++" {
 template <int NC>
-static int pure_scan_kernel_launch(mdpp_handle *h, const mdpp_learner *lp, const PureScanArgs &pa, cudaStream_t s) {
-    const size_t smem = sizeof(LeanTabs<NC>);
+static int pure_scan_kernel_launch(mdpp_handle *h, const mdpp_learner *lp, const PureScanArgs &pa, cudaStream_t s, bool beside) {
+    // beside: pulls run next to this kernel.  Four of its CTAs (256 threads x 64 registers each) would take every
+    // register of an SM for the whole launch, so the shared-memory request is padded until only three fit, which
+    // leaves registers and shared memory for two CTAs of q_pull_scan_kernel per SM.
+    const size_t pad = (size_t)58 * 1024, smem = beside ? std::max(sizeof(LeanTabs<NC>), pad) : sizeof(LeanTabs<NC>);
     if (!((h->smem_configured >> 31) & 1u)) {
-        MDPP_CUDA(cudaFuncSetAttribute(q_rounds_pure_scan_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MDPP_CUDA(cudaFuncSetAttribute(q_rounds_pure_scan_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)std::max(sizeof(LeanTabs<NC>), pad)));
+        // the largest shared-memory carve-out for both kernels: the pull's CTAs must fit the SM configuration the
+        // env kernel runs under (an SM does not change its carve-out while CTAs are resident)
+        MDPP_CUDA(cudaFuncSetAttribute(q_rounds_pure_scan_kernel<NC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+        MDPP_CUDA(cudaFuncSetAttribute(q_pull_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
         h->smem_configured |= 1u << 31;
     }
     const int64_t tiles = (h->n_envs + 31) / 32;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * 4, (tiles + 7) / 8));
+    const int per_sm = (beside || sizeof(LeanTabs<NC>) > pad) ? 3 : 4;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * per_sm, (tiles + 7) / 8));
     LearnLaunch ll(h, grid, s, kRolloutThreads, smem);
     MDPP_LAUNCH(h, cudaLaunchKernelEx(&ll.cfg, q_rounds_pure_scan_kernel<NC>, h->dev, *lp, pa, control_of(h)));
     h->chain = true;
     return MDPP_OK;
 }
 } // extern "C++"
+// The caller's stream waits for the pulls in flight on the handle's pull stream (no-op when there are none).
+static int overlap_join(mdpp_handle *h, cudaStream_t s) {
+    if (!h->pulls_pending) return MDPP_OK;
+    MDPP_CUDA(cudaStreamWaitEvent(s, h->ev_pull[(h->ov_groups - 1u) & 1u], 0));
+    h->pulls_pending = false;
+    h->ov_groups = 0;
+    h->chain = false;
+    return MDPP_OK;
+}
 static int q_pure_scan_rounds_launch(mdpp_handle *h, float *q, float *&cur, float *&alt, const mdpp_learner *lp, uint64_t round,
                                      int n, cudaStream_t s) {
     const int nc = h->cfg.n_cars;
     if (int rc = scan_begin(h, q, cur, alt, s)) return rc; // (mid-size tables after a dense pull: one copy)
+    // While every env explores, the env pass of a group of rounds reads no table: the pulls of group g run on a stream
+    // of the handle's own BESIDE the env pass of group g + 1.  Env pass g marks bank g % 3; pulls g read it, and clear
+    // the last bitmap of bank (g - 1) % 3 first; env pass g + 1 marks bank (g + 1) % 3, last read by the pulls of group
+    // g - 2 -- which env pass g + 1 therefore waits for (ev_pull), as pulls g wait for env pass g (ev_env).
+    const bool beside = h->scan_overlap && h->sync_world <= 1;
+    cudaStream_t ps = s;
+    uint32_t g = 0;
+    if (beside) {
+        if (!h->pull_stream) {
+            int lo = 0, hi = 0;
+            MDPP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            MDPP_CUDA(cudaStreamCreateWithPriority(&h->pull_stream, cudaStreamNonBlocking, hi)); // its CTAs first when an SM has room
+            for (int i = 0; i < 2; i++) {
+                MDPP_CUDA(cudaEventCreateWithFlags(&h->ev_env[i], cudaEventDisableTiming));
+                MDPP_CUDA(cudaEventCreateWithFlags(&h->ev_pull[i], cudaEventDisableTiming));
+            }
+        }
+        ps = h->pull_stream;
+        g = h->ov_groups++;
+        if (g >= 2) MDPP_CUDA(cudaStreamWaitEvent(s, h->ev_pull[g & 1u], 0)); // the pulls of group g - 2
+        h->chain = false; // plain stream order behind the previous env pass (whose records this one reads)
+    }
     const uint32_t bank = h->scan_bank;
     h->scan_bank = (h->scan_bank + 1u) % 3u;
     h->ep_bound += n;
@@ -1038,19 +1096,29 @@ static int q_pure_scan_rounds_launch(mdpp_handle *h, float *q, float *&cur, floa
     pa.l1_check = mk.l1_check;
     int rc;
     switch (nc) { // (the env pass touches records and marks only: an exchange in flight need not be joined first)
-    case 1: rc = pure_scan_kernel_launch<1>(h, lp, pa, s); break;
-    case 2: rc = pure_scan_kernel_launch<2>(h, lp, pa, s); break;
-    case 3: rc = pure_scan_kernel_launch<3>(h, lp, pa, s); break;
-    case 4: rc = pure_scan_kernel_launch<4>(h, lp, pa, s); break;
-    default: rc = pure_scan_kernel_launch<5>(h, lp, pa, s); break;
+    case 1: rc = pure_scan_kernel_launch<1>(h, lp, pa, s, beside); break;
+    case 2: rc = pure_scan_kernel_launch<2>(h, lp, pa, s, beside); break;
+    case 3: rc = pure_scan_kernel_launch<3>(h, lp, pa, s, beside); break;
+    case 4: rc = pure_scan_kernel_launch<4>(h, lp, pa, s, beside); break;
+    default: rc = pure_scan_kernel_launch<5>(h, lp, pa, s, beside); break;
     }
     if (rc) return rc;
+    if (beside) {
+        MDPP_CUDA(cudaEventRecord(h->ev_env[g & 1u], s));
+        MDPP_CUDA(cudaStreamWaitEvent(ps, h->ev_env[g & 1u], 0));
+        h->chain = false; // the first pull of the group follows an event wait
+    }
     for (int i = 0; i < n * nc; i++) {
         mk.bits = scan_region(h, bank, (uint32_t)i);
         mk.bits_prev = h->scan_stale;
-        if ((rc = sync_join(h, s))) return rc;
-        if ((rc = q_scan_pull_launch(h, cur, alt, lp, s, mk))) return rc;
+        if ((rc = sync_join(h, ps))) return rc;
+        if ((rc = q_scan_pull_launch(h, cur, alt, lp, ps, mk))) return rc;
         std::swap(cur, alt);
+    }
+    if (beside) {
+        MDPP_CUDA(cudaEventRecord(h->ev_pull[g & 1u], ps));
+        h->pulls_pending = true;
+        h->chain = false;
     }
     return MDPP_OK;
 }
@@ -1390,6 +1458,7 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
                 continue;
             }
         }
+        if (int rc = overlap_join(h, s)) return rc; // whatever follows reads the table or the marks
         if (h->cv.dense && h->scan_stale) // mid-size tables leaving the scan mode: the dense pulls know nothing of its bitmaps
             if (int rc = scan_settle(h, q, cur, alt, s)) return rc;
         if (fused) { // training fast path: a whole round per launch (q_round.cuh), several while every env explores
@@ -1428,8 +1497,8 @@ int mdpp_q_train_rounds(mdpp_handle *h, float *q, const mdpp_learner *lp, uint64
             std::swap(cur, alt);
         }
     }
-    int rc = MDPP_OK;
-    if (h->scan_stale) rc = scan_settle(h, q, cur, alt, s); // both copies complete: the caller's table is current
+    int rc = overlap_join(h, s);
+    if (!rc && h->scan_stale) rc = scan_settle(h, q, cur, alt, s); // both copies complete: the caller's table is current
     else if (cur != q) rc = q_copy_launch(h, cur, q, s); // odd number of sub-steps: bring the table home
     if (!rc) rc = sync_join(h, s); // (a frozen learner has no pull that would have joined)
     h->chain = false;

@@ -552,15 +552,16 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
 // destination are neighbours, and a popular configuration marks most of their 5 actions), and a thread that walked
 // the bits of its own words one dependent load chain after the other made the first version of this kernel 60 us
 // long for 20 k keys.  Each thread takes one word of each bitmap, the CTA queues the set bits in shared memory, and
-// the queue is processed one key per thread, every load chain of a pass in flight at once.  (Measured and dropped:
-// persistent CTAs walking four words per thread with a batched queue -- contiguous ranges 82 us per 4-car round
-// against 62, round-robin 32-word groups 72: fewer CTAs in flight, the same per-key latency chain.)
+// the queue is processed one key per thread, every load chain of a pass in flight at once; most CTAs find nothing
+// and leave at once.  (Measured and dropped, 4-car rounds at 2^20 envs: persistent CTAs walking four words per
+// thread with a batched queue -- contiguous ranges 82 us per round against 62, 32-word groups or 256-word chunks
+// dealt out round-robin 72-73: the same per-key latency chain with fewer CTAs in flight.)
 // The table is read past L1 (ld.global.cg): these pulls may run BESIDE a long env kernel on the same SM
 // (mdpp_api.inl, q_pure_scan_rounds_launch), where a line cached by the pull before last must not be trusted.
 constexpr uint32_t kScanQueue = kThreads * 4 * MDPP_N_ACT; // a word covers 4 states x 5 actions
 __global__ void __launch_bounds__(kThreads)
 q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk, float alpha, float discount, Control *ctl) {
-    __shared__ uint32_t queue[kScanQueue]; // key << 1 | marked in this sub-step
+    __shared__ uint16_t queue[kScanQueue]; // (key - first key of the CTA) << 1 | marked in this sub-step  (10 KB)
     __shared__ uint32_t n_queued;
     if (threadIdx.x == 0) n_queued = 0;
     pdl_wait();              // the env kernel that set the marks (and, by the chain rule, the previous pull) has completed
@@ -582,7 +583,7 @@ q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk,
         while (m) {
             const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
             m &= m - 1u;
-            queue[at++] = ((w * 32u + b) << 1) | ((c >> b) & 1u);
+            queue[at++] = (uint16_t)(((threadIdx.x * 32u + b) << 1) | ((c >> b) & 1u));
         }
     }
     const uint32_t touched = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(c & 0x1F1F1F1Fu));
@@ -591,7 +592,7 @@ q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk,
     __syncthreads();
     const uint32_t n = n_queued;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t item = queue[i], key = item >> 1;
+        const uint32_t item = queue[i], key = blockIdx.x * (kThreads * 32u) + (item >> 1);
         if (key >= mk.n_keys) { // guard: no env can mark beyond the table
             guard_tripped(ctl);
             continue;

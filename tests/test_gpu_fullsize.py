@@ -130,7 +130,9 @@ def test_fullsize_greedy_rounds_bit_exact(variant):
 
 
 def test_fullsize_four_car_learner_bit_exact():
-    """Max agents at full size: 4 cars, 1.65 M-state table (2^20 envs), 3 rounds through mdpp_q_train_rounds."""
+    """Max agents at full size: 4 cars, 1.65 M-state table (2^20 envs), 8 rounds through mdpp_q_train_rounds: scan
+    mode, every env exploring -- groups of two rounds per env pass, the pulls of a group on the handle's own stream
+    beside the env pass of the next (7 rounds: 2 + 2 + 2 + 1), then a single round in a call of its own."""
     m, BatchedEnv, BatchedQLearner, orc = _mods()
     boxes, idx = ["D2", "D6", "D4", "D8"], [0, 0, 0, 0]
     choose = [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]]
@@ -138,13 +140,13 @@ def test_fullsize_four_car_learner_bit_exact():
     sc = m.Scenario(m.layout_3[2], boxes, idx, choose, bad_states_text=bad, step_cap=300)
     env = BatchedEnv(sc, N_FULL, seed=41)
     lr = BatchedQLearner(env, episodes=5000, seed=41)
-    lr.train_rounds(2)
+    lr.train_rounds(7)
     lr.train_rounds(1)
     ob = orc.Batch(orc.Config(m.layout_3[2]), N_FULL, boxes, idx, choose, bad, 300)
     ob.reset(seed=41)
     oq = orc.QTable(f32=True)
     olp = orc.learner(5000, seed=41)
-    for r in range(3):
+    for r in range(8):
         ob.q_round(oq, olp, r)
     _assert_table_equal(lr, sc, oq)
     _assert_records_equal(env, ob)

@@ -36,7 +36,7 @@ def _mods():
     return m, BatchedEnv, BatchedQLearner, orc
 
 
-def _make(case, seed, pure_scan=True):
+def _make(case, seed, pure_scan=True, overlap=True):
     m, BatchedEnv, BatchedQLearner, orc = _mods()
     name, boxes, idx, choose, force, n, episodes, cap = case
     badtxt = bad_states_text(2)
@@ -45,11 +45,14 @@ def _make(case, seed, pure_scan=True):
         os.environ["MDPP_DENSE"] = "0"
     if not pure_scan:
         os.environ["MDPP_PURE_SCAN"] = "0"
+    if not overlap:
+        os.environ["MDPP_SCAN_OVERLAP"] = "0"
     try:
         env = BatchedEnv(sc, n, seed=seed)
     finally:
         os.environ.pop("MDPP_DENSE", None)
         os.environ.pop("MDPP_PURE_SCAN", None)
+        os.environ.pop("MDPP_SCAN_OVERLAP", None)
     lr = BatchedQLearner(env, episodes=episodes, seed=seed)
     ob = orc.Batch(orc.Config(m.layout_3[2]), n, boxes, idx, choose, badtxt, cap)
     ob.reset(seed=seed)
@@ -98,11 +101,13 @@ def test_scan_mode_rounds_match_oracle(case):
 
 
 def test_scan_mode_grouping_and_fused_pass_do_not_change_the_result():
-    """The same 4-car run as one call, as single-round calls, and with the fused pass switched off."""
+    """The same 4-car run as one call, as single-round calls, with the fused pass switched off, and with the pulls on
+    the caller's stream instead of beside the next env pass."""
     case = [c for c in CASES if c[0] == "b2_4car"][0]
     tables, records = [], []
-    for pure_scan, groups in ((True, [24]), (True, [1] * 24), (False, [24]), (True, [3, 8, 2, 11])):
-        sc, env, lr, ob, oq, olp, orc = _make(case, seed=4, pure_scan=pure_scan)
+    for pure_scan, overlap, groups in ((True, True, [24]), (True, True, [1] * 24), (False, True, [24]),
+                                       (True, True, [3, 8, 2, 11]), (True, False, [24])):
+        sc, env, lr, ob, oq, olp, orc = _make(case, seed=4, pure_scan=pure_scan, overlap=overlap)
         for k in groups:
             lr.train_rounds(k)
         tables.append(lr.q.cpu().numpy().copy())
