@@ -597,6 +597,40 @@ def main():
                                         "episodes": sf["episodes_done"], "value": sf["agent_steps"] / dt, "unit": UNIT,
                                         "note": "2^20 envs x 5000 episodes per env, every epsilon segment, host wall clock"}
             del lrf, envf
+        # the learner on larger tables ("max agents per layout": 3, 4, 5 cars; 126 540 / 1.65 M / 16.5 M states): scan mode
+        # -- global touched bitmaps + a mirror table, one scanning pull per sub-step, all cars of several pure-exploration
+        # rounds in one env pass with the pulls beside the next pass.  Rolled to the stationary mix first.
+        for kc, (bx, ix, ch) in (
+                (3, (["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]])),
+                (4, (["D2", "D6", "D4", "D8"], [0, 0, 0, 0], [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]])),
+                (5, (["D1", "D2", "D3", "D5", "D7"], [0, 1, 0, 1, 0], [[0, 1, 0], [2, 1, 0], [1, 0, 0], [2, 2, 0], [3, 4, 0]]))):
+            sck = m.Scenario(m.layout_3[BLOCK], bx, ix, ch, bad_states_text=bad_text(), step_cap=STEP_CAP)
+            envk = BatchedEnv(sck, n, device=dev, seed=3)
+            lrk = BatchedQLearner(envk, episodes=EPISODES, seed=3)
+            lrk.train_rounds(args.preroll // 2)
+            entry = {"states": sck.n_states, "algorithmic_bytes_per_step": FUSED_Q_BYTES_PER_STEP(kc)}
+            for tag, rounds_k in (("pure_exploration", 64), ("epsilon_0.5", 32)):
+                if tag == "epsilon_0.5":
+                    for i in range(6):
+                        lrk.params.eps_q16[i] = 32768
+                    lrk.train_rounds(8)
+                torch.cuda.synchronize()
+                envk.stats(reset=True)
+                a.record()
+                for _ in range(rounds_k // 8):
+                    lrk.train_rounds(8)
+                b.record()
+                torch.cuda.synchronize()
+                sk = envk.stats(reset=True)
+                ms = a.elapsed_time(b)
+                v = sk["agent_steps"] / (ms * 1e-3)
+                entry[tag] = {"value": v, "unit": UNIT, "us_per_round": ms / rounds_k * 1e3,
+                              "active_fraction": sk["agent_steps"] / float(rounds_k * n * kc),
+                              "touched_keys_per_substep": sk["touched_keys"] / float(rounds_k * kc),
+                              "frac_of_hbm_roofline": FUSED_Q_BYTES_PER_STEP(kc) * v / 1e9 / measured_peak()[0]}
+            assert envk.stats()["internal_errors"] == 0
+            aux["qlearning_%dcar_1Mi_envs" % kc] = entry
+            del lrk, envk
         # random-policy rollouts (BASELINE config 3).  Like the learner, every batch is first rolled (untimed) to its
         # stationary mix of active and finished cars -- a round costs the same whether or not a car still moves --
         # and the active fraction of the timed rounds is printed next to the rate.
