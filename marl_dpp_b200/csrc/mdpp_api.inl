@@ -29,7 +29,7 @@ static int fail(int code, const char *fmt, ...) {
 
 // marks of the dense modes are indexed by the compact key  state * 5 + action  (n_marks = n_states * 5)
 constexpr size_t kMaxByteMapMarks = 200 * 1024;   // shared-memory BYTE map of a persistent env CTA
-constexpr size_t kMaxDenseMarks = 8 * 200 * 1024; // shared-memory BIT map (atomic OR) up to here; list mode beyond
+constexpr size_t kMaxDenseMarks = 8 * 200 * 1024; // shared-memory BIT map (atomic OR) up to here; scan mode beyond
 constexpr uint32_t kMaxEnvCtas = 160;             // per-CTA bitmap slices per region: sub-step kernels, one CTA per SM
 constexpr uint32_t kMaxRoundCtas = 320;           // ... fused round kernels, up to two CTAs per SM (byte-map tables only)
 constexpr int kMaxPureRounds = 8;                 // pure-exploration rounds per q_rounds_pure_kernel launch
@@ -607,7 +607,8 @@ static Marks marks_of(mdpp_handle *h) {
     }
     if (h->cv.scan) {
         m.scan_words = h->cv.scan_words;
-        m.l1_check = keys / 8 <= ((size_t)4 << 20) ? 1u : 0u;
+        m.l1_check = 1u;
+        if (const char *env = getenv("MDPP_L1_CHECK")) m.l1_check = atoi(env) != 0 ? 1u : 0u; // A/B runs
     }
     m.visited = (uint32_t *)(h->ws + h->cv.visited);
     m.sinfo = (const uint32_t *)(h->ws + h->cv.sinfo);
@@ -698,7 +699,7 @@ static int q_env_launch(mdpp_handle *h, const float *q, const mdpp_learner *lp, 
     const bool bitmap = (size_t)mk.n_marks > kMaxByteMapMarks;
     const size_t map_bytes = bitmap ? (size_t)mk.words_per_cta * 4 : (((size_t)mk.n_marks + 15) / 16) * 16;
     const size_t tab_bytes = (step_tabs_bytes(h->cfg.n_cars) + 15) & ~(size_t)15;
-    const size_t smem_bytes = h->cv.dense ? tab_bytes + map_bytes : 0; // list mode reads the tables in place
+    const size_t smem_bytes = h->cv.dense ? tab_bytes + map_bytes : 0; // scan mode reads the tables in place
     LearnLaunch ll = h->cv.dense ? LearnLaunch(h, env_ctas(h), s, kEnvSmemThreads, smem_bytes)
                                  : LearnLaunch(h, grid_for(h->n_envs), s);
     ll.cfg.attrs = &ll.attr; // the struct was copied: re-point at this copy's attribute

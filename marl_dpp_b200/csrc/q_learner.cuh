@@ -331,8 +331,10 @@ __device__ __forceinline__ void scan_mark(uint32_t *__restrict__ bits, uint32_t 
     // Check through L1 first: atomics on a hot bitmap word are what L2 serialises (ncu, 4 cars: 80 us with 1.3 M
     // atomic sectors for the car slot whose envs share states, 21 us with 0.4 M for the one whose envs are spread).
     // L1 is not coherent, but the word can only be stale towards "clear" -- bits are set during this launch and were
-    // cleared by a pull that completed before it -- and a stale clear bit just costs the atomic.  Only for
-    // bitmaps of a few MB: on the 5-car table (16 MB bitmap, 1e5 keys per sub-step) the extra load misses.
+    // cleared by a pull that completed before it -- and a stale clear bit just costs the atomic.  Without the
+    // test (MDPP_L1_CHECK=0): 4 cars 60 -> 86 us per pure-exploration round, 101 -> 322 at epsilon 0.5; round 1 had
+    // switched it off for the 16 MB bitmaps of 5 cars ("the extra load misses"), which with these kernels costs a
+    // factor of two (epsilon 0.5: 468 against 237 us per round).
     // The result of the atomic is not used: a reduction (RED), nothing for the lane to wait for.
     const uint32_t bit = 1u << (key & 31u);
     uint32_t *w = bits + (key >> 5);

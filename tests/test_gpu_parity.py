@@ -224,10 +224,10 @@ QBATCH = [
     ("b2_2car_bad", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 400, 512, 40, 300),
     ("b0_1car", 0, ["U4"], [1], [[0, 0, 0]], False, 0, 256, 30, 200),
     ("b2_3car_bad", 2, ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 300, 384, 30, 150),
-    # 1.65 M states: touched bitmap + list + two-pass pull instead of the dense ping-pong
+    # 1.65 M states: scan mode (global touched bitmaps + mirror table + scanning pull) instead of the dense ping-pong
     ("b2_4car_bad_list", 2, ["D2", "D6", "D4", "D8"], [0, 0, 0, 0], [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]],
      True, 300, 320, 20, 80),
-    # the same small table forced through the list path
+    # the same small table forced through the scan path (global touched bitmaps + mirror table + scanning pull)
     ("b2_2car_bad_forced_list", 2, ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 400, 512, 40, 120),
 ]
 
