@@ -28,3 +28,12 @@ def bad_states_text(block):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def q_close(got, want):
+    """float32 table entry against the reference's float64 value (north star: 1e-5 relative).  Purely relative for
+    |value| >= 1.  The few entries below 1 in magnitude (16 of 3 230 in the recorded 2-car run, down to 0.017) are
+    differences of terms of magnitude >= 10 (reward -10 / +10 010, discount 0.15): float32 leaves them an ABSOLUTE
+    error of ~1e-6 whatever their size (2 of them are 3e-5 off relatively), so they are held to 2e-6 absolute."""
+    got, want = float(got), float(want)
+    return abs(got - want) <= (1e-5 * abs(want) if abs(want) >= 1.0 else 2e-6)

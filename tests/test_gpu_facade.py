@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import bad_states_text, load_golden
+from conftest import bad_states_text, load_golden, q_close
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -222,7 +222,7 @@ def test_rl_plugin_reproduces_reference_run_from_the_same_seed(scratch, name):
     updated = set(want_trace)
     assert set(rl.qvals) == updated
     for k, v in rl.qvals.items():
-        assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
+        assert q_close(v, want[k]), k
 
 
 @pytest.mark.parametrize("name", ["qrand_b2_2car", "qrand_b2_3car_bad"])
@@ -250,7 +250,7 @@ def test_rl_plugin_reproduces_reference_random_order_run(scratch, name):
     want = {(s, a): float(v) for s, a, v in g["qvals"]}
     assert set(rl.qvals) == {(s, a) for _, s, a in want_trace}
     for k, v in rl.qvals.items():
-        assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
+        assert q_close(v, want[k]), k
 
 
 def test_rl_plugin_random_order_batched(scratch):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, bad_states_text, load_golden
+from conftest import GOLDEN, bad_states_text, load_golden, q_close
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -207,7 +207,7 @@ def test_reference_qlearning_runs(name):
         got = q[sc.encode(s), A5.index(a)]
         assert got == np.float32(v32), (s, a)
         want = ref64[(s, a)]
-        assert abs(float(got) - want) <= 1e-5 * max(abs(want), 1.0), (s, a, got, want)
+        assert q_close(float(got), want), (s, a, got, want)
         n_checked += 1
     assert n_checked == len(ref64)
     # keys the CUDA path marks as updated == keys the reference updated (nonzero or not)

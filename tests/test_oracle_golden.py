@@ -4,7 +4,7 @@ import os
 
 import pytest
 
-from conftest import GOLDEN, bad_states_text, load_golden
+from conftest import GOLDEN, bad_states_text, load_golden, q_close
 from oracle import oracle as orc
 
 TRAJ = sorted(os.path.basename(p)[:-8] for p in glob.glob(os.path.join(GOLDEN, "traj_*.json.gz")))
@@ -206,7 +206,7 @@ def test_batch_oracle_random_order_reproduces_reference_run(name):
             assert A5[out["action"][0]] == action
             assert out["reward"][0] == reward
             got = q.get(orc.state_from_str(state), orc.ACTIONS.index(action))
-            assert abs(got - float(qafter)) <= 1e-5 * max(abs(float(qafter)), 1.0)
+            assert q_close(got, float(qafter))
         assert next(it, None) is None
     assert ob.stats()["episodes_done"] == len(g["log"])
     want = {(s, a): float(v) for s, a, v in g["qvals"]}
@@ -214,7 +214,7 @@ def test_batch_oracle_random_order_reproduces_reference_run(name):
     # the reference's Counter also holds the keys it only read (0.0); the batch table the updated ones
     assert set(got) == {(s[1], s[3]) for ep in g["log"] for s in ep["steps"]}
     for k, v in want.items():
-        assert abs(got.get(k, 0.0) - v) <= 1e-5 * max(abs(v), 1.0), k
+        assert q_close(got.get(k, 0.0), v), k
 
 
 def test_known_answers():
@@ -304,7 +304,7 @@ def test_float32_oracle_tracks_float64_reference_within_1e5():
     got = {(s, a): v for s, a, v in q.items()}
     assert set(got) <= set(want)
     for k, v in got.items():
-        assert abs(v - want[k]) <= 1e-5 * max(abs(want[k]), 1.0), k
+        assert q_close(v, want[k]), k
 
 
 BATCH_CLAIM = [
