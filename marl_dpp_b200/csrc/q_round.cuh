@@ -1137,11 +1137,23 @@ struct PureScanArgs {
     uint32_t l1_check;
 };
 
+// The mark of an agent-step is split in two.  Its bitmap word is REQUESTED (through L1, scan_mark's test) as soon as
+// the key is known; it is tested, and the atomic issued, one car-step later -- ncu on the first form, which tested
+// the word where it was loaded, had a third of the kernel's stall samples on those four instructions
+// (profiles/sass_pure_scan4_r02.txt).  `pend_key` / `pend_val`: the key marked by the previous car-step of this env
+// (kNoKey: none) and its word; its bitmap is the region before this car-step's.
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+__device__ __forceinline__ void scan_mark_resolve(uint32_t *__restrict__ bits, uint32_t key, uint32_t val) {
+    const uint32_t bit = 1u << (key & 31u);
+    if (key != kNoKey && !(val & bit)) atomicOr(bits + (key >> 5), bit);
+}
 template <int NC, int C>
 __device__ __forceinline__ void lean_mark_chain(const LeanTabs<NC> &S, const PureScanArgs &pa, uint32_t (&f)[NC],
                                                 const uint32_t (&w)[NC], uint32_t &steps, uint32_t &n_steps,
-                                                uint32_t *__restrict__ bits, Control *ctl) {
+                                                uint32_t *__restrict__ bits, uint32_t &pend_key, uint32_t &pend_val,
+                                                Control *ctl) {
     const uint32_t fc = f[C];
+    uint32_t key = kNoKey, val = 0;
     if (!(fc & 0x100u)) { // `if env.check_car_training(num): continue` (qlearning.py:216-217)
         const LeanView v = lean_view<NC, C>(S, f, pa.rank_stride); // the encode's ghost side effects stay in f[]
         uint32_t lm = v.lm;
@@ -1152,14 +1164,19 @@ __device__ __forceinline__ void lean_mark_chain(const LeanTabs<NC> &S, const Pur
         if (lm) {
             // random.choice(legal) (qlearning.py:102): low 16 bits of the decision word scaled to the legal count
             const uint32_t a = (S.nth[lm] >> (3u * (((w[C] & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
-            scan_mark(bits, v.sidx * MDPP_Q_ROW + a, pa.l1_check);
+            key = v.sidx * MDPP_Q_ROW + a;
+            if (pa.l1_check) val = bits[key >> 5]; // requested now, tested a car-step later
             const uint32_t mv = S.next[C][fc & 0xFFu][a]; // successor + update_car
             f[C] = (mv & 0x1FFu) | (fc & 0xE00u);
             steps += 1;
             n_steps += 1;
         }
     }
-    if constexpr (C + 1 < NC) lean_mark_chain<NC, C + 1>(S, pa, f, w, steps, n_steps, bits + pa.region_words, ctl);
+    scan_mark_resolve(bits - pa.region_words, pend_key, pend_val); // the previous car-step's mark
+    pend_key = key;
+    pend_val = val;
+    if constexpr (C + 1 < NC)
+        lean_mark_chain<NC, C + 1>(S, pa, f, w, steps, n_steps, bits + pa.region_words, pend_key, pend_val, ctl);
 }
 
 template <int NC>
@@ -1193,6 +1210,7 @@ q_rounds_pure_scan_kernel(DevCfg cfg, LearnArgs lp, PureScanArgs pa, Control *ct
         }
         const uint32_t env = pa.env_id_base + e;
         uint32_t *bits = pa.bits0;
+        uint32_t pend_key = kNoKey, pend_val = 0;
         for (uint32_t r = 0; r < pa.rounds; r++) {
             const uint64_t round = pa.first_round + (uint64_t)r;
             const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
@@ -1202,7 +1220,7 @@ q_rounds_pure_scan_kernel(DevCfg cfg, LearnArgs lp, PureScanArgs pa, Control *ct
             if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
             if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
             if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, lp.seed, env).x;
-            lean_mark_chain<NC, 0>(S, pa, f, w, steps, cnt.steps, bits, ctl);
+            lean_mark_chain<NC, 0>(S, pa, f, w, steps, cnt.steps, bits, pend_key, pend_val, ctl);
             bits += (size_t)NC * pa.region_words;
             steps = min(steps, 0xFFFFu);
             // end of the round-robin round (qlearning.py:233): is_game_ended or the step cap -> next episode
@@ -1225,6 +1243,7 @@ q_rounds_pure_scan_kernel(DevCfg cfg, LearnArgs lp, PureScanArgs pa, Control *ct
                 if ((int32_t)episode >= lp.episodes) break; // budget used up: frozen from here on
             }
         }
+        scan_mark_resolve(bits - pa.region_words, pend_key, pend_val); // the last car-step's mark
         uint64_t cars = 0;
 #pragma unroll
         for (int i = 0; i < NC; i++) cars |= (uint64_t)f[i] << (12 * i);
