@@ -735,6 +735,15 @@ def main():
             # roofline of the search: per live state one bit set in the result and one in a frontier, per examined
             # predecessor one result-bit probe (4-byte sector reads in L2); reported as states and probes per second
             entry["bfs_live_states_per_s"] = live / (entry["bfs"]["ms"] * 1e-3)
+            nck = scn.n_cars
+            entry["roofline"] = {
+                "unit": "bit operations/s",
+                "bits_set_per_s": 2.0 * live / (entry["bfs"]["ms"] * 1e-3),
+                "probes_per_s_upper_bound": 5.0 * nck * live / (entry["bfs"]["ms"] * 1e-3),
+                "note": "algorithmic work of the backward search (SURVEY 8d): per live state one bit set in the result and "
+                        "one in a frontier, and at most 5 x n_cars candidate predecessors examined (one result-bit probe "
+                        "each); the search is bound by its " + str(entry["bfs"].get("levels")) + " grid barriers and "
+                        "scattered L2 probes, not by HBM (the 4-car bitmaps are 3.5 MB)"}
             entry["note"] = ("bfs = backward breadth-first search, one cooperative launch, host wall clock incl. the "
                              "scratch memset and the final 8-byte read-back; sweep = forward sweeps to the fixpoint")
             aux["dd_reachability_" + tag] = entry
