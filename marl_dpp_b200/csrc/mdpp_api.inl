@@ -43,7 +43,7 @@ constexpr int kMaxPureRounds = 8;                 // pure-exploration rounds per
 
 struct Carve {
     size_t tables, fast, rng, bad, recs, sinfo, qalt, marks, flags, gbits, bits, visited, control, barrier, stage, dl, total;
-    uint32_t scan_words;    // scan mode: words of one touched bitmap (a multiple of 4; bit = key = state * 8 + action)
+    uint32_t scan_words;    // scan mode: words of one touched bitmap (a multiple of 4; compact keys in bit planes, scan_slot)
     uint32_t scan_regions;  // ... bitmaps per bank: sub-step i of a launch marks region i of the launch's bank.  THREE banks in
                             // rotation: the pull of a sub-step clears the bitmap of the sub-step BEFORE it (its last reader)
                             // while the next env kernel, which may already run, marks into the third
@@ -92,7 +92,7 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     c.scan = !c.dense || marks > kMaxByteMapMarks;
     if (const char *env = getenv("MDPP_HYBRID")) c.scan = c.scan && (!c.dense || atoi(env) != 0);
     if (c.scan) {
-        c.scan_words = (uint32_t)(((keys + 31) / 32 + 3) & ~(size_t)3);
+        c.scan_words = (uint32_t)(((marks + 31) / 32 + 3) & ~(size_t)3);
         // pure-exploration rounds share a launch (q_rounds_pure_scan_kernel): as many rounds as fit 16 MB of bitmaps per bank
         const size_t per_round = (size_t)cfg.n_cars * c.scan_words * 4;
         const int rounds = (int)std::max<size_t>(1, std::min<size_t>((size_t)kMaxPureRounds, ((size_t)16 << 20) / per_round));
@@ -607,6 +607,7 @@ static Marks marks_of(mdpp_handle *h) {
     }
     if (h->cv.scan) {
         m.scan_words = h->cv.scan_words;
+        m.scan_magic = (uint32_t)(((uint64_t)1 << 32) / h->cv.scan_words) + 1u;
         m.l1_check = 1u;
         if (const char *env = getenv("MDPP_L1_CHECK")) m.l1_check = atoi(env) != 0 ? 1u : 0u; // A/B runs
     }
@@ -1093,6 +1094,7 @@ static int q_pure_scan_rounds_launch(mdpp_handle *h, float *q, float *&cur, floa
     pa.n_states = (uint32_t)h->cfg.n_states;
     pa.bits0 = scan_region(h, bank, 0);
     pa.region_words = h->cv.scan_words;
+    pa.scan_magic = (uint32_t)(((uint64_t)1 << 32) / h->cv.scan_words) + 1u;
     Marks mk = marks_of(h);
     pa.l1_check = mk.l1_check;
     int rc;

@@ -55,6 +55,7 @@ struct Marks {
     uint32_t *bits;      // scan: [n_keys / 32] touched bitmap of the current sub-step (bit = key = state * 8 + action)
     uint32_t *bits_prev; // scan: bitmap of the previous sub-step (keys where the pull's destination table is stale) or NULL
     uint32_t scan_words; // scan: words of one bitmap (a multiple of 4)
+    uint32_t scan_magic; // scan: floor(2^32 / scan_words) + 1 (division by scan_words, see scan_slot)
     uint32_t *visited;   // [n_states] bit a = (state, a) has been updated at least once (qvalue file writer)
     const uint32_t *sinfo; // [n_states] per-state info words
     uint32_t dense;
@@ -327,7 +328,22 @@ __device__ __forceinline__ void flush_counts(const StepCounts &c, CtaCounters &c
 // scan mode (large tables): one CTA per 256-env tile, one touched bitmap per sub-step in global memory.  The step
 // tables are read in place through L1 (a 256-env CTA cannot amortise staging 40 KB; a persistent variant with
 // staged tables measured 10-40 % slower when the atomic still returned a value).
-__device__ __forceinline__ void scan_mark(uint32_t *__restrict__ bits, uint32_t key, uint32_t l1_check) {
+// Where a key lives in a scan-mode bitmap: the compact key m = state * 5 + action in BIT PLANES -- word m % NW, bit
+// m / NW (NW = words of the bitmap).  Keys that are hot together (the 5 actions of a state, the 4 headings of a box, the
+// 36-72 states that share the others and the destination) are neighbours in m; with bit = m % 32 they shared a few
+// words, and atomics on one address serialise in L2.  Bit planes put neighbouring keys into neighbouring WORDS, and
+// spread a hot cluster over many CTAs of the scanning pull.  Returns bit << 27 | word (NW < 2^27).
+__device__ __forceinline__ uint32_t scan_slot(uint32_t key /* state * 8 + action */, uint32_t nw, uint32_t magic) {
+    const uint32_t m = (key >> 3) * MDPP_N_ACT + (key & 7u);
+    uint32_t b = __umulhi(m, magic); // m / nw, or one more
+    uint32_t w = m - b * nw;
+    if ((int32_t)w < 0) {
+        b -= 1u;
+        w += nw;
+    }
+    return (b << 27) | w;
+}
+__device__ __forceinline__ void scan_mark(uint32_t *__restrict__ bits, uint32_t key, uint32_t l1_check, uint32_t nw, uint32_t magic) {
     // Check through L1 first: atomics on a hot bitmap word are what L2 serialises (ncu, 4 cars: 80 us with 1.3 M
     // atomic sectors for the car slot whose envs share states, 21 us with 0.4 M for the one whose envs are spread).
     // L1 is not coherent, but the word can only be stale towards "clear" -- bits are set during this launch and were
@@ -336,8 +352,8 @@ __device__ __forceinline__ void scan_mark(uint32_t *__restrict__ bits, uint32_t 
     // switched it off for the 16 MB bitmaps of 5 cars ("the extra load misses"), which with these kernels costs a
     // factor of two (epsilon 0.5: 468 against 237 us per round).
     // The result of the atomic is not used: a reduction (RED), nothing for the lane to wait for.
-    const uint32_t bit = 1u << (key & 31u);
-    uint32_t *w = bits + (key >> 5);
+    const uint32_t slot = scan_slot(key, nw, magic), bit = 1u << (slot >> 27);
+    uint32_t *w = bits + (slot & 0x7FFFFFFu);
     if (!l1_check || !(*w & bit)) atomicOr(w, bit);
 }
 
@@ -355,7 +371,7 @@ q_env_kernel(DevCfg cfg, LearnArgs lp, EnvArgs ea, Marks mk, Control *ctl) {
     StepCounts cnt;
     uint32_t key = 0;
     if (e < ea.n_envs)
-        if (env_substep<NC, C, PLAIN>(S, cfg, lp, ea, e, ea.recs[e], key, cnt)) scan_mark(mk.bits, key, mk.l1_check);
+        if (env_substep<NC, C, PLAIN>(S, cfg, lp, ea, e, ea.recs[e], key, cnt)) scan_mark(mk.bits, key, mk.l1_check, mk.scan_words, mk.scan_magic);
     flush_counts<PLAIN>(cnt, cc, PLAIN ? 0u : lp.flags, ctl);
     // every kernel of the chain waits for its predecessor before it exits, so that "my predecessor has
     // completed" implies "everything before it has completed" (lanes that explored never waited above)
@@ -560,10 +576,10 @@ q_pull_dense_kernel(const float *__restrict__ qold, float *__restrict__ qnew, Ma
 // dealt out round-robin 72-73: the same per-key latency chain with fewer CTAs in flight.)
 // The table is read past L1 (ld.global.cg): these pulls may run BESIDE a long env kernel on the same SM
 // (mdpp_api.inl, q_pure_scan_rounds_launch), where a line cached by the pull before last must not be trusted.
-constexpr uint32_t kScanQueue = kThreads * 4 * MDPP_N_ACT; // a word covers 4 states x 5 actions
+constexpr uint32_t kScanQueue = kThreads * 32; // every bit of a CTA's words may be set
 __global__ void __launch_bounds__(kThreads)
 q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk, float alpha, float discount, Control *ctl) {
-    __shared__ uint16_t queue[kScanQueue]; // (key - first key of the CTA) << 1 | marked in this sub-step  (10 KB)
+    __shared__ uint16_t queue[kScanQueue]; // (thread << 5 | bit) << 1 | marked in this sub-step  (16 KB)
     __shared__ uint32_t n_queued;
     if (threadIdx.x == 0) n_queued = 0;
     pdl_wait();              // the env kernel that set the marks (and, by the chain rule, the previous pull) has completed
@@ -579,7 +595,7 @@ q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk,
             if (p) mk.bits_prev[w] = 0; // last reader
         }
     }
-    uint32_t m = (c | p) & 0x1F1F1F1Fu; // (the padding slots 5..7 of a row are never marked)
+    uint32_t m = c | p;
     if (m) {
         uint32_t at = atomicAdd(&n_queued, (uint32_t)__popc(m));
         while (m) {
@@ -588,17 +604,20 @@ q_pull_scan_kernel(const float *__restrict__ X, float *__restrict__ Y, Marks mk,
             queue[at++] = (uint16_t)(((threadIdx.x * 32u + b) << 1) | ((c >> b) & 1u));
         }
     }
-    const uint32_t touched = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(c & 0x1F1F1F1Fu));
+    const uint32_t touched = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(c));
     if ((threadIdx.x & 31u) == 0 && touched)
         atomicAdd((unsigned long long *)&ctl->stats[blockIdx.x & (kStatSlots - 1)].touched_keys, (unsigned long long)touched);
     __syncthreads();
     const uint32_t n = n_queued;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t item = queue[i], key = blockIdx.x * (kThreads * 32u) + (item >> 1);
-        if (key >= mk.n_keys) { // guard: no env can mark beyond the table
+        // bit b of word w is the compact key b * NW + w (scan_slot)
+        const uint32_t item = queue[i];
+        const uint32_t cm = ((item >> 1) & 31u) * mk.scan_words + blockIdx.x * kThreads + (item >> 6);
+        if (cm >= mk.n_marks) { // guard: no env can mark beyond the table
             guard_tripped(ctl);
             continue;
         }
+        const uint32_t key = (cm / MDPP_N_ACT) * MDPP_Q_ROW + cm % MDPP_N_ACT;
         float v = __ldcg(X + key);
         if (item & 1u) {
             const uint32_t s = key >> 3, i1 = __ldg(mk.sinfo + s);

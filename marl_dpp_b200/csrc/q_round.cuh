@@ -1134,18 +1134,19 @@ struct PureScanArgs {
     uint32_t rank_stride, n_states;
     uint32_t *bits0;       // bitmap of sub-step (0, 0); sub-step (r, c) = bits0 + (r * NC + c) * region_words
     uint32_t region_words;
+    uint32_t scan_magic;   // floor(2^32 / region_words) + 1 (scan_slot)
     uint32_t l1_check;
 };
 
 // The mark of an agent-step is split in two.  Its bitmap word is REQUESTED (through L1, scan_mark's test) as soon as
 // the key is known; it is tested, and the atomic issued, one car-step later -- ncu on the first form, which tested
 // the word where it was loaded, had a third of the kernel's stall samples on those four instructions
-// (profiles/sass_pure_scan4_r02.txt).  `pend_key` / `pend_val`: the key marked by the previous car-step of this env
-// (kNoKey: none) and its word; its bitmap is the region before this car-step's.
+// (profiles/sass_pure_scan4_r02.txt).  `pend_key` / `pend_val`: where the key marked by the previous car-step of this
+// env lives (scan_slot; kNoKey: none) and that word; its bitmap is the region before this car-step's.
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
-__device__ __forceinline__ void scan_mark_resolve(uint32_t *__restrict__ bits, uint32_t key, uint32_t val) {
-    const uint32_t bit = 1u << (key & 31u);
-    if (key != kNoKey && !(val & bit)) atomicOr(bits + (key >> 5), bit);
+__device__ __forceinline__ void scan_mark_resolve(uint32_t *__restrict__ bits, uint32_t slot /* scan_slot */, uint32_t val) {
+    const uint32_t bit = 1u << (slot >> 27);
+    if (slot != kNoKey && !(val & bit)) atomicOr(bits + (slot & 0x7FFFFFFu), bit);
 }
 template <int NC, int C>
 __device__ __forceinline__ void lean_mark_chain(const LeanTabs<NC> &S, const PureScanArgs &pa, uint32_t (&f)[NC],
@@ -1164,8 +1165,8 @@ __device__ __forceinline__ void lean_mark_chain(const LeanTabs<NC> &S, const Pur
         if (lm) {
             // random.choice(legal) (qlearning.py:102): low 16 bits of the decision word scaled to the legal count
             const uint32_t a = (S.nth[lm] >> (3u * (((w[C] & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16))) & 7u;
-            key = v.sidx * MDPP_Q_ROW + a;
-            if (pa.l1_check) val = bits[key >> 5]; // requested now, tested a car-step later
+            key = scan_slot(v.sidx * MDPP_Q_ROW + a, pa.region_words, pa.scan_magic);
+            if (pa.l1_check) val = bits[key & 0x7FFFFFFu]; // requested now, tested a car-step later
             const uint32_t mv = S.next[C][fc & 0xFFu][a]; // successor + update_car
             f[C] = (mv & 0x1FFu) | (fc & 0xE00u);
             steps += 1;
