@@ -172,7 +172,7 @@ int mdpp_query_transitions(mdpp_handle *h, int car_slot, int reward_kind, const 
 int mdpp_update_car(mdpp_handle *h, int car_slot, const uint8_t *nodes /*DEV [n_envs]*/, void *stream);
 
 /* ---- env: lockstep rollout under the uniform-random legal policy (reference eps = 1 behaviour,
- * src/algorithms/qlearning.py:99-102) with Philox4x32-10 and auto-reset.  `rounds` full
+ * src/algorithms/qlearning.py:99-102) with Philox4x32 (MDPP_PHILOX_ROUNDS = 7 rounds) and auto-reset.  `rounds` full
  * round-robin rounds (qlearning.py:211-233) per launch; outputs (optional) are SoA
  * [rounds][n_cars][n_envs]: action (MDPP_ACT_SKIP when the car did not move), reward, env-done
  * flag after the step, next-state id. */

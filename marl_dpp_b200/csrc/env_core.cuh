@@ -62,11 +62,18 @@ __device__ __forceinline__ void load_tables(SmemTables &sm, const uint32_t *src)
     __syncthreads();
 }
 
-// ---- Philox4x32-10 (Salmon et al. SC'11), counter-based: no per-env generator state -------------
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+// ---- Philox4x32 (Salmon et al. SC'11), counter-based: no per-env generator state -------------
+// MDPP_PHILOX_ROUNDS rounds: 7 by default -- the fewest with which Philox4x32 passes BigCrush in the authors' tests
+// (their default of 10 is a safety margin) -- because the generator is a fifth of the round kernels' instructions
+// (65 of 290 per 32-env tile and round at 10 rounds, profiles/ncu_pure_rounds_r02.txt).  The oracle is built with the
+// same constant (oracle/mdpp_oracle.c); both check the 7- and the 10-round Random123 known-answer vectors.
+#ifndef MDPP_PHILOX_ROUNDS
+#define MDPP_PHILOX_ROUNDS 7
+#endif
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
         uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
         c0 = h1 ^ c1 ^ k0;
@@ -78,15 +85,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     }
     return make_uint4(c0, c1, c2, c3);
 }
+__device__ __forceinline__ uint4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32<MDPP_PHILOX_ROUNDS>(c0, c1, c2, c3, k0, k1);
+}
 // RNG streams (ctr word 2): 0 = decision words of cars 0..3, 1 = car 4, 2 = headings drawn at the
 // end-of-round reset, 3 = headings of mdpp_reset.  ctr = (round_lo, round_hi, stream, 0), key = (seed, env id).
 __device__ __forceinline__ uint32_t decision_word(uint64_t round, int car, uint32_t seed, uint32_t env) {
-    uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), car >> 2, 0, seed, env);
+    uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), car >> 2, 0, seed, env);
     int w = car & 3;
     return w == 0 ? p.x : w == 1 ? p.y : w == 2 ? p.z : p.w;
 }
 __device__ __forceinline__ uint32_t heading_word(uint64_t round, uint32_t stream, uint32_t seed, uint32_t env) {
-    return philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), stream, 0, seed, env).x;
+    return philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), stream, 0, seed, env).x;
 }
 
 // ---- packed car fields -----------------------------------------------------------------------

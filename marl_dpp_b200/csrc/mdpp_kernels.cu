@@ -254,7 +254,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
         const uint32_t env = env_id_base + (uint32_t)e;
         for (int r = 0; r < rounds; r++) {
             const uint64_t round = first_round + (uint64_t)r;
-            uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
+            uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 uint32_t a = MDPP_ACT_SKIP, nidx = 0xFFFFFFFFu;
@@ -264,7 +264,7 @@ rollout_random_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint
                     uint32_t lm = legal_mask(v, v.pnode, tab);
                     if (lm) {
                         uint32_t w = c == 0 ? p.x : c == 1 ? p.y : c == 2 ? p.z : c == 3 ? p.w
-                                     : philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
+                                     : philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
                         // random.choice(legal) (qlearning.py:102): low 16 bits scaled to the legal count
                         a = nth_set_bit(lm, ((w & 0xFFFFu) * (uint32_t)__popc(lm)) >> 16);
                         uint32_t nn = next_node(v.pnode, a, tab);

@@ -145,7 +145,7 @@ __device__ __forceinline__ bool env_substep_car(const Tabs &S, const DevCfg &cfg
         word = any_word;
     } else if (C == 0 && ea.rng_mode == 1) { // one Philox block per env and round: word c belongs to car c
         if (live) {
-            const uint4 p = philox4x32_10((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 0, 0, lp.seed, env);
+            const uint4 p = philox4x32_r((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 0, 0, lp.seed, env);
             word = p.x;
             if (NC > 1) ea.rng_words[e] = p.y;
             if (NC > 2) ea.rng_words[(size_t)ea.n_envs + e] = p.z;
@@ -270,7 +270,7 @@ __device__ __forceinline__ bool env_substep(const Tabs &S, const DevCfg &cfg, co
                                             const EnvArgs &ea, int64_t e, uint4 rec, uint32_t &key, StepCounts &cnt) {
     if constexpr (!PLAIN && C == 0) {
         if (lp.flags & MDPP_LEARN_RANDOM_ORDER) {
-            const uint4 p = philox4x32_10((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 4u + ea.order_slot, 0, lp.seed,
+            const uint4 p = philox4x32_r((uint32_t)ea.round, (uint32_t)(ea.round >> 32), 4u + ea.order_slot, 0, lp.seed,
                                           ea.env_id_base + (uint32_t)e);
             uint32_t f = ea.forced ? ea.forced[e] : 0xFFu;
             uint32_t c = ((p.x >> 16) * (uint32_t)NC) >> 16;

@@ -234,7 +234,7 @@ q_round_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
             if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
             uint32_t w[NC];
             if (CSTART == 0) { // one Philox block per env and round: word c belongs to car c
-                const uint4 p = philox4x32_10((uint32_t)ra.round, (uint32_t)(ra.round >> 32), 0, 0, lp.seed, env);
+                const uint4 p = philox4x32_r((uint32_t)ra.round, (uint32_t)(ra.round >> 32), 0, 0, lp.seed, env);
                 w[0] = p.x;
                 if (NC > 1) w[NC - 1] = p.y;
             } else {
@@ -395,7 +395,7 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                 const uint32_t env = ra.env_id_base + e;
                 uint32_t eps16 = lp.eps_q16[0];
                 if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
-                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+                const uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
                 uint32_t key;
                 bool moved, explore;
                 int st = round_car_step<NC, 0>(S, cfg, ra.tabs, ra, cars, p.x, eps16, false, key, moved, explore);
@@ -665,7 +665,7 @@ __device__ __forceinline__ void mixed_env_pass(const RoundSmem<NC> &S, const Dev
             if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
             uint32_t word;
             if (C == 0) { // one Philox block per env and round: word c belongs to car c
-                const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+                const uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
                 word = p.x;
                 if (NC > 1) ra.rng_words[e] = p.y;
             } else {
@@ -926,13 +926,13 @@ rollout_fast_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
         const uint32_t env = env_id_base + e;
         for (int r = 0; r < rounds; r++) {
             const uint64_t round = first_round + (uint64_t)r;
-            const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
+            const uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
             uint32_t w[NC];
             w[0] = p.x;
             if (NC > 1) w[NC > 1 ? 1 : 0] = p.y;
             if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
             if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
-            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
+            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
             rollout_chain<NC, 0>(S, cfg, tabs, rank_stride, kind, cars, w, steps, cnt, rsum, out,
                                  (size_t)r * NC * (size_t)n_envs + e, (size_t)n_envs);
             // end of round: is_game_ended (src/env_gym.py:622-638) or the step cap -> next episode
@@ -1063,13 +1063,13 @@ rollout_lean_kernel(DevCfg cfg, uint4 *__restrict__ recs, uint32_t n_envs, uint3
         int32_t rtile = 0;
         for (int r = 0; r < rounds; r++) {
             const uint64_t round = first_round + (uint64_t)r;
-            const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
+            const uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, seed, env);
             uint32_t w[NC];
             w[0] = p.x;
             if (NC > 1) w[NC > 1 ? 1 : 0] = p.y;
             if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
             if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
-            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
+            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 1, 0, seed, env).x;
             int32_t rr = 0;
             RolloutOut o = out; // this env's slot of car 0 in round r
             const size_t off = (size_t)r * NC * (size_t)n_envs + e;
@@ -1214,13 +1214,13 @@ q_rounds_pure_scan_kernel(DevCfg cfg, LearnArgs lp, PureScanArgs pa, Control *ct
         uint32_t pend_key = kNoKey, pend_val = 0;
         for (uint32_t r = 0; r < pa.rounds; r++) {
             const uint64_t round = pa.first_round + (uint64_t)r;
-            const uint4 p = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
+            const uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
             uint32_t w[NC];
             w[0] = p.x;
             if (NC > 1) w[NC > 1 ? 1 : 0] = p.y;
             if (NC > 2) w[NC > 2 ? 2 : 0] = p.z;
             if (NC > 3) w[NC > 3 ? 3 : 0] = p.w;
-            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), 1, 0, lp.seed, env).x;
+            if (NC > 4) w[NC > 4 ? 4 : 0] = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 1, 0, lp.seed, env).x;
             lean_mark_chain<NC, 0>(S, pa, f, w, steps, cnt.steps, bits, pend_key, pend_val, ctl);
             bits += (size_t)NC * pa.region_words;
             steps = min(steps, 0xFFFFu);

@@ -669,10 +669,10 @@ double orc_epsilon(int episodes, int episode, int model) {
     return 0; /* Python returns None for other models */
 }
 
-/* Philox4x32-10, Salmon/Moraes/Dror/Shaw SC'11 (Random123 constants) */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* Philox4x32, Salmon/Moraes/Dror/Shaw SC'11 (Random123 constants), any round count */
+void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -682,6 +682,12 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+/* the generator of the batch semantics: the round count the CUDA library is built with (env_core.cuh) */
+#ifndef MDPP_PHILOX_ROUNDS
+#define MDPP_PHILOX_ROUNDS 7
+#endif
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc_philox4x32(ctr, key, out, MDPP_PHILOX_ROUNDS); }
+int orc_philox_rounds(void) { return MDPP_PHILOX_ROUNDS; }
 
 /* index-level access for the batched driver (mdpp_oracle_batch.c) */
 int64_t orc_q_index(orc_q *q, const orc_state *s, int action) {

@@ -96,8 +96,10 @@ void orc_convert(const orc_state *s, int total_cars, uint8_t *out);
 /* epsilon schedule (reference src/utils/utils.py:12-52) */
 double orc_epsilon(int episodes, int episode, int model);
 
-/* Philox4x32-10 (Salmon et al., SC'11; Random123 reference constants) */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Philox4x32 (Salmon et al., SC'11; Random123 reference constants); the batch semantics use MDPP_PHILOX_ROUNDS = 7 rounds */
+void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds);
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]); /* MDPP_PHILOX_ROUNDS rounds */
+int orc_philox_rounds(void);
 
 #ifdef __cplusplus
 }

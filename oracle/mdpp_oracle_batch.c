@@ -3,7 +3,7 @@
  *
  * Restates, on the CPU and one env at a time, the BATCH semantics the CUDA path defines
  * (DESIGN.md "Batch semantics"): N independent envs stepped in lockstep, car slot by car slot,
- * decisions drawn from Philox4x32-10 keyed (seed, env id) with counter (round, stream), per-env
+ * decisions drawn from Philox4x32-7 (MDPP_PHILOX_ROUNDS) keyed (seed, env id) with counter (round, stream), per-env
  * episode counters driving the reference's epsilon schedule, auto-reset at the end of a round,
  * and -- for the learner -- every env of a sub-step reading the Q table as it was when the
  * sub-step began, with each touched key receiving the value its contributing envs computed.  All
@@ -130,7 +130,7 @@ void orc_batch_stats(const orc_batch *b, uint64_t *out5) {
 
 static uint32_t philox_word(uint64_t round, uint32_t stream, uint32_t seed, uint32_t env, int word) {
     uint32_t ctr[4] = {(uint32_t)round, (uint32_t)(round >> 32), stream, 0}, key[2] = {seed, env}, out[4];
-    orc_philox4x32_10(ctr, key, out);
+    orc_philox4x32_r(ctr, key, out);
     return out[word];
 }
 /* decision word of car c in round r: cars 0..3 share one Philox block, car 4 uses the next stream */
@@ -343,7 +343,7 @@ static void *substep_worker(void *arg) {
         uint32_t blk[4] = {0, 0, 0, 0};
         if (any_order) {
             uint32_t ctr[4] = {(uint32_t)round, (uint32_t)(round >> 32), 4u + (uint32_t)slot, 0}, key[2] = {lp->seed, envid};
-            orc_philox4x32_10(ctr, key, blk);
+            orc_philox4x32_r(ctr, key, blk);
             c = (int)(((blk[0] >> 16) * (uint32_t)nc) >> 16);
             if ((f >> 4) != 0xF) c = f >> 4;
             f = (f & 0xF) == 0xF ? ACT_SKIP : (f & 0xF) == 0xE ? ACT_GREEDY : (f & 0xF);

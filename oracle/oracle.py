@@ -141,7 +141,8 @@ def lib():
         "orc_q_size": (C.c_int64, [P]),
         "orc_q_entry": (None, [P, C.c_int64, SP, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
         "orc_epsilon": (C.c_double, [C.c_int, C.c_int, C.c_int]),
-        "orc_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+        "orc_philox4x32": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]),
+        "orc_philox_rounds": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -164,12 +165,17 @@ def state_from_str(s):
     return st
 
 
-def philox(ctr, key):
+def philox(ctr, key, rounds=10):
+    """Philox4x32 with `rounds` rounds; philox_rounds() = the count the batch semantics are built with."""
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
     o = (C.c_uint32 * 4)()
-    lib().orc_philox4x32_10(c, k, o)
+    lib().orc_philox4x32(c, k, o, rounds)
     return list(o)
+
+
+def philox_rounds():
+    return lib().orc_philox_rounds()
 
 
 class Config:
