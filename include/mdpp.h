@@ -326,6 +326,12 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap /*DEV*/, i
  * function above.  For joint spaces below 2^32 states (mdpp_deadlock_scratch_bytes returns 0 otherwise); scratch:
  * caller-owned device memory of mdpp_deadlock_scratch_bytes(cfg) bytes, 16-byte aligned.  Synchronous;
  * *levels_out (host) receives the number of search levels. */
+/* One forward sweep over the joint states [first_state, first_state + n_range) only (first_state a multiple of 32):
+ * bits of other states are read, never written; *changed (device word, set to 1 when a bit was set, never cleared
+ * here).  The building block of the search sharded over GPUs: every rank sweeps its own word range of a
+ * replicated bitmap and the ranks exchange their ranges until no sweep changes anything.  Asynchronous. */
+int mdpp_deadlock_sweep_range(mdpp_handle *h, uint32_t *reach_bitmap /*DEV*/, int64_t first_state, int64_t n_range,
+                              uint32_t *changed /*DEV*/, void *stream);
 int64_t mdpp_deadlock_scratch_bytes(const mdpp_config *cfg);
 int mdpp_deadlock_reachability_bfs(mdpp_handle *h, uint32_t *reach_bitmap /*DEV*/, void *scratch /*DEV*/,
                                    int64_t scratch_bytes, int32_t *levels_out, void *stream);

@@ -22,7 +22,7 @@ EXPORTS = ["mdpp_workspace_bytes", "mdpp_create", "mdpp_destroy", "mdpp_last_err
            "mdpp_q_train_rounds_host", "mdpp_q_profile_env_kernel", "mdpp_q_profile_env_rounds", "mdpp_fast_tables", "mdpp_decode_state", "mdpp_encode_state", "mdpp_get_stats_host",
            "mdpp_sync_buffer_bytes", "mdpp_sync_alloc", "mdpp_sync_free", "mdpp_sync_open", "mdpp_sync_close", "mdpp_sync_attach",
            "mdpp_q_sync_replicas", "mdpp_sync_count", "mdpp_q_table_written", "mdpp_sync_emulate", "mdpp_deadlock_scratch_bytes",
-           "mdpp_deadlock_reachability_bfs", "mdpp_replay_insert", "mdpp_replay_compact", "mdpp_dqn_target"]
+           "mdpp_deadlock_reachability_bfs", "mdpp_deadlock_sweep_range", "mdpp_replay_insert", "mdpp_replay_compact", "mdpp_dqn_target"]
 
 
 def needs_build():
@@ -101,6 +101,7 @@ def lib():
         "mdpp_replay_compact": (I, [I64, U32, U32, U32, P]),
         "mdpp_dqn_target": (I, [I64, F32, F32, U8, F32, P, F32, C.c_double, I, F32, F32, P, P]),
         "mdpp_deadlock_reachability_bfs": (I, [P, U32, P, I64, C.POINTER(C.c_int32), P]),
+        "mdpp_deadlock_sweep_range": (I, [P, U32, I64, I64, U32, P]),
     }
     for name, (res, args) in sig.items():
         if os.environ.get("MDPP_LIB") and not hasattr(L, name):

@@ -159,6 +159,19 @@ class BatchedEnv:
                 raise ValueError("unknown method %r" % (method,))
         return bitmap, int(count.value)
 
+    def joint_state_count(self):
+        n = self._L.mdpp_joint_state_count(C.byref(self.scenario.cfg))
+        if n <= 0:
+            raise _lib.MdppError("joint state space too large: " + _lib.last_error())
+        return int(n)
+
+    def deadlock_sweep_range(self, bitmap, first_state, n_range, changed):
+        """One forward sweep of the reachability fixpoint over joint states [first_state, first_state + n_range)
+        of `bitmap` (int32 words on this device); `changed` (int32[1]) is set to 1 when a bit was set."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mdpp_deadlock_sweep_range(self._h, _ptr(bitmap), int(first_state), int(n_range),
+                                                         _ptr(changed), _stream()))
+
     def joint_index(self, cars):
         """cars: [(node name or None for finished, destination_index)] -> joint state index."""
         from .tables import node_id

@@ -1590,7 +1590,7 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *
     int sweeps = 0;
     for (;;) {
         MDPP_CUDA(cudaMemsetAsync(changed, 0, 4, s));
-        MDPP_DISPATCH_NC(h, reach_sweep_kernel, grid_for(n), s, h->dev, reach_bitmap, (uint64_t)n, changed);
+        MDPP_DISPATCH_NC(h, reach_sweep_kernel, grid_for(n), s, h->dev, reach_bitmap, (uint64_t)0, (uint64_t)n, changed);
         MDPP_CUDA(cudaGetLastError());
         uint32_t flag = 0;
         MDPP_CUDA(cudaMemcpyAsync(&flag, changed, 4, cudaMemcpyDeviceToHost, s));
@@ -1600,6 +1600,25 @@ int mdpp_deadlock_reachability(mdpp_handle *h, uint32_t *reach_bitmap, int32_t *
         if (sweeps > 100000) return fail(MDPP_ECUDA, "reachability did not converge");
     }
     if (sweeps_out) *sweeps_out = sweeps;
+    return MDPP_OK;
+}
+
+// One forward sweep over the joint states [first_state, first_state + n_range): the building block of the search sharded
+// over ranks (parallel.sharded_reachability): every rank sweeps its own range of the replicated bitmap, the ranks
+// exchange their ranges, until a sweep changes nothing anywhere.
+int mdpp_deadlock_sweep_range(mdpp_handle *h, uint32_t *reach_bitmap, int64_t first_state, int64_t n_range,
+                              uint32_t *changed, void *stream) {
+    if (!h || !reach_bitmap || !changed) return fail(MDPP_EINVAL, "handle / bitmap / changed is NULL");
+    const int64_t n = mdpp_joint_state_count(&h->cfg);
+    if (n <= 0) return MDPP_EINVAL;
+    if (first_state < 0 || (first_state & 31) || n_range < 0)
+        return fail(MDPP_EINVAL, "first_state must be a non-negative multiple of 32 (a rank owns whole bitmap words), n_range >= 0");
+    const int64_t end = std::min<int64_t>(n, first_state + n_range);
+    if (end <= first_state) return MDPP_OK; // an empty shard
+    cudaStream_t s = (cudaStream_t)stream;
+    MDPP_DISPATCH_NC(h, reach_sweep_kernel, grid_for(end - first_state), s, h->dev, reach_bitmap, (uint64_t)first_state,
+                     (uint64_t)end, changed);
+    MDPP_CUDA(cudaGetLastError());
     return MDPP_OK;
 }
 

@@ -677,11 +677,13 @@ dqn_act_kernel(DevCfg cfg, uint4 *__restrict__ recs, int64_t n_envs, uint32_t en
 // ------------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void __launch_bounds__(kThreads)
-reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t n_joint, uint32_t *__restrict__ changed) {
+reach_sweep_kernel(DevCfg cfg, uint32_t *__restrict__ reach, uint64_t first, uint64_t n_joint, uint32_t *__restrict__ changed) {
+    // joint states [first, n_joint): the whole space, or one rank's shard of it (mdpp_deadlock_sweep_range) -- a
+    // thread writes the bit of its own state only and reads successor bits anywhere in the bitmap
     __shared__ SmemTables sm;
     load_tables(sm, cfg.tables);
     const SharedTab tab{&sm};
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t idx = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_joint) return;
     if ((reach[idx >> 5] >> (idx & 31u)) & 1u) return;
     const uint32_t V = 2u * (uint32_t)cfg.n_local_nodes + 1u;

@@ -188,3 +188,59 @@ class PeerExchange:
             self.close()
         except Exception:
             pass
+
+
+# ---- -dd reachability sharded over ranks (last sentence) ---------------------------------
+def shard_words(n_words, rank, world):
+    """Equal word ranges (the all-gather wants equal pieces): (first word, words per rank); the last ranks' pieces
+    may reach past n_words -- the bitmap is padded to world * words_per_rank."""
+    per = (n_words + world - 1) // world
+    return rank * per, per
+
+
+def sharded_fixpoint(bitmap, sweep_own, rank, world, group=None, max_sweeps=100000):
+    """Monotone fixpoint over a REPLICATED bitmap whose word range [rank * per, (rank + 1) * per) this rank owns.
+    sweep_own(bitmap) sets bits of own states only (reading any) and returns whether it set one.  After every
+    sweep the ranks exchange their ranges (all-gather: a word belongs to exactly one rank, so no OR is needed) and
+    the "anything changed anywhere" flag (all-reduce MAX).  Returns the number of sweeps.  bitmap: int32
+    [world * per], identical on every rank on entry."""
+    per = bitmap.numel() // world
+    assert per * world == bitmap.numel()
+    pieces = list(bitmap.view(world, per).unbind(0))
+    sweeps = 0
+    while True:
+        changed = bool(sweep_own(bitmap))
+        sweeps += 1
+        if world > 1:
+            own = pieces[rank].clone()
+            dist.all_gather(pieces, own, group=group)
+            flag = torch.tensor([1 if changed else 0], dtype=torch.int32, device=bitmap.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            changed = bool(int(flag.item()))
+        if not changed:
+            return sweeps
+        if sweeps >= max_sweeps:
+            raise RuntimeError("sharded reachability did not converge")
+
+
+def sharded_reachability(env, group=None):
+    """The -dd bitmap of env's scenario with the joint-state range split over the ranks of `group` (one process per
+    GPU): every rank sweeps its own word range (mdpp_deadlock_sweep_range), the ranks all-gather their ranges.
+    Returns (bitmap int32 [ceil(n / 32)], sweeps); every rank ends with the whole bitmap, bit-identical to
+    BatchedEnv.deadlock_reachability.  Without a process group: one rank, the plain sweeps."""
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    n = env.joint_state_count()
+    words = (n + 31) // 32
+    first_word, per = shard_words(words, rank, world)
+    bitmap = torch.zeros(per * world, dtype=torch.int32, device=env.device)
+    changed = torch.zeros(1, dtype=torch.int32, device=env.device)
+
+    def sweep_own(bm):
+        changed.zero_()
+        env.deadlock_sweep_range(bm, first_word * 32, per * 32, changed)
+        return int(changed.item())
+
+    sweeps = sharded_fixpoint(bitmap, sweep_own, rank, world, group)
+    return bitmap[:words], sweeps

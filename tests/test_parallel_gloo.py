@@ -75,3 +75,61 @@ def test_env_id_partitions_cover_exactly_once():
     with pytest.raises(ValueError):
         parallel.shard_env_ids(10, 3, 2)
     assert not parallel.ReplicaSync(0).due(8) and parallel.ReplicaSync(4).due(8) and not parallel.ReplicaSync(4).due(6)
+
+
+# ---- sharded reachability: the exchange logic on a toy monotone system (the sweeps themselves are CUDA) ----------
+def _toy_system(n=3000, seed=5):
+    """State i is live iff it is a goal or one of its successors is: random forward edges, a few goals."""
+    rng = np.random.default_rng(seed)
+    succ = [rng.integers(0, n, size=rng.integers(0, 4)) for _ in range(n)]
+    goal = rng.random(n) < 0.01
+    return succ, goal
+
+
+def _toy_sweep(bits, succ, goal, lo, hi):
+    """One in-place sweep over states [lo, hi): reads any bit, sets own bits; returns whether one was set."""
+    changed = False
+    for i in range(lo, min(hi, len(succ))):
+        if (int(bits[i >> 5]) >> (i & 31)) & 1:
+            continue
+        if goal[i] or any((int(bits[j >> 5]) >> (j & 31)) & 1 for j in succ[i]):
+            bits[i >> 5] = np.int32(np.uint32(int(bits[i >> 5]) & 0xFFFFFFFF | (1 << (i & 31))).astype(np.int32))
+            changed = True
+    return changed
+
+
+def _reach_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        succ, goal = _toy_system()
+        words = (len(succ) + 31) // 32
+        first, per = parallel.shard_words(words, rank, world)
+        bitmap = torch.zeros(per * world, dtype=torch.int32)
+        view = bitmap.numpy()
+        sweeps = parallel.sharded_fixpoint(
+            bitmap, lambda bm: _toy_sweep(view, succ, goal, first * 32, (first + per) * 32), rank, world)
+        np.save(os.path.join(out_dir, "reach%d.npy" % rank), np.concatenate([view[:words], [sweeps]]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_fixpoint_equals_the_single_process_fixpoint(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_reach_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    succ, goal = _toy_system()
+    words = (len(succ) + 31) // 32
+    want = np.zeros(words, dtype=np.int32)
+    while _toy_sweep(want, succ, goal, 0, len(succ)):
+        pass
+    got = [np.load(tmp_path / ("reach%d.npy" % r)) for r in range(world)]
+    for r in range(world):
+        np.testing.assert_array_equal(got[r][:words], want)      # every rank ends with the whole bitmap
+        assert got[r][-1] == got[0][-1] >= 2                       # the same number of sweeps everywhere
+    assert 0 < int(np.unpackbits(want.view(np.uint8)).sum()) < len(succ)
+    for words_, world_ in ((10, 3), (7, 8), (4096, 2)):
+        spans = [parallel.shard_words(words_, r, world_) for r in range(world_)]
+        assert spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world_ - 1))
+        assert spans[-1][0] + spans[-1][1] >= words_
