@@ -22,6 +22,6 @@ echo "launch list rc=$?"
 cap pure q_rounds_pure 40 2 $B
 cap round0 'q_round_kernel' 10 2 python tools/exp_round_parts.py
 cap mixed q_rounds_mixed 2 1 python tools/exp_mixed.py 0.5
-cap rollout4 rollout_lean 4 2 python tools/exp_rollout.py 4 24 10
+cap rollout4 rollout_lean 4 2 python tools/exp_rollout.py 4 24 10 0
 cap reach reach_bfs 1 1 python tools/exp_reach.py 2
 ls -la $out
