@@ -617,14 +617,14 @@ def main():
                 torch.cuda.synchronize()
                 envk.stats(reset=True)
                 a.record()
-                for _ in range(rounds_k // 8):
-                    lrk.train_rounds(8)
+                for _ in range(rounds_k // 32):   # 32 rounds per call (RL._run makes calls of 256): within a call the pulls of
+                    lrk.train_rounds(32)          # a group of pure-exploration rounds run beside the next group's env pass
                 b.record()
                 torch.cuda.synchronize()
                 sk = envk.stats(reset=True)
                 ms = a.elapsed_time(b)
                 v = sk["agent_steps"] / (ms * 1e-3)
-                entry[tag] = {"value": v, "unit": UNIT, "us_per_round": ms / rounds_k * 1e3,
+                entry[tag] = {"value": v, "unit": UNIT, "us_per_round": ms / rounds_k * 1e3, "rounds_per_call": 32,
                               "active_fraction": sk["agent_steps"] / float(rounds_k * n * kc),
                               "touched_keys_per_substep": sk["touched_keys"] / float(rounds_k * kc),
                               "frac_of_hbm_roofline": FUSED_Q_BYTES_PER_STEP(kc) * v / 1e9 / measured_peak()[0]}
