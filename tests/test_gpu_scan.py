@@ -18,6 +18,8 @@ pytestmark = pytest.mark.gpu
 A5 = "SLRFT"
 CASES = [
     # name, boxes, dest_index, choose, force scan mode, envs, episodes, step cap
+    ("b2_1car_forced_scan", ["D3"], [0], [[0, 1, 0]], True, 1000, 30, 40),
+    ("b2_2car_forced_scan", ["D3", "D2"], [0, 0], [[0, 1, 0], [0, 1, 0]], True, 2049, 24, 44),
     ("b2_3car_forced_scan", ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]], True, 3001, 20, 45),
     # mid-size table, default: shared-memory bit maps + dense pulls for rounds with greedy decisions, the scan mode's
     # fused pass + scanning pulls for pure-exploration rounds, a table copy / settle pass at every change-over
