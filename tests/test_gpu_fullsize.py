@@ -201,3 +201,37 @@ def test_reachability_four_cars_bit_exact():
         got = bitmap.cpu().numpy().view(np.uint32)
         assert np.array_equal(got, want), method
         assert int(np.unpackbits(got.view(np.uint8)).sum()) == live == 13968601
+
+
+def test_fullsize_three_car_hybrid_bit_exact():
+    """Mid-size table (3 cars, 126 540 states) at full size through every change-over of its two roads: the scan
+    mode's fused env pass + scanning pulls while the host's bound says "every env explores" (tightened by each
+    counter fetch), shared-memory bit maps + dense pulls otherwise, a table copy / settle pass in between.  An
+    episode budget of 3 (epsilon 1, then 0.8 .. 0) and a step cap of 30 take every env to frozen in ~45 rounds."""
+    m, BatchedEnv, BatchedQLearner, orc = _mods()
+    boxes, idx, choose = ["D6", "D4", "D8"], [0, 0, 0], [[0, 1, 0], [1, 0, 0], [2, 1, 0]]
+    bad = bad_states_text(2)
+    cap, episodes = 30, 3
+    sc = m.Scenario(m.layout_3[2], boxes, idx, choose, bad_states_text=bad, step_cap=cap)
+    env = BatchedEnv(sc, N_FULL, seed=47)
+    lr = BatchedQLearner(env, episodes=episodes, seed=47)
+    ob = orc.Batch(orc.Config(m.layout_3[2]), N_FULL, boxes, idx, choose, bad, cap)
+    ob.reset(seed=47)
+    oq = orc.QTable(f32=True)
+    olp = orc.learner(episodes, seed=47)
+    assert olp.eps_threshold[0] == 1                       # episode 0 explores, the others decide greedily too
+    done = 0
+    for k in (3, 4, 1, 6):                                 # fused pass(es) first, dense sub-steps once the bound says so;
+        lr.train_rounds(k)                                 # every stats fetch lets the fused pass back in while all
+        env.stats()                                        # envs are still in episode 0
+        done += k
+    while int(env.cars()["episode"].min()) < episodes:
+        assert done < episodes * (cap + 2)
+        lr.train_rounds(16)
+        done += 16
+    for r in range(done):
+        ob.q_round(oq, olp, r)
+    _assert_table_equal(lr, sc, oq)
+    _assert_records_equal(env, ob)
+    gs = _assert_counters_equal(env, ob)
+    assert 0 < gs["explore_steps"] < gs["agent_steps"]
