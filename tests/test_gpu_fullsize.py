@@ -235,3 +235,33 @@ def test_fullsize_three_car_hybrid_bit_exact():
     _assert_records_equal(env, ob)
     gs = _assert_counters_equal(env, ob)
     assert 0 < gs["explore_steps"] < gs["agent_steps"]
+
+
+def test_fullsize_four_car_greedy_rounds_bit_exact():
+    """Scan mode with greedy decisions at full size: 4 cars (1.65 M states), an episode budget of 2 (epsilon 0.8,
+    then 0) and a step cap of 24 -- every round takes the sub-step kernels (4 096 CTAs marking the global bitmaps,
+    three banks in rotation) and one scanning pull per car, to frozen envs."""
+    m, BatchedEnv, BatchedQLearner, orc = _mods()
+    boxes, idx = ["D2", "D6", "D4", "D8"], [0, 0, 0, 0]
+    choose = [[0, 1, 0], [0, 1, 0], [1, 0, 0], [2, 1, 0]]
+    bad = bad_states_text(2)
+    cap, episodes = 24, 2
+    sc = m.Scenario(m.layout_3[2], boxes, idx, choose, bad_states_text=bad, step_cap=cap)
+    env = BatchedEnv(sc, N_FULL, seed=53)
+    lr = BatchedQLearner(env, episodes=episodes, seed=53)
+    done = 0
+    while int(env.cars()["episode"].min()) < episodes:
+        assert done < episodes * (cap + 2)
+        lr.train_rounds(13)
+        done += 13
+    ob = orc.Batch(orc.Config(m.layout_3[2]), N_FULL, boxes, idx, choose, bad, cap)
+    ob.reset(seed=53)
+    oq = orc.QTable(f32=True)
+    olp = orc.learner(episodes, seed=53)
+    assert olp.eps_threshold[0] == 0                       # no episode explores only
+    for r in range(done):
+        ob.q_round(oq, olp, r)
+    _assert_table_equal(lr, sc, oq)
+    _assert_records_equal(env, ob)
+    gs = _assert_counters_equal(env, ob)
+    assert 0 < gs["explore_steps"] < gs["agent_steps"]
