@@ -1,7 +1,8 @@
 """BASELINE config 3: random-policy env-step throughput, max agents (4 cars), outputs materialised, env-count sweep.
 Single GPU: python tools/sweep_rollout.py.  N GPUs (independent env shards, no collective on the data path):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 tools/sweep_rollout.py
-Device time by CUDA events, max over ranks; agent-steps summed over ranks."""
+Device time by CUDA events, max over ranks; agent-steps summed over ranks.  Every batch is first rolled PREROLL rounds
+(argv[1], default 1024; 0 = from a fresh reset) to its stationary mix of moving and finished cars."""
 import gzip, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -33,8 +34,12 @@ for lg in (20, 22, 24, 26):
     n = 1 << lg
     env = BatchedEnv(sc, n, device=dev, env_id_base=rank * n, seed=5)
     outs = env.alloc_rollout_outputs(1)
+    pre = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    for w in range(pre // 16):
+        env.rollout_random(16, w * 16)
+    r0 = (pre // 16) * 16
     for w in range(3):
-        env.rollout_random(1, w, outputs=outs)
+        env.rollout_random(1, r0 + w, outputs=outs)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -43,15 +48,17 @@ for lg in (20, 22, 24, 26):
     reps = 16 if lg <= 22 else 8
     a.record()
     for w in range(reps):
-        env.rollout_random(1, 3 + w, outputs=outs)
+        env.rollout_random(1, r0 + 3 + w, outputs=outs)
     b.record()
     torch.cuda.synchronize()
     ms = allr(a.elapsed_time(b), dist.ReduceOp.MAX if world > 1 else None)
     steps = allr(float(env.stats()["agent_steps"]), dist.ReduceOp.SUM if world > 1 else None)
     v = steps / (ms * 1e-3)
     if rank == 0:
-        print("2^%d envs per GPU (%d in all): %.3e agent-env-steps/s, %.0f GB/s algorithmic (14 B/step) = %.1f %% of %d x 6545.9 GB/s"
-              % (lg, n * world, v, 14 * v / 1e9, 100 * 14 * v / 1e9 / (6545.9 * world), world), flush=True)
+        slots = reps * 4.0 * n * world / (ms * 1e-3)
+        print("2^%d envs per GPU (%d in all): %.3e agent-env-steps/s (%.0f %% of the car slots move; %.3e car slots/s), %.0f GB/s "
+              "algorithmic (14 B/step) = %.1f %% of %d x 6545.9 GB/s" % (lg, n * world, v, 100 * v / slots, slots, 14 * v / 1e9,
+              100 * 14 * v / 1e9 / (6545.9 * world), world), flush=True)
     del env, outs
 if world > 1:
     dist.destroy_process_group()
