@@ -17,10 +17,7 @@ namespace mdpp {
 constexpr int kStatSlots = 128;
 struct Control {
     mdpp_stats stats[kStatSlots];
-    // double-buffered by sub-step parity: the sub-step appends under [p], its finalize consumes [p] and
-    // zeroes [p^1] for the next sub-step -- no grid-wide fence or "last block" ticket is needed
-    uint32_t touched_count[2];
-    uint32_t pad[14];
+    uint32_t reserved[16]; // (round 1's list mode kept its touched-key counters here)
     // largest per-env episode counter the learner kernels have produced, privatised like the stats; the host
     // uses it (mdpp_get_stats_host) to tighten its bound on "is any env past the epsilon = 1 segment?"
     uint32_t max_episode[kStatSlots];
