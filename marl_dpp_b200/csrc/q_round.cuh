@@ -393,24 +393,22 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
                 uint32_t cars = rec.x; // 1-2 cars: both 12-bit fields live in the first word
                 uint32_t steps = rec.z >> 16;
                 const uint32_t env = ra.env_id_base + e;
-                uint32_t eps16 = lp.eps_q16[0];
-                if ((int32_t)episode >= lp.eps_threshold[0]) eps16 = eps_q16_of(lp, (int32_t)episode);
+                // epsilon = 1 here by the host's bound: the coin is a compile-time "explore" (no schedule lookup, no
+                // parking path); an env found outside the first segment all the same is counted as an internal error
+                constexpr uint32_t kAlwaysExplore = 0x10000u;
+                parked += (int32_t)episode >= lp.eps_threshold[0];
                 const uint4 p = philox4x32_r((uint32_t)round, (uint32_t)(round >> 32), 0, 0, lp.seed, env);
                 uint32_t key;
                 bool moved, explore;
-                int st = round_car_step<NC, 0>(S, cfg, ra.tabs, ra, cars, p.x, eps16, false, key, moved, explore);
+                int st = round_car_step<NC, 0>(S, cfg, ra.tabs, ra, cars, p.x, kAlwaysExplore, false, key, moved, explore);
                 if (st == kStepDone) rmaps[key] = 1;
-                parked += st == kStepDefer;
                 steps += moved;
                 cnt.steps += moved;
-                cnt.explore += explore;
                 if (NC > 1) {
-                    st = round_car_step<NC, NC - 1>(S, cfg, ra.tabs, ra, cars, p.y, eps16, false, key, moved, explore);
+                    st = round_car_step<NC, NC - 1>(S, cfg, ra.tabs, ra, cars, p.y, kAlwaysExplore, false, key, moved, explore);
                     if (st == kStepDone) rmaps[(uint32_t)(NC - 1) * ra.map_bytes + key] = 1;
-                    parked += st == kStepDefer;
                     steps += moved;
                     cnt.steps += moved;
-                    cnt.explore += explore;
                 }
                 steps = steps > 0xFFFFu ? 0xFFFFu : steps;
                 { // end of the round-robin round (qlearning.py:233)
@@ -440,6 +438,7 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
         flush_round_maps<NC>(rmaps, ra.bits_a + (size_t)r * NC * ra.region_words, ra);
     }
     if (__any_sync(0xFFFFFFFFu, parked != 0u) && lane == 0) guard_tripped(ctl);
+    cnt.explore = cnt.steps; // every decision of this kernel explores
     flush_counts<true>(cnt, S.cc, 0u, ctl);
     pdl_wait();
 }
