@@ -383,6 +383,7 @@ q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     for (uint32_t r = 0; r < ra.n_rounds; r++) {
         const uint64_t round = ra.round + r;
         uint8_t *rmaps = maps + (size_t)(r & 1u) * NC * ra.map_bytes;
+#pragma unroll 2 // (the record hand-over rec = rec_next costs four moves per lap; 4 laps per trip measured slower)
         while (t < t1) {
             const uint32_t e = t * 32u + lane, tn = t + n_warps;
             uint4 rec_next = make_uint4(0u, 0u, 0u, 0u);
