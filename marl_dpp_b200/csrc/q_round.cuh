@@ -355,7 +355,7 @@ __device__ __forceinline__ void flush_round_maps(const uint8_t *maps, uint32_t *
 }
 
 template <int NC>
-__global__ void __maxnreg__(56)
+__global__ void __maxnreg__(64)
 q_rounds_pure_kernel(DevCfg cfg, LearnArgs lp, RoundArgs ra, Control *ctl) {
     static_assert(NC >= 1 && NC <= 2, "the fused rounds are built for 1- and 2-car tables");
     extern __shared__ uint4 smem_dyn[];
