@@ -299,3 +299,27 @@ def test_dqn_reward_division_needs_no_float64():
     via_f64 = (r.astype(np.float64) / 100.0).astype(np.float32)
     via_f32 = r.astype(np.float32) / np.float32(100.0)
     assert via_f32.dtype == np.float32 and np.array_equal(via_f64, via_f32)
+
+
+def test_scan_slot_division_trick():
+    """csrc/q_learner.cuh scan_slot: bit = m / NW by one multiply-high with magic = floor(2^32 / NW) + 1 and a
+    one-step correction (m < 32 * NW, NW < 2^27).  The same arithmetic in Python, over the bitmap sizes of the real
+    tables (1-5 cars, layout 3) and the edges of every bit plane."""
+    import random
+    rng = random.Random(7)
+    for n_states in (108, 6660, 126540, 1645020, 16450200, 3, 4_000_000_000 // 5 // 32):
+        marks = n_states * 5
+        nw = ((marks + 31) // 32 + 3) & ~3
+        assert nw < 1 << 27
+        magic = (1 << 32) // nw + 1
+        assert magic < 1 << 32
+        probes = [0, marks - 1] + [b * nw + d for b in range(32) for d in (-1, 0, 1)] + [rng.randrange(marks) for _ in range(2000)]
+        for m in probes:
+            if not 0 <= m < marks:
+                continue
+            b = (m * magic) >> 32
+            w = (m - b * nw) & 0xFFFFFFFF
+            if w >= 1 << 31:                     # (int32_t)w < 0
+                b -= 1
+                w = (w + nw) & 0xFFFFFFFF
+            assert (b, w) == divmod(m, nw) and b < 32, (n_states, m)
