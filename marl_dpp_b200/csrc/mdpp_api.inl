@@ -93,9 +93,12 @@ static Carve carve(const mdpp_config &cfg, int64_t n_envs) {
     if (const char *env = getenv("MDPP_HYBRID")) c.scan = c.scan && (!c.dense || atoi(env) != 0);
     if (c.scan) {
         c.scan_words = (uint32_t)(((marks + 31) / 32 + 3) & ~(size_t)3);
-        // pure-exploration rounds share a launch (q_rounds_pure_scan_kernel): as many rounds as fit 16 MB of bitmaps per bank
+        // pure-exploration rounds share a launch (q_rounds_pure_scan_kernel): as many rounds as fit 34 MB of bitmaps per bank
+        // (4 cars: 8 rounds of 4 x 1.03 MB; 4 rounds per launch measured 49.4 us per round, 8 rounds 46.4, 1 round 59.6)
         const size_t per_round = (size_t)cfg.n_cars * c.scan_words * 4;
-        const int rounds = (int)std::max<size_t>(1, std::min<size_t>((size_t)kMaxPureRounds, ((size_t)16 << 20) / per_round));
+        size_t bank_mb = 34;
+        if (const char *env = getenv("MDPP_SCAN_BANK_MB")) bank_mb = (size_t)std::max(1, atoi(env)); // A/B runs
+        const int rounds = (int)std::max<size_t>(1, std::min<size_t>((size_t)kMaxPureRounds, (bank_mb << 20) / per_round));
         c.scan_regions = (uint32_t)(rounds * cfg.n_cars);
         c.bits = take((size_t)3 * c.scan_regions * c.scan_words * 4);
     }
